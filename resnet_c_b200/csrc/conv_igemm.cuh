@@ -1,0 +1,346 @@
+// conv_igemm.cuh — implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// Replaces, for every non-stem convolution of the network, the reference's chain
+//   conv2dForwardKernel (/root/reference/cuda/ops.cu:14-48)      — direct conv, 1 thread / output
+//   batchNorm2dForwardKernel (ops.cu:139-151)                    — folded into weights + bias
+//   addForwardKernel (ops.cu:153-160)                            — residual, fused in the epilogue
+//   reluForwardKernel (ops.cu:130-137)                           — fused in the epilogue
+// as issued by layerForward (/root/reference/cuda/inference/main.cu:127-166).
+//
+// GEMM view (per launch):  D[M, N] = A[M, K] * B[N, K]^T
+//   M = batch*OH*OW output pixels (NHWC rows), N = Cout, K = kh*kw*Cin (tap-major, Cin innermost)
+//   A is never materialised: each 128-pixel x 128-byte K-slab is fetched by ONE im2col-mode TMA
+//   (cuTensorMapEncodeIm2col) straight from the NHWC activation tensor, zero-filling the padding
+//   halo and wrapping across rows/images in hardware.
+//   B is the BN-folded weight matrix [Cout][kh][kw][Cin], fetched by a tiled TMA.
+//   D accumulates in TMEM (fp32), double-buffered so the epilogue of tile i overlaps the MMAs of
+//   tile i+1. The epilogue adds bias (+ residual, TMA-prefetched into the staging buffer), applies
+//   ReLU, rounds to the activation type and leaves through a swizzled smem tile + TMA store.
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer (A im2col + B tiled) over an NSTAGE ring
+//   warp 1 lane 0 : tcgen05.mma issuer
+//   warp 2        : TMEM allocator / deallocator
+//   warps 4..7    : epilogue (thread t owns TMEM lane t = output pixel m0 + t)
+#pragma once
+#include "sm100_ptx.cuh"
+
+namespace rnb {
+
+struct ConvGeom {
+    int M;                // batch * OH * OW
+    int OH, OW;           // output spatial size
+    int Cout;             // N of the GEMM
+    int stride;           // conv stride (traversal stride of the im2col map)
+    int lower;            // -padding: coordinate of the first filter tap for output pixel 0
+    int ksize;            // square filter size (1 or 3)
+    int kblocks_per_tap;  // Cin / BK
+    int num_kblocks;      // ksize*ksize*kblocks_per_tap
+    int m_tiles, n_tiles;
+    int relu;     // apply max(x, 0)
+    int has_res;  // add residual[M][Cout] before the ReLU
+};
+
+template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_>
+struct ConvCfg {
+    static constexpr int BM = 128;
+    static constexpr int BN = BN_;
+    static constexpr int ESZ = ESZ_;                 // bytes per activation/weight element (2 = bf16, 4 = tf32)
+    static constexpr int BK = 128 / ESZ_;            // one 128-byte swizzle row of K per stage
+    static constexpr int NSTAGE = NSTAGE_;
+    static constexpr int NCBUF = NCBUF_;             // epilogue staging buffers (>= 2)
+    static constexpr int A_BYTES = BM * 128;
+    static constexpr int B_BYTES = BN_ * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BOX_COLS = 128 / ESZ_;      // output columns per 128-byte staging row
+    static constexpr int NBOX = BN_ / BOX_COLS;
+    static constexpr int BOX_BYTES = BM * 128;
+    static constexpr int CBUF_BYTES = NBOX * BOX_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN_;        // two accumulator stages
+    static constexpr int NBAR = 2 * NSTAGE_ + 4 + NCBUF_;
+    static constexpr int SMEM_BYTES =
+        1024 /*align slack*/ + NSTAGE_ * STAGE_BYTES + NCBUF_ * CBUF_BYTES + NBAR * 8 + 16;
+    static constexpr int THREADS = 256;
+    static_assert(NCBUF_ >= 2, "need at least two staging buffers");
+    static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512,
+                  "TMEM allocation must be a power of two >= 32 columns");
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmOut,
+                  const __grid_constant__ CUtensorMap tmRes, const float* __restrict__ bias,
+                  const ConvGeom g) {
+    using namespace ptx;
+    constexpr int BN = Cfg::BN;
+    constexpr int NSTAGE = Cfg::NSTAGE;
+    constexpr int NCBUF = Cfg::NCBUF;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_stage = smem;
+    uint8_t* smem_c = smem + NSTAGE * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + NCBUF * Cfg::CBUF_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + NSTAGE;
+    uint64_t* tmem_full = bars + 2 * NSTAGE;
+    uint64_t* tmem_empty = bars + 2 * NSTAGE + 2;
+    uint64_t* res_full = bars + 2 * NSTAGE + 4;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = g.m_tiles * g.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmOut);
+        if (g.has_res) tma_prefetch_desc(&tmRes);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NSTAGE; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
+        for (int i = 0; i < NCBUF; ++i) mbar_init(&res_full[i], 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        __syncwarp();
+        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int ohw = g.OH * g.OW;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int n_blk = t % g.n_tiles;
+                const int m_blk = t / g.n_tiles;
+                const int m0 = m_blk * Cfg::BM;
+                const int img = m0 / ohw;
+                const int rem = m0 - img * ohw;
+                const int p = rem / g.OW;
+                const int q = rem - p * g.OW;
+                const int w0 = g.lower + q * g.stride;
+                const int h0 = g.lower + p * g.stride;
+                int tap = 0, cblk = 0;
+                for (int kb = 0; kb < g.num_kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem_stage + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    const int r = tap / g.ksize;
+                    const int s = tap - r * g.ksize;
+                    tma_load_im2col_4d(sa, &tmA, &full_bar[stage], cblk * Cfg::BK, w0, h0, img,
+                                       static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+                    tma_load_2d(sb, &tmB, &full_bar[stage], kb * Cfg::BK, n_blk * BN);
+                    if (++cblk == g.kblocks_per_tap) {
+                        cblk = 0;
+                        ++tap;
+                    }
+                    if (++stage == NSTAGE) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc =
+                umma_instr_desc(Cfg::ESZ == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, Cfg::BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < g.num_kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_stage + stage * Cfg::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // 32 bytes of K per instruction (16 bf16 / 8 tf32) inside the 128-byte swizzle row
+                        const uint64_t ad = umma_smem_desc(a_addr + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
+                        const uint64_t bd = umma_smem_desc(b_addr + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
+                        if (Cfg::ESZ == 2)
+                            mma_f16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                        else
+                            mma_tf32_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                    }
+                    tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == NSTAGE) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== epilogue
+        const int et = threadIdx.x - 128;  // 0..127 == TMEM lane == row of the tile
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const uint32_t swz = static_cast<uint32_t>(et & 7);
+        const bool leader = (et == 0);
+        const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                             static_cast<int>(gridDim.x);
+
+        auto issue_residual = [&](int it_local) {
+            const int t = blockIdx.x + it_local * gridDim.x;
+            const int n_blk = t % g.n_tiles;
+            const int m_blk = t / g.n_tiles;
+            const int cs = it_local % NCBUF;
+            uint8_t* buf = smem_c + cs * Cfg::CBUF_BYTES;
+            mbar_expect_tx(&res_full[cs], Cfg::CBUF_BYTES);
+#pragma unroll
+            for (int b = 0; b < Cfg::NBOX; ++b)
+                tma_load_2d(buf + b * Cfg::BOX_BYTES, &tmRes, &res_full[cs],
+                            n_blk * BN + b * Cfg::BOX_COLS, m_blk * Cfg::BM);
+        };
+        if (leader && g.has_res) {
+            if (my_tiles > 0) issue_residual(0);
+            if (my_tiles > 1) issue_residual(1);
+        }
+
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int n_blk = t % g.n_tiles;
+            const int m_blk = t / g.n_tiles;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int cs = it % NCBUF;
+            uint8_t* cbuf = smem_c + cs * Cfg::CBUF_BYTES;
+            if (g.has_res) mbar_wait(&res_full[cs], (it / NCBUF) & 1);
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            const float* bias_n = bias + n_blk * BN;
+#pragma unroll 1
+            for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld_32x32(taddr + chunk * 32, v);
+                tmem_ld_wait();
+                const int byte_off = chunk * 32 * Cfg::ESZ;
+                uint8_t* row = cbuf + (byte_off >> 7) * Cfg::BOX_BYTES + et * 128;
+                const uint32_t c16_base = (byte_off & 127) >> 4;
+                if (Cfg::ESZ == 2) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4* p16 = reinterpret_cast<uint4*>(row + (((c16_base + j) ^ swz) << 4));
+                        float x[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]);
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_n + chunk * 32 + j * 8));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_n + chunk * 32 + j * 8 + 4));
+                        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                        x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                        if (g.has_res) {
+                            const uint4 rr = *p16;
+                            x[0] += bf16_lo(rr.x); x[1] += bf16_hi(rr.x);
+                            x[2] += bf16_lo(rr.y); x[3] += bf16_hi(rr.y);
+                            x[4] += bf16_lo(rr.z); x[5] += bf16_hi(rr.z);
+                            x[6] += bf16_lo(rr.w); x[7] += bf16_hi(rr.w);
+                        }
+                        if (g.relu) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e], 0.f);
+                        }
+                        uint4 o;
+                        o.x = pack_bf16x2(x[0], x[1]);
+                        o.y = pack_bf16x2(x[2], x[3]);
+                        o.z = pack_bf16x2(x[4], x[5]);
+                        o.w = pack_bf16x2(x[6], x[7]);
+                        *p16 = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint4* p16 = reinterpret_cast<uint4*>(row + (((c16_base + j) ^ swz) << 4));
+                        float x[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(v[j * 4 + e]);
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_n + chunk * 32 + j * 4));
+                        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                        if (g.has_res) {
+                            const float4 rr = *reinterpret_cast<const float4*>(p16);
+                            x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
+                        }
+                        if (g.relu) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+                        }
+                        uint4 o;
+                        o.x = __float_as_uint(round_tf32(x[0]));
+                        o.y = __float_as_uint(round_tf32(x[1]));
+                        o.z = __float_as_uint(round_tf32(x[2]));
+                        o.w = __float_as_uint(round_tf32(x[3]));
+                        *p16 = o;
+                    }
+                }
+            }
+            // accumulator drained: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[as]);
+            // publish the staged tile to the async proxy and store it
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (leader) {
+#pragma unroll
+                for (int b = 0; b < Cfg::NBOX; ++b)
+                    tma_store_2d(&tmOut, cbuf + b * Cfg::BOX_BYTES, n_blk * BN + b * Cfg::BOX_COLS,
+                                 m_blk * Cfg::BM);
+                tma_store_commit();
+                // stores of tiles <= it-(NCBUF-2) have finished reading smem: the buffer tile it+2
+                // will use is free, so its residual can be fetched now (one full tile ahead).
+                tma_store_wait_read<NCBUF - 2>();
+                if (g.has_res && it + 2 < my_tiles) issue_residual(it + 2);
+            }
+        }
+        if (leader) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace rnb

@@ -1,0 +1,109 @@
+// conv_plan.cu — host side of the implicit-GEMM conv: tile selection, TMA descriptors, launch.
+#include "conv_plan.h"
+
+#include <cstdio>
+#include <cstring>
+
+#include "tensormap.h"
+
+namespace rnb {
+
+// Tile configurations (BN, element bytes, smem stages, staging buffers). All use BM = 128.
+using CfgBf16N128 = ConvCfg<128, 2, 4, 3>;
+using CfgBf16N64 = ConvCfg<64, 2, 6, 3>;
+using CfgTf32N128 = ConvCfg<128, 4, 3, 2>;
+using CfgTf32N64 = ConvCfg<64, 4, 5, 3>;
+
+static_assert(CfgBf16N128::SMEM_BYTES <= 232448, "smem budget");
+static_assert(CfgBf16N64::SMEM_BYTES <= 232448, "smem budget");
+static_assert(CfgTf32N128::SMEM_BYTES <= 232448, "smem budget");
+static_assert(CfgTf32N64::SMEM_BYTES <= 232448, "smem budget");
+
+template <class Cfg>
+static cudaError_t set_smem() {
+    return cudaFuncSetAttribute(conv_igemm_kernel<Cfg>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+}
+
+cudaError_t conv_kernels_init() {
+    cudaError_t e;
+    if ((e = set_smem<CfgBf16N128>()) != cudaSuccess) return e;
+    if ((e = set_smem<CfgBf16N64>()) != cudaSuccess) return e;
+    if ((e = set_smem<CfgTf32N128>()) != cudaSuccess) return e;
+    if ((e = set_smem<CfgTf32N64>()) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+static int fail(char* err, int errlen, const char* msg, int code) {
+    if (err && errlen > 0) snprintf(err, errlen, "%s (code %d)", msg, code);
+    return code ? code : -1;
+}
+
+int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn, char* err,
+                   int errlen) {
+    memset(plan, 0, sizeof(*plan));
+    const int esz = static_cast<int>(d.act);
+    const int bk = 128 / esz;
+    if (d.ksize != 1 && d.ksize != 3) return fail(err, errlen, "conv_plan: ksize must be 1 or 3", -2);
+    if (d.Cin % bk != 0) return fail(err, errlen, "conv_plan: Cin must be a multiple of the K block", -3);
+    if (d.Cout % 64 != 0) return fail(err, errlen, "conv_plan: Cout must be a multiple of 64", -4);
+    const int OH = (2 * d.pad + d.H - d.ksize) / d.stride + 1;  // convOutputSize, ops.cuh:9-13
+    const int OW = (2 * d.pad + d.W - d.ksize) / d.stride + 1;
+    const long long M = 1LL * d.B * OH * OW;
+    if (M <= 0 || M > 0x7fffffffLL) return fail(err, errlen, "conv_plan: bad M", -5);
+
+    int bn = (d.Cout % 128 == 0) ? 128 : 64;
+    if (force_bn == 64 || force_bn == 128) {
+        if (d.Cout % force_bn != 0) return fail(err, errlen, "conv_plan: forced BN does not divide Cout", -6);
+        bn = force_bn;
+    }
+    ConvGeom& g = plan->g;
+    g.M = static_cast<int>(M);
+    g.OH = OH;
+    g.OW = OW;
+    g.Cout = d.Cout;
+    g.stride = d.stride;
+    g.lower = -d.pad;
+    g.ksize = d.ksize;
+    g.kblocks_per_tap = d.Cin / bk;
+    g.num_kblocks = d.ksize * d.ksize * g.kblocks_per_tap;
+    g.m_tiles = static_cast<int>((M + 127) / 128);
+    g.n_tiles = d.Cout / bn;
+    g.relu = d.relu ? 1 : 0;
+    g.has_res = d.residual ? 1 : 0;
+    plan->bias = d.bias;
+    plan->bn = bn;
+    plan->esz = esz;
+    const int tiles = g.m_tiles * g.n_tiles;
+    plan->grid = tiles < num_sms ? tiles : num_sms;
+    plan->flops = 2.0 * static_cast<double>(M) * d.Cout * (1.0 * d.ksize * d.ksize * d.Cin);
+
+    const TmDtype dt = d.act == ActType::BF16 ? TmDtype::BF16 : TmDtype::F32;
+    int r;
+    if ((r = make_im2col_nhwc(&plan->tmA, dt, d.in, d.B, d.H, d.W, d.Cin, d.ksize, d.stride, d.pad,
+                              128)) != 0)
+        return fail(err, errlen, "conv_plan: im2col tensor map (A) failed", r);
+    const uint64_t K = 1ull * d.ksize * d.ksize * d.Cin;
+    if ((r = make_tiled_2d(&plan->tmB, dt, d.weight, d.Cout, K, bn)) != 0)
+        return fail(err, errlen, "conv_plan: tiled tensor map (B) failed", r);
+    if ((r = make_tiled_2d(&plan->tmOut, dt, d.out, M, d.Cout, 128)) != 0)
+        return fail(err, errlen, "conv_plan: tiled tensor map (out) failed", r);
+    const void* res = d.residual ? d.residual : d.out;
+    if ((r = make_tiled_2d(&plan->tmRes, dt, res, M, d.Cout, 128)) != 0)
+        return fail(err, errlen, "conv_plan: tiled tensor map (residual) failed", r);
+    return 0;
+}
+
+template <class Cfg>
+static cudaError_t launch(const ConvPlan& p, cudaStream_t stream) {
+    conv_igemm_kernel<Cfg><<<p.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(
+        p.tmA, p.tmB, p.tmOut, p.tmRes, p.bias, p.g);
+    return cudaGetLastError();
+}
+
+cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
+    if (p.esz == 2) return p.bn == 128 ? launch<CfgBf16N128>(p, stream) : launch<CfgBf16N64>(p, stream);
+    return p.bn == 128 ? launch<CfgTf32N128>(p, stream) : launch<CfgTf32N64>(p, stream);
+}
+
+}  // namespace rnb

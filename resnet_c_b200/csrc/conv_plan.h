@@ -1,0 +1,42 @@
+// conv_plan.h — one planned (descriptor-complete) launch of the implicit-GEMM conv kernel.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "conv_igemm.cuh"
+
+namespace rnb {
+
+enum class ActType { BF16 = 2, TF32 = 4 };  // value = bytes per element
+
+struct ConvDesc {
+    int B, H, W, Cin, Cout, ksize, stride, pad;
+    bool relu;
+    ActType act;
+    const void* in;        // NHWC [B][H][W][Cin]
+    const void* weight;    // [Cout][ksize][ksize][Cin], BN-folded, same element type as `in`
+    const float* bias;     // [Cout] fp32 (folded BN shift)
+    const void* residual;  // NHWC [B][OH][OW][Cout] or nullptr
+    void* out;             // NHWC [B][OH][OW][Cout]
+};
+
+struct ConvPlan {
+    CUtensorMap tmA, tmB, tmOut, tmRes;
+    ConvGeom g;
+    const float* bias;
+    int bn;       // tile N
+    int esz;      // element bytes
+    int grid;     // persistent CTAs
+    double flops;  // 2*M*N*K
+};
+
+// Builds the tensor maps and tile geometry. Returns 0 on success; on failure writes a message to
+// `err` (if non-null, at most errlen bytes).
+int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn, char* err,
+                   int errlen);
+// Enqueues the kernel on `stream` (no synchronisation).
+cudaError_t conv_plan_launch(const ConvPlan& plan, cudaStream_t stream);
+// One-time per process: raise the dynamic shared memory limit of every kernel instantiation.
+cudaError_t conv_kernels_init();
+
+}  // namespace rnb
