@@ -1,0 +1,142 @@
+/* rnb.h — C ABI of librnb.so, the B200-native (sm_100a) ResNet inference hot path.
+ *
+ * This is the boundary a host program binds (C/C++ directly, Python through ctypes, anything else
+ * through its FFI): plain pointers and sizes, no C++ or torch types. Every entry point cites the
+ * reference interface it replaces (paths are into olehskip/resnet.c).
+ *
+ * Conventions
+ *   - All `*_dev` pointers are CUDA device pointers on the device passed to rnb_init().
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - Functions return 0 on success and a non-zero code on failure; rnb_last_error() then returns a
+ *     thread-local, human-readable message. Nothing here aborts the process (the C++ shims in
+ *     cuda/nn.cu add the reference's abort-on-error behaviour on top).
+ *   - Calls are asynchronous on `stream` unless stated otherwise.
+ *   - There is no CPU fallback: without a B200-class GPU every compute call fails.
+ */
+#ifndef RNB_H
+#define RNB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RNB_OK 0
+#define RNB_ERR_INVALID 1   /* bad argument */
+#define RNB_ERR_CUDA 2      /* CUDA runtime / driver failure */
+#define RNB_ERR_IO 3        /* weight / image file problem */
+#define RNB_ERR_UNSUPPORTED 4
+
+/* Arithmetic type of the tensor-core path. Activations and weights are stored in this type,
+ * accumulation is always FP32, logits are always FP32. */
+#define RNB_DTYPE_BF16 0
+#define RNB_DTYPE_TF32 1
+
+typedef struct rnb_model rnb_model_t;
+
+/* ---- library ---------------------------------------------------------------------------- */
+
+/* Select the CUDA device, check it is sm_100, raise kernel shared-memory limits. Idempotent. */
+int rnb_init(int device);
+/* Message of the last failing call on this thread ("" if none). */
+const char* rnb_last_error(void);
+/* "resnet.c_b200 x.y (sm_100a)". */
+const char* rnb_version(void);
+
+/* ---- whole-model path (replaces createResnet152 / resnet152Forward / the CPU arg-max,
+ *      cuda/inference/main.cu:109-125, 168-226, 243-251) -------------------------------------- */
+
+/* Build a model: `arch` is "resnet18" | "resnet34" | "resnet50" | "resnet101" | "resnet152".
+ * `weights_dir` holds one raw little-endian float32 file per state_dict key exactly as written by
+ * save_weights.py:8-12 (conv OIHW, bn .weight/.bias/.running_mean/.running_var, fc [out,in]).
+ * BatchNorm is folded into the conv weights/bias in FP64 at load time (ops.cu:149-150 evaluates the
+ * same expression in double). `max_batch` sizes the activation arena; `chunk` is the number of
+ * images pushed through the whole network at a time (0 = library default) so that inter-layer
+ * activations stay L2-resident. */
+int rnb_model_create(const char* arch, int dtype, const char* weights_dir, int max_batch, int chunk,
+                     rnb_model_t** out);
+int rnb_model_destroy(rnb_model_t* m);
+
+/* Forward pass on device buffers: x_dev is [batch,3,224,224] float32 NCHW (the layout of the files
+ * written by convert_imgs_to_bin.py:20-23), logits_dev is [batch,num_classes] float32,
+ * top1_dev is [batch] int32 (lowest index among ties, as main.cu:243-251); either output may be
+ * NULL. The whole pass is replayed from a CUDA graph cached per batch size. */
+int rnb_model_forward(rnb_model_t* m, const float* x_dev, int batch, float* logits_dev,
+                      int32_t* top1_dev, void* stream);
+
+/* Same through HOST buffers (what main.cu does with loadToCuda / fc_out.cpu()): copies the input
+ * host->device chunk by chunk overlapped with compute, runs the pass, copies logits/top-1 back and
+ * synchronises. Pinned host memory is used as-is; pageable memory goes through the driver's
+ * staging. */
+int rnb_model_forward_host(rnb_model_t* m, const float* x_host, int batch, float* logits_host,
+                           int32_t* top1_host);
+
+/* Introspection used by the benchmarks. */
+int rnb_model_num_classes(const rnb_model_t* m);
+int rnb_model_num_convs(const rnb_model_t* m);
+/* Kernel launches one forward of `batch` images issues (graph nodes). */
+int rnb_model_launches_per_forward(rnb_model_t* m, int batch);
+/* Algorithmic FLOPs per image: 2*MAC over convs + fc. */
+double rnb_model_flops_per_image(const rnb_model_t* m);
+/* Copy an intermediate activation of the LAST forward (chunk 0) to `out_dev` as float32 NCHW.
+ * `name` is "stem" | "maxpool" | "layer{L}.{i}" (block output) | "avgpool". Returns the element
+ * count through *numel (call with out_dev = NULL to query). Debug / parity use only. */
+int rnb_model_get_activation(rnb_model_t* m, const char* name, float* out_dev, int64_t* numel,
+                             void* stream);
+
+/* ---- fused tensor-core convolution on caller-owned FP32 NCHW tensors
+ *      (conv2dForwardKernel + batchNorm2dForwardKernel [+ addForwardKernel] [+ reluForwardKernel],
+ *      ops.cu:14-48,139-151,153-160,130-137 as chained by layerForward, main.cu:127-166) -------- */
+
+/* y = act( bn(conv(x, w)) + residual ). x [B,Cin,H,W]; w [Cout,Cin,k,k]; bn_* are [Cout] or all
+ * NULL (no BN); residual [B,Cout,OH,OW] or NULL; k in {1,3}; Cin % 64 == 0, Cout % 64 == 0.
+ * Internally converts to NHWC `dtype`, runs the tcgen05 implicit-GEMM kernel, converts back. */
+int rnb_conv_bn_act_forward(const float* x_dev, const float* w_dev, const float* bn_weight_dev,
+                            const float* bn_bias_dev, const float* bn_mean_dev,
+                            const float* bn_var_dev, const float* residual_dev, float* out_dev,
+                            int B, int Cin, int H, int W, int Cout, int k, int stride, int pad,
+                            int relu, int dtype, void* stream);
+
+/* Fused stem: conv 7x7/2 pad 3 (3 -> 64) + BN + ReLU + maxpool 3x3/2 pad 1
+ * (main.cu:181-192). x [B,3,H,W] -> out [B,64,OH/2,OW/2] float32 NCHW. */
+int rnb_stem_forward(const float* x_dev, const float* w_dev, const float* bn_weight_dev,
+                     const float* bn_bias_dev, const float* bn_mean_dev, const float* bn_var_dev,
+                     float* out_dev, int B, int H, int W, int dtype, void* stream);
+
+/* Fused tail: global average pool + fc + arg-max (main.cu:213-224, 243-251).
+ * x [B,C,HW] float32 NCHW, fc_w [classes,C], fc_b [classes] -> logits [B,classes], top1 [B]. */
+int rnb_tail_forward(const float* x_dev, const float* fc_w_dev, const float* fc_b_dev,
+                     float* logits_dev, int32_t* top1_dev, int B, int C, int HW, int classes,
+                     void* stream);
+
+/* ---- per-op FP32 NCHW entry points with the reference kernels' exact semantics
+ *      (what cuda/nn.cu's module forwards call; ops.cuh:15-32) --------------------------------- */
+
+/* conv2dForwardKernel, ops.cu:14-48 — square kernel, zero padding, no bias. */
+int rnb_conv2d_forward(const float* x_dev, float* out_dev, const float* w_dev, int B, int Cin, int H,
+                       int W, int Cout, int k, int stride, int pad, void* stream);
+/* batchNorm2dForwardKernel, ops.cu:139-151 — eval mode, eps 1e-5 evaluated in double; in place OK. */
+int rnb_batchnorm2d_forward(const float* x_dev, float* out_dev, const float* weight_dev,
+                            const float* bias_dev, const float* mean_dev, const float* var_dev, int B,
+                            int C, int HW, void* stream);
+/* reluForwardKernel, ops.cu:130-137 — in place OK. */
+int rnb_relu_forward(const float* x_dev, float* out_dev, int64_t n, void* stream);
+/* addForwardKernel, ops.cu:153-160 — in place OK. */
+int rnb_add_forward(const float* a_dev, const float* b_dev, float* out_dev, int64_t n, void* stream);
+/* maxPool2dKernel, ops.cu:50-78 — -inf init, out-of-bounds taps skipped. */
+int rnb_maxpool2d_forward(const float* x_dev, float* out_dev, int B, int C, int H, int W, int k,
+                          int stride, int pad, void* stream);
+/* avgPool2dKernel, ops.cu:80-108 — divides by k*k even when taps are skipped. */
+int rnb_avgpool2d_forward(const float* x_dev, float* out_dev, int B, int C, int H, int W, int k,
+                          int stride, int pad, void* stream);
+/* linearForwardKernel, ops.cu:110-128 — bias may be NULL. */
+int rnb_linear_forward(const float* x_dev, float* out_dev, const float* w_dev, const float* bias_dev,
+                       int B, int in_features, int out_features, void* stream);
+/* Row-wise arg-max, lowest index on ties (main.cu:243-251). */
+int rnb_argmax_forward(const float* x_dev, int32_t* out_dev, int B, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNB_H */

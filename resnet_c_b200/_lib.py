@@ -1,0 +1,98 @@
+"""ctypes binding of librnb.so (the C ABI declared in include/rnb.h).
+
+The library is the product; this module only declares prototypes. Importing the package works
+without a GPU (so the CPU test-suite can check that the .so loads and exports every symbol), but any
+compute call fails loudly when there is no B200 — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB_PATH = Path(__file__).resolve().parent / "librnb.so"
+HEADER_PATH = ROOT / "include" / "rnb.h"
+
+RNB_OK = 0
+DTYPE_BF16 = 0
+DTYPE_TF32 = 1
+DTYPES = {"bf16": DTYPE_BF16, "tf32": DTYPE_TF32}
+
+
+class RnbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes). Pointers to device memory are passed as integers (c_void_p).
+PROTOTYPES = {
+    "rnb_init": (C.c_int, [C.c_int]),
+    "rnb_last_error": (C.c_char_p, []),
+    "rnb_version": (C.c_char_p, []),
+    "rnb_model_create": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "rnb_model_destroy": (C.c_int, [_vp]),
+    "rnb_model_forward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "rnb_model_forward_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "rnb_model_num_classes": (C.c_int, [_vp]),
+    "rnb_model_num_convs": (C.c_int, [_vp]),
+    "rnb_model_launches_per_forward": (C.c_int, [_vp, C.c_int]),
+    "rnb_model_flops_per_image": (C.c_double, [_vp]),
+    "rnb_model_get_activation": (C.c_int, [_vp, C.c_char_p, _vp, C.POINTER(C.c_int64), _vp]),
+    "rnb_conv_bn_act_forward": (C.c_int, [_vp] * 8 + [C.c_int] * 10 + [_vp]),
+    "rnb_stem_forward": (C.c_int, [_vp] * 7 + [C.c_int] * 4 + [_vp]),
+    "rnb_tail_forward": (C.c_int, [_vp] * 5 + [C.c_int] * 4 + [_vp]),
+    "rnb_conv2d_forward": (C.c_int, [_vp] * 3 + [C.c_int] * 8 + [_vp]),
+    "rnb_batchnorm2d_forward": (C.c_int, [_vp] * 6 + [C.c_int] * 3 + [_vp]),
+    "rnb_relu_forward": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "rnb_add_forward": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp]),
+    "rnb_maxpool2d_forward": (C.c_int, [_vp, _vp] + [C.c_int] * 7 + [_vp]),
+    "rnb_avgpool2d_forward": (C.c_int, [_vp, _vp] + [C.c_int] * 7 + [_vp]),
+    "rnb_linear_forward": (C.c_int, [_vp] * 4 + [C.c_int] * 3 + [_vp]),
+    "rnb_argmax_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
+}
+
+
+def header_symbols() -> list[str]:
+    """Every function name declared in include/rnb.h."""
+    text = HEADER_PATH.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rnb_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib() -> C.CDLL:
+    """Load librnb.so (once). Raises if the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RnbError(
+                f"{LIB_PATH} is missing: build it with `python -m resnet_c_b200.build librnb` "
+                "(there is no Python/CPU fallback for the hot path)")
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != RNB_OK:
+        msg = lib().rnb_last_error().decode(errors="replace")
+        raise RnbError(f"librnb error {rc}: {msg}")
+
+
+_initialised_device = None
+
+
+def init(device: int = 0) -> None:
+    global _initialised_device
+    if _initialised_device != device:
+        check(lib().rnb_init(device))
+        _initialised_device = device

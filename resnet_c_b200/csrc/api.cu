@@ -1,0 +1,400 @@
+// api.cu — the extern "C" surface declared in include/rnb.h.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/rnb.h"
+#include "conv_plan.h"
+#include "internal.h"
+#include "model.h"
+
+struct rnb_model {
+    rnb::Model impl;
+};
+
+namespace rnb {
+
+namespace {
+thread_local std::string g_error;
+int g_num_sms = 0;
+int g_device = -1;
+std::mutex g_init_mutex;
+}  // namespace
+
+int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+void set_error(const std::string& msg) { g_error = msg; }
+int fail_cuda(cudaError_t e, const char* what) {
+    g_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return RNB_ERR_CUDA;
+}
+
+}  // namespace rnb
+
+using namespace rnb;
+
+#define API_CUDA(expr)                                        \
+    do {                                                      \
+        cudaError_t e__ = (expr);                             \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #expr); \
+    } while (0)
+
+static int require_init() {
+    if (g_device < 0) {
+        set_error("rnb_init() has not been called (or failed): no CUDA device selected");
+        return RNB_ERR_CUDA;
+    }
+    return RNB_OK;
+}
+
+extern "C" {
+
+int rnb_init(int device) {
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error(std::string("no CUDA device available: ") +
+                  (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                  " — librnb has no CPU fallback");
+        return RNB_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        set_error("device index out of range");
+        return RNB_ERR_INVALID;
+    }
+    API_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    API_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                  std::to_string(prop.minor) + "; librnb is built for sm_100a (B200) only");
+        return RNB_ERR_UNSUPPORTED;
+    }
+    g_num_sms = prop.multiProcessorCount;
+    API_CUDA(conv_kernels_init());
+    g_device = device;
+    set_error("");
+    return RNB_OK;
+}
+
+const char* rnb_last_error(void) { return g_error.c_str(); }
+const char* rnb_version(void) { return "resnet.c_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------ model
+int rnb_model_create(const char* arch, int dtype, const char* weights_dir, int max_batch, int chunk,
+                     rnb_model_t** out) {
+    if (!arch || !weights_dir || !out) {
+        set_error("rnb_model_create: NULL argument");
+        return RNB_ERR_INVALID;
+    }
+    int r = require_init();
+    if (r) return r;
+    rnb_model* m = new rnb_model();
+    r = m->impl.load(arch, dtype, weights_dir, max_batch, chunk);
+    if (r) {
+        const std::string keep = g_error;
+        delete m;
+        g_error = keep;
+        return r;
+    }
+    *out = m;
+    return RNB_OK;
+}
+
+int rnb_model_destroy(rnb_model_t* m) {
+    if (m) {
+        cudaDeviceSynchronize();
+        delete m;
+    }
+    return RNB_OK;
+}
+
+int rnb_model_forward(rnb_model_t* m, const float* x_dev, int batch, float* logits_dev,
+                      int32_t* top1_dev, void* stream) {
+    if (!m) {
+        set_error("rnb_model_forward: NULL model");
+        return RNB_ERR_INVALID;
+    }
+    return m->impl.forward(x_dev, batch, logits_dev, top1_dev, static_cast<cudaStream_t>(stream));
+}
+
+int rnb_model_forward_host(rnb_model_t* m, const float* x_host, int batch, float* logits_host,
+                           int32_t* top1_host) {
+    if (!m || !x_host) {
+        set_error("rnb_model_forward_host: NULL argument");
+        return RNB_ERR_INVALID;
+    }
+    return m->impl.forward_host(x_host, batch, logits_host, top1_host);
+}
+
+int rnb_model_num_classes(const rnb_model_t* m) { return m ? m->impl.classes : 0; }
+int rnb_model_num_convs(const rnb_model_t* m) { return m ? m->impl.num_convs : 0; }
+int rnb_model_launches_per_forward(rnb_model_t* m, int batch) {
+    if (!m || batch <= 0) return 0;
+    const int chunks = (batch + m->impl.chunk - 1) / m->impl.chunk;
+    return chunks * m->impl.launches_per_chunk();
+}
+double rnb_model_flops_per_image(const rnb_model_t* m) { return m ? m->impl.flops_per_image : 0.0; }
+
+int rnb_model_get_activation(rnb_model_t* m, const char* name, float* out_dev, int64_t* numel,
+                             void* stream) {
+    if (!m || !name) {
+        set_error("rnb_model_get_activation: NULL argument");
+        return RNB_ERR_INVALID;
+    }
+    Model& M = m->impl;
+    auto pit = M.plans.find(M.last_chunk_n);
+    if (pit == M.plans.end()) {
+        set_error("rnb_model_get_activation: no forward has run yet");
+        return RNB_ERR_INVALID;
+    }
+    auto ait = pit->second.named.find(name);
+    if (ait == pit->second.named.end()) {
+        set_error(std::string("rnb_model_get_activation: unknown activation '") + name + "'");
+        return RNB_ERR_INVALID;
+    }
+    const NamedAct& a = ait->second;
+    const int n = pit->second.n;
+    if (numel) *numel = 1LL * n * a.C * a.H * a.W;
+    if (!out_dev) return RNB_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (std::string(name) == "avgpool") {
+        API_CUDA(cudaMemcpyAsync(out_dev, a.ptr, 1ull * n * a.C * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+        return RNB_OK;
+    }
+    API_CUDA(launch_nhwc_to_nchw(a.ptr, out_dev, n, a.C, a.H * a.W, M.esz, s));
+    return RNB_OK;
+}
+
+// ------------------------------------------------------------------------------ fused conv
+int rnb_conv_bn_act_forward(const float* x_dev, const float* w_dev, const float* bn_weight_dev,
+                            const float* bn_bias_dev, const float* bn_mean_dev,
+                            const float* bn_var_dev, const float* residual_dev, float* out_dev,
+                            int B, int Cin, int H, int W, int Cout, int k, int stride, int pad,
+                            int relu, int dtype, void* stream) {
+    int r = require_init();
+    if (r) return r;
+    if (!x_dev || !w_dev || !out_dev || B <= 0 || H <= 0 || W <= 0 || stride <= 0 || pad < 0) {
+        set_error("rnb_conv_bn_act_forward: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    const int nbn = (bn_weight_dev != nullptr) + (bn_bias_dev != nullptr) + (bn_mean_dev != nullptr) +
+                    (bn_var_dev != nullptr);
+    if (nbn != 0 && nbn != 4) {
+        set_error("rnb_conv_bn_act_forward: BN vectors must be all set or all NULL");
+        return RNB_ERR_INVALID;
+    }
+    if (dtype != RNB_DTYPE_BF16 && dtype != RNB_DTYPE_TF32) {
+        set_error("rnb_conv_bn_act_forward: bad dtype");
+        return RNB_ERR_INVALID;
+    }
+    const int esz = dtype == RNB_DTYPE_BF16 ? 2 : 4;
+    if ((k != 1 && k != 3) || Cin % (128 / esz) != 0 || Cout % 64 != 0 || 2 * pad + H < k ||
+        2 * pad + W < k) {
+        set_error("rnb_conv_bn_act_forward: unsupported shape (k in {1,3}, Cin % 64 == 0 "
+                  "(32 for tf32), Cout % 64 == 0)");
+        return RNB_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int OH = (2 * pad + H - k) / stride + 1, OW = (2 * pad + W - k) / stride + 1;
+    const size_t in_b = 1ull * B * H * W * Cin * esz, out_b = 1ull * B * OH * OW * Cout * esz;
+    const size_t w_b = 1ull * Cout * k * k * Cin * esz;
+    void *xin = nullptr, *wp = nullptr, *res = nullptr, *y = nullptr;
+    float* bias = nullptr;
+    API_CUDA(cudaMallocAsync(&xin, in_b, s));
+    API_CUDA(cudaMallocAsync(&wp, w_b, s));
+    API_CUDA(cudaMallocAsync(&y, out_b, s));
+    API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&bias), Cout * sizeof(float), s));
+    if (residual_dev) API_CUDA(cudaMallocAsync(&res, out_b, s));
+    API_CUDA(launch_nchw_to_nhwc(x_dev, xin, B, Cin, H * W, esz, s));
+    if (residual_dev) API_CUDA(launch_nchw_to_nhwc(residual_dev, res, B, Cout, OH * OW, esz, s));
+    API_CUDA(launch_fold_pack(w_dev, bn_weight_dev, bn_bias_dev, bn_mean_dev, bn_var_dev, wp, bias,
+                              Cout, Cin, k, esz, s));
+    ConvDesc d{};
+    d.B = B; d.H = H; d.W = W; d.Cin = Cin; d.Cout = Cout; d.ksize = k; d.stride = stride; d.pad = pad;
+    d.relu = relu != 0;
+    d.act = esz == 2 ? ActType::BF16 : ActType::TF32;
+    d.in = xin; d.weight = wp; d.bias = bias; d.residual = res; d.out = y;
+    ConvPlan plan;
+    char err[256];
+    if (conv_plan_init(&plan, d, num_sms(), 0, err, sizeof(err))) {
+        set_error(err);
+        return RNB_ERR_CUDA;
+    }
+    API_CUDA(conv_plan_launch(plan, s));
+    API_CUDA(launch_nhwc_to_nchw(y, out_dev, B, Cout, OH * OW, esz, s));
+    API_CUDA(cudaFreeAsync(xin, s));
+    API_CUDA(cudaFreeAsync(wp, s));
+    API_CUDA(cudaFreeAsync(y, s));
+    API_CUDA(cudaFreeAsync(bias, s));
+    if (res) API_CUDA(cudaFreeAsync(res, s));
+    return RNB_OK;
+}
+
+int rnb_stem_forward(const float* x_dev, const float* w_dev, const float* bn_weight_dev,
+                     const float* bn_bias_dev, const float* bn_mean_dev, const float* bn_var_dev,
+                     float* out_dev, int B, int H, int W, int dtype, void* stream) {
+    int r = require_init();
+    if (r) return r;
+    if (!x_dev || !w_dev || !out_dev || B <= 0 || H < 7 || W < 7) {
+        set_error("rnb_stem_forward: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    const int nbn = (bn_weight_dev != nullptr) + (bn_bias_dev != nullptr) + (bn_mean_dev != nullptr) +
+                    (bn_var_dev != nullptr);
+    if (nbn != 0 && nbn != 4) {
+        set_error("rnb_stem_forward: BN vectors must be all set or all NULL");
+        return RNB_ERR_INVALID;
+    }
+    const int esz = dtype == RNB_DTYPE_BF16 ? 2 : 4;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int OH = (6 + H - 7) / 2 + 1, OW = (6 + W - 7) / 2 + 1;
+    const int PH = (2 + OH - 3) / 2 + 1, PW = (2 + OW - 3) / 2 + 1;
+    float *wf = nullptr, *bias = nullptr;
+    void *conv = nullptr, *pool = nullptr;
+    API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wf), 64 * 147 * sizeof(float), s));
+    API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&bias), 64 * sizeof(float), s));
+    API_CUDA(cudaMallocAsync(&conv, 1ull * B * OH * OW * 64 * esz, s));
+    API_CUDA(cudaMallocAsync(&pool, 1ull * B * PH * PW * 64 * esz, s));
+    API_CUDA(launch_fold_f32(w_dev, bn_weight_dev, bn_bias_dev, bn_mean_dev, bn_var_dev, wf, bias, 64,
+                             147, s));
+    API_CUDA(launch_stem_conv(x_dev, wf, bias, conv, B, H, W, esz, s));
+    API_CUDA(launch_maxpool_nhwc(conv, pool, B, OH, OW, 64, esz, s));
+    API_CUDA(launch_nhwc_to_nchw(pool, out_dev, B, 64, PH * PW, esz, s));
+    API_CUDA(cudaFreeAsync(wf, s));
+    API_CUDA(cudaFreeAsync(bias, s));
+    API_CUDA(cudaFreeAsync(conv, s));
+    API_CUDA(cudaFreeAsync(pool, s));
+    return RNB_OK;
+}
+
+int rnb_tail_forward(const float* x_dev, const float* fc_w_dev, const float* fc_b_dev,
+                     float* logits_dev, int32_t* top1_dev, int B, int C, int HW, int classes,
+                     void* stream) {
+    int r = require_init();
+    if (r) return r;
+    if (!x_dev || !fc_w_dev || !logits_dev || B <= 0 || C <= 0 || C % 4 != 0 || HW <= 0 ||
+        classes <= 0) {
+        set_error("rnb_tail_forward: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    int k = 0;
+    for (int i = 1; i * i <= HW; ++i)
+        if (i * i == HW) k = i;
+    if (k == 0) {
+        set_error("rnb_tail_forward: HW must be a perfect square (global k x k average pool)");
+        return RNB_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* pooled = nullptr;
+    API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pooled), 1ull * B * C * sizeof(float), s));
+    API_CUDA(launch_pool2d_f32(false, x_dev, pooled, B, C, k, k, k, 1, 0, s));
+    API_CUDA(launch_fc(pooled, fc_w_dev, fc_b_dev, logits_dev, B, C, classes, s));
+    if (top1_dev) API_CUDA(launch_argmax_f32(logits_dev, top1_dev, B, classes, s));
+    API_CUDA(cudaFreeAsync(pooled, s));
+    return RNB_OK;
+}
+
+// ------------------------------------------------------------------------------ per-op fp32
+int rnb_conv2d_forward(const float* x_dev, float* out_dev, const float* w_dev, int B, int Cin, int H,
+                       int W, int Cout, int k, int stride, int pad, void* stream) {
+    int r = require_init();
+    if (r) return r;
+    if (!x_dev || !out_dev || !w_dev || B <= 0 || Cin <= 0 || Cout <= 0 || k <= 0 || stride <= 0 ||
+        pad < 0 || 2 * pad + H < k || 2 * pad + W < k) {
+        set_error("rnb_conv2d_forward: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    API_CUDA(launch_conv2d_f32(x_dev, out_dev, w_dev, B, Cin, H, W, Cout, k, stride, pad,
+                               static_cast<cudaStream_t>(stream)));
+    return RNB_OK;
+}
+
+int rnb_batchnorm2d_forward(const float* x_dev, float* out_dev, const float* weight_dev,
+                            const float* bias_dev, const float* mean_dev, const float* var_dev, int B,
+                            int C, int HW, void* stream) {
+    int r = require_init();
+    if (r) return r;
+    if (!x_dev || !out_dev || !weight_dev || !bias_dev || !mean_dev || !var_dev || B <= 0 || C <= 0 ||
+        HW <= 0) {
+        set_error("rnb_batchnorm2d_forward: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    API_CUDA(launch_batchnorm2d_f32(x_dev, out_dev, weight_dev, bias_dev, mean_dev, var_dev, B, C, HW,
+                                    static_cast<cudaStream_t>(stream)));
+    return RNB_OK;
+}
+
+int rnb_relu_forward(const float* x_dev, float* out_dev, int64_t n, void* stream) {
+    int r = require_init();
+    if (r) return r;
+    if (!x_dev || !out_dev || n < 0) {
+        set_error("rnb_relu_forward: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    if (n == 0) return RNB_OK;
+    API_CUDA(launch_relu_f32(x_dev, out_dev, n, static_cast<cudaStream_t>(stream)));
+    return RNB_OK;
+}
+
+int rnb_add_forward(const float* a_dev, const float* b_dev, float* out_dev, int64_t n, void* stream) {
+    int r = require_init();
+    if (r) return r;
+    if (!a_dev || !b_dev || !out_dev || n < 0) {
+        set_error("rnb_add_forward: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    if (n == 0) return RNB_OK;
+    API_CUDA(launch_add_f32(a_dev, b_dev, out_dev, n, static_cast<cudaStream_t>(stream)));
+    return RNB_OK;
+}
+
+static int pool_common(bool is_max, const float* x_dev, float* out_dev, int B, int C, int H, int W,
+                       int k, int stride, int pad, void* stream) {
+    int r = require_init();
+    if (r) return r;
+    if (!x_dev || !out_dev || B <= 0 || C <= 0 || k <= 0 || stride <= 0 || pad < 0 ||
+        2 * pad + H < k || 2 * pad + W < k) {
+        set_error("rnb pool forward: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    API_CUDA(launch_pool2d_f32(is_max, x_dev, out_dev, B, C, H, W, k, stride, pad,
+                               static_cast<cudaStream_t>(stream)));
+    return RNB_OK;
+}
+int rnb_maxpool2d_forward(const float* x_dev, float* out_dev, int B, int C, int H, int W, int k,
+                          int stride, int pad, void* stream) {
+    return pool_common(true, x_dev, out_dev, B, C, H, W, k, stride, pad, stream);
+}
+int rnb_avgpool2d_forward(const float* x_dev, float* out_dev, int B, int C, int H, int W, int k,
+                          int stride, int pad, void* stream) {
+    return pool_common(false, x_dev, out_dev, B, C, H, W, k, stride, pad, stream);
+}
+
+int rnb_linear_forward(const float* x_dev, float* out_dev, const float* w_dev, const float* bias_dev,
+                       int B, int in_features, int out_features, void* stream) {
+    int r = require_init();
+    if (r) return r;
+    if (!x_dev || !out_dev || !w_dev || B <= 0 || in_features <= 0 || out_features <= 0) {
+        set_error("rnb_linear_forward: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    API_CUDA(launch_linear_f32(x_dev, out_dev, w_dev, bias_dev, B, in_features, out_features,
+                               static_cast<cudaStream_t>(stream)));
+    return RNB_OK;
+}
+
+int rnb_argmax_forward(const float* x_dev, int32_t* out_dev, int B, int n, void* stream) {
+    int r = require_init();
+    if (r) return r;
+    if (!x_dev || !out_dev || B <= 0 || n <= 0) {
+        set_error("rnb_argmax_forward: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    API_CUDA(launch_argmax_f32(x_dev, out_dev, B, n, static_cast<cudaStream_t>(stream)));
+    return RNB_OK;
+}
+
+}  // extern "C"

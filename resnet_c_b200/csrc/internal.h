@@ -1,0 +1,60 @@
+// internal.h — declarations shared by the translation units of librnb.so (not part of the ABI).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <string>
+
+namespace rnb {
+
+// ---- process state (api.cu)
+int num_sms();
+void set_error(const std::string& msg);
+int fail_cuda(cudaError_t e, const char* what);  // records the message, returns RNB_ERR_CUDA
+
+// ---- FP32 NCHW per-op kernels (ops_f32.cu)
+cudaError_t launch_conv2d_f32(const float* x, float* out, const float* w, int B, int Cin, int H,
+                              int W, int Cout, int k, int stride, int pad, cudaStream_t s);
+cudaError_t launch_batchnorm2d_f32(const float* x, float* out, const float* weight,
+                                   const float* bias, const float* mean, const float* var, int B,
+                                   int C, int HW, cudaStream_t s);
+cudaError_t launch_relu_f32(const float* x, float* out, int64_t n, cudaStream_t s);
+cudaError_t launch_add_f32(const float* a, const float* b, float* out, int64_t n, cudaStream_t s);
+cudaError_t launch_pool2d_f32(bool is_max, const float* x, float* out, int B, int C, int H, int W,
+                              int k, int stride, int pad, cudaStream_t s);
+cudaError_t launch_linear_f32(const float* x, float* out, const float* w, const float* bias, int B,
+                              int in_f, int out_f, cudaStream_t s);
+cudaError_t launch_argmax_f32(const float* x, int32_t* out, int B, int n, cudaStream_t s);
+
+// ---- layout / weight preparation (layout.cu). `esz` = 2 (bf16) or 4 (tf32-rounded fp32).
+cudaError_t launch_nchw_to_nhwc(const float* x, void* out, int B, int C, int HW, int esz,
+                                cudaStream_t s);
+cudaError_t launch_nhwc_to_nchw(const void* x, float* out, int B, int C, int HW, int esz,
+                                cudaStream_t s);
+// w [Cout][Cin][k][k] fp32 (+ optional BN vectors, all-or-none) -> packed [Cout][k][k][Cin_pad] in
+// the activation type and bias[Cout] fp32. The fold is evaluated in double.
+cudaError_t launch_fold_pack(const float* w, const float* bn_w, const float* bn_b, const float* bn_m,
+                             const float* bn_v, void* packed, float* bias, int Cout, int Cin, int k,
+                             int esz, cudaStream_t s);
+// Same fold, but keeps fp32 OIHW order (used by the CUDA-core stem).
+cudaError_t launch_fold_f32(const float* w, const float* bn_w, const float* bn_b, const float* bn_m,
+                            const float* bn_v, float* w_out, float* bias, int Cout, int per_out,
+                            cudaStream_t s);
+
+// ---- stem + max-pool (stem.cu)
+// conv 7x7/2 pad 3, 3 -> 64, + bias + ReLU: x fp32 NCHW [B,3,H,W] -> out NHWC [B,OH,OW,64].
+cudaError_t launch_stem_conv(const float* x, const float* w_folded /*[64][3][7][7]*/,
+                             const float* bias, void* out, int B, int H, int W, int esz,
+                             cudaStream_t s);
+// max-pool 3x3/2 pad 1 over NHWC.
+cudaError_t launch_maxpool_nhwc(const void* x, void* out, int B, int H, int W, int C, int esz,
+                                cudaStream_t s);
+
+// ---- tail (tail.cu)
+// global average pool over NHWC [B,HW,C] -> pooled [B,C] fp32
+cudaError_t launch_avgpool_nhwc(const void* x, float* pooled, int B, int HW, int C, int esz,
+                                cudaStream_t s);
+// logits[B,classes] = pooled[B,C] * W[classes,C]^T + bias
+cudaError_t launch_fc(const float* pooled, const float* w, const float* bias, float* logits, int B,
+                      int C, int classes, cudaStream_t s);
+
+}  // namespace rnb

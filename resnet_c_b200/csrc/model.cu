@@ -1,0 +1,473 @@
+// model.cu — see model.h
+#include "model.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+
+#include "../../include/rnb.h"
+#include "internal.h"
+
+namespace rnb {
+
+#define RNB_CUDA(expr)                                      \
+    do {                                                    \
+        cudaError_t e__ = (expr);                           \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #expr); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ arena
+void* Arena::acquire(size_t bytes) {
+    bytes = (bytes + 1023) & ~static_cast<size_t>(1023);
+    int best = -1;
+    for (int i = 0; i < static_cast<int>(blocks_.size()); ++i)
+        if (!blocks_[i].busy && blocks_[i].bytes >= bytes &&
+            (best < 0 || blocks_[i].bytes < blocks_[best].bytes))
+            best = i;
+    if (best >= 0) {
+        blocks_[best].busy = true;
+        return blocks_[best].p;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    blocks_.push_back({p, bytes, true});
+    total_ += bytes;
+    return p;
+}
+void Arena::release(void* p) {
+    if (keep) return;
+    for (auto& b : blocks_)
+        if (b.p == p) b.busy = false;
+}
+void Arena::free_all() {
+    for (auto& b : blocks_) cudaFree(b.p);
+    blocks_.clear();
+    total_ = 0;
+}
+
+// ------------------------------------------------------------------------------------ weights
+namespace {
+
+// One raw little-endian float32 file per state_dict key (save_weights.py:8-12), read the way
+// Tensor::loadToCpu does (tensor.cuh:126-147): size comes from the file, shape from the caller.
+int read_f32_file(const std::string& path, size_t expect, std::vector<float>& out) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f.is_open()) {
+        set_error("cannot open weight file " + path);
+        return RNB_ERR_IO;
+    }
+    const std::streamsize bytes = f.tellg();
+    if (bytes != static_cast<std::streamsize>(expect * sizeof(float))) {
+        set_error("weight file " + path + " has " + std::to_string(bytes) + " bytes, expected " +
+                  std::to_string(expect * sizeof(float)));
+        return RNB_ERR_IO;
+    }
+    f.seekg(0);
+    out.resize(expect);
+    f.read(reinterpret_cast<char*>(out.data()), bytes);
+    if (f.fail()) {
+        set_error("short read on " + path);
+        return RNB_ERR_IO;
+    }
+    return RNB_OK;
+}
+
+int upload(const std::vector<float>& h, float** d) {
+    RNB_CUDA(cudaMalloc(d, h.size() * sizeof(float)));
+    RNB_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return RNB_OK;
+}
+
+struct BnDev {
+    float *w = nullptr, *b = nullptr, *m = nullptr, *v = nullptr;
+    void free_all() {
+        cudaFree(w); cudaFree(b); cudaFree(m); cudaFree(v);
+        w = b = m = v = nullptr;
+    }
+};
+
+int load_bn(const std::string& dir, const std::string& name, int C, BnDev& bn) {
+    std::vector<float> h;
+    int r;
+    if ((r = read_f32_file(dir + "/" + name + ".weight", C, h)) || (r = upload(h, &bn.w))) return r;
+    if ((r = read_f32_file(dir + "/" + name + ".bias", C, h)) || (r = upload(h, &bn.b))) return r;
+    if ((r = read_f32_file(dir + "/" + name + ".running_mean", C, h)) || (r = upload(h, &bn.m))) return r;
+    if ((r = read_f32_file(dir + "/" + name + ".running_var", C, h)) || (r = upload(h, &bn.v))) return r;
+    return RNB_OK;
+}
+
+// conv `cname`.weight + bn `bname`.* -> folded, packed device weights.
+int load_conv(const std::string& dir, const std::string& cname, const std::string& bname, int Cin,
+              int Cout, int k, int stride, int pad, int esz, ConvWeights& cw) {
+    std::vector<float> h;
+    int r;
+    if ((r = read_f32_file(dir + "/" + cname + ".weight", 1ull * Cout * Cin * k * k, h))) return r;
+    float* raw = nullptr;
+    if ((r = upload(h, &raw))) return r;
+    BnDev bn;
+    if ((r = load_bn(dir, bname, Cout, bn))) {
+        cudaFree(raw);
+        return r;
+    }
+    cw.Cin = Cin; cw.Cout = Cout; cw.k = k; cw.stride = stride; cw.pad = pad;
+    RNB_CUDA(cudaMalloc(&cw.w, 1ull * Cout * Cin * k * k * esz));
+    RNB_CUDA(cudaMalloc(&cw.bias, Cout * sizeof(float)));
+    RNB_CUDA(launch_fold_pack(raw, bn.w, bn.b, bn.m, bn.v, cw.w, cw.bias, Cout, Cin, k, esz, 0));
+    RNB_CUDA(cudaDeviceSynchronize());
+    cudaFree(raw);
+    bn.free_all();
+    return RNB_OK;
+}
+
+struct ArchSpec {
+    const char* name;
+    bool bottleneck;
+    int blocks[4];
+};
+const ArchSpec kArchs[] = {
+    {"resnet18", false, {2, 2, 2, 2}},  {"resnet34", false, {3, 4, 6, 3}},
+    {"resnet50", true, {3, 4, 6, 3}},   {"resnet101", true, {3, 4, 23, 3}},
+    {"resnet152", true, {3, 8, 36, 3}},  // main.cu:116-119
+};
+
+}  // namespace
+
+Model::~Model() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    for (auto e : copy_events) cudaEventDestroy(e);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    arena.free_all();
+    cudaFree(stem_w); cudaFree(stem_bias); cudaFree(fc_w); cudaFree(fc_b);
+    cudaFree(host_x_dev); cudaFree(host_logits_dev); cudaFree(host_top1_dev); cudaFree(scratch_logits);
+    for (auto& b : blocks) {
+        for (ConvWeights* c : {&b.conv1, &b.conv2, &b.conv3, &b.ds}) {
+            cudaFree(c->w);
+            cudaFree(c->bias);
+        }
+    }
+}
+
+int Model::load(const std::string& arch_name, int dtype, const std::string& dir, int max_batch_,
+                int chunk_) {
+    const ArchSpec* spec = nullptr;
+    for (const auto& a : kArchs)
+        if (arch_name == a.name) spec = &a;
+    if (!spec) {
+        set_error("unknown arch '" + arch_name + "' (resnet18|34|50|101|152)");
+        return RNB_ERR_INVALID;
+    }
+    if (dtype != RNB_DTYPE_BF16 && dtype != RNB_DTYPE_TF32) {
+        set_error("dtype must be RNB_DTYPE_BF16 or RNB_DTYPE_TF32");
+        return RNB_ERR_INVALID;
+    }
+    if (max_batch_ <= 0) {
+        set_error("max_batch must be positive");
+        return RNB_ERR_INVALID;
+    }
+    arch = arch_name;
+    esz = dtype == RNB_DTYPE_BF16 ? 2 : 4;
+    bottleneck = spec->bottleneck;
+    max_batch = max_batch_;
+    num_sms = rnb::num_sms();
+    if (chunk_ <= 0) {
+        const char* env = getenv("RNB_CHUNK");
+        chunk_ = env ? atoi(env) : 0;
+        if (chunk_ <= 0) chunk_ = max_batch_;
+    }
+    chunk = std::min(chunk_, max_batch_);
+    const char* ng = getenv("RNB_NO_GRAPH");
+    use_graph = !(ng && atoi(ng) != 0);
+    const char* ka = getenv("RNB_KEEP_ACTIVATIONS");  // parity debugging: never recycle arena blocks
+    arena.keep = ka && atoi(ka) != 0;
+
+    int r;
+    // ---- stem: conv1 + bn1 (main.cu:110-111), folded in fp32 OIHW for the CUDA-core stem
+    {
+        std::vector<float> h;
+        if ((r = read_f32_file(dir + "/conv1.weight", 64 * 147, h))) return r;
+        float* raw = nullptr;
+        if ((r = upload(h, &raw))) return r;
+        BnDev bn;
+        if ((r = load_bn(dir, "bn1", 64, bn))) return r;
+        RNB_CUDA(cudaMalloc(&stem_w, 64 * 147 * sizeof(float)));
+        RNB_CUDA(cudaMalloc(&stem_bias, 64 * sizeof(float)));
+        RNB_CUDA(launch_fold_f32(raw, bn.w, bn.b, bn.m, bn.v, stem_w, stem_bias, 64, 147, 0));
+        RNB_CUDA(cudaDeviceSynchronize());
+        cudaFree(raw);
+        bn.free_all();
+    }
+    double macs = 64.0 * 147 * 112 * 112;
+    // ---- residual layers (createLayer, main.cu:53-89; BasicBlock per torchvision)
+    int in_c = 64;
+    int hw = 56;
+    num_convs = 1;
+    for (int L = 0; L < 4; ++L) {
+        const int mid = 64 << L;
+        const int out_c = bottleneck ? mid * 4 : mid;
+        const int layer_stride = L == 0 ? 1 : 2;
+        for (int i = 0; i < spec->blocks[L]; ++i) {
+            BlockWeights bw;
+            bw.bottleneck = bottleneck;
+            bw.name = "layer" + std::to_string(L + 1) + "." + std::to_string(i);
+            const std::string p = bw.name + ".";
+            const int stride = i == 0 ? layer_stride : 1;
+            const int out_hw = hw / stride;
+            if (bottleneck) {
+                if ((r = load_conv(dir, p + "conv1", p + "bn1", in_c, mid, 1, 1, 0, esz, bw.conv1))) return r;
+                if ((r = load_conv(dir, p + "conv2", p + "bn2", mid, mid, 3, stride, 1, esz, bw.conv2))) return r;
+                if ((r = load_conv(dir, p + "conv3", p + "bn3", mid, out_c, 1, 1, 0, esz, bw.conv3))) return r;
+                macs += 1.0 * hw * hw * in_c * mid + 1.0 * out_hw * out_hw * mid * mid * 9 +
+                        1.0 * out_hw * out_hw * mid * out_c;
+                num_convs += 3;
+            } else {
+                if ((r = load_conv(dir, p + "conv1", p + "bn1", in_c, mid, 3, stride, 1, esz, bw.conv1))) return r;
+                if ((r = load_conv(dir, p + "conv2", p + "bn2", mid, mid, 3, 1, 1, esz, bw.conv2))) return r;
+                macs += 1.0 * out_hw * out_hw * in_c * mid * 9 + 1.0 * out_hw * out_hw * mid * mid * 9;
+                num_convs += 2;
+            }
+            if (i == 0 && (stride != 1 || in_c != out_c)) {  // main.cu:71
+                bw.has_ds = true;
+                if ((r = load_conv(dir, p + "downsample.0", p + "downsample.1", in_c, out_c, 1, stride, 0,
+                                   esz, bw.ds)))
+                    return r;
+                macs += 1.0 * out_hw * out_hw * in_c * out_c;
+                num_convs += 1;
+            }
+            blocks.push_back(bw);
+            in_c = out_c;
+            hw = out_hw;
+        }
+    }
+    final_c = in_c;
+    // ---- fc (main.cu:122)
+    {
+        std::vector<float> h;
+        // class count comes from the bias file size
+        std::ifstream f(dir + "/fc.bias", std::ios::binary | std::ios::ate);
+        if (!f.is_open()) {
+            set_error("cannot open weight file " + dir + "/fc.bias");
+            return RNB_ERR_IO;
+        }
+        classes = static_cast<int>(f.tellg() / sizeof(float));
+        if (classes <= 0) {
+            set_error("fc.bias is empty");
+            return RNB_ERR_IO;
+        }
+        if ((r = read_f32_file(dir + "/fc.bias", classes, h)) || (r = upload(h, &fc_b))) return r;
+        if ((r = read_f32_file(dir + "/fc.weight", 1ull * classes * final_c, h)) || (r = upload(h, &fc_w)))
+            return r;
+        macs += 1.0 * classes * final_c;
+    }
+    flops_per_image = 2.0 * macs;
+    RNB_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+    RNB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    set_error("");
+    return RNB_OK;
+}
+
+// ------------------------------------------------------------------------------------ planning
+ChunkPlan* Model::plan_for(int n) {
+    auto it = plans.find(n);
+    if (it != plans.end()) return &it->second;
+    ChunkPlan p;
+    p.n = n;
+    const size_t e = esz;
+    auto bytes = [&](int c, int h) { return 1ull * n * h * h * c * e; };
+    auto fail_alloc = [&]() -> ChunkPlan* {
+        set_error("activation arena allocation failed");
+        return nullptr;
+    };
+    const int s_hw = (6 + image - 7) / 2 + 1;     // 112
+    const int p_hw = (2 + s_hw - 3) / 2 + 1;      // 56
+    if (!(p.stem_out = arena.acquire(bytes(64, s_hw)))) return fail_alloc();
+    if (!(p.pool_out = arena.acquire(bytes(64, p_hw)))) return fail_alloc();
+    p.named["stem"] = {p.stem_out, 64, s_hw, s_hw};
+    p.named["maxpool"] = {p.pool_out, 64, p_hw, p_hw};
+    arena.release(p.stem_out);  // dead once the pool has run
+
+    void* x = p.pool_out;
+    int hw = p_hw;
+    const ActType act = esz == 2 ? ActType::BF16 : ActType::TF32;
+    char err[256];
+    auto add_conv = [&](const ConvWeights& cw, const void* in, int in_hw, const void* res, bool relu,
+                        void* out) -> int {
+        ConvDesc d{};
+        d.B = n; d.H = in_hw; d.W = in_hw; d.Cin = cw.Cin; d.Cout = cw.Cout;
+        d.ksize = cw.k; d.stride = cw.stride; d.pad = cw.pad; d.relu = relu; d.act = act;
+        d.in = in; d.weight = cw.w; d.bias = cw.bias; d.residual = res; d.out = out;
+        ConvPlan cp;
+        const int rc = conv_plan_init(&cp, d, num_sms, 0, err, sizeof(err));
+        if (rc) {
+            set_error(err);
+            return rc;
+        }
+        p.convs.push_back(cp);
+        return 0;
+    };
+    for (const BlockWeights& bw : blocks) {
+        const int stride = bw.bottleneck ? bw.conv2.stride : bw.conv1.stride;
+        const int out_hw = hw / stride;
+        const int out_c = bw.bottleneck ? bw.conv3.Cout : bw.conv2.Cout;
+        void* shortcut = x;
+        void* ds = nullptr;
+        if (bw.has_ds) {
+            if (!(ds = arena.acquire(bytes(out_c, out_hw)))) return fail_alloc();
+            if (add_conv(bw.ds, x, hw, nullptr, false, ds)) return nullptr;
+            shortcut = ds;
+        }
+        void* y = nullptr;
+        if (bw.bottleneck) {
+            // conv1 -> bn1 -> relu -> conv2(stride) -> bn2 -> relu -> conv3 -> bn3 -> +shortcut -> relu
+            // (layerForward, main.cu:138-163)
+            void* t1 = arena.acquire(bytes(bw.conv1.Cout, hw));
+            if (!t1) return fail_alloc();
+            if (add_conv(bw.conv1, x, hw, nullptr, true, t1)) return nullptr;
+            void* t2 = arena.acquire(bytes(bw.conv2.Cout, out_hw));
+            if (!t2) return fail_alloc();
+            if (add_conv(bw.conv2, t1, hw, nullptr, true, t2)) return nullptr;
+            arena.release(t1);
+            if (!(y = arena.acquire(bytes(out_c, out_hw)))) return fail_alloc();
+            if (add_conv(bw.conv3, t2, out_hw, shortcut, true, y)) return nullptr;
+            arena.release(t2);
+        } else {
+            void* t1 = arena.acquire(bytes(bw.conv1.Cout, out_hw));
+            if (!t1) return fail_alloc();
+            if (add_conv(bw.conv1, x, hw, nullptr, true, t1)) return nullptr;
+            if (!(y = arena.acquire(bytes(out_c, out_hw)))) return fail_alloc();
+            if (add_conv(bw.conv2, t1, out_hw, shortcut, true, y)) return nullptr;
+            arena.release(t1);
+        }
+        if (ds) arena.release(ds);
+        arena.release(x);
+        x = y;
+        hw = out_hw;
+        p.named[bw.name] = {y, out_c, hw, hw};
+    }
+    p.last = x;
+    p.last_hw = hw * hw;
+    p.last_c = final_c;
+    p.pooled = static_cast<float*>(arena.acquire(1ull * n * final_c * sizeof(float)));
+    if (!p.pooled) return fail_alloc();
+    p.named["avgpool"] = {p.pooled, final_c, 1, 1};
+    // Everything is released again: the next plan (another chunk size) may share the blocks, since
+    // chunks run back to back on one stream.
+    arena.release(x);
+    arena.release(p.pooled);
+    auto ins = plans.emplace(n, std::move(p));
+    return &ins.first->second;
+}
+
+int Model::enqueue_chunk(ChunkPlan& p, const float* x, float* logits, int32_t* top1, cudaStream_t s) {
+    const int n = p.n;
+    const int s_hw = (6 + image - 7) / 2 + 1;
+    RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
+    RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
+    for (const ConvPlan& cp : p.convs) RNB_CUDA(conv_plan_launch(cp, s));
+    RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, n, p.last_hw, p.last_c, esz, s));
+    RNB_CUDA(launch_fc(p.pooled, fc_w, fc_b, logits, n, p.last_c, classes, s));
+    if (top1) RNB_CUDA(launch_argmax_f32(logits, top1, n, classes, s));
+    return RNB_OK;
+}
+
+int Model::forward(const float* x, int batch, float* logits, int32_t* top1, cudaStream_t s) {
+    if (batch <= 0 || batch > max_batch) {
+        set_error("batch must be in [1, max_batch]");
+        return RNB_ERR_INVALID;
+    }
+    if (!x) {
+        set_error("x_dev is NULL");
+        return RNB_ERR_INVALID;
+    }
+    if (!logits) {
+        if (!scratch_logits)
+            RNB_CUDA(cudaMalloc(&scratch_logits, 1ull * max_batch * classes * sizeof(float)));
+        logits = scratch_logits;
+    }
+    const size_t img_elems = 3ull * image * image;
+    for (int off = 0; off < batch; off += chunk) {
+        const int n = std::min(chunk, batch - off);
+        ChunkPlan* p = plan_for(n);
+        if (!p) return RNB_ERR_CUDA;
+        const float* xc = x + off * img_elems;
+        float* lc = logits + 1ull * off * classes;
+        int32_t* tc = top1 ? top1 + off : nullptr;
+        if (!use_graph) {
+            int r = enqueue_chunk(*p, xc, lc, tc, s);
+            if (r) return r;
+            continue;
+        }
+        const GraphKey key{n, xc, lc, tc};
+        auto g = graphs.find(key);
+        if (g == graphs.end()) {
+            if (graphs.size() >= 256) {
+                for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+                graphs.clear();
+            }
+            RNB_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+            int r = enqueue_chunk(*p, xc, lc, tc, cap_stream);
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+            if (r) return r;
+            if (ce != cudaSuccess) return fail_cuda(ce, "cudaStreamEndCapture");
+            cudaGraphExec_t exec = nullptr;
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail_cuda(ce, "cudaGraphInstantiate");
+            g = graphs.emplace(key, exec).first;
+        }
+        RNB_CUDA(cudaGraphLaunch(g->second, s));
+    }
+    last_chunk_n = std::min(chunk, batch);
+    return RNB_OK;
+}
+
+int Model::forward_host(const float* x, int batch, float* logits, int32_t* top1) {
+    if (batch <= 0 || batch > max_batch) {
+        set_error("batch must be in [1, max_batch]");
+        return RNB_ERR_INVALID;
+    }
+    const size_t img_elems = 3ull * image * image;
+    if (!host_x_dev) {
+        RNB_CUDA(cudaMalloc(&host_x_dev, 1ull * max_batch * img_elems * sizeof(float)));
+        RNB_CUDA(cudaMalloc(&host_logits_dev, 1ull * max_batch * classes * sizeof(float)));
+        RNB_CUDA(cudaMalloc(&host_top1_dev, 1ull * max_batch * sizeof(int32_t)));
+    }
+    // Pipeline: every chunk's H2D copy is queued on copy_stream up front; the compute stream waits
+    // per chunk, so chunk i+1 crosses PCIe while chunk i runs.
+    const int nchunks = (batch + chunk - 1) / chunk;
+    while (static_cast<int>(copy_events.size()) < nchunks) {
+        cudaEvent_t e;
+        RNB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        copy_events.push_back(e);
+    }
+    static thread_local cudaStream_t compute = nullptr;
+    if (!compute) RNB_CUDA(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+    for (int c = 0; c < nchunks; ++c) {
+        const int off = c * chunk;
+        const int n = std::min(chunk, batch - off);
+        RNB_CUDA(cudaMemcpyAsync(host_x_dev + off * img_elems, x + off * img_elems,
+                                 n * img_elems * sizeof(float), cudaMemcpyHostToDevice, copy_stream));
+        RNB_CUDA(cudaEventRecord(copy_events[c], copy_stream));
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        const int off = c * chunk;
+        const int n = std::min(chunk, batch - off);
+        RNB_CUDA(cudaStreamWaitEvent(compute, copy_events[c], 0));
+        int r = forward(host_x_dev + off * img_elems, n, host_logits_dev + 1ull * off * classes,
+                        host_top1_dev + off, compute);
+        if (r) return r;
+    }
+    if (logits)
+        RNB_CUDA(cudaMemcpyAsync(logits, host_logits_dev, 1ull * batch * classes * sizeof(float),
+                                 cudaMemcpyDeviceToHost, compute));
+    if (top1)
+        RNB_CUDA(cudaMemcpyAsync(top1, host_top1_dev, 1ull * batch * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, compute));
+    RNB_CUDA(cudaStreamSynchronize(compute));
+    return RNB_OK;
+}
+
+}  // namespace rnb

@@ -1,0 +1,107 @@
+// model.h — the planned ResNet inference engine behind rnb_model_* (include/rnb.h).
+//
+// Mirrors the graph that /root/reference/cuda/inference/main.cu builds by hand (ResnetModel :91-107,
+// createLayer :53-89, layerForward :127-166, resnet152Forward :168-226) for five depths, but plans
+// it once: weights are BN-folded and repacked at load, every convolution becomes one fused tcgen05
+// launch with pre-built TMA descriptors over a liveness-packed activation arena, and each chunk of
+// images is replayed from a CUDA graph.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "conv_plan.h"
+
+namespace rnb {
+
+struct ConvWeights {
+    void* w = nullptr;       // packed [Cout][k][k][Cin] in the activation type, BN folded
+    float* bias = nullptr;   // [Cout]
+    int Cin = 0, Cout = 0, k = 0, stride = 1, pad = 0;
+};
+
+struct BlockWeights {
+    bool bottleneck = false;
+    ConvWeights conv1, conv2, conv3;  // conv3 unused for BasicBlock
+    bool has_ds = false;
+    ConvWeights ds;
+    std::string name;  // "layer{L}.{i}"
+};
+
+struct NamedAct {
+    void* ptr;
+    int C, H, W;
+};
+
+// Everything needed to run `n` images through the network once.
+struct ChunkPlan {
+    int n = 0;
+    void* stem_out = nullptr;   // NHWC [n,112,112,64]
+    void* pool_out = nullptr;   // NHWC [n,56,56,64]
+    std::vector<ConvPlan> convs;
+    void* last = nullptr;       // NHWC [n,7,7,C_final]
+    int last_hw = 0, last_c = 0;
+    float* pooled = nullptr;    // [n, C_final]
+    std::map<std::string, NamedAct> named;
+};
+
+class Arena {
+public:
+    void* acquire(size_t bytes);
+    void release(void* p);
+    void free_all();
+    size_t total_bytes() const { return total_; }
+    bool keep = false;  // debug: never recycle
+private:
+    struct Block { void* p; size_t bytes; bool busy; };
+    std::vector<Block> blocks_;
+    size_t total_ = 0;
+};
+
+struct Model {
+    std::string arch;
+    int esz = 2;            // activation bytes: 2 bf16, 4 tf32
+    int classes = 1000;
+    int image = 224;
+    int max_batch = 0;
+    int chunk = 0;
+    int num_sms = 148;
+    bool bottleneck = true;
+    int final_c = 2048;
+
+    float* stem_w = nullptr;     // folded fp32 [64][3][7][7]
+    float* stem_bias = nullptr;  // [64]
+    std::vector<BlockWeights> blocks;
+    float* fc_w = nullptr;  // [classes][final_c]
+    float* fc_b = nullptr;
+    int num_convs = 0;
+    double flops_per_image = 0;
+
+    Arena arena;
+    std::map<int, ChunkPlan> plans;
+    using GraphKey = std::tuple<int, const void*, void*, void*>;
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    cudaStream_t cap_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_events;
+    float* host_x_dev = nullptr;    // device staging for forward_host
+    float* host_logits_dev = nullptr;
+    int32_t* host_top1_dev = nullptr;
+    float* scratch_logits = nullptr;  // used when the caller passes logits = NULL
+    int last_chunk_n = 0;
+    bool use_graph = true;
+
+    ~Model();
+    int load(const std::string& arch, int dtype, const std::string& dir, int max_batch, int chunk);
+    ChunkPlan* plan_for(int n);
+    int enqueue_chunk(ChunkPlan& p, const float* x, float* logits, int32_t* top1, cudaStream_t s);
+    int forward(const float* x, int batch, float* logits, int32_t* top1, cudaStream_t s);
+    int forward_host(const float* x, int batch, float* logits, int32_t* top1);
+    // stem conv + max-pool + (num_convs - 1) tensor-core convs + avg-pool + fc + arg-max
+    int launches_per_chunk() const { return num_convs + 4; }
+};
+
+}  // namespace rnb

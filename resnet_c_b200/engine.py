@@ -1,0 +1,235 @@
+"""Python face of librnb.so for tests and benchmarks.
+
+torch is used for device memory and streams only; every number comes out of the CUDA kernels behind
+include/rnb.h. Names follow the reference's host API (cuda/nn.cuh): Conv2d / BatchNorm2d / Pool2d /
+Linear forwards, reluForward, addForward, plus the whole-model object.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import DTYPES, RnbError, check
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32_cuda(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RnbError(f"{what} must be a CUDA tensor: librnb has no CPU path")
+    if t.dtype != torch.float32:
+        raise RnbError(f"{what} must be float32")
+    return t.contiguous()
+
+
+def conv_out(x: int, k: int, stride: int, pad: int) -> int:
+    """convOutputSize, cuda/ops.cuh:9-13."""
+    return (2 * pad + x - k) // stride + 1
+
+
+# --------------------------------------------------------------------------- per-op fp32 NCHW
+def conv2d_forward(x, weight, stride=1, padding=0):
+    """Conv2d::forward, cuda/nn.cu:3-16."""
+    x, weight = _f32_cuda(x, "x"), _f32_cuda(weight, "weight")
+    B, Cin, H, W = x.shape
+    Cout, Cin2, k, k2 = weight.shape
+    assert Cin == Cin2 and k == k2
+    out = torch.empty(B, Cout, conv_out(H, k, stride, padding), conv_out(W, k, stride, padding),
+                      device=x.device, dtype=torch.float32)
+    _lib.init(x.device.index or 0)
+    check(_lib.lib().rnb_conv2d_forward(_ptr(x), _ptr(out), _ptr(weight), B, Cin, H, W, Cout, k,
+                                        stride, padding, _stream()))
+    return out
+
+
+def batchnorm2d_forward(x, weight, bias, mean, var, out=None):
+    """BatchNorm2d::forward, cuda/nn.cu:18-29 (in place when out is x)."""
+    x = _f32_cuda(x, "x")
+    B, Cc, H, W = x.shape
+    out = torch.empty_like(x) if out is None else out
+    _lib.init(x.device.index or 0)
+    check(_lib.lib().rnb_batchnorm2d_forward(_ptr(x), _ptr(out), _ptr(_f32_cuda(weight, "weight")),
+                                             _ptr(_f32_cuda(bias, "bias")), _ptr(_f32_cuda(mean, "mean")),
+                                             _ptr(_f32_cuda(var, "var")), B, Cc, H * W, _stream()))
+    return out
+
+
+def relu_forward(x, out=None):
+    """reluForward, cuda/nn.cu:66-75."""
+    x = _f32_cuda(x, "x")
+    out = torch.empty_like(x) if out is None else out
+    _lib.init(x.device.index or 0)
+    check(_lib.lib().rnb_relu_forward(_ptr(x), _ptr(out), x.numel(), _stream()))
+    return out
+
+
+def add_forward(a, b, out=None):
+    """addForward, cuda/nn.cu:77-87."""
+    a, b = _f32_cuda(a, "a"), _f32_cuda(b, "b")
+    assert a.shape == b.shape
+    out = torch.empty_like(a) if out is None else out
+    _lib.init(a.device.index or 0)
+    check(_lib.lib().rnb_add_forward(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()))
+    return out
+
+
+def _pool(fn_name, x, k, stride, padding):
+    x = _f32_cuda(x, "x")
+    B, Cc, H, W = x.shape
+    out = torch.empty(B, Cc, conv_out(H, k, stride, padding), conv_out(W, k, stride, padding),
+                      device=x.device, dtype=torch.float32)
+    _lib.init(x.device.index or 0)
+    check(getattr(_lib.lib(), fn_name)(_ptr(x), _ptr(out), B, Cc, H, W, k, stride, padding, _stream()))
+    return out
+
+
+def maxpool2d_forward(x, k, stride=1, padding=0):
+    """Pool2d::maxforward, cuda/nn.cu:43-53."""
+    return _pool("rnb_maxpool2d_forward", x, k, stride, padding)
+
+
+def avgpool2d_forward(x, k, stride=1, padding=0):
+    """Pool2d::avgforward, cuda/nn.cu:31-41."""
+    return _pool("rnb_avgpool2d_forward", x, k, stride, padding)
+
+
+def linear_forward(x, weight, bias=None):
+    """Linear::forward, cuda/nn.cu:55-64."""
+    x, weight = _f32_cuda(x, "x"), _f32_cuda(weight, "weight")
+    B, fin = x.shape
+    fout = weight.shape[0]
+    out = torch.empty(B, fout, device=x.device, dtype=torch.float32)
+    _lib.init(x.device.index or 0)
+    check(_lib.lib().rnb_linear_forward(_ptr(x), _ptr(out), _ptr(weight),
+                                        _ptr(None if bias is None else _f32_cuda(bias, "bias")), B, fin,
+                                        fout, _stream()))
+    return out
+
+
+def argmax_forward(x):
+    """Row arg-max with the tie rule of cuda/inference/main.cu:243-251."""
+    x = _f32_cuda(x, "x")
+    B, n = x.shape
+    out = torch.empty(B, device=x.device, dtype=torch.int32)
+    _lib.init(x.device.index or 0)
+    check(_lib.lib().rnb_argmax_forward(_ptr(x), _ptr(out), B, n, _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------- fused tensor-core ops
+def conv_bn_act_forward(x, weight, bn=None, residual=None, relu=True, stride=1, padding=0,
+                        dtype="bf16"):
+    """conv -> bn -> (+residual) -> relu in one tcgen05 launch (layerForward, main.cu:138-163).
+    `bn` is (weight, bias, running_mean, running_var) or None."""
+    x, weight = _f32_cuda(x, "x"), _f32_cuda(weight, "weight")
+    B, Cin, H, W = x.shape
+    Cout, _, k, _ = weight.shape
+    out = torch.empty(B, Cout, conv_out(H, k, stride, padding), conv_out(W, k, stride, padding),
+                      device=x.device, dtype=torch.float32)
+    bnp = [None] * 4 if bn is None else [_f32_cuda(t, "bn") for t in bn]
+    res = None if residual is None else _f32_cuda(residual, "residual")
+    _lib.init(x.device.index or 0)
+    check(_lib.lib().rnb_conv_bn_act_forward(_ptr(x), _ptr(weight), _ptr(bnp[0]), _ptr(bnp[1]),
+                                             _ptr(bnp[2]), _ptr(bnp[3]), _ptr(res), _ptr(out), B, Cin, H,
+                                             W, Cout, k, stride, padding, int(bool(relu)),
+                                             DTYPES[dtype], _stream()))
+    return out
+
+
+def stem_forward(x, weight, bn=None, dtype="bf16"):
+    """conv 7x7/2 + bn + relu + maxpool 3x3/2 (main.cu:176-192)."""
+    x, weight = _f32_cuda(x, "x"), _f32_cuda(weight, "weight")
+    B, _, H, W = x.shape
+    oh, ow = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
+    out = torch.empty(B, 64, conv_out(oh, 3, 2, 1), conv_out(ow, 3, 2, 1), device=x.device,
+                      dtype=torch.float32)
+    bnp = [None] * 4 if bn is None else [_f32_cuda(t, "bn") for t in bn]
+    _lib.init(x.device.index or 0)
+    check(_lib.lib().rnb_stem_forward(_ptr(x), _ptr(weight), _ptr(bnp[0]), _ptr(bnp[1]), _ptr(bnp[2]),
+                                      _ptr(bnp[3]), _ptr(out), B, H, W, DTYPES[dtype], _stream()))
+    return out
+
+
+def tail_forward(x, fc_weight, fc_bias):
+    """avgpool + fc + arg-max (main.cu:213-224, 243-251). x is [B,C,h,w] fp32."""
+    x = _f32_cuda(x, "x")
+    B, Cc, H, W = x.shape
+    classes = fc_weight.shape[0]
+    logits = torch.empty(B, classes, device=x.device, dtype=torch.float32)
+    top1 = torch.empty(B, device=x.device, dtype=torch.int32)
+    _lib.init(x.device.index or 0)
+    check(_lib.lib().rnb_tail_forward(_ptr(x), _ptr(_f32_cuda(fc_weight, "fc_weight")),
+                                      _ptr(_f32_cuda(fc_bias, "fc_bias")), _ptr(logits), _ptr(top1), B,
+                                      Cc, H * W, classes, _stream()))
+    return logits, top1
+
+
+# --------------------------------------------------------------------------- whole model
+class ResNet:
+    """Planned engine over a save_weights.py-format directory (ResnetModel, main.cu:91-125)."""
+
+    def __init__(self, arch: str, weights_dir, dtype: str = "bf16", max_batch: int = 256,
+                 chunk: int = 0, device: int = 0):
+        _lib.init(device)
+        self.arch, self.dtype, self.max_batch, self.device = arch, dtype, max_batch, device
+        handle = C.c_void_p()
+        check(_lib.lib().rnb_model_create(arch.encode(), DTYPES[dtype], str(weights_dir).encode(),
+                                          max_batch, chunk, C.byref(handle)))
+        self._h = handle
+        self.num_classes = _lib.lib().rnb_model_num_classes(self._h)
+        self.flops_per_image = _lib.lib().rnb_model_flops_per_image(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().rnb_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launches_per_forward(self, batch: int) -> int:
+        return _lib.lib().rnb_model_launches_per_forward(self._h, batch)
+
+    def forward(self, x: torch.Tensor, logits=None, top1=None):
+        """x: [B,3,224,224] fp32 CUDA tensor -> (logits [B,classes] fp32, top1 [B] int32)."""
+        x = _f32_cuda(x, "x")
+        B = x.shape[0]
+        if logits is None:
+            logits = torch.empty(B, self.num_classes, device=x.device, dtype=torch.float32)
+        if top1 is None:
+            top1 = torch.empty(B, device=x.device, dtype=torch.int32)
+        check(_lib.lib().rnb_model_forward(self._h, _ptr(x), B, _ptr(logits), _ptr(top1), _stream()))
+        return logits, top1
+
+    def forward_host(self, x: torch.Tensor, logits=None, top1=None):
+        """x: [B,3,224,224] fp32 HOST tensor (pinned for full PCIe speed) -> host logits / top1.
+        Host->device copy, compute and device->host copy all happen inside the call."""
+        if x.is_cuda or x.dtype != torch.float32:
+            raise RnbError("forward_host takes a float32 host tensor")
+        x = x.contiguous()
+        B = x.shape[0]
+        if logits is None:
+            logits = torch.empty(B, self.num_classes, dtype=torch.float32).pin_memory()
+        if top1 is None:
+            top1 = torch.empty(B, dtype=torch.int32).pin_memory()
+        check(_lib.lib().rnb_model_forward_host(self._h, _ptr(x), B, _ptr(logits), _ptr(top1)))
+        return logits, top1
+
+    def activation(self, name: str) -> torch.Tensor:
+        """Intermediate activation of the last forward (first chunk) as fp32 NCHW (flat)."""
+        n = C.c_int64()
+        check(_lib.lib().rnb_model_get_activation(self._h, name.encode(), None, C.byref(n), _stream()))
+        out = torch.empty(n.value, device=f"cuda:{self.device}", dtype=torch.float32)
+        check(_lib.lib().rnb_model_get_activation(self._h, name.encode(), _ptr(out), C.byref(n), _stream()))
+        return out
