@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Headline benchmark: ResNet inference images/sec on B200 (BASELINE.json `metric`).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a engine
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1: one rank per GPU)
+
+A "step" is one forward pass over the per-GPU batch (default: ResNet-50, BF16, 256 images of
+synthetic 224x224 input — BASELINE.json configs[2]); with N > 1 every rank runs a full replica on
+its own 256 images (weak scaling) and the step ends with ONE NCCL all-gather of logits + top-1
+(north_star). Rank 0 prints exactly one JSON line.
+
+  value     images/s, whole job, inputs already resident in HBM, CUDA-graph replay, device-timed
+  e2e       images/s through rnb_model_forward_host(): pinned HOST input -> H2D -> forward -> D2H of
+            logits/top-1, everything inside the timed region
+  roofline  the dominant kernel (conv_igemm_kernel, every tensor-core conv launch of a step):
+            algorithmic FLOPs / CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline  the oracle (PyTorch restatement of the reference's pytorch_inference.py) on the
+            host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return d, "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_throughput(arch: str, sample_batch: int, iters: int, warmup: int = 1):
+    """images/s of the oracle (CPU restatement of the reference's PyTorch path) with all host threads."""
+    import torch
+
+    from oracle import torch_model
+    from resnet_c_b200 import weights
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = weights.make_state_dict(arch, 0)
+    model = torch_model.build(arch, sd)
+    x = weights.synthetic_images(sample_batch)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + iters):
+            t0 = time.perf_counter()
+            model(x)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    med = statistics.median(times)
+    return sample_batch / med, cores, med
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path, on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample = args.cpu_sample
+    # bound the whole run to a few minutes whatever K is
+    value, cores, med = cpu_oracle_throughput(args.arch, sample, max(1, min(args.steps, 10)),
+                                              max(1, min(args.warmup, 2)))
+    unit = "images/s"
+    line = {
+        "impl": "reference",
+        "metric": f"{args.arch} inference throughput (CPU oracle)",
+        "value": value, "unit": unit, "n_gpus": args.gpus, "steps": max(1, min(args.steps, 10)),
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": med * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.arch} fp32 inference, {sample}-image sample of the "
+                               f"batch-{args.batch} synthetic 224x224 workload, CPU",
+                   "per_gpu_batch": args.batch},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": f"{sample} images per step (PyTorch restatement of "
+                                   f"pytorch_inference.py, torch.set_num_threads({cores}))"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--arch", default="resnet50")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--chunk", type=int, default=0, help="images pushed through the net at a time (0 = default)")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default="", help="write the per-launch table (JSON) here")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    from resnet_c_b200 import engine, weights
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the native arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = args.batch
+    wdir = weights.cached_weights_dir(args.arch, 0, root=f"/tmp/rnb_cache_rank{local_rank}" if world > 1 else None)
+    model = engine.ResNet(args.arch, wdir, dtype=args.dtype, max_batch=B, chunk=args.chunk, device=local_rank)
+    classes = model.num_classes
+    dev = torch.device("cuda", local_rank)
+    # every rank gets its own slice of the global synthetic batch
+    x = weights.synthetic_images(B, seed=1234 + rank).to(dev)
+    logits = torch.empty(B, classes, device=dev, dtype=torch.float32)
+    top1 = torch.empty(B, device=dev, dtype=torch.int32)
+    if world > 1:
+        all_logits = torch.empty(world * B, classes, device=dev, dtype=torch.float32)
+        all_top1 = torch.empty(world * B, device=dev, dtype=torch.int32)
+
+    def step():
+        model.forward(x, logits, top1)
+        if world > 1:
+            dist.all_gather_into_tensor(all_logits, logits)
+            dist.all_gather_into_tensor(all_top1, top1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    ms_per_step = ms_total / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- end to end through host buffers (H2D + forward + D2H inside the timed region)
+    xh = weights.synthetic_images(B, seed=1234 + rank).pin_memory()
+    lh = torch.empty(B, classes, dtype=torch.float32).pin_memory()
+    th = torch.empty(B, dtype=torch.int32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        model.forward_host(xh, lh, th)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        model.forward_host(xh, lh, th)   # synchronous: returns with the results on the host
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / t.item()
+    same = bool((th.to(dev) == top1).all().item())
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events (no graph)
+    peaks, peak_kind = load_peaks()
+    prof = model.profile(x, iters=3)
+    chunk_n = min(B, args.chunk) if args.chunk > 0 else min(B, int(os.environ.get("RNB_CHUNK", "0") or B))
+    conv = [p for p in prof if p["kind"] == "conv_igemm"]
+    conv_ms = sum(p["ms"] for p in conv)
+    conv_flops = sum(p["flops"] for p in conv)
+    chunk_ms = sum(p["ms"] for p in prof)
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
+    if args.dtype == "tf32":
+        peak *= 0.5
+    traffic = None
+    tpath = ROOT / "profiles" / "traffic.json"
+    if tpath.exists():
+        try:
+            traffic = json.loads(tpath.read_text()).get(f"{args.arch}_{args.dtype}_b{B}")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "tensor", "kernel": "conv_igemm_kernel (all tensor-core conv launches of one step)",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+        "peak_source": f"{peak_kind} bf16_tflops_sustained" + (" x 0.5 (tf32 assumed)" if args.dtype == "tf32" else ""),
+        "traffic": traffic,
+        "kernel_share_of_step": conv_ms / chunk_ms if chunk_ms else None,
+        "whole_net_tflops": value / world * model.flops_per_image / 1e12,
+        "whole_net_frac_of_burst": value / world * model.flops_per_image / 1e12 / float(peaks.get("bf16_tflops", 1590.0)),
+    }
+    if args.profile_out and rank == 0:
+        Path(args.profile_out).write_text(json.dumps({"chunk": chunk_n, "launches": prof}, indent=1))
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, med = cpu_oracle_throughput(args.arch, args.cpu_sample, iters=3, warmup=1)
+        cpu_baseline = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": f"{args.cpu_sample} images x 3 timed passes (+1 warm-up) of the PyTorch "
+                                  f"restatement of pytorch_inference.py, {cores} threads"}
+
+    img_bytes = 3 * 224 * 224 * 4
+    line = {
+        "metric": f"{args.arch} inference images/sec @ batch {B} per GPU",
+        "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"{args.arch} {args.dtype} inference, batch {B} per GPU, synthetic 224x224 "
+                               f"fp32 NCHW input, seeded random-init weights",
+                   "global_batch": world * B, "per_gpu_batch": B, "chunk": chunk_n,
+                   "parallelism": f"dp{world} (replica per GPU, one NCCL all-gather of logits+top1 per step)"
+                   if world > 1 else "single GPU",
+                   "l2": f"input {B * img_bytes / 1e6:.0f} MB per step > 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * img_bytes,
+                "d2h_bytes_per_step": B * classes * 4 + B * 4, "steps": e2e_steps,
+                "top1_equal_to_device_path": same},
+        "gpu_launches": model.launches_per_forward(B) * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "tflops_per_gpu": value / world * model.flops_per_image / 1e12,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,260 @@
+// nn.cu — host side of the drop-in modules (reference: cuda/nn.cu:3-87). Every forward hands raw
+// device pointers to the C ABI of librnb.so (include/rnb.h), then restores the reference's calling
+// convention: synchronous on return, abort on any error.
+#include "nn.cuh"
+
+#include <cstdlib>
+#include <vector>
+
+#include "../include/rnb.h"
+
+namespace
+{
+
+// The reference aborts on every failure (helpers.cuh:13-22); keep that at the module boundary.
+void rnbCheck(int rc, const char* what)
+{
+    if (rc != RNB_OK) {
+        std::cerr << "rnb: " << what << " failed (" << rc << "): " << rnb_last_error() << "\n";
+        std::abort();
+    }
+}
+
+void ensureInit()
+{
+    static bool done = false;
+    if (!done) {
+        int device = 0;
+        gpuErrchk(cudaGetDevice(&device));
+        rnbCheck(rnb_init(device), "rnb_init");
+        done = true;
+    }
+}
+
+void syncAndCheck()
+{
+    gpuErrchk(cudaDeviceSynchronize());
+    gpuErrchk(cudaGetLastError());
+}
+
+int asInt(uint64_t v)
+{
+    assert(v <= 0x7fffffffULL);
+    return static_cast<int>(v);
+}
+
+bool tensorCoreEligible(const Conv2d& c)
+{
+    return (c.kernel_size == 1 || c.kernel_size == 3) && c.in_channels % 64 == 0 && c.out_channels % 64 == 0;
+}
+
+// conv -> bn -> (+residual) -> relu through the fused tcgen05 path when the shape allows it,
+// otherwise through the per-op FP32 kernels (e.g. a 3-channel input).
+void convBnAct(Conv2d& conv, BatchNorm2d& bn, FloatTensor& x, FloatTensor* residual, bool relu,
+               Precision precision, FloatTensor& out)
+{
+    const auto [B, C, H, W] = x.shape().as_tuple<4>();
+    if (tensorCoreEligible(conv)) {
+        rnbCheck(rnb_conv_bn_act_forward(x.data(), conv.weight.data(), bn.weight.data(), bn.bias.data(),
+                                         bn.mean.data(), bn.var.data(), residual ? residual->data() : nullptr,
+                                         out.data(), asInt(B), asInt(C), asInt(H), asInt(W),
+                                         asInt(conv.out_channels), asInt(conv.kernel_size), asInt(conv.stride),
+                                         asInt(conv.padding), relu ? 1 : 0, static_cast<int>(precision),
+                                         nullptr),
+                 "rnb_conv_bn_act_forward");
+        syncAndCheck();
+        return;
+    }
+    conv.forward(x, out);
+    bn.forward(out, out);
+    if (residual) {
+        addForward(out, *residual, out);
+    }
+    if (relu) {
+        reluForward(out, out);
+    }
+}
+
+std::optional<std::pair<Conv2d, BatchNorm2d>> loadDownsample(const std::string& prefix, uint64_t in_channels,
+                                                             uint64_t out_channels, uint64_t stride,
+                                                             bool with_downsample)
+{
+    std::optional<std::pair<Conv2d, BatchNorm2d>> ds;
+    if (with_downsample) {
+        ds.emplace(Conv2d::loadWeightToCuda(prefix + "downsample.0", in_channels, out_channels, 1, stride),
+                   BatchNorm2d::loadWeightToCuda(prefix + "downsample.1", out_channels));
+    }
+    return ds;
+}
+
+}  // namespace
+
+void Conv2d::forward(FloatTensor& x, FloatTensor& out)
+{
+    ensureInit();
+    const auto [B, C, H, W] = x.shape().as_tuple<4>();
+    assert(C == in_channels);
+    assert(out.shape() == getOutShape(x.shape()));
+    rnbCheck(rnb_conv2d_forward(x.data(), out.data(), weight.data(), asInt(B), asInt(C), asInt(H), asInt(W),
+                                asInt(out_channels), asInt(kernel_size), asInt(stride), asInt(padding),
+                                nullptr),
+             "rnb_conv2d_forward");
+    syncAndCheck();
+}
+
+void BatchNorm2d::forward(FloatTensor& x, FloatTensor& out)
+{
+    ensureInit();
+    const auto [B, C, H, W] = x.shape().as_tuple<4>();
+    assert(C == channels_num);
+    rnbCheck(rnb_batchnorm2d_forward(x.data(), out.data(), weight.data(), bias.data(), mean.data(), var.data(),
+                                     asInt(B), asInt(C), asInt(H * W), nullptr),
+             "rnb_batchnorm2d_forward");
+    syncAndCheck();
+}
+
+void Pool2d::maxforward(FloatTensor& x, FloatTensor& out)
+{
+    ensureInit();
+    const auto [B, C, H, W] = x.shape().as_tuple<4>();
+    rnbCheck(rnb_maxpool2d_forward(x.data(), out.data(), asInt(B), asInt(C), asInt(H), asInt(W),
+                                   asInt(kernel_size), asInt(stride), asInt(padding), nullptr),
+             "rnb_maxpool2d_forward");
+    syncAndCheck();
+}
+
+void Pool2d::avgforward(FloatTensor& x, FloatTensor& out)
+{
+    ensureInit();
+    const auto [B, C, H, W] = x.shape().as_tuple<4>();
+    rnbCheck(rnb_avgpool2d_forward(x.data(), out.data(), asInt(B), asInt(C), asInt(H), asInt(W),
+                                   asInt(kernel_size), asInt(stride), asInt(padding), nullptr),
+             "rnb_avgpool2d_forward");
+    syncAndCheck();
+}
+
+void Linear::forward(FloatTensor& x, FloatTensor& out)
+{
+    ensureInit();
+    const uint64_t B = x.shape().at(0);
+    rnbCheck(rnb_linear_forward(x.data(), out.data(), weight.data(), bias.data(), asInt(B), asInt(in_features),
+                                asInt(out_features), nullptr),
+             "rnb_linear_forward");
+    syncAndCheck();
+}
+
+void reluForward(FloatTensor& x, FloatTensor& out)
+{
+    ensureInit();
+    assert(x.shape() == out.shape());
+    rnbCheck(rnb_relu_forward(x.data(), out.data(), static_cast<int64_t>(x.numel()), nullptr),
+             "rnb_relu_forward");
+    syncAndCheck();
+}
+
+void addForward(FloatTensor& a, FloatTensor& b, FloatTensor& out)
+{
+    ensureInit();
+    assert(a.shape() == b.shape());
+    assert(a.shape() == out.shape());
+    rnbCheck(rnb_add_forward(a.data(), b.data(), out.data(), static_cast<int64_t>(a.numel()), nullptr),
+             "rnb_add_forward");
+    syncAndCheck();
+}
+
+// ------------------------------------------------------------------------------------------------
+Bottleneck Bottleneck::loadWeightToCuda(std::string prefix, uint64_t in_channels, uint64_t inter_channels,
+                                        uint64_t out_channels, uint64_t stride, bool with_downsample,
+                                        Precision precision)
+{
+    return Bottleneck(Conv2d::loadWeightToCuda(prefix + "conv1", in_channels, inter_channels, 1),
+                      BatchNorm2d::loadWeightToCuda(prefix + "bn1", inter_channels),
+                      Conv2d::loadWeightToCuda(prefix + "conv2", inter_channels, inter_channels, 3, stride, 1),
+                      BatchNorm2d::loadWeightToCuda(prefix + "bn2", inter_channels),
+                      Conv2d::loadWeightToCuda(prefix + "conv3", inter_channels, out_channels, 1),
+                      BatchNorm2d::loadWeightToCuda(prefix + "bn3", out_channels),
+                      loadDownsample(prefix, in_channels, out_channels, stride, with_downsample), precision);
+}
+
+void Bottleneck::forward(FloatTensor& x, FloatTensor& out)
+{
+    ensureInit();
+    assert(out.shape() == getOutShape(x.shape()));
+    FloatTensor shortcut(Device::GPU);
+    if (downsample) {
+        shortcut = FloatTensor(downsample->first.getOutShape(x.shape()), Device::GPU);
+        convBnAct(downsample->first, downsample->second, x, nullptr, false, precision, shortcut);
+    }
+    FloatTensor t1(conv1.getOutShape(x.shape()), Device::GPU);
+    convBnAct(conv1, bn1, x, nullptr, true, precision, t1);
+    FloatTensor t2(conv2.getOutShape(t1.shape()), Device::GPU);
+    convBnAct(conv2, bn2, t1, nullptr, true, precision, t2);
+    convBnAct(conv3, bn3, t2, downsample ? &shortcut : &x, true, precision, out);
+}
+
+BasicBlock BasicBlock::loadWeightToCuda(std::string prefix, uint64_t in_channels, uint64_t out_channels,
+                                        uint64_t stride, bool with_downsample, Precision precision)
+{
+    return BasicBlock(Conv2d::loadWeightToCuda(prefix + "conv1", in_channels, out_channels, 3, stride, 1),
+                      BatchNorm2d::loadWeightToCuda(prefix + "bn1", out_channels),
+                      Conv2d::loadWeightToCuda(prefix + "conv2", out_channels, out_channels, 3, 1, 1),
+                      BatchNorm2d::loadWeightToCuda(prefix + "bn2", out_channels),
+                      loadDownsample(prefix, in_channels, out_channels, stride, with_downsample), precision);
+}
+
+void BasicBlock::forward(FloatTensor& x, FloatTensor& out)
+{
+    ensureInit();
+    assert(out.shape() == getOutShape(x.shape()));
+    FloatTensor shortcut(Device::GPU);
+    if (downsample) {
+        shortcut = FloatTensor(downsample->first.getOutShape(x.shape()), Device::GPU);
+        convBnAct(downsample->first, downsample->second, x, nullptr, false, precision, shortcut);
+    }
+    FloatTensor t1(conv1.getOutShape(x.shape()), Device::GPU);
+    convBnAct(conv1, bn1, x, nullptr, true, precision, t1);
+    convBnAct(conv2, bn2, t1, downsample ? &shortcut : &x, true, precision, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+ResNet::ResNet(const std::string& arch, Precision precision, const std::string& weights_dir,
+               uint64_t max_batch)
+    : max_batch_(max_batch)
+{
+    ensureInit();
+    rnbCheck(rnb_model_create(arch.c_str(), static_cast<int>(precision), weights_dir.c_str(), asInt(max_batch),
+                              0, &handle_),
+             "rnb_model_create");
+}
+
+ResNet::~ResNet()
+{
+    rnb_model_destroy(handle_);
+}
+
+uint64_t ResNet::numClasses() const
+{
+    return static_cast<uint64_t>(rnb_model_num_classes(handle_));
+}
+
+void ResNet::forward(FloatTensor& x, FloatTensor& logits)
+{
+    assert(x.device == Device::GPU && logits.device == Device::GPU);
+    assert(logits.shape() == getOutShape(x.shape()));
+    rnbCheck(rnb_model_forward(handle_, x.data(), asInt(x.shape().at(0)), logits.data(), nullptr, nullptr),
+             "rnb_model_forward");
+    syncAndCheck();
+}
+
+std::vector<int32_t> ResNet::predict(FloatTensor& x, FloatTensor& logits)
+{
+    const uint64_t B = x.shape().at(0);
+    int32_t* top1_dev = static_cast<int32_t*>(safeCudaMalloc(B * sizeof(int32_t)));
+    rnbCheck(rnb_model_forward(handle_, x.data(), asInt(B), logits.data(), top1_dev, nullptr),
+             "rnb_model_forward");
+    syncAndCheck();
+    std::vector<int32_t> top1(B);
+    gpuErrchk(cudaMemcpy(top1.data(), top1_dev, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    gpuErrchk(cudaFree(top1_dev));
+    return top1;
+}

@@ -79,6 +79,15 @@ int rnb_model_num_convs(const rnb_model_t* m);
 int rnb_model_launches_per_forward(rnb_model_t* m, int batch);
 /* Algorithmic FLOPs per image: 2*MAC over convs + fc. */
 double rnb_model_flops_per_image(const rnb_model_t* m);
+/* Per-launch device timing of one chunk of min(batch, chunk) images, launched WITHOUT the graph and
+ * with a CUDA event between consecutive launches on `stream` (average over `iters` passes, after one
+ * warm-up pass). For launch i: kind_out[i] (0 stem conv, 1 max-pool, 2 tcgen05 conv, 3 avg-pool,
+ * 4 fc, 5 arg-max), ms_out[i], flops_out[i] (algorithmic 2*MAC, 0 for pools/arg-max) and
+ * bytes_out[i] (algorithmic HBM bytes: operands read once + result written once). Arrays hold
+ * `max_entries`; the count is returned through *n_entries. Synchronises the stream. */
+int rnb_model_profile(rnb_model_t* m, const float* x_dev, int batch, int iters, int* kind_out,
+                      float* ms_out, double* flops_out, double* bytes_out, int max_entries,
+                      int* n_entries, void* stream);
 /* Copy an intermediate activation of the LAST forward (chunk 0) to `out_dev` as float32 NCHW.
  * `name` is "stem" | "maxpool" | "layer{L}.{i}" (block output) | "avgpool". Returns the element
  * count through *numel (call with out_dev = NULL to query). Debug / parity use only. */

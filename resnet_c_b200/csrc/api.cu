@@ -137,6 +137,17 @@ int rnb_model_launches_per_forward(rnb_model_t* m, int batch) {
 }
 double rnb_model_flops_per_image(const rnb_model_t* m) { return m ? m->impl.flops_per_image : 0.0; }
 
+int rnb_model_profile(rnb_model_t* m, const float* x_dev, int batch, int iters, int* kind_out,
+                      float* ms_out, double* flops_out, double* bytes_out, int max_entries,
+                      int* n_entries, void* stream) {
+    if (!m || !kind_out || !ms_out || !flops_out || !bytes_out) {
+        set_error("rnb_model_profile: NULL argument");
+        return RNB_ERR_INVALID;
+    }
+    return m->impl.profile(x_dev, batch, iters, kind_out, ms_out, flops_out, bytes_out, max_entries,
+                           n_entries, static_cast<cudaStream_t>(stream));
+}
+
 int rnb_model_get_activation(rnb_model_t* m, const char* name, float* out_dev, int64_t* numel,
                              void* stream) {
     if (!m || !name) {

@@ -77,6 +77,8 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     const int tiles = g.m_tiles * g.n_tiles;
     plan->grid = tiles < num_sms ? tiles : num_sms;
     plan->flops = 2.0 * static_cast<double>(M) * d.Cout * (1.0 * d.ksize * d.ksize * d.Cin);
+    plan->bytes = 1.0 * d.B * d.H * d.W * d.Cin * esz + 1.0 * d.Cout * d.ksize * d.ksize * d.Cin * esz +
+                  4.0 * d.Cout + (d.residual ? 2.0 : 1.0) * static_cast<double>(M) * d.Cout * esz;
 
     const TmDtype dt = d.act == ActType::BF16 ? TmDtype::BF16 : TmDtype::F32;
     int r;

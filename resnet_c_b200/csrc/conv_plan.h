@@ -28,6 +28,7 @@ struct ConvPlan {
     int esz;      // element bytes
     int grid;     // persistent CTAs
     double flops;  // 2*M*N*K
+    double bytes;  // algorithmic HBM bytes: input + weights + bias (+ residual) read once, output written once
 };
 
 // Builds the tensor maps and tile geometry. Returns 0 on success; on failure writes a message to

@@ -424,6 +424,73 @@ int Model::forward(const float* x, int batch, float* logits, int32_t* top1, cuda
     return RNB_OK;
 }
 
+int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, double* flops,
+                   double* bytes, int max_entries, int* n_entries, cudaStream_t s) {
+    if (batch <= 0 || batch > max_batch || iters <= 0 || !x || !n_entries) {
+        set_error("profile: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    const int n = std::min(chunk, batch);
+    ChunkPlan* pp = plan_for(n);
+    if (!pp) return RNB_ERR_CUDA;
+    ChunkPlan& p = *pp;
+    const int L = launches_per_chunk();
+    *n_entries = L;
+    if (max_entries < L) {
+        set_error("profile: output arrays too small");
+        return RNB_ERR_INVALID;
+    }
+    if (!scratch_logits)
+        RNB_CUDA(cudaMalloc(&scratch_logits, 1ull * max_batch * classes * sizeof(float)));
+    if (!host_top1_dev) RNB_CUDA(cudaMalloc(&host_top1_dev, 1ull * max_batch * sizeof(int32_t)));
+    std::vector<cudaEvent_t> ev(L + 1);
+    for (auto& e : ev) RNB_CUDA(cudaEventCreate(&e));
+    std::vector<double> acc(L, 0.0);
+    const int s_hw = (6 + image - 7) / 2 + 1, p_hw = (2 + s_hw - 3) / 2 + 1;
+    for (int it = -1; it < iters; ++it) {
+        int i = 0;
+        RNB_CUDA(cudaEventRecord(ev[i], s));
+        RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
+        RNB_CUDA(cudaEventRecord(ev[++i], s));
+        RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
+        RNB_CUDA(cudaEventRecord(ev[++i], s));
+        for (const ConvPlan& cp : p.convs) {
+            RNB_CUDA(conv_plan_launch(cp, s));
+            RNB_CUDA(cudaEventRecord(ev[++i], s));
+        }
+        RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, n, p.last_hw, p.last_c, esz, s));
+        RNB_CUDA(cudaEventRecord(ev[++i], s));
+        RNB_CUDA(launch_fc(p.pooled, fc_w, fc_b, scratch_logits, n, p.last_c, classes, s));
+        RNB_CUDA(cudaEventRecord(ev[++i], s));
+        RNB_CUDA(launch_argmax_f32(scratch_logits, host_top1_dev, n, classes, s));
+        RNB_CUDA(cudaEventRecord(ev[++i], s));
+        RNB_CUDA(cudaStreamSynchronize(s));
+        if (it < 0) continue;  // warm-up pass
+        for (int k = 0; k < L; ++k) {
+            float t = 0.f;
+            RNB_CUDA(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
+            acc[k] += t;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    int i = 0;
+    auto put = [&](int k, double f, double b) {
+        kind[i] = k;
+        ms[i] = static_cast<float>(acc[i] / iters);
+        flops[i] = f;
+        bytes[i] = b;
+        ++i;
+    };
+    const double img_px = 1.0 * image * image;
+    put(0, 2.0 * n * 64 * 147 * s_hw * s_hw, n * (3.0 * img_px * 4 + 64.0 * s_hw * s_hw * esz) + 64 * 148 * 4.0);
+    put(1, 0.0, n * 64.0 * esz * (1.0 * s_hw * s_hw + 1.0 * p_hw * p_hw));
+    for (const ConvPlan& cp : p.convs) put(2, cp.flops, cp.bytes);
+    put(3, 0.0, 1.0 * n * p.last_c * (1.0 * p.last_hw * esz + 4.0));
+    put(4, 2.0 * n * p.last_c * classes, 4.0 * (1.0 * n * p.last_c + 1.0 * classes * p.last_c + 1.0 * n * classes));
+    put(5, 0.0, 4.0 * n * (classes + 1.0));
+    return RNB_OK;
+}
+
 int Model::forward_host(const float* x, int batch, float* logits, int32_t* top1) {
     if (batch <= 0 || batch > max_batch) {
         set_error("batch must be in [1, max_batch]");

@@ -100,6 +100,8 @@ struct Model {
     int enqueue_chunk(ChunkPlan& p, const float* x, float* logits, int32_t* top1, cudaStream_t s);
     int forward(const float* x, int batch, float* logits, int32_t* top1, cudaStream_t s);
     int forward_host(const float* x, int batch, float* logits, int32_t* top1);
+    int profile(const float* x, int batch, int iters, int* kind, float* ms, double* flops,
+                double* bytes, int max_entries, int* n_entries, cudaStream_t s);
     // stem conv + max-pool + (num_convs - 1) tensor-core convs + avg-pool + fc + arg-max
     int launches_per_chunk() const { return num_convs + 4; }
 };

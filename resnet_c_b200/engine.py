@@ -226,6 +226,22 @@ class ResNet:
         check(_lib.lib().rnb_model_forward_host(self._h, _ptr(x), B, _ptr(logits), _ptr(top1)))
         return logits, top1
 
+    KINDS = ("stem_conv", "maxpool", "conv_igemm", "avgpool", "fc", "argmax")
+
+    def profile(self, x: torch.Tensor, iters: int = 3):
+        """Per-launch device times of one chunk: list of dicts(kind, ms, flops, bytes)."""
+        x = _f32_cuda(x, "x")
+        cap = 1024
+        kind = (C.c_int * cap)()
+        ms = (C.c_float * cap)()
+        flops = (C.c_double * cap)()
+        nbytes = (C.c_double * cap)()
+        n = C.c_int()
+        check(_lib.lib().rnb_model_profile(self._h, _ptr(x), x.shape[0], iters, kind, ms, flops, nbytes,
+                                           cap, C.byref(n), _stream()))
+        return [dict(kind=self.KINDS[kind[i]], ms=ms[i], flops=flops[i], bytes=nbytes[i])
+                for i in range(n.value)]
+
     def activation(self, name: str) -> torch.Tensor:
         """Intermediate activation of the last forward (first chunk) as fp32 NCHW (flat)."""
         n = C.c_int64()

@@ -1,0 +1,124 @@
+"""-m gpu: the tcgen05 implicit-GEMM convolution (conv + folded BN + residual + ReLU in one launch)
+against the plain-C oracle running the reference's unfused chain conv2d -> batchnorm -> add -> relu
+(layerForward, cuda/inference/main.cu:138-163), on every distinct layer shape of ResNet-18/50/152
+ at small batch.
+
+Tolerance = BASELINE.json north_star, applied per layer: max|d| / max|y| <= 2e-2 (BF16 operands,
+FP32 accumulate) and <= 1e-3 (TF32, round-to-nearest operands, FP32 accumulate)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"bf16": 2e-2, "tf32": 1e-3}
+
+# (Cin, Cout, H, k, stride, pad, residual, relu, B)
+BOTTLENECK_SHAPES = [
+    (64, 64, 56, 1, 1, 0, False, True, 1),
+    (64, 64, 56, 3, 1, 1, False, True, 1),
+    (64, 256, 56, 1, 1, 0, True, True, 1),      # conv3 + identity shortcut
+    (64, 256, 56, 1, 1, 0, False, False, 1),    # layer1.0 downsample
+    (256, 64, 56, 1, 1, 0, False, True, 1),
+    (256, 128, 56, 1, 1, 0, False, True, 1),
+    (128, 128, 56, 3, 2, 1, False, True, 2),
+    (128, 512, 28, 1, 1, 0, True, True, 2),
+    (256, 512, 56, 1, 2, 0, False, False, 2),   # strided downsample
+    (512, 128, 28, 1, 1, 0, False, True, 2),
+    (128, 128, 28, 3, 1, 1, False, True, 2),
+    (512, 256, 28, 1, 1, 0, False, True, 2),
+    (256, 256, 28, 3, 2, 1, False, True, 3),
+    (256, 1024, 14, 1, 1, 0, True, True, 3),
+    (512, 1024, 28, 1, 2, 0, False, False, 3),
+    (1024, 256, 14, 1, 1, 0, False, True, 3),
+    (256, 256, 14, 3, 1, 1, False, True, 3),
+    (1024, 512, 14, 1, 1, 0, False, True, 3),
+    (512, 512, 14, 3, 2, 1, False, True, 3),
+    (512, 2048, 7, 1, 1, 0, True, True, 3),
+    (1024, 2048, 14, 1, 2, 0, False, False, 3),
+    (2048, 512, 7, 1, 1, 0, False, True, 3),
+    (512, 512, 7, 3, 1, 1, False, True, 3),
+]
+BASIC_SHAPES = [
+    (64, 64, 56, 3, 1, 1, True, True, 1),       # BasicBlock conv2 + identity shortcut
+    (64, 128, 56, 3, 2, 1, False, True, 2),
+    (128, 128, 28, 3, 1, 1, True, True, 2),
+    (64, 128, 56, 1, 2, 0, False, False, 2),
+    (128, 256, 28, 3, 2, 1, False, True, 3),
+    (256, 256, 14, 3, 1, 1, True, True, 3),
+    (128, 256, 28, 1, 2, 0, False, False, 3),
+    (256, 512, 14, 3, 2, 1, False, True, 3),
+    (512, 512, 7, 3, 1, 1, True, True, 3),
+    (256, 512, 14, 1, 2, 0, False, False, 3),
+]
+
+
+def _case(oracle_lib, Cin, Cout, H, k, stride, pad, residual, relu, B, dtype, seed):
+    from resnet_c_b200 import engine
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cin, H, H, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+    bn = (torch.rand(Cout, generator=g) * 0.5 + 0.75, torch.randn(Cout, generator=g) * 0.1,
+          torch.randn(Cout, generator=g) * 0.1, torch.rand(Cout, generator=g) * 0.5 + 0.75)
+    OH = (2 * pad + H - k) // stride + 1
+    res = torch.randn(B, Cout, OH, OH, generator=g) if residual else None
+    y = oracle_lib.batchnorm2d(oracle_lib.conv2d(x, w, stride, pad), *bn)
+    if residual:
+        y = oracle_lib.add(y, res)
+    if relu:
+        y = oracle_lib.relu(y)
+    got = engine.conv_bn_act_forward(x.cuda(), w.cuda(), tuple(t.cuda() for t in bn),
+                                     None if res is None else res.cuda(), relu, stride, pad, dtype)
+    return rel_err(got.cpu().numpy().reshape(B, -1), y.reshape(B, -1))
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+@pytest.mark.parametrize("shape", BOTTLENECK_SHAPES, ids=lambda s: "x".join(map(str, s[:6])))
+def test_bottleneck_layer_shapes(oracle_lib, shape, dtype):
+    e = _case(oracle_lib, *shape, dtype, seed=hash(shape) % 1000)
+    assert e < TOL[dtype], f"{shape} {dtype}: rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+@pytest.mark.parametrize("shape", BASIC_SHAPES, ids=lambda s: "x".join(map(str, s[:6])))
+def test_basicblock_layer_shapes(oracle_lib, shape, dtype):
+    e = _case(oracle_lib, *shape, dtype, seed=hash(shape) % 1000)
+    assert e < TOL[dtype], f"{shape} {dtype}: rel err {e:.3e}"
+
+
+def test_no_bn_no_relu_plain_conv(oracle_lib):
+    from resnet_c_b200 import engine
+    g = torch.Generator().manual_seed(3)
+    x, w = torch.randn(2, 64, 10, 10, generator=g), torch.randn(128, 64, 3, 3, generator=g) * 0.05
+    got = engine.conv_bn_act_forward(x.cuda(), w.cuda(), None, None, False, 1, 1, "tf32")
+    assert rel_err(got.cpu().numpy().reshape(2, -1), oracle_lib.conv2d(x, w, 1, 1).reshape(2, -1)) < 1e-3
+
+
+def test_linearity_at_full_size():
+    """Size-independent property at the BASELINE batch (256 x 56 x 56 x 64 -> 256): with bias-free,
+    ReLU-free conv, f(2x) == 2 f(x) exactly (power-of-two scaling commutes with every rounding), and
+    f(0) == 0."""
+    from resnet_c_b200 import engine
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(256, 64, 56, 56, generator=g).cuda()
+    w = (torch.randn(256, 64, 1, 1, generator=g) * 0.1).cuda()
+    y1 = engine.conv_bn_act_forward(x, w, None, None, False, 1, 0, "bf16")
+    y2 = engine.conv_bn_act_forward(x * 2, w, None, None, False, 1, 0, "bf16")
+    assert torch.equal(y2, y1 * 2)
+    y0 = engine.conv_bn_act_forward(torch.zeros_like(x), w, None, None, False, 1, 0, "bf16")
+    assert float(y0.abs().max()) == 0.0
+
+
+def test_batch_rows_are_independent():
+    """Tile boundaries must not leak between images: the first image of a batch of 5 equals the same
+    image run alone, bit for bit (3x3 pad 1, 14x14: 196 pixels per image straddle the 128-row tiles)."""
+    from resnet_c_b200 import engine
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(5, 128, 14, 14, generator=g).cuda()
+    w = (torch.randn(128, 128, 3, 3, generator=g) * 0.03).cuda()
+    full = engine.conv_bn_act_forward(x, w, None, None, True, 1, 1, "bf16")
+    for i in (0, 2, 4):
+        one = engine.conv_bn_act_forward(x[i:i + 1].contiguous(), w, None, None, True, 1, 1, "bf16")
+        assert torch.equal(full[i:i + 1], one)

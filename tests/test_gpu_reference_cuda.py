@@ -1,0 +1,132 @@
+"""-m gpu: second opinion from the reference's OWN CUDA build (oracle/_ref, compiled from
+/root/reference/cuda/{ops.cu,nn.cu,inference/main.cu} in the build container; the binaries travel to
+the GPU box, the sources do not).
+
+  * libref_cuda.so  : the reference modules on the GPU  vs  the C oracle  vs  our per-op entry points
+  * cuda_inference_out (unmodified main.cu, reference headers/kernels)
+    vs  ref_main_dropin (the SAME unmodified main.cu compiled against OUR cuda/*.cuh + librnb.so)
+    vs  resnet_infer (our whole-model driver)  vs  the golden top-1 of the reference's PyTorch class.
+"""
+import ctypes as C
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_golden
+
+pytestmark = pytest.mark.gpu
+
+REF_LIB = ROOT / "oracle" / "_ref" / "libref_cuda.so"
+REF_BIN = ROOT / "oracle" / "_ref" / "cuda_inference_out"
+DROPIN_BIN = ROOT / "build" / "ref_main_dropin"
+INFER_BIN = ROOT / "build" / "resnet_infer"
+
+_fp = C.POINTER(C.c_float)
+_u64 = C.c_uint64
+
+
+def _p(a):
+    return a.ctypes.data_as(_fp)
+
+
+@pytest.fixture(scope="module")
+def refcuda():
+    if not REF_LIB.exists():
+        pytest.skip("oracle/_ref/libref_cuda.so not built (reference tree was not mounted at build time)")
+    h = C.CDLL(str(REF_LIB))
+    h.refcuda_conv2d.argtypes = [_fp, _fp, _fp] + [_u64] * 8
+    h.refcuda_batchnorm2d.argtypes = [_fp] * 6 + [_u64] * 4
+    h.refcuda_relu.argtypes = [_fp, _fp, _u64]
+    h.refcuda_add.argtypes = [_fp, _fp, _fp, _u64]
+    h.refcuda_pool2d.argtypes = [C.c_int, _fp, _fp] + [_u64] * 7
+    h.refcuda_linear.argtypes = [_fp] * 4 + [_u64] * 3
+    return h
+
+
+def _rand(*shape, seed=0):
+    return np.random.default_rng(seed).standard_normal(shape).astype(np.float32)
+
+
+def test_reference_cuda_conv_equals_oracle_and_ours(refcuda, oracle_lib):
+    from resnet_c_b200 import engine
+    for (B, Cin, H, W, Cout, k, s, p) in [(2, 8, 9, 11, 4, 3, 1, 1), (1, 3, 32, 32, 16, 7, 2, 3), (1, 64, 14, 14, 32, 1, 2, 0)]:
+        x, w = _rand(B, Cin, H, W, seed=1), _rand(Cout, Cin, k, k, seed=2)
+        ref_cpu = oracle_lib.conv2d(x, w, s, p)
+        out = np.empty_like(ref_cpu)
+        refcuda.refcuda_conv2d(_p(x), _p(w), _p(out), B, Cin, H, W, Cout, k, s, p)
+        np.testing.assert_array_equal(out, ref_cpu)  # the C restatement is bit-exact vs the reference kernel
+        ours = engine.conv2d_forward(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), s, p)
+        np.testing.assert_array_equal(ours.cpu().numpy(), out)
+
+
+def test_reference_cuda_elementwise_pool_linear(refcuda, oracle_lib):
+    x = _rand(2, 6, 9, 7, seed=3)
+    w, b, m = _rand(6, seed=4), _rand(6, seed=5), _rand(6, seed=6)
+    v = np.random.default_rng(7).random(6).astype(np.float32) + 0.5
+    out = np.empty_like(x)
+    refcuda.refcuda_batchnorm2d(_p(x), _p(w), _p(b), _p(m), _p(v), _p(out), 2, 6, 9, 7)
+    np.testing.assert_array_equal(out, oracle_lib.batchnorm2d(x, w, b, m, v))
+    flat = x.reshape(-1)
+    out1 = np.empty_like(flat)
+    refcuda.refcuda_relu(_p(flat), _p(out1), flat.size)
+    np.testing.assert_array_equal(out1, oracle_lib.relu(flat))
+    other = _rand(flat.size, seed=8)
+    refcuda.refcuda_add(_p(flat), _p(other), _p(out1), flat.size)
+    np.testing.assert_array_equal(out1, oracle_lib.add(flat, other))
+    for is_max, fn in ((1, oracle_lib.maxpool2d), (0, oracle_lib.avgpool2d)):
+        ref = fn(x, 3, 2, 1)
+        outp = np.empty_like(ref)
+        refcuda.refcuda_pool2d(is_max, _p(x), _p(outp), 2, 6, 9, 7, 3, 2, 1)
+        np.testing.assert_array_equal(outp, ref)
+    xl, wl, bl = _rand(3, 64, seed=9), _rand(10, 64, seed=10), _rand(10, seed=11)
+    outl = np.empty((3, 10), np.float32)
+    refcuda.refcuda_linear(_p(xl), _p(wl), _p(bl), _p(outl), 3, 64, 10)
+    np.testing.assert_array_equal(outl, oracle_lib.linear(xl, wl, bl))
+
+
+@pytest.fixture(scope="module")
+def r152_workdir(tmp_path_factory):
+    """CWD laid out the way main.cu expects: weights_bin/<key> and test_bins/<image>.bin."""
+    from resnet_c_b200 import weights
+    d = tmp_path_factory.mktemp("r152")
+    wdir = weights.cached_weights_dir("resnet152", 0)
+    (d / "weights_bin").symlink_to(wdir)
+    (d / "test_bins").mkdir()
+    (d / "test_bins" / "ILSVRC2012_val_00004749.bin").symlink_to(GOLDEN / "ILSVRC2012_val_00004749.bin")
+    return d
+
+
+def _max_index(stdout):
+    return [int(m) for m in re.findall(r"max index is (\d+)", stdout)]
+
+
+def test_unmodified_reference_main_on_our_headers(r152_workdir):
+    """Acceptance test of the drop-in boundary."""
+    if not DROPIN_BIN.exists():
+        pytest.skip("build/ref_main_dropin not built (reference tree was not mounted at build time)")
+    expect = load_golden("ref_class_resnet152")["top1"].tolist()
+    r = subprocess.run([str(DROPIN_BIN)], cwd=r152_workdir, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert _max_index(r.stdout) == expect == [176]
+
+
+def test_reference_binary_agrees(r152_workdir):
+    if not REF_BIN.exists():
+        pytest.skip("oracle/_ref/cuda_inference_out not built")
+    expect = load_golden("ref_class_resnet152")["top1"].tolist()
+    r = subprocess.run([str(REF_BIN)], cwd=r152_workdir, capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert _max_index(r.stdout) == expect
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+def test_whole_model_driver(r152_workdir, dtype):
+    assert INFER_BIN.exists(), "build/resnet_infer missing: run python -m resnet_c_b200.build dropin"
+    expect = load_golden("ref_class_resnet152")["top1"].tolist()
+    r = subprocess.run([str(INFER_BIN), "resnet152", dtype, "3"], cwd=r152_workdir, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert _max_index(r.stdout) == expect * 3

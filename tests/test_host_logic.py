@@ -1,0 +1,123 @@
+"""Host-side logic that needs no GPU: on-disk formats (save_weights.py / convert_imgs_to_bin.py),
+shard arithmetic, and the N>1 gather path run as a real world_size-2 gloo job on CPU."""
+import os
+import struct
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REFERENCE, ROOT
+from resnet_c_b200 import dist as rdist
+from resnet_c_b200 import weights
+
+
+def test_weight_files_match_the_reference_writer(tmp_path):
+    """save_weights.py:9-12 writes each element with struct.pack('f', x.item()); ours must be
+    byte-identical, including the 4-byte float it makes of the int64 num_batches_tracked."""
+    sd = {
+        "conv1.weight": torch.randn(4, 3, 2, 2),
+        "bn1.running_var": torch.rand(4) + 0.5,
+        "bn1.num_batches_tracked": torch.tensor(7, dtype=torch.int64),
+    }
+    n = weights.save_weights_dir(sd, tmp_path)
+    assert n == 3
+    for name, t in sd.items():
+        expected = b"".join(struct.pack("f", x.item()) for x in t.data.flatten())
+        assert (tmp_path / name).read_bytes() == expected
+    assert (tmp_path / "bn1.num_batches_tracked").stat().st_size == 4
+
+
+def test_weight_dir_round_trip_and_file_inventory(tmp_path):
+    sd = weights.make_state_dict("resnet18", 0, randomize_bn=True)
+    n = weights.save_weights_dir(sd, tmp_path)
+    assert n == 122  # ResNet-18 = 122 files
+    back = weights.load_weights_dir("resnet18", tmp_path)
+    for k, v in sd.items():
+        assert torch.equal(back[k], v), k
+    # names the reference's loaders ask for (nn.cuh:21,58-61,113-117; main.cu:59-75)
+    for f in ("conv1.weight", "bn1.running_mean", "layer2.0.downsample.0.weight",
+              "layer2.0.downsample.1.running_var", "layer4.1.conv2.weight", "fc.weight", "fc.bias"):
+        assert (tmp_path / f).exists()
+
+
+def test_image_bin_round_trip(tmp_path, jpeg_tensor):
+    assert jpeg_tensor.shape == (1, 3, 224, 224)
+    p = tmp_path / "img.bin"
+    weights.save_image_bin(jpeg_tensor, p)
+    assert p.stat().st_size == 3 * 224 * 224 * 4  # convert_imgs_to_bin.py:20-23
+    assert torch.equal(weights.load_image_bin(p), jpeg_tensor)
+    # statistics recorded by the survey for this fixture
+    assert float(jpeg_tensor.min()) == pytest.approx(-1.98, abs=0.01)
+    assert float(jpeg_tensor.max()) == pytest.approx(2.45, abs=0.01)
+
+
+@pytest.mark.skipif(not (REFERENCE / "test_imgs").exists(), reason="reference tree not mounted")
+def test_preprocess_reproduces_committed_image(jpeg_tensor):
+    live = weights.preprocess_jpeg(REFERENCE / "test_imgs" / "ILSVRC2012_val_00004749.jpeg")
+    assert torch.equal(live, jpeg_tensor)
+
+
+def test_shard_bounds_cover_the_batch_exactly():
+    for total in (0, 1, 7, 256, 2048, 1000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [rdist.shard_bounds(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and b - a >= d - c >= 0
+    with pytest.raises(ValueError):
+        rdist.shard_bounds(8, 2, 2)
+
+
+_WORKER = textwrap.dedent("""
+    import os, sys, torch, torch.distributed as dist
+    sys.path.insert(0, {root!r})
+    from resnet_c_b200 import dist as rdist
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    total, classes = {total}, 10
+    g = torch.Generator().manual_seed(5)
+    full = torch.randn(total, classes, generator=g)
+    lo, hi = rdist.shard_bounds(total, world, rank)
+    logits = full[lo:hi].clone()
+    top1 = logits.argmax(1).to(torch.int32) if hi > lo else torch.empty(0, dtype=torch.int32)
+    all_l, all_t = rdist.gather_results(logits, top1, total)
+    assert torch.equal(all_l, full), "gathered logits differ"
+    assert torch.equal(all_t, full.argmax(1).to(torch.int32)), "gathered top1 differ"
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+@pytest.mark.parametrize("total", [8, 7, 1])
+def test_gather_world_size_2_gloo(tmp_path, total):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=str(ROOT), total=total))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    port = 29500 + (os.getpid() + total) % 2000
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference` prints ONE JSON line with the keys the driver reads."""
+    import json
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--cpu-sample", "2", "--arch", "resnet18"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["value"] > 0
+    assert d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
