@@ -73,6 +73,7 @@ int rnb_init(int device) {
     }
     g_num_sms = prop.multiProcessorCount;
     API_CUDA(conv_kernels_init());
+    API_CUDA(stem_tc_init());
     g_device = device;
     set_error("");
     return RNB_OK;
@@ -263,6 +264,24 @@ int rnb_stem_forward(const float* x_dev, const float* w_dev, const float* bn_wei
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int OH = (6 + H - 7) / 2 + 1, OW = (6 + W - 7) / 2 + 1;
     const int PH = (2 + OH - 3) / 2 + 1, PW = (2 + OW - 3) / 2 + 1;
+    if (esz == 2 && H == 224 && W == 224) {
+        // tensor-core stem (stem_tc.cu)
+        void *wk = nullptr, *xp = nullptr, *pool_tc = nullptr;
+        float* bias_tc = nullptr;
+        API_CUDA(cudaMallocAsync(&wk, stem_tc_packed_weight_bytes(), s));
+        API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&bias_tc), 64 * sizeof(float), s));
+        API_CUDA(cudaMallocAsync(&xp, stem_tc_packed_input_bytes(B), s));
+        API_CUDA(cudaMallocAsync(&pool_tc, 1ull * B * PH * PW * 64 * esz, s));
+        API_CUDA(launch_stem_tc_pack_weights(w_dev, bn_weight_dev, bn_bias_dev, bn_mean_dev, bn_var_dev, wk,
+                                             bias_tc, s));
+        API_CUDA(launch_stem_tc(x_dev, xp, wk, bias_tc, pool_tc, B, s));
+        API_CUDA(launch_nhwc_to_nchw(pool_tc, out_dev, B, 64, PH * PW, esz, s));
+        API_CUDA(cudaFreeAsync(wk, s));
+        API_CUDA(cudaFreeAsync(bias_tc, s));
+        API_CUDA(cudaFreeAsync(xp, s));
+        API_CUDA(cudaFreeAsync(pool_tc, s));
+        return RNB_OK;
+    }
     float *wf = nullptr, *bias = nullptr;
     void *conv = nullptr, *pool = nullptr;
     API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wf), 64 * 147 * sizeof(float), s));

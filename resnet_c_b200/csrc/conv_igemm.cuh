@@ -137,78 +137,87 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     if (warp == 0) {
         // ===================================================== TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const int ohw = g.OH * g.OW;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int n_blk = t % g.n_tiles;
-                const int m_blk = t / g.n_tiles;
-                const int m0 = m_blk * Cfg::BM;
-                const int img = m0 / ohw;
-                const int rem = m0 - img * ohw;
-                const int p = rem / g.OW;
-                const int q = rem - p * g.OW;
-                const int w0 = g.lower + q * g.stride;
-                const int h0 = g.lower + p * g.stride;
-                int tap = 0, cblk = 0;
-                for (int kb = 0; kb < g.num_kblocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // The whole warp walks the loop (uniform control flow keeps barrier addresses and TMA
+        // coordinates in uniform registers); one elected lane issues.
+        int stage = 0;
+        uint32_t phase = 0;
+        const int ohw = g.OH * g.OW;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int n_blk = t % g.n_tiles;
+            const int m_blk = t / g.n_tiles;
+            const int m0 = m_blk * Cfg::BM;
+            const int img = m0 / ohw;
+            const int rem = m0 - img * ohw;
+            const int p = rem / g.OW;
+            const int q = rem - p * g.OW;
+            const int w0 = g.lower + q * g.stride;
+            const int h0 = g.lower + p * g.stride;
+            int tap_r = 0, tap_s = 0, cblk = 0;
+            for (int kb = 0; kb < g.num_kblocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     uint8_t* sa = smem_stage + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    const int r = tap / g.ksize;
-                    const int s = tap - r * g.ksize;
                     tma_load_im2col_4d(sa, &tmA, &full_bar[stage], cblk * Cfg::BK, w0, h0, img,
-                                       static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+                                       static_cast<uint16_t>(tap_s), static_cast<uint16_t>(tap_r));
                     tma_load_2d(sb, &tmB, &full_bar[stage], kb * Cfg::BK, n_blk * BN);
-                    if (++cblk == g.kblocks_per_tap) {
-                        cblk = 0;
-                        ++tap;
+                }
+                __syncwarp();
+                if (++cblk == g.kblocks_per_tap) {
+                    cblk = 0;
+                    if (++tap_s == g.ksize) {
+                        tap_s = 0;
+                        ++tap_r;
                     }
-                    if (++stage == NSTAGE) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                }
+                if (++stage == NSTAGE) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc =
-                umma_instr_desc(Cfg::ESZ == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, Cfg::BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty[as], aphase ^ 1);
+        // Whole warp in the loop, one elected lane issues tcgen05.mma / tcgen05.commit. Descriptors
+        // are a per-kernel constant plus (stage offset + 32-byte K step) >> 4 in the address field.
+        constexpr uint32_t idesc =
+            umma_instr_desc(Cfg::ESZ == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, Cfg::BM, BN);
+        const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_stage), 0, 1024, UMMA_LAYOUT_SW128);
+        const uint64_t b_desc0 =
+            umma_smem_desc(smem_u32(smem_stage) + Cfg::A_BYTES, 0, 1024, UMMA_LAYOUT_SW128);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BN;
+            for (int kb = 0; kb < g.num_kblocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < g.num_kblocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_stage + stage * Cfg::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+                if (elect_one()) {
+                    const uint64_t soff = static_cast<uint64_t>((stage * Cfg::STAGE_BYTES) >> 4);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         // 32 bytes of K per instruction (16 bf16 / 8 tf32) inside the 128-byte swizzle row
-                        const uint64_t ad = umma_smem_desc(a_addr + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
-                        const uint64_t bd = umma_smem_desc(b_addr + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
+                        const uint64_t ad = a_desc0 + soff + static_cast<uint64_t>(k * 2);
+                        const uint64_t bd = b_desc0 + soff + static_cast<uint64_t>(k * 2);
                         if (Cfg::ESZ == 2)
                             mma_f16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
                         else
                             mma_tf32_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
                     }
                     tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                    if (++stage == NSTAGE) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                    if (kb == g.num_kblocks - 1) tc_commit(&tmem_full[as]);  // accumulator complete
                 }
-                tc_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+                __syncwarp();
+                if (++stage == NSTAGE) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
         }
     } else if (warp >= 4) {

@@ -49,6 +49,19 @@ cudaError_t launch_stem_conv(const float* x, const float* w_folded /*[64][3][7][
 cudaError_t launch_maxpool_nhwc(const void* x, void* out, int B, int H, int W, int C, int esz,
                                 cudaStream_t s);
 
+// ---- tensor-core stem, BF16 path, 224x224 inputs (stem_tc.cu)
+size_t stem_tc_packed_input_bytes(int B);
+size_t stem_tc_packed_weight_bytes();
+cudaError_t stem_tc_init();
+cudaError_t launch_stem_tc_pack_weights(const float* w, const float* bn_w, const float* bn_b,
+                                        const float* bn_m, const float* bn_v, void* wk, float* bias,
+                                        cudaStream_t s);
+// Two launches: NCHW fp32 -> padded NHWC4 bf16 (scratch `xp`), then conv7x7/2 + BN + ReLU + maxpool.
+cudaError_t launch_stem_tc(const float* x, void* xp, const void* wk, const float* bias, void* out, int B,
+                           cudaStream_t s);
+cudaError_t launch_stem_tc_part(int part, const float* x, void* xp, const void* wk, const float* bias,
+                                void* out, int B, cudaStream_t s);
+
 // ---- tail (tail.cu)
 // global average pool over NHWC [B,HW,C] -> pooled [B,C] fp32
 cudaError_t launch_avgpool_nhwc(const void* x, float* pooled, int B, int HW, int C, int esz,

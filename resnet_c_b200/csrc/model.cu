@@ -140,7 +140,7 @@ Model::~Model() {
     if (cap_stream) cudaStreamDestroy(cap_stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     arena.free_all();
-    cudaFree(stem_w); cudaFree(stem_bias); cudaFree(fc_w); cudaFree(fc_b);
+    cudaFree(stem_w); cudaFree(stem_bias); cudaFree(stem_wk); cudaFree(fc_w); cudaFree(fc_b);
     cudaFree(host_x_dev); cudaFree(host_logits_dev); cudaFree(host_top1_dev); cudaFree(scratch_logits);
     for (auto& b : blocks) {
         for (ConvWeights* c : {&b.conv1, &b.conv2, &b.conv3, &b.ds}) {
@@ -195,6 +195,12 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
         RNB_CUDA(cudaMalloc(&stem_w, 64 * 147 * sizeof(float)));
         RNB_CUDA(cudaMalloc(&stem_bias, 64 * sizeof(float)));
         RNB_CUDA(launch_fold_f32(raw, bn.w, bn.b, bn.m, bn.v, stem_w, stem_bias, 64, 147, 0));
+        const char* nostc = getenv("RNB_NO_STEM_TC");
+        stem_tc = esz == 2 && image == 224 && !(nostc && atoi(nostc) != 0);
+        if (stem_tc) {
+            RNB_CUDA(cudaMalloc(&stem_wk, stem_tc_packed_weight_bytes()));
+            RNB_CUDA(launch_stem_tc_pack_weights(raw, bn.w, bn.b, bn.m, bn.v, stem_wk, stem_bias, 0));
+        }
         RNB_CUDA(cudaDeviceSynchronize());
         cudaFree(raw);
         bn.free_all();
@@ -282,9 +288,10 @@ ChunkPlan* Model::plan_for(int n) {
     };
     const int s_hw = (6 + image - 7) / 2 + 1;     // 112
     const int p_hw = (2 + s_hw - 3) / 2 + 1;      // 56
-    if (!(p.stem_out = arena.acquire(bytes(64, s_hw)))) return fail_alloc();
+    if (!(p.stem_out = arena.acquire(stem_tc ? stem_tc_packed_input_bytes(n) : bytes(64, s_hw))))
+        return fail_alloc();
     if (!(p.pool_out = arena.acquire(bytes(64, p_hw)))) return fail_alloc();
-    p.named["stem"] = {p.stem_out, 64, s_hw, s_hw};
+    if (!stem_tc) p.named["stem"] = {p.stem_out, 64, s_hw, s_hw};
     p.named["maxpool"] = {p.pool_out, 64, p_hw, p_hw};
     arena.release(p.stem_out);  // dead once the pool has run
 
@@ -363,8 +370,12 @@ ChunkPlan* Model::plan_for(int n) {
 int Model::enqueue_chunk(ChunkPlan& p, const float* x, float* logits, int32_t* top1, cudaStream_t s) {
     const int n = p.n;
     const int s_hw = (6 + image - 7) / 2 + 1;
-    RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
-    RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
+    if (stem_tc) {
+        RNB_CUDA(launch_stem_tc(x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
+    } else {
+        RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
+        RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
+    }
     for (const ConvPlan& cp : p.convs) RNB_CUDA(conv_plan_launch(cp, s));
     RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, n, p.last_hw, p.last_c, esz, s));
     RNB_CUDA(launch_fc(p.pooled, fc_w, fc_b, logits, n, p.last_c, classes, s));
@@ -450,9 +461,15 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
     for (int it = -1; it < iters; ++it) {
         int i = 0;
         RNB_CUDA(cudaEventRecord(ev[i], s));
-        RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
+        if (stem_tc)
+            RNB_CUDA(launch_stem_tc_part(0, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
+        else
+            RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
         RNB_CUDA(cudaEventRecord(ev[++i], s));
-        RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
+        if (stem_tc)
+            RNB_CUDA(launch_stem_tc_part(1, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
+        else
+            RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
         RNB_CUDA(cudaEventRecord(ev[++i], s));
         for (const ConvPlan& cp : p.convs) {
             RNB_CUDA(conv_plan_launch(cp, s));
@@ -482,8 +499,15 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
         ++i;
     };
     const double img_px = 1.0 * image * image;
-    put(0, 2.0 * n * 64 * 147 * s_hw * s_hw, n * (3.0 * img_px * 4 + 64.0 * s_hw * s_hw * esz) + 64 * 148 * 4.0);
-    put(1, 0.0, n * 64.0 * esz * (1.0 * s_hw * s_hw + 1.0 * p_hw * p_hw));
+    if (stem_tc) {
+        // launch 0 = layout pre-pass (fp32 NCHW -> padded NHWC4 bf16), launch 1 = fused conv+BN+ReLU+pool
+        const double packed = static_cast<double>(stem_tc_packed_input_bytes(1));
+        put(0, 0.0, n * (3.0 * img_px * 4 + packed));
+        put(1, 2.0 * n * 64 * 147 * s_hw * s_hw, n * (packed + 64.0 * p_hw * p_hw * esz) + 28672.0);
+    } else {
+        put(0, 2.0 * n * 64 * 147 * s_hw * s_hw, n * (3.0 * img_px * 4 + 64.0 * s_hw * s_hw * esz) + 64 * 148 * 4.0);
+        put(1, 0.0, n * 64.0 * esz * (1.0 * s_hw * s_hw + 1.0 * p_hw * p_hw));
+    }
     for (const ConvPlan& cp : p.convs) put(2, cp.flops, cp.bytes);
     put(3, 0.0, 1.0 * n * p.last_c * (1.0 * p.last_hw * esz + 4.0));
     put(4, 2.0 * n * p.last_c * classes, 4.0 * (1.0 * n * p.last_c + 1.0 * classes * p.last_c + 1.0 * n * classes));

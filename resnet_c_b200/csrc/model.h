@@ -39,7 +39,7 @@ struct NamedAct {
 // Everything needed to run `n` images through the network once.
 struct ChunkPlan {
     int n = 0;
-    void* stem_out = nullptr;   // NHWC [n,112,112,64]
+    void* stem_out = nullptr;   // NHWC [n,112,112,64] (CUDA-core stem) or packed NHWC4 input (tensor-core stem)
     void* pool_out = nullptr;   // NHWC [n,56,56,64]
     std::vector<ConvPlan> convs;
     void* last = nullptr;       // NHWC [n,7,7,C_final]
@@ -74,6 +74,8 @@ struct Model {
 
     float* stem_w = nullptr;     // folded fp32 [64][3][7][7]
     float* stem_bias = nullptr;  // [64]
+    void* stem_wk = nullptr;     // tensor-core stem weights (bf16 path), see stem_tc.cu
+    bool stem_tc = false;
     std::vector<BlockWeights> blocks;
     float* fc_w = nullptr;  // [classes][final_c]
     float* fc_b = nullptr;
