@@ -172,8 +172,8 @@ int rnb_model_get_activation(rnb_model_t* m, const char* name, float* out_dev, i
     if (!out_dev) return RNB_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (std::string(name) == "avgpool") {
-        API_CUDA(cudaMemcpyAsync(out_dev, a.ptr, 1ull * n * a.C * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, s));
+        // stored transposed ([C][n], see tail.cu); hand back [n][C]
+        API_CUDA(launch_transpose_f32(static_cast<const float*>(a.ptr), out_dev, a.C, n, s));
         return RNB_OK;
     }
     API_CUDA(launch_nhwc_to_nchw(a.ptr, out_dev, n, a.C, a.H * a.W, M.esz, s));
@@ -318,12 +318,15 @@ int rnb_tail_forward(const float* x_dev, const float* fc_w_dev, const float* fc_
         return RNB_ERR_UNSUPPORTED;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    float* pooled = nullptr;
+    float *pooled = nullptr, *pooledT = nullptr;
     API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pooled), 1ull * B * C * sizeof(float), s));
+    API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pooledT), 1ull * B * C * sizeof(float), s));
     API_CUDA(launch_pool2d_f32(false, x_dev, pooled, B, C, k, k, k, 1, 0, s));
-    API_CUDA(launch_fc(pooled, fc_w_dev, fc_b_dev, logits_dev, B, C, classes, s));
+    API_CUDA(launch_transpose_f32(pooled, pooledT, B, C, s));
+    API_CUDA(launch_fc(pooledT, fc_w_dev, fc_b_dev, logits_dev, B, C, classes, s));
     if (top1_dev) API_CUDA(launch_argmax_f32(logits_dev, top1_dev, B, classes, s));
     API_CUDA(cudaFreeAsync(pooled, s));
+    API_CUDA(cudaFreeAsync(pooledT, s));
     return RNB_OK;
 }
 

@@ -1,0 +1,438 @@
+// conv_igemm2.cuh — the 2-CTA (cta_group::2) variant of the implicit-GEMM convolution.
+//
+// Same math and same fused epilogue as conv_igemm.cuh (the replacement of conv2dForwardKernel +
+// batchNorm2dForwardKernel + addForwardKernel + reluForwardKernel, /root/reference/cuda/ops.cu:14-48,
+// 139-151,153-160,130-137), but each tile is computed by a PAIR of CTAs on the two SMs of a TPC:
+//
+//   tile = 256 pixels x BN channels (BN = 128 or 256); CTA r of the pair owns pixels [128r, 128r+128)
+//   A: each CTA im2col-loads its own 128-pixel K-slab        (16 KB / stage)
+//   B: each CTA loads HALF of the weight tile (BN/2 rows)    (8 or 16 KB / stage)
+//   one tcgen05.mma.cta_group::2 (M = 256), issued by the leader CTA, reads A from both SMs and the
+//   two B halves from both SMs; each SM's TMEM receives its own 128 x BN half of the accumulator.
+//
+// Why: with 128 x 128 single-CTA tiles every 1 M MACs pull 32 KB through L2 (32 MAC/B) and the
+// compute-bound layers saturate the L2 -> SM fabric (~13 TB/s) at ~40 % of tensor peak. The pair
+// halves the bytes per MAC (64 MAC/B at BN = 256) and halves each SM's shared-memory operand reads.
+//
+// Synchronisation (barriers have the same offsets in both CTAs):
+//   full[s]       lives in the LEADER: the leader's producer arms it with the byte count of BOTH
+//                 CTAs; both CTAs' TMA loads complete_tx on it (.cta_group::2 form, peer bit cleared)
+//   empty[s]      one per CTA, released by the leader's multicast tcgen05.commit
+//   tmem_full[a]  one per CTA, multicast commit after the last K block of a tile
+//   tmem_empty[a] in the leader, 8 arrivals: one per epilogue warp of both CTAs (remote arrive)
+//   res_full[c]   per CTA (each CTA prefetches the residual rows it owns)
+// The epilogue works on 32 KB sub-tiles (128 rows x 256 bytes) through NCBUF rotating staging
+// buffers, exactly as in the single-CTA kernel.
+#pragma once
+#include "conv_igemm.cuh"
+
+namespace rnb {
+
+template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_>
+struct Conv2Cfg {
+    static constexpr int BM = 256;                    // pixels per CTA pair
+    static constexpr int BM_CTA = 128;                // pixels per CTA
+    static constexpr int BN = BN_;
+    static constexpr int ESZ = ESZ_;
+    static constexpr int BK = 128 / ESZ_;
+    static constexpr int NSTAGE = NSTAGE_;
+    static constexpr int NCBUF = NCBUF_;
+    static constexpr int A_BYTES = BM_CTA * 128;
+    static constexpr int B_BYTES = (BN_ / 2) * 128;    // this CTA's half of the weight tile
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BOX_COLS = 128 / ESZ_;
+    static constexpr int EPI_N = 2 * BOX_COLS;         // columns per epilogue sub-tile (256 bytes / row)
+    static constexpr int NSUB = BN_ / EPI_N;
+    static constexpr int BOX_BYTES = BM_CTA * 128;
+    static constexpr int CBUF_BYTES = 2 * BOX_BYTES;   // 32 KB
+    static constexpr int TMEM_COLS = 2 * BN_;
+    static constexpr int NBAR = 2 * NSTAGE_ + 4 + NCBUF_;
+    static constexpr int SMEM_BYTES =
+        1024 + NSTAGE_ * STAGE_BYTES + NCBUF_ * CBUF_BYTES + NBAR * 8 + 16;
+    static constexpr int THREADS = 256;
+    static_assert(NCBUF_ >= 2, "need at least two staging buffers");
+    static_assert(BN_ % EPI_N == 0, "tile N must be a multiple of the epilogue sub-tile");
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+};
+
+namespace ptx {
+
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in the pair's leader CTA (works from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                                int32_t x, int32_t y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)),
+          "r"(smem_u32(bar) & kPeerBitMask), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_2sm(void* smem_dst, const CUtensorMap* m,
+                                                       uint64_t* bar, int32_t c, int32_t w, int32_t h,
+                                                       int32_t n, uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)),
+          "r"(smem_u32(bar) & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(smem_result)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+// commit: arrive on the barrier at this offset in BOTH CTAs of the pair once prior MMAs retire
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+}  // namespace ptx
+
+// One 32-column chunk of the accumulator: + bias (+ residual read from the staging row) -> ReLU ->
+// round to the activation type -> write back to the same swizzled staging row.
+template <int ESZ>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint8_t* row, uint32_t c16_base,
+                                               uint32_t swz, const float* __restrict__ bias32,
+                                               int has_res, int relu) {
+    if (ESZ == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4* p16 = reinterpret_cast<uint4*>(row + (((c16_base + j) ^ swz) << 4));
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias32 + j * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias32 + j * 8 + 4));
+            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+            x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            if (has_res) {
+                const uint4 rr = *p16;
+                x[0] += bf16_lo(rr.x); x[1] += bf16_hi(rr.x);
+                x[2] += bf16_lo(rr.y); x[3] += bf16_hi(rr.y);
+                x[4] += bf16_lo(rr.z); x[5] += bf16_hi(rr.z);
+                x[6] += bf16_lo(rr.w); x[7] += bf16_hi(rr.w);
+            }
+            if (relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e], 0.f);
+            }
+            uint4 o;
+            o.x = pack_bf16x2(x[0], x[1]);
+            o.y = pack_bf16x2(x[2], x[3]);
+            o.z = pack_bf16x2(x[4], x[5]);
+            o.w = pack_bf16x2(x[6], x[7]);
+            *p16 = o;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint4* p16 = reinterpret_cast<uint4*>(row + (((c16_base + j) ^ swz) << 4));
+            float x[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(v[j * 4 + e]);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias32 + j * 4));
+            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+            if (has_res) {
+                const float4 rr = *reinterpret_cast<const float4*>(p16);
+                x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
+            }
+            if (relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+            }
+            uint4 o;
+            o.x = __float_as_uint(round_tf32(x[0]));
+            o.y = __float_as_uint(round_tf32(x[1]));
+            o.z = __float_as_uint(round_tf32(x[2]));
+            o.w = __float_as_uint(round_tf32(x[3]));
+            *p16 = o;
+        }
+    }
+}
+
+// Tensor maps: tmA im2col over the input (128 pixels x 128 bytes per load), tmB tiled over the packed
+// weights with a box of BN/2 rows, tmOut / tmRes tiled over [M][Cout] with boxes of 128 rows.
+template <class Cfg>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::THREADS, 1)
+conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmOut,
+                   const __grid_constant__ CUtensorMap tmRes, const float* __restrict__ bias,
+                   const ConvGeom g) {
+    using namespace ptx;
+    constexpr int BN = Cfg::BN;
+    constexpr int NSTAGE = Cfg::NSTAGE;
+    constexpr int NCBUF = Cfg::NCBUF;
+    constexpr int NSUB = Cfg::NSUB;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_stage = smem;
+    uint8_t* smem_c = smem + NSTAGE * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + NCBUF * Cfg::CBUF_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + NSTAGE;
+    uint64_t* tmem_full = bars + 2 * NSTAGE;
+    uint64_t* tmem_empty = bars + 2 * NSTAGE + 2;
+    uint64_t* res_full = bars + 2 * NSTAGE + 4;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int num_tiles = g.m_tiles * g.n_tiles;       // m_tiles counts 256-pixel tiles here
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmOut);
+        if (g.has_res) tma_prefetch_desc(&tmRes);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NSTAGE; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 8);
+        }
+        for (int i = 0; i < NCBUF; ++i) mbar_init(&res_full[i], 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        __syncwarp();
+        tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer (both CTAs)
+        int stage = 0;
+        uint32_t phase = 0;
+        const int ohw = g.OH * g.OW;
+        for (int t = pair; t < num_tiles; t += num_pairs) {
+            const int n_blk = t % g.n_tiles;
+            const int m_blk = t / g.n_tiles;
+            const int m0 = m_blk * Cfg::BM + static_cast<int>(rank) * Cfg::BM_CTA;
+            const int img = m0 / ohw;
+            const int rem = m0 - img * ohw;
+            const int p = rem / g.OW;
+            const int q = rem - p * g.OW;
+            const int w0 = g.lower + q * g.stride;
+            const int h0 = g.lower + p * g.stride;
+            const int nrow0 = n_blk * BN + static_cast<int>(rank) * (BN / 2);
+            int tap_r = 0, tap_s = 0, cblk = 0;
+            for (int kb = 0; kb < g.num_kblocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
+                    uint8_t* sa = smem_stage + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    tma_load_im2col_4d_2sm(sa, &tmA, &full_bar[stage], cblk * Cfg::BK, w0, h0, img,
+                                           static_cast<uint16_t>(tap_s), static_cast<uint16_t>(tap_r));
+                    tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * Cfg::BK, nrow0);
+                }
+                __syncwarp();
+                if (++cblk == g.kblocks_per_tap) {
+                    cblk = 0;
+                    if (++tap_s == g.ksize) {
+                        tap_s = 0;
+                        ++tap_r;
+                    }
+                }
+                if (++stage == NSTAGE) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (leader CTA only)
+        if (rank == 0) {
+            constexpr uint32_t idesc =
+                umma_instr_desc(Cfg::ESZ == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, Cfg::BM, BN);
+            const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_stage), 0, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t b_desc0 =
+                umma_smem_desc(smem_u32(smem_stage) + Cfg::A_BYTES, 0, 1024, UMMA_LAYOUT_SW128);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < g.num_kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t soff = static_cast<uint64_t>((stage * Cfg::STAGE_BYTES) >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = a_desc0 + soff + static_cast<uint64_t>(k * 2);
+                            const uint64_t bd = b_desc0 + soff + static_cast<uint64_t>(k * 2);
+                            if (Cfg::ESZ == 2)
+                                mma_f16_ss_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                            else
+                                mma_tf32_ss_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                        }
+                        tc_commit_2sm(&empty_bar[stage]);
+                        if (kb == g.num_kblocks - 1) tc_commit_2sm(&tmem_full[as]);
+                    }
+                    __syncwarp();
+                    if (++stage == NSTAGE) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== epilogue (both CTAs)
+        const int et = threadIdx.x - 128;
+        const int q = warp & 3;
+        const uint32_t swz = static_cast<uint32_t>(et & 7);
+        const bool leader = (et == 0);
+        const int my_tiles = (num_tiles - pair + num_pairs - 1) / num_pairs;
+        const int my_items = my_tiles * NSUB;  // (tile, sub-tile) work items of this CTA
+
+        auto item_coords = [&](int item, int& col0, int& row0) {
+            const int it_local = item / NSUB, sub = item - it_local * NSUB;
+            const int t = pair + it_local * num_pairs;
+            const int n_blk = t % g.n_tiles;
+            const int m_blk = t / g.n_tiles;
+            col0 = n_blk * BN + sub * Cfg::EPI_N;
+            row0 = m_blk * Cfg::BM + static_cast<int>(rank) * Cfg::BM_CTA;
+        };
+        auto issue_residual = [&](int item) {
+            int col0, row0;
+            item_coords(item, col0, row0);
+            const int cs = item % NCBUF;
+            uint8_t* buf = smem_c + cs * Cfg::CBUF_BYTES;
+            mbar_expect_tx(&res_full[cs], Cfg::CBUF_BYTES);
+            tma_load_2d(buf, &tmRes, &res_full[cs], col0, row0);
+            tma_load_2d(buf + Cfg::BOX_BYTES, &tmRes, &res_full[cs], col0 + Cfg::BOX_COLS, row0);
+        };
+        if (leader && g.has_res) {
+            if (my_items > 0) issue_residual(0);
+            if (my_items > 1) issue_residual(1);
+        }
+
+        int item = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+            for (int sub = 0; sub < NSUB; ++sub, ++item) {
+                int col0, row0;
+                item_coords(item, col0, row0);
+                const int cs = item % NCBUF;
+                uint8_t* cbuf = smem_c + cs * Cfg::CBUF_BYTES;
+                if (g.has_res) mbar_wait(&res_full[cs], (item / NCBUF) & 1);
+#pragma unroll 1
+                for (int chunk = 0; chunk < Cfg::EPI_N / 32; ++chunk) {
+                    uint32_t v[32];
+                    __syncwarp();
+                    tmem_ld_32x32(taddr + sub * Cfg::EPI_N + chunk * 32, v);
+                    tmem_ld_wait();
+                    const int byte_off = chunk * 32 * Cfg::ESZ;
+                    uint8_t* row = cbuf + (byte_off >> 7) * Cfg::BOX_BYTES + et * 128;
+                    epilogue_chunk<Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz,
+                                             bias + col0 + chunk * 32, g.has_res, g.relu);
+                }
+                if (sub == NSUB - 1) {
+                    // accumulator drained: one arrival per epilogue warp of both CTAs, in the leader
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (leader) {
+                    tma_store_2d(&tmOut, cbuf, col0, row0);
+                    tma_store_2d(&tmOut, cbuf + Cfg::BOX_BYTES, col0 + Cfg::BOX_COLS, row0);
+                    tma_store_commit();
+                    tma_store_wait_read<NCBUF - 2>();
+                    if (g.has_res && item + 2 < my_items) issue_residual(item + 2);
+                }
+            }
+        }
+        if (leader) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's smem/TMEM must stay alive until the leader's MMAs have retired
+    if (warp == 2) {
+        __syncwarp();
+        tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace rnb

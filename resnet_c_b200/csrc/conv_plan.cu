@@ -4,6 +4,9 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
+#include "conv_igemm2.cuh"
 #include "tensormap.h"
 
 namespace rnb {
@@ -13,6 +16,16 @@ using CfgBf16N128 = ConvCfg<128, 2, 4, 3>;
 using CfgBf16N64 = ConvCfg<64, 2, 6, 3>;
 using CfgTf32N128 = ConvCfg<128, 4, 3, 2>;
 using CfgTf32N64 = ConvCfg<64, 4, 5, 3>;
+
+// 2-CTA (cta_group::2) configurations: 256-pixel tiles, BN = 256 or 128.
+using Cfg2Bf16N256 = Conv2Cfg<256, 2, 4, 3>;
+using Cfg2Bf16N128 = Conv2Cfg<128, 2, 5, 3>;
+using Cfg2Tf32N256 = Conv2Cfg<256, 4, 4, 3>;
+using Cfg2Tf32N128 = Conv2Cfg<128, 4, 5, 3>;
+static_assert(Cfg2Bf16N256::SMEM_BYTES <= 232448, "smem budget");
+static_assert(Cfg2Bf16N128::SMEM_BYTES <= 232448, "smem budget");
+static_assert(Cfg2Tf32N256::SMEM_BYTES <= 232448, "smem budget");
+static_assert(Cfg2Tf32N128::SMEM_BYTES <= 232448, "smem budget");
 
 static_assert(CfgBf16N128::SMEM_BYTES <= 232448, "smem budget");
 static_assert(CfgBf16N64::SMEM_BYTES <= 232448, "smem budget");
@@ -24,6 +37,11 @@ static cudaError_t set_smem() {
     return cudaFuncSetAttribute(conv_igemm_kernel<Cfg>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
 }
+template <class Cfg>
+static cudaError_t set_smem2() {
+    return cudaFuncSetAttribute(conv_igemm2_kernel<Cfg>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+}
 
 cudaError_t conv_kernels_init() {
     cudaError_t e;
@@ -31,6 +49,10 @@ cudaError_t conv_kernels_init() {
     if ((e = set_smem<CfgBf16N64>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgTf32N128>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgTf32N64>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Bf16N256>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Bf16N128>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Tf32N256>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Tf32N128>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -52,10 +74,30 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     const long long M = 1LL * d.B * OH * OW;
     if (M <= 0 || M > 0x7fffffffLL) return fail(err, errlen, "conv_plan: bad M", -5);
 
+    // Tile selection. force_bn: 64 / 128 = single-CTA tiles, 1128 / 1256 = CTA-pair tiles (testing).
+    // Default: the CTA-pair kernel (256-pixel tiles, half the L2 bytes per MAC) whenever the layer
+    // offers at least one full wave of pair tiles; single-CTA 128-pixel tiles otherwise.
     int bn = (d.Cout % 128 == 0) ? 128 : 64;
+    int ctas = 1;
+    const char* kind_env = getenv("RNB_CONV_KIND");  // "1" forces single-CTA tiles everywhere
+    const bool allow_pair = !(kind_env && atoi(kind_env) == 1);
     if (force_bn == 64 || force_bn == 128) {
         if (d.Cout % force_bn != 0) return fail(err, errlen, "conv_plan: forced BN does not divide Cout", -6);
         bn = force_bn;
+    } else if (force_bn == 1128 || force_bn == 1256) {
+        if (d.Cout % (force_bn - 1000) != 0) return fail(err, errlen, "conv_plan: forced BN does not divide Cout", -6);
+        bn = force_bn - 1000;
+        ctas = 2;
+    } else if (allow_pair && d.Cout % 128 == 0 && !d.residual && d.ksize * d.ksize * d.Cin > 64) {
+        // Measured on B200 (profiles/): pairs win wherever the K loop dominates (3x3 and wide 1x1
+        // layers, up to 1.45x); layers whose time is the epilogue's HBM traffic (residual add, or a
+        // single K block) are no faster with pairs and slightly slower, so they keep 128-pixel tiles.
+        const int pbn = d.Cout % 256 == 0 ? 256 : 128;
+        const long long pair_tiles = ((M + 255) / 256) * (d.Cout / pbn);
+        if (pair_tiles >= num_sms / 2) {
+            bn = pbn;
+            ctas = 2;
+        }
     }
     ConvGeom& g = plan->g;
     g.M = static_cast<int>(M);
@@ -67,15 +109,21 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     g.ksize = d.ksize;
     g.kblocks_per_tap = d.Cin / bk;
     g.num_kblocks = d.ksize * d.ksize * g.kblocks_per_tap;
-    g.m_tiles = static_cast<int>((M + 127) / 128);
+    g.m_tiles = static_cast<int>(ctas == 2 ? (M + 255) / 256 : (M + 127) / 128);
     g.n_tiles = d.Cout / bn;
     g.relu = d.relu ? 1 : 0;
     g.has_res = d.residual ? 1 : 0;
     plan->bias = d.bias;
     plan->bn = bn;
     plan->esz = esz;
+    plan->ctas = ctas;
     const int tiles = g.m_tiles * g.n_tiles;
-    plan->grid = tiles < num_sms ? tiles : num_sms;
+    if (ctas == 2) {
+        const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+        plan->grid = 2 * pairs;
+    } else {
+        plan->grid = tiles < num_sms ? tiles : num_sms;
+    }
     plan->flops = 2.0 * static_cast<double>(M) * d.Cout * (1.0 * d.ksize * d.ksize * d.Cin);
     plan->bytes = 1.0 * d.B * d.H * d.W * d.Cin * esz + 1.0 * d.Cout * d.ksize * d.ksize * d.Cin * esz +
                   4.0 * d.Cout + (d.residual ? 2.0 : 1.0) * static_cast<double>(M) * d.Cout * esz;
@@ -86,7 +134,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
                               128)) != 0)
         return fail(err, errlen, "conv_plan: im2col tensor map (A) failed", r);
     const uint64_t K = 1ull * d.ksize * d.ksize * d.Cin;
-    if ((r = make_tiled_2d(&plan->tmB, dt, d.weight, d.Cout, K, bn)) != 0)
+    if ((r = make_tiled_2d(&plan->tmB, dt, d.weight, d.Cout, K, ctas == 2 ? bn / 2 : bn)) != 0)
         return fail(err, errlen, "conv_plan: tiled tensor map (B) failed", r);
     if ((r = make_tiled_2d(&plan->tmOut, dt, d.out, M, d.Cout, 128)) != 0)
         return fail(err, errlen, "conv_plan: tiled tensor map (out) failed", r);
@@ -103,7 +151,18 @@ static cudaError_t launch(const ConvPlan& p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+template <class Cfg>
+static cudaError_t launch2(const ConvPlan& p, cudaStream_t stream) {
+    conv_igemm2_kernel<Cfg><<<p.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(
+        p.tmA, p.tmB, p.tmOut, p.tmRes, p.bias, p.g);
+    return cudaGetLastError();
+}
+
 cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
+    if (p.ctas == 2) {
+        if (p.esz == 2) return p.bn == 256 ? launch2<Cfg2Bf16N256>(p, stream) : launch2<Cfg2Bf16N128>(p, stream);
+        return p.bn == 256 ? launch2<Cfg2Tf32N256>(p, stream) : launch2<Cfg2Tf32N128>(p, stream);
+    }
     if (p.esz == 2) return p.bn == 128 ? launch<CfgBf16N128>(p, stream) : launch<CfgBf16N64>(p, stream);
     return p.bn == 128 ? launch<CfgTf32N128>(p, stream) : launch<CfgTf32N64>(p, stream);
 }

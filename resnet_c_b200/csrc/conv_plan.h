@@ -25,6 +25,7 @@ struct ConvPlan {
     ConvGeom g;
     const float* bias;
     int bn;       // tile N
+    int ctas;     // 1 = single-CTA 128-pixel tiles, 2 = CTA-pair 256-pixel tiles (cta_group::2)
     int esz;      // element bytes
     int grid;     // persistent CTAs
     double flops;  // 2*M*N*K

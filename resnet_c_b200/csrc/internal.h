@@ -63,11 +63,13 @@ cudaError_t launch_stem_tc_part(int part, const float* x, void* xp, const void* 
                                 void* out, int B, cudaStream_t s);
 
 // ---- tail (tail.cu)
-// global average pool over NHWC [B,HW,C] -> pooled [B,C] fp32
-cudaError_t launch_avgpool_nhwc(const void* x, float* pooled, int B, int HW, int C, int esz,
+// global average pool over NHWC [B,HW,C] -> pooledT [C][B] fp32 (transposed, see tail.cu)
+cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, int B, int HW, int C, int esz,
                                 cudaStream_t s);
-// logits[B,classes] = pooled[B,C] * W[classes,C]^T + bias
-cudaError_t launch_fc(const float* pooled, const float* w, const float* bias, float* logits, int B,
+// logits[B,classes] = pooledT[C,B]^T * W[classes,C]^T + bias
+cudaError_t launch_fc(const float* pooledT, const float* w, const float* bias, float* logits, int B,
                       int C, int classes, cudaStream_t s);
+// out[cols][rows] = in[rows][cols]^T, fp32
+cudaError_t launch_transpose_f32(const float* in, float* out, int rows, int cols, cudaStream_t s);
 
 }  // namespace rnb

@@ -45,7 +45,8 @@ constexpr int W_BYTES = 28 * 1024;    // [kh*4 + j][64 oc][8 e] bf16
 constexpr int VBUF_BYTES = 112 * 128; // [ow][64 ch] bf16, 16-byte chunks XOR-swizzled by (ow & 7)
 constexpr int NBAR = 4 + 2 * ROWS_PER_UNIT;
 constexpr int STEM_SMEM = 1024 + 2 * IN_SLOT_BYTES + W_BYTES + 2 * VBUF_BYTES + NBAR * 8 + 16;
-constexpr int STEM_TC_THREADS = 256;
+constexpr int EPI_THREADS = 256;                 // 8 epilogue warps
+constexpr int STEM_TC_THREADS = 128 + EPI_THREADS;
 
 // x [B,3,224,224] fp32 -> xp [B][235][232][4] bf16, zero border and zero 4th channel.
 __global__ void stem_pack_kernel(const float* __restrict__ x, uint2* __restrict__ xp, int B) {
@@ -100,6 +101,12 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
         : "memory");
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
     __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);
@@ -132,7 +139,7 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
         }
         for (int i = 0; i < ROWS_PER_UNIT; ++i) {
             mbar_init(&slot_full[i], 1);
-            mbar_init(&slot_empty[i], 128);
+            mbar_init(&slot_empty[i], EPI_THREADS);
         }
         fence_mbar_init();
     }
@@ -202,9 +209,16 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
         }
     } else if (warp >= 4) {
         // ===================================================== epilogue
-        const int et = threadIdx.x - 128;  // TMEM lane == conv output column ow
+        // 8 warps: warp quarter q = warp & 3 owns TMEM lanes 32q..32q+31 (conv columns ow), and the
+        // two warps of a quarter split the 64 channels (half 0 / half 1).
         const int q = warp & 3;
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int half = (warp - 4) >> 2;
+        const int et = q * 32 + (threadIdx.x & 31);   // conv output column ow == TMEM lane
+        const int etid = threadIdx.x - 128;           // 0..255 within the epilogue group
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32;
+        float bias_r[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bias_r[i] = __ldg(bias + half * 32 + i);
         int it = 0;
         int vb = 0;  // vbuf ping-pong
         for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
@@ -217,40 +231,38 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
                 mbar_wait(&slot_full[2 * p + 1], par);
                 mbar_wait(&slot_full[2 * p + 2], par);
                 tc_fence_after();
-                uint8_t* vrow = vbuf + vb * VBUF_BYTES + et * 128;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    float m[32];
+                // vertical max over the three conv rows of this pooled row. max_k(x_k + b) =
+                // max_k(x_k) + b and ReLU output is >= 0, so a missing row (-1 or 112) is simply
+                // left out; the middle row 2*ph always exists for a stored pooled row.
+                float m[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) m[i] = 0.f;  // post-ReLU values are >= 0: 0 == "no tap"
+                for (int k = 0; k < 3; ++k) {
+                    const int oh = 6 * v - 1 + 2 * p + k;
+                    uint32_t raw[32];
+                    __syncwarp();
+                    tmem_ld_32x32(lane_addr + (2 * p + k) * 64, raw);
+                    tmem_ld_wait();
+                    if (k == 0) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int slot = 2 * p + k;
-                        const int oh = 6 * v - 1 + slot;
-                        uint32_t raw[32];
-                        __syncwarp();
-                        tmem_ld_32x32(lane_addr + slot * 64 + half * 32, raw);
-                        tmem_ld_wait();
-                        if (oh >= 0 && oh < CONV) {
+                        for (int i = 0; i < 32; ++i) m[i] = oh >= 0 ? __uint_as_float(raw[i]) : -INFINITY;
+                    } else if (oh < CONV) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                m[i] = fmaxf(m[i], __uint_as_float(raw[i]) + __ldg(bias + half * 32 + i));
-                        }
+                        for (int i = 0; i < 32; ++i) m[i] = fmaxf(m[i], __uint_as_float(raw[i]));
                     }
-                    if (et < CONV) {
+                }
+                if (et < CONV) {
+                    uint8_t* vrow = vbuf + vb * VBUF_BYTES + et * 128;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 o;
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(m[j * 8 + 0], m[j * 8 + 1]);
-                            __nv_bfloat162 t1 = __floats2bfloat162_rn(m[j * 8 + 2], m[j * 8 + 3]);
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(m[j * 8 + 4], m[j * 8 + 5]);
-                            __nv_bfloat162 t3 = __floats2bfloat162_rn(m[j * 8 + 6], m[j * 8 + 7]);
-                            o.x = *reinterpret_cast<uint32_t*>(&t0);
-                            o.y = *reinterpret_cast<uint32_t*>(&t1);
-                            o.z = *reinterpret_cast<uint32_t*>(&t2);
-                            o.w = *reinterpret_cast<uint32_t*>(&t3);
-                            *reinterpret_cast<uint4*>(vrow + (((half * 4 + j) ^ (et & 7)) << 4)) = o;
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        float x[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) x[e] = fmaxf(m[j * 8 + e] + bias_r[j * 8 + e], 0.f);
+                        uint4 o;
+                        o.x = pack_bf16x2(x[0], x[1]);
+                        o.y = pack_bf16x2(x[2], x[3]);
+                        o.z = pack_bf16x2(x[4], x[5]);
+                        o.w = pack_bf16x2(x[6], x[7]);
+                        *reinterpret_cast<uint4*>(vrow + (((half * 4 + j) ^ (et & 7)) << 4)) = o;
                     }
                 }
                 // slots 2p and 2p+1 are drained; 2p+2 is re-read by the next pooled row (or drained
@@ -259,12 +271,12 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
                 mbar_arrive(&slot_empty[2 * p]);
                 mbar_arrive(&slot_empty[2 * p + 1]);
                 if (p == POOLED_PER_UNIT - 1) mbar_arrive(&slot_empty[2 * p + 2]);
-                named_bar_sync(1, 128);
+                named_bar_sync(1, EPI_THREADS);
                 // horizontal 3-tap max (cols 2pw-1, 2pw, 2pw+1) and coalesced store of the pooled row
                 if (ph < POOL) {
                     const uint8_t* vr = vbuf + vb * VBUF_BYTES;
                     __nv_bfloat16* orow = out + ((1LL * b * POOL + ph) * POOL) * 64;
-                    for (int task = et; task < POOL * 8; task += 128) {
+                    for (int task = etid; task < POOL * 8; task += EPI_THREADS) {
                         const int pw = task >> 3, c16 = task & 7;
                         const int c0 = 2 * pw;
                         uint4 a = *reinterpret_cast<const uint4*>(vr + c0 * 128 + ((c16 ^ (c0 & 7)) << 4));

@@ -81,6 +81,8 @@ def test_intermediate_activations_resnet50(monkeypatch):
     model = _model(arch, True, "bf16", batch)
     model.forward(x.cuda())
     for name, ref in taps.items():
+        if name == "stem":
+            continue  # the BF16 path fuses conv1+bn+relu+maxpool: the 112x112 map never exists
         got = model.activation(name).cpu().numpy().reshape(batch, -1)
         e = rel_err(got, ref.numpy().reshape(batch, -1))
         assert e < 2e-2, f"{name}: rel err {e:.3e}"

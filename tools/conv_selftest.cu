@@ -68,6 +68,18 @@ int main(int argc, char** argv) {
         {4, 14, 14, 1024, 2048, 1, 2, 0, 0, 0, 0}, // layer4 downsample
         {2, 56, 56, 64, 256, 1, 1, 0, 1, 1, 64},   // forced BN=64
         {32, 56, 56, 64, 256, 1, 1, 0, 1, 1, 0},   // many tiles per CTA (persistence, ring wrap)
+        // CTA-pair kernel (force_bn 1128 / 1256)
+        {1, 16, 16, 64, 256, 1, 1, 0, 0, 0, 1256},     // one pair tile, one k-block
+        {1, 16, 16, 64, 256, 1, 1, 0, 1, 1, 1256},     // + residual + relu
+        {1, 12, 12, 128, 128, 3, 1, 1, 1, 0, 1128},    // M=144: peer half mostly out of range
+        {3, 14, 14, 128, 256, 3, 1, 1, 1, 1, 1256},    // wraps images, residual
+        {2, 28, 28, 256, 512, 1, 2, 0, 0, 0, 1256},    // strided 1x1, 2 n-tiles
+        {2, 28, 28, 128, 128, 3, 2, 1, 1, 0, 1128},    // 3x3 stride 2
+        {4, 7, 7, 512, 2048, 1, 1, 0, 1, 1, 1256},     // M=196 (tail), 8 n-tiles, residual
+        {32, 56, 56, 64, 256, 1, 1, 0, 1, 1, 1256},    // many tiles per pair
+        {32, 28, 28, 128, 128, 3, 1, 1, 1, 0, 1128},   // compute-bound 3x3, BN=128 pairs
+        {32, 14, 14, 256, 256, 3, 1, 1, 1, 0, 1256},   // compute-bound 3x3, BN=256 pairs
+        {32, 14, 14, 256, 256, 3, 1, 1, 1, 0, 128},    // same, single-CTA tiles (for comparison)
     };
 
     int failures = 0;
@@ -185,7 +197,7 @@ int main(int argc, char** argv) {
         const double tflops = plan.flops / (ms * 1e-3) / 1e12;
         printf("[%s] B%d %dx%d Cin%d Cout%d k%d s%d p%d relu%d res%d bn%d grid%d : max_err %.4g (max |ref| %.4g) bad %lld/%zu  %.3f ms  %.1f TFLOP/s %s\n",
                tf32 ? "tf32" : "bf16", s.B, s.H, s.W, s.Cin, s.Cout, s.k, s.stride, s.pad, s.relu,
-               s.res, plan.bn, plan.grid, max_err, max_ref, bad, n_out, ms, tflops,
+               s.res, plan.bn * (plan.ctas == 2 ? -1 : 1), plan.grid, max_err, max_ref, bad, n_out, ms, tflops,
                bad ? "FAIL" : "ok");
         if (bad) {
             ++failures;
