@@ -139,7 +139,7 @@ def run_reference(args):
     unit = "images/s"
     line = {
         "impl": "reference",
-        "metric": f"{args.arch} inference throughput (CPU oracle)",
+        "metric": f"{args.arch} inference images/sec @ batch {args.batch} per GPU",
         "value": value, "unit": unit, "n_gpus": args.gpus, "steps": max(1, min(args.steps, 10)),
         "warmup": max(1, min(args.warmup, 2)), "ms_per_step": med * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -159,7 +159,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--arch", default="resnet50")

@@ -17,11 +17,16 @@
 //   tile i+1. The epilogue adds bias (+ residual, TMA-prefetched into the staging buffer), applies
 //   ReLU, rounds to the activation type and leaves through a swizzled smem tile + TMA store.
 //
-// Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
-//   warp 0 lane 0 : TMA producer (A im2col + B tiled) over an NSTAGE ring
-//   warp 1 lane 0 : tcgen05.mma issuer
+// Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0        : TMA producer (A im2col + B tiled) over an NSTAGE ring — whole warp in the loop,
+//   warp 1        : tcgen05.mma issuer                                      one elected lane issues
 //   warp 2        : TMEM allocator / deallocator
-//   warps 4..7    : epilogue (thread t owns TMEM lane t = output pixel m0 + t)
+//   warp 3        : store warp — TMA stores of finished tiles, residual prefetch, staging recycling
+//   warps 4..11   : epilogue. Warps w and w+4 share TMEM lane quarter (w & 3) = 32 output pixels and
+//                   split the tile's columns, thread t owns one pixel row of the staging tile.
+// The epilogue is the critical path of every layer whose K loop is short (1x1 convs into wide
+// tensors, i.e. most of the HBM traffic of the network): it never waits for a store or issues one —
+// it only signals c_full[buf] and moves on; warp 3 does the rest.
 #pragma once
 #include "sm100_ptx.cuh"
 
@@ -39,6 +44,10 @@ struct ConvGeom {
     int m_tiles, n_tiles;
     int relu;     // apply max(x, 0)
     int has_res;  // add residual[M][Cout] before the ReLU
+    // Tile traversal direction. Consecutive launches of the network alternate it, so that a kernel
+    // starts with the part of its input the previous kernel wrote LAST — the part still in the
+    // 126 MB L2 — instead of the part that has already been evicted to HBM.
+    int reverse;
 };
 
 template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_>
@@ -57,11 +66,13 @@ struct ConvCfg {
     static constexpr int BOX_BYTES = BM * 128;
     static constexpr int CBUF_BYTES = NBOX * BOX_BYTES;
     static constexpr int TMEM_COLS = 2 * BN_;        // two accumulator stages
-    static constexpr int NBAR = 2 * NSTAGE_ + 4 + NCBUF_;
+    static constexpr int NBAR = 2 * NSTAGE_ + 4 + 3 * NCBUF_;
     static constexpr int SMEM_BYTES =
         1024 /*align slack*/ + NSTAGE_ * STAGE_BYTES + NCBUF_ * CBUF_BYTES + NBAR * 8 + 16;
-    static constexpr int THREADS = 256;
+    static constexpr int EPI_WARPS = 8;
+    static constexpr int THREADS = 128 + EPI_WARPS * 32;
     static_assert(NCBUF_ >= 2, "need at least two staging buffers");
+    static_assert((BN_ / 32) % 2 == 0, "the two warps of a lane quarter split the 32-column chunks");
     static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512,
                   "TMEM allocation must be a power of two >= 32 columns");
 };
@@ -77,6 +88,68 @@ __device__ __forceinline__ float round_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
+}
+
+// One 32-column chunk of the accumulator: + bias (+ residual read from the staging row) -> ReLU ->
+// round to the activation type -> write back to the same swizzled staging row.
+template <int ESZ>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint8_t* row, uint32_t c16_base,
+                                               uint32_t swz, const float* __restrict__ bias32,
+                                               int has_res, int relu) {
+    if (ESZ == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4* p16 = reinterpret_cast<uint4*>(row + (((c16_base + j) ^ swz) << 4));
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias32 + j * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias32 + j * 8 + 4));
+            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+            x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            if (has_res) {
+                const uint4 rr = *p16;
+                x[0] += bf16_lo(rr.x); x[1] += bf16_hi(rr.x);
+                x[2] += bf16_lo(rr.y); x[3] += bf16_hi(rr.y);
+                x[4] += bf16_lo(rr.z); x[5] += bf16_hi(rr.z);
+                x[6] += bf16_lo(rr.w); x[7] += bf16_hi(rr.w);
+            }
+            if (relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e], 0.f);
+            }
+            uint4 o;
+            o.x = pack_bf16x2(x[0], x[1]);
+            o.y = pack_bf16x2(x[2], x[3]);
+            o.z = pack_bf16x2(x[4], x[5]);
+            o.w = pack_bf16x2(x[6], x[7]);
+            *p16 = o;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint4* p16 = reinterpret_cast<uint4*>(row + (((c16_base + j) ^ swz) << 4));
+            float x[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(v[j * 4 + e]);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias32 + j * 4));
+            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+            if (has_res) {
+                const float4 rr = *reinterpret_cast<const float4*>(p16);
+                x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
+            }
+            if (relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+            }
+            uint4 o;
+            o.x = __float_as_uint(round_tf32(x[0]));
+            o.y = __float_as_uint(round_tf32(x[1]));
+            o.z = __float_as_uint(round_tf32(x[2]));
+            o.w = __float_as_uint(round_tf32(x[3]));
+            *p16 = o;
+        }
+    }
 }
 
 template <class Cfg>
@@ -100,12 +173,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* empty_bar = bars + NSTAGE;
     uint64_t* tmem_full = bars + 2 * NSTAGE;
     uint64_t* tmem_empty = bars + 2 * NSTAGE + 2;
-    uint64_t* res_full = bars + 2 * NSTAGE + 4;
+    uint64_t* res_full = bars + 2 * NSTAGE + 4;           // residual tile landed in staging buffer
+    uint64_t* c_full = res_full + NCBUF;                  // staging buffer holds a finished tile
+    uint64_t* c_free = c_full + NCBUF;                    // staging buffer may be overwritten
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = g.m_tiles * g.n_tiles;
+    const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                         static_cast<int>(gridDim.x);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -120,9 +197,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 128);
+            mbar_init(&tmem_empty[i], Cfg::EPI_WARPS);
         }
-        for (int i = 0; i < NCBUF; ++i) mbar_init(&res_full[i], 1);
+        for (int i = 0; i < NCBUF; ++i) {
+            mbar_init(&res_full[i], 1);
+            mbar_init(&c_full[i], Cfg::EPI_WARPS);
+            mbar_init(&c_free[i], 1);
+        }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -135,16 +216,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
+    // local tile index -> (m_blk, n_blk)
+    auto tile_coords = [&](int it_local, int& m_blk, int& n_blk) {
+        const int t = blockIdx.x + it_local * gridDim.x;
+        const int tt = g.reverse ? num_tiles - 1 - t : t;
+        n_blk = tt % g.n_tiles;
+        m_blk = tt / g.n_tiles;
+    };
+
     if (warp == 0) {
         // ===================================================== TMA producer
-        // The whole warp walks the loop (uniform control flow keeps barrier addresses and TMA
-        // coordinates in uniform registers); one elected lane issues.
         int stage = 0;
         uint32_t phase = 0;
         const int ohw = g.OH * g.OW;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int n_blk = t % g.n_tiles;
-            const int m_blk = t / g.n_tiles;
+        for (int it = 0; it < my_tiles; ++it) {
+            int m_blk, n_blk;
+            tile_coords(it, m_blk, n_blk);
             const int m0 = m_blk * Cfg::BM;
             const int img = m0 / ohw;
             const int rem = m0 - img * ohw;
@@ -179,8 +266,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        // Whole warp in the loop, one elected lane issues tcgen05.mma / tcgen05.commit. Descriptors
-        // are a per-kernel constant plus (stage offset + 32-byte K step) >> 4 in the address field.
+        // Descriptors are a per-kernel constant plus (stage offset + 32-byte K step) >> 4 in the
+        // address field.
         constexpr uint32_t idesc =
             umma_instr_desc(Cfg::ESZ == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, Cfg::BM, BN);
         const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_stage), 0, 1024, UMMA_LAYOUT_SW128);
@@ -188,8 +275,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             umma_smem_desc(smem_u32(smem_stage) + Cfg::A_BYTES, 0, 1024, UMMA_LAYOUT_SW128);
         int stage = 0;
         uint32_t phase = 0;
-        int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        for (int it = 0; it < my_tiles; ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -220,19 +306,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ===================================================== epilogue
-        const int et = threadIdx.x - 128;  // 0..127 == TMEM lane == row of the tile
-        const int q = warp & 3;            // TMEM lane quarter this warp may access
-        const uint32_t swz = static_cast<uint32_t>(et & 7);
-        const bool leader = (et == 0);
-        const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                             static_cast<int>(gridDim.x);
-
+    } else if (warp == 3) {
+        // ===================================================== store warp
+        // tile it lives in staging buffer it % NCBUF. When its store has been read out of shared
+        // memory the buffer is recycled: with a residual, the residual tile of tile it+NCBUF is
+        // prefetched straight into it (NCBUF tiles ahead of the epilogue); without, c_free is raised.
         auto issue_residual = [&](int it_local) {
-            const int t = blockIdx.x + it_local * gridDim.x;
-            const int n_blk = t % g.n_tiles;
-            const int m_blk = t / g.n_tiles;
+            int m_blk, n_blk;
+            tile_coords(it_local, m_blk, n_blk);
             const int cs = it_local % NCBUF;
             uint8_t* buf = smem_c + cs * Cfg::CBUF_BYTES;
             mbar_expect_tx(&res_full[cs], Cfg::CBUF_BYTES);
@@ -241,107 +322,76 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tma_load_2d(buf + b * Cfg::BOX_BYTES, &tmRes, &res_full[cs],
                             n_blk * BN + b * Cfg::BOX_COLS, m_blk * Cfg::BM);
         };
-        if (leader && g.has_res) {
-            if (my_tiles > 0) issue_residual(0);
-            if (my_tiles > 1) issue_residual(1);
+        if (g.has_res && elect_one()) {
+            for (int i = 0; i < NCBUF && i < my_tiles; ++i) issue_residual(i);
         }
-
-        int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-            const int n_blk = t % g.n_tiles;
-            const int m_blk = t / g.n_tiles;
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
+        __syncwarp();
+        for (int it = 0; it < my_tiles; ++it) {
             const int cs = it % NCBUF;
-            uint8_t* cbuf = smem_c + cs * Cfg::CBUF_BYTES;
-            if (g.has_res) mbar_wait(&res_full[cs], (it / NCBUF) & 1);
-            mbar_wait(&tmem_full[as], aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-            const float* bias_n = bias + n_blk * BN;
-#pragma unroll 1
-            for (int chunk = 0; chunk < BN / 32; ++chunk) {
-                uint32_t v[32];
-                __syncwarp();
-                tmem_ld_32x32(taddr + chunk * 32, v);
-                tmem_ld_wait();
-                const int byte_off = chunk * 32 * Cfg::ESZ;
-                uint8_t* row = cbuf + (byte_off >> 7) * Cfg::BOX_BYTES + et * 128;
-                const uint32_t c16_base = (byte_off & 127) >> 4;
-                if (Cfg::ESZ == 2) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4* p16 = reinterpret_cast<uint4*>(row + (((c16_base + j) ^ swz) << 4));
-                        float x[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]);
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_n + chunk * 32 + j * 8));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_n + chunk * 32 + j * 8 + 4));
-                        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                        x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-                        if (g.has_res) {
-                            const uint4 rr = *p16;
-                            x[0] += bf16_lo(rr.x); x[1] += bf16_hi(rr.x);
-                            x[2] += bf16_lo(rr.y); x[3] += bf16_hi(rr.y);
-                            x[4] += bf16_lo(rr.z); x[5] += bf16_hi(rr.z);
-                            x[6] += bf16_lo(rr.w); x[7] += bf16_hi(rr.w);
-                        }
-                        if (g.relu) {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e], 0.f);
-                        }
-                        uint4 o;
-                        o.x = pack_bf16x2(x[0], x[1]);
-                        o.y = pack_bf16x2(x[2], x[3]);
-                        o.z = pack_bf16x2(x[4], x[5]);
-                        o.w = pack_bf16x2(x[6], x[7]);
-                        *p16 = o;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        uint4* p16 = reinterpret_cast<uint4*>(row + (((c16_base + j) ^ swz) << 4));
-                        float x[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(v[j * 4 + e]);
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_n + chunk * 32 + j * 4));
-                        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                        if (g.has_res) {
-                            const float4 rr = *reinterpret_cast<const float4*>(p16);
-                            x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
-                        }
-                        if (g.relu) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
-                        }
-                        uint4 o;
-                        o.x = __float_as_uint(round_tf32(x[0]));
-                        o.y = __float_as_uint(round_tf32(x[1]));
-                        o.z = __float_as_uint(round_tf32(x[2]));
-                        o.w = __float_as_uint(round_tf32(x[3]));
-                        *p16 = o;
-                    }
-                }
-            }
-            // accumulator drained: hand the TMEM stage back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(&tmem_empty[as]);
-            // publish the staged tile to the async proxy and store it
-            fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (leader) {
+            mbar_wait(&c_full[cs], (it / NCBUF) & 1);
+            if (elect_one()) {
+                int m_blk, n_blk;
+                tile_coords(it, m_blk, n_blk);
+                const uint8_t* cbuf = smem_c + cs * Cfg::CBUF_BYTES;
 #pragma unroll
                 for (int b = 0; b < Cfg::NBOX; ++b)
                     tma_store_2d(&tmOut, cbuf + b * Cfg::BOX_BYTES, n_blk * BN + b * Cfg::BOX_COLS,
                                  m_blk * Cfg::BM);
                 tma_store_commit();
-                // stores of tiles <= it-(NCBUF-2) have finished reading smem: the buffer tile it+2
-                // will use is free, so its residual can be fetched now (one full tile ahead).
-                tma_store_wait_read<NCBUF - 2>();
-                if (g.has_res && it + 2 < my_tiles) issue_residual(it + 2);
+                tma_store_wait_read<0>();  // smem of this buffer has been read: recycle it
+                if (it + NCBUF < my_tiles) {
+                    if (g.has_res)
+                        issue_residual(it + NCBUF);
+                    else
+                        mbar_arrive(&c_free[cs]);
+                }
+            }
+            __syncwarp();
+        }
+        if (elect_one()) tma_store_wait_all<0>();
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================================================== epilogue
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int h = (warp - 4) >> 2;                // which half of the 32-column chunks
+        const int row_in_tile = q * 32 + lane;        // TMEM lane == pixel row of the tile
+        const uint32_t swz = static_cast<uint32_t>(row_in_tile & 7);
+        for (int it = 0; it < my_tiles; ++it) {
+            int m_blk, n_blk;
+            tile_coords(it, m_blk, n_blk);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int cs = it % NCBUF;
+            uint8_t* cbuf = smem_c + cs * Cfg::CBUF_BYTES;
+            if (g.has_res)
+                mbar_wait(&res_full[cs], (it / NCBUF) & 1);
+            else if (it >= NCBUF)
+                mbar_wait(&c_free[cs], ((it / NCBUF) - 1) & 1);
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            const float* bias_n = bias + n_blk * BN;
+#pragma unroll 1
+            for (int chunk = h; chunk < BN / 32; chunk += 2) {
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld_32x32(taddr + chunk * 32, v);
+                tmem_ld_wait();
+                const int byte_off = chunk * 32 * Cfg::ESZ;
+                uint8_t* row = cbuf + (byte_off >> 7) * Cfg::BOX_BYTES + row_in_tile * 128;
+                epilogue_chunk<Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz, bias_n + chunk * 32,
+                                         g.has_res, g.relu);
+            }
+            // accumulator drained by this warp: hand the TMEM stage back; publish the staged rows
+            // to the async proxy and tell the store warp
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&tmem_empty[as]);
+                mbar_arrive(&c_full[cs]);
             }
         }
-        if (leader) tma_store_wait_all<0>();
     }
 
     tc_fence_before();

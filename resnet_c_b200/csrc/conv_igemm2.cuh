@@ -19,10 +19,10 @@
 //                 CTAs; both CTAs' TMA loads complete_tx on it (.cta_group::2 form, peer bit cleared)
 //   empty[s]      one per CTA, released by the leader's multicast tcgen05.commit
 //   tmem_full[a]  one per CTA, multicast commit after the last K block of a tile
-//   tmem_empty[a] in the leader, 8 arrivals: one per epilogue warp of both CTAs (remote arrive)
-//   res_full[c]   per CTA (each CTA prefetches the residual rows it owns)
+//   tmem_empty[a] in the leader, 16 arrivals: one per epilogue warp of both CTAs (remote arrive)
+//   res_full[c] / c_full[c] / c_free[c]   per CTA (each CTA stores / prefetches the rows it owns)
 // The epilogue works on 32 KB sub-tiles (128 rows x 256 bytes) through NCBUF rotating staging
-// buffers, exactly as in the single-CTA kernel.
+// buffers handed to a dedicated store warp, exactly as in the single-CTA kernel.
 #pragma once
 #include "conv_igemm.cuh"
 
@@ -46,10 +46,11 @@ struct Conv2Cfg {
     static constexpr int BOX_BYTES = BM_CTA * 128;
     static constexpr int CBUF_BYTES = 2 * BOX_BYTES;   // 32 KB
     static constexpr int TMEM_COLS = 2 * BN_;
-    static constexpr int NBAR = 2 * NSTAGE_ + 4 + NCBUF_;
+    static constexpr int NBAR = 2 * NSTAGE_ + 4 + 3 * NCBUF_;
     static constexpr int SMEM_BYTES =
         1024 + NSTAGE_ * STAGE_BYTES + NCBUF_ * CBUF_BYTES + NBAR * 8 + 16;
-    static constexpr int THREADS = 256;
+    static constexpr int EPI_WARPS = 8;
+    static constexpr int THREADS = 128 + EPI_WARPS * 32;
     static_assert(NCBUF_ >= 2, "need at least two staging buffers");
     static_assert(BN_ % EPI_N == 0, "tile N must be a multiple of the epilogue sub-tile");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
@@ -142,70 +143,11 @@ __device__ __forceinline__ void mma_tf32_ss_2sm(uint32_t tmem_d, uint64_t adesc,
 
 }  // namespace ptx
 
-// One 32-column chunk of the accumulator: + bias (+ residual read from the staging row) -> ReLU ->
-// round to the activation type -> write back to the same swizzled staging row.
-template <int ESZ>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint8_t* row, uint32_t c16_base,
-                                               uint32_t swz, const float* __restrict__ bias32,
-                                               int has_res, int relu) {
-    if (ESZ == 2) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4* p16 = reinterpret_cast<uint4*>(row + (((c16_base + j) ^ swz) << 4));
-            float x[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias32 + j * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias32 + j * 8 + 4));
-            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-            x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-            if (has_res) {
-                const uint4 rr = *p16;
-                x[0] += bf16_lo(rr.x); x[1] += bf16_hi(rr.x);
-                x[2] += bf16_lo(rr.y); x[3] += bf16_hi(rr.y);
-                x[4] += bf16_lo(rr.z); x[5] += bf16_hi(rr.z);
-                x[6] += bf16_lo(rr.w); x[7] += bf16_hi(rr.w);
-            }
-            if (relu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e], 0.f);
-            }
-            uint4 o;
-            o.x = pack_bf16x2(x[0], x[1]);
-            o.y = pack_bf16x2(x[2], x[3]);
-            o.z = pack_bf16x2(x[4], x[5]);
-            o.w = pack_bf16x2(x[6], x[7]);
-            *p16 = o;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            uint4* p16 = reinterpret_cast<uint4*>(row + (((c16_base + j) ^ swz) << 4));
-            float x[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(v[j * 4 + e]);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias32 + j * 4));
-            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-            if (has_res) {
-                const float4 rr = *reinterpret_cast<const float4*>(p16);
-                x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
-            }
-            if (relu) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
-            }
-            uint4 o;
-            o.x = __float_as_uint(round_tf32(x[0]));
-            o.y = __float_as_uint(round_tf32(x[1]));
-            o.z = __float_as_uint(round_tf32(x[2]));
-            o.w = __float_as_uint(round_tf32(x[3]));
-            *p16 = o;
-        }
-    }
-}
-
 // Tensor maps: tmA im2col over the input (128 pixels x 128 bytes per load), tmB tiled over the packed
 // weights with a box of BN/2 rows, tmOut / tmRes tiled over [M][Cout] with boxes of 128 rows.
+// Warp roles per CTA (384 threads): 0 TMA producer, 1 MMA issuer (leader CTA only), 2 TMEM alloc,
+// 3 store warp (TMA stores, residual prefetch, staging recycling), 4..11 epilogue (two warps per
+// TMEM lane quarter, splitting the 32-column chunks of each sub-tile).
 template <class Cfg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::THREADS, 1)
 conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -229,6 +171,8 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint64_t* tmem_full = bars + 2 * NSTAGE;
     uint64_t* tmem_empty = bars + 2 * NSTAGE + 2;
     uint64_t* res_full = bars + 2 * NSTAGE + 4;
+    uint64_t* c_full = res_full + NCBUF;
+    uint64_t* c_free = c_full + NCBUF;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
 
     const int warp = threadIdx.x >> 5;
@@ -237,6 +181,8 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int pair = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
     const int num_tiles = g.m_tiles * g.n_tiles;       // m_tiles counts 256-pixel tiles here
+    const int my_tiles = (num_tiles - pair + num_pairs - 1) / num_pairs;
+    const int my_items = my_tiles * NSUB;              // (tile, sub-tile) epilogue work items
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -251,9 +197,13 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 8);
+            mbar_init(&tmem_empty[i], 2 * Cfg::EPI_WARPS);
         }
-        for (int i = 0; i < NCBUF; ++i) mbar_init(&res_full[i], 1);
+        for (int i = 0; i < NCBUF; ++i) {
+            mbar_init(&res_full[i], 1);
+            mbar_init(&c_full[i], Cfg::EPI_WARPS);
+            mbar_init(&c_free[i], 1);
+        }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -267,14 +217,30 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
+    // local tile index -> (m_blk, n_blk)
+    auto tile_coords = [&](int it_local, int& m_blk, int& n_blk) {
+        const int t = pair + it_local * num_pairs;
+        const int tt = g.reverse ? num_tiles - 1 - t : t;
+        n_blk = tt % g.n_tiles;
+        m_blk = tt / g.n_tiles;
+    };
+    // epilogue work item -> first output column / first pixel row of this CTA's half
+    auto item_coords = [&](int item, int& col0, int& row0) {
+        const int it_local = item / NSUB, sub = item - it_local * NSUB;
+        int m_blk, n_blk;
+        tile_coords(it_local, m_blk, n_blk);
+        col0 = n_blk * BN + sub * Cfg::EPI_N;
+        row0 = m_blk * Cfg::BM + static_cast<int>(rank) * Cfg::BM_CTA;
+    };
+
     if (warp == 0) {
         // ===================================================== TMA producer (both CTAs)
         int stage = 0;
         uint32_t phase = 0;
         const int ohw = g.OH * g.OW;
-        for (int t = pair; t < num_tiles; t += num_pairs) {
-            const int n_blk = t % g.n_tiles;
-            const int m_blk = t / g.n_tiles;
+        for (int it = 0; it < my_tiles; ++it) {
+            int m_blk, n_blk;
+            tile_coords(it, m_blk, n_blk);
             const int m0 = m_blk * Cfg::BM + static_cast<int>(rank) * Cfg::BM_CTA;
             const int img = m0 / ohw;
             const int rem = m0 - img * ohw;
@@ -318,8 +284,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 umma_smem_desc(smem_u32(smem_stage) + Cfg::A_BYTES, 0, 1024, UMMA_LAYOUT_SW128);
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+            for (int it = 0; it < my_tiles; ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -350,23 +315,8 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ===================================================== epilogue (both CTAs)
-        const int et = threadIdx.x - 128;
-        const int q = warp & 3;
-        const uint32_t swz = static_cast<uint32_t>(et & 7);
-        const bool leader = (et == 0);
-        const int my_tiles = (num_tiles - pair + num_pairs - 1) / num_pairs;
-        const int my_items = my_tiles * NSUB;  // (tile, sub-tile) work items of this CTA
-
-        auto item_coords = [&](int item, int& col0, int& row0) {
-            const int it_local = item / NSUB, sub = item - it_local * NSUB;
-            const int t = pair + it_local * num_pairs;
-            const int n_blk = t % g.n_tiles;
-            const int m_blk = t / g.n_tiles;
-            col0 = n_blk * BN + sub * Cfg::EPI_N;
-            row0 = m_blk * Cfg::BM + static_cast<int>(rank) * Cfg::BM_CTA;
-        };
+    } else if (warp == 3) {
+        // ===================================================== store warp (both CTAs)
         auto issue_residual = [&](int item) {
             int col0, row0;
             item_coords(item, col0, row0);
@@ -376,11 +326,38 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             tma_load_2d(buf, &tmRes, &res_full[cs], col0, row0);
             tma_load_2d(buf + Cfg::BOX_BYTES, &tmRes, &res_full[cs], col0 + Cfg::BOX_COLS, row0);
         };
-        if (leader && g.has_res) {
-            if (my_items > 0) issue_residual(0);
-            if (my_items > 1) issue_residual(1);
+        if (g.has_res && elect_one()) {
+            for (int i = 0; i < NCBUF && i < my_items; ++i) issue_residual(i);
         }
-
+        __syncwarp();
+        for (int item = 0; item < my_items; ++item) {
+            const int cs = item % NCBUF;
+            mbar_wait(&c_full[cs], (item / NCBUF) & 1);
+            if (elect_one()) {
+                int col0, row0;
+                item_coords(item, col0, row0);
+                const uint8_t* cbuf = smem_c + cs * Cfg::CBUF_BYTES;
+                tma_store_2d(&tmOut, cbuf, col0, row0);
+                tma_store_2d(&tmOut, cbuf + Cfg::BOX_BYTES, col0 + Cfg::BOX_COLS, row0);
+                tma_store_commit();
+                tma_store_wait_read<0>();
+                if (item + NCBUF < my_items) {
+                    if (g.has_res)
+                        issue_residual(item + NCBUF);
+                    else
+                        mbar_arrive(&c_free[cs]);
+                }
+            }
+            __syncwarp();
+        }
+        if (elect_one()) tma_store_wait_all<0>();
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================================================== epilogue (both CTAs)
+        const int q = warp & 3;
+        const int h = (warp - 4) >> 2;
+        const int row_in_tile = q * 32 + lane;
+        const uint32_t swz = static_cast<uint32_t>(row_in_tile & 7);
         int item = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int as = it & 1;
@@ -394,36 +371,31 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 item_coords(item, col0, row0);
                 const int cs = item % NCBUF;
                 uint8_t* cbuf = smem_c + cs * Cfg::CBUF_BYTES;
-                if (g.has_res) mbar_wait(&res_full[cs], (item / NCBUF) & 1);
+                if (g.has_res)
+                    mbar_wait(&res_full[cs], (item / NCBUF) & 1);
+                else if (item >= NCBUF)
+                    mbar_wait(&c_free[cs], ((item / NCBUF) - 1) & 1);
 #pragma unroll 1
-                for (int chunk = 0; chunk < Cfg::EPI_N / 32; ++chunk) {
+                for (int chunk = h; chunk < Cfg::EPI_N / 32; chunk += 2) {
                     uint32_t v[32];
                     __syncwarp();
                     tmem_ld_32x32(taddr + sub * Cfg::EPI_N + chunk * 32, v);
                     tmem_ld_wait();
                     const int byte_off = chunk * 32 * Cfg::ESZ;
-                    uint8_t* row = cbuf + (byte_off >> 7) * Cfg::BOX_BYTES + et * 128;
+                    uint8_t* row = cbuf + (byte_off >> 7) * Cfg::BOX_BYTES + row_in_tile * 128;
                     epilogue_chunk<Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz,
                                              bias + col0 + chunk * 32, g.has_res, g.relu);
                 }
-                if (sub == NSUB - 1) {
-                    // accumulator drained: one arrival per epilogue warp of both CTAs, in the leader
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
-                }
+                tc_fence_before();
                 fence_proxy_async_smem();
-                named_bar_sync(1, 128);
-                if (leader) {
-                    tma_store_2d(&tmOut, cbuf, col0, row0);
-                    tma_store_2d(&tmOut, cbuf + Cfg::BOX_BYTES, col0 + Cfg::BOX_COLS, row0);
-                    tma_store_commit();
-                    tma_store_wait_read<NCBUF - 2>();
-                    if (g.has_res && item + 2 < my_items) issue_residual(item + 2);
+                __syncwarp();
+                if (lane == 0) {
+                    // last sub-tile: this warp has drained its part of the accumulator -> tell the leader
+                    if (sub == NSUB - 1) mbar_arrive_leader(&tmem_empty[as]);
+                    mbar_arrive(&c_full[cs]);
                 }
             }
         }
-        if (leader) tma_store_wait_all<0>();
     }
 
     tc_fence_before();

@@ -88,7 +88,8 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
         if (d.Cout % (force_bn - 1000) != 0) return fail(err, errlen, "conv_plan: forced BN does not divide Cout", -6);
         bn = force_bn - 1000;
         ctas = 2;
-    } else if (allow_pair && d.Cout % 128 == 0 && !d.residual && d.ksize * d.ksize * d.Cin > 64) {
+    } else if (allow_pair && d.Cout % 128 == 0 && (!d.residual || getenv("RNB_PAIR_RES")) &&
+               d.ksize * d.ksize * d.Cin > 64) {
         // Measured on B200 (profiles/): pairs win wherever the K loop dominates (3x3 and wide 1x1
         // layers, up to 1.45x); layers whose time is the epilogue's HBM traffic (residual add, or a
         // single K block) are no faster with pairs and slightly slower, so they keep 128-pixel tiles.
@@ -113,6 +114,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     g.n_tiles = d.Cout / bn;
     g.relu = d.relu ? 1 : 0;
     g.has_res = d.residual ? 1 : 0;
+    g.reverse = d.reverse ? 1 : 0;
     plan->bias = d.bias;
     plan->bn = bn;
     plan->esz = esz;

@@ -12,6 +12,7 @@ enum class ActType { BF16 = 2, TF32 = 4 };  // value = bytes per element
 struct ConvDesc {
     int B, H, W, Cin, Cout, ksize, stride, pad;
     bool relu;
+    bool reverse = false;  // walk the tiles last-to-first (see ConvGeom::reverse)
     ActType act;
     const void* in;        // NHWC [B][H][W][Cin]
     const void* weight;    // [Cout][ksize][ksize][Cin], BN-folded, same element type as `in`

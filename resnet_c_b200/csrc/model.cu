@@ -180,6 +180,8 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
     chunk = std::min(chunk_, max_batch_);
     const char* ng = getenv("RNB_NO_GRAPH");
     use_graph = !(ng && atoi(ng) != 0);
+    const char* na = getenv("RNB_NO_ALTERNATE");
+    alternate_tiles = !(na && atoi(na) != 0);
     const char* ka = getenv("RNB_KEEP_ACTIVATIONS");  // parity debugging: never recycle arena blocks
     arena.keep = ka && atoi(ka) != 0;
 
@@ -304,6 +306,9 @@ ChunkPlan* Model::plan_for(int n) {
         ConvDesc d{};
         d.B = n; d.H = in_hw; d.W = in_hw; d.Cin = cw.Cin; d.Cout = cw.Cout;
         d.ksize = cw.k; d.stride = cw.stride; d.pad = cw.pad; d.relu = relu; d.act = act;
+        // Boustrophedon over the launch sequence: every conv walks its tiles in the opposite
+        // direction of the previous one, so it begins where its producer just finished (L2-hot).
+        d.reverse = alternate_tiles && (p.convs.size() & 1) != 0;
         d.in = in; d.weight = cw.w; d.bias = cw.bias; d.residual = res; d.out = out;
         ConvPlan cp;
         const int rc = conv_plan_init(&cp, d, num_sms, 0, err, sizeof(err));
@@ -526,9 +531,14 @@ int Model::forward_host(const float* x, int batch, float* logits, int32_t* top1)
         RNB_CUDA(cudaMalloc(&host_logits_dev, 1ull * max_batch * classes * sizeof(float)));
         RNB_CUDA(cudaMalloc(&host_top1_dev, 1ull * max_batch * sizeof(int32_t)));
     }
-    // Pipeline: every chunk's H2D copy is queued on copy_stream up front; the compute stream waits
-    // per chunk, so chunk i+1 crosses PCIe while chunk i runs.
-    const int nchunks = (batch + chunk - 1) / chunk;
+    // Pipeline: every piece's H2D copy is queued on copy_stream up front; the compute stream waits
+    // per piece, so piece i+1 crosses PCIe while piece i runs. Pieces are at most 64 images (and at
+    // most the engine's chunk): a 256-batch of FP32 input is 154 MB, i.e. as long on PCIe as the whole
+    // forward pass, so overlapping the two matters more than the per-launch efficiency of big pieces.
+    const char* hc_env = getenv("RNB_HOST_CHUNK");
+    int hchunk = hc_env ? atoi(hc_env) : 64;
+    if (hchunk <= 0 || hchunk > chunk) hchunk = chunk;
+    const int nchunks = (batch + hchunk - 1) / hchunk;
     while (static_cast<int>(copy_events.size()) < nchunks) {
         cudaEvent_t e;
         RNB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -537,15 +547,15 @@ int Model::forward_host(const float* x, int batch, float* logits, int32_t* top1)
     static thread_local cudaStream_t compute = nullptr;
     if (!compute) RNB_CUDA(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
     for (int c = 0; c < nchunks; ++c) {
-        const int off = c * chunk;
-        const int n = std::min(chunk, batch - off);
+        const int off = c * hchunk;
+        const int n = std::min(hchunk, batch - off);
         RNB_CUDA(cudaMemcpyAsync(host_x_dev + off * img_elems, x + off * img_elems,
                                  n * img_elems * sizeof(float), cudaMemcpyHostToDevice, copy_stream));
         RNB_CUDA(cudaEventRecord(copy_events[c], copy_stream));
     }
     for (int c = 0; c < nchunks; ++c) {
-        const int off = c * chunk;
-        const int n = std::min(chunk, batch - off);
+        const int off = c * hchunk;
+        const int n = std::min(hchunk, batch - off);
         RNB_CUDA(cudaStreamWaitEvent(compute, copy_events[c], 0));
         int r = forward(host_x_dev + off * img_elems, n, host_logits_dev + 1ull * off * classes,
                         host_top1_dev + off, compute);

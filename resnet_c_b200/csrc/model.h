@@ -95,6 +95,7 @@ struct Model {
     float* scratch_logits = nullptr;  // used when the caller passes logits = NULL
     int last_chunk_n = 0;
     bool use_graph = true;
+    bool alternate_tiles = true;  // consecutive convs walk their tiles in opposite directions (L2 reuse)
 
     ~Model();
     int load(const std::string& arch, int dtype, const std::string& dir, int max_batch, int chunk);
