@@ -182,6 +182,8 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
     use_graph = !(ng && atoi(ng) != 0);
     const char* na = getenv("RNB_NO_ALTERNATE");
     alternate_tiles = !(na && atoi(na) != 0);
+    const char* at = getenv("RNB_AUTOTUNE");
+    autotune = !(at && atoi(at) == 0);
     const char* ka = getenv("RNB_KEEP_ACTIVATIONS");  // parity debugging: never recycle arena blocks
     arena.keep = ka && atoi(ka) != 0;
 
@@ -280,6 +282,9 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
 ChunkPlan* Model::plan_for(int n) {
     auto it = plans.find(n);
     if (it != plans.end()) return &it->second;
+    // A new plan is rare (first use of a batch size). Tuning launches kernels on the arena, so nothing
+    // else may be in flight on it.
+    if (autotune) cudaDeviceSynchronize();
     ChunkPlan p;
     p.n = n;
     const size_t e = esz;
@@ -311,11 +316,60 @@ ChunkPlan* Model::plan_for(int n) {
         d.reverse = alternate_tiles && (p.convs.size() & 1) != 0;
         d.in = in; d.weight = cw.w; d.bias = cw.bias; d.residual = res; d.out = out;
         ConvPlan cp;
-        const int rc = conv_plan_init(&cp, d, num_sms, 0, err, sizeof(err));
+        int rc = conv_plan_init(&cp, d, num_sms, 0, err, sizeof(err));
         if (rc) {
             set_error(err);
             return rc;
         }
+        if (autotune) {
+            // Measure the tile families this layer admits on the buffers it will really use and keep
+            // the fastest (results are cached per layer shape). The heuristic choice above is the
+            // fallback and the first candidate.
+            const std::tuple<int, int, int, int, int, int, int> key{n, in_hw, cw.Cin, cw.Cout, cw.k,
+                                                                    cw.stride, res ? 1 : 0};
+            auto hit = tuned.find(key);
+            int best_force = hit != tuned.end() ? hit->second : -1;
+            if (best_force < 0) {
+                const int cands[4] = {64, 128, 1128, 1256};
+                float best_ms = 1e30f;
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0);
+                cudaEventCreate(&e1);
+                for (int force : cands) {
+                    if (cw.Cout % (force % 1000) != 0) continue;
+                    if (force == 64 && cw.Cout % 128 == 0 && 1LL * n * in_hw * in_hw > 4096) continue;
+                    ConvPlan trial;
+                    if (conv_plan_init(&trial, d, num_sms, force, err, sizeof(err))) continue;
+                    bool ok = true;
+                    for (int i = 0; i < 2 && ok; ++i) ok = conv_plan_launch(trial, cap_stream) == cudaSuccess;
+                    cudaEventRecord(e0, cap_stream);
+                    for (int i = 0; i < 5 && ok; ++i) ok = conv_plan_launch(trial, cap_stream) == cudaSuccess;
+                    cudaEventRecord(e1, cap_stream);
+                    if (cudaStreamSynchronize(cap_stream) != cudaSuccess || !ok) continue;
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    if (ms < best_ms) {
+                        best_ms = ms;
+                        best_force = force;
+                    }
+                }
+                cudaEventDestroy(e0);
+                cudaEventDestroy(e1);
+                if (best_force < 0) best_force = 0;
+                tuned[key] = best_force;
+            }
+            if (best_force > 0) {
+                rc = conv_plan_init(&cp, d, num_sms, best_force, err, sizeof(err));
+                if (rc) {
+                    set_error(err);
+                    return rc;
+                }
+            }
+        }
+        if (getenv("RNB_VERBOSE"))
+            fprintf(stderr, "rnb plan: conv#%zu n=%d %dx%d %d->%d k%d s%d res=%d : %s tile %dx%d grid %d\n",
+                    p.convs.size(), n, in_hw, in_hw, cw.Cin, cw.Cout, cw.k, cw.stride, res ? 1 : 0,
+                    cp.ctas == 2 ? "pair" : "single", cp.ctas == 2 ? 256 : 128, cp.bn, cp.grid);
         p.convs.push_back(cp);
         return 0;
     };

@@ -96,6 +96,8 @@ struct Model {
     int last_chunk_n = 0;
     bool use_graph = true;
     bool alternate_tiles = true;  // consecutive convs walk their tiles in opposite directions (L2 reuse)
+    bool autotune = true;         // time the admissible tile families per layer shape at plan time
+    std::map<std::tuple<int, int, int, int, int, int, int>, int> tuned;  // layer shape -> force_bn code
 
     ~Model();
     int load(const std::string& arch, int dtype, const std::string& dir, int max_batch, int chunk);
