@@ -53,6 +53,9 @@ cudaError_t conv_kernels_init() {
     if ((e = set_smem2<Cfg2Bf16N128>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Tf32N256>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Tf32N128>()) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_halo_kernel<HaloCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  HaloCfg::SMEM_BYTES)) != cudaSuccess)
+        return e;
     return cudaSuccess;
 }
 
@@ -61,9 +64,48 @@ static int fail(char* err, int errlen, const char* msg, int code) {
     return code ? code : -1;
 }
 
+bool conv_plan_halo_ok(const ConvDesc& d) {
+    return d.act == ActType::BF16 && d.ksize == 3 && d.stride == 1 && d.pad == 1 && d.Cin == 64 &&
+           d.Cout == 64 && !d.residual && d.W <= 62 && d.W >= 8 && d.H % 2 == 0;
+}
+
+static int halo_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, char* err, int errlen) {
+    if (!conv_plan_halo_ok(d)) return fail(err, errlen, "conv_plan: layer is not eligible for the halo kernel", -7);
+    plan->halo = 1;
+    plan->bn = 64;
+    plan->esz = 2;
+    plan->ctas = 1;
+    plan->bias = d.bias;
+    HaloGeom& g = plan->hg;
+    g.N = d.B; g.H = d.H; g.W = d.W;
+    g.rows_per_img = d.H / 2;
+    g.tiles = d.B * g.rows_per_img;
+    g.relu = d.relu ? 1 : 0;
+    g.reverse = d.reverse ? 1 : 0;
+    plan->grid = g.tiles < num_sms ? g.tiles : num_sms;
+    const double M = 1.0 * d.B * d.H * d.W;
+    plan->flops = 2.0 * M * 64 * 576;
+    plan->bytes = 2.0 * M * 64 * 2 + 64.0 * 576 * 2 + 256;
+    const uint64_t dims[4] = {64, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
+    const uint64_t strides[3] = {128, 128ull * d.W, 128ull * d.W * d.H};
+    const uint32_t box_in[4] = {64, 64, 2, 1};
+    const uint32_t box_out[4] = {64, static_cast<uint32_t>(d.W), 1, 1};
+    int r;
+    if ((r = make_tiled_nd(&plan->tmA, TmDtype::BF16, d.in, 4, dims, strides, box_in, true)) != 0)
+        return fail(err, errlen, "conv_plan: halo input tensor map failed", r);
+    if ((r = make_tiled_2d(&plan->tmB, TmDtype::BF16, d.weight, 64, 576, 64)) != 0)
+        return fail(err, errlen, "conv_plan: halo weight tensor map failed", r);
+    if ((r = make_tiled_nd(&plan->tmOut, TmDtype::BF16, d.out, 4, dims, strides, box_out, true)) != 0)
+        return fail(err, errlen, "conv_plan: halo output tensor map failed", r);
+    plan->tmRes = plan->tmOut;
+    return 0;
+}
+
 int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn, char* err,
                    int errlen) {
     memset(plan, 0, sizeof(*plan));
+    if (force_bn == 3064 || (force_bn == 0 && conv_plan_halo_ok(d) && !getenv("RNB_NO_HALO")))
+        return halo_plan_init(plan, d, num_sms, err, errlen);
     const int esz = static_cast<int>(d.act);
     const int bk = 128 / esz;
     if (d.ksize != 1 && d.ksize != 3) return fail(err, errlen, "conv_plan: ksize must be 1 or 3", -2);
@@ -161,6 +203,11 @@ static cudaError_t launch2(const ConvPlan& p, cudaStream_t stream) {
 }
 
 cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
+    if (p.halo) {
+        conv3x3_halo_kernel<HaloCfg><<<p.grid, HaloCfg::THREADS, HaloCfg::SMEM_BYTES, stream>>>(
+            p.tmA, p.tmB, p.tmOut, p.bias, p.hg);
+        return cudaGetLastError();
+    }
     if (p.ctas == 2) {
         if (p.esz == 2) return p.bn == 256 ? launch2<Cfg2Bf16N256>(p, stream) : launch2<Cfg2Bf16N128>(p, stream);
         return p.bn == 256 ? launch2<Cfg2Tf32N256>(p, stream) : launch2<Cfg2Tf32N128>(p, stream);

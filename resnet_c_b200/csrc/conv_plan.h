@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "conv3x3_halo.cuh"
 #include "conv_igemm.cuh"
 
 namespace rnb {
@@ -27,12 +28,17 @@ struct ConvPlan {
     const float* bias;
     int bn;       // tile N
     int ctas;     // 1 = single-CTA 128-pixel tiles, 2 = CTA-pair 256-pixel tiles (cta_group::2)
+    int halo;     // 1 = conv3x3_halo_kernel (3x3/1, 64->64, bf16): tmA/tmOut are 4-D tiled maps, geometry in hg
+    HaloGeom hg;
     int esz;      // element bytes
     int grid;     // persistent CTAs
     double flops;  // 2*M*N*K
     double bytes;  // algorithmic HBM bytes: input + weights + bias (+ residual) read once, output written once
 };
 
+// force_bn codes: 0 = heuristic, 64 / 128 = single-CTA tiles, 1128 / 1256 = CTA-pair tiles,
+// 3064 = halo-resident 3x3 kernel (only where conv_plan_halo_ok()).
+bool conv_plan_halo_ok(const ConvDesc& d);
 // Builds the tensor maps and tile geometry. Returns 0 on success; on failure writes a message to
 // `err` (if non-null, at most errlen bytes).
 int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn, char* err,

@@ -80,6 +80,12 @@ int main(int argc, char** argv) {
         {32, 28, 28, 128, 128, 3, 1, 1, 1, 0, 1128},   // compute-bound 3x3, BN=128 pairs
         {32, 14, 14, 256, 256, 3, 1, 1, 1, 0, 1256},   // compute-bound 3x3, BN=256 pairs
         {32, 14, 14, 256, 256, 3, 1, 1, 1, 0, 128},    // same, single-CTA tiles (for comparison)
+        // halo-resident 3x3 kernel (force_bn 3064)
+        {1, 8, 8, 64, 64, 3, 1, 1, 0, 0, 3064},        // small: 4 tiles, borders everywhere
+        {2, 56, 56, 64, 64, 3, 1, 1, 1, 0, 3064},      // layer1 conv2 shape
+        {3, 28, 28, 64, 64, 3, 1, 1, 1, 0, 3064},      // narrower rows
+        {32, 56, 56, 64, 64, 3, 1, 1, 1, 0, 3064},     // many tiles per CTA
+        {32, 56, 56, 64, 64, 3, 1, 1, 1, 0, 64},       // same through the im2col kernel (for comparison)
     };
 
     int failures = 0;
