@@ -134,6 +134,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    griddep_launch_dependents();  // see conv_igemm.cuh
+    griddep_wait();
 
     auto tile_coords = [&](int it_local, int& img, int& h0) {
         const int t = blockIdx.x + it_local * gridDim.x;

@@ -215,6 +215,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // Everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail;
+    // from here on we touch tensors it produced (or still reads), so wait for it to finish.
+    griddep_launch_dependents();
+    griddep_wait();
 
     // local tile index -> (m_blk, n_blk)
     auto tile_coords = [&](int it_local, int& m_blk, int& n_blk) {

@@ -216,6 +216,8 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    griddep_launch_dependents();  // see conv_igemm.cuh
+    griddep_wait();
 
     // local tile index -> (m_blk, n_blk)
     auto tile_coords = [&](int it_local, int& m_blk, int& n_blk) {

@@ -188,25 +188,46 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     return 0;
 }
 
+// Every conv kernel is launched with programmatic stream serialization (PDL): its prologue may run
+// while the previous kernel of the stream drains; the kernels call griddepcontrol.wait before they
+// touch global tensors. RNB_NO_PDL=1 turns the attribute off (plain stream order).
+static bool pdl_enabled() {
+    static const bool on = !(getenv("RNB_NO_PDL") && atoi(getenv("RNB_NO_PDL")) != 0);
+    return on;
+}
+
+template <class Kernel, class... Args>
+static cudaError_t launch_pdl(Kernel kernel, int grid, int threads, int smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <class Cfg>
 static cudaError_t launch(const ConvPlan& p, cudaStream_t stream) {
-    conv_igemm_kernel<Cfg><<<p.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(
-        p.tmA, p.tmB, p.tmOut, p.tmRes, p.bias, p.g);
-    return cudaGetLastError();
+    return launch_pdl(conv_igemm_kernel<Cfg>, p.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, p.tmA, p.tmB,
+                      p.tmOut, p.tmRes, p.bias, p.g);
 }
 
 template <class Cfg>
 static cudaError_t launch2(const ConvPlan& p, cudaStream_t stream) {
-    conv_igemm2_kernel<Cfg><<<p.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(
-        p.tmA, p.tmB, p.tmOut, p.tmRes, p.bias, p.g);
-    return cudaGetLastError();
+    return launch_pdl(conv_igemm2_kernel<Cfg>, p.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, p.tmA, p.tmB,
+                      p.tmOut, p.tmRes, p.bias, p.g);
 }
 
 cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
     if (p.halo) {
-        conv3x3_halo_kernel<HaloCfg><<<p.grid, HaloCfg::THREADS, HaloCfg::SMEM_BYTES, stream>>>(
-            p.tmA, p.tmB, p.tmOut, p.bias, p.hg);
-        return cudaGetLastError();
+        return launch_pdl(conv3x3_halo_kernel<HaloCfg>, p.grid, HaloCfg::THREADS, HaloCfg::SMEM_BYTES, stream,
+                          p.tmA, p.tmB, p.tmOut, p.bias, p.hg);
     }
     if (p.ctas == 2) {
         if (p.esz == 2) return p.bn == 256 ? launch2<Cfg2Bf16N256>(p, stream) : launch2<Cfg2Bf16N128>(p, stream);

@@ -203,6 +203,17 @@ __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Programmatic dependent launch: `griddep_launch_dependents` lets the next kernel of the stream start
+// its prologue on SMs this grid has vacated; `griddep_wait` blocks until every kernel this one depends
+// on has completed and its memory is visible. Both are no-ops for a kernel launched without the
+// programmatic-stream-serialization attribute.
+__device__ __forceinline__ void griddep_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // Named barrier among a subset of the CTA's warps.
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
