@@ -22,6 +22,13 @@ using Cfg2Bf16N256 = Conv2Cfg<256, 2, 4, 3>;
 using Cfg2Bf16N128 = Conv2Cfg<128, 2, 5, 3>;
 using Cfg2Tf32N256 = Conv2Cfg<256, 4, 4, 3>;
 using Cfg2Tf32N128 = Conv2Cfg<128, 4, 5, 3>;
+// deep variants (bf16 only): one/two more pipeline stages, two staging buffers
+using CfgBf16N128D = ConvCfg<128, 2, 5, 2>;
+using Cfg2Bf16N256D = Conv2Cfg<256, 2, 5, 2>;
+using Cfg2Bf16N128D = Conv2Cfg<128, 2, 6, 2>;
+static_assert(CfgBf16N128D::SMEM_BYTES <= 232448, "smem budget");
+static_assert(Cfg2Bf16N256D::SMEM_BYTES <= 232448, "smem budget");
+static_assert(Cfg2Bf16N128D::SMEM_BYTES <= 232448, "smem budget");
 static_assert(Cfg2Bf16N256::SMEM_BYTES <= 232448, "smem budget");
 static_assert(Cfg2Bf16N128::SMEM_BYTES <= 232448, "smem budget");
 static_assert(Cfg2Tf32N256::SMEM_BYTES <= 232448, "smem budget");
@@ -53,6 +60,9 @@ cudaError_t conv_kernels_init() {
     if ((e = set_smem2<Cfg2Bf16N128>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Tf32N256>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Tf32N128>()) != cudaSuccess) return e;
+    if ((e = set_smem<CfgBf16N128D>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Bf16N256D>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Bf16N128D>()) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_halo_kernel<HaloCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   HaloCfg::SMEM_BYTES)) != cudaSuccess)
         return e;
@@ -106,6 +116,11 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     memset(plan, 0, sizeof(*plan));
     if (force_bn == 3064 || (force_bn == 0 && conv_plan_halo_ok(d) && !getenv("RNB_NO_HALO")))
         return halo_plan_init(plan, d, num_sms, err, errlen);
+    // +10000: "deep" variant of a tile family — one or two more shared-memory stages in flight paid
+    // for with one staging buffer less (for layers whose K loop, not whose epilogue, is the bottleneck)
+    const int deep = force_bn >= 10000 ? 1 : 0;
+    if (deep) force_bn -= 10000;
+    plan->deep = deep;
     const int esz = static_cast<int>(d.act);
     const int bk = 128 / esz;
     if (d.ksize != 1 && d.ksize != 3) return fail(err, errlen, "conv_plan: ksize must be 1 or 3", -2);
@@ -228,6 +243,10 @@ cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
     if (p.halo) {
         return launch_pdl(conv3x3_halo_kernel<HaloCfg>, p.grid, HaloCfg::THREADS, HaloCfg::SMEM_BYTES, stream,
                           p.tmA, p.tmB, p.tmOut, p.bias, p.hg);
+    }
+    if (p.deep && p.esz == 2) {
+        if (p.ctas == 2) return p.bn == 256 ? launch2<Cfg2Bf16N256D>(p, stream) : launch2<Cfg2Bf16N128D>(p, stream);
+        if (p.bn == 128) return launch<CfgBf16N128D>(p, stream);
     }
     if (p.ctas == 2) {
         if (p.esz == 2) return p.bn == 256 ? launch2<Cfg2Bf16N256>(p, stream) : launch2<Cfg2Bf16N128>(p, stream);
