@@ -49,24 +49,51 @@ constexpr int EPI_THREADS = 256;                 // 8 epilogue warps
 constexpr int STEM_TC_THREADS = 128 + EPI_THREADS;
 
 // x [B,3,224,224] fp32 -> xp [B][235][232][4] bf16, zero border and zero 4th channel.
-__global__ void stem_pack_kernel(const float* __restrict__ x, uint2* __restrict__ xp, int B) {
-    const int64_t total = 1LL * B * PAD_H * PAD_W;
+// One thread per group of 4 padded pixels (PAD_W = 232 = 58 groups): interior groups read one float4
+// from each colour plane (image column 4g-4 .. 4g-1 for group g >= 1; 224 = 56 groups) and write 32 B.
+__global__ void stem_pack_kernel(const float* __restrict__ x, uint4* __restrict__ xp, int B) {
+    constexpr int GROUPS = PAD_W / 4;  // 58
+    const int64_t total = 1LL * B * PAD_H * GROUPS;
     for (int64_t i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
          i += 1LL * gridDim.x * blockDim.x) {
-        const int pw = static_cast<int>(i % PAD_W);
-        int64_t t = i / PAD_W;
+        const int gidx = static_cast<int>(i % GROUPS);
+        int64_t t = i / GROUPS;
         const int pr = static_cast<int>(t % PAD_H);
         const int b = static_cast<int>(t / PAD_H);
-        const int ih = pr - 5, iw = pw - 3;
-        uint2 v = make_uint2(0u, 0u);
-        if (ih >= 0 && ih < IMG && iw >= 0 && iw < IMG) {
-            const float* p = x + (1LL * b * 3 * IMG + ih) * IMG + iw;
-            const __nv_bfloat162 rg = __floats2bfloat162_rn(__ldg(p), __ldg(p + IMG * IMG));
-            const __nv_bfloat162 b0 = __floats2bfloat162_rn(__ldg(p + 2 * IMG * IMG), 0.f);
-            v.x = *reinterpret_cast<const uint32_t*>(&rg);
-            v.y = *reinterpret_cast<const uint32_t*>(&b0);
+        const int ih = pr - 5;
+        float r[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f}, bl[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ih >= 0 && ih < IMG) {
+            // padded pixels 4g..4g+3 are image columns 4g-3..4g: not 16-byte aligned, so read the two
+            // aligned float4s that cover them (columns 4g-4..4g-1 and 4g..4g+3) and pick
+            const float* row = x + (1LL * b * 3 * IMG + ih) * IMG;
+            const int c0 = 4 * gidx - 4;
+            float lo[3][4], hi[3][4];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* pl = row + 1LL * c * IMG * IMG;
+                const float4 a = (c0 >= 0 && c0 < IMG) ? __ldg(reinterpret_cast<const float4*>(pl + c0))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 d = (c0 + 4 < IMG) ? __ldg(reinterpret_cast<const float4*>(pl + c0 + 4))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                lo[c][0] = a.x; lo[c][1] = a.y; lo[c][2] = a.z; lo[c][3] = a.w;
+                hi[c][0] = d.x; hi[c][1] = d.y; hi[c][2] = d.z; hi[c][3] = d.w;
+            }
+            // image column of padded pixel 4g+j is 4g+j-3 = c0 + 1 + j
+            r[0] = lo[0][1]; r[1] = lo[0][2]; r[2] = lo[0][3]; r[3] = hi[0][0];
+            g[0] = lo[1][1]; g[1] = lo[1][2]; g[2] = lo[1][3]; g[3] = hi[1][0];
+            bl[0] = lo[2][1]; bl[1] = lo[2][2]; bl[2] = lo[2][3]; bl[3] = hi[2][0];
         }
-        xp[i] = v;
+        uint4 o0, o1;
+        auto px = [&](int j, uint32_t& a, uint32_t& c) {
+            const __nv_bfloat162 rg = __floats2bfloat162_rn(r[j], g[j]);
+            const __nv_bfloat162 b0 = __floats2bfloat162_rn(bl[j], 0.f);
+            a = *reinterpret_cast<const uint32_t*>(&rg);
+            c = *reinterpret_cast<const uint32_t*>(&b0);
+        };
+        px(0, o0.x, o0.y); px(1, o0.z, o0.w); px(2, o1.x, o1.y); px(3, o1.z, o1.w);
+        uint4* dst = xp + 2 * i;
+        dst[0] = o0;
+        dst[1] = o1;
     }
 }
 
@@ -224,6 +251,8 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
         for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
             const int b = u / UNITS_PER_IMG, v = u - b * UNITS_PER_IMG;
             const uint32_t par = it & 1;
+            float carry[32];
+#pragma unroll
             for (int p = 0; p < POOLED_PER_UNIT; ++p) {
                 const int ph = v * POOLED_PER_UNIT + p;
                 // slots 2p, 2p+1, 2p+2 hold conv rows oh = 6v - 1 + slot
@@ -234,9 +263,12 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
                 // vertical max over the three conv rows of this pooled row. max_k(x_k + b) =
                 // max_k(x_k) + b and ReLU output is >= 0, so a missing row (-1 or 112) is simply
                 // left out; the middle row 2*ph always exists for a stored pooled row.
+                // TMEM reads are the scarce resource of this epilogue (64 B/clk/SM): the conv row shared
+                // by two consecutive pooled rows (slot 2p+2 == slot 2(p+1)) is read once and carried in
+                // registers.
                 float m[32];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
+                for (int k = (p == 0 ? 0 : 1); k < 3; ++k) {
                     const int oh = 6 * v - 1 + 2 * p + k;
                     uint32_t raw[32];
                     __syncwarp();
@@ -245,9 +277,18 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
                     if (k == 0) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) m[i] = oh >= 0 ? __uint_as_float(raw[i]) : -INFINITY;
-                    } else if (oh < CONV) {
+                    } else {
+                        const bool valid = oh < CONV;
+                        if (k == 1 && p > 0) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) m[i] = fmaxf(m[i], __uint_as_float(raw[i]));
+                            for (int i = 0; i < 32; ++i) m[i] = carry[i];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float x = valid ? __uint_as_float(raw[i]) : -INFINITY;
+                            m[i] = fmaxf(m[i], x);
+                            if (k == 2) carry[i] = x;
+                        }
                     }
                 }
                 if (et < CONV) {
@@ -326,11 +367,11 @@ cudaError_t stem_tc_init() {
 cudaError_t launch_stem_tc_part(int part, const float* x, void* xp, const void* wk, const float* bias,
                                 void* out, int B, cudaStream_t s) {
     if (part == 0) {
-        const int64_t total = 1LL * B * PAD_H * PAD_W;
+        const int64_t total = 1LL * B * PAD_H * (PAD_W / 4);
         int64_t blocks = (total + 255) / 256;
         const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
         if (blocks > cap) blocks = cap;
-        stem_pack_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(x, static_cast<uint2*>(xp), B);
+        stem_pack_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(x, static_cast<uint4*>(xp), B);
     } else {
         const int units = B * UNITS_PER_IMG;
         const int grid = units < num_sms() ? units : num_sms();

@@ -58,26 +58,27 @@ __global__ void avgpool_nhwc_kernel(const T* __restrict__ x, float* __restrict__
 }
 
 // logits[b][o] = sum_k pooledT[k][b] * w[o][k] + bias[o].
-// Block = FC_OUT classes x 32 images; its FC_WARPS warps split K (warp w takes k = w, w+FC_WARPS, ..)
-// so ~1000 blocks x 8 warps keep every SM busy; lane = image, so a warp reads 128 contiguous bytes
-// of pooledT per k while the 8 class weights for that k are two broadcast LDS.128. Partial sums
-// meet in shared memory. FP32 FMA on CUDA cores: the layer is 2 MMAC per image.
-constexpr int FC_OUT = 8;
+// Block = 16 classes x 64 images; thread = 2 images x 16 classes (32 FP32 accumulators), so one k costs
+// 2 coalesced loads of pooledT + 4 broadcast LDS.128 of weights for 32 FMAs (the first version, 1 image
+// x 8 classes, was instruction-issue-bound at 14 instructions per 8 FMAs). The block's 8 warps split K
+// (warp w takes k = w, w+8, ..) and meet in shared memory with a fixed summation order.
+// FP32 FMA on CUDA cores: the layer is 2 MMAC per image.
+constexpr int FC_OUT = 16;
+constexpr int FC_IMG = 64;       // images per block (2 per lane)
 constexpr int FC_WARPS = 8;
 constexpr int FC_THREADS = FC_WARPS * 32;
-constexpr int FC_KCHUNK = 1024;  // weights staged per pass: 1024 x 8 x 4 B = 32 KB
+constexpr int FC_KCHUNK = 512;   // weights staged per pass: 512 x 16 x 4 B = 32 KB
 __global__ void __launch_bounds__(FC_THREADS)
 fc_kernel(const float* __restrict__ pooledT, const float* __restrict__ w, const float* __restrict__ bias,
           float* __restrict__ out, int n, int C, int classes) {
-    __shared__ __align__(16) float ws[FC_KCHUNK][FC_OUT];
-    __shared__ float part[FC_WARPS][32][FC_OUT + 1];
+    __shared__ __align__(16) float ws[FC_KCHUNK][FC_OUT];   // 32 KB, later reused for the partial sums
     const int o0 = blockIdx.x * FC_OUT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y * 32 + lane;
-    const bool active = b < n;
-    float acc[FC_OUT];
+    const int b0 = blockIdx.y * FC_IMG + lane, b1 = b0 + 32;
+    const bool act0 = b0 < n, act1 = b1 < n;
+    float acc0[FC_OUT], acc1[FC_OUT];
 #pragma unroll
-    for (int j = 0; j < FC_OUT; ++j) acc[j] = 0.f;
+    for (int j = 0; j < FC_OUT; ++j) acc0[j] = acc1[j] = 0.f;
     for (int k0 = 0; k0 < C; k0 += FC_KCHUNK) {
         const int kc = min(FC_KCHUNK, C - k0);
         __syncthreads();
@@ -87,31 +88,51 @@ fc_kernel(const float* __restrict__ pooledT, const float* __restrict__ w, const 
             ws[k][j] = o < classes ? __ldg(w + 1LL * o * C + k0 + k) : 0.f;
         }
         __syncthreads();
-        if (active) {
-            const float* xp = pooledT + 1LL * k0 * n + b;
-#pragma unroll 8
-            for (int k = warp; k < kc; k += FC_WARPS) {
-                const float xv = __ldg(xp + 1LL * k * n);
-                const float4 w0 = *reinterpret_cast<const float4*>(&ws[k][0]);
-                const float4 w1 = *reinterpret_cast<const float4*>(&ws[k][4]);
-                acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
-                acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-                acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
-                acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+        const float* xp = pooledT + 1LL * k0 * n;
+#pragma unroll 16
+        for (int k = warp; k < kc; k += FC_WARPS) {
+            const float x0 = act0 ? __ldg(xp + 1LL * k * n + b0) : 0.f;
+            const float x1 = act1 ? __ldg(xp + 1LL * k * n + b1) : 0.f;
+#pragma unroll
+            for (int q = 0; q < FC_OUT / 4; ++q) {
+                const float4 wv = *reinterpret_cast<const float4*>(&ws[k][q * 4]);
+                acc0[q * 4 + 0] = fmaf(x0, wv.x, acc0[q * 4 + 0]); acc1[q * 4 + 0] = fmaf(x1, wv.x, acc1[q * 4 + 0]);
+                acc0[q * 4 + 1] = fmaf(x0, wv.y, acc0[q * 4 + 1]); acc1[q * 4 + 1] = fmaf(x1, wv.y, acc1[q * 4 + 1]);
+                acc0[q * 4 + 2] = fmaf(x0, wv.z, acc0[q * 4 + 2]); acc1[q * 4 + 2] = fmaf(x1, wv.z, acc1[q * 4 + 2]);
+                acc0[q * 4 + 3] = fmaf(x0, wv.w, acc0[q * 4 + 3]); acc1[q * 4 + 3] = fmaf(x1, wv.w, acc1[q * 4 + 3]);
             }
         }
     }
+    // partial sums: part[warp][image 0..63][class 0..15] (+1 pad) = 8 x 64 x 17 floats = 34.8 KB > ws,
+    // so reduce in two halves of 4 warps through the 32 KB of ws: [4][64][16] floats = 16 KB per half
+    float* part = &ws[0][0];
+    // this thread finally owns the outputs (image = tid >> 2 (0..63), classes 4*(tid&3)..+3)
+    float res[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int half = 0; half < 2; ++half) {
+        __syncthreads();
+        if ((warp >> 2) == half) {
+            const int wl = warp & 3;
 #pragma unroll
-    for (int j = 0; j < FC_OUT; ++j) part[warp][lane][j] = acc[j];
-    __syncthreads();
-    // 32 images x 8 classes = 256 outputs, one per thread; fixed summation order over the warps
-    const int ol = threadIdx.x & 7, bl = threadIdx.x >> 3;
-    const int o = o0 + ol, bo = blockIdx.y * 32 + bl;
-    if (o < classes && bo < n) {
-        float sum = 0.f;
+            for (int j = 0; j < FC_OUT; ++j) {
+                part[(wl * FC_IMG + lane) * FC_OUT + j] = acc0[j];
+                part[(wl * FC_IMG + lane + 32) * FC_OUT + j] = acc1[j];
+            }
+        }
+        __syncthreads();
+        const int img = threadIdx.x >> 2, c4 = (threadIdx.x & 3) * 4;
 #pragma unroll
-        for (int wi = 0; wi < FC_WARPS; ++wi) sum += part[wi][bl][ol];
-        out[1LL * bo * classes + o] = sum + (bias ? __ldg(bias + o) : 0.f);
+        for (int wl = 0; wl < 4; ++wl) {
+            const float4 v = *reinterpret_cast<const float4*>(&part[(wl * FC_IMG + img) * FC_OUT + c4]);
+            res[0] += v.x; res[1] += v.y; res[2] += v.z; res[3] += v.w;
+        }
+    }
+    const int img = blockIdx.y * FC_IMG + (threadIdx.x >> 2);
+    if (img < n) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = o0 + (threadIdx.x & 3) * 4 + j;
+            if (o < classes) out[1LL * img * classes + o] = res[j] + (bias ? __ldg(bias + o) : 0.f);
+        }
     }
 }
 
@@ -151,7 +172,7 @@ cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, int B, int HW, in
 
 cudaError_t launch_fc(const float* pooledT, const float* w, const float* bias, float* logits, int B,
                       int C, int classes, cudaStream_t s) {
-    dim3 grid((classes + FC_OUT - 1) / FC_OUT, (B + 31) / 32);
+    dim3 grid((classes + FC_OUT - 1) / FC_OUT, (B + FC_IMG - 1) / FC_IMG);
     fc_kernel<<<grid, FC_THREADS, 0, s>>>(pooledT, w, bias, logits, B, C, classes);
     return cudaGetLastError();
 }
