@@ -74,6 +74,7 @@ int rnb_init(int device) {
     g_num_sms = prop.multiProcessorCount;
     API_CUDA(conv_kernels_init());
     API_CUDA(stem_tc_init());
+    API_CUDA(stem_tc_split_init());
     g_device = device;
     set_error("");
     return RNB_OK;
@@ -264,17 +265,18 @@ int rnb_stem_forward(const float* x_dev, const float* w_dev, const float* bn_wei
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int OH = (6 + H - 7) / 2 + 1, OW = (6 + W - 7) / 2 + 1;
     const int PH = (2 + OH - 3) / 2 + 1, PW = (2 + OW - 3) / 2 + 1;
-    if (esz == 2 && H == 224 && W == 224) {
-        // tensor-core stem (stem_tc.cu)
+    if (H == 224 && W == 224 && !getenv("RNB_NO_STEM_TC")) {
+        // tensor-core stem (stem_tc.cu for BF16, stem_tc_split.cu for TF32)
         void *wk = nullptr, *xp = nullptr, *pool_tc = nullptr;
         float* bias_tc = nullptr;
-        API_CUDA(cudaMallocAsync(&wk, stem_tc_packed_weight_bytes(), s));
+        API_CUDA(cudaMallocAsync(&wk, stem_any_weight_bytes(esz), s));
         API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&bias_tc), 64 * sizeof(float), s));
-        API_CUDA(cudaMallocAsync(&xp, stem_tc_packed_input_bytes(B), s));
+        API_CUDA(cudaMallocAsync(&xp, stem_any_input_bytes(esz, B), s));
         API_CUDA(cudaMallocAsync(&pool_tc, 1ull * B * PH * PW * 64 * esz, s));
-        API_CUDA(launch_stem_tc_pack_weights(w_dev, bn_weight_dev, bn_bias_dev, bn_mean_dev, bn_var_dev, wk,
-                                             bias_tc, s));
-        API_CUDA(launch_stem_tc(x_dev, xp, wk, bias_tc, pool_tc, B, s));
+        API_CUDA(launch_stem_any_pack_weights(esz, w_dev, bn_weight_dev, bn_bias_dev, bn_mean_dev, bn_var_dev, wk,
+                                              bias_tc, s));
+        API_CUDA(launch_stem_any_part(esz, 0, x_dev, xp, wk, bias_tc, pool_tc, B, s));
+        API_CUDA(launch_stem_any_part(esz, 1, x_dev, xp, wk, bias_tc, pool_tc, B, s));
         API_CUDA(launch_nhwc_to_nchw(pool_tc, out_dev, B, 64, PH * PW, esz, s));
         API_CUDA(cudaFreeAsync(wk, s));
         API_CUDA(cudaFreeAsync(bias_tc, s));

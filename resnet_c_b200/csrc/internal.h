@@ -62,6 +62,35 @@ cudaError_t launch_stem_tc(const float* x, void* xp, const void* wk, const float
 cudaError_t launch_stem_tc_part(int part, const float* x, void* xp, const void* wk, const float* bias,
                                 void* out, int B, cudaStream_t s);
 
+// ---- tensor-core stem, TF32 path (3-term BF16 split, FP32/TF32 output), 224x224 (stem_tc_split.cu)
+size_t stem_tc_split_packed_input_bytes(int B);
+size_t stem_tc_split_packed_weight_bytes();
+cudaError_t stem_tc_split_init();
+cudaError_t launch_stem_tc_split_pack_weights(const float* w, const float* bn_w, const float* bn_b,
+                                              const float* bn_m, const float* bn_v, void* wk, float* bias,
+                                              cudaStream_t s);
+cudaError_t launch_stem_tc_split_part(int part, const float* x, void* xp, const void* wk, const float* bias,
+                                      void* out, int B, cudaStream_t s);
+
+// dispatch on the activation type (2 = BF16 kernel, 4 = TF32 split kernel)
+inline size_t stem_any_input_bytes(int esz, int B) {
+    return esz == 2 ? stem_tc_packed_input_bytes(B) : stem_tc_split_packed_input_bytes(B);
+}
+inline size_t stem_any_weight_bytes(int esz) {
+    return esz == 2 ? stem_tc_packed_weight_bytes() : stem_tc_split_packed_weight_bytes();
+}
+inline cudaError_t launch_stem_any_pack_weights(int esz, const float* w, const float* bn_w, const float* bn_b,
+                                                const float* bn_m, const float* bn_v, void* wk, float* bias,
+                                                cudaStream_t s) {
+    return esz == 2 ? launch_stem_tc_pack_weights(w, bn_w, bn_b, bn_m, bn_v, wk, bias, s)
+                    : launch_stem_tc_split_pack_weights(w, bn_w, bn_b, bn_m, bn_v, wk, bias, s);
+}
+inline cudaError_t launch_stem_any_part(int esz, int part, const float* x, void* xp, const void* wk,
+                                        const float* bias, void* out, int B, cudaStream_t s) {
+    return esz == 2 ? launch_stem_tc_part(part, x, xp, wk, bias, out, B, s)
+                    : launch_stem_tc_split_part(part, x, xp, wk, bias, out, B, s);
+}
+
 // ---- tail (tail.cu)
 // global average pool over NHWC [B,HW,C] -> pooledT [C][B] fp32 (transposed, see tail.cu)
 cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, int B, int HW, int C, int esz,

@@ -200,10 +200,10 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
         RNB_CUDA(cudaMalloc(&stem_bias, 64 * sizeof(float)));
         RNB_CUDA(launch_fold_f32(raw, bn.w, bn.b, bn.m, bn.v, stem_w, stem_bias, 64, 147, 0));
         const char* nostc = getenv("RNB_NO_STEM_TC");
-        stem_tc = esz == 2 && image == 224 && !(nostc && atoi(nostc) != 0);
+        stem_tc = image == 224 && !(nostc && atoi(nostc) != 0);
         if (stem_tc) {
-            RNB_CUDA(cudaMalloc(&stem_wk, stem_tc_packed_weight_bytes()));
-            RNB_CUDA(launch_stem_tc_pack_weights(raw, bn.w, bn.b, bn.m, bn.v, stem_wk, stem_bias, 0));
+            RNB_CUDA(cudaMalloc(&stem_wk, stem_any_weight_bytes(esz)));
+            RNB_CUDA(launch_stem_any_pack_weights(esz, raw, bn.w, bn.b, bn.m, bn.v, stem_wk, stem_bias, 0));
         }
         RNB_CUDA(cudaDeviceSynchronize());
         cudaFree(raw);
@@ -295,7 +295,7 @@ ChunkPlan* Model::plan_for(int n) {
     };
     const int s_hw = (6 + image - 7) / 2 + 1;     // 112
     const int p_hw = (2 + s_hw - 3) / 2 + 1;      // 56
-    if (!(p.stem_out = arena.acquire(stem_tc ? stem_tc_packed_input_bytes(n) : bytes(64, s_hw))))
+    if (!(p.stem_out = arena.acquire(stem_tc ? stem_any_input_bytes(esz, n) : bytes(64, s_hw))))
         return fail_alloc();
     if (!(p.pool_out = arena.acquire(bytes(64, p_hw)))) return fail_alloc();
     if (!stem_tc) p.named["stem"] = {p.stem_out, 64, s_hw, s_hw};
@@ -436,7 +436,8 @@ int Model::enqueue_chunk(ChunkPlan& p, const float* x, float* logits, int32_t* t
     const int n = p.n;
     const int s_hw = (6 + image - 7) / 2 + 1;
     if (stem_tc) {
-        RNB_CUDA(launch_stem_tc(x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
+        RNB_CUDA(launch_stem_any_part(esz, 0, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
+        RNB_CUDA(launch_stem_any_part(esz, 1, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
     } else {
         RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
         RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
@@ -527,12 +528,12 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
         int i = 0;
         RNB_CUDA(cudaEventRecord(ev[i], s));
         if (stem_tc)
-            RNB_CUDA(launch_stem_tc_part(0, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
+            RNB_CUDA(launch_stem_any_part(esz, 0, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
         else
             RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
         RNB_CUDA(cudaEventRecord(ev[++i], s));
         if (stem_tc)
-            RNB_CUDA(launch_stem_tc_part(1, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
+            RNB_CUDA(launch_stem_any_part(esz, 1, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
         else
             RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
         RNB_CUDA(cudaEventRecord(ev[++i], s));
@@ -566,7 +567,7 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
     const double img_px = 1.0 * image * image;
     if (stem_tc) {
         // launch 0 = layout pre-pass (fp32 NCHW -> padded NHWC4 bf16), launch 1 = fused conv+BN+ReLU+pool
-        const double packed = static_cast<double>(stem_tc_packed_input_bytes(1));
+        const double packed = static_cast<double>(stem_any_input_bytes(esz, 1));
         put(0, 0.0, n * (3.0 * img_px * 4 + packed));
         put(1, 2.0 * n * 64 * 147 * s_hw * s_hw, n * (packed + 64.0 * p_hw * p_hw * esz) + 28672.0);
     } else {
