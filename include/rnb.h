@@ -72,6 +72,15 @@ int rnb_model_forward(rnb_model_t* m, const float* x_dev, int batch, float* logi
 int rnb_model_forward_host(rnb_model_t* m, const float* x_host, int batch, float* logits_host,
                            int32_t* top1_host);
 
+/* Pipelined host path for a stream of batches (a serving loop): rnb_model_submit_host() queues the
+ * H2D copy of one batch, its forward pass and the D2H copy of the results into `slot` (0 or 1) and
+ * returns without blocking; rnb_model_wait_host() blocks until that slot's logits / top-1 are in the
+ * host buffers given at submit time. With two slots the PCIe transfer of batch i+1 overlaps the
+ * forward pass of batch i. Host buffers should be pinned; they must stay valid until the wait. */
+int rnb_model_submit_host(rnb_model_t* m, int slot, const float* x_host, int batch, float* logits_host,
+                          int32_t* top1_host);
+int rnb_model_wait_host(rnb_model_t* m, int slot);
+
 /* Introspection used by the benchmarks. */
 int rnb_model_num_classes(const rnb_model_t* m);
 int rnb_model_num_convs(const rnb_model_t* m);

@@ -130,6 +130,23 @@ int rnb_model_forward_host(rnb_model_t* m, const float* x_host, int batch, float
     return m->impl.forward_host(x_host, batch, logits_host, top1_host);
 }
 
+int rnb_model_submit_host(rnb_model_t* m, int slot, const float* x_host, int batch, float* logits_host,
+                          int32_t* top1_host) {
+    if (!m || !x_host) {
+        set_error("rnb_model_submit_host: NULL argument");
+        return RNB_ERR_INVALID;
+    }
+    return m->impl.submit_host(slot, x_host, batch, logits_host, top1_host);
+}
+
+int rnb_model_wait_host(rnb_model_t* m, int slot) {
+    if (!m) {
+        set_error("rnb_model_wait_host: NULL model");
+        return RNB_ERR_INVALID;
+    }
+    return m->impl.wait_host(slot);
+}
+
 int rnb_model_num_classes(const rnb_model_t* m) { return m ? m->impl.classes : 0; }
 int rnb_model_num_convs(const rnb_model_t* m) { return m ? m->impl.num_convs : 0; }
 int rnb_model_launches_per_forward(rnb_model_t* m, int batch) {

@@ -139,6 +139,12 @@ Model::~Model() {
     for (auto e : copy_events) cudaEventDestroy(e);
     if (cap_stream) cudaStreamDestroy(cap_stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (pipe_compute) cudaStreamDestroy(pipe_compute);
+    for (HostSlot& hs : slots) {
+        cudaFree(hs.x_dev); cudaFree(hs.logits_dev); cudaFree(hs.top1_dev);
+        if (hs.copied) cudaEventDestroy(hs.copied);
+        if (hs.done) cudaEventDestroy(hs.done);
+    }
     arena.free_all();
     cudaFree(stem_w); cudaFree(stem_bias); cudaFree(stem_wk); cudaFree(fc_w); cudaFree(fc_b);
     cudaFree(host_x_dev); cudaFree(host_logits_dev); cudaFree(host_top1_dev); cudaFree(scratch_logits);
@@ -629,6 +635,63 @@ int Model::forward_host(const float* x, int batch, float* logits, int32_t* top1)
         RNB_CUDA(cudaMemcpyAsync(top1, host_top1_dev, 1ull * batch * sizeof(int32_t),
                                  cudaMemcpyDeviceToHost, compute));
     RNB_CUDA(cudaStreamSynchronize(compute));
+    return RNB_OK;
+}
+
+// Pipelined host path. submit_host() queues, without blocking, the H2D copy of one batch (copy
+// stream), its forward pass (compute stream, after the copy) and the D2H copy of logits / top-1;
+// wait_host() blocks until that slot's results are in the caller's host buffers. With two slots the
+// PCIe transfer of batch i+1 (154 MB for 256 FP32 images — as long as the forward pass itself)
+// overlaps the forward pass of batch i, and the full batch still runs as ONE chunk.
+int Model::submit_host(int slot, const float* x, int batch, float* logits, int32_t* top1) {
+    if (slot < 0 || slot > 1) {
+        set_error("slot must be 0 or 1");
+        return RNB_ERR_INVALID;
+    }
+    if (batch <= 0 || batch > max_batch || !x) {
+        set_error("submit_host: bad batch or NULL input");
+        return RNB_ERR_INVALID;
+    }
+    HostSlot& hs = slots[slot];
+    if (hs.pending) {
+        int r = wait_host(slot);
+        if (r) return r;
+    }
+    const size_t img_elems = 3ull * image * image;
+    if (!hs.x_dev) {
+        RNB_CUDA(cudaMalloc(&hs.x_dev, 1ull * max_batch * img_elems * sizeof(float)));
+        RNB_CUDA(cudaMalloc(&hs.logits_dev, 1ull * max_batch * classes * sizeof(float)));
+        RNB_CUDA(cudaMalloc(&hs.top1_dev, 1ull * max_batch * sizeof(int32_t)));
+        RNB_CUDA(cudaEventCreateWithFlags(&hs.copied, cudaEventDisableTiming));
+        RNB_CUDA(cudaEventCreateWithFlags(&hs.done, cudaEventDisableTiming));
+    }
+    if (!pipe_compute) RNB_CUDA(cudaStreamCreateWithFlags(&pipe_compute, cudaStreamNonBlocking));
+    RNB_CUDA(cudaMemcpyAsync(hs.x_dev, x, batch * img_elems * sizeof(float), cudaMemcpyHostToDevice,
+                             copy_stream));
+    RNB_CUDA(cudaEventRecord(hs.copied, copy_stream));
+    RNB_CUDA(cudaStreamWaitEvent(pipe_compute, hs.copied, 0));
+    int r = forward(hs.x_dev, batch, hs.logits_dev, hs.top1_dev, pipe_compute);
+    if (r) return r;
+    if (logits)
+        RNB_CUDA(cudaMemcpyAsync(logits, hs.logits_dev, 1ull * batch * classes * sizeof(float),
+                                 cudaMemcpyDeviceToHost, pipe_compute));
+    if (top1)
+        RNB_CUDA(cudaMemcpyAsync(top1, hs.top1_dev, 1ull * batch * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 pipe_compute));
+    RNB_CUDA(cudaEventRecord(hs.done, pipe_compute));
+    hs.pending = true;
+    return RNB_OK;
+}
+
+int Model::wait_host(int slot) {
+    if (slot < 0 || slot > 1) {
+        set_error("slot must be 0 or 1");
+        return RNB_ERR_INVALID;
+    }
+    HostSlot& hs = slots[slot];
+    if (!hs.pending) return RNB_OK;
+    RNB_CUDA(cudaEventSynchronize(hs.done));
+    hs.pending = false;
     return RNB_OK;
 }
 

@@ -105,6 +105,17 @@ struct Model {
     int enqueue_chunk(ChunkPlan& p, const float* x, float* logits, int32_t* top1, cudaStream_t s);
     int forward(const float* x, int batch, float* logits, int32_t* top1, cudaStream_t s);
     int forward_host(const float* x, int batch, float* logits, int32_t* top1);
+    // pipelined host path: two slots, each with its own device input / output buffers
+    struct HostSlot {
+        float* x_dev = nullptr;
+        float* logits_dev = nullptr;
+        int32_t* top1_dev = nullptr;
+        cudaEvent_t copied = nullptr, done = nullptr;
+        bool pending = false;
+    } slots[2];
+    cudaStream_t pipe_compute = nullptr;
+    int submit_host(int slot, const float* x, int batch, float* logits, int32_t* top1);
+    int wait_host(int slot);
     int profile(const float* x, int batch, int iters, int* kind, float* ms, double* flops,
                 double* bytes, int max_entries, int* n_entries, cudaStream_t s);
     // stem conv + max-pool + (num_convs - 1) tensor-core convs + avg-pool + fc + arg-max

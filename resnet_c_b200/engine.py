@@ -226,6 +226,16 @@ class ResNet:
         check(_lib.lib().rnb_model_forward_host(self._h, _ptr(x), B, _ptr(logits), _ptr(top1)))
         return logits, top1
 
+    def submit_host(self, slot: int, x: torch.Tensor, logits: torch.Tensor, top1: torch.Tensor) -> None:
+        """Pipelined host path: queue H2D + forward + D2H of one (pinned) host batch into slot 0/1 and
+        return at once; results are valid after wait_host(slot)."""
+        if x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+            raise RnbError("submit_host takes a contiguous float32 host tensor")
+        check(_lib.lib().rnb_model_submit_host(self._h, slot, _ptr(x), x.shape[0], _ptr(logits), _ptr(top1)))
+
+    def wait_host(self, slot: int) -> None:
+        check(_lib.lib().rnb_model_wait_host(self._h, slot))
+
     KINDS = ("stem_conv", "maxpool", "conv_igemm", "avgpool", "fc", "argmax")
 
     def profile(self, x: torch.Tensor, iters: int = 3):

@@ -101,6 +101,28 @@ def test_forward_host_equals_device_path():
     model.close()
 
 
+def test_pipelined_host_path_equals_device_path():
+    """submit_host / wait_host with two batches in flight must return each batch's own results."""
+    from resnet_c_b200 import weights
+    model = _model("resnet18", True, "bf16", 16)
+    xs = [weights.synthetic_images(16, seed=s).pin_memory() for s in (1, 2, 3)]
+    want = []
+    for x in xs:
+        l, t = model.forward(x.cuda())
+        want.append((l.cpu(), t.cpu()))
+    outs = [(torch.empty(16, model.num_classes).pin_memory(), torch.empty(16, dtype=torch.int32).pin_memory())
+            for _ in xs]
+    model.submit_host(0, xs[0], *outs[0])
+    model.submit_host(1, xs[1], *outs[1])
+    model.wait_host(0)
+    model.submit_host(0, xs[2], *outs[2])
+    model.wait_host(1)
+    model.wait_host(0)
+    for (l, t), (wl, wt) in zip(outs, want):
+        assert torch.equal(l, wl) and torch.equal(t, wt)
+    model.close()
+
+
 @pytest.mark.parametrize("arch,dtype", [("resnet50", "bf16"), ("resnet18", "tf32")])
 def test_full_batch_properties(arch, dtype):
     """BASELINE configs[1]/[2] sizes (batch 256): the oracle cannot run these in seconds, so check
