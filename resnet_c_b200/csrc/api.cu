@@ -1,4 +1,5 @@
 // api.cu — the extern "C" surface declared in include/rnb.h.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -151,8 +152,10 @@ int rnb_model_num_classes(const rnb_model_t* m) { return m ? m->impl.classes : 0
 int rnb_model_num_convs(const rnb_model_t* m) { return m ? m->impl.num_convs : 0; }
 int rnb_model_launches_per_forward(rnb_model_t* m, int batch) {
     if (!m || batch <= 0) return 0;
-    const int chunks = (batch + m->impl.chunk - 1) / m->impl.chunk;
-    return chunks * m->impl.launches_per_chunk();
+    int total = 0;
+    for (int off = 0; off < batch; off += m->impl.chunk)
+        total += m->impl.launches_per_chunk(std::min(m->impl.chunk, batch - off));
+    return total;
 }
 double rnb_model_flops_per_image(const rnb_model_t* m) { return m ? m->impl.flops_per_image : 0.0; }
 

@@ -66,6 +66,12 @@ cudaError_t conv_kernels_init() {
     if ((e = cudaFuncSetAttribute(conv3x3_halo_kernel<HaloCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   HaloCfg::SMEM_BYTES)) != cudaSuccess)
         return e;
+    if ((e = cudaFuncSetAttribute(bneck_l1_kernel<BneckCfg<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  BneckCfg<false>::SMEM_BYTES)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncSetAttribute(bneck_l1_kernel<BneckCfg<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  BneckCfg<true>::SMEM_BYTES)) != cudaSuccess)
+        return e;
     return cudaSuccess;
 }
 
@@ -108,6 +114,61 @@ static int halo_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, char* 
     if ((r = make_tiled_nd(&plan->tmOut, TmDtype::BF16, d.out, 4, dims, strides, box_out, true)) != 0)
         return fail(err, errlen, "conv_plan: halo output tensor map failed", r);
     plan->tmRes = plan->tmOut;
+    return 0;
+}
+
+bool bneck_plan_ok(int H, int W, int esz) { return esz == 2 && W >= 8 && W <= 62 && H >= 4 && H % 4 == 0; }
+
+int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, int errlen) {
+    memset(plan, 0, sizeof(*plan));
+    if (!bneck_plan_ok(d.H, d.W, 2)) return fail(err, errlen, "bneck_plan: geometry not eligible", -7);
+    plan->bneck = d.wds ? 2 : 1;
+    plan->bn = 256;
+    plan->esz = 2;
+    plan->ctas = 2;
+    BneckGeom& g = plan->bg;
+    g.N = d.B; g.H = d.H; g.W = d.W;
+    g.tiles_per_img = d.H / 4;
+    g.tiles = d.B * g.tiles_per_img;
+    g.has_next = d.w1n ? 1 : 0;
+    g.reverse = d.reverse ? 1 : 0;
+    plan->bp.bias2 = d.bias2;
+    plan->bp.bias3 = d.bias3;
+    plan->bp.bias1n = d.bias1n ? d.bias1n : d.bias2;
+    const int pairs = g.tiles < num_sms / 2 ? g.tiles : num_sms / 2;
+    plan->grid = 2 * pairs;
+    const double M = 1.0 * d.B * d.H * d.W;
+    const double macs = 64.0 * 576 + 256.0 * 64 + (d.wds ? 256.0 * 64 : 0.0) + (d.w1n ? 64.0 * 256 : 0.0);
+    plan->flops = 2.0 * M * macs;
+    plan->bytes = 2.0 * M * (64 + (d.wds ? 64 : 256) + 256 + (d.w1n ? 64 : 0)) + 2.0 * macs + 4.0 * (64 + 256 + 64);
+    auto act_map = [&](CUtensorMap* tm, const void* base, int C, uint32_t bw, uint32_t bh) {
+        const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H),
+                                  static_cast<uint64_t>(d.B)};
+        const uint64_t strides[3] = {2ull * C, 2ull * C * d.W, 2ull * C * d.W * d.H};
+        const uint32_t box[4] = {64, bw, bh, 1};
+        return make_tiled_nd(tm, TmDtype::BF16, base, 4, dims, strides, box, true);
+    };
+    int r;
+    if ((r = act_map(&plan->tmA, d.t1, 64, 64, 2)) != 0) return fail(err, errlen, "bneck_plan: t1 tensor map failed", r);
+    if ((r = make_tiled_2d(&plan->tmB, TmDtype::BF16, d.w2, 64, 576, 32)) != 0)
+        return fail(err, errlen, "bneck_plan: w2 tensor map failed", r);
+    if ((r = make_tiled_2d(&plan->tmW3, TmDtype::BF16, d.w3, 256, 64, 64)) != 0)
+        return fail(err, errlen, "bneck_plan: w3 tensor map failed", r);
+    plan->tmWds = plan->tmW3;
+    if (d.wds && (r = make_tiled_2d(&plan->tmWds, TmDtype::BF16, d.wds, 256, 64, 64)) != 0)
+        return fail(err, errlen, "bneck_plan: wds tensor map failed", r);
+    if ((r = act_map(&plan->tmRes, d.shortcut, d.wds ? 64 : 256, 64, 2)) != 0)
+        return fail(err, errlen, "bneck_plan: shortcut tensor map failed", r);
+    if ((r = act_map(&plan->tmOut, d.y, 256, static_cast<uint32_t>(d.W), 1)) != 0)
+        return fail(err, errlen, "bneck_plan: y tensor map failed", r);
+    plan->tmW1n = plan->tmB;
+    plan->tmT1n = plan->tmOut;
+    if (d.w1n) {
+        if ((r = make_tiled_2d(&plan->tmW1n, TmDtype::BF16, d.w1n, 64, 256, 32)) != 0)
+            return fail(err, errlen, "bneck_plan: w1n tensor map failed", r);
+        if ((r = act_map(&plan->tmT1n, d.t1n, 64, static_cast<uint32_t>(d.W), 1)) != 0)
+            return fail(err, errlen, "bneck_plan: t1n tensor map failed", r);
+    }
     return 0;
 }
 
@@ -240,6 +301,14 @@ static cudaError_t launch2(const ConvPlan& p, cudaStream_t stream) {
 }
 
 cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
+    if (p.bneck == 1)
+        return launch_pdl(bneck_l1_kernel<BneckCfg<false>>, p.grid, BneckCfg<false>::THREADS,
+                          BneckCfg<false>::SMEM_BYTES, stream, p.tmA, p.tmB, p.tmW3, p.tmWds, p.tmW1n, p.tmRes,
+                          p.tmOut, p.tmT1n, p.bp, p.bg);
+    if (p.bneck == 2)
+        return launch_pdl(bneck_l1_kernel<BneckCfg<true>>, p.grid, BneckCfg<true>::THREADS,
+                          BneckCfg<true>::SMEM_BYTES, stream, p.tmA, p.tmB, p.tmW3, p.tmWds, p.tmW1n, p.tmRes,
+                          p.tmOut, p.tmT1n, p.bp, p.bg);
     if (p.halo) {
         return launch_pdl(conv3x3_halo_kernel<HaloCfg>, p.grid, HaloCfg::THREADS, HaloCfg::SMEM_BYTES, stream,
                           p.tmA, p.tmB, p.tmOut, p.bias, p.hg);

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "bneck_l1.cuh"
 #include "conv3x3_halo.cuh"
 #include "conv_igemm.cuh"
 
@@ -22,8 +23,30 @@ struct ConvDesc {
     void* out;             // NHWC [B][OH][OW][Cout]
 };
 
+// Fused layer1 Bottleneck tail (bneck_l1.cuh): conv2 3x3 + conv3 1x1 + shortcut + ReLU, optionally
+// with the downsample conv folded into conv3's accumulator and the next block's conv1 appended.
+struct BneckDesc {
+    int B, H, W;             // t1 is NHWC [B][H][W][64]
+    bool reverse = false;
+    const void* t1;          // conv1 output of this block
+    const void* w2;          // [64][3][3][64] bf16, BN folded
+    const float* bias2;
+    const void* w3;          // [256][64]
+    const float* bias3;      // conv3 shift; with `wds`: conv3 shift + downsample shift
+    const void* wds;         // [256][64] downsample weights, or nullptr
+    const void* shortcut;    // wds ? block input NHWC [B][H][W][64] : residual NHWC [B][H][W][256]
+    void* y;                 // NHWC [B][H][W][256]
+    const void* w1n;         // next block's conv1 weights [64][256], or nullptr
+    const float* bias1n;
+    void* t1n;               // next block's conv1 output NHWC [B][H][W][64]
+};
+
 struct ConvPlan {
     CUtensorMap tmA, tmB, tmOut, tmRes;
+    CUtensorMap tmW3, tmWds, tmW1n, tmT1n;  // fused Bottleneck tail only
+    int bneck;    // 0 = plain conv, 1 = fused tail with residual tensor, 2 = fused tail with folded downsample
+    BneckGeom bg;
+    BneckParams bp;
     ConvGeom g;
     const float* bias;
     int bn;       // tile N
@@ -44,6 +67,8 @@ bool conv_plan_halo_ok(const ConvDesc& d);
 // `err` (if non-null, at most errlen bytes).
 int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn, char* err,
                    int errlen);
+bool bneck_plan_ok(int H, int W, int esz);
+int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, int errlen);
 // Enqueues the kernel on `stream` (no synchronisation).
 cudaError_t conv_plan_launch(const ConvPlan& plan, cudaStream_t stream);
 // One-time per process: raise the dynamic shared memory limit of every kernel instantiation.

@@ -153,6 +153,7 @@ Model::~Model() {
             cudaFree(c->w);
             cudaFree(c->bias);
         }
+        cudaFree(b.bias3ds);
     }
 }
 
@@ -192,6 +193,10 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
     autotune = !(at && atoi(at) == 0);
     const char* ka = getenv("RNB_KEEP_ACTIVATIONS");  // parity debugging: never recycle arena blocks
     arena.keep = ka && atoi(ka) != 0;
+    const char* fu = getenv("RNB_FUSE");
+    fuse_level = fu ? atoi(fu) : 2;
+    const char* fn = getenv("RNB_FUSE_NEXT");
+    fuse_next = !(fn && atoi(fn) == 0);
 
     int r;
     // ---- stem: conv1 + bn1 (main.cu:110-111), folded in fp32 OIHW for the CUDA-core stem
@@ -251,6 +256,13 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
                     return r;
                 macs += 1.0 * out_hw * out_hw * in_c * out_c;
                 num_convs += 1;
+                if (bottleneck) {
+                    std::vector<float> b3(out_c), bd(out_c);
+                    RNB_CUDA(cudaMemcpy(b3.data(), bw.conv3.bias, out_c * sizeof(float), cudaMemcpyDeviceToHost));
+                    RNB_CUDA(cudaMemcpy(bd.data(), bw.ds.bias, out_c * sizeof(float), cudaMemcpyDeviceToHost));
+                    for (int c = 0; c < out_c; ++c) b3[c] += bd[c];
+                    if ((r = upload(b3, &bw.bias3ds))) return r;
+                }
             }
             blocks.push_back(bw);
             in_c = out_c;
@@ -385,19 +397,62 @@ ChunkPlan* Model::plan_for(int n) {
         p.convs.push_back(cp);
         return 0;
     };
-    for (const BlockWeights& bw : blocks) {
+    void* pre_t1 = nullptr;  // this block's conv1 output, already produced by the previous fused launch
+    for (size_t bi = 0; bi < blocks.size(); ++bi) {
+        const BlockWeights& bw = blocks[bi];
         const int stride = bw.bottleneck ? bw.conv2.stride : bw.conv1.stride;
         const int out_hw = hw / stride;
         const int out_c = bw.bottleneck ? bw.conv3.Cout : bw.conv2.Cout;
+        // layer1-shaped Bottleneck (64 -> 64 -> 256, stride 1): conv2 + conv3 + shortcut in one launch
+        const bool fuse = fuse_level >= 1 && bw.bottleneck && stride == 1 && bw.conv2.Cin == 64 &&
+                          bw.conv2.Cout == 64 && out_c == 256 && bneck_plan_ok(hw, hw, esz);
+        const bool fuse_ds = fuse && fuse_level >= 2 && bw.has_ds && bw.ds.stride == 1 && bw.ds.Cin == 64 &&
+                             bw.bias3ds;
         void* shortcut = x;
         void* ds = nullptr;
-        if (bw.has_ds) {
+        if (bw.has_ds && !fuse_ds) {
             if (!(ds = arena.acquire(bytes(out_c, out_hw)))) return fail_alloc();
             if (add_conv(bw.ds, x, hw, nullptr, false, ds)) return nullptr;
             shortcut = ds;
         }
         void* y = nullptr;
-        if (bw.bottleneck) {
+        if (fuse) {
+            void* t1 = pre_t1;
+            pre_t1 = nullptr;
+            if (!t1) {
+                if (!(t1 = arena.acquire(bytes(64, hw)))) return fail_alloc();
+                if (add_conv(bw.conv1, x, hw, nullptr, true, t1)) return nullptr;
+            }
+            const BlockWeights* nb = bi + 1 < blocks.size() ? &blocks[bi + 1] : nullptr;
+            const bool next = fuse_next && nb && nb->bottleneck && !nb->has_ds && nb->conv1.Cin == 256 &&
+                              nb->conv1.Cout == 64 && nb->conv2.stride == 1 && nb->conv2.Cin == 64 &&
+                              nb->conv2.Cout == 64 && nb->conv3.Cout == 256;
+            void* t1n = nullptr;
+            if (next && !(t1n = arena.acquire(bytes(64, hw)))) return fail_alloc();
+            if (!(y = arena.acquire(bytes(out_c, hw)))) return fail_alloc();
+            BneckDesc bd{};
+            bd.B = n; bd.H = hw; bd.W = hw;
+            bd.reverse = alternate_tiles && (p.convs.size() & 1) != 0;
+            bd.t1 = t1; bd.w2 = bw.conv2.w; bd.bias2 = bw.conv2.bias; bd.w3 = bw.conv3.w;
+            bd.bias3 = fuse_ds ? bw.bias3ds : bw.conv3.bias;
+            bd.wds = fuse_ds ? bw.ds.w : nullptr;
+            bd.shortcut = shortcut;
+            bd.y = y;
+            bd.w1n = next ? nb->conv1.w : nullptr;
+            bd.bias1n = next ? nb->conv1.bias : nullptr;
+            bd.t1n = t1n;
+            ConvPlan cp;
+            if (bneck_plan_init(&cp, bd, num_sms, err, sizeof(err))) {
+                set_error(err);
+                return nullptr;
+            }
+            if (getenv("RNB_VERBOSE"))
+                fprintf(stderr, "rnb plan: conv#%zu n=%d %dx%d fused bottleneck tail%s%s grid %d\n", p.convs.size(), n,
+                        hw, hw, fuse_ds ? " +downsample" : "", next ? " +next conv1" : "", cp.grid);
+            p.convs.push_back(cp);
+            arena.release(t1);
+            pre_t1 = t1n;
+        } else if (bw.bottleneck) {
             // conv1 -> bn1 -> relu -> conv2(stride) -> bn2 -> relu -> conv3 -> bn3 -> +shortcut -> relu
             // (layerForward, main.cu:138-163)
             void* t1 = arena.acquire(bytes(bw.conv1.Cout, hw));
@@ -448,7 +503,17 @@ int Model::enqueue_chunk(ChunkPlan& p, const float* x, float* logits, int32_t* t
         RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
         RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
     }
-    for (const ConvPlan& cp : p.convs) RNB_CUDA(conv_plan_launch(cp, s));
+    static const bool sync_each = getenv("RNB_SYNC_EACH") != nullptr;  // bring-up: localise a faulting launch
+    for (size_t i = 0; i < p.convs.size(); ++i) {
+        RNB_CUDA(conv_plan_launch(p.convs[i], s));
+        if (sync_each) {
+            cudaError_t e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) {
+                set_error("conv launch #" + std::to_string(i) + " failed: " + cudaGetErrorString(e));
+                return RNB_ERR_CUDA;
+            }
+        }
+    }
     RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, n, p.last_hw, p.last_c, esz, s));
     RNB_CUDA(launch_fc(p.pooled, fc_w, fc_b, logits, n, p.last_c, classes, s));
     if (top1) RNB_CUDA(launch_argmax_f32(logits, top1, n, classes, s));
@@ -517,7 +582,7 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
     ChunkPlan* pp = plan_for(n);
     if (!pp) return RNB_ERR_CUDA;
     ChunkPlan& p = *pp;
-    const int L = launches_per_chunk();
+    const int L = static_cast<int>(p.convs.size()) + 5;
     *n_entries = L;
     if (max_entries < L) {
         set_error("profile: output arrays too small");

@@ -28,6 +28,7 @@ struct BlockWeights {
     ConvWeights conv1, conv2, conv3;  // conv3 unused for BasicBlock
     bool has_ds = false;
     ConvWeights ds;
+    float* bias3ds = nullptr;  // conv3 shift + downsample shift (fused-tail kernel with folded downsample)
     std::string name;  // "layer{L}.{i}"
 };
 
@@ -97,6 +98,11 @@ struct Model {
     bool use_graph = true;
     bool alternate_tiles = true;  // consecutive convs walk their tiles in opposite directions (L2 reuse)
     bool autotune = true;         // time the admissible tile families per layer shape at plan time
+    // Fused layer1 Bottleneck tail (bneck_l1.cuh). RNB_FUSE: 0 = off, 1 = conv2+conv3+residual,
+    // 2 (default) = also fold the downsample conv of block 0; RNB_FUSE_NEXT=0 keeps the next block's
+    // conv1 as its own launch.
+    int fuse_level = 2;
+    bool fuse_next = true;
     std::map<std::tuple<int, int, int, int, int, int, int>, int> tuned;  // layer shape -> force_bn code
 
     ~Model();
@@ -118,8 +124,11 @@ struct Model {
     int wait_host(int slot);
     int profile(const float* x, int batch, int iters, int* kind, float* ms, double* flops,
                 double* bytes, int max_entries, int* n_entries, cudaStream_t s);
-    // stem conv + max-pool + (num_convs - 1) tensor-core convs + avg-pool + fc + arg-max
-    int launches_per_chunk() const { return num_convs + 4; }
+    // stem pre-pass/conv + stem/max-pool + planned conv launches + avg-pool + fc + arg-max
+    int launches_per_chunk(int n) {
+        ChunkPlan* p = plan_for(n);
+        return p ? static_cast<int>(p->convs.size()) + 5 : 0;
+    }
 };
 
 }  // namespace rnb

@@ -156,11 +156,52 @@ def test_full_batch_properties(arch, dtype):
     small.close()
 
 
-def test_launch_accounting():
+def _run_with_env(monkeypatch, env, arch, batch, names):
+    from resnet_c_b200 import weights
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    monkeypatch.setenv("RNB_KEEP_ACTIVATIONS", "1")
+    model = _model(arch, True, "bf16", batch)
+    logits, top1 = model.forward(weights.synthetic_images(batch).cuda())
+    torch.cuda.synchronize()
+    acts = {n: model.activation(n).clone() for n in names}
+    launches = model.launches_per_forward(batch)
+    model.close()
+    return logits.clone(), top1.clone(), acts, launches
+
+
+@pytest.mark.parametrize("arch,batch", [("resnet50", 3), ("resnet50", 37), ("resnet152", 2)])
+def test_fused_bottleneck_tail_equals_layer_by_layer(monkeypatch, arch, batch):
+    """csrc/bneck_l1.cuh: conv2 + conv3 + residual (+ next conv1) in one launch rounds at the same
+    points as the separate kernels, so RNB_FUSE=1 must be BIT-IDENTICAL to RNB_FUSE=0; RNB_FUSE=2 also
+    folds the downsample conv into the conv3 accumulator (one BF16 rounding fewer on the shortcut), so
+    it is compared within the BF16 bar. Odd batch sizes leave CTA pairs with unequal tile counts."""
+    names = ("layer1.0", "layer1.1", "layer1.2", "layer2.0")
+    base = _run_with_env(monkeypatch, {"RNB_FUSE": "0"}, arch, batch, names)
+    for nxt in ("0", "1"):
+        got = _run_with_env(monkeypatch, {"RNB_FUSE": "1", "RNB_FUSE_NEXT": nxt}, arch, batch, names)
+        assert got[3] < base[3]
+        for n in names:
+            assert torch.equal(got[2][n], base[2][n]), f"{n} differs (fuse=1 next={nxt})"
+        assert torch.equal(got[0], base[0]) and torch.equal(got[1], base[1])
+        got = _run_with_env(monkeypatch, {"RNB_FUSE": "2", "RNB_FUSE_NEXT": nxt}, arch, batch, names)
+        for n in names:
+            e = rel_err(got[2][n].cpu().numpy().reshape(batch, -1), base[2][n].cpu().numpy().reshape(batch, -1))
+            assert e < 2e-2, f"{n}: rel err {e:.3e} (fuse=2 next={nxt})"
+        assert rel_err(got[0].cpu().numpy(), base[0].cpu().numpy()) < 2e-2
+
+
+def test_launch_accounting(monkeypatch):
+    monkeypatch.setenv("RNB_FUSE", "0")
     model = _model("resnet50", True, "bf16", 64, chunk=16)
     # stem + maxpool + 52 tensor-core convs + avgpool + fc + argmax per chunk
     assert model.launches_per_forward(16) == 57
     assert model.launches_per_forward(64) == 4 * 57
+    model.close()
+    monkeypatch.setenv("RNB_FUSE", "2")
+    model = _model("resnet50", True, "bf16", 64, chunk=16)
+    # layer1: downsample + conv2 + conv3 of block 0 and conv1 + conv2 + conv3 of blocks 1, 2 -> 3 launches
+    assert model.launches_per_forward(16) == 51
     assert model.flops_per_image == pytest.approx(8_178_368_512, rel=1e-9)  # SURVEY.md section 8(d)
     model.close()
     m18 = _model("resnet18", True, "tf32", 4)
