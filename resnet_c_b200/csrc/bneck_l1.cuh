@@ -19,17 +19,21 @@
 // Structure: a CTA PAIR (cta_group::2) per tile of 4 image rows x 64-pixel pitch (256 GEMM rows, 2
 // rows per CTA). All weights are resident in shared memory, split across the pair (each CTA holds
 // half of the output channels of every matrix: 36 + 16 (+16) + 16 KB).
-//   conv2 : halo-resident 3x3 as in conv3x3_halo.cuh — one TMA load per filter row, three taps =
-//           row-shifted UMMA descriptors on the same tile; accumulator D1 (64 cols, double-buffered)
-//   E1    : D1 + bias2 -> ReLU -> BF16 -> A2 tile in shared memory (swizzled K-major = UMMA A operand)
-//   conv3 : A2 x W3^T (K = 64) [+ x_tile x Wds^T] -> D2 (256 cols, two 128-col halves)
+//   conv2 : halo-resident 3x3 (cf. conv3x3_halo.cuh) — ONE TMA load per tile fetches the 4 input rows
+//           x 64-pixel pitch a CTA needs (zero halo by hardware OOB fill); the nine taps are the same
+//           tile read through UMMA descriptors shifted by r rows (8 KB) + s pixels (128 B);
+//           accumulator D1 (64 cols, double-buffered), input tile double-buffered
+//   E1    : D1 + bias2 -> ReLU -> BF16 pairs -> tcgen05.st back into TMEM (A2, 32 cols, double-buffered)
+//   conv3 : A2 (A operand FROM TMEM) x W3^T (K = 64) [+ x_tile x Wds^T] -> D2 (256 cols, two halves)
 //   E2    : D2 + bias3 (+ residual, TMA-prefetched into the staging box) -> ReLU -> BF16 -> four
 //           64-channel staging boxes -> TMA store to y; each box is ALSO the K block of
 //   conv1': box_j x W1n_j^T accumulated over j = 0..3 -> D3 (64 cols)
 //   E3    : D3 + bias1' -> ReLU -> BF16 -> staging box -> TMA store to t1'
-// Warp roles per CTA (384 threads): 0 TMA producer (weights once, input ring), 1 MMA issuer (leader
-// CTA only), 2 TMEM allocator + shortcut-input loader (DS mode), 3 store warp (stores, residual
-// prefetch, box recycling), 4..11 epilogue (two warps per TMEM lane quarter, 32 columns each).
+// Warp roles per CTA (416 threads): 0 TMA producer (weights once, input tiles), 1 conv2 MMA issuer
+// (leader CTA only), 2 TMEM allocator + shortcut-input loader (DS mode), 3 store warp (stores, residual
+// prefetch, box recycling), 4..11 epilogue (two warps per TMEM lane quarter, 32 columns each), 12
+// conv3 / conv1' MMA issuer (leader only). Two issuers on purpose: conv2 waits for HBM, conv3 / conv1'
+// wait for the epilogue — one in-order issuer makes each stall the other.
 // The epilogue is software-pipelined one tile ahead: iteration i runs E1(i+1), E3(i-1), E2(i), so
 // every MMA group has a full epilogue phase to complete before its result is needed.
 // Rows w >= W of the 64-pixel pitch are garbage end to end (GEMM rows are independent) and are never
@@ -46,14 +50,17 @@ struct BneckGeom {
     int tiles_per_img;  // H / 4
     int has_next;       // compute and store the next block's conv1 output
     int reverse;        // tile traversal direction (see ConvGeom::reverse)
+    int debug;          // timing experiments: 1 = no residual loads, 2 = no stores, 8 = all stores to one tile
+                        // (results wrong); 4 = L2 prefetch of residual tiles (results right)
 };
 
 template <bool DS_>
 struct BneckCfg {
     static constexpr bool DS = DS_;  // shortcut = downsample conv of x, fused as a second K block
     static constexpr int PITCH = 64;
-    static constexpr int NSLOT = 3;                 // input ring: one slot per (tile, filter row)
-    static constexpr int SLOT_BYTES = 16384;        // 2 rows x 64 pixels x 128 B
+    static constexpr int NABUF = 2;                 // input tiles in flight
+    static constexpr int ATILE_BYTES = 32768;       // 4 rows x 64 pixels x 128 B
+    static constexpr int AROW_BYTES = 8192;         // one input row of the tile
     static constexpr int W2_TAP_BYTES = 32 * 128;   // this CTA's 32 output channels of one tap
     static constexpr int W2_BYTES = 9 * W2_TAP_BYTES;
     static constexpr int W3_HALF_BYTES = 64 * 128;  // this CTA's 64 channels of one 128-channel half
@@ -62,18 +69,17 @@ struct BneckCfg {
     static constexpr int W1N_KB_BYTES = 32 * 128;   // this CTA's 32 channels x one 64-wide K block
     static constexpr int W1N_BYTES = 4 * W1N_KB_BYTES;
     static constexpr int W_BYTES = W2_BYTES + W3_BYTES + WDS_BYTES + W1N_BYTES;
-    static constexpr int RING_BYTES = NSLOT * SLOT_BYTES + 1024;  // + read-past pad of the shifted views
+    static constexpr int RING_BYTES = NABUF * ATILE_BYTES + 1024;  // + read-past pad of the shifted views
     static constexpr int BOX_BYTES = 16384;         // 128 rows x 64 bf16, 128-byte swizzled
-    static constexpr int A2_BYTES = 2 * BOX_BYTES;
     static constexpr int P_BYTES = DS_ ? BOX_BYTES : 0;
-    static constexpr int NPOOL = DS_ ? 2 : 4;       // staging boxes (R mode: also the residual prefetch depth)
+    static constexpr int NPOOL = DS_ ? 3 : 5;       // staging boxes (R mode: also the residual prefetch depth)
     static constexpr int TMEM_COLS = 512;
-    static constexpr int D1_COL = 0, D2_COL = 128, D3_COL = 384;
-    static constexpr int NBAR = 1 + 2 * NSLOT + 4 + 2 + 4 + 2 + 2 + 4 * NPOOL;
+    static constexpr int D1_COL = 0, D2_COL = 128, D3_COL = 384, A2_COL = 448;
+    static constexpr int NBAR = 1 + 2 * NABUF + 4 + 2 + 4 + 2 + 2 + 4 * NPOOL;
     static constexpr int SMEM_BYTES =
-        1024 + W_BYTES + RING_BYTES + A2_BYTES + P_BYTES + NPOOL * BOX_BYTES + NBAR * 8 + 16;
+        1024 + W_BYTES + RING_BYTES + P_BYTES + NPOOL * BOX_BYTES + NBAR * 8 + 16;
     static constexpr int EPI_WARPS = 8;
-    static constexpr int THREADS = 128 + EPI_WARPS * 32;
+    static constexpr int THREADS = 128 + EPI_WARPS * 32 + 32;
 };
 static_assert(BneckCfg<false>::SMEM_BYTES <= 232448, "smem budget");
 static_assert(BneckCfg<true>::SMEM_BYTES <= 232448, "smem budget");
@@ -89,12 +95,47 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMa
           "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// pull one box of a 4-D tiled tensor into L2 (no shared-memory destination, no completion signal)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int32_t c0, int32_t c1, int32_t c2,
+                                                int32_t c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 // cluster-scope release arrive on the leader's barrier: orders this CTA's shared-memory writes
 // (already fenced to the async proxy) before the leader's MMAs that read them through the pair
 __device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) &
                                                                                       kPeerBitMask)
                  : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T over a CTA pair: A = 128 rows per CTA, 16-bit elements packed two
+// per 32-bit column (element k of row m: lane m, column k / 2, low half first)
+__device__ __forceinline__ void mma_f16_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes x 16 consecutive 32-bit columns (thread t writes lane t)
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0],"
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+        :
+        : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -119,7 +160,7 @@ struct BneckParams {
 };
 
 // Tensor maps (all BF16, 128-byte swizzle):
-//   tmA   input t1      [C=64,  W, H, N]  box {64, 64, 2, 1}   (loaded at w = -1: zero halo)
+//   tmA   input t1      [C=64,  W, H, N]  box {64, 64, 4, 1}   (loaded at w = -1, h = h0 - 1: zero halo)
 //   tmW2  conv2 weights [64][576]         box {64, 32}
 //   tmW3  conv3 weights [256][64]         box {64, 64}
 //   tmWds downsample weights [256][64]    box {64, 64}         (DS mode; else unused)
@@ -136,7 +177,7 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const BneckParams prm, const BneckGeom g) {
     using namespace ptx;
     constexpr bool DS = Cfg::DS;
-    constexpr int NSLOT = Cfg::NSLOT, NPOOL = Cfg::NPOOL;
+    constexpr int NABUF = Cfg::NABUF, NPOOL = Cfg::NPOOL;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -146,14 +187,13 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint8_t* smem_wds = smem_w3 + Cfg::W3_BYTES;
     uint8_t* smem_w1n = smem_wds + Cfg::WDS_BYTES;
     uint8_t* smem_ring = smem_w1n + Cfg::W1N_BYTES;
-    uint8_t* smem_a2 = smem_ring + Cfg::RING_BYTES;
-    uint8_t* smem_p = smem_a2 + Cfg::A2_BYTES;
+    uint8_t* smem_p = smem_ring + Cfg::RING_BYTES;
     uint8_t* smem_pool = smem_p + Cfg::P_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_pool + NPOOL * Cfg::BOX_BYTES);
     uint64_t* w_full = bars;                 // leader: all resident weights of both CTAs landed
-    uint64_t* a_full = w_full + 1;           // leader: ring slot landed in both CTAs
-    uint64_t* a_empty = a_full + NSLOT;      // per CTA (multicast commit)
-    uint64_t* d1_full = a_empty + NSLOT;     // per CTA (multicast commit), [2]
+    uint64_t* a_full = w_full + 1;           // leader: input tile landed in both CTAs
+    uint64_t* a_empty = a_full + NABUF;      // per CTA (multicast commit)
+    uint64_t* d1_full = a_empty + NABUF;     // per CTA (multicast commit), [2]
     uint64_t* d1_empty = d1_full + 2;        // leader, 16 arrivals, [2]
     uint64_t* a2_full = d1_empty + 2;        // leader, 16 arrivals, [2]
     uint64_t* d2_full = a2_full + 2;         // per CTA (multicast commit), [2 halves]
@@ -191,7 +231,7 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         mbar_init(w_full, 1);
-        for (int i = 0; i < NSLOT; ++i) {
+        for (int i = 0; i < NABUF; ++i) {
             mbar_init(&a_full[i], 1);
             mbar_init(&a_empty[i], 1);
         }
@@ -221,7 +261,7 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     // read-past pad of the ring (garbage rows only; keep it defined)
     for (int i = threadIdx.x; i < 64; i += Cfg::THREADS)
-        reinterpret_cast<uint4*>(smem_ring + NSLOT * Cfg::SLOT_BYTES)[i] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(smem_ring + NABUF * Cfg::ATILE_BYTES)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -257,74 +297,69 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tma_load_2d_2sm(smem_w1n + kb * Cfg::W1N_KB_BYTES, &tmW1n, w_full, kb * 64, r32);
         }
         __syncwarp();
-        int slot = 0;
-        uint32_t phase = 0;
         for (int it = 0; it < T; ++it) {
             int img, h0;
             tile_coords(it, img, h0);
-            for (int r = 0; r < 3; ++r) {
-                mbar_wait(&a_empty[slot], phase ^ 1);
-                if (elect_one()) {
-                    if (rank == 0) mbar_expect_tx(&a_full[slot], 2 * Cfg::SLOT_BYTES);
-                    // pixels [-1, 63) of input rows h0+r-1, h0+r; out-of-image parts are zero-filled
-                    tma_load_4d_2sm(smem_ring + slot * Cfg::SLOT_BYTES, &tmA, &a_full[slot], 0, -1, h0 + r - 1, img);
-                }
-                __syncwarp();
-                if (++slot == NSLOT) {
-                    slot = 0;
-                    phase ^= 1;
-                }
+            const int ab = it & 1;
+            mbar_wait(&a_empty[ab], ((it >> 1) & 1) ^ 1);
+            if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(&a_full[ab], 2 * Cfg::ATILE_BYTES);
+                // pixels [-1, 63) of input rows h0-1 .. h0+2; out-of-image parts are zero-filled
+                tma_load_4d_2sm(smem_ring + ab * Cfg::ATILE_BYTES, &tmA, &a_full[ab], 0, -1, h0 - 1, img);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer (leader CTA only)
+        // ===================================================== conv2 MMA issuer (leader CTA only)
         if (rank == 0) {
             constexpr uint32_t idesc64 = umma_instr_desc(UMMA_FMT_BF16, 256, 64);
-            constexpr uint32_t idesc128 = umma_instr_desc(UMMA_FMT_BF16, 256, 128);
             const uint64_t ring_desc = umma_smem_desc(smem_u32(smem_ring), 0, 1024, UMMA_LAYOUT_SW128);
             const uint64_t w2_desc = umma_smem_desc(smem_u32(smem_w2), 0, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t w3_desc = umma_smem_desc(smem_u32(smem_w3), 0, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t wds_desc = umma_smem_desc(smem_u32(smem_wds), 0, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t w1n_desc = umma_smem_desc(smem_u32(smem_w1n), 0, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t a2_desc = umma_smem_desc(smem_u32(smem_a2), 0, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t p_desc = umma_smem_desc(smem_u32(smem_p), 0, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t pool_desc = umma_smem_desc(smem_u32(smem_pool), 0, 1024, UMMA_LAYOUT_SW128);
-            int slot = 0;
-            uint32_t ring_phase = 0;
-            uint32_t cx_phase_bits = 0;  // bit cs = parity of the next cx_full[cs] wait
             mbar_wait(w_full, 0);
             tc_fence_after();
-
-            // conv2 of tile i -> D1[i & 1]
-            auto conv2 = [&](int i) {
+            for (int i = 0; i < T; ++i) {
                 const int buf = i & 1;
-                mbar_wait(&d1_empty[buf], ((i >> 1) & 1) ^ 1);
+                const uint32_t ph = (i >> 1) & 1;
+                mbar_wait(&d1_empty[buf], ph ^ 1);
+                mbar_wait(&a_full[buf], ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + Cfg::D1_COL + buf * 64;
-                for (int r = 0; r < 3; ++r) {
-                    mbar_wait(&a_full[slot], ring_phase);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t a_slot = ring_desc + static_cast<uint64_t>((slot * Cfg::SLOT_BYTES) >> 4);
+                if (elect_one()) {
+                    const uint32_t d_tmem = tmem_base + Cfg::D1_COL + buf * 64;
+                    const uint64_t a_tile = ring_desc + static_cast<uint64_t>((buf * Cfg::ATILE_BYTES) >> 4);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
 #pragma unroll
                         for (int s = 0; s < 3; ++s) {
-                            const uint64_t a_tap = a_slot + static_cast<uint64_t>((s * 128) >> 4);
+                            // tap (r, s): the same tile, shifted by r input rows and s pixels (the 128-byte
+                            // swizzle is a function of the address bits, see conv3x3_halo.cuh)
+                            const uint64_t a_tap = a_tile + static_cast<uint64_t>((r * Cfg::AROW_BYTES + s * 128) >> 4);
                             const uint64_t b_tap = w2_desc + static_cast<uint64_t>(((r * 3 + s) * Cfg::W2_TAP_BYTES) >> 4);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 mma_f16_ss_2sm(d_tmem, a_tap + static_cast<uint64_t>(k * 2),
                                                b_tap + static_cast<uint64_t>(k * 2), idesc64, (r | s | k) != 0);
                         }
-                        tc_commit_2sm(&a_empty[slot]);
-                        if (r == 2) tc_commit_2sm(&d1_full[buf]);
                     }
-                    __syncwarp();
-                    if (++slot == NSLOT) {
-                        slot = 0;
-                        ring_phase ^= 1;
-                    }
+                    tc_commit_2sm(&a_empty[buf]);
+                    tc_commit_2sm(&d1_full[buf]);
                 }
-            };
+                __syncwarp();
+            }
+        }
+    } else if (warp == 12) {
+        // ===================================================== conv3 / conv1' MMA issuer (leader CTA only)
+        if (rank == 0) {
+            constexpr uint32_t idesc64 = umma_instr_desc(UMMA_FMT_BF16, 256, 64);
+            constexpr uint32_t idesc128 = umma_instr_desc(UMMA_FMT_BF16, 256, 128);
+            const uint64_t w3_desc = umma_smem_desc(smem_u32(smem_w3), 0, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t wds_desc = umma_smem_desc(smem_u32(smem_wds), 0, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t w1n_desc = umma_smem_desc(smem_u32(smem_w1n), 0, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t p_desc = umma_smem_desc(smem_u32(smem_p), 0, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t pool_desc = umma_smem_desc(smem_u32(smem_pool), 0, 1024, UMMA_LAYOUT_SW128);
+            uint32_t cx_phase_bits = 0;  // bit cs = parity of the next cx_full[cs] wait
+            mbar_wait(w_full, 0);
+            tc_fence_after();
+
             // conv3 of tile i, 128-channel half hf -> D2 half hf
             auto conv3 = [&](int i, int hf) {
                 const int buf = i & 1;
@@ -336,12 +371,11 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + Cfg::D2_COL + hf * 128;
-                    const uint64_t a = a2_desc + static_cast<uint64_t>((buf * Cfg::BOX_BYTES) >> 4);
+                    const uint32_t a_tmem = tmem_base + Cfg::A2_COL + buf * 32;
                     const uint64_t b = w3_desc + static_cast<uint64_t>((hf * Cfg::W3_HALF_BYTES) >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        mma_f16_ss_2sm(d_tmem, a + static_cast<uint64_t>(k * 2), b + static_cast<uint64_t>(k * 2),
-                                       idesc128, k != 0);
+                    for (int k = 0; k < 4; ++k)  // 16 BF16 of K = 8 TMEM columns per instruction
+                        mma_f16_ts_2sm(d_tmem, a_tmem + k * 8, b + static_cast<uint64_t>(k * 2), idesc128, k != 0);
                     if (DS) {
                         const uint64_t bd = wds_desc + static_cast<uint64_t>((hf * Cfg::W3_HALF_BYTES) >> 4);
 #pragma unroll
@@ -375,12 +409,9 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 __syncwarp();
             };
 
-            conv2(0);
-            if (T > 1) conv2(1);
             conv3(0, 0);
             conv3(0, 1);
             for (int i = 0; i < T; ++i) {
-                if (i + 2 < T) conv2(i + 2);
                 for (int j = 0; j < 4; ++j) {
                     if (g.has_next) conv1n(i, j);
                     if (j == 1 && i + 1 < T) conv3(i + 1, 0);
@@ -405,23 +436,48 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else if (warp == 3) {
         // ===================================================== store warp (both CTAs)
         // item = tile * IPT + sub: sub 0..3 = 64-channel boxes of y, sub 4 = t1' (has_next).
+        // Stores are pipelined: the box of item k is recycled only after the store of item k+1 has been
+        // issued (cp.async.bulk.wait_group.read 1), so one store is always in flight behind the one
+        // being waited for. Optional (debug bit 4; measured SLOWER on B200, 167 -> 190 us, so off):
+        // residual tiles pulled into L2 PF_TILES tiles ahead with cp.async.bulk.prefetch.tensor.
+        constexpr int PF_TILES = 3;
+        auto prefetch_tile = [&](int it_local) {  // whole 128-row x 256-channel residual tile -> L2
+            int img, h0;
+            tile_coords(it_local, img, h0);
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) tma_prefetch_4d(&tmRes, sub * 64, 0, h0, img);
+        };
         auto prepare = [&](int item) {  // make box (item % NPOOL) ready for `item`
             const int cs = item % NPOOL;
             const int it_local = item / IPT, sub = item - it_local * IPT;
-            if (!DS && sub < 4) {
+            if (!DS && sub < 4 && !(g.debug & 1)) {
                 int img, h0;
                 tile_coords(it_local, img, h0);
                 mbar_expect_tx(&box_ready[cs], Cfg::BOX_BYTES);
                 tma_load_4d(smem_pool + cs * Cfg::BOX_BYTES, &tmRes, &box_ready[cs], sub * 64, 0, h0, img);
+                if (sub == 0 && it_local + PF_TILES < T && (g.debug & 4)) prefetch_tile(it_local + PF_TILES);
             } else {
                 mbar_arrive(&box_ready[cs]);
             }
         };
         if (elect_one()) {
+            if (!DS && (g.debug & 4))
+                for (int t = 1; t < PF_TILES && t < T; ++t) prefetch_tile(t);
             for (int i = 0; i < NPOOL && i < items; ++i) prepare(i);
         }
         __syncwarp();
         uint32_t md_phase_bits = 0;  // bit cs = parity of the next c_mma_done[cs] wait
+        // recycle the box of `item` (its store has been read out of shared memory)
+        auto recycle = [&](int item) {
+            const int cs = item % NPOOL;
+            const int sub = item % IPT;
+            if (g.has_next && sub < 4) {  // conv1' must have consumed the box as well
+                mbar_wait(&c_mma_done[cs], (md_phase_bits >> cs) & 1);
+                md_phase_bits ^= 1u << cs;
+            }
+            if (item + NPOOL < items && elect_one()) prepare(item + NPOOL);
+            __syncwarp();
+        };
         for (int item = 0; item < items; ++item) {
             const int cs = item % NPOOL;
             const int it_local = item / IPT, sub = item - it_local * IPT;
@@ -429,8 +485,13 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (elect_one()) {
                 int img, h0;
                 tile_coords(it_local, img, h0);
+                if (g.debug & 8) {  // timing experiment: every store hits the same (L2-resident) tile
+                    img = static_cast<int>(blockIdx.x) % g.N;
+                    h0 = 0;
+                }
                 const uint8_t* box = smem_pool + cs * Cfg::BOX_BYTES;
-                if (sub < 4) {
+                if (g.debug & 2) {
+                } else if (sub < 4) {
                     tma_store_4d(&tmY, box, sub * 64, 0, h0, img);
                     tma_store_4d(&tmY, box + Cfg::PITCH * 128, sub * 64, 0, h0 + 1, img);
                 } else {
@@ -438,19 +499,17 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tma_store_4d(&tmT1n, box + Cfg::PITCH * 128, 0, 0, h0 + 1, img);
                 }
                 tma_store_commit();
-                tma_store_wait_read<0>();
+                tma_store_wait_read<1>();  // every store but the one just issued has left shared memory
             }
             __syncwarp();
-            if (g.has_next && sub < 4) {  // conv1' must have consumed the box as well
-                mbar_wait(&c_mma_done[cs], (md_phase_bits >> cs) & 1);
-                md_phase_bits ^= 1u << cs;
-            }
-            if (item + NPOOL < items && elect_one()) prepare(item + NPOOL);
-            __syncwarp();
+            if (item > 0) recycle(item - 1);
         }
+        if (elect_one()) tma_store_wait_read<0>();
+        __syncwarp();
+        if (items > 0) recycle(items - 1);
         if (elect_one()) tma_store_wait_all<0>();
         __syncwarp();
-    } else {
+    } else if (warp >= 4 && warp < 12) {
         // ===================================================== epilogue (both CTAs)
         const int q = warp & 3;
         const int h = (warp - 4) >> 2;  // which 32-column half of a 64-column group
@@ -464,7 +523,7 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             fence_proxy_async_smem();
             __syncwarp();
         };
-        // D1[i & 1] + bias2 -> ReLU -> A2[i & 1]
+        // D1[i & 1] + bias2 -> ReLU -> BF16 pairs -> A2[i & 1] in TMEM (the A operand of conv3)
         auto E1 = [&](int i) {
             const int buf = i & 1;
             mbar_wait(&d1_full[buf], (i >> 1) & 1);
@@ -473,9 +532,18 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             __syncwarp();
             tmem_ld_32x32(lane_base + Cfg::D1_COL + buf * 64 + h * 32, v);
             tmem_ld_wait();
-            epilogue_chunk<2>(v, smem_a2 + buf * Cfg::BOX_BYTES + row_off, static_cast<uint32_t>(h * 4), swz,
-                              prm.bias2 + h * 32, 0, 1);
-            publish();
+            uint32_t pk[16];
+            const float* b32 = prm.bias2 + h * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(b32 + j * 4));
+                pk[j * 2 + 0] = pack_bf16x2_relu(__uint_as_float(v[j * 4 + 0]) + b.x, __uint_as_float(v[j * 4 + 1]) + b.y);
+                pk[j * 2 + 1] = pack_bf16x2_relu(__uint_as_float(v[j * 4 + 2]) + b.z, __uint_as_float(v[j * 4 + 3]) + b.w);
+            }
+            tmem_st_32x16(lane_base + Cfg::A2_COL + buf * 32 + h * 16, pk);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
             if (lane == 0) {
                 mbar_arrive_leader(&d1_empty[buf]);
                 mbar_arrive_leader(&a2_full[buf]);

@@ -90,64 +90,91 @@ __device__ __forceinline__ float round_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// relu + round-to-nearest BF16 of two floats in one instruction
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
 // One 32-column chunk of the accumulator: + bias (+ residual read from the staging row) -> ReLU ->
 // round to the activation type -> write back to the same swizzled staging row.
+// All loads (residual from shared memory, bias) are issued before the first store so that their
+// latencies overlap (the staging row is addressed in the shared window: the compiler cannot prove
+// that a generic store does not alias the next generic load and would serialise them).
 template <int ESZ>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint8_t* row, uint32_t c16_base,
                                                uint32_t swz, const float* __restrict__ bias32,
                                                int has_res, int relu) {
+    const uint32_t row_addr = ptx::smem_u32(row);
     if (ESZ == 2) {
+        uint4 rr[4];
+        if (has_res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rr[j] = lds128(row_addr + (((c16_base + j) ^ swz) << 4));
+        }
+        float4 b[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = __ldg(reinterpret_cast<const float4*>(bias32 + j * 4));
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            uint4* p16 = reinterpret_cast<uint4*>(row + (((c16_base + j) ^ swz) << 4));
             float x[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias32 + j * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias32 + j * 8 + 4));
-            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-            x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            x[0] += b[2 * j].x; x[1] += b[2 * j].y; x[2] += b[2 * j].z; x[3] += b[2 * j].w;
+            x[4] += b[2 * j + 1].x; x[5] += b[2 * j + 1].y; x[6] += b[2 * j + 1].z; x[7] += b[2 * j + 1].w;
             if (has_res) {
-                const uint4 rr = *p16;
-                x[0] += bf16_lo(rr.x); x[1] += bf16_hi(rr.x);
-                x[2] += bf16_lo(rr.y); x[3] += bf16_hi(rr.y);
-                x[4] += bf16_lo(rr.z); x[5] += bf16_hi(rr.z);
-                x[6] += bf16_lo(rr.w); x[7] += bf16_hi(rr.w);
+                x[0] += bf16_lo(rr[j].x); x[1] += bf16_hi(rr[j].x);
+                x[2] += bf16_lo(rr[j].y); x[3] += bf16_hi(rr[j].y);
+                x[4] += bf16_lo(rr[j].z); x[5] += bf16_hi(rr[j].z);
+                x[6] += bf16_lo(rr[j].w); x[7] += bf16_hi(rr[j].w);
             }
-            if (relu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e], 0.f);
-            }
-            uint4 o;
-            o.x = pack_bf16x2(x[0], x[1]);
-            o.y = pack_bf16x2(x[2], x[3]);
-            o.z = pack_bf16x2(x[4], x[5]);
-            o.w = pack_bf16x2(x[6], x[7]);
-            *p16 = o;
+            const uint32_t dst = row_addr + (((c16_base + j) ^ swz) << 4);
+            if (relu)
+                sts128(dst, pack_bf16x2_relu(x[0], x[1]), pack_bf16x2_relu(x[2], x[3]),
+                       pack_bf16x2_relu(x[4], x[5]), pack_bf16x2_relu(x[6], x[7]));
+            else
+                sts128(dst, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                       pack_bf16x2(x[6], x[7]));
         }
     } else {
+        // 32 fp32 columns = 8 16-byte pieces of the row; residual loaded four pieces at a time
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            uint4* p16 = reinterpret_cast<uint4*>(row + (((c16_base + j) ^ swz) << 4));
-            float x[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(v[j * 4 + e]);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias32 + j * 4));
-            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+        for (int half = 0; half < 2; ++half) {
+            uint4 rr[4];
             if (has_res) {
-                const float4 rr = *reinterpret_cast<const float4*>(p16);
-                x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
-            }
-            if (relu) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+                for (int j = 0; j < 4; ++j) rr[j] = lds128(row_addr + (((c16_base + half * 4 + j) ^ swz) << 4));
             }
-            uint4 o;
-            o.x = __float_as_uint(round_tf32(x[0]));
-            o.y = __float_as_uint(round_tf32(x[1]));
-            o.z = __float_as_uint(round_tf32(x[2]));
-            o.w = __float_as_uint(round_tf32(x[3]));
-            *p16 = o;
+            float4 b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = __ldg(reinterpret_cast<const float4*>(bias32 + (half * 4 + j) * 4));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float x[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(v[(half * 4 + j) * 4 + e]);
+                x[0] += b[j].x; x[1] += b[j].y; x[2] += b[j].z; x[3] += b[j].w;
+                if (has_res) {
+                    x[0] += __uint_as_float(rr[j].x); x[1] += __uint_as_float(rr[j].y);
+                    x[2] += __uint_as_float(rr[j].z); x[3] += __uint_as_float(rr[j].w);
+                }
+                if (relu) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+                }
+                sts128(row_addr + (((c16_base + half * 4 + j) ^ swz) << 4), __float_as_uint(round_tf32(x[0])),
+                       __float_as_uint(round_tf32(x[1])), __float_as_uint(round_tf32(x[2])),
+                       __float_as_uint(round_tf32(x[3])));
+            }
         }
     }
 }

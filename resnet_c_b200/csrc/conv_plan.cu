@@ -132,6 +132,7 @@ int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, 
     g.tiles = d.B * g.tiles_per_img;
     g.has_next = d.w1n ? 1 : 0;
     g.reverse = d.reverse ? 1 : 0;
+    g.debug = getenv("RNB_BNECK_DEBUG") ? atoi(getenv("RNB_BNECK_DEBUG")) : 0;
     plan->bp.bias2 = d.bias2;
     plan->bp.bias3 = d.bias3;
     plan->bp.bias1n = d.bias1n ? d.bias1n : d.bias2;
@@ -149,7 +150,7 @@ int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, 
         return make_tiled_nd(tm, TmDtype::BF16, base, 4, dims, strides, box, true);
     };
     int r;
-    if ((r = act_map(&plan->tmA, d.t1, 64, 64, 2)) != 0) return fail(err, errlen, "bneck_plan: t1 tensor map failed", r);
+    if ((r = act_map(&plan->tmA, d.t1, 64, 64, 4)) != 0) return fail(err, errlen, "bneck_plan: t1 tensor map failed", r);
     if ((r = make_tiled_2d(&plan->tmB, TmDtype::BF16, d.w2, 64, 576, 32)) != 0)
         return fail(err, errlen, "bneck_plan: w2 tensor map failed", r);
     if ((r = make_tiled_2d(&plan->tmW3, TmDtype::BF16, d.w3, 256, 64, 64)) != 0)
