@@ -50,18 +50,19 @@ struct ConvGeom {
     int reverse;
 };
 
-template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_>
+template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_, int OSZ_ = ESZ_>
 struct ConvCfg {
     static constexpr int BM = 128;
     static constexpr int BN = BN_;
     static constexpr int ESZ = ESZ_;                 // bytes per activation/weight element (2 = bf16, 4 = tf32)
+    static constexpr int OSZ = OSZ_;                 // bytes per OUTPUT element; OSZ != ESZ: unrounded FP32 out (FC)
     static constexpr int BK = 128 / ESZ_;            // one 128-byte swizzle row of K per stage
     static constexpr int NSTAGE = NSTAGE_;
     static constexpr int NCBUF = NCBUF_;             // epilogue staging buffers (>= 2)
     static constexpr int A_BYTES = BM * 128;
     static constexpr int B_BYTES = BN_ * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BOX_COLS = 128 / ESZ_;      // output columns per 128-byte staging row
+    static constexpr int BOX_COLS = 128 / OSZ_;      // output columns per 128-byte staging row
     static constexpr int NBOX = BN_ / BOX_COLS;
     static constexpr int BOX_BYTES = BM * 128;
     static constexpr int CBUF_BYTES = NBOX * BOX_BYTES;
@@ -176,6 +177,30 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint8_t*
                        __float_as_uint(round_tf32(x[3])));
             }
         }
+    }
+}
+
+// FP32-output variant (the FC layer: logits stay FP32): 32 columns = one full 128-byte staging row,
+// + bias, optional ReLU, NO rounding, no residual.
+__device__ __forceinline__ void epilogue_chunk_f32out(const uint32_t (&v)[32], uint8_t* row, uint32_t swz,
+                                                      const float* __restrict__ bias32, int relu) {
+    const uint32_t row_addr = ptx::smem_u32(row);
+    float4 b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = __ldg(reinterpret_cast<const float4*>(bias32 + j * 4));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float x[4];
+        x[0] = __uint_as_float(v[j * 4 + 0]) + b[j].x;
+        x[1] = __uint_as_float(v[j * 4 + 1]) + b[j].y;
+        x[2] = __uint_as_float(v[j * 4 + 2]) + b[j].z;
+        x[3] = __uint_as_float(v[j * 4 + 3]) + b[j].w;
+        if (relu) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+        }
+        sts128(row_addr + ((static_cast<uint32_t>(j) ^ swz) << 4), __float_as_uint(x[0]), __float_as_uint(x[1]),
+               __float_as_uint(x[2]), __float_as_uint(x[3]));
     }
 }
 
@@ -408,10 +433,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 __syncwarp();
                 tmem_ld_32x32(taddr + chunk * 32, v);
                 tmem_ld_wait();
-                const int byte_off = chunk * 32 * Cfg::ESZ;
+                const int byte_off = chunk * 32 * Cfg::OSZ;
                 uint8_t* row = cbuf + (byte_off >> 7) * Cfg::BOX_BYTES + row_in_tile * 128;
-                epilogue_chunk<Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz, bias_n + chunk * 32,
-                                         g.has_res, g.relu);
+                if (Cfg::OSZ != Cfg::ESZ)
+                    epilogue_chunk_f32out(v, row, swz, bias_n + chunk * 32, g.relu);
+                else
+                    epilogue_chunk<Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz, bias_n + chunk * 32,
+                                             g.has_res, g.relu);
             }
             // accumulator drained by this warp: hand the TMEM stage back; publish the staged rows
             // to the async proxy and tell the store warp

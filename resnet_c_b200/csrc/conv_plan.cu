@@ -24,6 +24,8 @@ using Cfg2Tf32N256 = Conv2Cfg<256, 4, 4, 3>;
 using Cfg2Tf32N128 = Conv2Cfg<128, 4, 5, 3>;
 // deep variants (bf16 only): one/two more pipeline stages, two staging buffers
 using CfgBf16N128D = ConvCfg<128, 2, 5, 2>;
+using CfgBf16N64F32 = ConvCfg<64, 2, 4, 3, 4>;  // BF16 operands, FP32 output (FC)
+static_assert(CfgBf16N64F32::SMEM_BYTES <= 232448, "smem budget");
 using Cfg2Bf16N256D = Conv2Cfg<256, 2, 5, 2>;
 using Cfg2Bf16N128D = Conv2Cfg<128, 2, 6, 2>;
 static_assert(CfgBf16N128D::SMEM_BYTES <= 232448, "smem budget");
@@ -61,6 +63,7 @@ cudaError_t conv_kernels_init() {
     if ((e = set_smem2<Cfg2Tf32N256>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Tf32N128>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgBf16N128D>()) != cudaSuccess) return e;
+    if ((e = set_smem<CfgBf16N64F32>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Bf16N256D>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Bf16N128D>()) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_halo_kernel<HaloCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -176,6 +179,11 @@ int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, 
 int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn, char* err,
                    int errlen) {
     memset(plan, 0, sizeof(*plan));
+    if (d.out_f32) {
+        if (d.act != ActType::BF16 || d.residual || d.out_cols <= 0 || d.out_cols > d.Cout || d.out_cols % 4 != 0)
+            return fail(err, errlen, "conv_plan: FP32-output mode needs BF16 operands, no residual, out_cols % 4 == 0", -8);
+        force_bn = 64;
+    }
     if (force_bn == 3064 || (force_bn == 0 && conv_plan_halo_ok(d) && !getenv("RNB_NO_HALO")))
         return halo_plan_init(plan, d, num_sms, err, errlen);
     // +10000: "deep" variant of a tile family — one or two more shared-memory stages in flight paid
@@ -257,10 +265,19 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     const uint64_t K = 1ull * d.ksize * d.ksize * d.Cin;
     if ((r = make_tiled_2d(&plan->tmB, dt, d.weight, d.Cout, K, ctas == 2 ? bn / 2 : bn)) != 0)
         return fail(err, errlen, "conv_plan: tiled tensor map (B) failed", r);
-    if ((r = make_tiled_2d(&plan->tmOut, dt, d.out, M, d.Cout, 128)) != 0)
+    plan->f32out = d.out_f32 ? 1 : 0;
+    if (d.out_f32) {
+        if ((r = make_tiled_2d(&plan->tmOut, TmDtype::F32, d.out, M, d.out_cols, 128)) != 0)
+            return fail(err, errlen, "conv_plan: tiled tensor map (fp32 out) failed", r);
+        plan->bytes = 1.0 * d.B * d.H * d.W * d.Cin * esz + 1.0 * d.out_cols * d.Cin * esz + 4.0 * d.out_cols +
+                      4.0 * static_cast<double>(M) * d.out_cols;
+        plan->flops = 2.0 * static_cast<double>(M) * d.out_cols * d.Cin;
+    } else if ((r = make_tiled_2d(&plan->tmOut, dt, d.out, M, d.Cout, 128)) != 0)
         return fail(err, errlen, "conv_plan: tiled tensor map (out) failed", r);
     const void* res = d.residual ? d.residual : d.out;
-    if ((r = make_tiled_2d(&plan->tmRes, dt, res, M, d.Cout, 128)) != 0)
+    if (d.out_f32)
+        plan->tmRes = plan->tmOut;
+    else if ((r = make_tiled_2d(&plan->tmRes, dt, res, M, d.Cout, 128)) != 0)
         return fail(err, errlen, "conv_plan: tiled tensor map (residual) failed", r);
     return 0;
 }
@@ -314,6 +331,7 @@ cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
         return launch_pdl(conv3x3_halo_kernel<HaloCfg>, p.grid, HaloCfg::THREADS, HaloCfg::SMEM_BYTES, stream,
                           p.tmA, p.tmB, p.tmOut, p.bias, p.hg);
     }
+    if (p.f32out) return launch<CfgBf16N64F32>(p, stream);
     if (p.deep && p.esz == 2) {
         if (p.ctas == 2) return p.bn == 256 ? launch2<Cfg2Bf16N256D>(p, stream) : launch2<Cfg2Bf16N128D>(p, stream);
         if (p.bn == 128) return launch<CfgBf16N128D>(p, stream);

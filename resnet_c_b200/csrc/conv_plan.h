@@ -21,6 +21,10 @@ struct ConvDesc {
     const float* bias;     // [Cout] fp32 (folded BN shift)
     const void* residual;  // NHWC [B][OH][OW][Cout] or nullptr
     void* out;             // NHWC [B][OH][OW][Cout]
+    // FC mode (BF16 operands only): the output is UNROUNDED FP32, row-major [M][out_cols] with
+    // out_cols <= Cout (weights / bias are padded to Cout rows; the padded columns are clipped by TMA)
+    bool out_f32 = false;
+    int out_cols = 0;
 };
 
 // Fused layer1 Bottleneck tail (bneck_l1.cuh): conv2 3x3 + conv3 1x1 + shortcut + ReLU, optionally
@@ -52,6 +56,7 @@ struct ConvPlan {
     int bn;       // tile N
     int ctas;     // 1 = single-CTA 128-pixel tiles, 2 = CTA-pair 256-pixel tiles (cta_group::2)
     int deep;     // 1 = deeper smem pipeline / fewer staging buffers variant of the tile family (bf16)
+    int f32out;   // 1 = FP32-output variant of the single-CTA kernel (FC layer)
     int halo;     // 1 = conv3x3_halo_kernel (3x3/1, 64->64, bf16): tmA/tmOut are 4-D tiled maps, geometry in hg
     HaloGeom hg;
     int esz;      // element bytes

@@ -93,8 +93,12 @@ inline cudaError_t launch_stem_any_part(int esz, int part, const float* x, void*
 
 // ---- tail (tail.cu)
 // global average pool over NHWC [B,HW,C] -> pooledT [C][B] fp32 (transposed, see tail.cu)
-cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, int B, int HW, int C, int esz,
+// (+ optional row-major BF16 copy pooled_bf16[B][C] for the tensor-core FC; BF16 activations only)
+cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, void* pooled_bf16, int B, int HW, int C, int esz,
                                 cudaStream_t s);
+// fc.weight [classes][C] fp32 -> [cpad][C] bf16 (zero rows beyond classes), fc.bias -> [cpad] fp32
+cudaError_t launch_fc_pack(const float* w, const float* b, void* wq, float* bq, int classes, int C, int cpad,
+                           cudaStream_t s);
 // logits[B,classes] = pooledT[C,B]^T * W[classes,C]^T + bias
 cudaError_t launch_fc(const float* pooledT, const float* w, const float* bias, float* logits, int B,
                       int C, int classes, cudaStream_t s);

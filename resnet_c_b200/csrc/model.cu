@@ -147,6 +147,7 @@ Model::~Model() {
     }
     arena.free_all();
     cudaFree(stem_w); cudaFree(stem_bias); cudaFree(stem_wk); cudaFree(fc_w); cudaFree(fc_b);
+    cudaFree(fc_wq); cudaFree(fc_bq);
     cudaFree(host_x_dev); cudaFree(host_logits_dev); cudaFree(host_top1_dev); cudaFree(scratch_logits);
     for (auto& b : blocks) {
         for (ConvWeights* c : {&b.conv1, &b.conv2, &b.conv3, &b.ds}) {
@@ -288,6 +289,16 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
         if ((r = read_f32_file(dir + "/fc.weight", 1ull * classes * final_c, h)) || (r = upload(h, &fc_w)))
             return r;
         macs += 1.0 * classes * final_c;
+        // BF16 path: FC on tensor cores (BF16 operands, FP32 accumulate and FP32 logits)
+        const char* ft = getenv("RNB_FC_TC");
+        fc_tc = esz == 2 && final_c % 64 == 0 && classes % 4 == 0 && !(ft && atoi(ft) == 0);
+        if (fc_tc) {
+            classes_pad = (classes + 63) / 64 * 64;
+            RNB_CUDA(cudaMalloc(&fc_wq, 1ull * classes_pad * final_c * 2));
+            RNB_CUDA(cudaMalloc(&fc_bq, classes_pad * sizeof(float)));
+            RNB_CUDA(launch_fc_pack(fc_w, fc_b, fc_wq, fc_bq, classes, final_c, classes_pad, 0));
+            RNB_CUDA(cudaDeviceSynchronize());
+        }
     }
     flops_per_image = 2.0 * macs;
     RNB_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -485,10 +496,16 @@ ChunkPlan* Model::plan_for(int n) {
     p.pooled = static_cast<float*>(arena.acquire(1ull * n * final_c * sizeof(float)));
     if (!p.pooled) return fail_alloc();
     p.named["avgpool"] = {p.pooled, final_c, 1, 1};
+    if (fc_tc) {
+        if (!(p.pooled_bf16 = arena.acquire(1ull * n * final_c * 2))) return fail_alloc();
+        // the logits buffer is the caller's: the output tensor map is patched per launch target in
+        // enqueue_chunk (fc_plan_for), here only the shape-dependent part is fixed
+    }
     // Everything is released again: the next plan (another chunk size) may share the blocks, since
     // chunks run back to back on one stream.
     arena.release(x);
     arena.release(p.pooled);
+    if (p.pooled_bf16) arena.release(p.pooled_bf16);
     auto ins = plans.emplace(n, std::move(p));
     return &ins.first->second;
 }
@@ -514,9 +531,35 @@ int Model::enqueue_chunk(ChunkPlan& p, const float* x, float* logits, int32_t* t
             }
         }
     }
-    RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, n, p.last_hw, p.last_c, esz, s));
-    RNB_CUDA(launch_fc(p.pooled, fc_w, fc_b, logits, n, p.last_c, classes, s));
+    RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, p.pooled_bf16, n, p.last_hw, p.last_c, esz, s));
+    int r = enqueue_fc(p, logits, s);
+    if (r) return r;
     if (top1) RNB_CUDA(launch_argmax_f32(logits, top1, n, classes, s));
+    return RNB_OK;
+}
+
+// logits = pooled x fc.weight^T + fc.bias (Linear::forward, nn.cu:55-64; main.cu:222-224). BF16 path:
+// the single-CTA tcgen05 conv kernel as a 1x1 "conv" over [n,1,1,C] with unrounded FP32 output straight
+// into the caller's logits buffer (plan cached per output pointer); otherwise the FP32 CUDA-core kernel.
+int Model::enqueue_fc(ChunkPlan& p, float* logits, cudaStream_t s) {
+    if (!p.pooled_bf16) {
+        RNB_CUDA(launch_fc(p.pooled, fc_w, fc_b, logits, p.n, p.last_c, classes, s));
+        return RNB_OK;
+    }
+    if (p.fc_out != logits) {
+        ConvDesc d{};
+        d.B = p.n; d.H = 1; d.W = 1; d.Cin = p.last_c; d.Cout = classes_pad;
+        d.ksize = 1; d.stride = 1; d.pad = 0; d.relu = false; d.act = ActType::BF16;
+        d.in = p.pooled_bf16; d.weight = fc_wq; d.bias = fc_bq; d.residual = nullptr; d.out = logits;
+        d.out_f32 = true; d.out_cols = classes;
+        char err[256];
+        if (conv_plan_init(&p.fc_plan, d, num_sms, 0, err, sizeof(err))) {
+            set_error(err);
+            return RNB_ERR_CUDA;
+        }
+        p.fc_out = logits;
+    }
+    RNB_CUDA(conv_plan_launch(p.fc_plan, s));
     return RNB_OK;
 }
 
@@ -612,9 +655,12 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
             RNB_CUDA(conv_plan_launch(cp, s));
             RNB_CUDA(cudaEventRecord(ev[++i], s));
         }
-        RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, n, p.last_hw, p.last_c, esz, s));
+        RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, p.pooled_bf16, n, p.last_hw, p.last_c, esz, s));
         RNB_CUDA(cudaEventRecord(ev[++i], s));
-        RNB_CUDA(launch_fc(p.pooled, fc_w, fc_b, scratch_logits, n, p.last_c, classes, s));
+        {
+            int rr = enqueue_fc(p, scratch_logits, s);
+            if (rr) return rr;
+        }
         RNB_CUDA(cudaEventRecord(ev[++i], s));
         RNB_CUDA(launch_argmax_f32(scratch_logits, host_top1_dev, n, classes, s));
         RNB_CUDA(cudaEventRecord(ev[++i], s));

@@ -45,7 +45,10 @@ struct ChunkPlan {
     std::vector<ConvPlan> convs;
     void* last = nullptr;       // NHWC [n,7,7,C_final]
     int last_hw = 0, last_c = 0;
-    float* pooled = nullptr;    // [n, C_final]
+    float* pooled = nullptr;    // [C_final][n] fp32 (transposed, see tail.cu)
+    void* pooled_bf16 = nullptr;  // [n][C_final] bf16: A operand of the tensor-core FC (BF16 path)
+    float* fc_out = nullptr;    // logits pointer fc_plan was built for
+    ConvPlan fc_plan;           // FC as a 1x1 conv on tcgen05 with FP32 output (BF16 path); valid iff pooled_bf16
     std::map<std::string, NamedAct> named;
 };
 
@@ -80,6 +83,10 @@ struct Model {
     std::vector<BlockWeights> blocks;
     float* fc_w = nullptr;  // [classes][final_c]
     float* fc_b = nullptr;
+    void* fc_wq = nullptr;   // [classes_pad][final_c] bf16 (BF16 path: tensor-core FC), rows >= classes zero
+    float* fc_bq = nullptr;  // [classes_pad]
+    int classes_pad = 0;
+    bool fc_tc = false;      // RNB_FC_TC=0 keeps the FP32 CUDA-core FC
     int num_convs = 0;
     double flops_per_image = 0;
 
@@ -109,6 +116,7 @@ struct Model {
     int load(const std::string& arch, int dtype, const std::string& dir, int max_batch, int chunk);
     ChunkPlan* plan_for(int n);
     int enqueue_chunk(ChunkPlan& p, const float* x, float* logits, int32_t* top1, cudaStream_t s);
+    int enqueue_fc(ChunkPlan& p, float* logits, cudaStream_t s);
     int forward(const float* x, int batch, float* logits, int32_t* top1, cudaStream_t s);
     int forward_host(const float* x, int batch, float* logits, int32_t* top1);
     // pipelined host path: two slots, each with its own device input / output buffers

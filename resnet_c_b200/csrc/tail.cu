@@ -16,12 +16,18 @@ namespace rnb {
 
 namespace {
 
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 // [n][HW][C] T -> pooledT[C][n] fp32. One thread per (image, 16-byte channel group); consecutive
 // threads read consecutive 16-byte groups of the same pixel (coalesced). The sum is sequential over
 // pixels in FP32 as in avgPool2dKernel, and divided by k twice when HW = k*k (ops.cu:107).
 template <typename T>
-__global__ void avgpool_nhwc_kernel(const T* __restrict__ x, float* __restrict__ pooledT, int n, int HW,
-                                    int C, int ksq) {
+__global__ void avgpool_nhwc_kernel(const T* __restrict__ x, float* __restrict__ pooledT,
+                                    __nv_bfloat16* __restrict__ pooled_bf16, int n, int HW, int C, int ksq) {
     constexpr int VEC = 16 / sizeof(T);
     const int groups = C / VEC;
     const int64_t total = 1LL * n * groups;
@@ -33,6 +39,8 @@ __global__ void avgpool_nhwc_kernel(const T* __restrict__ x, float* __restrict__
         float acc[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+        // unrolled: seven independent 16-byte loads in flight per thread (the adds stay in pixel order)
+#pragma unroll 7
         for (int p = 0; p < HW; ++p) {
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(xp + 1LL * p * C));
             if constexpr (sizeof(T) == 2) {
@@ -50,10 +58,31 @@ __global__ void avgpool_nhwc_kernel(const T* __restrict__ x, float* __restrict__
             }
         }
 #pragma unroll
-        for (int e = 0; e < VEC; ++e)
-            pooledT[1LL * (gidx * VEC + e) * n + b] =
-                ksq > 0 ? acc[e] / static_cast<float>(ksq) / static_cast<float>(ksq)
-                        : acc[e] / static_cast<float>(HW);
+        for (int e = 0; e < VEC; ++e) {
+            acc[e] = ksq > 0 ? acc[e] / static_cast<float>(ksq) / static_cast<float>(ksq)
+                             : acc[e] / static_cast<float>(HW);
+            pooledT[1LL * (gidx * VEC + e) * n + b] = acc[e];
+        }
+        if constexpr (sizeof(T) == 2) {
+            if (pooled_bf16) {  // row-major BF16 copy: the A operand of the tensor-core FC
+                uint4 o;
+                o.x = pack2(acc[0], acc[1]); o.y = pack2(acc[2], acc[3]);
+                o.z = pack2(acc[4], acc[5]); o.w = pack2(acc[6], acc[7]);
+                *reinterpret_cast<uint4*>(pooled_bf16 + 1LL * b * C + gidx * VEC) = o;
+            }
+        }
+    }
+}
+
+// fc.weight [classes][C] fp32 -> [cpad][C] bf16 (rows >= classes zero), fc.bias -> [cpad] fp32 (zero padded)
+__global__ void fc_pack_kernel(const float* __restrict__ w, const float* __restrict__ b,
+                               __nv_bfloat16* __restrict__ wq, float* __restrict__ bq, int classes, int C,
+                               int cpad) {
+    const int64_t total = 1LL * cpad * C;
+    for (int64_t i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int o = static_cast<int>(i / C);
+        wq[i] = __float2bfloat16_rn(o < classes ? w[i] : 0.f);
+        if (i < cpad) bq[i] = i < classes ? b[i] : 0.f;
     }
 }
 
@@ -154,7 +183,13 @@ __global__ void transpose_f32_kernel(const float* __restrict__ in, float* __rest
 
 }  // namespace
 
-cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, int B, int HW, int C, int esz,
+cudaError_t launch_fc_pack(const float* w, const float* b, void* wq, float* bq, int classes, int C, int cpad,
+                           cudaStream_t s) {
+    fc_pack_kernel<<<1024, 256, 0, s>>>(w, b, static_cast<__nv_bfloat16*>(wq), bq, classes, C, cpad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, void* pooled_bf16, int B, int HW, int C, int esz,
                                 cudaStream_t s) {
     int ksq = 0;
     for (int k = 1; k * k <= HW; ++k)
@@ -163,9 +198,9 @@ cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, int B, int HW, in
     const int blocks = static_cast<int>((total + 127) / 128);
     if (esz == 2)
         avgpool_nhwc_kernel<__nv_bfloat16><<<blocks, 128, 0, s>>>(
-            static_cast<const __nv_bfloat16*>(x), pooledT, B, HW, C, ksq);
+            static_cast<const __nv_bfloat16*>(x), pooledT, static_cast<__nv_bfloat16*>(pooled_bf16), B, HW, C, ksq);
     else
-        avgpool_nhwc_kernel<float><<<blocks, 128, 0, s>>>(static_cast<const float*>(x), pooledT, B, HW,
+        avgpool_nhwc_kernel<float><<<blocks, 128, 0, s>>>(static_cast<const float*>(x), pooledT, nullptr, B, HW,
                                                          C, ksq);
     return cudaGetLastError();
 }
