@@ -2,7 +2,7 @@
 # usage: tools/fuse_bench.sh tag "fuse next" ...   (GPU box) — bench + per-launch profile per config
 tag=$1; shift
 for cfg in "$@"; do set -- $cfg
-  RNB_FUSE=$1 RNB_FUSE_NEXT=$2 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --profile-out gpurun_out/prof${tag}_$1$2.json > gpurun_out/bench${tag}_$1$2.json 2> gpurun_out/bench${tag}_$1$2.err
+  RNB_FUSE=$1 RNB_FUSE_NEXT=$2 timeout 60 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --profile-out gpurun_out/prof${tag}_$1$2.json > gpurun_out/bench${tag}_$1$2.json 2> gpurun_out/bench${tag}_$1$2.err
   python - <<P
 import json
 d=json.loads(open("gpurun_out/bench${tag}_$1$2.json").read().strip().splitlines()[-1])
