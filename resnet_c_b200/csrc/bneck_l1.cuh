@@ -499,14 +499,20 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tma_store_4d(&tmT1n, box + Cfg::PITCH * 128, 0, 0, h0 + 1, img);
                 }
                 tma_store_commit();
-                tma_store_wait_read<1>();  // every store but the one just issued has left shared memory
+                if (g.debug & 32)
+                    tma_store_wait_read<0>();
+                else
+                    tma_store_wait_read<1>();  // every store but the one just issued has left shared memory
             }
             __syncwarp();
-            if (item > 0) recycle(item - 1);
+            if (g.debug & 32)
+                recycle(item);
+            else if (item > 0)
+                recycle(item - 1);
         }
         if (elect_one()) tma_store_wait_read<0>();
         __syncwarp();
-        if (items > 0) recycle(items - 1);
+        if (items > 0 && !(g.debug & 32)) recycle(items - 1);
         if (elect_one()) tma_store_wait_all<0>();
         __syncwarp();
     } else if (warp >= 4 && warp < 12) {
@@ -537,8 +543,12 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(b32 + j * 4));
-                pk[j * 2 + 0] = pack_bf16x2_relu(__uint_as_float(v[j * 4 + 0]) + b.x, __uint_as_float(v[j * 4 + 1]) + b.y);
-                pk[j * 2 + 1] = pack_bf16x2_relu(__uint_as_float(v[j * 4 + 2]) + b.z, __uint_as_float(v[j * 4 + 3]) + b.w);
+                float x0 = __uint_as_float(v[j * 4 + 0]), x1 = __uint_as_float(v[j * 4 + 1]);
+                float x2 = __uint_as_float(v[j * 4 + 2]), x3 = __uint_as_float(v[j * 4 + 3]);
+                add2(x0, x1, b.x, b.y);
+                add2(x2, x3, b.z, b.w);
+                pk[j * 2 + 0] = pack_bf16x2_relu(x0, x1);
+                pk[j * 2 + 1] = pack_bf16x2_relu(x2, x3);
             }
             tmem_st_32x16(lane_base + Cfg::A2_COL + buf * 32 + h * 16, pk);
             tmem_st_wait();

@@ -97,6 +97,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// (a0, a1) += (b0, b1) as ONE packed FP32 instruction (FADD2, sm_100): IEEE round-to-nearest per lane,
+// i.e. bit-identical to two FADDs at half the issue slots — the epilogues are issue-bound
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+    asm("{\n\t"
+        ".reg .b64 ra, rb;\n\t"
+        "mov.b64 ra, {%0, %1};\n\t"
+        "mov.b64 rb, {%2, %3};\n\t"
+        "add.rn.f32x2 ra, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, ra;\n\t"
+        "}"
+        : "+f"(a0), "+f"(a1)
+        : "f"(b0), "f"(b1));
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -130,13 +143,15 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint8_t*
             float x[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]);
-            x[0] += b[2 * j].x; x[1] += b[2 * j].y; x[2] += b[2 * j].z; x[3] += b[2 * j].w;
-            x[4] += b[2 * j + 1].x; x[5] += b[2 * j + 1].y; x[6] += b[2 * j + 1].z; x[7] += b[2 * j + 1].w;
+            add2(x[0], x[1], b[2 * j].x, b[2 * j].y);
+            add2(x[2], x[3], b[2 * j].z, b[2 * j].w);
+            add2(x[4], x[5], b[2 * j + 1].x, b[2 * j + 1].y);
+            add2(x[6], x[7], b[2 * j + 1].z, b[2 * j + 1].w);
             if (has_res) {
-                x[0] += bf16_lo(rr[j].x); x[1] += bf16_hi(rr[j].x);
-                x[2] += bf16_lo(rr[j].y); x[3] += bf16_hi(rr[j].y);
-                x[4] += bf16_lo(rr[j].z); x[5] += bf16_hi(rr[j].z);
-                x[6] += bf16_lo(rr[j].w); x[7] += bf16_hi(rr[j].w);
+                add2(x[0], x[1], bf16_lo(rr[j].x), bf16_hi(rr[j].x));
+                add2(x[2], x[3], bf16_lo(rr[j].y), bf16_hi(rr[j].y));
+                add2(x[4], x[5], bf16_lo(rr[j].z), bf16_hi(rr[j].z));
+                add2(x[6], x[7], bf16_lo(rr[j].w), bf16_hi(rr[j].w));
             }
             const uint32_t dst = row_addr + (((c16_base + j) ^ swz) << 4);
             if (relu)
