@@ -299,6 +299,32 @@ def main():
     e2e_value = world * B * e2e_steps / t.item()
     same = same and bool((th2[0].to(dev) == top1).all().item())
 
+    # ---- the same serving loop fed with DECODED uint8 HWC images (rnb_model_submit_host_u8): the /255 +
+    # mean/std normalisation of convert_imgs_to_bin.py:18 runs on the GPU inside the stem pre-pass, so a
+    # quarter of the bytes cross PCIe. Reported beside `e2e` (which keeps the reference's FP32 tensor input).
+    e2e_u8 = None
+    if hasattr(model, "submit_host_u8"):
+        xu = [weights.synthetic_images_u8(B, seed=77 + rank + i).pin_memory() for i in range(2)]
+        for i in range(2):
+            model.submit_host_u8(i, xu[i], lh2[i], th2[i])
+        for i in range(2):
+            model.wait_host(i)
+        barrier()
+        t0 = time.perf_counter()
+        model.submit_host_u8(0, xu[0], lh2[0], th2[0])
+        for i in range(1, e2e_steps):
+            model.submit_host_u8(i & 1, xu[i & 1], lh2[i & 1], th2[i & 1])
+            model.wait_host((i - 1) & 1)
+        model.wait_host((e2e_steps - 1) & 1)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_u8 = {"value": world * B * e2e_steps / t.item(), "unit": "images/s",
+                  "h2d_bytes_per_step": B * 3 * 224 * 224, "d2h_bytes_per_step": B * classes * 4 + B * 4,
+                  "mode": "rnb_model_submit_host_u8 / rnb_model_wait_host: uint8 HWC host input, normalisation "
+                          "fused into the stem pre-pass"}
+
     # ---- roofline of the dominant kernel, measured live with CUDA events (no graph)
     peaks, peak_kind = load_peaks()
     prof = model.profile(x, iters=3)
@@ -366,6 +392,7 @@ def main():
                 "sync_mode": "rnb_model_forward_host: one blocking call per step (H2D in 64-image pieces "
                              "overlapped with per-piece compute, then D2H)",
                 "top1_equal_to_device_path": same},
+        "e2e_u8": e2e_u8,
         "gpu_launches": model.launches_per_forward(B) * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

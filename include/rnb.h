@@ -81,6 +81,17 @@ int rnb_model_submit_host(rnb_model_t* m, int slot, const float* x_host, int bat
                           int32_t* top1_host);
 int rnb_model_wait_host(rnb_model_t* m, int slot);
 
+/* Decoded-image input: x is uint8 HWC [batch][224][224][3] — the output of JPEG decode + resize 256 +
+ * centre-crop 224 (convert_imgs_to_bin.py:12). The remaining step of that script (:18, torchvision
+ * ToTensor + Normalize: (float(u8) / 255 - mean) / std in FP32) is fused into the stem's layout pre-pass,
+ * bit-identically to feeding rnb_model_forward() the float tensor the script writes. A quarter of the
+ * bytes cross PCIe. mean / std default to the ImageNet constants of the torchvision preset. */
+int rnb_model_set_normalization(rnb_model_t* m, const float mean[3], const float std[3]);
+int rnb_model_forward_u8(rnb_model_t* m, const uint8_t* x_dev, int batch, float* logits_dev,
+                         int32_t* top1_dev, void* stream);
+int rnb_model_submit_host_u8(rnb_model_t* m, int slot, const uint8_t* x_host, int batch, float* logits_host,
+                             int32_t* top1_host);
+
 /* Introspection used by the benchmarks. */
 int rnb_model_num_classes(const rnb_model_t* m);
 int rnb_model_num_convs(const rnb_model_t* m);

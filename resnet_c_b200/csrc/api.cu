@@ -140,6 +140,32 @@ int rnb_model_submit_host(rnb_model_t* m, int slot, const float* x_host, int bat
     return m->impl.submit_host(slot, x_host, batch, logits_host, top1_host);
 }
 
+int rnb_model_set_normalization(rnb_model_t* m, const float mean[3], const float std[3]) {
+    if (!m || !mean || !std) {
+        set_error("rnb_model_set_normalization: NULL argument");
+        return RNB_ERR_INVALID;
+    }
+    return m->impl.set_normalization(mean, std);
+}
+
+int rnb_model_forward_u8(rnb_model_t* m, const uint8_t* x_dev, int batch, float* logits_dev,
+                         int32_t* top1_dev, void* stream) {
+    if (!m || !x_dev) {
+        set_error("rnb_model_forward_u8: NULL argument");
+        return RNB_ERR_INVALID;
+    }
+    return m->impl.forward_u8(x_dev, batch, logits_dev, top1_dev, static_cast<cudaStream_t>(stream));
+}
+
+int rnb_model_submit_host_u8(rnb_model_t* m, int slot, const uint8_t* x_host, int batch, float* logits_host,
+                             int32_t* top1_host) {
+    if (!m || !x_host) {
+        set_error("rnb_model_submit_host_u8: NULL argument");
+        return RNB_ERR_INVALID;
+    }
+    return m->impl.submit_host_u8(slot, x_host, batch, logits_host, top1_host);
+}
+
 int rnb_model_wait_host(rnb_model_t* m, int slot) {
     if (!m) {
         set_error("rnb_model_wait_host: NULL model");

@@ -62,6 +62,14 @@ cudaError_t launch_stem_tc(const float* x, void* xp, const void* wk, const float
 cudaError_t launch_stem_tc_part(int part, const float* x, void* xp, const void* wk, const float* bias,
                                 void* out, int B, cudaStream_t s);
 
+// Decoded-image input (uint8 HWC [B][224][224][3]) with the /255 + mean/std normalisation of
+// convert_imgs_to_bin.py:18 fused in: straight into the packed stem input (BF16 path) ...
+cudaError_t launch_stem_tc_pack_u8(const uint8_t* x, void* xp, int B, const float* mean, const float* std,
+                                   cudaStream_t s);
+// ... or into a normalised FP32 NCHW tensor (every other path)
+cudaError_t launch_u8_hwc_to_f32_nchw(const uint8_t* x, float* out, int B, int H, int W, const float* mean,
+                                      const float* std, cudaStream_t s);
+
 // ---- tensor-core stem, TF32 path (3-term BF16 split, FP32/TF32 output), 224x224 (stem_tc_split.cu)
 size_t stem_tc_split_packed_input_bytes(int B);
 size_t stem_tc_split_packed_weight_bytes();

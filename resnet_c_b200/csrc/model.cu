@@ -147,7 +147,7 @@ Model::~Model() {
     }
     arena.free_all();
     cudaFree(stem_w); cudaFree(stem_bias); cudaFree(stem_wk); cudaFree(fc_w); cudaFree(fc_b);
-    cudaFree(fc_wq); cudaFree(fc_bq);
+    cudaFree(fc_wq); cudaFree(fc_bq); cudaFree(u8_scratch);
     cudaFree(host_x_dev); cudaFree(host_logits_dev); cudaFree(host_top1_dev); cudaFree(scratch_logits);
     for (auto& b : blocks) {
         for (ConvWeights* c : {&b.conv1, &b.conv2, &b.conv3, &b.ds}) {
@@ -510,11 +510,21 @@ ChunkPlan* Model::plan_for(int n) {
     return &ins.first->second;
 }
 
-int Model::enqueue_chunk(ChunkPlan& p, const float* x, float* logits, int32_t* top1, cudaStream_t s) {
+int Model::enqueue_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1,
+                         cudaStream_t s) {
     const int n = p.n;
     const int s_hw = (6 + image - 7) / 2 + 1;
+    if (x_u8 && !(stem_tc && esz == 2)) {
+        // generic path: normalise into an FP32 NCHW staging tensor, then proceed as with float input
+        RNB_CUDA(launch_u8_hwc_to_f32_nchw(x_u8, u8_scratch, n, image, image, norm_mean, norm_std, s));
+        x = u8_scratch;
+        x_u8 = nullptr;
+    }
     if (stem_tc) {
-        RNB_CUDA(launch_stem_any_part(esz, 0, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
+        if (x_u8)
+            RNB_CUDA(launch_stem_tc_pack_u8(x_u8, p.stem_out, n, norm_mean, norm_std, s));
+        else
+            RNB_CUDA(launch_stem_any_part(esz, 0, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
         RNB_CUDA(launch_stem_any_part(esz, 1, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
     } else {
         RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
@@ -564,14 +574,42 @@ int Model::enqueue_fc(ChunkPlan& p, float* logits, cudaStream_t s) {
 }
 
 int Model::forward(const float* x, int batch, float* logits, int32_t* top1, cudaStream_t s) {
+    return forward_any(x, nullptr, batch, logits, top1, s);
+}
+
+int Model::forward_u8(const uint8_t* x, int batch, float* logits, int32_t* top1, cudaStream_t s) {
+    return forward_any(nullptr, x, batch, logits, top1, s);
+}
+
+int Model::set_normalization(const float* mean, const float* std) {
+    for (int c = 0; c < 3; ++c) {
+        if (!(std[c] > 0.f)) {
+            set_error("set_normalization: std must be positive");
+            return RNB_ERR_INVALID;
+        }
+    }
+    cudaDeviceSynchronize();
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);  // the constants are baked into captured launches
+    graphs.clear();
+    for (int c = 0; c < 3; ++c) {
+        norm_mean[c] = mean[c];
+        norm_std[c] = std[c];
+    }
+    return RNB_OK;
+}
+
+int Model::forward_any(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1,
+                       cudaStream_t s) {
     if (batch <= 0 || batch > max_batch) {
         set_error("batch must be in [1, max_batch]");
         return RNB_ERR_INVALID;
     }
-    if (!x) {
+    if (!x && !x_u8) {
         set_error("x_dev is NULL");
         return RNB_ERR_INVALID;
     }
+    if (x_u8 && !(stem_tc && esz == 2) && !u8_scratch)
+        RNB_CUDA(cudaMalloc(&u8_scratch, 1ull * chunk * 3 * image * image * sizeof(float)));
     if (!logits) {
         if (!scratch_logits)
             RNB_CUDA(cudaMalloc(&scratch_logits, 1ull * max_batch * classes * sizeof(float)));
@@ -582,15 +620,16 @@ int Model::forward(const float* x, int batch, float* logits, int32_t* top1, cuda
         const int n = std::min(chunk, batch - off);
         ChunkPlan* p = plan_for(n);
         if (!p) return RNB_ERR_CUDA;
-        const float* xc = x + off * img_elems;
+        const float* xc = x ? x + off * img_elems : nullptr;
+        const uint8_t* xu = x_u8 ? x_u8 + off * img_elems : nullptr;
         float* lc = logits + 1ull * off * classes;
         int32_t* tc = top1 ? top1 + off : nullptr;
         if (!use_graph) {
-            int r = enqueue_chunk(*p, xc, lc, tc, s);
+            int r = enqueue_chunk(*p, xc, xu, lc, tc, s);
             if (r) return r;
             continue;
         }
-        const GraphKey key{n, xc, lc, tc};
+        const GraphKey key{n | (xu ? 1 << 30 : 0), xu ? static_cast<const void*>(xu) : static_cast<const void*>(xc), lc, tc};
         auto g = graphs.find(key);
         if (g == graphs.end()) {
             if (graphs.size() >= 256) {
@@ -598,7 +637,7 @@ int Model::forward(const float* x, int batch, float* logits, int32_t* top1, cuda
                 graphs.clear();
             }
             RNB_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
-            int r = enqueue_chunk(*p, xc, lc, tc, cap_stream);
+            int r = enqueue_chunk(*p, xc, xu, lc, tc, cap_stream);
             cudaGraph_t graph = nullptr;
             cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
             if (r) return r;
@@ -755,6 +794,14 @@ int Model::forward_host(const float* x, int batch, float* logits, int32_t* top1)
 // PCIe transfer of batch i+1 (154 MB for 256 FP32 images — as long as the forward pass itself)
 // overlaps the forward pass of batch i, and the full batch still runs as ONE chunk.
 int Model::submit_host(int slot, const float* x, int batch, float* logits, int32_t* top1) {
+    return submit_host_any(slot, x, false, batch, logits, top1);
+}
+
+int Model::submit_host_u8(int slot, const uint8_t* x, int batch, float* logits, int32_t* top1) {
+    return submit_host_any(slot, x, true, batch, logits, top1);
+}
+
+int Model::submit_host_any(int slot, const void* x, bool u8, int batch, float* logits, int32_t* top1) {
     if (slot < 0 || slot > 1) {
         set_error("slot must be 0 or 1");
         return RNB_ERR_INVALID;
@@ -777,11 +824,13 @@ int Model::submit_host(int slot, const float* x, int batch, float* logits, int32
         RNB_CUDA(cudaEventCreateWithFlags(&hs.done, cudaEventDisableTiming));
     }
     if (!pipe_compute) RNB_CUDA(cudaStreamCreateWithFlags(&pipe_compute, cudaStreamNonBlocking));
-    RNB_CUDA(cudaMemcpyAsync(hs.x_dev, x, batch * img_elems * sizeof(float), cudaMemcpyHostToDevice,
+    // uint8 input: a quarter of the bytes cross PCIe (the device buffer is reused as a byte buffer)
+    RNB_CUDA(cudaMemcpyAsync(hs.x_dev, x, batch * img_elems * (u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice,
                              copy_stream));
     RNB_CUDA(cudaEventRecord(hs.copied, copy_stream));
     RNB_CUDA(cudaStreamWaitEvent(pipe_compute, hs.copied, 0));
-    int r = forward(hs.x_dev, batch, hs.logits_dev, hs.top1_dev, pipe_compute);
+    int r = u8 ? forward_u8(reinterpret_cast<const uint8_t*>(hs.x_dev), batch, hs.logits_dev, hs.top1_dev, pipe_compute)
+               : forward(hs.x_dev, batch, hs.logits_dev, hs.top1_dev, pipe_compute);
     if (r) return r;
     if (logits)
         RNB_CUDA(cudaMemcpyAsync(logits, hs.logits_dev, 1ull * batch * classes * sizeof(float),

@@ -92,7 +92,7 @@ struct Model {
 
     Arena arena;
     std::map<int, ChunkPlan> plans;
-    using GraphKey = std::tuple<int, const void*, void*, void*>;
+    using GraphKey = std::tuple<int, const void*, void*, void*>;  // (n | u8 flag << 30, x, logits, top1)
     std::map<GraphKey, cudaGraphExec_t> graphs;
     cudaStream_t cap_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
@@ -101,6 +101,10 @@ struct Model {
     float* host_logits_dev = nullptr;
     int32_t* host_top1_dev = nullptr;
     float* scratch_logits = nullptr;  // used when the caller passes logits = NULL
+    float* u8_scratch = nullptr;      // normalised FP32 NCHW staging for uint8 input on the non-BF16-stem paths
+    // ImageNet mean / std of convert_imgs_to_bin.py:18 (torchvision ImageClassification preset)
+    float norm_mean[3] = {0.485f, 0.456f, 0.406f};
+    float norm_std[3] = {0.229f, 0.224f, 0.225f};
     int last_chunk_n = 0;
     bool use_graph = true;
     bool alternate_tiles = true;  // consecutive convs walk their tiles in opposite directions (L2 reuse)
@@ -115,9 +119,13 @@ struct Model {
     ~Model();
     int load(const std::string& arch, int dtype, const std::string& dir, int max_batch, int chunk);
     ChunkPlan* plan_for(int n);
-    int enqueue_chunk(ChunkPlan& p, const float* x, float* logits, int32_t* top1, cudaStream_t s);
+    // x_u8 != nullptr: decoded uint8 HWC input (x is then ignored), normalised with norm_mean / norm_std
+    int enqueue_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1, cudaStream_t s);
     int enqueue_fc(ChunkPlan& p, float* logits, cudaStream_t s);
     int forward(const float* x, int batch, float* logits, int32_t* top1, cudaStream_t s);
+    int forward_u8(const uint8_t* x, int batch, float* logits, int32_t* top1, cudaStream_t s);
+    int forward_any(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1, cudaStream_t s);
+    int set_normalization(const float* mean, const float* std);
     int forward_host(const float* x, int batch, float* logits, int32_t* top1);
     // pipelined host path: two slots, each with its own device input / output buffers
     struct HostSlot {
@@ -129,6 +137,8 @@ struct Model {
     } slots[2];
     cudaStream_t pipe_compute = nullptr;
     int submit_host(int slot, const float* x, int batch, float* logits, int32_t* top1);
+    int submit_host_u8(int slot, const uint8_t* x, int batch, float* logits, int32_t* top1);
+    int submit_host_any(int slot, const void* x, bool u8, int batch, float* logits, int32_t* top1);
     int wait_host(int slot);
     int profile(const float* x, int batch, int iters, int* kind, float* ms, double* flops,
                 double* bytes, int max_entries, int* n_entries, cudaStream_t s);

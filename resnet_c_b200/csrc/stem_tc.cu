@@ -97,6 +97,68 @@ __global__ void stem_pack_kernel(const float* __restrict__ x, uint4* __restrict_
     }
 }
 
+// Same layout pre-pass from the DECODED image: x [B][224][224][3] uint8 HWC (what a JPEG decoder + resize/crop
+// yields, convert_imgs_to_bin.py:12) -> xp, with the /255 + mean/std normalisation of convert_imgs_to_bin.py:18
+// (torchvision ToTensor + Normalize) evaluated in FP32 exactly as torch does: (float(u8) / 255 - mean) / std.
+// 4x fewer input bytes than the FP32 NCHW tensor (the host->device copy is what bounds end-to-end throughput).
+struct StemNorm {
+    float mean[3], std[3];
+};
+__global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ x, uint4* __restrict__ xp, int B, StemNorm nm) {
+    constexpr int GROUPS = PAD_W / 4;  // 58
+    const int64_t total = 1LL * B * PAD_H * GROUPS;
+    for (int64_t i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
+         i += 1LL * gridDim.x * blockDim.x) {
+        const int gidx = static_cast<int>(i % GROUPS);
+        int64_t t = i / GROUPS;
+        const int pr = static_cast<int>(t % PAD_H);
+        const int b = static_cast<int>(t / PAD_H);
+        const int ih = pr - 5;
+        float v[4][3];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j][0] = v[j][1] = v[j][2] = 0.f;
+        if (ih >= 0 && ih < IMG) {
+            const uint8_t* row = x + (1LL * b * IMG + ih) * IMG * 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int iw = 4 * gidx - 3 + j;  // image column of padded pixel 4g + j
+                if (iw >= 0 && iw < IMG) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float f = __fdiv_rn(static_cast<float>(__ldg(row + iw * 3 + c)), 255.f);
+                        v[j][c] = __fdiv_rn(__fsub_rn(f, nm.mean[c]), nm.std[c]);
+                    }
+                }
+            }
+        }
+        uint4 o0, o1;
+        auto px = [&](int j, uint32_t& a, uint32_t& c) {
+            const __nv_bfloat162 rg = __floats2bfloat162_rn(v[j][0], v[j][1]);
+            const __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j][2], 0.f);
+            a = *reinterpret_cast<const uint32_t*>(&rg);
+            c = *reinterpret_cast<const uint32_t*>(&b0);
+        };
+        px(0, o0.x, o0.y); px(1, o0.z, o0.w); px(2, o1.x, o1.y); px(3, o1.z, o1.w);
+        uint4* dst = xp + 2 * i;
+        dst[0] = o0;
+        dst[1] = o1;
+    }
+}
+
+// x [B][H][W][3] uint8 HWC -> out [B][3][H][W] fp32 NCHW, normalised as above (generic path: TF32 stem,
+// CUDA-core stem). One thread per pixel.
+__global__ void u8_hwc_to_f32_nchw_kernel(const uint8_t* __restrict__ x, float* __restrict__ out, int64_t pixels,
+                                          int HW, StemNorm nm) {
+    for (int64_t i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < pixels; i += 1LL * gridDim.x * blockDim.x) {
+        const int64_t b = i / HW, p = i - b * HW;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float f = __fdiv_rn(static_cast<float>(__ldg(x + i * 3 + c)), 255.f);
+            out[(b * 3 + c) * HW + p] = __fdiv_rn(__fsub_rn(f, nm.mean[c]), nm.std[c]);
+        }
+    }
+}
+
 // w [64][3][7][7] fp32 + BN -> wk [kh*4+j][oc][e] bf16 with e = (kw - 2j)*4 + c, kw in {2j, 2j+1};
 // kw = 7 and c = 3 are zero. bias[oc] = folded BN shift.
 __global__ void stem_pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
@@ -379,6 +441,37 @@ cudaError_t launch_stem_tc_part(int part, const float* x, void* xp, const void* 
             static_cast<const uint8_t*>(xp), static_cast<const uint8_t*>(wk), bias,
             static_cast<__nv_bfloat16*>(out), B);
     }
+    return cudaGetLastError();
+}
+
+// part 0 from decoded uint8 HWC images (see stem_pack_u8_kernel)
+cudaError_t launch_stem_tc_pack_u8(const uint8_t* x, void* xp, int B, const float* mean, const float* std,
+                                   cudaStream_t s) {
+    StemNorm nm;
+    for (int c = 0; c < 3; ++c) {
+        nm.mean[c] = mean[c];
+        nm.std[c] = std[c];
+    }
+    const int64_t total = 1LL * B * PAD_H * (PAD_W / 4);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    stem_pack_u8_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(x, static_cast<uint4*>(xp), B, nm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_u8_hwc_to_f32_nchw(const uint8_t* x, float* out, int B, int H, int W, const float* mean,
+                                      const float* std, cudaStream_t s) {
+    StemNorm nm;
+    for (int c = 0; c < 3; ++c) {
+        nm.mean[c] = mean[c];
+        nm.std[c] = std[c];
+    }
+    const int64_t pixels = 1LL * B * H * W;
+    int64_t blocks = (pixels + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    u8_hwc_to_f32_nchw_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(x, out, pixels, H * W, nm);
     return cudaGetLastError();
 }
 

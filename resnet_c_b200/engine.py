@@ -233,6 +233,31 @@ class ResNet:
             raise RnbError("submit_host takes a contiguous float32 host tensor")
         check(_lib.lib().rnb_model_submit_host(self._h, slot, _ptr(x), x.shape[0], _ptr(logits), _ptr(top1)))
 
+    def forward_u8(self, x: torch.Tensor, logits=None, top1=None):
+        """x: [B,224,224,3] uint8 CUDA tensor (decoded, resized, cropped image, HWC). The /255 + mean/std
+        normalisation of convert_imgs_to_bin.py:18 runs inside the stem's layout pre-pass."""
+        if not x.is_cuda or x.dtype != torch.uint8 or x.dim() != 4 or x.shape[-1] != 3:
+            raise RnbError("forward_u8 takes a [B,H,W,3] uint8 CUDA tensor")
+        x = x.contiguous()
+        B = x.shape[0]
+        if logits is None:
+            logits = torch.empty(B, self.num_classes, device=x.device, dtype=torch.float32)
+        if top1 is None:
+            top1 = torch.empty(B, device=x.device, dtype=torch.int32)
+        check(_lib.lib().rnb_model_forward_u8(self._h, _ptr(x), B, _ptr(logits), _ptr(top1), _stream()))
+        return logits, top1
+
+    def submit_host_u8(self, slot: int, x: torch.Tensor, logits: torch.Tensor, top1: torch.Tensor) -> None:
+        """submit_host for a [B,224,224,3] uint8 HOST tensor (a quarter of the PCIe bytes)."""
+        if x.is_cuda or x.dtype != torch.uint8 or not x.is_contiguous():
+            raise RnbError("submit_host_u8 takes a contiguous uint8 host tensor")
+        check(_lib.lib().rnb_model_submit_host_u8(self._h, slot, _ptr(x), x.shape[0], _ptr(logits), _ptr(top1)))
+
+    def set_normalization(self, mean, std) -> None:
+        m = (C.c_float * 3)(*[float(v) for v in mean])
+        s = (C.c_float * 3)(*[float(v) for v in std])
+        check(_lib.lib().rnb_model_set_normalization(self._h, m, s))
+
     def wait_host(self, slot: int) -> None:
         check(_lib.lib().rnb_model_wait_host(self._h, slot))
 

@@ -126,6 +126,34 @@ def preprocess_jpeg(path) -> torch.Tensor:
         return preprocess(img).unsqueeze(0).contiguous()
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def decode_jpeg_u8(path) -> torch.Tensor:
+    """JPEG -> [1,224,224,3] uint8 HWC: the first half of convert_imgs_to_bin.py:12 (resize 256 with
+    antialiased bilinear, centre-crop 224) — the input of ResNet.forward_u8."""
+    import numpy as np
+    from PIL import Image
+    from torchvision.transforms import functional as F
+
+    with open(path, "rb") as f:
+        img = Image.open(f).convert("RGB")
+        img = F.center_crop(F.resize(img, [256], interpolation=F.InterpolationMode.BILINEAR, antialias=True), [224])
+        return torch.from_numpy(np.asarray(img).copy()).unsqueeze(0)
+
+
+def load_u8_image_bin(path, size: int = 224) -> torch.Tensor:
+    import numpy as np
+    return torch.from_numpy(np.fromfile(path, dtype=np.uint8).copy()).reshape(-1, size, size, 3)
+
+
+def synthetic_images_u8(batch: int, seed: int = 1234, size: int = 224) -> torch.Tensor:
+    """Synthetic decoded images [B,size,size,3] uint8."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (batch, size, size, 3), generator=g, dtype=torch.uint8)
+
+
 def save_image_bin(tensor: torch.Tensor, path) -> None:
     Path(path).parent.mkdir(parents=True, exist_ok=True)
     tensor.detach().cpu().to(torch.float32).contiguous().numpy().reshape(-1).tofile(path)

@@ -69,6 +69,8 @@ def main():
     jpeg_path = REFERENCE / "test_imgs" / "ILSVRC2012_val_00004749.jpeg"
     jpeg = weights.preprocess_jpeg(jpeg_path)
     weights.save_image_bin(jpeg, HERE / "ILSVRC2012_val_00004749.bin")
+    # the decoded / resized / cropped uint8 HWC image before normalisation (input of rnb_model_forward_u8)
+    weights.decode_jpeg_u8(jpeg_path).numpy().tofile(HERE / "ILSVRC2012_val_00004749_u8hwc.bin")
     print("image", tuple(jpeg.shape), float(jpeg.min()), float(jpeg.max()), float(jpeg.mean()))
 
     # 2. the reference's own class

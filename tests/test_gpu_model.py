@@ -156,6 +156,45 @@ def test_full_batch_properties(arch, dtype):
     small.close()
 
 
+@pytest.mark.parametrize("arch,dtype", [("resnet50", "bf16"), ("resnet18", "bf16"), ("resnet18", "tf32")])
+def test_uint8_input_path_is_bit_identical_to_float_input(arch, dtype, golden_dir):
+    """rnb_model_forward_u8 (decoded uint8 HWC in, /255 + mean/std fused into the stem pre-pass — or the
+    generic FP32 conversion kernel on the TF32 path) against rnb_model_forward fed with the oracle's
+    normalised tensor: identical logits; and through the pipelined host path."""
+    from oracle import preprocess
+    from resnet_c_b200 import weights
+    B = 5
+    u8 = torch.cat([weights.load_u8_image_bin(golden_dir / "ILSVRC2012_val_00004749_u8hwc.bin"),
+                    weights.synthetic_images_u8(B - 1)])
+    model = _model(arch, True, dtype, B)
+    want, want_top1 = model.forward(preprocess.normalize_u8(u8).cuda())
+    got, got_top1 = model.forward_u8(u8.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(got, want) and torch.equal(got_top1, want_top1)
+    lh, th = torch.empty(B, model.num_classes).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory()
+    model.submit_host_u8(0, u8.pin_memory(), lh, th)
+    model.wait_host(0)
+    assert torch.equal(lh, want.cpu()) and torch.equal(th, want_top1.cpu())
+    # other constants are honoured (and cached graphs dropped)
+    model.set_normalization((0.5, 0.5, 0.5), (0.25, 0.25, 0.25))
+    want2, _ = model.forward(preprocess.normalize_u8(u8, (0.5, 0.5, 0.5), (0.25, 0.25, 0.25)).cuda())
+    got2, _ = model.forward_u8(u8.cuda())
+    assert torch.equal(got2, want2) and not torch.equal(got2, got)
+    model.close()
+
+
+def test_uint8_reference_image_top1(golden_dir):
+    """The reference's own scenario from the decoded JPEG: ResNet-152 -> 176, ResNet-18 -> 238."""
+    from resnet_c_b200 import weights
+    u8 = weights.load_u8_image_bin(golden_dir / "ILSVRC2012_val_00004749_u8hwc.bin").cuda()
+    for name, arch in [("resnet18_default_jpeg_b1", "resnet18"), ("resnet152_default_jpeg_b1", "resnet152")]:
+        g = load_golden(name)
+        model = _model(arch, False, "bf16", 1)
+        _, top1 = model.forward_u8(u8)
+        assert top1.cpu().tolist() == g["top1"].tolist()
+        model.close()
+
+
 def _run_with_env(monkeypatch, env, arch, batch, names):
     from resnet_c_b200 import weights
     for k, v in env.items():

@@ -109,3 +109,20 @@ def test_c_oracle_matches_golden_on_the_reference_image(oracle_lib, jpeg_tensor)
     y, top = oracle_lib.resnet_forward("resnet18", sd, jpeg_tensor.numpy())
     assert rel_err(y, g["logits_fp64"]) < 1e-5
     assert top.tolist() == g["top1"].tolist() == [238]
+
+
+def test_u8_normalisation_reproduces_the_reference_preprocessing(jpeg_tensor, golden_dir):
+    """oracle/preprocess.py::normalize_u8 on the committed uint8 crop of the reference's test JPEG must give,
+    bit for bit, the tensor the reference's convert_imgs_to_bin.py preset produced (the committed .bin)."""
+    from oracle import preprocess
+    from resnet_c_b200 import weights
+    u8 = weights.load_u8_image_bin(golden_dir / "ILSVRC2012_val_00004749_u8hwc.bin")
+    assert u8.shape == (1, 224, 224, 3)
+    assert torch.equal(preprocess.normalize_u8(u8), jpeg_tensor)
+
+
+@pytest.mark.skipif(not REFERENCE.exists(), reason="reference tree not mounted (GPU box)")
+def test_u8_crop_golden_matches_live_decode(golden_dir):
+    from resnet_c_b200 import weights
+    live = weights.decode_jpeg_u8(REFERENCE / "test_imgs" / "ILSVRC2012_val_00004749.jpeg")
+    assert torch.equal(live, weights.load_u8_image_bin(golden_dir / "ILSVRC2012_val_00004749_u8hwc.bin"))
