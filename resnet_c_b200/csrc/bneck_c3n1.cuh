@@ -1,0 +1,351 @@
+// bneck_c3n1.cuh — conv3 (1x1, 128 -> 512) + BN + shortcut + ReLU of a layer2-shaped Bottleneck block AND the
+// next block's conv1 (1x1, 512 -> 128) + BN + ReLU in ONE launch (BF16):
+//
+//     y   = relu(bn3(conv3_1x1(t2)) + x)           t2 [M,128], x / y [M,512]     (layerForward, main.cu:153-163)
+//     t1' = relu(bn1'(conv1'_1x1(y)))              t1' [M,128]                    (next block, main.cu:138-146)
+//
+// replacing two launches of the conv2dForwardKernel / batchNorm2dForwardKernel / addForwardKernel /
+// reluForwardKernel chain (/root/reference/cuda/ops.cu:14-48,139-151,153-160,130-137). At 28x28 both are
+// HBM-bound; fused, y is consumed from the staging tiles it is stored from, so the 206 MB (per 256 images)
+// re-read of y by conv1' disappears: 51 + 206 + 206 + 51 MB instead of 463 + 257 MB.
+//
+// Structure (the machinery of bneck_l1.cuh without its 3x3 stage): a CTA PAIR (cta_group::2) per tile of
+// 256 consecutive pixel rows (128 per CTA); 1x1 convs need no halo, so all tensors are plain 2-D [M][C] TMA
+// maps. Both weight matrices are resident, split across the pair (64 + 64 KB per CTA).
+//   conv3 : A2 tile (128 rows x 128 K, one TMA pair per tile) x W3_q^T for the four 128-channel quarters q of
+//           y -> D2 (two 128-column halves, quarter q in half q & 1)
+//   E2    : D2 + bias3 + residual (TMA-prefetched into the staging box) -> ReLU -> BF16 -> staging boxes
+//           (64 channels each, 8 per tile) -> TMA store of y; each box is also the K block of
+//   conv1': box_b x W1n_b^T accumulated over b = 0..7 -> D3 (128 columns, double-buffered)
+//   E3    : D3 + bias1' -> ReLU -> BF16 -> two staging boxes -> TMA store of t1'
+// Warps (384 threads): 0 TMA producer (weights once, A2 tiles), 1 conv3 issuer, 2 TMEM alloc + conv1'
+// issuer, 3 store warp (pipelined stores, residual prefetch, box recycling), 4..11 epilogue.
+// Rounding points and K order are those of the separate kernels: the result is bit-identical to them.
+#pragma once
+#include "bneck_l1.cuh"
+
+namespace rnb {
+
+struct C3n1Geom {
+    int M;        // pixel rows (batch * H * W)
+    int tiles;    // ceil(M / 256) pair tiles
+    int reverse;  // tile traversal direction (see ConvGeom::reverse)
+};
+
+struct C3n1Cfg {
+    static constexpr int K3 = 128, N3 = 512, N1 = 128;        // conv3: K3 -> N3; conv1': N3 -> N1
+    static constexpr int W3_BLK_BYTES = 64 * 128;             // this CTA's 64 rows of one (quarter, k-block)
+    static constexpr int W3_BYTES = 4 * 2 * W3_BLK_BYTES;     // 64 KB
+    static constexpr int W1N_BLK_BYTES = 64 * 128;            // this CTA's 64 rows of one 64-wide K block
+    static constexpr int W1N_BYTES = 8 * W1N_BLK_BYTES;       // 64 KB
+    static constexpr int BOX_BYTES = 16384;                   // 128 rows x 64 bf16, 128-byte swizzled
+    static constexpr int A2_BYTES = 2 * BOX_BYTES;            // two K blocks
+    static constexpr int NPOOL = 4;
+    static constexpr int IPT = 10;                            // staging items per tile: 8 boxes of y + 2 of t1'
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int D2_COL = 0, D3_COL = 256;
+    static constexpr int NBAR = 1 + 2 + 4 + 4 + 4 * NPOOL;
+    static constexpr int SMEM_BYTES = 1024 + W3_BYTES + W1N_BYTES + A2_BYTES + NPOOL * BOX_BYTES + NBAR * 8 + 16;
+    static constexpr int EPI_WARPS = 8;
+    static constexpr int THREADS = 128 + EPI_WARPS * 32;
+};
+static_assert(C3n1Cfg::SMEM_BYTES <= 232448, "smem budget");
+
+struct C3n1Params {
+    const float* bias3;   // [512]
+    const float* bias1n;  // [128]
+};
+
+// Tensor maps (BF16, 128-byte swizzle, 2-D [rows][cols], box = 64 cols x box_rows):
+//   tmA   t2  [M][128]   box rows 128      tmW3  [512][128] box rows 64      tmW1n [128][512] box rows 64
+//   tmRes x   [M][512]   box rows 128      tmY   y [M][512] box rows 128     tmT1n t1' [M][128] box rows 128
+template <class Cfg>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::THREADS, 1)
+bneck_c3n1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW3,
+                  const __grid_constant__ CUtensorMap tmW1n, const __grid_constant__ CUtensorMap tmRes,
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmT1n,
+                  const C3n1Params prm, const C3n1Geom g) {
+    using namespace ptx;
+    constexpr int NPOOL = Cfg::NPOOL, IPT = Cfg::IPT;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_w3 = smem;
+    uint8_t* smem_w1n = smem_w3 + Cfg::W3_BYTES;
+    uint8_t* smem_a2 = smem_w1n + Cfg::W1N_BYTES;
+    uint8_t* smem_pool = smem_a2 + Cfg::A2_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_pool + NPOOL * Cfg::BOX_BYTES);
+    uint64_t* w_full = bars;                 // leader: weights of both CTAs landed
+    uint64_t* a_full = w_full + 1;           // leader: A2 tile landed in both CTAs
+    uint64_t* a_empty = a_full + 1;          // per CTA (multicast commit)
+    uint64_t* d2_full = a_empty + 1;         // per CTA (multicast commit), [2 halves]
+    uint64_t* d2_empty = d2_full + 2;        // leader, 16 arrivals, [2 halves]
+    uint64_t* d3_full = d2_empty + 2;        // per CTA (multicast commit), [2]
+    uint64_t* d3_empty = d3_full + 2;        // leader, 16 arrivals, [2]
+    uint64_t* box_ready = d3_empty + 2;      // per CTA: staging box free (or its residual tile landed)
+    uint64_t* c_full = box_ready + NPOOL;    // per CTA, 8 arrivals
+    uint64_t* cx_full = c_full + NPOOL;      // leader, 16 arrivals (conv1' operand complete in both CTAs)
+    uint64_t* c_mma_done = cx_full + NPOOL;  // per CTA (multicast commit)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int T = (g.tiles - pair + num_pairs - 1) / num_pairs;
+    const int items = T * IPT;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmW3);
+        tma_prefetch_desc(&tmW1n);
+        tma_prefetch_desc(&tmRes);
+        tma_prefetch_desc(&tmY);
+        tma_prefetch_desc(&tmT1n);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(w_full, 1);
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&d2_full[i], 1);
+            mbar_init(&d2_empty[i], 2 * Cfg::EPI_WARPS);
+            mbar_init(&d3_full[i], 1);
+            mbar_init(&d3_empty[i], 2 * Cfg::EPI_WARPS);
+        }
+        for (int i = 0; i < NPOOL; ++i) {
+            mbar_init(&box_ready[i], 1);
+            mbar_init(&c_full[i], Cfg::EPI_WARPS);
+            mbar_init(&cx_full[i], 2 * Cfg::EPI_WARPS);
+            mbar_init(&c_mma_done[i], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        __syncwarp();
+        tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    griddep_launch_dependents();  // see conv_igemm.cuh
+    griddep_wait();
+
+    // local tile index -> first pixel row owned by THIS CTA
+    auto tile_row0 = [&](int it_local) {
+        const int t = pair + it_local * num_pairs;
+        const int tt = g.reverse ? g.tiles - 1 - t : t;
+        return tt * 256 + static_cast<int>(rank) * 128;
+    };
+
+    if (warp == 0) {
+        // ===================================================== TMA producer (both CTAs)
+        if (elect_one()) {
+            const int r64 = static_cast<int>(rank) * 64;
+            if (rank == 0) mbar_expect_tx(w_full, 2 * (Cfg::W3_BYTES + Cfg::W1N_BYTES));
+            for (int q = 0; q < 4; ++q)
+                for (int kb = 0; kb < 2; ++kb)
+                    tma_load_2d_2sm(smem_w3 + (q * 2 + kb) * Cfg::W3_BLK_BYTES, &tmW3, w_full, kb * 64, q * 128 + r64);
+            for (int kb = 0; kb < 8; ++kb)
+                tma_load_2d_2sm(smem_w1n + kb * Cfg::W1N_BLK_BYTES, &tmW1n, w_full, kb * 64, r64);
+        }
+        __syncwarp();
+        for (int it = 0; it < T; ++it) {
+            const int row0 = tile_row0(it);
+            mbar_wait(a_empty, (it & 1) ^ 1);
+            if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(a_full, 2 * Cfg::A2_BYTES);
+                tma_load_2d_2sm(smem_a2, &tmA, a_full, 0, row0);
+                tma_load_2d_2sm(smem_a2 + Cfg::BOX_BYTES, &tmA, a_full, 64, row0);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===================================================== conv3 MMA issuer (leader CTA only)
+        if (rank == 0) {
+            constexpr uint32_t idesc128 = umma_instr_desc(UMMA_FMT_BF16, 256, 128);
+            const uint64_t a2_desc = umma_smem_desc(smem_u32(smem_a2), 0, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t w3_desc = umma_smem_desc(smem_u32(smem_w3), 0, 1024, UMMA_LAYOUT_SW128);
+            mbar_wait(w_full, 0);
+            tc_fence_after();
+            for (int i = 0; i < T; ++i) {
+                mbar_wait(a_full, i & 1);
+#pragma unroll 1
+                for (int hq = 0; hq < 2; ++hq) {      // quarter q = 2 * hq + hf lives in D2 half hf
+#pragma unroll 1
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int q = 2 * hq + hf;
+                        // use number 2i + hq of this half
+                        mbar_wait(hf == 0 ? &d2_empty[0] : &d2_empty[1], (hq & 1) ^ 1);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t d_tmem = tmem_base + Cfg::D2_COL + hf * 128;
+#pragma unroll
+                            for (int kb = 0; kb < 2; ++kb) {
+                                const uint64_t a = a2_desc + static_cast<uint64_t>((kb * Cfg::BOX_BYTES) >> 4);
+                                const uint64_t b = w3_desc + static_cast<uint64_t>(((q * 2 + kb) * Cfg::W3_BLK_BYTES) >> 4);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    mma_f16_ss_2sm(d_tmem, a + static_cast<uint64_t>(k * 2),
+                                                   b + static_cast<uint64_t>(k * 2), idesc128, (kb | k) != 0);
+                            }
+                            if (q == 3) tc_commit_2sm(a_empty);  // the A2 tile is fully consumed
+                            tc_commit_2sm(hf == 0 ? &d2_full[0] : &d2_full[1]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================================================== conv1' MMA issuer (leader CTA only)
+        if (rank == 0) {
+            constexpr uint32_t idesc128 = umma_instr_desc(UMMA_FMT_BF16, 256, 128);
+            const uint64_t w1n_desc = umma_smem_desc(smem_u32(smem_w1n), 0, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t pool_desc = umma_smem_desc(smem_u32(smem_pool), 0, 1024, UMMA_LAYOUT_SW128);
+            uint32_t cx_phase_bits = 0;  // bit cs = parity of the next cx_full[cs] wait
+            mbar_wait(w_full, 0);
+            tc_fence_after();
+            for (int i = 0; i < T; ++i) {
+                const int buf = i & 1;
+                mbar_wait(buf == 0 ? &d3_empty[0] : &d3_empty[1], ((i >> 1) & 1) ^ 1);
+#pragma unroll 1
+                for (int b = 0; b < 8; ++b) {
+                    const int cs = (i * IPT + b) % NPOOL;
+                    mbar_wait(&cx_full[cs], (cx_phase_bits >> cs) & 1);
+                    cx_phase_bits ^= 1u << cs;
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t d_tmem = tmem_base + Cfg::D3_COL + buf * 128;
+                        const uint64_t a = pool_desc + static_cast<uint64_t>((cs * Cfg::BOX_BYTES) >> 4);
+                        const uint64_t bd = w1n_desc + static_cast<uint64_t>((b * Cfg::W1N_BLK_BYTES) >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_f16_ss_2sm(d_tmem, a + static_cast<uint64_t>(k * 2), bd + static_cast<uint64_t>(k * 2),
+                                           idesc128, (b | k) != 0);
+                        tc_commit_2sm(&c_mma_done[cs]);
+                        if (b == 7) tc_commit_2sm(buf == 0 ? &d3_full[0] : &d3_full[1]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================================================== store warp (both CTAs), see bneck_l1.cuh
+        // item = tile * IPT + sub: sub 0..7 = 64-channel boxes of y (residual prefetched), 8..9 = boxes of t1'
+        auto prepare = [&](int item) {
+            const int cs = item % NPOOL;
+            const int it_local = item / IPT, sub = item - it_local * IPT;
+            if (sub < 8) {
+                mbar_expect_tx(&box_ready[cs], Cfg::BOX_BYTES);
+                tma_load_2d(smem_pool + cs * Cfg::BOX_BYTES, &tmRes, &box_ready[cs], sub * 64, tile_row0(it_local));
+            } else {
+                mbar_arrive(&box_ready[cs]);
+            }
+        };
+        if (elect_one()) {
+            for (int i = 0; i < NPOOL && i < items; ++i) prepare(i);
+        }
+        __syncwarp();
+        uint32_t md_phase_bits = 0;
+        auto recycle = [&](int item) {
+            const int cs = item % NPOOL;
+            if (item % IPT < 8) {  // conv1' must have consumed the box as well
+                mbar_wait(&c_mma_done[cs], (md_phase_bits >> cs) & 1);
+                md_phase_bits ^= 1u << cs;
+            }
+            if (item + NPOOL < items && elect_one()) prepare(item + NPOOL);
+            __syncwarp();
+        };
+        for (int item = 0; item < items; ++item) {
+            const int cs = item % NPOOL;
+            const int it_local = item / IPT, sub = item - it_local * IPT;
+            mbar_wait(&c_full[cs], (item / NPOOL) & 1);
+            if (elect_one()) {
+                const uint8_t* box = smem_pool + cs * Cfg::BOX_BYTES;
+                if (sub < 8)
+                    tma_store_2d(&tmY, box, sub * 64, tile_row0(it_local));
+                else
+                    tma_store_2d(&tmT1n, box, (sub - 8) * 64, tile_row0(it_local));
+                tma_store_commit();
+                tma_store_wait_read<1>();
+            }
+            __syncwarp();
+            if (item > 0) recycle(item - 1);
+        }
+        if (elect_one()) tma_store_wait_read<0>();
+        __syncwarp();
+        if (items > 0) recycle(items - 1);
+        if (elect_one()) tma_store_wait_all<0>();
+        __syncwarp();
+    } else {
+        // ===================================================== epilogue (both CTAs)
+        const int q4 = warp & 3;
+        const int h = (warp - 4) >> 2;  // which 32-column half of a 64-column box
+        const int row_in_tile = q4 * 32 + lane;
+        const uint32_t swz = static_cast<uint32_t>(row_in_tile & 7);
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+        const uint32_t row_off = static_cast<uint32_t>(row_in_tile) * 128;
+
+        auto publish = [&]() {
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+        };
+        // one 64-channel box: accumulator columns [col, col + 64) -> staging box of `item`
+        auto box_step = [&](int item, uint32_t col, const float* bias64, int has_res, bool to_mma) {
+            const int cs = item % NPOOL;
+            mbar_wait(&box_ready[cs], (item / NPOOL) & 1);
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld_32x32(lane_base + col + h * 32, v);
+            tmem_ld_wait();
+            epilogue_chunk<2>(v, smem_pool + cs * Cfg::BOX_BYTES + row_off, static_cast<uint32_t>(h * 4), swz,
+                              bias64 + h * 32, has_res, 1);
+            publish();
+            if (lane == 0) {
+                mbar_arrive(&c_full[cs]);
+                if (to_mma) mbar_arrive_leader(&cx_full[cs]);
+            }
+        };
+        // quarter q = 2 * hq + hf of y for tile i (D2 half hf)
+        auto E2 = [&](int i, int hq, int hf) {
+            const int q = 2 * hq + hf;
+            mbar_wait(hf == 0 ? &d2_full[0] : &d2_full[1], hq & 1);
+            tc_fence_after();
+            box_step(i * IPT + 2 * q, Cfg::D2_COL + hf * 128, prm.bias3 + q * 128, 1, true);
+            box_step(i * IPT + 2 * q + 1, Cfg::D2_COL + hf * 128 + 64, prm.bias3 + q * 128 + 64, 1, true);
+            if (lane == 0) mbar_arrive_leader(hf == 0 ? &d2_empty[0] : &d2_empty[1]);
+        };
+        auto E3 = [&](int i) {
+            const int buf = i & 1;
+            mbar_wait(buf == 0 ? &d3_full[0] : &d3_full[1], (i >> 1) & 1);
+            tc_fence_after();
+            box_step(i * IPT + 8, Cfg::D3_COL + buf * 128, prm.bias1n, 0, false);
+            box_step(i * IPT + 9, Cfg::D3_COL + buf * 128 + 64, prm.bias1n + 64, 0, false);
+            if (lane == 0) mbar_arrive_leader(buf == 0 ? &d3_empty[0] : &d3_empty[1]);
+        };
+        for (int i = 0; i < T; ++i) {
+            E2(i, 0, 0);
+            E2(i, 0, 1);
+            E2(i, 1, 0);
+            E2(i, 1, 1);
+            E3(i);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's smem/TMEM must stay alive until the leader's MMAs have retired
+    if (warp == 2) {
+        __syncwarp();
+        tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace rnb

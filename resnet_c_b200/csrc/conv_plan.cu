@@ -72,6 +72,9 @@ cudaError_t conv_kernels_init() {
     if ((e = cudaFuncSetAttribute(bneck_l1_kernel<BneckCfg<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   BneckCfg<false>::SMEM_BYTES)) != cudaSuccess)
         return e;
+    if ((e = cudaFuncSetAttribute(bneck_c3n1_kernel<C3n1Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C3n1Cfg::SMEM_BYTES)) != cudaSuccess)
+        return e;
     if ((e = cudaFuncSetAttribute(bneck_l1_kernel<BneckCfg<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   BneckCfg<true>::SMEM_BYTES)) != cudaSuccess)
         return e;
@@ -173,6 +176,41 @@ int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, 
         if ((r = act_map(&plan->tmT1n, d.t1n, 64, static_cast<uint32_t>(d.W), 1)) != 0)
             return fail(err, errlen, "bneck_plan: t1n tensor map failed", r);
     }
+    return 0;
+}
+
+int c3n1_plan_init(ConvPlan* plan, const C3n1Desc& d, int num_sms, char* err, int errlen) {
+    memset(plan, 0, sizeof(*plan));
+    if (d.M <= 0) return fail(err, errlen, "c3n1_plan: bad M", -5);
+    plan->bneck = 3;
+    plan->bn = 128;
+    plan->esz = 2;
+    plan->ctas = 2;
+    plan->cg.M = d.M;
+    plan->cg.tiles = (d.M + 255) / 256;
+    plan->cg.reverse = d.reverse ? 1 : 0;
+    plan->cp.bias3 = d.bias3;
+    plan->cp.bias1n = d.bias1n;
+    const int pairs = plan->cg.tiles < num_sms / 2 ? plan->cg.tiles : num_sms / 2;
+    plan->grid = 2 * pairs;
+    const double M = d.M;
+    plan->flops = 2.0 * M * (512.0 * 128 + 128.0 * 512);
+    plan->bytes = 2.0 * M * (128 + 512 + 512 + 128) + 2.0 * (512.0 * 128 + 128.0 * 512) + 4.0 * (512 + 128);
+    int r;
+    if ((r = make_tiled_2d(&plan->tmA, TmDtype::BF16, d.t2, d.M, 128, 128)) != 0)
+        return fail(err, errlen, "c3n1_plan: t2 tensor map failed", r);
+    if ((r = make_tiled_2d(&plan->tmB, TmDtype::BF16, d.w3, 512, 128, 64)) != 0)
+        return fail(err, errlen, "c3n1_plan: w3 tensor map failed", r);
+    if ((r = make_tiled_2d(&plan->tmW1n, TmDtype::BF16, d.w1n, 128, 512, 64)) != 0)
+        return fail(err, errlen, "c3n1_plan: w1n tensor map failed", r);
+    if ((r = make_tiled_2d(&plan->tmRes, TmDtype::BF16, d.residual, d.M, 512, 128)) != 0)
+        return fail(err, errlen, "c3n1_plan: residual tensor map failed", r);
+    if ((r = make_tiled_2d(&plan->tmOut, TmDtype::BF16, d.y, d.M, 512, 128)) != 0)
+        return fail(err, errlen, "c3n1_plan: y tensor map failed", r);
+    if ((r = make_tiled_2d(&plan->tmT1n, TmDtype::BF16, d.t1n, d.M, 128, 128)) != 0)
+        return fail(err, errlen, "c3n1_plan: t1n tensor map failed", r);
+    plan->tmW3 = plan->tmB;
+    plan->tmWds = plan->tmB;
     return 0;
 }
 
@@ -319,6 +357,9 @@ static cudaError_t launch2(const ConvPlan& p, cudaStream_t stream) {
 }
 
 cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
+    if (p.bneck == 3)
+        return launch_pdl(bneck_c3n1_kernel<C3n1Cfg>, p.grid, C3n1Cfg::THREADS, C3n1Cfg::SMEM_BYTES, stream, p.tmA, p.tmB,
+                          p.tmW1n, p.tmRes, p.tmOut, p.tmT1n, p.cp, p.cg);
     if (p.bneck == 1)
         return launch_pdl(bneck_l1_kernel<BneckCfg<false>>, p.grid, BneckCfg<false>::THREADS,
                           BneckCfg<false>::SMEM_BYTES, stream, p.tmA, p.tmB, p.tmW3, p.tmWds, p.tmW1n, p.tmRes,

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "bneck_c3n1.cuh"
 #include "bneck_l1.cuh"
 #include "conv3x3_halo.cuh"
 #include "conv_igemm.cuh"
@@ -45,10 +46,27 @@ struct BneckDesc {
     void* t1n;               // next block's conv1 output NHWC [B][H][W][64]
 };
 
+// conv3 (128 -> 512) + shortcut + ReLU fused with the next block's conv1 (512 -> 128) (bneck_c3n1.cuh)
+struct C3n1Desc {
+    int M;                 // pixel rows
+    bool reverse = false;
+    const void* t2;        // [M][128]
+    const void* w3;        // [512][128]
+    const float* bias3;
+    const void* residual;  // [M][512]
+    void* y;               // [M][512]
+    const void* w1n;       // [128][512]
+    const float* bias1n;
+    void* t1n;             // [M][128]
+};
+
 struct ConvPlan {
     CUtensorMap tmA, tmB, tmOut, tmRes;
     CUtensorMap tmW3, tmWds, tmW1n, tmT1n;  // fused Bottleneck tail only
-    int bneck;    // 0 = plain conv, 1 = fused tail with residual tensor, 2 = fused tail with folded downsample
+    int bneck;    // 0 = plain conv, 1 = fused tail with residual tensor, 2 = fused tail with folded downsample,
+                  // 3 = conv3 + next conv1 (bneck_c3n1.cuh; geometry in cg / cp)
+    C3n1Geom cg;
+    C3n1Params cp;
     BneckGeom bg;
     BneckParams bp;
     ConvGeom g;
@@ -73,6 +91,7 @@ bool conv_plan_halo_ok(const ConvDesc& d);
 int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn, char* err,
                    int errlen);
 bool bneck_plan_ok(int H, int W, int esz);
+int c3n1_plan_init(ConvPlan* plan, const C3n1Desc& d, int num_sms, char* err, int errlen);
 int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, int errlen);
 // Enqueues the kernel on `stream` (no synchronisation).
 cudaError_t conv_plan_launch(const ConvPlan& plan, cudaStream_t stream);

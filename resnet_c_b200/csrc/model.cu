@@ -466,15 +466,43 @@ ChunkPlan* Model::plan_for(int n) {
         } else if (bw.bottleneck) {
             // conv1 -> bn1 -> relu -> conv2(stride) -> bn2 -> relu -> conv3 -> bn3 -> +shortcut -> relu
             // (layerForward, main.cu:138-163)
-            void* t1 = arena.acquire(bytes(bw.conv1.Cout, hw));
-            if (!t1) return fail_alloc();
-            if (add_conv(bw.conv1, x, hw, nullptr, true, t1)) return nullptr;
+            void* t1 = pre_t1;  // already produced by the previous block's fused conv3 + conv1' launch
+            pre_t1 = nullptr;
+            if (!t1) {
+                if (!(t1 = arena.acquire(bytes(bw.conv1.Cout, hw)))) return fail_alloc();
+                if (add_conv(bw.conv1, x, hw, nullptr, true, t1)) return nullptr;
+            }
             void* t2 = arena.acquire(bytes(bw.conv2.Cout, out_hw));
             if (!t2) return fail_alloc();
             if (add_conv(bw.conv2, t1, hw, nullptr, true, t2)) return nullptr;
             arena.release(t1);
             if (!(y = arena.acquire(bytes(out_c, out_hw)))) return fail_alloc();
-            if (add_conv(bw.conv3, t2, out_hw, shortcut, true, y)) return nullptr;
+            // layer2-shaped blocks (128 -> 512): conv3 + shortcut + ReLU and the NEXT block's conv1 in one launch
+            const BlockWeights* nb = bi + 1 < blocks.size() ? &blocks[bi + 1] : nullptr;
+            const bool c3n1 = fuse_level >= 1 && fuse_next && esz == 2 && bw.conv3.Cin == 128 && out_c == 512 && nb &&
+                              nb->bottleneck && !nb->has_ds && nb->conv1.Cin == 512 && nb->conv1.Cout == 128 &&
+                              nb->conv2.stride == 1 && !getenv("RNB_NO_C3N1");
+            if (c3n1) {
+                void* t1n = arena.acquire(bytes(128, out_hw));
+                if (!t1n) return fail_alloc();
+                C3n1Desc cd{};
+                cd.M = n * out_hw * out_hw;
+                cd.reverse = alternate_tiles && (p.convs.size() & 1) != 0;
+                cd.t2 = t2; cd.w3 = bw.conv3.w; cd.bias3 = bw.conv3.bias; cd.residual = shortcut; cd.y = y;
+                cd.w1n = nb->conv1.w; cd.bias1n = nb->conv1.bias; cd.t1n = t1n;
+                ConvPlan cp;
+                if (c3n1_plan_init(&cp, cd, num_sms, err, sizeof(err))) {
+                    set_error(err);
+                    return nullptr;
+                }
+                if (getenv("RNB_VERBOSE"))
+                    fprintf(stderr, "rnb plan: conv#%zu n=%d %dx%d fused conv3 + next conv1 grid %d\n", p.convs.size(), n,
+                            out_hw, out_hw, cp.grid);
+                p.convs.push_back(cp);
+                pre_t1 = t1n;
+            } else if (add_conv(bw.conv3, t2, out_hw, shortcut, true, y)) {
+                return nullptr;
+            }
             arena.release(t2);
         } else {
             void* t1 = arena.acquire(bytes(bw.conv1.Cout, out_hw));

@@ -211,11 +211,12 @@ def _run_with_env(monkeypatch, env, arch, batch, names):
 
 @pytest.mark.parametrize("arch,batch", [("resnet50", 3), ("resnet50", 37), ("resnet152", 2)])
 def test_fused_bottleneck_tail_equals_layer_by_layer(monkeypatch, arch, batch):
-    """csrc/bneck_l1.cuh: conv2 + conv3 + residual (+ next conv1) in one launch rounds at the same
+    """csrc/bneck_l1.cuh (layer1: conv2 + conv3 + residual (+ next conv1) in one launch) and
+    csrc/bneck_c3n1.cuh (layer2: conv3 + residual + next conv1, active with RNB_FUSE_NEXT=1) round at the same
     points as the separate kernels, so RNB_FUSE=1 must be BIT-IDENTICAL to RNB_FUSE=0; RNB_FUSE=2 also
     folds the downsample conv into the conv3 accumulator (one BF16 rounding fewer on the shortcut), so
     it is compared within the BF16 bar. Odd batch sizes leave CTA pairs with unequal tile counts."""
-    names = ("layer1.0", "layer1.1", "layer1.2", "layer2.0")
+    names = ("layer1.0", "layer1.1", "layer1.2", "layer2.0", "layer2.1", "layer2.2", "layer2.3", "layer3.0")
     base = _run_with_env(monkeypatch, {"RNB_FUSE": "0"}, arch, batch, names)
     for nxt in ("0", "1"):
         got = _run_with_env(monkeypatch, {"RNB_FUSE": "1", "RNB_FUSE_NEXT": nxt}, arch, batch, names)
@@ -239,8 +240,9 @@ def test_launch_accounting(monkeypatch):
     model.close()
     monkeypatch.setenv("RNB_FUSE", "2")
     model = _model("resnet50", True, "bf16", 64, chunk=16)
-    # layer1: downsample + conv2 + conv3 of block 0 and conv1 + conv2 + conv3 of blocks 1, 2 -> 3 launches
-    assert model.launches_per_forward(16) == 51
+    # layer1: downsample + conv2 + conv3 of block 0 and conv1 + conv2 + conv3 of blocks 1, 2 -> 3 launches;
+    # layer2: conv3 of blocks 0..2 absorbs conv1 of blocks 1..3 -> 3 launches fewer
+    assert model.launches_per_forward(16) == 48
     assert model.flops_per_image == pytest.approx(8_178_368_512, rel=1e-9)
     model.close()
     m18 = _model("resnet18", True, "tf32", 4)
