@@ -348,4 +348,374 @@ bneck_c3n1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Streamed-weights variant for wider blocks (layer3: conv3 256 -> 1024, conv1' 1024 -> 256, 2 x 512 KB of
+// weights): same dataflow, but the weight matrices pass through two small shared-memory rings instead of being
+// resident. Per CTA: A2 tile (128 rows x K3, single buffer), W3 ring (2 stages, one 128-channel chunk of y =
+// 64 rows x K3 per stage), W1n ring (2 stages, one 64-wide K block of conv1' = N1/2 rows x 128 B per stage),
+// 4 staging boxes. TMEM: D2 2 x 128 columns + D3 N1 (= 256) columns.
+// Warps (416 threads): 0 producer (A2 + W3 ring), 1 conv3 issuer, 2 TMEM alloc + conv1' issuer, 3 store warp,
+// 4..11 epilogue, 12 W1n-ring producer.
+template <int K3_, int N3_, int N1_>
+struct C3n1sCfg {
+    static constexpr int K3 = K3_, N3 = N3_, N1 = N1_;
+    static constexpr int KB3 = K3_ / 64;                      // K blocks of conv3
+    static constexpr int NCHUNK = N3_ / 128;                  // 128-channel chunks of y
+    static constexpr int NBOX_Y = N3_ / 64;                   // staging boxes of y per tile (= K blocks of conv1')
+    static constexpr int NBOX_T = N1_ / 64;                   // staging boxes of t1' per tile
+    static constexpr int IPT = NBOX_Y + NBOX_T;
+    static constexpr int BOX_BYTES = 16384;
+    static constexpr int A2_BYTES = KB3 * BOX_BYTES;
+    static constexpr int W3_BLK_BYTES = 64 * 128;             // this CTA's 64 rows of one K block of a chunk
+    static constexpr int W3_STAGE_BYTES = KB3 * W3_BLK_BYTES;
+    static constexpr int NW3 = 2;
+    static constexpr int W1N_STAGE_BYTES = (N1_ / 2) * 128;   // this CTA's N1/2 rows of one K block
+    static constexpr int NW1 = 2;
+    static constexpr int NPOOL = 4;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int D2_COL = 0, D3_COL = 256;
+    static constexpr int NBAR = 2 + 2 * NW3 + 2 * NW1 + 4 + 2 + 4 * NPOOL;
+    static constexpr int SMEM_BYTES = 1024 + A2_BYTES + NW3 * W3_STAGE_BYTES + NW1 * W1N_STAGE_BYTES +
+                                      NPOOL * BOX_BYTES + NBAR * 8 + 16;
+    static constexpr int EPI_WARPS = 8;
+    static constexpr int THREADS = 128 + EPI_WARPS * 32 + 32;
+    static_assert(N1_ <= 256 && N1_ % 64 == 0 && N3_ % 128 == 0 && K3_ % 64 == 0, "shape");
+    static_assert((N3_ / 128) % 4 == 0, "each D2 half must be used an even number of times per tile");
+};
+using C3n1sL3 = C3n1sCfg<256, 1024, 256>;
+static_assert(C3n1sL3::SMEM_BYTES <= 232448, "smem budget");
+
+// Tensor maps: tmA t2 [M][K3] box rows 128; tmW3 [N3][K3] box rows 64; tmW1n [N1][N3] box rows N1/2;
+//              tmRes / tmY [M][N3] box rows 128; tmT1n [M][N1] box rows 128
+template <class Cfg>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::THREADS, 1)
+bneck_c3n1s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW3,
+                   const __grid_constant__ CUtensorMap tmW1n, const __grid_constant__ CUtensorMap tmRes,
+                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmT1n,
+                   const C3n1Params prm, const C3n1Geom g) {
+    using namespace ptx;
+    constexpr int NPOOL = Cfg::NPOOL, IPT = Cfg::IPT, NW3 = Cfg::NW3, NW1 = Cfg::NW1;
+    constexpr int NCHUNK = Cfg::NCHUNK, NBOX_Y = Cfg::NBOX_Y, NBOX_T = Cfg::NBOX_T, KB3 = Cfg::KB3;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_a2 = smem;
+    uint8_t* smem_w3 = smem_a2 + Cfg::A2_BYTES;
+    uint8_t* smem_w1n = smem_w3 + NW3 * Cfg::W3_STAGE_BYTES;
+    uint8_t* smem_pool = smem_w1n + NW1 * Cfg::W1N_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_pool + NPOOL * Cfg::BOX_BYTES);
+    uint64_t* a_full = bars;                 // leader
+    uint64_t* a_empty = a_full + 1;          // per CTA (multicast commit)
+    uint64_t* w3_full = a_empty + 1;         // leader, [NW3]
+    uint64_t* w3_empty = w3_full + NW3;      // per CTA (multicast commit), [NW3]
+    uint64_t* w1_full = w3_empty + NW3;      // leader, [NW1]
+    uint64_t* w1_empty = w1_full + NW1;      // per CTA (multicast commit), [NW1]
+    uint64_t* d2_full = w1_empty + NW1;      // per CTA, [2 halves]
+    uint64_t* d2_empty = d2_full + 2;        // leader, 16 arrivals, [2 halves]
+    uint64_t* d3_full = d2_empty + 2;        // per CTA
+    uint64_t* d3_empty = d3_full + 1;        // leader, 16 arrivals
+    uint64_t* box_ready = d3_empty + 1;
+    uint64_t* c_full = box_ready + NPOOL;
+    uint64_t* cx_full = c_full + NPOOL;
+    uint64_t* c_mma_done = cx_full + NPOOL;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int T = (g.tiles - pair + num_pairs - 1) / num_pairs;
+    const int items = T * IPT;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmW3);
+        tma_prefetch_desc(&tmW1n);
+        tma_prefetch_desc(&tmRes);
+        tma_prefetch_desc(&tmY);
+        tma_prefetch_desc(&tmT1n);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int i = 0; i < NW3; ++i) {
+            mbar_init(&w3_full[i], 1);
+            mbar_init(&w3_empty[i], 1);
+        }
+        for (int i = 0; i < NW1; ++i) {
+            mbar_init(&w1_full[i], 1);
+            mbar_init(&w1_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&d2_full[i], 1);
+            mbar_init(&d2_empty[i], 2 * Cfg::EPI_WARPS);
+        }
+        mbar_init(d3_full, 1);
+        mbar_init(d3_empty, 2 * Cfg::EPI_WARPS);
+        for (int i = 0; i < NPOOL; ++i) {
+            mbar_init(&box_ready[i], 1);
+            mbar_init(&c_full[i], Cfg::EPI_WARPS);
+            mbar_init(&cx_full[i], 2 * Cfg::EPI_WARPS);
+            mbar_init(&c_mma_done[i], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        __syncwarp();
+        tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    griddep_launch_dependents();  // see conv_igemm.cuh
+    griddep_wait();
+
+    auto tile_row0 = [&](int it_local) {
+        const int t = pair + it_local * num_pairs;
+        const int tt = g.reverse ? g.tiles - 1 - t : t;
+        return tt * 256 + static_cast<int>(rank) * 128;
+    };
+
+    if (warp == 0) {
+        // ===================================================== producer: A2 tile + W3 ring (both CTAs)
+        const int r64 = static_cast<int>(rank) * 64;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < T; ++it) {
+            const int row0 = tile_row0(it);
+            mbar_wait(a_empty, (it & 1) ^ 1);
+            if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(a_full, 2 * Cfg::A2_BYTES);
+                for (int kb = 0; kb < KB3; ++kb)
+                    tma_load_2d_2sm(smem_a2 + kb * Cfg::BOX_BYTES, &tmA, a_full, kb * 64, row0);
+            }
+            __syncwarp();
+            for (int c = 0; c < NCHUNK; ++c) {
+                mbar_wait(&w3_empty[stage], phase ^ 1);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(&w3_full[stage], 2 * Cfg::W3_STAGE_BYTES);
+                    for (int kb = 0; kb < KB3; ++kb)
+                        tma_load_2d_2sm(smem_w3 + stage * Cfg::W3_STAGE_BYTES + kb * Cfg::W3_BLK_BYTES, &tmW3,
+                                        &w3_full[stage], kb * 64, c * 128 + r64);
+                }
+                __syncwarp();
+                if (++stage == NW3) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 12) {
+        // ===================================================== producer: W1n ring (both CTAs)
+        const int rrow = static_cast<int>(rank) * (Cfg::N1 / 2);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < T; ++it) {
+            for (int b = 0; b < NBOX_Y; ++b) {
+                mbar_wait(&w1_empty[stage], phase ^ 1);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(&w1_full[stage], 2 * Cfg::W1N_STAGE_BYTES);
+                    tma_load_2d_2sm(smem_w1n + stage * Cfg::W1N_STAGE_BYTES, &tmW1n, &w1_full[stage], b * 64, rrow);
+                }
+                __syncwarp();
+                if (++stage == NW1) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== conv3 MMA issuer (leader CTA only)
+        if (rank == 0) {
+            constexpr uint32_t idesc128 = umma_instr_desc(UMMA_FMT_BF16, 256, 128);
+            const uint64_t a2_desc = umma_smem_desc(smem_u32(smem_a2), 0, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t w3_desc = umma_smem_desc(smem_u32(smem_w3), 0, 1024, UMMA_LAYOUT_SW128);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < T; ++i) {
+                mbar_wait(a_full, i & 1);
+#pragma unroll 1
+                for (int hc = 0; hc < NCHUNK / 2; ++hc) {  // chunk c = 2 * hc + hf lives in D2 half hf
+#pragma unroll 1
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int c = 2 * hc + hf;
+                        mbar_wait(&w3_full[stage], phase);
+                        // use number (NCHUNK / 2) * i + hc of this half (NCHUNK / 2 is even)
+                        mbar_wait(hf == 0 ? &d2_empty[0] : &d2_empty[1], (hc & 1) ^ 1);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t d_tmem = tmem_base + Cfg::D2_COL + hf * 128;
+                            const uint64_t bs = w3_desc + static_cast<uint64_t>((stage * Cfg::W3_STAGE_BYTES) >> 4);
+#pragma unroll
+                            for (int kb = 0; kb < KB3; ++kb) {
+                                const uint64_t a = a2_desc + static_cast<uint64_t>((kb * Cfg::BOX_BYTES) >> 4);
+                                const uint64_t b = bs + static_cast<uint64_t>((kb * Cfg::W3_BLK_BYTES) >> 4);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    mma_f16_ss_2sm(d_tmem, a + static_cast<uint64_t>(k * 2),
+                                                   b + static_cast<uint64_t>(k * 2), idesc128, (kb | k) != 0);
+                            }
+                            tc_commit_2sm(&w3_empty[stage]);
+                            if (c == NCHUNK - 1) tc_commit_2sm(a_empty);  // the A2 tile is fully consumed
+                            tc_commit_2sm(hf == 0 ? &d2_full[0] : &d2_full[1]);
+                        }
+                        __syncwarp();
+                        if (++stage == NW3) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================================================== conv1' MMA issuer (leader CTA only)
+        if (rank == 0) {
+            constexpr uint32_t idescn1 = umma_instr_desc(UMMA_FMT_BF16, 256, Cfg::N1);
+            const uint64_t w1n_desc = umma_smem_desc(smem_u32(smem_w1n), 0, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t pool_desc = umma_smem_desc(smem_u32(smem_pool), 0, 1024, UMMA_LAYOUT_SW128);
+            uint32_t cx_phase_bits = 0;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < T; ++i) {
+                mbar_wait(d3_empty, (i & 1) ^ 1);
+#pragma unroll 1
+                for (int b = 0; b < NBOX_Y; ++b) {
+                    const int cs = (i * IPT + b) % NPOOL;
+                    mbar_wait(&w1_full[stage], phase);
+                    mbar_wait(&cx_full[cs], (cx_phase_bits >> cs) & 1);
+                    cx_phase_bits ^= 1u << cs;
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t d_tmem = tmem_base + Cfg::D3_COL;
+                        const uint64_t a = pool_desc + static_cast<uint64_t>((cs * Cfg::BOX_BYTES) >> 4);
+                        const uint64_t bd = w1n_desc + static_cast<uint64_t>((stage * Cfg::W1N_STAGE_BYTES) >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_f16_ss_2sm(d_tmem, a + static_cast<uint64_t>(k * 2), bd + static_cast<uint64_t>(k * 2),
+                                           idescn1, (b | k) != 0);
+                        tc_commit_2sm(&c_mma_done[cs]);
+                        tc_commit_2sm(&w1_empty[stage]);
+                        if (b == NBOX_Y - 1) tc_commit_2sm(d3_full);
+                    }
+                    __syncwarp();
+                    if (++stage == NW1) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================================================== store warp (both CTAs), see bneck_l1.cuh
+        auto prepare = [&](int item) {
+            const int cs = item % NPOOL;
+            const int it_local = item / IPT, sub = item - it_local * IPT;
+            if (sub < NBOX_Y) {
+                mbar_expect_tx(&box_ready[cs], Cfg::BOX_BYTES);
+                tma_load_2d(smem_pool + cs * Cfg::BOX_BYTES, &tmRes, &box_ready[cs], sub * 64, tile_row0(it_local));
+            } else {
+                mbar_arrive(&box_ready[cs]);
+            }
+        };
+        if (elect_one()) {
+            for (int i = 0; i < NPOOL && i < items; ++i) prepare(i);
+        }
+        __syncwarp();
+        uint32_t md_phase_bits = 0;
+        auto recycle = [&](int item) {
+            const int cs = item % NPOOL;
+            if (item % IPT < NBOX_Y) {
+                mbar_wait(&c_mma_done[cs], (md_phase_bits >> cs) & 1);
+                md_phase_bits ^= 1u << cs;
+            }
+            if (item + NPOOL < items && elect_one()) prepare(item + NPOOL);
+            __syncwarp();
+        };
+        for (int item = 0; item < items; ++item) {
+            const int cs = item % NPOOL;
+            const int it_local = item / IPT, sub = item - it_local * IPT;
+            mbar_wait(&c_full[cs], (item / NPOOL) & 1);
+            if (elect_one()) {
+                const uint8_t* box = smem_pool + cs * Cfg::BOX_BYTES;
+                if (sub < NBOX_Y)
+                    tma_store_2d(&tmY, box, sub * 64, tile_row0(it_local));
+                else
+                    tma_store_2d(&tmT1n, box, (sub - NBOX_Y) * 64, tile_row0(it_local));
+                tma_store_commit();
+                tma_store_wait_read<1>();
+            }
+            __syncwarp();
+            if (item > 0) recycle(item - 1);
+        }
+        if (elect_one()) tma_store_wait_read<0>();
+        __syncwarp();
+        if (items > 0) recycle(items - 1);
+        if (elect_one()) tma_store_wait_all<0>();
+        __syncwarp();
+    } else if (warp >= 4 && warp < 12) {
+        // ===================================================== epilogue (both CTAs)
+        const int q4 = warp & 3;
+        const int h = (warp - 4) >> 2;
+        const int row_in_tile = q4 * 32 + lane;
+        const uint32_t swz = static_cast<uint32_t>(row_in_tile & 7);
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+        const uint32_t row_off = static_cast<uint32_t>(row_in_tile) * 128;
+
+        auto box_step = [&](int item, uint32_t col, const float* bias64, int has_res, bool to_mma) {
+            const int cs = item % NPOOL;
+            mbar_wait(&box_ready[cs], (item / NPOOL) & 1);
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld_32x32(lane_base + col + h * 32, v);
+            tmem_ld_wait();
+            epilogue_chunk<2>(v, smem_pool + cs * Cfg::BOX_BYTES + row_off, static_cast<uint32_t>(h * 4), swz,
+                              bias64 + h * 32, has_res, 1);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&c_full[cs]);
+                if (to_mma) mbar_arrive_leader(&cx_full[cs]);
+            }
+        };
+        for (int i = 0; i < T; ++i) {
+#pragma unroll 1
+            for (int hc = 0; hc < NCHUNK / 2; ++hc) {
+                // half 0: chunk 2 hc
+                mbar_wait(&d2_full[0], hc & 1);
+                tc_fence_after();
+                box_step(i * IPT + 4 * hc, Cfg::D2_COL, prm.bias3 + hc * 256, 1, true);
+                box_step(i * IPT + 4 * hc + 1, Cfg::D2_COL + 64, prm.bias3 + hc * 256 + 64, 1, true);
+                if (lane == 0) mbar_arrive_leader(&d2_empty[0]);
+                // half 1: chunk 2 hc + 1
+                mbar_wait(&d2_full[1], hc & 1);
+                tc_fence_after();
+                box_step(i * IPT + 4 * hc + 2, Cfg::D2_COL + 128, prm.bias3 + hc * 256 + 128, 1, true);
+                box_step(i * IPT + 4 * hc + 3, Cfg::D2_COL + 192, prm.bias3 + hc * 256 + 192, 1, true);
+                if (lane == 0) mbar_arrive_leader(&d2_empty[1]);
+            }
+            mbar_wait(d3_full, i & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int jb = 0; jb < NBOX_T; ++jb)
+                box_step(i * IPT + NBOX_Y + jb, Cfg::D3_COL + jb * 64, prm.bias1n + jb * 64, 0, false);
+            if (lane == 0) mbar_arrive_leader(d3_empty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        __syncwarp();
+        tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
 }  // namespace rnb

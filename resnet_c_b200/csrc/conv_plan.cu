@@ -72,6 +72,9 @@ cudaError_t conv_kernels_init() {
     if ((e = cudaFuncSetAttribute(bneck_l1_kernel<BneckCfg<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   BneckCfg<false>::SMEM_BYTES)) != cudaSuccess)
         return e;
+    if ((e = cudaFuncSetAttribute(bneck_c3n1s_kernel<C3n1sL3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C3n1sL3::SMEM_BYTES)) != cudaSuccess)
+        return e;
     if ((e = cudaFuncSetAttribute(bneck_c3n1_kernel<C3n1Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C3n1Cfg::SMEM_BYTES)) != cudaSuccess)
         return e;
@@ -179,10 +182,16 @@ int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, 
     return 0;
 }
 
+bool c3n1_shape_ok(int K3, int N3, int N1) {
+    return (K3 == 128 && N3 == 512 && N1 == 128) || (K3 == 256 && N3 == 1024 && N1 == 256);
+}
+
 int c3n1_plan_init(ConvPlan* plan, const C3n1Desc& d, int num_sms, char* err, int errlen) {
     memset(plan, 0, sizeof(*plan));
     if (d.M <= 0) return fail(err, errlen, "c3n1_plan: bad M", -5);
-    plan->bneck = 3;
+    if (!c3n1_shape_ok(d.K3, d.N3, d.N1)) return fail(err, errlen, "c3n1_plan: unsupported channel counts", -7);
+    const bool streamed = d.K3 != 128;
+    plan->bneck = streamed ? 4 : 3;
     plan->bn = 128;
     plan->esz = 2;
     plan->ctas = 2;
@@ -194,20 +203,21 @@ int c3n1_plan_init(ConvPlan* plan, const C3n1Desc& d, int num_sms, char* err, in
     const int pairs = plan->cg.tiles < num_sms / 2 ? plan->cg.tiles : num_sms / 2;
     plan->grid = 2 * pairs;
     const double M = d.M;
-    plan->flops = 2.0 * M * (512.0 * 128 + 128.0 * 512);
-    plan->bytes = 2.0 * M * (128 + 512 + 512 + 128) + 2.0 * (512.0 * 128 + 128.0 * 512) + 4.0 * (512 + 128);
+    const double wel = 1.0 * d.N3 * d.K3 + 1.0 * d.N1 * d.N3;
+    plan->flops = 2.0 * M * wel;
+    plan->bytes = 2.0 * M * (d.K3 + 2.0 * d.N3 + d.N1) + 2.0 * wel + 4.0 * (d.N3 + d.N1);
     int r;
-    if ((r = make_tiled_2d(&plan->tmA, TmDtype::BF16, d.t2, d.M, 128, 128)) != 0)
+    if ((r = make_tiled_2d(&plan->tmA, TmDtype::BF16, d.t2, d.M, d.K3, 128)) != 0)
         return fail(err, errlen, "c3n1_plan: t2 tensor map failed", r);
-    if ((r = make_tiled_2d(&plan->tmB, TmDtype::BF16, d.w3, 512, 128, 64)) != 0)
+    if ((r = make_tiled_2d(&plan->tmB, TmDtype::BF16, d.w3, d.N3, d.K3, 64)) != 0)
         return fail(err, errlen, "c3n1_plan: w3 tensor map failed", r);
-    if ((r = make_tiled_2d(&plan->tmW1n, TmDtype::BF16, d.w1n, 128, 512, 64)) != 0)
+    if ((r = make_tiled_2d(&plan->tmW1n, TmDtype::BF16, d.w1n, d.N1, d.N3, streamed ? d.N1 / 2 : 64)) != 0)
         return fail(err, errlen, "c3n1_plan: w1n tensor map failed", r);
-    if ((r = make_tiled_2d(&plan->tmRes, TmDtype::BF16, d.residual, d.M, 512, 128)) != 0)
+    if ((r = make_tiled_2d(&plan->tmRes, TmDtype::BF16, d.residual, d.M, d.N3, 128)) != 0)
         return fail(err, errlen, "c3n1_plan: residual tensor map failed", r);
-    if ((r = make_tiled_2d(&plan->tmOut, TmDtype::BF16, d.y, d.M, 512, 128)) != 0)
+    if ((r = make_tiled_2d(&plan->tmOut, TmDtype::BF16, d.y, d.M, d.N3, 128)) != 0)
         return fail(err, errlen, "c3n1_plan: y tensor map failed", r);
-    if ((r = make_tiled_2d(&plan->tmT1n, TmDtype::BF16, d.t1n, d.M, 128, 128)) != 0)
+    if ((r = make_tiled_2d(&plan->tmT1n, TmDtype::BF16, d.t1n, d.M, d.N1, 128)) != 0)
         return fail(err, errlen, "c3n1_plan: t1n tensor map failed", r);
     plan->tmW3 = plan->tmB;
     plan->tmWds = plan->tmB;
@@ -357,6 +367,9 @@ static cudaError_t launch2(const ConvPlan& p, cudaStream_t stream) {
 }
 
 cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
+    if (p.bneck == 4)
+        return launch_pdl(bneck_c3n1s_kernel<C3n1sL3>, p.grid, C3n1sL3::THREADS, C3n1sL3::SMEM_BYTES, stream, p.tmA, p.tmB,
+                          p.tmW1n, p.tmRes, p.tmOut, p.tmT1n, p.cp, p.cg);
     if (p.bneck == 3)
         return launch_pdl(bneck_c3n1_kernel<C3n1Cfg>, p.grid, C3n1Cfg::THREADS, C3n1Cfg::SMEM_BYTES, stream, p.tmA, p.tmB,
                           p.tmW1n, p.tmRes, p.tmOut, p.tmT1n, p.cp, p.cg);

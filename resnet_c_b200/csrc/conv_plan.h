@@ -49,6 +49,7 @@ struct BneckDesc {
 // conv3 (128 -> 512) + shortcut + ReLU fused with the next block's conv1 (512 -> 128) (bneck_c3n1.cuh)
 struct C3n1Desc {
     int M;                 // pixel rows
+    int K3 = 128, N3 = 512, N1 = 128;  // conv3: K3 -> N3, conv1': N3 -> N1. (128,512,128) or (256,1024,256)
     bool reverse = false;
     const void* t2;        // [M][128]
     const void* w3;        // [512][128]
@@ -64,7 +65,8 @@ struct ConvPlan {
     CUtensorMap tmA, tmB, tmOut, tmRes;
     CUtensorMap tmW3, tmWds, tmW1n, tmT1n;  // fused Bottleneck tail only
     int bneck;    // 0 = plain conv, 1 = fused tail with residual tensor, 2 = fused tail with folded downsample,
-                  // 3 = conv3 + next conv1 (bneck_c3n1.cuh; geometry in cg / cp)
+                  // 3 = conv3 + next conv1 (bneck_c3n1.cuh; geometry in cg / cp), resident weights (layer2 shape),
+                  // 4 = the same with streamed weights (layer3 shape)
     C3n1Geom cg;
     C3n1Params cp;
     BneckGeom bg;
@@ -91,6 +93,7 @@ bool conv_plan_halo_ok(const ConvDesc& d);
 int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn, char* err,
                    int errlen);
 bool bneck_plan_ok(int H, int W, int esz);
+bool c3n1_shape_ok(int K3, int N3, int N1);
 int c3n1_plan_init(ConvPlan* plan, const C3n1Desc& d, int num_sms, char* err, int errlen);
 int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, int errlen);
 // Enqueues the kernel on `stream` (no synchronisation).

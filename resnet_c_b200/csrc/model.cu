@@ -479,14 +479,20 @@ ChunkPlan* Model::plan_for(int n) {
             if (!(y = arena.acquire(bytes(out_c, out_hw)))) return fail_alloc();
             // layer2-shaped blocks (128 -> 512): conv3 + shortcut + ReLU and the NEXT block's conv1 in one launch
             const BlockWeights* nb = bi + 1 < blocks.size() ? &blocks[bi + 1] : nullptr;
-            const bool c3n1 = fuse_level >= 1 && fuse_next && esz == 2 && bw.conv3.Cin == 128 && out_c == 512 && nb &&
-                              nb->bottleneck && !nb->has_ds && nb->conv1.Cin == 512 && nb->conv1.Cout == 128 &&
-                              nb->conv2.stride == 1 && !getenv("RNB_NO_C3N1");
+            // (layer2 shape 128 -> 512 -> 128: resident weights; layer3 shape 256 -> 1024 -> 256: streamed weights;
+            // RNB_C3N1=0 off, 1 = layer2 only, default both)
+            const char* c3env = getenv("RNB_C3N1");
+            const int c3level = c3env ? atoi(c3env) : 2;
+            const bool c3n1 = fuse_level >= 1 && fuse_next && esz == 2 && nb && nb->bottleneck && !nb->has_ds &&
+                              nb->conv1.Cin == out_c && nb->conv2.stride == 1 &&
+                              c3n1_shape_ok(bw.conv3.Cin, out_c, nb->conv1.Cout) &&
+                              c3level >= (bw.conv3.Cin == 128 ? 1 : 2);
             if (c3n1) {
-                void* t1n = arena.acquire(bytes(128, out_hw));
+                void* t1n = arena.acquire(bytes(nb->conv1.Cout, out_hw));
                 if (!t1n) return fail_alloc();
                 C3n1Desc cd{};
                 cd.M = n * out_hw * out_hw;
+                cd.K3 = bw.conv3.Cin; cd.N3 = out_c; cd.N1 = nb->conv1.Cout;
                 cd.reverse = alternate_tiles && (p.convs.size() & 1) != 0;
                 cd.t2 = t2; cd.w3 = bw.conv3.w; cd.bias3 = bw.conv3.bias; cd.residual = shortcut; cd.y = y;
                 cd.w1n = nb->conv1.w; cd.bias1n = nb->conv1.bias; cd.t1n = t1n;

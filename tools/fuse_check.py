@@ -23,7 +23,7 @@ def run(arch, batch, env):
         x = weights.synthetic_images(batch).cuda()
         logits, top1 = m.forward(x)
         torch.cuda.synchronize()
-        acts = {n: m.activation(n).clone() for n in ("maxpool", "layer1.2", "layer2.0", "layer2.1", "layer2.2", "layer2.3", "layer3.0")}
+        acts = {n: m.activation(n).clone() for n in ("maxpool", "layer1.2", "layer2.0", "layer2.1", "layer2.2", "layer2.3", "layer3.0", "layer3.1", "layer3.3", "layer3.5", "layer4.0")}
         out = (logits.clone(), top1.clone(), acts, m.launches_per_forward(batch))
         m.close()
         return out
