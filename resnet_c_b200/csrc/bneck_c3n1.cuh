@@ -367,8 +367,10 @@ struct C3n1sCfg {
     static constexpr int BOX_BYTES = 16384;
     static constexpr int A2_BYTES = KB3 * BOX_BYTES;
     static constexpr int W3_BLK_BYTES = 64 * 128;             // this CTA's 64 rows of one K block of a chunk
-    static constexpr int W3_STAGE_BYTES = KB3 * W3_BLK_BYTES;
-    static constexpr int NW3 = 2;
+    static constexpr int KBS = 2;                             // K blocks per W3 ring stage (fine-grained ring:
+    static constexpr int W3_STAGE_BYTES = KBS * W3_BLK_BYTES; //  more stages in flight for the same bytes)
+    static constexpr int NW3 = 4;
+    static_assert(KB3 % KBS == 0, "stage granularity");
     static constexpr int W1N_STAGE_BYTES = (N1_ / 2) * 128;   // this CTA's N1/2 rows of one K block
     static constexpr int NW1 = 2;
     static constexpr int NPOOL = 4;
@@ -496,17 +498,19 @@ bneck_c3n1s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             __syncwarp();
             for (int c = 0; c < NCHUNK; ++c) {
-                mbar_wait(&w3_empty[stage], phase ^ 1);
-                if (elect_one()) {
-                    if (rank == 0) mbar_expect_tx(&w3_full[stage], 2 * Cfg::W3_STAGE_BYTES);
-                    for (int kb = 0; kb < KB3; ++kb)
-                        tma_load_2d_2sm(smem_w3 + stage * Cfg::W3_STAGE_BYTES + kb * Cfg::W3_BLK_BYTES, &tmW3,
-                                        &w3_full[stage], kb * 64, c * 128 + r64);
-                }
-                __syncwarp();
-                if (++stage == NW3) {
-                    stage = 0;
-                    phase ^= 1;
+                for (int ks = 0; ks < KB3 / Cfg::KBS; ++ks) {
+                    mbar_wait(&w3_empty[stage], phase ^ 1);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(&w3_full[stage], 2 * Cfg::W3_STAGE_BYTES);
+                        for (int kk = 0; kk < Cfg::KBS; ++kk)
+                            tma_load_2d_2sm(smem_w3 + stage * Cfg::W3_STAGE_BYTES + kk * Cfg::W3_BLK_BYTES, &tmW3,
+                                            &w3_full[stage], (ks * Cfg::KBS + kk) * 64, c * 128 + r64);
+                    }
+                    __syncwarp();
+                    if (++stage == NW3) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
@@ -544,30 +548,36 @@ bneck_c3n1s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll 1
                     for (int hf = 0; hf < 2; ++hf) {
                         const int c = 2 * hc + hf;
-                        mbar_wait(&w3_full[stage], phase);
                         // use number (NCHUNK / 2) * i + hc of this half (NCHUNK / 2 is even)
                         mbar_wait(hf == 0 ? &d2_empty[0] : &d2_empty[1], (hc & 1) ^ 1);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint32_t d_tmem = tmem_base + Cfg::D2_COL + hf * 128;
-                            const uint64_t bs = w3_desc + static_cast<uint64_t>((stage * Cfg::W3_STAGE_BYTES) >> 4);
+                        const uint32_t d_tmem = tmem_base + Cfg::D2_COL + hf * 128;
+#pragma unroll 1
+                        for (int ks = 0; ks < KB3 / Cfg::KBS; ++ks) {
+                            mbar_wait(&w3_full[stage], phase);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t bs = w3_desc + static_cast<uint64_t>((stage * Cfg::W3_STAGE_BYTES) >> 4);
 #pragma unroll
-                            for (int kb = 0; kb < KB3; ++kb) {
-                                const uint64_t a = a2_desc + static_cast<uint64_t>((kb * Cfg::BOX_BYTES) >> 4);
-                                const uint64_t b = bs + static_cast<uint64_t>((kb * Cfg::W3_BLK_BYTES) >> 4);
+                                for (int kk = 0; kk < Cfg::KBS; ++kk) {
+                                    const int kb = ks * Cfg::KBS + kk;
+                                    const uint64_t a = a2_desc + static_cast<uint64_t>((kb * Cfg::BOX_BYTES) >> 4);
+                                    const uint64_t b = bs + static_cast<uint64_t>((kk * Cfg::W3_BLK_BYTES) >> 4);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    mma_f16_ss_2sm(d_tmem, a + static_cast<uint64_t>(k * 2),
-                                                   b + static_cast<uint64_t>(k * 2), idesc128, (kb | k) != 0);
+                                    for (int k = 0; k < 4; ++k)
+                                        mma_f16_ss_2sm(d_tmem, a + static_cast<uint64_t>(k * 2),
+                                                       b + static_cast<uint64_t>(k * 2), idesc128, (kb | k) != 0);
+                                }
+                                tc_commit_2sm(&w3_empty[stage]);
+                                if (ks == KB3 / Cfg::KBS - 1) {
+                                    if (c == NCHUNK - 1) tc_commit_2sm(a_empty);  // the A2 tile is fully consumed
+                                    tc_commit_2sm(hf == 0 ? &d2_full[0] : &d2_full[1]);
+                                }
                             }
-                            tc_commit_2sm(&w3_empty[stage]);
-                            if (c == NCHUNK - 1) tc_commit_2sm(a_empty);  // the A2 tile is fully consumed
-                            tc_commit_2sm(hf == 0 ? &d2_full[0] : &d2_full[1]);
-                        }
-                        __syncwarp();
-                        if (++stage == NW3) {
-                            stage = 0;
-                            phase ^= 1;
+                            __syncwarp();
+                            if (++stage == NW3) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
                         }
                     }
                 }
