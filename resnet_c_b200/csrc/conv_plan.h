@@ -81,6 +81,8 @@ struct ConvPlan {
     HaloGeom hg;
     int esz;      // element bytes
     int grid;     // persistent CTAs
+    int side;     // 1 = launched on the engine's side stream (downsample conv overlapped with conv1/conv2)
+    int join;     // 1 = must wait for the side stream before it starts (consumes the downsample output)
     double flops;  // 2*M*N*K
     double bytes;  // algorithmic HBM bytes: input + weights + bias (+ residual) read once, output written once
 };

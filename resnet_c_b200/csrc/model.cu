@@ -138,6 +138,9 @@ Model::~Model() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
     for (auto e : copy_events) cudaEventDestroy(e);
     if (cap_stream) cudaStreamDestroy(cap_stream);
+    if (side_stream) cudaStreamDestroy(side_stream);
+    for (auto e : fork_ev) if (e) cudaEventDestroy(e);
+    for (auto e : join_ev) if (e) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (pipe_compute) cudaStreamDestroy(pipe_compute);
     for (HostSlot& hs : slots) {
@@ -196,6 +199,10 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
     arena.keep = ka && atoi(ka) != 0;
     const char* fu = getenv("RNB_FUSE");
     fuse_level = fu ? atoi(fu) : 2;
+    const char* ss = getenv("RNB_SIDE_SMS");
+    side_sms = ss ? atoi(ss) : 0;
+    if (side_sms < 0 || side_sms > num_sms - 16) side_sms = 0;
+    side_sms &= ~1;  // CTA pairs
     const char* fn = getenv("RNB_FUSE_NEXT");
     fuse_next = !(fn && atoi(fn) == 0);
 
@@ -303,6 +310,11 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
     flops_per_image = 2.0 * macs;
     RNB_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
     RNB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    RNB_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) {
+        RNB_CUDA(cudaEventCreateWithFlags(&fork_ev[i], cudaEventDisableTiming));
+        RNB_CUDA(cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming));
+    }
     set_error("");
     return RNB_OK;
 }
@@ -335,6 +347,7 @@ ChunkPlan* Model::plan_for(int n) {
     int hw = p_hw;
     const ActType act = esz == 2 ? ActType::BF16 : ActType::TF32;
     char err[256];
+    int sm_budget = num_sms;  // SMs the next planned conv may use (reduced while a downsample conv runs beside it)
     auto add_conv = [&](const ConvWeights& cw, const void* in, int in_hw, const void* res, bool relu,
                         void* out) -> int {
         ConvDesc d{};
@@ -345,7 +358,7 @@ ChunkPlan* Model::plan_for(int n) {
         d.reverse = alternate_tiles && (p.convs.size() & 1) != 0;
         d.in = in; d.weight = cw.w; d.bias = cw.bias; d.residual = res; d.out = out;
         ConvPlan cp;
-        int rc = conv_plan_init(&cp, d, num_sms, 0, err, sizeof(err));
+        int rc = conv_plan_init(&cp, d, sm_budget, 0, err, sizeof(err));
         if (rc) {
             set_error(err);
             return rc;
@@ -354,8 +367,8 @@ ChunkPlan* Model::plan_for(int n) {
             // Measure the tile families this layer admits on the buffers it will really use and keep
             // the fastest (results are cached per layer shape). The heuristic choice above is the
             // fallback and the first candidate.
-            const std::tuple<int, int, int, int, int, int, int> key{n, in_hw, cw.Cin, cw.Cout, cw.k,
-                                                                    cw.stride, res ? 1 : 0};
+            const std::tuple<int, int, int, int, int, int, int, int> key{n, in_hw, cw.Cin, cw.Cout, cw.k,
+                                                                         cw.stride, res ? 1 : 0, sm_budget};
             auto hit = tuned.find(key);
             int best_force = hit != tuned.end() ? hit->second : -1;
             if (best_force < 0) {
@@ -373,7 +386,7 @@ ChunkPlan* Model::plan_for(int n) {
                     if (cw.Cout % (force % 1000) != 0) continue;
                     if (force == 64 && cw.Cout % 128 == 0 && 1LL * n * in_hw * in_hw > 4096) continue;
                     ConvPlan trial;
-                    if (conv_plan_init(&trial, d, num_sms, force, err, sizeof(err))) continue;
+                    if (conv_plan_init(&trial, d, sm_budget, force, err, sizeof(err))) continue;
                     bool ok = true;
                     for (int i = 0; i < 2 && ok; ++i) ok = conv_plan_launch(trial, cap_stream) == cudaSuccess;
                     cudaEventRecord(e0, cap_stream);
@@ -393,7 +406,7 @@ ChunkPlan* Model::plan_for(int n) {
                 tuned[key] = best_force;
             }
             if (best_force > 0) {
-                rc = conv_plan_init(&cp, d, num_sms, best_force, err, sizeof(err));
+                rc = conv_plan_init(&cp, d, sm_budget, best_force, err, sizeof(err));
                 if (rc) {
                     set_error(err);
                     return rc;
@@ -421,11 +434,17 @@ ChunkPlan* Model::plan_for(int n) {
                              bw.bias3ds;
         void* shortcut = x;
         void* ds = nullptr;
+        // Bottleneck block 0 of layers 2-4: the downsample conv is independent of conv1 -> conv2 and (stride 2,
+        // write-heavy) HBM-bound while conv2 is tensor-bound: run it beside them on its own slice of the SMs
+        const bool overlap_ds = side_sms > 0 && bw.has_ds && !fuse_ds && bw.bottleneck && !fuse;
         if (bw.has_ds && !fuse_ds) {
             if (!(ds = arena.acquire(bytes(out_c, out_hw)))) return fail_alloc();
+            sm_budget = overlap_ds ? side_sms : num_sms;
             if (add_conv(bw.ds, x, hw, nullptr, false, ds)) return nullptr;
+            if (overlap_ds) p.convs.back().side = 1;
             shortcut = ds;
         }
+        sm_budget = overlap_ds ? num_sms - side_sms : num_sms;
         void* y = nullptr;
         if (fuse) {
             void* t1 = pre_t1;
@@ -477,6 +496,7 @@ ChunkPlan* Model::plan_for(int n) {
             if (add_conv(bw.conv2, t1, hw, nullptr, true, t2)) return nullptr;
             arena.release(t1);
             if (!(y = arena.acquire(bytes(out_c, out_hw)))) return fail_alloc();
+            sm_budget = num_sms;
             // layer2-shaped blocks (128 -> 512): conv3 + shortcut + ReLU and the NEXT block's conv1 in one launch
             const BlockWeights* nb = bi + 1 < blocks.size() ? &blocks[bi + 1] : nullptr;
             // (layer2 shape 128 -> 512 -> 128: resident weights; layer3 shape 256 -> 1024 -> 256: streamed weights;
@@ -509,6 +529,7 @@ ChunkPlan* Model::plan_for(int n) {
             } else if (add_conv(bw.conv3, t2, out_hw, shortcut, true, y)) {
                 return nullptr;
             }
+            if (overlap_ds) p.convs.back().join = 1;
             arena.release(t2);
         } else {
             void* t1 = arena.acquire(bytes(bw.conv1.Cout, out_hw));
@@ -564,21 +585,45 @@ int Model::enqueue_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, floa
         RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
         RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
     }
+    {
+        int rc = launch_convs(p, s, nullptr);
+        if (rc) return rc;
+    }
+    RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, p.pooled_bf16, n, p.last_hw, p.last_c, esz, s));
+    int r = enqueue_fc(p, logits, s);
+    if (r) return r;
+    if (top1) RNB_CUDA(launch_argmax_f32(logits, top1, n, classes, s));
+    return RNB_OK;
+}
+
+// The planned conv launches of one chunk, in order. A launch marked `side` goes to the side stream (forked
+// from `s` by an event, so it also works under stream capture); the launch marked `join` waits for it.
+// `evs` (profiling): an event is recorded on `s` after every launch.
+int Model::launch_convs(ChunkPlan& p, cudaStream_t s, cudaEvent_t* evs) {
     static const bool sync_each = getenv("RNB_SYNC_EACH") != nullptr;  // bring-up: localise a faulting launch
+    int nfork = 0;
     for (size_t i = 0; i < p.convs.size(); ++i) {
-        RNB_CUDA(conv_plan_launch(p.convs[i], s));
+        const ConvPlan& cp = p.convs[i];
+        if (cp.side) {
+            const int k = nfork++ & 3;
+            RNB_CUDA(cudaEventRecord(fork_ev[k], s));
+            RNB_CUDA(cudaStreamWaitEvent(side_stream, fork_ev[k], 0));
+            RNB_CUDA(conv_plan_launch(cp, side_stream));
+            RNB_CUDA(cudaEventRecord(join_ev[k], side_stream));
+        } else {
+            if (cp.join && nfork > 0) RNB_CUDA(cudaStreamWaitEvent(s, join_ev[(nfork - 1) & 3], 0));
+            RNB_CUDA(conv_plan_launch(cp, s));
+        }
+        if (evs) RNB_CUDA(cudaEventRecord(evs[i], s));
         if (sync_each) {
             cudaError_t e = cudaStreamSynchronize(s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(side_stream);
             if (e != cudaSuccess) {
                 set_error("conv launch #" + std::to_string(i) + " failed: " + cudaGetErrorString(e));
                 return RNB_ERR_CUDA;
             }
         }
     }
-    RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, p.pooled_bf16, n, p.last_hw, p.last_c, esz, s));
-    int r = enqueue_fc(p, logits, s);
-    if (r) return r;
-    if (top1) RNB_CUDA(launch_argmax_f32(logits, top1, n, classes, s));
     return RNB_OK;
 }
 
@@ -724,9 +769,10 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
         else
             RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
         RNB_CUDA(cudaEventRecord(ev[++i], s));
-        for (const ConvPlan& cp : p.convs) {
-            RNB_CUDA(conv_plan_launch(cp, s));
-            RNB_CUDA(cudaEventRecord(ev[++i], s));
+        {
+            int rc = launch_convs(p, s, &ev[i + 1]);
+            if (rc) return rc;
+            i += static_cast<int>(p.convs.size());
         }
         RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, p.pooled_bf16, n, p.last_hw, p.last_c, esz, s));
         RNB_CUDA(cudaEventRecord(ev[++i], s));

@@ -112,9 +112,15 @@ struct Model {
     // Fused layer1 Bottleneck tail (bneck_l1.cuh). RNB_FUSE: 0 = off, 1 = conv2+conv3+residual,
     // 2 (default) = also fold the downsample conv of block 0; RNB_FUSE_NEXT=0 keeps the next block's
     // conv1 as its own launch.
+    // Downsample conv of block 0 (layers 2-4) on a side stream, concurrently with conv1 -> conv2 of the same
+    // block: it gets `side_sms` SMs, the main chain the rest (RNB_SIDE_SMS, 0 = off).
+    int side_sms = 0;
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t fork_ev[4] = {nullptr, nullptr, nullptr, nullptr}, join_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int launch_convs(ChunkPlan& p, cudaStream_t s, cudaEvent_t* per_launch_events);
     int fuse_level = 2;
     bool fuse_next = true;
-    std::map<std::tuple<int, int, int, int, int, int, int>, int> tuned;  // layer shape -> force_bn code
+    std::map<std::tuple<int, int, int, int, int, int, int, int>, int> tuned;  // layer shape (+ SM budget) -> force_bn code
 
     ~Model();
     int load(const std::string& arch, int dtype, const std::string& dir, int max_batch, int chunk);
