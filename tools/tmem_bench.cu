@@ -9,7 +9,7 @@ using namespace rnb::ptx;
 
 // nld warps (4..4+nld-1) each issue `iters` x (tcgen05.ld.32x32b.x32 + wait); warp 1 issues `mma_iters` MMAs
 // (M=128, N=256, K=16, bf16, operands = zeroed smem) back to back.
-__global__ void __launch_bounds__(384, 1) k(int nld, int iters, int mma_iters, long long* out, float* sink) {
+__global__ void __launch_bounds__(384, 1) k(int nld, int iters, int mma_iters, long long* out, float* sink, int fence_mode = 0) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint32_t tptr;
@@ -43,7 +43,15 @@ __global__ void __launch_bounds__(384, 1) k(int nld, int iters, int mma_iters, l
         for (int i = 0; i < iters; ++i) {
             uint32_t v[32];
             tmem_ld_32x32(lb + ((i & 3) * 32) + ((warp - 4) >> 2) * 128, v);   // columns 0..255
+            if (fence_mode == 1) {          // a shared-memory store + proxy fence while the load is in flight
+                reinterpret_cast<uint32_t*>(smem)[12288 + threadIdx.x] = i;
+                fence_proxy_async_smem();
+            }
             tmem_ld_wait();
+            if (fence_mode == 2) {          // the same after the load has completed
+                reinterpret_cast<uint32_t*>(smem)[12288 + threadIdx.x] = i;
+                fence_proxy_async_smem();
+            }
             acc += __uint_as_float(v[i & 31]);
         }
         if (acc == 123.f) sink[0] = acc;
@@ -71,6 +79,16 @@ int main() {
                    nld, mma, cudaGetErrorString(e), nld ? double(h[0]) / iters : 0.0,
                    nld && h[0] ? 4096.0 * nld * iters / double(h[0]) : 0.0, mma ? double(h[1]) / mma : 0.0);
         }
+    }
+    // does fence.proxy.async (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) wait for a tcgen05.ld in flight?
+    for (int fm : {1, 2}) {
+        cudaMemset(out, 0, 16);
+        k<<<148, 384, 60000>>>(1, iters, 0, out, sink, fm);
+        cudaDeviceSynchronize();
+        long long h[2];
+        cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+        printf("1 ld warp, st.shared + fence.proxy.async %s the load: %.1f clk per iteration\n",
+               fm == 1 ? "WHILE IN FLIGHT (before wait::ld of)" : "AFTER wait::ld of", double(h[0]) / iters);
     }
     return 0;
 }
