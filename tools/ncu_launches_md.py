@@ -66,7 +66,7 @@ def main(path, title):
         a[0] += 1
         a[1] += t
         a[2] += rdmb + wrmb
-        if any(s in base for s in ("conv_igemm", "conv3x3_halo", "bneck_l1")):
+        if any(s in base for s in ("conv_igemm", "conv3x3_halo", "bneck_")):
             conv_traffic += (rdmb + wrmb) * 1e6
     print("\n## Per-kernel totals\n")
     print("| kernel | launches | time us | share % | DRAM traffic MB |")
