@@ -346,7 +346,7 @@ def main():
             traffic = None
     roofline = {
         "bound": "tensor",
-        "kernel": "tcgen05 conv launches of one step (conv_igemm / conv_igemm2 / conv3x3_halo / bneck_l1 kernels)",
+        "kernel": "tcgen05 conv launches of one step (conv_igemm / conv_igemm2 / conv3x3_halo / bneck_l1 / bneck_c3n1 kernels)",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
         "peak_source": f"{peak_kind} bf16_tflops_sustained" + (" x 0.5 (tf32 assumed)" if args.dtype == "tf32" else ""),
         "traffic": traffic,
