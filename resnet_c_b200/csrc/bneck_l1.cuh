@@ -54,9 +54,17 @@ struct BneckGeom {
                         // (results wrong); 4 = L2 prefetch of residual tiles (results right)
 };
 
-template <bool DS_>
+// N1_ = output channels of the fused next conv1: 64 (next block of the same layer) or 128 (first block of
+// the NEXT layer, 256 -> 128 at the same resolution). N1 = 128 needs a 128-column D3, paid for with a
+// single-buffered D1 (the epilogue runs one tile ahead, so conv2 still has a whole tile of slack).
+template <bool DS_, int N1_ = 64>
 struct BneckCfg {
     static constexpr bool DS = DS_;  // shortcut = downsample conv of x, fused as a second K block
+    static constexpr int N1 = N1_;
+    static constexpr int NT = N1_ / 64;             // staging boxes of t1' per tile
+    static constexpr int ND1 = N1_ == 64 ? 2 : 1;   // D1 buffers
+    static_assert(N1_ == 64 || N1_ == 128, "next conv1 width");
+    static_assert(!(DS_ && N1_ != 64), "the folded-downsample form is only built with N1 = 64");
     static constexpr int PITCH = 64;
     static constexpr int NABUF = 2;                 // input tiles in flight
     static constexpr int ATILE_BYTES = 32768;       // 4 rows x 64 pixels x 128 B
@@ -66,15 +74,16 @@ struct BneckCfg {
     static constexpr int W3_HALF_BYTES = 64 * 128;  // this CTA's 64 channels of one 128-channel half
     static constexpr int W3_BYTES = 2 * W3_HALF_BYTES;
     static constexpr int WDS_BYTES = DS_ ? W3_BYTES : 0;
-    static constexpr int W1N_KB_BYTES = 32 * 128;   // this CTA's 32 channels x one 64-wide K block
+    static constexpr int W1N_KB_BYTES = (N1_ / 2) * 128;  // this CTA's N1/2 channels x one 64-wide K block
     static constexpr int W1N_BYTES = 4 * W1N_KB_BYTES;
     static constexpr int W_BYTES = W2_BYTES + W3_BYTES + WDS_BYTES + W1N_BYTES;
     static constexpr int RING_BYTES = NABUF * ATILE_BYTES + 1024;  // + read-past pad of the shifted views
     static constexpr int BOX_BYTES = 16384;         // 128 rows x 64 bf16, 128-byte swizzled
     static constexpr int P_BYTES = DS_ ? BOX_BYTES : 0;
-    static constexpr int NPOOL = DS_ ? 3 : 5;       // staging boxes (R mode: also the residual prefetch depth)
+    static constexpr int NPOOL = DS_ ? 3 : (N1_ == 64 ? 5 : 4);  // staging boxes (R mode: also the residual prefetch depth)
     static constexpr int TMEM_COLS = 512;
-    static constexpr int D1_COL = 0, D2_COL = 128, D3_COL = 384, A2_COL = 448;
+    static constexpr int D1_COL = 0, D2_COL = 64 * ND1, D3_COL = D2_COL + 256, A2_COL = D3_COL + N1_;
+    static_assert(A2_COL + 64 <= 512, "TMEM budget");
     static constexpr int NBAR = 1 + 2 * NABUF + 4 + 2 + 4 + 2 + 2 + 4 * NPOOL;
     static constexpr int SMEM_BYTES =
         1024 + W_BYTES + RING_BYTES + P_BYTES + NPOOL * BOX_BYTES + NBAR * 8 + 16;
@@ -83,6 +92,7 @@ struct BneckCfg {
 };
 static_assert(BneckCfg<false>::SMEM_BYTES <= 232448, "smem budget");
 static_assert(BneckCfg<true>::SMEM_BYTES <= 232448, "smem budget");
+static_assert(BneckCfg<false, 128>::SMEM_BYTES <= 232448, "smem budget");
 
 namespace ptx {
 __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
@@ -214,7 +224,7 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int pair = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
     const int T = (g.tiles - pair + num_pairs - 1) / num_pairs;   // tiles of this pair
-    const int IPT = g.has_next ? 5 : 4;                            // staging items per tile
+    const int IPT = g.has_next ? 4 + Cfg::NT : 4;                  // staging items per tile
     const int items = T * IPT;
 
     if (warp == 0 && lane == 0) {
@@ -294,7 +304,8 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             if (g.has_next)
                 for (int kb = 0; kb < 4; ++kb)
-                    tma_load_2d_2sm(smem_w1n + kb * Cfg::W1N_KB_BYTES, &tmW1n, w_full, kb * 64, r32);
+                    tma_load_2d_2sm(smem_w1n + kb * Cfg::W1N_KB_BYTES, &tmW1n, w_full, kb * 64,
+                                    static_cast<int>(rank) * (Cfg::N1 / 2));
         }
         __syncwarp();
         for (int it = 0; it < T; ++it) {
@@ -318,14 +329,14 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(w_full, 0);
             tc_fence_after();
             for (int i = 0; i < T; ++i) {
-                const int buf = i & 1;
-                const uint32_t ph = (i >> 1) & 1;
+                const int buf = i % Cfg::ND1;
+                const uint32_t ph = (i / Cfg::ND1) & 1;
                 mbar_wait(&d1_empty[buf], ph ^ 1);
-                mbar_wait(&a_full[buf], ph);
+                mbar_wait(&a_full[i & 1], (i >> 1) & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + Cfg::D1_COL + buf * 64;
-                    const uint64_t a_tile = ring_desc + static_cast<uint64_t>((buf * Cfg::ATILE_BYTES) >> 4);
+                    const uint64_t a_tile = ring_desc + static_cast<uint64_t>(((i & 1) * Cfg::ATILE_BYTES) >> 4);
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -340,7 +351,7 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                                b_tap + static_cast<uint64_t>(k * 2), idesc64, (r | s | k) != 0);
                         }
                     }
-                    tc_commit_2sm(&a_empty[buf]);
+                    tc_commit_2sm(&a_empty[i & 1]);
                     tc_commit_2sm(&d1_full[buf]);
                 }
                 __syncwarp();
@@ -349,7 +360,7 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else if (warp == 12) {
         // ===================================================== conv3 / conv1' MMA issuer (leader CTA only)
         if (rank == 0) {
-            constexpr uint32_t idesc64 = umma_instr_desc(UMMA_FMT_BF16, 256, 64);
+            constexpr uint32_t idescn1 = umma_instr_desc(UMMA_FMT_BF16, 256, Cfg::N1);
             constexpr uint32_t idesc128 = umma_instr_desc(UMMA_FMT_BF16, 256, 128);
             const uint64_t w3_desc = umma_smem_desc(smem_u32(smem_w3), 0, 1024, UMMA_LAYOUT_SW128);
             const uint64_t wds_desc = umma_smem_desc(smem_u32(smem_wds), 0, 1024, UMMA_LAYOUT_SW128);
@@ -402,7 +413,7 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         mma_f16_ss_2sm(d_tmem, a + static_cast<uint64_t>(k * 2), b + static_cast<uint64_t>(k * 2),
-                                       idesc64, (j | k) != 0);
+                                       idescn1, (j | k) != 0);
                     tc_commit_2sm(&c_mma_done[cs]);
                     if (j == 3) tc_commit_2sm(d3_full);
                 }
@@ -495,8 +506,8 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tma_store_4d(&tmY, box, sub * 64, 0, h0, img);
                     tma_store_4d(&tmY, box + Cfg::PITCH * 128, sub * 64, 0, h0 + 1, img);
                 } else {
-                    tma_store_4d(&tmT1n, box, 0, 0, h0, img);
-                    tma_store_4d(&tmT1n, box + Cfg::PITCH * 128, 0, 0, h0 + 1, img);
+                    tma_store_4d(&tmT1n, box, (sub - 4) * 64, 0, h0, img);
+                    tma_store_4d(&tmT1n, box + Cfg::PITCH * 128, (sub - 4) * 64, 0, h0 + 1, img);
                 }
                 tma_store_commit();
                 if (g.debug & 32)
@@ -531,12 +542,13 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         };
         // D1[i & 1] + bias2 -> ReLU -> BF16 pairs -> A2[i & 1] in TMEM (the A operand of conv3)
         auto E1 = [&](int i) {
-            const int buf = i & 1;
-            mbar_wait(&d1_full[buf], (i >> 1) & 1);
+            const int buf = i & 1;            // A2 buffer
+            const int dbuf = i % Cfg::ND1;    // D1 buffer
+            mbar_wait(&d1_full[dbuf], (i / Cfg::ND1) & 1);
             tc_fence_after();
             uint32_t v[32];
             __syncwarp();
-            tmem_ld_32x32(lane_base + Cfg::D1_COL + buf * 64 + h * 32, v);
+            tmem_ld_32x32(lane_base + Cfg::D1_COL + dbuf * 64 + h * 32, v);
             tmem_ld_wait();
             uint32_t pk[16];
             const float* b32 = prm.bias2 + h * 32;
@@ -555,7 +567,7 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive_leader(&d1_empty[buf]);
+                mbar_arrive_leader(&d1_empty[dbuf]);
                 mbar_arrive_leader(&a2_full[buf]);
             }
         };
@@ -588,24 +600,25 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (lane == 0) mbar_arrive_leader(&d2_empty[hf]);  // this warp has drained half hf
             }
         };
-        // D3 + bias1' -> ReLU -> staging box of item i*IPT + 4
+        // D3 + bias1' -> ReLU -> staging boxes of items i*IPT + 4 .. (NT boxes of 64 channels)
         auto E3 = [&](int i) {
-            const int item = i * IPT + 4;
-            const int cs = item % NPOOL;
-            mbar_wait(&box_ready[cs], (item / NPOOL) & 1);
             mbar_wait(d3_full, i & 1);
             tc_fence_after();
-            uint32_t v[32];
-            __syncwarp();
-            tmem_ld_32x32(lane_base + Cfg::D3_COL + h * 32, v);
-            tmem_ld_wait();
-            epilogue_chunk<2>(v, smem_pool + cs * Cfg::BOX_BYTES + row_off, static_cast<uint32_t>(h * 4), swz,
-                              prm.bias1n + h * 32, 0, 1);
-            publish();
-            if (lane == 0) {
-                mbar_arrive(&c_full[cs]);
-                mbar_arrive_leader(d3_empty);
+#pragma unroll 1
+            for (int jb = 0; jb < Cfg::NT; ++jb) {
+                const int item = i * IPT + 4 + jb;
+                const int cs = item % NPOOL;
+                mbar_wait(&box_ready[cs], (item / NPOOL) & 1);
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld_32x32(lane_base + Cfg::D3_COL + jb * 64 + h * 32, v);
+                tmem_ld_wait();
+                epilogue_chunk<2>(v, smem_pool + cs * Cfg::BOX_BYTES + row_off, static_cast<uint32_t>(h * 4), swz,
+                                  prm.bias1n + jb * 64 + h * 32, 0, 1);
+                publish();
+                if (lane == 0) mbar_arrive(&c_full[cs]);
             }
+            if (lane == 0) mbar_arrive_leader(d3_empty);
         };
 
         if (T > 0) E1(0);

@@ -78,6 +78,9 @@ cudaError_t conv_kernels_init() {
     if ((e = cudaFuncSetAttribute(bneck_c3n1_kernel<C3n1Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C3n1Cfg::SMEM_BYTES)) != cudaSuccess)
         return e;
+    if ((e = cudaFuncSetAttribute(bneck_l1_kernel<BneckCfg<false, 128>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  BneckCfg<false, 128>::SMEM_BYTES)) != cudaSuccess)
+        return e;
     if ((e = cudaFuncSetAttribute(bneck_l1_kernel<BneckCfg<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   BneckCfg<true>::SMEM_BYTES)) != cudaSuccess)
         return e;
@@ -131,7 +134,10 @@ bool bneck_plan_ok(int H, int W, int esz) { return esz == 2 && W >= 8 && W <= 62
 int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, int errlen) {
     memset(plan, 0, sizeof(*plan));
     if (!bneck_plan_ok(d.H, d.W, 2)) return fail(err, errlen, "bneck_plan: geometry not eligible", -7);
-    plan->bneck = d.wds ? 2 : 1;
+    if (d.w1n && d.n1 != 64 && (d.n1 != 128 || d.wds))
+        return fail(err, errlen, "bneck_plan: next conv1 must have 64 (or, without folded downsample, 128) outputs", -7);
+    const int n1 = d.w1n ? d.n1 : 64;
+    plan->bneck = d.wds ? 2 : (n1 == 128 ? 5 : 1);
     plan->bn = 256;
     plan->esz = 2;
     plan->ctas = 2;
@@ -148,9 +154,9 @@ int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, 
     const int pairs = g.tiles < num_sms / 2 ? g.tiles : num_sms / 2;
     plan->grid = 2 * pairs;
     const double M = 1.0 * d.B * d.H * d.W;
-    const double macs = 64.0 * 576 + 256.0 * 64 + (d.wds ? 256.0 * 64 : 0.0) + (d.w1n ? 64.0 * 256 : 0.0);
+    const double macs = 64.0 * 576 + 256.0 * 64 + (d.wds ? 256.0 * 64 : 0.0) + (d.w1n ? 1.0 * n1 * 256 : 0.0);
     plan->flops = 2.0 * M * macs;
-    plan->bytes = 2.0 * M * (64 + (d.wds ? 64 : 256) + 256 + (d.w1n ? 64 : 0)) + 2.0 * macs + 4.0 * (64 + 256 + 64);
+    plan->bytes = 2.0 * M * (64 + (d.wds ? 64 : 256) + 256 + (d.w1n ? n1 : 0)) + 2.0 * macs + 4.0 * (64 + 256 + 64);
     auto act_map = [&](CUtensorMap* tm, const void* base, int C, uint32_t bw, uint32_t bh) {
         const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H),
                                   static_cast<uint64_t>(d.B)};
@@ -174,9 +180,9 @@ int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, 
     plan->tmW1n = plan->tmB;
     plan->tmT1n = plan->tmOut;
     if (d.w1n) {
-        if ((r = make_tiled_2d(&plan->tmW1n, TmDtype::BF16, d.w1n, 64, 256, 32)) != 0)
+        if ((r = make_tiled_2d(&plan->tmW1n, TmDtype::BF16, d.w1n, n1, 256, n1 / 2)) != 0)
             return fail(err, errlen, "bneck_plan: w1n tensor map failed", r);
-        if ((r = act_map(&plan->tmT1n, d.t1n, 64, static_cast<uint32_t>(d.W), 1)) != 0)
+        if ((r = act_map(&plan->tmT1n, d.t1n, n1, static_cast<uint32_t>(d.W), 1)) != 0)
             return fail(err, errlen, "bneck_plan: t1n tensor map failed", r);
     }
     return 0;
@@ -376,6 +382,10 @@ cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
     if (p.bneck == 1)
         return launch_pdl(bneck_l1_kernel<BneckCfg<false>>, p.grid, BneckCfg<false>::THREADS,
                           BneckCfg<false>::SMEM_BYTES, stream, p.tmA, p.tmB, p.tmW3, p.tmWds, p.tmW1n, p.tmRes,
+                          p.tmOut, p.tmT1n, p.bp, p.bg);
+    if (p.bneck == 5)
+        return launch_pdl(bneck_l1_kernel<BneckCfg<false, 128>>, p.grid, BneckCfg<false, 128>::THREADS,
+                          BneckCfg<false, 128>::SMEM_BYTES, stream, p.tmA, p.tmB, p.tmW3, p.tmWds, p.tmW1n, p.tmRes,
                           p.tmOut, p.tmT1n, p.bp, p.bg);
     if (p.bneck == 2)
         return launch_pdl(bneck_l1_kernel<BneckCfg<true>>, p.grid, BneckCfg<true>::THREADS,

@@ -41,7 +41,8 @@ struct BneckDesc {
     const void* wds;         // [256][64] downsample weights, or nullptr
     const void* shortcut;    // wds ? block input NHWC [B][H][W][64] : residual NHWC [B][H][W][256]
     void* y;                 // NHWC [B][H][W][256]
-    const void* w1n;         // next block's conv1 weights [64][256], or nullptr
+    const void* w1n;         // next block's conv1 weights [n1][256], or nullptr
+    int n1 = 64;             // its output channels: 64 (same layer) or 128 (first block of the next layer)
     const float* bias1n;
     void* t1n;               // next block's conv1 output NHWC [B][H][W][64]
 };
@@ -66,7 +67,8 @@ struct ConvPlan {
     CUtensorMap tmW3, tmWds, tmW1n, tmT1n;  // fused Bottleneck tail only
     int bneck;    // 0 = plain conv, 1 = fused tail with residual tensor, 2 = fused tail with folded downsample,
                   // 3 = conv3 + next conv1 (bneck_c3n1.cuh; geometry in cg / cp), resident weights (layer2 shape),
-                  // 4 = the same with streamed weights (layer3 shape)
+                  // 4 = the same with streamed weights (layer3 shape),
+                  // 5 = fused layer1 tail with residual tensor + the NEXT LAYER's conv1 (256 -> 128)
     C3n1Geom cg;
     C3n1Params cp;
     BneckGeom bg;

@@ -454,11 +454,22 @@ ChunkPlan* Model::plan_for(int n) {
                 if (add_conv(bw.conv1, x, hw, nullptr, true, t1)) return nullptr;
             }
             const BlockWeights* nb = bi + 1 < blocks.size() ? &blocks[bi + 1] : nullptr;
-            const bool next = fuse_next && nb && nb->bottleneck && !nb->has_ds && nb->conv1.Cin == 256 &&
-                              nb->conv1.Cout == 64 && nb->conv2.stride == 1 && nb->conv2.Cin == 64 &&
-                              nb->conv2.Cout == 64 && nb->conv3.Cout == 256;
+            bool next = fuse_next && nb && nb->bottleneck && !nb->has_ds && nb->conv1.Cin == 256 &&
+                        nb->conv1.Cout == 64 && nb->conv2.stride == 1 && nb->conv2.Cin == 64 &&
+                        nb->conv2.Cout == 64 && nb->conv3.Cout == 256;
+            int n1 = 64;
+            // last block of the layer: the NEXT LAYER's conv1 (256 -> 128, same resolution; the stride sits on
+            // its conv2) can ride along instead (BneckCfg<false, 128>). Bit-identical, but measured no faster
+            // (the fused launch grows 165 -> 252 us, the separate conv1 it replaces took 101 us: a seventh
+            // epilogue step per tile and one staging box fewer), so it is opt-in: RNB_L1L2=1.
+            const char* l1l2 = getenv("RNB_L1L2");
+            if (!next && l1l2 && atoi(l1l2) != 0 && fuse_next && !fuse_ds && nb && nb->bottleneck && nb->has_ds &&
+                nb->conv1.Cin == 256 && nb->conv1.Cout == 128 && nb->conv1.k == 1 && nb->conv1.stride == 1) {
+                next = true;
+                n1 = 128;
+            }
             void* t1n = nullptr;
-            if (next && !(t1n = arena.acquire(bytes(64, hw)))) return fail_alloc();
+            if (next && !(t1n = arena.acquire(bytes(n1, hw)))) return fail_alloc();
             if (!(y = arena.acquire(bytes(out_c, hw)))) return fail_alloc();
             BneckDesc bd{};
             bd.B = n; bd.H = hw; bd.W = hw;
@@ -470,6 +481,7 @@ ChunkPlan* Model::plan_for(int n) {
             bd.y = y;
             bd.w1n = next ? nb->conv1.w : nullptr;
             bd.bias1n = next ? nb->conv1.bias : nullptr;
+            bd.n1 = n1;
             bd.t1n = t1n;
             ConvPlan cp;
             if (bneck_plan_init(&cp, bd, num_sms, err, sizeof(err))) {
