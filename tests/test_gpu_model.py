@@ -229,6 +229,13 @@ def test_fused_bottleneck_tail_equals_layer_by_layer(monkeypatch, arch, batch):
             e = rel_err(got[2][n].cpu().numpy().reshape(batch, -1), base[2][n].cpu().numpy().reshape(batch, -1))
             assert e < 2e-2, f"{n}: rel err {e:.3e} (fuse=2 next={nxt})"
         assert rel_err(got[0].cpu().numpy(), base[0].cpu().numpy()) < 2e-2
+    # opt-in variant: the last layer1 block also computes the next LAYER's conv1 (BneckCfg<false, 128>)
+    got = _run_with_env(monkeypatch, {"RNB_FUSE": "1", "RNB_FUSE_NEXT": "1", "RNB_L1L2": "1"}, arch, batch, names)
+    assert got[3] == base[3] - 14 if arch == "resnet50" else got[3] < base[3]
+    for n in names:
+        assert torch.equal(got[2][n], base[2][n]), f"{n} differs (RNB_L1L2=1)"
+    assert torch.equal(got[0], base[0]) and torch.equal(got[1], base[1])
+    monkeypatch.delenv("RNB_L1L2")
 
 
 def test_launch_accounting(monkeypatch):
