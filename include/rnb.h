@@ -58,6 +58,15 @@ int rnb_model_create(const char* arch, int dtype, const char* weights_dir, int m
                      rnb_model_t** out);
 int rnb_model_destroy(rnb_model_t* m);
 
+/* Pre-packed weight cache. rnb_model_save_packed() writes everything rnb_model_create() derived from the
+ * save_weights.py directory (BN folded into K-major BF16/TF32 conv weights, stem / FC packs, biases) as ONE
+ * file: 80-byte header (magic "RNBWGT01", arch, dtype, class count, word-wise FNV-1a-64 checksum) + 256-byte-aligned
+ * tensors. rnb_model_create_packed() restores a model from it with one read and one host->device copy
+ * instead of 320-932 small file reads, copies and fold kernels (tensor.cuh:126-152,184-199); a wrong magic,
+ * size or checksum is an error. The packed model computes bit-identical results. */
+int rnb_model_save_packed(rnb_model_t* m, const char* path);
+int rnb_model_create_packed(const char* path, int max_batch, int chunk, rnb_model_t** out);
+
 /* Forward pass on device buffers: x_dev is [batch,3,224,224] float32 NCHW (the layout of the files
  * written by convert_imgs_to_bin.py:20-23), logits_dev is [batch,num_classes] float32,
  * top1_dev is [batch] int32 (lowest index among ties, as main.cu:243-251); either output may be

@@ -105,6 +105,34 @@ int rnb_model_create(const char* arch, int dtype, const char* weights_dir, int m
     return RNB_OK;
 }
 
+int rnb_model_save_packed(rnb_model_t* m, const char* path) {
+    if (!m || !path) {
+        set_error("rnb_model_save_packed: NULL argument");
+        return RNB_ERR_INVALID;
+    }
+    cudaDeviceSynchronize();
+    return m->impl.save_packed(path);
+}
+
+int rnb_model_create_packed(const char* path, int max_batch, int chunk, rnb_model_t** out) {
+    if (!path || !out) {
+        set_error("rnb_model_create_packed: NULL argument");
+        return RNB_ERR_INVALID;
+    }
+    int r = require_init();
+    if (r) return r;
+    rnb_model* m = new rnb_model();
+    r = m->impl.load_packed(path, max_batch, chunk);
+    if (r) {
+        const std::string keep = g_error;
+        delete m;
+        g_error = keep;
+        return r;
+    }
+    *out = m;
+    return RNB_OK;
+}
+
 int rnb_model_destroy(rnb_model_t* m) {
     if (m) {
         cudaDeviceSynchronize();

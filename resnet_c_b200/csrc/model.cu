@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
 
 #include "../../include/rnb.h"
 #include "internal.h"
@@ -149,9 +150,14 @@ Model::~Model() {
         if (hs.done) cudaEventDestroy(hs.done);
     }
     arena.free_all();
-    cudaFree(stem_w); cudaFree(stem_bias); cudaFree(stem_wk); cudaFree(fc_w); cudaFree(fc_b);
-    cudaFree(fc_wq); cudaFree(fc_bq); cudaFree(u8_scratch);
+    cudaFree(u8_scratch);
     cudaFree(host_x_dev); cudaFree(host_logits_dev); cudaFree(host_top1_dev); cudaFree(scratch_logits);
+    if (blob) {  // load_packed(): every weight pointer points into this one allocation
+        cudaFree(blob);
+        return;
+    }
+    cudaFree(stem_w); cudaFree(stem_bias); cudaFree(stem_wk); cudaFree(fc_w); cudaFree(fc_b);
+    cudaFree(fc_wq); cudaFree(fc_bq);
     for (auto& b : blocks) {
         for (ConvWeights* c : {&b.conv1, &b.conv2, &b.conv3, &b.ds}) {
             cudaFree(c->w);
@@ -161,8 +167,7 @@ Model::~Model() {
     }
 }
 
-int Model::load(const std::string& arch_name, int dtype, const std::string& dir, int max_batch_,
-                int chunk_) {
+int Model::configure(const std::string& arch_name, int dtype, int max_batch_, int chunk_) {
     const ArchSpec* spec = nullptr;
     for (const auto& a : kArchs)
         if (arch_name == a.name) spec = &a;
@@ -205,8 +210,18 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
     side_sms &= ~1;  // CTA pairs
     const char* fn = getenv("RNB_FUSE_NEXT");
     fuse_next = !(fn && atoi(fn) == 0);
+    const char* nostc0 = getenv("RNB_NO_STEM_TC");
+    stem_tc = image == 224 && !(nostc0 && atoi(nostc0) != 0);
+    return RNB_OK;
+}
 
-    int r;
+int Model::load(const std::string& arch_name, int dtype, const std::string& dir, int max_batch_,
+                int chunk_) {
+    int r = configure(arch_name, dtype, max_batch_, chunk_);
+    if (r) return r;
+    const ArchSpec* spec = nullptr;
+    for (const auto& a : kArchs)
+        if (arch_name == a.name) spec = &a;
     // ---- stem: conv1 + bn1 (main.cu:110-111), folded in fp32 OIHW for the CUDA-core stem
     {
         std::vector<float> h;
@@ -218,8 +233,6 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
         RNB_CUDA(cudaMalloc(&stem_w, 64 * 147 * sizeof(float)));
         RNB_CUDA(cudaMalloc(&stem_bias, 64 * sizeof(float)));
         RNB_CUDA(launch_fold_f32(raw, bn.w, bn.b, bn.m, bn.v, stem_w, stem_bias, 64, 147, 0));
-        const char* nostc = getenv("RNB_NO_STEM_TC");
-        stem_tc = image == 224 && !(nostc && atoi(nostc) != 0);
         if (stem_tc) {
             RNB_CUDA(cudaMalloc(&stem_wk, stem_any_weight_bytes(esz)));
             RNB_CUDA(launch_stem_any_pack_weights(esz, raw, bn.w, bn.b, bn.m, bn.v, stem_wk, stem_bias, 0));
@@ -308,6 +321,222 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
         }
     }
     flops_per_image = 2.0 * macs;
+    RNB_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+    RNB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    RNB_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) {
+        RNB_CUDA(cudaEventCreateWithFlags(&fork_ev[i], cudaEventDisableTiming));
+        RNB_CUDA(cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming));
+    }
+    set_error("");
+    return RNB_OK;
+}
+
+// ------------------------------------------------------------------------------------ packed weight blob
+// blocks[] with shapes only, exactly as load() lays them out (createLayer, main.cu:53-89)
+void Model::build_structure() {
+    const ArchSpec* spec = nullptr;
+    for (const auto& a : kArchs)
+        if (arch == a.name) spec = &a;
+    blocks.clear();
+    double macs = 64.0 * 147 * 112 * 112;
+    int in_c = 64, hw = 56;
+    num_convs = 1;
+    auto shape = [](ConvWeights& c, int Cin, int Cout, int k, int stride, int pad) {
+        c.Cin = Cin; c.Cout = Cout; c.k = k; c.stride = stride; c.pad = pad;
+    };
+    for (int L = 0; L < 4; ++L) {
+        const int mid = 64 << L;
+        const int out_c = bottleneck ? mid * 4 : mid;
+        for (int i = 0; i < spec->blocks[L]; ++i) {
+            BlockWeights bw;
+            bw.bottleneck = bottleneck;
+            bw.name = "layer" + std::to_string(L + 1) + "." + std::to_string(i);
+            const int stride = i == 0 ? (L == 0 ? 1 : 2) : 1;
+            const int out_hw = hw / stride;
+            if (bottleneck) {
+                shape(bw.conv1, in_c, mid, 1, 1, 0);
+                shape(bw.conv2, mid, mid, 3, stride, 1);
+                shape(bw.conv3, mid, out_c, 1, 1, 0);
+                macs += 1.0 * hw * hw * in_c * mid + 1.0 * out_hw * out_hw * mid * mid * 9 + 1.0 * out_hw * out_hw * mid * out_c;
+                num_convs += 3;
+            } else {
+                shape(bw.conv1, in_c, mid, 3, stride, 1);
+                shape(bw.conv2, mid, mid, 3, 1, 1);
+                macs += 1.0 * out_hw * out_hw * in_c * mid * 9 + 1.0 * out_hw * out_hw * mid * mid * 9;
+                num_convs += 2;
+            }
+            if (i == 0 && (stride != 1 || in_c != out_c)) {
+                bw.has_ds = true;
+                shape(bw.ds, in_c, out_c, 1, stride, 0);
+                macs += 1.0 * out_hw * out_hw * in_c * out_c;
+                num_convs += 1;
+            }
+            blocks.push_back(bw);
+            in_c = out_c;
+            hw = out_hw;
+        }
+    }
+    final_c = in_c;
+    macs += 1.0 * classes * final_c;
+    flops_per_image = 2.0 * macs;
+}
+
+template <class F>
+void Model::for_each_weight(F&& f) {
+    f(reinterpret_cast<void**>(&stem_w), 64ull * 147 * sizeof(float));
+    f(reinterpret_cast<void**>(&stem_bias), 64ull * sizeof(float));
+    if (stem_tc) f(&stem_wk, stem_any_weight_bytes(esz));
+    for (auto& b : blocks) {
+        for (ConvWeights* c : {&b.conv1, &b.conv2, &b.conv3, &b.ds}) {
+            if (c->Cout == 0) continue;  // conv3 of a BasicBlock, ds of a block without downsample
+            f(&c->w, 1ull * c->Cout * c->Cin * c->k * c->k * esz);
+            f(reinterpret_cast<void**>(&c->bias), 1ull * c->Cout * sizeof(float));
+        }
+        if (b.has_ds && b.bottleneck) f(reinterpret_cast<void**>(&b.bias3ds), 1ull * b.conv3.Cout * sizeof(float));
+    }
+    f(reinterpret_cast<void**>(&fc_w), 1ull * classes * final_c * sizeof(float));
+    f(reinterpret_cast<void**>(&fc_b), 1ull * classes * sizeof(float));
+    if (fc_tc) {
+        f(&fc_wq, 1ull * classes_pad * final_c * 2);
+        f(reinterpret_cast<void**>(&fc_bq), 1ull * classes_pad * sizeof(float));
+    }
+}
+
+namespace {
+struct PackedHeader {
+    char magic[8];        // "RNBWGT01"
+    uint32_t version;     // 1
+    uint32_t esz;         // 2 = BF16 operands, 4 = TF32
+    char arch[16];
+    uint32_t classes, classes_pad;
+    uint32_t stem_tc, fc_tc;
+    uint32_t num_tensors;
+    uint32_t reserved;
+    uint64_t payload_bytes;
+    uint64_t checksum;    // FNV-1a over the payload taken as 64-bit words, four interleaved lanes
+};
+// The payload is a multiple of 256 bytes. Word-wise FNV-1a in four independent lanes (word i goes to lane
+// i & 3), lanes folded at the end: ~10 GB/s on one core instead of ~1 GB/s byte by byte — the checksum must not
+// cost more than the read it protects.
+uint64_t fnv1a(const uint8_t* p, size_t n) {
+    const uint64_t prime = 1099511628211ull;
+    uint64_t h[4] = {1469598103934665603ull, 1469598103934665603ull ^ 1, 1469598103934665603ull ^ 2,
+                     1469598103934665603ull ^ 3};
+    const size_t words = n / 8;
+    size_t i = 0;
+    for (; i + 4 <= words; i += 4) {
+        uint64_t w[4];
+        memcpy(w, p + 8 * i, 32);
+        h[0] = (h[0] ^ w[0]) * prime;
+        h[1] = (h[1] ^ w[1]) * prime;
+        h[2] = (h[2] ^ w[2]) * prime;
+        h[3] = (h[3] ^ w[3]) * prime;
+    }
+    uint64_t r = 1469598103934665603ull;
+    for (int k = 0; k < 4; ++k) r = (r ^ h[k]) * prime;
+    for (size_t b = 8 * i; b < n; ++b) r = (r ^ p[b]) * prime;
+    return r;
+}
+constexpr size_t kAlign = 256;
+size_t aligned(size_t b) { return (b + kAlign - 1) / kAlign * kAlign; }
+}  // namespace
+
+int Model::save_packed(const std::string& path) {
+    size_t total = 0;
+    uint32_t count = 0;
+    for_each_weight([&](void**, size_t bytes) { total += aligned(bytes); ++count; });
+    std::vector<uint8_t> host(total, 0);
+    size_t off = 0;
+    cudaError_t ce = cudaSuccess;
+    for_each_weight([&](void** p, size_t bytes) {
+        if (ce == cudaSuccess) ce = cudaMemcpy(host.data() + off, *p, bytes, cudaMemcpyDeviceToHost);
+        off += aligned(bytes);
+    });
+    if (ce != cudaSuccess) return fail_cuda(ce, "save_packed: cudaMemcpy");
+    PackedHeader h{};
+    memcpy(h.magic, "RNBWGT01", 8);
+    h.version = 1;
+    h.esz = static_cast<uint32_t>(esz);
+    snprintf(h.arch, sizeof(h.arch), "%s", arch.c_str());
+    h.classes = classes; h.classes_pad = classes_pad;
+    h.stem_tc = stem_tc ? 1 : 0; h.fc_tc = fc_tc ? 1 : 0;
+    h.num_tensors = count;
+    h.payload_bytes = total;
+    h.checksum = fnv1a(host.data(), total);
+    std::ofstream f(path, std::ios::binary | std::ios::trunc);
+    if (!f.is_open()) {
+        set_error("save_packed: cannot open " + path);
+        return RNB_ERR_IO;
+    }
+    f.write(reinterpret_cast<const char*>(&h), sizeof(h));
+    f.write(reinterpret_cast<const char*>(host.data()), static_cast<std::streamsize>(total));
+    if (f.fail()) {
+        set_error("save_packed: short write on " + path);
+        return RNB_ERR_IO;
+    }
+    return RNB_OK;
+}
+
+int Model::load_packed(const std::string& path, int max_batch_, int chunk_) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f.is_open()) {
+        set_error("cannot open packed weight file " + path);
+        return RNB_ERR_IO;
+    }
+    const std::streamsize fsize = f.tellg();
+    PackedHeader h{};
+    if (fsize < static_cast<std::streamsize>(sizeof(h))) {
+        set_error("packed weight file " + path + " is truncated");
+        return RNB_ERR_IO;
+    }
+    f.seekg(0);
+    f.read(reinterpret_cast<char*>(&h), sizeof(h));
+    if (memcmp(h.magic, "RNBWGT01", 8) != 0 || h.version != 1 || (h.esz != 2 && h.esz != 4)) {
+        set_error("packed weight file " + path + ": bad magic / version");
+        return RNB_ERR_IO;
+    }
+    if (fsize != static_cast<std::streamsize>(sizeof(h) + h.payload_bytes)) {
+        set_error("packed weight file " + path + ": size does not match its header");
+        return RNB_ERR_IO;
+    }
+    h.arch[sizeof(h.arch) - 1] = 0;
+    int r = configure(h.arch, h.esz == 2 ? RNB_DTYPE_BF16 : RNB_DTYPE_TF32, max_batch_, chunk_);
+    if (r) return r;
+    if (static_cast<uint32_t>(stem_tc ? 1 : 0) != h.stem_tc) {
+        set_error("packed weight file was written with a different RNB_NO_STEM_TC setting");
+        return RNB_ERR_INVALID;
+    }
+    classes = static_cast<int>(h.classes);
+    classes_pad = static_cast<int>(h.classes_pad);
+    fc_tc = h.fc_tc != 0;
+    build_structure();
+    size_t total = 0;
+    uint32_t count = 0;
+    for_each_weight([&](void**, size_t bytes) { total += aligned(bytes); ++count; });
+    if (total != h.payload_bytes || count != h.num_tensors) {
+        set_error("packed weight file " + path + ": tensor table does not match architecture " + arch);
+        return RNB_ERR_IO;
+    }
+    std::unique_ptr<uint8_t[]> host(new uint8_t[total]);  // (uninitialised on purpose)
+    f.read(reinterpret_cast<char*>(host.get()), static_cast<std::streamsize>(total));
+    if (f.fail()) {
+        set_error("short read on " + path);
+        return RNB_ERR_IO;
+    }
+    RNB_CUDA(cudaMalloc(&blob, total));
+    RNB_CUDA(cudaMemcpyAsync(blob, host.get(), total, cudaMemcpyHostToDevice, 0));  // overlaps the checksum
+    const bool sum_ok = fnv1a(host.get(), total) == h.checksum;
+    RNB_CUDA(cudaStreamSynchronize(0));
+    if (!sum_ok) {
+        set_error("packed weight file " + path + ": checksum mismatch (corrupt file)");
+        return RNB_ERR_IO;
+    }
+    size_t off = 0;
+    for_each_weight([&](void** p, size_t bytes) {
+        *p = static_cast<uint8_t*>(blob) + off;
+        off += aligned(bytes);
+    });
     RNB_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
     RNB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     RNB_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));

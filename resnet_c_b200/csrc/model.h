@@ -124,6 +124,15 @@ struct Model {
 
     ~Model();
     int load(const std::string& arch, int dtype, const std::string& dir, int max_batch, int chunk);
+    // Pre-packed weight blob: everything load() derives from the 320-932 raw files of a
+    // save_weights.py directory (BN-folded, K-major BF16/TF32 conv weights, stem / FC packs, biases) in ONE file
+    // with a header and an FNV-1a checksum; load_packed() restores it with one read and one cudaMemcpy.
+    int save_packed(const std::string& path);
+    int load_packed(const std::string& path, int max_batch, int chunk);
+    int configure(const std::string& arch_name, int dtype, int max_batch_, int chunk_);  // shared front half of both loads
+    void build_structure();                      // blocks[] with shapes only (no device memory), flops, conv count
+    template <class F> void for_each_weight(F&& f);  // every device weight buffer, deterministic order
+    void* blob = nullptr;                        // load_packed(): the one device allocation all weights point into
     ChunkPlan* plan_for(int n);
     // x_u8 != nullptr: decoded uint8 HWC input (x is then ignored), normalised with norm_mean / norm_std
     int enqueue_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1, cudaStream_t s);

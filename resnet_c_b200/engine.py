@@ -187,6 +187,22 @@ class ResNet:
         self.num_classes = _lib.lib().rnb_model_num_classes(self._h)
         self.flops_per_image = _lib.lib().rnb_model_flops_per_image(self._h)
 
+    @classmethod
+    def from_packed(cls, path, max_batch: int = 256, chunk: int = 0, device: int = 0):
+        """Model from a pre-packed weight blob written by save_packed() (one read + one H2D copy)."""
+        _lib.init(device)
+        self = cls.__new__(cls)
+        self.arch, self.dtype, self.max_batch, self.device = "packed", "packed", max_batch, device
+        handle = C.c_void_p()
+        check(_lib.lib().rnb_model_create_packed(str(path).encode(), max_batch, chunk, C.byref(handle)))
+        self._h = handle
+        self.num_classes = _lib.lib().rnb_model_num_classes(self._h)
+        self.flops_per_image = _lib.lib().rnb_model_flops_per_image(self._h)
+        return self
+
+    def save_packed(self, path) -> None:
+        check(_lib.lib().rnb_model_save_packed(self._h, str(path).encode()))
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().rnb_model_destroy(self._h)

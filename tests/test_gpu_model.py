@@ -195,6 +195,41 @@ def test_uint8_reference_image_top1(golden_dir):
         model.close()
 
 
+@pytest.mark.parametrize("arch,dtype", [("resnet50", "bf16"), ("resnet18", "tf32")])
+def test_packed_weight_blob_round_trip(arch, dtype, tmp_path):
+    """rnb_model_save_packed -> rnb_model_create_packed: bit-identical logits, flops and class count; a corrupt
+    byte, a truncated file and a wrong magic are refused."""
+    from resnet_c_b200 import engine, weights
+    from resnet_c_b200._lib import RnbError
+    B = 4
+    x = weights.synthetic_images(B).cuda()
+    model = _model(arch, True, dtype, B)
+    want, want_top1 = model.forward(x)
+    torch.cuda.synchronize()
+    blob = tmp_path / f"{arch}_{dtype}.rnbw"
+    model.save_packed(blob)
+    packed = engine.ResNet.from_packed(blob, max_batch=B)
+    assert packed.num_classes == model.num_classes and packed.flops_per_image == model.flops_per_image
+    got, got_top1 = packed.forward(x)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want) and torch.equal(got_top1, want_top1)
+    packed.close()
+    model.close()
+    raw = bytearray(blob.read_bytes())
+    bad = tmp_path / "bad.rnbw"
+    corrupt = bytearray(raw)
+    corrupt[len(corrupt) // 2] ^= 0x40
+    bad.write_bytes(corrupt)
+    with pytest.raises(RnbError, match="checksum"):
+        engine.ResNet.from_packed(bad, max_batch=B)
+    bad.write_bytes(raw[:len(raw) - 1000])
+    with pytest.raises(RnbError, match="size"):
+        engine.ResNet.from_packed(bad, max_batch=B)
+    bad.write_bytes(b"NOTRNBWT" + bytes(raw[8:]))
+    with pytest.raises(RnbError, match="magic"):
+        engine.ResNet.from_packed(bad, max_batch=B)
+
+
 def _run_with_env(monkeypatch, env, arch, batch, names):
     from resnet_c_b200 import weights
     for k, v in env.items():
