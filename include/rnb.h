@@ -174,6 +174,17 @@ int rnb_linear_forward(const float* x_dev, float* out_dev, const float* w_dev, c
 /* Row-wise arg-max, lowest index on ties (main.cu:243-251). */
 int rnb_argmax_forward(const float* x_dev, int32_t* out_dev, int B, int n, void* stream);
 
+/* The step after the path (main.cu:240-251 and beyond): row softmax of the logits and the k most probable
+ * classes (value descending, lowest index first on ties), 1 <= k <= min(n, 32). probs_full_dev [B][n] may be
+ * NULL; top_probs_dev [B][k], top_idx_dev [B][k]. */
+int rnb_softmax_topk_forward(const float* logits_dev, float* probs_full_dev, float* top_probs_dev,
+                             int32_t* top_idx_dev, int B, int n, int k, void* stream);
+
+/* Result writer: numel FP32 values from device memory to a raw little-endian file — the format of
+ * Tensor::save (tensor.cuh:154-163) and of the cuda_out.bin / torch_out.bin pair that the reference's check_out()
+ * (pytorch_inference.py:8-11) compares. Synchronises the device. */
+int rnb_save_f32(const float* dev, int64_t numel, const char* path);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,8 @@ PROTOTYPES = {
     "rnb_avgpool2d_forward": (C.c_int, [_vp, _vp] + [C.c_int] * 7 + [_vp]),
     "rnb_linear_forward": (C.c_int, [_vp] * 4 + [C.c_int] * 3 + [_vp]),
     "rnb_argmax_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
+    "rnb_softmax_topk_forward": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "rnb_save_f32": (C.c_int, [_vp, C.c_int64, C.c_char_p]),
 }
 
 

@@ -1,6 +1,7 @@
 // api.cu — the extern "C" surface declared in include/rnb.h.
 #include <algorithm>
 #include <cstdio>
+#include <vector>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -503,6 +504,43 @@ int rnb_argmax_forward(const float* x_dev, int32_t* out_dev, int B, int n, void*
         return RNB_ERR_INVALID;
     }
     API_CUDA(launch_argmax_f32(x_dev, out_dev, B, n, static_cast<cudaStream_t>(stream)));
+    return RNB_OK;
+}
+
+int rnb_softmax_topk_forward(const float* logits_dev, float* probs_full_dev, float* top_probs_dev,
+                             int32_t* top_idx_dev, int B, int n, int k, void* stream) {
+    int r = require_init();
+    if (r) return r;
+    if (!logits_dev || !top_probs_dev || !top_idx_dev || B <= 0 || n <= 0 || k <= 0 || k > n || k > 32) {
+        set_error("rnb_softmax_topk_forward: bad argument (1 <= k <= min(n, 32))");
+        return RNB_ERR_INVALID;
+    }
+    API_CUDA(launch_softmax_topk_f32(logits_dev, probs_full_dev, top_probs_dev, top_idx_dev, B, n, k,
+                                     static_cast<cudaStream_t>(stream)));
+    return RNB_OK;
+}
+
+int rnb_save_f32(const float* dev, int64_t numel, const char* path) {
+    int r = require_init();
+    if (r) return r;
+    if (!dev || numel <= 0 || !path) {
+        set_error("rnb_save_f32: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    std::vector<float> host(static_cast<size_t>(numel));
+    API_CUDA(cudaDeviceSynchronize());
+    API_CUDA(cudaMemcpy(host.data(), dev, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+        set_error(std::string("rnb_save_f32: cannot open ") + path);
+        return RNB_ERR_IO;
+    }
+    const size_t wrote = fwrite(host.data(), sizeof(float), host.size(), f);
+    fclose(f);
+    if (wrote != host.size()) {
+        set_error(std::string("rnb_save_f32: short write on ") + path);
+        return RNB_ERR_IO;
+    }
     return RNB_OK;
 }
 

@@ -24,6 +24,9 @@ cudaError_t launch_pool2d_f32(bool is_max, const float* x, float* out, int B, in
 cudaError_t launch_linear_f32(const float* x, float* out, const float* w, const float* bias, int B,
                               int in_f, int out_f, cudaStream_t s);
 cudaError_t launch_argmax_f32(const float* x, int32_t* out, int B, int n, cudaStream_t s);
+// row softmax (optional full output) + top-k probabilities / indices (value desc, index asc)
+cudaError_t launch_softmax_topk_f32(const float* x, float* probs_full, float* top_p, int32_t* top_i, int B, int n,
+                                    int k, cudaStream_t s);
 
 // ---- layout / weight preparation (layout.cu). `esz` = 2 (bf16) or 4 (tf32-rounded fp32).
 cudaError_t launch_nchw_to_nhwc(const float* x, void* out, int B, int C, int HW, int esz,

@@ -168,7 +168,65 @@ __global__ void argmax_f32_kernel(const float* __restrict__ x, int32_t* __restri
     if (lane == 0) out[warp] = best_i == 0x7fffffff ? 0 : best_i;
 }
 
+// Row softmax + top-k (the step after the hot path: what a caller does with fc_out, main.cu:240-251, beyond the
+// single arg-max). One warp per row: max, sum of exp(x - max) (expf, not the fast intrinsic), then k rounds of
+// arg-max over the not-yet-taken entries (lowest index wins ties, like argmax_f32_kernel). probs_full (optional)
+// receives the whole softmax row.
+constexpr int kMaxTopK = 32;
+__global__ void softmax_topk_kernel(const float* __restrict__ x, float* __restrict__ probs_full,
+                                    float* __restrict__ top_p, int32_t* __restrict__ top_i, int B, int n, int k) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const float* row = x + 1LL * warp * n;
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) mx = fmaxf(mx, row[j]);
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) sum += expf(row[j] - mx);
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (probs_full)
+        for (int j = lane; j < n; j += 32) probs_full[1LL * warp * n + j] = expf(row[j] - mx) / sum;
+    float last_v = INFINITY;
+    int last_i = -1;
+    for (int t = 0; t < k; ++t) {
+        // next entry in (value desc, index asc) order strictly after (last_v, last_i)
+        float best = -INFINITY;
+        int best_i = 0x7fffffff;
+        for (int j = lane; j < n; j += 32) {
+            const float v = row[j];
+            const bool after = v < last_v || (v == last_v && j > last_i);
+            if (after && (v > best || (v == best && j < best_i) || best_i == 0x7fffffff)) {
+                best = v;
+                best_i = j;
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+            if (oi != 0x7fffffff && (best_i == 0x7fffffff || ov > best || (ov == best && oi < best_i))) {
+                best = ov;
+                best_i = oi;
+            }
+        }
+        if (lane == 0) {
+            top_i[1LL * warp * k + t] = best_i == 0x7fffffff ? -1 : best_i;
+            top_p[1LL * warp * k + t] = best_i == 0x7fffffff ? 0.f : expf(best - mx) / sum;
+        }
+        last_v = best;
+        last_i = best_i;
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_softmax_topk_f32(const float* x, float* probs_full, float* top_p, int32_t* top_i, int B, int n,
+                                    int k, cudaStream_t s) {
+    const int warps_per_block = kThreads / 32;
+    softmax_topk_kernel<<<(B + warps_per_block - 1) / warps_per_block, kThreads, 0, s>>>(x, probs_full, top_p, top_i,
+                                                                                       B, n, k);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_conv2d_f32(const float* x, float* out, const float* w, int B, int Cin, int H,
                               int W, int Cout, int k, int stride, int pad, cudaStream_t s) {

@@ -124,6 +124,27 @@ def argmax_forward(x):
     return out
 
 
+def softmax_topk_forward(logits, k=5, full=False):
+    """Row softmax + top-k of the logits (the caller's next step after main.cu:240-251).
+    Returns (top_probs [B,k], top_idx [B,k] int32[, probs [B,n])."""
+    logits = _f32_cuda(logits, "logits")
+    B, n = logits.shape
+    top_p = torch.empty(B, k, device=logits.device, dtype=torch.float32)
+    top_i = torch.empty(B, k, device=logits.device, dtype=torch.int32)
+    probs = torch.empty(B, n, device=logits.device, dtype=torch.float32) if full else None
+    _lib.init(logits.device.index or 0)
+    check(_lib.lib().rnb_softmax_topk_forward(_ptr(logits), _ptr(probs), _ptr(top_p), _ptr(top_i), B, n, k,
+                                              _stream()))
+    return (top_p, top_i, probs) if full else (top_p, top_i)
+
+
+def save_f32(t, path):
+    """Raw FP32 dump of a CUDA tensor (Tensor::save format, tensor.cuh:154-163)."""
+    t = _f32_cuda(t, "tensor")
+    _lib.init(t.device.index or 0)
+    check(_lib.lib().rnb_save_f32(_ptr(t), t.numel(), str(path).encode()))
+
+
 # --------------------------------------------------------------------------- fused tensor-core ops
 def conv_bn_act_forward(x, weight, bn=None, residual=None, relu=True, stride=1, padding=0,
                         dtype="bf16"):

@@ -83,6 +83,26 @@ def test_argmax_tie_rule(eng, oracle_lib):
     assert int(eng.argmax_forward(x.cuda())[3]) == 10
 
 
+def test_softmax_topk_matches_oracle(eng, tmp_path):
+    """rnb_softmax_topk_forward against oracle/postprocess.py (float64): probabilities to 1e-6, indices exact
+    (value descending, lowest index first on ties); rnb_save_f32 writes Tensor::save's raw format."""
+    from oracle import postprocess
+    x = _rand(37, 1000, seed=21) * 3.0
+    x[4, 17] = x[4, 903] = x[4].max() + 1.0      # a tie for first place
+    x[9, :] = 0.25                                # all equal: indices 0..k-1
+    for k in (1, 5, 32):
+        top_p, top_i, probs = eng.softmax_topk_forward(x.cuda(), k=k, full=True)
+        ref_p, ref_i, ref_full = postprocess.softmax_topk(x.numpy(), k)
+        np.testing.assert_array_equal(top_i.cpu().numpy(), ref_i)
+        np.testing.assert_allclose(top_p.cpu().numpy(), ref_p, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(probs.cpu().numpy(), ref_full, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(probs.cpu().numpy().sum(1), 1.0, atol=1e-5)
+    assert top_i[4, :2].cpu().tolist() == [17, 903] and top_i[9, :4].cpu().tolist() == [0, 1, 2, 3]
+    out = tmp_path / "cuda_out.bin"
+    eng.save_f32(x.cuda(), out)
+    np.testing.assert_array_equal(postprocess.load_f32(out), x.numpy().reshape(-1))
+
+
 def test_tail_matches_oracle(eng, oracle_lib):
     x, w, b = _rand(5, 512, 7, 7, seed=15), _rand(1000, 512, seed=16) * 0.05, _rand(1000, seed=17)
     logits, top1 = eng.tail_forward(x.cuda(), w.cuda(), b.cuda())

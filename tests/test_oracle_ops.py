@@ -84,3 +84,19 @@ def test_linear(oracle_lib):
 def test_argmax_first_maximum_wins(oracle_lib):
     x = np.array([[1, 5, 5, 2], [7, 7, 7, 7], [-3, -1, -2, -1], [0, 0, 1, 0]], np.float32)
     np.testing.assert_array_equal(oracle_lib.argmax_rows(x), [1, 0, 1, 2])
+
+
+def test_softmax_topk_oracle_pinned_against_torch():
+    """oracle/postprocess.py::softmax_topk == torch.softmax / torch.topk (float64) incl. the tie rule."""
+    import torch
+    from oracle import postprocess
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(16, 1000, generator=g, dtype=torch.float64) * 4
+    p, i, full = postprocess.softmax_topk(x.numpy(), 5)
+    tp = torch.softmax(x, dim=1)
+    np.testing.assert_allclose(full, tp.numpy(), rtol=1e-12, atol=1e-15)
+    tv, ti = torch.topk(tp, 5, dim=1)
+    np.testing.assert_array_equal(i, ti.numpy())
+    np.testing.assert_allclose(p, tv.numpy(), rtol=1e-12)
+    y = np.zeros((1, 8)); y[0, 2] = y[0, 6] = 1.0
+    assert postprocess.softmax_topk(y, 3)[1].tolist() == [[2, 6, 0]]
