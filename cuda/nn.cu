@@ -227,6 +227,30 @@ ResNet::ResNet(const std::string& arch, Precision precision, const std::string& 
              "rnb_model_create");
 }
 
+ResNet::ResNet(Packed, const std::string& path, uint64_t max_batch) : max_batch_(max_batch)
+{
+    ensureInit();
+    rnbCheck(rnb_model_create_packed(path.c_str(), asInt(max_batch), 0, &handle_), "rnb_model_create_packed");
+}
+
+void ResNet::savePacked(const std::string& path)
+{
+    rnbCheck(rnb_model_save_packed(handle_, path.c_str()), "rnb_model_save_packed");
+}
+
+std::vector<int32_t> ResNet::predictU8(const uint8_t* x_u8_dev, uint64_t B, FloatTensor& logits)
+{
+    assert(logits.device == Device::GPU && logits.shape() == Shape({B, numClasses()}));
+    int32_t* top1_dev = static_cast<int32_t*>(safeCudaMalloc(B * sizeof(int32_t)));
+    rnbCheck(rnb_model_forward_u8(handle_, x_u8_dev, asInt(B), logits.data(), top1_dev, nullptr),
+             "rnb_model_forward_u8");
+    syncAndCheck();
+    std::vector<int32_t> top1(B);
+    gpuErrchk(cudaMemcpy(top1.data(), top1_dev, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    gpuErrchk(cudaFree(top1_dev));
+    return top1;
+}
+
 ResNet::~ResNet()
 {
     rnb_model_destroy(handle_);

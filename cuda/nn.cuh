@@ -271,6 +271,14 @@ public:
     void forward(FloatTensor& x, FloatTensor& logits);
     // Same, and also returns the per-image arg-max (first maximum wins) on the host.
     std::vector<int32_t> predict(FloatTensor& x, FloatTensor& logits);
+    // Decoded images: x_u8_dev is uint8 HWC [B,224,224,3] on the GPU; the /255 + mean/std normalisation of
+    // convert_imgs_to_bin.py:18 runs inside the stem pre-pass (bit-identical to predict() on the float tensor).
+    std::vector<int32_t> predictU8(const uint8_t* x_u8_dev, uint64_t B, FloatTensor& logits);
+
+    // Pre-packed weight blob: one checksummed file instead of one raw file per state_dict key.
+    void savePacked(const std::string& path);
+    struct Packed {};  // tag
+    ResNet(Packed, const std::string& path, uint64_t max_batch = 1);
 
 private:
     struct rnb_model* handle_ = nullptr;
