@@ -72,6 +72,9 @@ cudaError_t conv_kernels_init() {
     if ((e = cudaFuncSetAttribute(bneck_l1_kernel<BneckCfg<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   BneckCfg<false>::SMEM_BYTES)) != cudaSuccess)
         return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_halo2_kernel<Halo2Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Halo2Cfg::SMEM_BYTES)) != cudaSuccess)
+        return e;
     if ((e = cudaFuncSetAttribute(bneck_c3n1s_kernel<C3n1sL3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C3n1sL3::SMEM_BYTES)) != cudaSuccess)
         return e;
@@ -126,6 +129,47 @@ static int halo_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, char* 
     if ((r = make_tiled_nd(&plan->tmOut, TmDtype::BF16, d.out, 4, dims, strides, box_out, true)) != 0)
         return fail(err, errlen, "conv_plan: halo output tensor map failed", r);
     plan->tmRes = plan->tmOut;
+    return 0;
+}
+
+bool conv_plan_halo2_ok(const ConvDesc& d) {
+    return d.act == ActType::TF32 && d.ksize == 3 && d.stride == 1 && d.pad == 1 && d.Cin == 64 && d.Cout == 64 &&
+           d.W <= 62 && d.W >= 8 && d.H >= 4 && d.H % 4 == 0 && !d.out_f32;
+}
+
+static int halo2_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, char* err, int errlen) {
+    if (!conv_plan_halo2_ok(d)) return fail(err, errlen, "conv_plan: layer is not eligible for the TF32 halo kernel", -7);
+    plan->halo2 = 1;
+    plan->bn = 64;
+    plan->esz = 4;
+    plan->ctas = 2;
+    plan->bias = d.bias;
+    Halo2Geom& g = plan->h2g;
+    g.N = d.B; g.H = d.H; g.W = d.W;
+    g.tiles_per_img = d.H / 4;
+    g.tiles = d.B * g.tiles_per_img;
+    g.relu = d.relu ? 1 : 0;
+    g.has_res = d.residual ? 1 : 0;
+    g.reverse = d.reverse ? 1 : 0;
+    const int pairs = g.tiles < num_sms / 2 ? g.tiles : num_sms / 2;
+    plan->grid = 2 * pairs;
+    const double M = 1.0 * d.B * d.H * d.W;
+    plan->flops = 2.0 * M * 64 * 576;
+    plan->bytes = (d.residual ? 3.0 : 2.0) * M * 64 * 4 + 64.0 * 576 * 4 + 256;
+    const uint64_t dims[4] = {64, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
+    const uint64_t strides[3] = {256, 256ull * d.W, 256ull * d.W * d.H};
+    const uint32_t box_in[4] = {32, 64, 2, 1};
+    const uint32_t box_out[4] = {32, static_cast<uint32_t>(d.W), 1, 1};
+    int r;
+    if ((r = make_tiled_nd(&plan->tmA, TmDtype::F32, d.in, 4, dims, strides, box_in, true)) != 0)
+        return fail(err, errlen, "conv_plan: halo2 input tensor map failed", r);
+    if ((r = make_tiled_2d(&plan->tmB, TmDtype::F32, d.weight, 64, 576, 32)) != 0)
+        return fail(err, errlen, "conv_plan: halo2 weight tensor map failed", r);
+    if ((r = make_tiled_nd(&plan->tmOut, TmDtype::F32, d.out, 4, dims, strides, box_out, true)) != 0)
+        return fail(err, errlen, "conv_plan: halo2 output tensor map failed", r);
+    plan->tmRes = plan->tmA;
+    if (d.residual && (r = make_tiled_nd(&plan->tmRes, TmDtype::F32, d.residual, 4, dims, strides, box_in, true)) != 0)
+        return fail(err, errlen, "conv_plan: halo2 residual tensor map failed", r);
     return 0;
 }
 
@@ -240,6 +284,8 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     }
     if (force_bn == 3064 || (force_bn == 0 && conv_plan_halo_ok(d) && !getenv("RNB_NO_HALO")))
         return halo_plan_init(plan, d, num_sms, err, errlen);
+    if (force_bn == 4064 || (force_bn == 0 && conv_plan_halo2_ok(d) && !getenv("RNB_NO_HALO")))
+        return halo2_plan_init(plan, d, num_sms, err, errlen);
     // +10000: "deep" variant of a tile family — one or two more shared-memory stages in flight paid
     // for with one staging buffer less (for layers whose K loop, not whose epilogue, is the bottleneck)
     const int deep = force_bn >= 10000 ? 1 : 0;
@@ -391,6 +437,9 @@ cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
         return launch_pdl(bneck_l1_kernel<BneckCfg<true>>, p.grid, BneckCfg<true>::THREADS,
                           BneckCfg<true>::SMEM_BYTES, stream, p.tmA, p.tmB, p.tmW3, p.tmWds, p.tmW1n, p.tmRes,
                           p.tmOut, p.tmT1n, p.bp, p.bg);
+    if (p.halo2)
+        return launch_pdl(conv3x3_halo2_kernel<Halo2Cfg>, p.grid, Halo2Cfg::THREADS, Halo2Cfg::SMEM_BYTES, stream, p.tmA,
+                          p.tmB, p.tmRes, p.tmOut, p.bias, p.h2g);
     if (p.halo) {
         return launch_pdl(conv3x3_halo_kernel<HaloCfg>, p.grid, HaloCfg::THREADS, HaloCfg::SMEM_BYTES, stream,
                           p.tmA, p.tmB, p.tmOut, p.bias, p.hg);

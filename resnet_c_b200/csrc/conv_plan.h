@@ -5,6 +5,7 @@
 
 #include "bneck_c3n1.cuh"
 #include "bneck_l1.cuh"
+#include "conv3x3_halo2.cuh"
 #include "conv3x3_halo.cuh"
 #include "conv_igemm.cuh"
 
@@ -81,6 +82,8 @@ struct ConvPlan {
     int f32out;   // 1 = FP32-output variant of the single-CTA kernel (FC layer)
     int halo;     // 1 = conv3x3_halo_kernel (3x3/1, 64->64, bf16): tmA/tmOut are 4-D tiled maps, geometry in hg
     HaloGeom hg;
+    int halo2;    // 1 = conv3x3_halo2_kernel (3x3/1, 64->64, tf32, CTA pair): tmA/tmRes/tmOut are 4-D maps, geometry in h2g
+    Halo2Geom h2g;
     int esz;      // element bytes
     int grid;     // persistent CTAs
     int side;     // 1 = launched on the engine's side stream (downsample conv overlapped with conv1/conv2)
@@ -92,6 +95,7 @@ struct ConvPlan {
 // force_bn codes: 0 = heuristic, 64 / 128 = single-CTA tiles, 1128 / 1256 = CTA-pair tiles,
 // 3064 = halo-resident 3x3 kernel (only where conv_plan_halo_ok()).
 bool conv_plan_halo_ok(const ConvDesc& d);
+bool conv_plan_halo2_ok(const ConvDesc& d);  // force_bn code 4064
 // Builds the tensor maps and tile geometry. Returns 0 on success; on failure writes a message to
 // `err` (if non-null, at most errlen bytes).
 int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn, char* err,

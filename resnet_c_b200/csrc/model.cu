@@ -601,13 +601,14 @@ ChunkPlan* Model::plan_for(int n) {
             auto hit = tuned.find(key);
             int best_force = hit != tuned.end() ? hit->second : -1;
             if (best_force < 0) {
-                const int cands[8] = {64, 128, 1128, 1256, 3064, 10128, 11128, 11256};
+                const int cands[9] = {64, 128, 1128, 1256, 3064, 4064, 10128, 11128, 11256};
                 float best_ms = 1e30f;
                 cudaEvent_t e0, e1;
                 cudaEventCreate(&e0);
                 cudaEventCreate(&e1);
                 for (int force : cands) {
                     if (force == 3064 && !conv_plan_halo_ok(d)) continue;
+                    if (force == 4064 && !conv_plan_halo2_ok(d)) continue;
                     // deep-pipeline variants trade a staging buffer for pipeline stages: only for layers
                     // whose epilogue is light (no residual prefetch) and whose K loop is long; timing a
                     // residual layer alone flatters them (measured in the full network: slower)
@@ -645,7 +646,7 @@ ChunkPlan* Model::plan_for(int n) {
         if (getenv("RNB_VERBOSE"))
             fprintf(stderr, "rnb plan: conv#%zu n=%d %dx%d %d->%d k%d s%d res=%d : %s tile %dx%d grid %d\n",
                     p.convs.size(), n, in_hw, in_hw, cw.Cin, cw.Cout, cw.k, cw.stride, res ? 1 : 0,
-                    cp.halo ? "halo" : (cp.ctas == 2 ? (cp.deep ? "pair-deep" : "pair") : (cp.deep ? "single-deep" : "single")),
+                    cp.halo2 ? "halo-pair" : cp.halo ? "halo" : (cp.ctas == 2 ? (cp.deep ? "pair-deep" : "pair") : (cp.deep ? "single-deep" : "single")),
                     cp.ctas == 2 ? 256 : 128, cp.bn, cp.grid);
         p.convs.push_back(cp);
         return 0;

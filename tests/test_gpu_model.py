@@ -273,6 +273,30 @@ def test_fused_bottleneck_tail_equals_layer_by_layer(monkeypatch, arch, batch):
     monkeypatch.delenv("RNB_L1L2")
 
 
+@pytest.mark.parametrize("arch,batch", [("resnet18", 3), ("resnet18", 37), ("resnet34", 2)])
+def test_tf32_halo_pair_kernel_equals_generic_kernel(monkeypatch, arch, batch):
+    """csrc/conv3x3_halo2.cuh (layer1 of the BasicBlock nets on the TF32 path: CTA pair, resident weights, halo
+    ring) keeps the K order and rounding of the generic im2col kernel: block outputs and logits bit-identical."""
+    from resnet_c_b200 import weights
+    monkeypatch.setenv("RNB_AUTOTUNE", "0")
+    monkeypatch.setenv("RNB_KEEP_ACTIVATIONS", "1")
+    names = ("layer1.0", "layer1.1", "layer2.0")
+    outs = []
+    for no_halo in ("1", ""):
+        if no_halo:
+            monkeypatch.setenv("RNB_NO_HALO", no_halo)
+        else:
+            monkeypatch.delenv("RNB_NO_HALO", raising=False)
+        model = _model(arch, True, "tf32", batch)
+        logits, top1 = model.forward(weights.synthetic_images(batch).cuda())
+        torch.cuda.synchronize()
+        outs.append((logits.clone(), top1.clone(), {n: model.activation(n).clone() for n in names}))
+        model.close()
+    for n in names:
+        assert torch.equal(outs[0][2][n], outs[1][2][n]), f"{n} differs"
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_launch_accounting(monkeypatch):
     monkeypatch.setenv("RNB_FUSE", "0")
     model = _model("resnet50", True, "bf16", 64, chunk=16)
