@@ -315,11 +315,12 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
         if (d.Cout % (force_bn - 1000) != 0) return fail(err, errlen, "conv_plan: forced BN does not divide Cout", -6);
         bn = force_bn - 1000;
         ctas = 2;
-    } else if (allow_pair && d.Cout % 128 == 0 && (!d.residual || getenv("RNB_PAIR_RES")) &&
+    } else if (allow_pair && d.Cout % 128 == 0 && (!d.residual || d.ksize == 3 || getenv("RNB_PAIR_RES")) &&
                d.ksize * d.ksize * d.Cin > 64) {
         // Measured on B200 (profiles/): pairs win wherever the K loop dominates (3x3 and wide 1x1
-        // layers, up to 1.45x); layers whose time is the epilogue's HBM traffic (residual add, or a
-        // single K block) are no faster with pairs and slightly slower, so they keep 128-pixel tiles.
+        // layers, up to 1.45x); layers whose time is the epilogue's HBM traffic (1x1 with residual add, or a
+        // single K block) are no faster with pairs and slightly slower, so they keep 128-pixel tiles. A 3x3
+        // conv with residual (conv2 of a BasicBlock) is K-loop-bound: pairs (88-106 us vs 148 us, TF32).
         const int pbn = d.Cout % 256 == 0 ? 256 : 128;
         const long long pair_tiles = ((M + 255) / 256) * (d.Cout / pbn);
         if (pair_tiles >= num_sms / 2) {
