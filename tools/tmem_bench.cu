@@ -47,6 +47,58 @@ __global__ void __launch_bounds__(384, 1) k(int iters, long long* out, float* si
     if (warp == 2) { __syncwarp(); tmem_dealloc(tb, 512); }
 }
 
+// Does fence.proxy.async (the fence an epilogue needs before a TMA store / UMMA may read what it wrote) wait for a
+// tcgen05.ld in flight?  mode 0: ld; wait::ld; work; st.shared; fence     mode 1: ld(next); work(cur); st.shared; fence; wait::ld
+__global__ void __launch_bounds__(384, 1) kf(int iters, int mode, long long* out, float* sink) {
+    __shared__ uint32_t tptr;
+    __shared__ uint32_t buf[256 * 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 2) { __syncwarp(); tmem_alloc(&tptr, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tptr;
+    long long t0 = clock64();
+    if (warp >= 4) {
+        const uint32_t lb = tb + (static_cast<uint32_t>((warp & 3) * 32) << 16) + ((warp - 4) >> 2) * 256;
+        uint32_t acc = 0;
+        uint32_t va[32], vb[32];
+        auto work = [&](uint32_t (&v)[32]) {   // ~100 dependent-ish ALU ops + 4 shared stores + proxy fence
+            uint32_t x = acc;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x = x * 1664525u + v[j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) buf[(threadIdx.x - 128) * 4 + j] = x + j;
+            fence_proxy_async_smem();
+            acc = x;
+        };
+        if (mode == 0) {
+            for (int i = 0; i < iters; ++i) {
+                Ld<32>::go(lb + ((i * 32) & 224), va);
+                tmem_ld_wait();
+                work(va);
+            }
+        } else {
+            Ld<32>::go(lb, va);
+            for (int i = 0; i < iters; i += 2) {
+                tmem_ld_wait();
+                Ld<32>::go(lb + (((i + 1) * 32) & 224), vb);
+                work(va);
+                tmem_ld_wait();
+                Ld<32>::go(lb + (((i + 2) * 32) & 224), va);
+                work(vb);
+            }
+            tmem_ld_wait();
+        }
+        if (acc == 0x12345u) sink[0] = 1.f;
+        __syncwarp();
+        if (lane == 0 && blockIdx.x == 0 && warp == 4) out[0] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { __syncwarp(); tmem_dealloc(tb, 512); }
+}
+
 template <int N> void run(long long* out, float* sink) {
     const int iters = 4000;
     cudaMemset(out, 0, 16);
@@ -61,5 +113,16 @@ int main() {
     long long* out; float* sink;
     cudaMalloc(&out, 16); cudaMalloc(&sink, 4);
     run<16>(out, sink); run<32>(out, sink); run<64>(out, sink);
+    for (int mode = 0; mode < 2; ++mode) {
+        const int iters = 4000;
+        cudaMemset(out, 0, 16);
+        kf<<<148, 384>>>(iters, mode, out, sink);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h;
+        cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
+        printf("ld.x32 + work + st.shared + fence.proxy.async, %s: %s  %.1f clk per step (8 warps)\n",
+               mode ? "next load issued BEFORE the work (double-buffered)" : "load; wait; work (serial)",
+               cudaGetErrorString(e), double(h) / iters);
+    }
     return 0;
 }
