@@ -248,8 +248,12 @@ int rnb_model_get_activation(rnb_model_t* m, const char* name, float* out_dev, i
     if (!out_dev) return RNB_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (std::string(name) == "avgpool") {
-        // stored transposed ([C][n], see tail.cu); hand back [n][C]
-        API_CUDA(launch_transpose_f32(static_cast<const float*>(a.ptr), out_dev, a.C, n, s));
+        // stored transposed ([C][n], see tail.cu) for the CUDA-core FC, row-major beside the BF16 copy of the
+        // tensor-core FC; hand back [n][C]
+        if (pit->second.pooled_bf16)
+            API_CUDA(cudaMemcpyAsync(out_dev, a.ptr, 1ull * n * a.C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        else
+            API_CUDA(launch_transpose_f32(static_cast<const float*>(a.ptr), out_dev, a.C, n, s));
         return RNB_OK;
     }
     API_CUDA(launch_nhwc_to_nchw(a.ptr, out_dev, n, a.C, a.H * a.W, M.esz, s));

@@ -57,7 +57,11 @@ struct BneckGeom {
 // N1_ = output channels of the fused next conv1: 64 (next block of the same layer) or 128 (first block of
 // the NEXT layer, 256 -> 128 at the same resolution). N1 = 128 needs a 128-column D3, paid for with a
 // single-buffered D1 (the epilogue runs one tile ahead, so conv2 still has a whole tile of slack).
-template <bool DS_, int N1_ = 64>
+// NABUF_ = input tiles in flight. The folded-downsample form (DS) is short of shared memory: with two input
+// tiles it has room for three staging boxes only; with ONE input tile (the next load starts when conv2 has consumed
+// the tile — the epilogue runs a whole tile behind conv2, which hides the load) it gets five (measured: 2.597 ->
+// 2.586 ms per ResNet-50 step; a second shortcut-input tile instead of the fifth box: no gain).
+template <bool DS_, int N1_ = 64, int NABUF_ = 2>
 struct BneckCfg {
     static constexpr bool DS = DS_;  // shortcut = downsample conv of x, fused as a second K block
     static constexpr int N1 = N1_;
@@ -66,7 +70,7 @@ struct BneckCfg {
     static_assert(N1_ == 64 || N1_ == 128, "next conv1 width");
     static_assert(!(DS_ && N1_ != 64), "the folded-downsample form is only built with N1 = 64");
     static constexpr int PITCH = 64;
-    static constexpr int NABUF = 2;                 // input tiles in flight
+    static constexpr int NABUF = NABUF_;            // input tiles in flight
     static constexpr int ATILE_BYTES = 32768;       // 4 rows x 64 pixels x 128 B
     static constexpr int AROW_BYTES = 8192;         // one input row of the tile
     static constexpr int W2_TAP_BYTES = 32 * 128;   // this CTA's 32 output channels of one tap
@@ -80,7 +84,7 @@ struct BneckCfg {
     static constexpr int RING_BYTES = NABUF * ATILE_BYTES + 1024;  // + read-past pad of the shifted views
     static constexpr int BOX_BYTES = 16384;         // 128 rows x 64 bf16, 128-byte swizzled
     static constexpr int P_BYTES = DS_ ? BOX_BYTES : 0;
-    static constexpr int NPOOL = DS_ ? 3 : (N1_ == 64 ? 5 : 4);  // staging boxes (R mode: also the residual prefetch depth)
+    static constexpr int NPOOL = DS_ ? (NABUF_ == 1 ? 5 : 3) : (N1_ == 64 ? 5 : 4);  // staging boxes (R mode: also the residual prefetch depth)
     static constexpr int TMEM_COLS = 512;
     static constexpr int D1_COL = 0, D2_COL = 64 * ND1, D3_COL = D2_COL + 256, A2_COL = D3_COL + N1_;
     static_assert(A2_COL + 64 <= 512, "TMEM budget");
@@ -92,6 +96,7 @@ struct BneckCfg {
 };
 static_assert(BneckCfg<false>::SMEM_BYTES <= 232448, "smem budget");
 static_assert(BneckCfg<true>::SMEM_BYTES <= 232448, "smem budget");
+static_assert(BneckCfg<true, 64, 1>::SMEM_BYTES <= 232448, "smem budget");
 static_assert(BneckCfg<false, 128>::SMEM_BYTES <= 232448, "smem budget");
 
 namespace ptx {
@@ -311,8 +316,8 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int it = 0; it < T; ++it) {
             int img, h0;
             tile_coords(it, img, h0);
-            const int ab = it & 1;
-            mbar_wait(&a_empty[ab], ((it >> 1) & 1) ^ 1);
+            const int ab = it % NABUF;
+            mbar_wait(&a_empty[ab], ((it / NABUF) & 1) ^ 1);
             if (elect_one()) {
                 if (rank == 0) mbar_expect_tx(&a_full[ab], 2 * Cfg::ATILE_BYTES);
                 // pixels [-1, 63) of input rows h0-1 .. h0+2; out-of-image parts are zero-filled
@@ -332,11 +337,12 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int buf = i % Cfg::ND1;
                 const uint32_t ph = (i / Cfg::ND1) & 1;
                 mbar_wait(&d1_empty[buf], ph ^ 1);
-                mbar_wait(&a_full[i & 1], (i >> 1) & 1);
+                const int ab = i % NABUF;
+                mbar_wait(&a_full[ab], (i / NABUF) & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + Cfg::D1_COL + buf * 64;
-                    const uint64_t a_tile = ring_desc + static_cast<uint64_t>(((i & 1) * Cfg::ATILE_BYTES) >> 4);
+                    const uint64_t a_tile = ring_desc + static_cast<uint64_t>((ab * Cfg::ATILE_BYTES) >> 4);
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -351,7 +357,7 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                                b_tap + static_cast<uint64_t>(k * 2), idesc64, (r | s | k) != 0);
                         }
                     }
-                    tc_commit_2sm(&a_empty[i & 1]);
+                    tc_commit_2sm(&a_empty[ab]);
                     tc_commit_2sm(&d1_full[buf]);
                 }
                 __syncwarp();

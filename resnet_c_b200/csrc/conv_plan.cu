@@ -84,6 +84,9 @@ cudaError_t conv_kernels_init() {
     if ((e = cudaFuncSetAttribute(bneck_l1_kernel<BneckCfg<false, 128>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   BneckCfg<false, 128>::SMEM_BYTES)) != cudaSuccess)
         return e;
+    if ((e = cudaFuncSetAttribute(bneck_l1_kernel<BneckCfg<true, 64, 1>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  BneckCfg<true, 64, 1>::SMEM_BYTES)) != cudaSuccess)
+        return e;
     if ((e = cudaFuncSetAttribute(bneck_l1_kernel<BneckCfg<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   BneckCfg<true>::SMEM_BYTES)) != cudaSuccess)
         return e;
@@ -434,10 +437,17 @@ cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
         return launch_pdl(bneck_l1_kernel<BneckCfg<false, 128>>, p.grid, BneckCfg<false, 128>::THREADS,
                           BneckCfg<false, 128>::SMEM_BYTES, stream, p.tmA, p.tmB, p.tmW3, p.tmWds, p.tmW1n, p.tmRes,
                           p.tmOut, p.tmT1n, p.bp, p.bg);
-    if (p.bneck == 2)
+    if (p.bneck == 2) {
+        // RNB_DS_NABUF=2: two input tiles in flight and three staging boxes (the first form of this kernel)
+        static const bool one_tile = !(getenv("RNB_DS_NABUF") && atoi(getenv("RNB_DS_NABUF")) == 2);
+        if (one_tile)
+            return launch_pdl(bneck_l1_kernel<BneckCfg<true, 64, 1>>, p.grid, BneckCfg<true, 64, 1>::THREADS,
+                              BneckCfg<true, 64, 1>::SMEM_BYTES, stream, p.tmA, p.tmB, p.tmW3, p.tmWds, p.tmW1n,
+                              p.tmRes, p.tmOut, p.tmT1n, p.bp, p.bg);
         return launch_pdl(bneck_l1_kernel<BneckCfg<true>>, p.grid, BneckCfg<true>::THREADS,
                           BneckCfg<true>::SMEM_BYTES, stream, p.tmA, p.tmB, p.tmW3, p.tmWds, p.tmW1n, p.tmRes,
                           p.tmOut, p.tmT1n, p.bp, p.bg);
+    }
     if (p.halo2)
         return launch_pdl(conv3x3_halo2_kernel<Halo2Cfg>, p.grid, Halo2Cfg::THREADS, Halo2Cfg::SMEM_BYTES, stream, p.tmA,
                           p.tmB, p.tmRes, p.tmOut, p.bias, p.h2g);

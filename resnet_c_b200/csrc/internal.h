@@ -1,6 +1,7 @@
 // internal.h — declarations shared by the translation units of librnb.so (not part of the ABI).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <string>
 
@@ -10,6 +11,26 @@ namespace rnb {
 int num_sms();
 void set_error(const std::string& msg);
 int fail_cuda(cudaError_t e, const char* what);  // records the message, returns RNB_ERR_CUDA
+
+// Launch with programmatic stream serialization (PDL): the kernel may be scheduled while its predecessor in the
+// stream drains; it MUST execute griddepcontrol.wait before touching anything an earlier kernel wrote (and every
+// kernel launched this way must execute it, so that completion stays transitive). RNB_NO_PDL=1 -> plain launch.
+template <class Kernel, class... Args>
+inline cudaError_t launch_pdl_small(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    Args... args) {
+    static const bool on = !(getenv("RNB_NO_PDL") && atoi(getenv("RNB_NO_PDL")) != 0);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = on ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 // ---- FP32 NCHW per-op kernels (ops_f32.cu)
 cudaError_t launch_conv2d_f32(const float* x, float* out, const float* w, int B, int Cin, int H,
@@ -105,6 +126,8 @@ inline cudaError_t launch_stem_any_part(int esz, int part, const float* x, void*
 // ---- tail (tail.cu)
 // global average pool over NHWC [B,HW,C] -> pooledT [C][B] fp32 (transposed, see tail.cu)
 // (+ optional row-major BF16 copy pooled_bf16[B][C] for the tensor-core FC; BF16 activations only)
+// With pooled_bf16 (tensor-core FC) the FP32 result is written ROW-MAJOR [B][C] instead (nobody reads it on the hot
+// path; rnb_model_get_activation hands it out).
 cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, void* pooled_bf16, int B, int HW, int C, int esz,
                                 cudaStream_t s);
 // fc.weight [classes][C] fp32 -> [cpad][C] bf16 (zero rows beyond classes), fc.bias -> [cpad] fp32

@@ -146,11 +146,24 @@ __global__ void argmax_f32_kernel(const float* __restrict__ x, int32_t* __restri
                                   int n) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // launched with PDL: x is the previous kernel's output
     if (warp >= B) return;
     const float* row = x + 1LL * warp * n;
     float best = -INFINITY;
     int best_i = 0x7fffffff;
-    for (int j = lane; j < n; j += 32) {
+    int j = lane;
+    for (; j + 96 < n; j += 128) {  // four independent loads in flight; compared in index order
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = row[j + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (v[u] > best || best_i == 0x7fffffff) {
+                best = v[u];
+                best_i = j + 32 * u;
+            }
+    }
+    for (; j < n; j += 32) {
         const float v = row[j];
         if (v > best || (v == best && j < best_i) || best_i == 0x7fffffff) {
             best = v;
@@ -274,9 +287,9 @@ cudaError_t launch_linear_f32(const float* x, float* out, const float* w, const 
     return cudaGetLastError();
 }
 cudaError_t launch_argmax_f32(const float* x, int32_t* out, int B, int n, cudaStream_t s) {
-    const int warps_per_block = kThreads / 32;
-    argmax_f32_kernel<<<(B + warps_per_block - 1) / warps_per_block, kThreads, 0, s>>>(x, out, B, n);
-    return cudaGetLastError();
+    const int warps_per_block = 2;  // 128 blocks for 256 rows: spread over the SMs (the kernel is latency-bound)
+    return launch_pdl_small(argmax_f32_kernel, dim3((B + warps_per_block - 1) / warps_per_block),
+                            dim3(32 * warps_per_block), 0, s, x, out, B, n);
 }
 
 }  // namespace rnb

@@ -54,6 +54,7 @@ constexpr int STEM_TC_THREADS = 128 + EPI_THREADS;
 __global__ void stem_pack_kernel(const float* __restrict__ x, uint4* __restrict__ xp, int B) {
     constexpr int GROUPS = PAD_W / 4;  // 58
     const int64_t total = 1LL * B * PAD_H * GROUPS;
+    ptx::griddep_launch_dependents();
     for (int64_t i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
          i += 1LL * gridDim.x * blockDim.x) {
         const int gidx = static_cast<int>(i % GROUPS);
@@ -107,6 +108,7 @@ struct StemNorm {
 __global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ x, uint4* __restrict__ xp, int B, StemNorm nm) {
     constexpr int GROUPS = PAD_W / 4;  // 58
     const int64_t total = 1LL * B * PAD_H * GROUPS;
+    ptx::griddep_launch_dependents();
     for (int64_t i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
          i += 1LL * gridDim.x * blockDim.x) {
         const int gidx = static_cast<int>(i % GROUPS);
@@ -249,6 +251,10 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // PDL: the prologue above (barriers, TMEM, weights — constants) overlaps the tail of the layout pre-pass, and
+    // the first conv kernel's prologue overlaps this kernel's tail
+    griddep_launch_dependents();
+    griddep_wait();
 
     if (warp == 0) {
         // ===================================================== producer: one bulk copy per unit
@@ -437,9 +443,9 @@ cudaError_t launch_stem_tc_part(int part, const float* x, void* xp, const void* 
     } else {
         const int units = B * UNITS_PER_IMG;
         const int grid = units < num_sms() ? units : num_sms();
-        stem_tc_kernel<<<grid, STEM_TC_THREADS, STEM_SMEM, s>>>(
-            static_cast<const uint8_t*>(xp), static_cast<const uint8_t*>(wk), bias,
-            static_cast<__nv_bfloat16*>(out), B);
+        return launch_pdl_small(stem_tc_kernel, dim3(grid), dim3(STEM_TC_THREADS), STEM_SMEM, s,
+                                static_cast<const uint8_t*>(xp), static_cast<const uint8_t*>(wk), bias,
+                                static_cast<__nv_bfloat16*>(out), B);
     }
     return cudaGetLastError();
 }

@@ -31,6 +31,8 @@ __global__ void avgpool_nhwc_kernel(const T* __restrict__ x, float* __restrict__
     constexpr int VEC = 16 / sizeof(T);
     const int groups = C / VEC;
     const int64_t total = 1LL * n * groups;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // launched with PDL: x is the previous kernel's output
     for (int64_t i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
          i += 1LL * gridDim.x * blockDim.x) {
         const int gidx = static_cast<int>(i % groups);
@@ -58,13 +60,19 @@ __global__ void avgpool_nhwc_kernel(const T* __restrict__ x, float* __restrict__
             }
         }
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
+        for (int e = 0; e < VEC; ++e)
             acc[e] = ksq > 0 ? acc[e] / static_cast<float>(ksq) / static_cast<float>(ksq)
                              : acc[e] / static_cast<float>(HW);
-            pooledT[1LL * (gidx * VEC + e) * n + b] = acc[e];
+        if (sizeof(T) != 2 || !pooled_bf16) {
+            // transposed FP32 for fc_kernel (scattered 4-byte stores: fine for the CUDA-core FC path only)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) pooledT[1LL * (gidx * VEC + e) * n + b] = acc[e];
         }
         if constexpr (sizeof(T) == 2) {
-            if (pooled_bf16) {  // row-major BF16 copy: the A operand of the tensor-core FC
+            if (pooled_bf16) {  // row-major BF16 copy: the A operand of the tensor-core FC (+ row-major FP32)
+                float4* pr = reinterpret_cast<float4*>(pooledT + 1LL * b * C + gidx * VEC);
+                pr[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                pr[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
                 uint4 o;
                 o.x = pack2(acc[0], acc[1]); o.y = pack2(acc[2], acc[3]);
                 o.z = pack2(acc[4], acc[5]); o.w = pack2(acc[6], acc[7]);
@@ -197,12 +205,11 @@ cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, void* pooled_bf16
     const int64_t total = 1LL * B * (C * esz / 16);
     const int blocks = static_cast<int>((total + 127) / 128);
     if (esz == 2)
-        avgpool_nhwc_kernel<__nv_bfloat16><<<blocks, 128, 0, s>>>(
-            static_cast<const __nv_bfloat16*>(x), pooledT, static_cast<__nv_bfloat16*>(pooled_bf16), B, HW, C, ksq);
-    else
-        avgpool_nhwc_kernel<float><<<blocks, 128, 0, s>>>(static_cast<const float*>(x), pooledT, nullptr, B, HW,
-                                                         C, ksq);
-    return cudaGetLastError();
+        return launch_pdl_small(avgpool_nhwc_kernel<__nv_bfloat16>, dim3(blocks), dim3(128), 0, s,
+                                static_cast<const __nv_bfloat16*>(x), pooledT,
+                                static_cast<__nv_bfloat16*>(pooled_bf16), B, HW, C, ksq);
+    return launch_pdl_small(avgpool_nhwc_kernel<float>, dim3(blocks), dim3(128), 0, s, static_cast<const float*>(x),
+                            pooledT, static_cast<__nv_bfloat16*>(nullptr), B, HW, C, ksq);
 }
 
 cudaError_t launch_fc(const float* pooledT, const float* w, const float* bias, float* logits, int B,
