@@ -222,6 +222,13 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
 
     const int warp = threadIdx.x >> 5;
     const int num_units = B * UNITS_PER_IMG;
+    // Each CTA takes a CONTIGUOUS range of units, so that most units follow the previous unit of the same image: the conv
+    // row the two share (slot 0 of the new unit = slot 6 of the old one) is then neither recomputed nor re-read — the
+    // epilogue already holds it in registers (`carry`). One seventh of the MMAs of this tensor-bound kernel disappears.
+    const int upc = num_units / static_cast<int>(gridDim.x), urem = num_units % static_cast<int>(gridDim.x);
+    const int u_begin = static_cast<int>(blockIdx.x) * upc + min(static_cast<int>(blockIdx.x), urem);
+    const int u_end = u_begin + upc + (static_cast<int>(blockIdx.x) < urem ? 1 : 0);
+    auto continues = [&](int u) { return u > u_begin && (u % UNITS_PER_IMG) != 0; };
 
     if (threadIdx.x == 32) {
         for (int i = 0; i < 2; ++i) {
@@ -259,7 +266,7 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
     if (warp == 0) {
         // ===================================================== producer: one bulk copy per unit
         int it = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+        for (int u = u_begin; u < u_end; ++u, ++it) {
             const int s = it & 1;
             mbar_wait(&in_empty[s], ((it >> 1) & 1) ^ 1);
             if (elect_one()) {
@@ -276,11 +283,14 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
         const uint64_t a_desc0 = umma_smem_desc(smem_u32(in_slot), 16, 128, UMMA_LAYOUT_NONE);
         const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 1024, 128, UMMA_LAYOUT_NONE);
         int it = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+        uint32_t n0 = 0;  // uses of slot 0 so far
+        for (int u = u_begin; u < u_end; ++u, ++it) {
             const int s = it & 1;
             mbar_wait(&in_full[s], (it >> 1) & 1);
-            for (int r = 0; r < ROWS_PER_UNIT; ++r) {
-                mbar_wait(&slot_empty[r], (it & 1) ^ 1);
+            const bool cont = continues(u);
+            for (int r = cont ? 1 : 0; r < ROWS_PER_UNIT; ++r) {
+                // slot 0 is skipped by continuing units: its barriers count their own uses
+                mbar_wait(&slot_empty[r], r == 0 ? (n0 & 1) ^ 1 : (it & 1) ^ 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + r * 64;
@@ -301,6 +311,7 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
                 }
                 __syncwarp();
             }
+            if (!cont) ++n0;
         }
     } else if (warp >= 4) {
         // ===================================================== epilogue
@@ -316,15 +327,19 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
         for (int i = 0; i < 32; ++i) bias_r[i] = __ldg(bias + half * 32 + i);
         int it = 0;
         int vb = 0;  // vbuf ping-pong
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+        uint32_t n0 = 0;  // uses of slot 0 so far
+        float carry[32];  // the last conv row of the previous pooled row (and of the previous unit)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) carry[i] = -INFINITY;
+        for (int u = u_begin; u < u_end; ++u, ++it) {
             const int b = u / UNITS_PER_IMG, v = u - b * UNITS_PER_IMG;
             const uint32_t par = it & 1;
-            float carry[32];
+            const bool cont = continues(u);
 #pragma unroll
             for (int p = 0; p < POOLED_PER_UNIT; ++p) {
                 const int ph = v * POOLED_PER_UNIT + p;
                 // slots 2p, 2p+1, 2p+2 hold conv rows oh = 6v - 1 + slot
-                if (p == 0) mbar_wait(&slot_full[0], par);
+                if (p == 0 && !cont) mbar_wait(&slot_full[0], n0 & 1);
                 mbar_wait(&slot_full[2 * p + 1], par);
                 mbar_wait(&slot_full[2 * p + 2], par);
                 tc_fence_after();
@@ -337,6 +352,7 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
                 float m[32];
 #pragma unroll
                 for (int k = (p == 0 ? 0 : 1); k < 3; ++k) {
+                    if (p == 0 && k == 0 && cont) continue;  // that row is `carry`
                     const int oh = 6 * v - 1 + 2 * p + k;
                     uint32_t raw[32];
                     __syncwarp();
@@ -347,7 +363,7 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
                         for (int i = 0; i < 32; ++i) m[i] = oh >= 0 ? __uint_as_float(raw[i]) : -INFINITY;
                     } else {
                         const bool valid = oh < CONV;
-                        if (k == 1 && p > 0) {
+                        if (k == 1 && (p > 0 || cont)) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) m[i] = carry[i];
                         }
@@ -377,7 +393,7 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
                 // slots 2p and 2p+1 are drained; 2p+2 is re-read by the next pooled row (or drained
                 // with the last one)
                 tc_fence_before();
-                mbar_arrive(&slot_empty[2 * p]);
+                if (p > 0 || !cont) mbar_arrive(&slot_empty[2 * p]);
                 mbar_arrive(&slot_empty[2 * p + 1]);
                 if (p == POOLED_PER_UNIT - 1) mbar_arrive(&slot_empty[2 * p + 2]);
                 named_bar_sync(1, EPI_THREADS);
@@ -402,6 +418,7 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
                 }
                 vb ^= 1;
             }
+            if (!cont) ++n0;
         }
     }
 
