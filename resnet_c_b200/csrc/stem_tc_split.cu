@@ -138,6 +138,12 @@ stem_tc_split_kernel(const uint8_t* __restrict__ xp_hi, const uint8_t* __restric
 
     const int warp = threadIdx.x >> 5;
     const int num_units = B * UNITS_PER_IMG;
+    // contiguous unit range per CTA; the conv row shared with the previous unit of the same image is carried in
+    // registers by the epilogue instead of being recomputed (see stem_tc.cu)
+    const int upc = num_units / static_cast<int>(gridDim.x), urem = num_units % static_cast<int>(gridDim.x);
+    const int u_begin = static_cast<int>(blockIdx.x) * upc + min(static_cast<int>(blockIdx.x), urem);
+    const int u_end = u_begin + upc + (static_cast<int>(blockIdx.x) < urem ? 1 : 0);
+    auto continues = [&](int u) { return u > u_begin && (u % UNITS_PER_IMG) != 0; };
 
     if (threadIdx.x == 32) {
         for (int i = 0; i < 2; ++i) {
@@ -172,7 +178,7 @@ stem_tc_split_kernel(const uint8_t* __restrict__ xp_hi, const uint8_t* __restric
     if (warp == 0) {
         // ===================================================== producer: two bulk copies per unit
         int it = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+        for (int u = u_begin; u < u_end; ++u, ++it) {
             const int s = it & 1;
             mbar_wait(&in_empty[s], ((it >> 1) & 1) ^ 1);
             if (elect_one()) {
@@ -192,11 +198,14 @@ stem_tc_split_kernel(const uint8_t* __restrict__ xp_hi, const uint8_t* __restric
         constexpr uint64_t A_LO = IN_SLOT_BYTES >> 4;   // hi -> lo image inside a slot
         constexpr uint64_t B_LO = W_BYTES >> 4;         // hi -> lo weights
         int it = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+        uint32_t n0 = 0;  // uses of slot 0 so far (continuing units skip it)
+        for (int u = u_begin; u < u_end; ++u, ++it) {
             const int s = it & 1;
             mbar_wait(&in_full[s], (it >> 1) & 1);
-            for (int r = 0; r < ROWS_PER_UNIT; ++r) {
-                mbar_wait(&slot_empty[r], (it & 1) ^ 1);
+            const bool cont = continues(u);
+            if (!cont) ++n0;
+            for (int r = cont ? 1 : 0; r < ROWS_PER_UNIT; ++r) {
+                mbar_wait(&slot_empty[r], r == 0 ? (n0 & 1) : (it & 1) ^ 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + r * 64;
@@ -227,18 +236,29 @@ stem_tc_split_kernel(const uint8_t* __restrict__ xp_hi, const uint8_t* __restric
         const int etid = threadIdx.x - 128;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32;
         int it = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+        uint32_t n0 = 0;  // uses of slot 0 so far
+        float carry[32];  // the last conv row of the previous pooled row (and of the previous unit)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) carry[i] = -INFINITY;
+        for (int u = u_begin; u < u_end; ++u, ++it) {
             const int b = u / UNITS_PER_IMG, v = u - b * UNITS_PER_IMG;
             const uint32_t par = it & 1;
+            const bool cont = continues(u);
+            if (!cont) ++n0;
             for (int p = 0; p < POOLED_PER_UNIT; ++p) {
                 const int ph = v * POOLED_PER_UNIT + p;
-                if (p == 0) mbar_wait(&slot_full[0], par);
+                if (p == 0 && !cont) mbar_wait(&slot_full[0], (n0 & 1) ^ 1);
                 mbar_wait(&slot_full[2 * p + 1], par);
                 mbar_wait(&slot_full[2 * p + 2], par);
                 tc_fence_after();
                 float m[32];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
+                    if (k == 0 && (p > 0 || cont)) {  // read once, as row k = 2 of the previous pooled row
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) m[i] = carry[i];
+                        continue;
+                    }
                     const int oh = 6 * v - 1 + 2 * p + k;
                     uint32_t raw[32];
                     __syncwarp();
@@ -249,10 +269,11 @@ stem_tc_split_kernel(const uint8_t* __restrict__ xp_hi, const uint8_t* __restric
                     for (int i = 0; i < 32; ++i) {
                         const float x = valid ? __uint_as_float(raw[i]) : -INFINITY;
                         m[i] = k == 0 ? x : fmaxf(m[i], x);
+                        if (k == 2) carry[i] = x;
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&slot_empty[2 * p]);
+                if (p > 0 || !cont) mbar_arrive(&slot_empty[2 * p]);
                 mbar_arrive(&slot_empty[2 * p + 1]);
                 if (p == POOLED_PER_UNIT - 1) mbar_arrive(&slot_empty[2 * p + 2]);
                 // single staging buffer: the previous pooled row's horizontal pass must be over
