@@ -61,3 +61,20 @@ def test_stem_tc_borders_and_channels(oracle_lib):
     want_q = _oracle_stem(oracle_lib, x, wq, bn)
     np.testing.assert_allclose(got, want_q, rtol=1e-2, atol=1e-6)
     assert (np.abs(got) > 0).sum() == (np.abs(want) > 0).sum()
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+def test_stem_tc_unit_partitioning_is_bit_exact(dtype):
+    """The tensor-core stems give each CTA a contiguous range of work units and carry the conv row two consecutive
+    units of an image share in registers (stem_tc.cu / stem_tc_split.cu). A batch of 20 images (380 units on 148 CTAs:
+    ranges of 2-3 units, most starting in the middle of an image) must equal, bit for bit, the same images pushed
+    through one at a time (19 units on 19 CTAs: no unit continues another) and a batch of 9 (171 units: ranges of 1-2)."""
+    from resnet_c_b200 import engine, weights
+    w, bn = _params(13)
+    x = weights.synthetic_images(20, seed=21).cuda()
+    wc, bnc = w.cuda(), tuple(t.cuda() for t in bn)
+    full = engine.stem_forward(x, wc, bnc, dtype).cpu()
+    singles = torch.cat([engine.stem_forward(x[i:i + 1].contiguous(), wc, bnc, dtype).cpu() for i in range(20)])
+    assert torch.equal(full, singles)
+    nine = engine.stem_forward(x[:9].contiguous(), wc, bnc, dtype).cpu()
+    assert torch.equal(full[:9], nine)
