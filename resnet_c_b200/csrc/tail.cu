@@ -41,10 +41,7 @@ __global__ void avgpool_nhwc_kernel(const T* __restrict__ x, float* __restrict__
         float acc[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
-        // unrolled: seven independent 16-byte loads in flight per thread (the adds stay in pixel order)
-#pragma unroll 7
-        for (int p = 0; p < HW; ++p) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(xp + 1LL * p * C));
+        auto add_pixel = [&](const uint4& v) {
             if constexpr (sizeof(T) == 2) {
                 const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -58,6 +55,26 @@ __global__ void avgpool_nhwc_kernel(const T* __restrict__ x, float* __restrict__
                 acc[2] += __uint_as_float(v.z);
                 acc[3] += __uint_as_float(v.w);
             }
+        };
+        // Batches of NB independent 16-byte loads are issued before the first add (the adds stay in pixel order):
+        // two latency rounds for the 7x7 map of the network tail (the kernel is latency-, not bandwidth-bound: 51 MB).
+        constexpr int NB = 25;
+        int p = 0;
+        for (; p + NB <= HW; p += NB) {
+            uint4 v[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(xp + 1LL * (p + j) * C));
+#pragma unroll
+            for (int j = 0; j < NB; ++j) add_pixel(v[j]);
+        }
+        {
+            uint4 v[NB - 1];
+#pragma unroll
+            for (int j = 0; j < NB - 1; ++j)
+                v[j] = p + j < HW ? __ldg(reinterpret_cast<const uint4*>(xp + 1LL * (p + j) * C)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < NB - 1; ++j)
+                if (p + j < HW) add_pixel(v[j]);
         }
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
@@ -204,8 +221,8 @@ cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, void* pooled_bf16
         if (k * k == HW) ksq = k;
     const int64_t total = 1LL * B * (C * esz / 16);
     const int blocks = static_cast<int>((total + 127) / 128);
-    if (esz == 2)
-        return launch_pdl_small(avgpool_nhwc_kernel<__nv_bfloat16>, dim3(blocks), dim3(128), 0, s,
+    if (esz == 2)  // 64-thread blocks: ~145 registers per thread, and the whole grid should be resident at once
+        return launch_pdl_small(avgpool_nhwc_kernel<__nv_bfloat16>, dim3(static_cast<int>((total + 63) / 64)), dim3(64), 0, s,
                                 static_cast<const __nv_bfloat16*>(x), pooledT,
                                 static_cast<__nv_bfloat16*>(pooled_bf16), B, HW, C, ksq);
     return launch_pdl_small(avgpool_nhwc_kernel<float>, dim3(blocks), dim3(128), 0, s, static_cast<const float*>(x),
