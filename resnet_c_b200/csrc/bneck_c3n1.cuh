@@ -26,6 +26,34 @@
 
 namespace rnb {
 
+// In-kernel timeline (tools/c3n1s_timeline.py builds a separate library with -DRNB_TIMELINE; the product build
+// compiles all of this away): one thread of each of four warp roles of CTA 0 records clock64() at its hand-off points
+// while it works on its SECOND tile, into thread-local storage, and dumps it to global memory when the kernel ends.
+#ifdef RNB_TIMELINE
+constexpr int kTlMax = 160;
+__device__ long long g_c3n1s_tl[4][kTlMax];
+__device__ int g_c3n1s_tl_n[4];
+#define TL_DECL(role_)                                                                                  \
+    long long tl_buf[kTlMax];                                                                           \
+    int tl_n = 0;                                                                                       \
+    const int tl_role = (role_);                                                                        \
+    const bool tl_me = blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((role_) != 0 || threadIdx.x == 128); \
+    int tl_tile = -1;
+#define TL_TILE(i_) tl_tile = (i_);
+#define TL(tag_)                                                                             \
+    if (tl_me && tl_tile == 1 && tl_n < kTlMax) tl_buf[tl_n++] = (clock64() << 8) | (tag_);
+#define TL_DUMP()                                                        \
+    if (tl_me) {                                                         \
+        for (int i_ = 0; i_ < tl_n; ++i_) g_c3n1s_tl[tl_role][i_] = tl_buf[i_]; \
+        g_c3n1s_tl_n[tl_role] = tl_n;                                    \
+    }
+#else
+#define TL_DECL(role_)
+#define TL_TILE(i_)
+#define TL(tag_)
+#define TL_DUMP()
+#endif
+
 struct C3n1Geom {
     int M;        // pixel rows (batch * H * W)
     int tiles;    // ceil(M / 256) pair tiles
@@ -356,7 +384,7 @@ bneck_c3n1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // 4 staging boxes. TMEM: D2 2 x 128 columns + D3 N1 (= 256) columns.
 // Warps (416 threads): 0 producer (A2 + W3 ring), 1 conv3 issuer, 2 TMEM alloc + conv1' issuer, 3 store warp,
 // 4..11 epilogue, 12 W1n-ring producer.
-template <int K3_, int N3_, int N1_>
+template <int K3_, int N3_, int N1_, int NW3_ = 4, int NW1_ = 2, int NPOOL_ = 4>
 struct C3n1sCfg {
     static constexpr int K3 = K3_, N3 = N3_, N1 = N1_;
     static constexpr int KB3 = K3_ / 64;                      // K blocks of conv3
@@ -369,11 +397,11 @@ struct C3n1sCfg {
     static constexpr int W3_BLK_BYTES = 64 * 128;             // this CTA's 64 rows of one K block of a chunk
     static constexpr int KBS = 2;                             // K blocks per W3 ring stage (fine-grained ring:
     static constexpr int W3_STAGE_BYTES = KBS * W3_BLK_BYTES; //  more stages in flight for the same bytes)
-    static constexpr int NW3 = 4;
+    static constexpr int NW3 = NW3_;
     static_assert(KB3 % KBS == 0, "stage granularity");
     static constexpr int W1N_STAGE_BYTES = (N1_ / 2) * 128;   // this CTA's N1/2 rows of one K block
-    static constexpr int NW1 = 2;
-    static constexpr int NPOOL = 4;
+    static constexpr int NW1 = NW1_;
+    static constexpr int NPOOL = NPOOL_;
     static constexpr int TMEM_COLS = 512;
     static constexpr int D2_COL = 0, D3_COL = 256;
     static constexpr int NBAR = 2 + 2 * NW3 + 2 * NW1 + 4 + 2 + 4 * NPOOL;
@@ -386,6 +414,14 @@ struct C3n1sCfg {
 };
 using C3n1sL3 = C3n1sCfg<256, 1024, 256>;
 static_assert(C3n1sL3::SMEM_BYTES <= 232448, "smem budget");
+// The same 224 KB split differently (RNB_C3N1S_RINGS=1/2/3, tools/stem_ab.py A/B): the in-kernel timeline
+// (profiles/c3n1s_timeline_r1.md) shows the epilogue waiting on box_ready — residual loads take 2-4 k clocks under
+// load and only two of four boxes can be in flight — while the conv3 issuer waits on the epilogue, not on its ring.
+using C3n1sL3P5 = C3n1sCfg<256, 1024, 256, 3, 2, 5>;    // W3 ring 3 x 16 KB, five staging boxes
+using C3n1sL3W3P5 = C3n1sCfg<256, 1024, 256, 2, 3, 5>;  // W3 ring 2, W1n ring 3, five boxes
+using C3n1sL3P6 = C3n1sCfg<256, 1024, 256, 2, 2, 6>;    // W3 ring 2, six boxes
+static_assert(C3n1sL3P5::SMEM_BYTES <= 232448 && C3n1sL3W3P5::SMEM_BYTES <= 232448 && C3n1sL3P6::SMEM_BYTES <= 232448,
+              "smem budget");
 
 // Tensor maps: tmA t2 [M][K3] box rows 128; tmW3 [N3][K3] box rows 64; tmW1n [N1][N3] box rows N1/2;
 //              tmRes / tmY [M][N3] box rows 128; tmT1n [M][N1] box rows 128
@@ -541,19 +577,26 @@ bneck_c3n1s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint64_t w3_desc = umma_smem_desc(smem_u32(smem_w3), 0, 1024, UMMA_LAYOUT_SW128);
             int stage = 0;
             uint32_t phase = 0;
+            TL_DECL(1)
             for (int i = 0; i < T; ++i) {
+                TL_TILE(i)
+                TL(1)
                 mbar_wait(a_full, i & 1);
+                TL(2)
 #pragma unroll 1
                 for (int hc = 0; hc < NCHUNK / 2; ++hc) {  // chunk c = 2 * hc + hf lives in D2 half hf
 #pragma unroll 1
                     for (int hf = 0; hf < 2; ++hf) {
                         const int c = 2 * hc + hf;
                         // use number (NCHUNK / 2) * i + hc of this half (NCHUNK / 2 is even)
+                        TL(10 + c)
                         mbar_wait(hf == 0 ? &d2_empty[0] : &d2_empty[1], (hc & 1) ^ 1);
+                        TL(20 + c)
                         const uint32_t d_tmem = tmem_base + Cfg::D2_COL + hf * 128;
 #pragma unroll 1
                         for (int ks = 0; ks < KB3 / Cfg::KBS; ++ks) {
                             mbar_wait(&w3_full[stage], phase);
+                            TL(30 + c)
                             tc_fence_after();
                             if (elect_one()) {
                                 const uint64_t bs = w3_desc + static_cast<uint64_t>((stage * Cfg::W3_STAGE_BYTES) >> 4);
@@ -582,6 +625,7 @@ bneck_c3n1s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                 }
             }
+            TL_DUMP()
         }
     } else if (warp == 2) {
         // ===================================================== conv1' MMA issuer (leader CTA only)
@@ -592,13 +636,19 @@ bneck_c3n1s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             uint32_t cx_phase_bits = 0;
             int stage = 0;
             uint32_t phase = 0;
+            TL_DECL(2)
             for (int i = 0; i < T; ++i) {
+                TL_TILE(i)
+                TL(1)
                 mbar_wait(d3_empty, (i & 1) ^ 1);
+                TL(2)
 #pragma unroll 1
                 for (int b = 0; b < NBOX_Y; ++b) {
                     const int cs = (i * IPT + b) % NPOOL;
                     mbar_wait(&w1_full[stage], phase);
+                    TL(10 + b)
                     mbar_wait(&cx_full[cs], (cx_phase_bits >> cs) & 1);
+                    TL(30 + b)
                     cx_phase_bits ^= 1u << cs;
                     tc_fence_after();
                     if (elect_one()) {
@@ -620,6 +670,7 @@ bneck_c3n1s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                 }
             }
+            TL_DUMP()
         }
     } else if (warp == 3) {
         // ===================================================== store warp (both CTAs), see bneck_l1.cuh
@@ -638,19 +689,24 @@ bneck_c3n1s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         __syncwarp();
         uint32_t md_phase_bits = 0;
+        TL_DECL(3)
         auto recycle = [&](int item) {
             const int cs = item % NPOOL;
             if (item % IPT < NBOX_Y) {
                 mbar_wait(&c_mma_done[cs], (md_phase_bits >> cs) & 1);
                 md_phase_bits ^= 1u << cs;
             }
+            TL(90 + item % IPT)
             if (item + NPOOL < items && elect_one()) prepare(item + NPOOL);
             __syncwarp();
         };
         for (int item = 0; item < items; ++item) {
             const int cs = item % NPOOL;
             const int it_local = item / IPT, sub = item - it_local * IPT;
+            TL_TILE(it_local)
+            TL(10 + sub)
             mbar_wait(&c_full[cs], (item / NPOOL) & 1);
+            TL(40 + sub)
             if (elect_one()) {
                 const uint8_t* box = smem_pool + cs * Cfg::BOX_BYTES;
                 if (sub < NBOX_Y)
@@ -661,6 +717,7 @@ bneck_c3n1s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 tma_store_wait_read<1>();
             }
             __syncwarp();
+            TL(65 + sub)
             if (item > 0) recycle(item - 1);
         }
         if (elect_one()) tma_store_wait_read<0>();
@@ -668,6 +725,7 @@ bneck_c3n1s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (items > 0) recycle(items - 1);
         if (elect_one()) tma_store_wait_all<0>();
         __syncwarp();
+        TL_DUMP()
     } else if (warp >= 4 && warp < 12) {
         // ===================================================== epilogue (both CTAs)
         const int q4 = warp & 3;
@@ -677,13 +735,17 @@ bneck_c3n1s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
         const uint32_t row_off = static_cast<uint32_t>(row_in_tile) * 128;
 
+        TL_DECL(0)
         auto box_step = [&](int item, uint32_t col, const float* bias64, int has_res, bool to_mma) {
             const int cs = item % NPOOL;
+            TL(20 + item % IPT)
             mbar_wait(&box_ready[cs], (item / NPOOL) & 1);
+            TL(50 + item % IPT)
             uint32_t v[32];
             __syncwarp();
             tmem_ld_32x32(lane_base + col + h * 32, v);
             tmem_ld_wait();
+            TL(80 + item % IPT)
             epilogue_chunk<2>(v, smem_pool + cs * Cfg::BOX_BYTES + row_off, static_cast<uint32_t>(h * 4), swz,
                               bias64 + h * 32, has_res, 1);
             tc_fence_before();
@@ -693,30 +755,40 @@ bneck_c3n1s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 mbar_arrive(&c_full[cs]);
                 if (to_mma) mbar_arrive_leader(&cx_full[cs]);
             }
+            TL(110 + item % IPT)
         };
         for (int i = 0; i < T; ++i) {
+            TL_TILE(i)
 #pragma unroll 1
             for (int hc = 0; hc < NCHUNK / 2; ++hc) {
                 // half 0: chunk 2 hc
+                TL(1)
                 mbar_wait(&d2_full[0], hc & 1);
+                TL(2)
                 tc_fence_after();
                 box_step(i * IPT + 4 * hc, Cfg::D2_COL, prm.bias3 + hc * 256, 1, true);
                 box_step(i * IPT + 4 * hc + 1, Cfg::D2_COL + 64, prm.bias3 + hc * 256 + 64, 1, true);
                 if (lane == 0) mbar_arrive_leader(&d2_empty[0]);
                 // half 1: chunk 2 hc + 1
+                TL(3)
                 mbar_wait(&d2_full[1], hc & 1);
+                TL(4)
                 tc_fence_after();
                 box_step(i * IPT + 4 * hc + 2, Cfg::D2_COL + 128, prm.bias3 + hc * 256 + 128, 1, true);
                 box_step(i * IPT + 4 * hc + 3, Cfg::D2_COL + 192, prm.bias3 + hc * 256 + 192, 1, true);
                 if (lane == 0) mbar_arrive_leader(&d2_empty[1]);
             }
+            TL(5)
             mbar_wait(d3_full, i & 1);
+            TL(6)
             tc_fence_after();
 #pragma unroll 1
             for (int jb = 0; jb < NBOX_T; ++jb)
                 box_step(i * IPT + NBOX_Y + jb, Cfg::D3_COL + jb * 64, prm.bias1n + jb * 64, 0, false);
             if (lane == 0) mbar_arrive_leader(d3_empty);
+            TL(7)
         }
+        TL_DUMP()
     }
 
     tc_fence_before();

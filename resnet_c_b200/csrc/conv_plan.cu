@@ -78,6 +78,15 @@ cudaError_t conv_kernels_init() {
     if ((e = cudaFuncSetAttribute(bneck_c3n1s_kernel<C3n1sL3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C3n1sL3::SMEM_BYTES)) != cudaSuccess)
         return e;
+    if ((e = cudaFuncSetAttribute(bneck_c3n1s_kernel<C3n1sL3P5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C3n1sL3P5::SMEM_BYTES)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncSetAttribute(bneck_c3n1s_kernel<C3n1sL3W3P5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C3n1sL3W3P5::SMEM_BYTES)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncSetAttribute(bneck_c3n1s_kernel<C3n1sL3P6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C3n1sL3P6::SMEM_BYTES)) != cudaSuccess)
+        return e;
     if ((e = cudaFuncSetAttribute(bneck_c3n1_kernel<C3n1Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C3n1Cfg::SMEM_BYTES)) != cudaSuccess)
         return e;
@@ -422,10 +431,31 @@ static cudaError_t launch2(const ConvPlan& p, cudaStream_t stream) {
                       p.tmOut, p.tmRes, p.bias, p.g);
 }
 
+#ifdef RNB_TIMELINE
+// tools/c3n1s_timeline.py: copies the in-kernel timeline of the last bneck_c3n1s launch to the host
+extern "C" int rnb_debug_read_timeline(long long* host, int* counts) {
+    if (cudaMemcpyFromSymbol(counts, g_c3n1s_tl_n, 4 * sizeof(int)) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(host, g_c3n1s_tl, 4 * kTlMax * sizeof(long long)) != cudaSuccess) return -1;
+    return kTlMax;
+}
+#endif
+
 cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
-    if (p.bneck == 4)
+    if (p.bneck == 4) {
+        // how the 224 KB of shared memory are split between the weight rings and the staging boxes (bit-identical)
+        static const int rings = getenv("RNB_C3N1S_RINGS") ? atoi(getenv("RNB_C3N1S_RINGS")) : 0;
+        if (rings == 1)
+            return launch_pdl(bneck_c3n1s_kernel<C3n1sL3P5>, p.grid, C3n1sL3P5::THREADS, C3n1sL3P5::SMEM_BYTES, stream,
+                              p.tmA, p.tmB, p.tmW1n, p.tmRes, p.tmOut, p.tmT1n, p.cp, p.cg);
+        if (rings == 2)
+            return launch_pdl(bneck_c3n1s_kernel<C3n1sL3W3P5>, p.grid, C3n1sL3W3P5::THREADS, C3n1sL3W3P5::SMEM_BYTES,
+                              stream, p.tmA, p.tmB, p.tmW1n, p.tmRes, p.tmOut, p.tmT1n, p.cp, p.cg);
+        if (rings == 3)
+            return launch_pdl(bneck_c3n1s_kernel<C3n1sL3P6>, p.grid, C3n1sL3P6::THREADS, C3n1sL3P6::SMEM_BYTES, stream,
+                              p.tmA, p.tmB, p.tmW1n, p.tmRes, p.tmOut, p.tmT1n, p.cp, p.cg);
         return launch_pdl(bneck_c3n1s_kernel<C3n1sL3>, p.grid, C3n1sL3::THREADS, C3n1sL3::SMEM_BYTES, stream, p.tmA, p.tmB,
                           p.tmW1n, p.tmRes, p.tmOut, p.tmT1n, p.cp, p.cg);
+    }
     if (p.bneck == 3)
         return launch_pdl(bneck_c3n1_kernel<C3n1Cfg>, p.grid, C3n1Cfg::THREADS, C3n1Cfg::SMEM_BYTES, stream, p.tmA, p.tmB,
                           p.tmW1n, p.tmRes, p.tmOut, p.tmT1n, p.cp, p.cg);
