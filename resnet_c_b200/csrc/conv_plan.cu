@@ -102,6 +102,18 @@ cudaError_t conv_kernels_init() {
     return cudaSuccess;
 }
 
+// Persistent CTA pairs: with RNB_BALANCE (bit mask: 1 fused layer2/3 tails, 2 fused layer1 tails, 4 generic pair convs,
+// 8 TF32 halo convs) the grid is shrunk to ceil(tiles / waves) pairs so that every pair runs the same number of tiles
+// (196 tiles: 66 pairs x 3 instead of 48 x 3 + 26 x 2) — the same critical path with less HBM contention per wave.
+static int pair_count(int tiles, int num_sms, int bit) {
+    const int max_pairs = num_sms / 2;
+    if (tiles <= max_pairs) return tiles;
+    const int mask = getenv("RNB_BALANCE") ? atoi(getenv("RNB_BALANCE")) : 0;
+    if (!(mask & bit)) return max_pairs;
+    const int waves = (tiles + max_pairs - 1) / max_pairs;
+    return (tiles + waves - 1) / waves;
+}
+
 static int fail(char* err, int errlen, const char* msg, int code) {
     if (err && errlen > 0) snprintf(err, errlen, "%s (code %d)", msg, code);
     return code ? code : -1;
@@ -163,7 +175,7 @@ static int halo2_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, char*
     g.relu = d.relu ? 1 : 0;
     g.has_res = d.residual ? 1 : 0;
     g.reverse = d.reverse ? 1 : 0;
-    const int pairs = g.tiles < num_sms / 2 ? g.tiles : num_sms / 2;
+    const int pairs = pair_count(g.tiles, num_sms, 8);
     plan->grid = 2 * pairs;
     const double M = 1.0 * d.B * d.H * d.W;
     plan->flops = 2.0 * M * 64 * 576;
@@ -207,7 +219,7 @@ int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, 
     plan->bp.bias2 = d.bias2;
     plan->bp.bias3 = d.bias3;
     plan->bp.bias1n = d.bias1n ? d.bias1n : d.bias2;
-    const int pairs = g.tiles < num_sms / 2 ? g.tiles : num_sms / 2;
+    const int pairs = pair_count(g.tiles, num_sms, 2);
     plan->grid = 2 * pairs;
     const double M = 1.0 * d.B * d.H * d.W;
     const double macs = 64.0 * 576 + 256.0 * 64 + (d.wds ? 256.0 * 64 : 0.0) + (d.w1n ? 1.0 * n1 * 256 : 0.0);
@@ -254,6 +266,7 @@ int c3n1_plan_init(ConvPlan* plan, const C3n1Desc& d, int num_sms, char* err, in
     if (!c3n1_shape_ok(d.K3, d.N3, d.N1)) return fail(err, errlen, "c3n1_plan: unsupported channel counts", -7);
     const bool streamed = d.K3 != 128;
     plan->bneck = streamed ? 4 : 3;
+    plan->rings = getenv("RNB_C3N1S_RINGS") ? atoi(getenv("RNB_C3N1S_RINGS")) : 0;
     plan->bn = 128;
     plan->esz = 2;
     plan->ctas = 2;
@@ -262,7 +275,7 @@ int c3n1_plan_init(ConvPlan* plan, const C3n1Desc& d, int num_sms, char* err, in
     plan->cg.reverse = d.reverse ? 1 : 0;
     plan->cp.bias3 = d.bias3;
     plan->cp.bias1n = d.bias1n;
-    const int pairs = plan->cg.tiles < num_sms / 2 ? plan->cg.tiles : num_sms / 2;
+    const int pairs = pair_count(plan->cg.tiles, num_sms, 1);
     plan->grid = 2 * pairs;
     const double M = d.M;
     const double wel = 1.0 * d.N3 * d.K3 + 1.0 * d.N1 * d.N3;
@@ -361,7 +374,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     plan->ctas = ctas;
     const int tiles = g.m_tiles * g.n_tiles;
     if (ctas == 2) {
-        const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+        const int pairs = pair_count(tiles, num_sms, 4);
         plan->grid = 2 * pairs;
     } else {
         plan->grid = tiles < num_sms ? tiles : num_sms;
@@ -443,7 +456,7 @@ extern "C" int rnb_debug_read_timeline(long long* host, int* counts) {
 cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
     if (p.bneck == 4) {
         // how the 224 KB of shared memory are split between the weight rings and the staging boxes (bit-identical)
-        static const int rings = getenv("RNB_C3N1S_RINGS") ? atoi(getenv("RNB_C3N1S_RINGS")) : 0;
+        const int rings = p.rings;
         if (rings == 1)
             return launch_pdl(bneck_c3n1s_kernel<C3n1sL3P5>, p.grid, C3n1sL3P5::THREADS, C3n1sL3P5::SMEM_BYTES, stream,
                               p.tmA, p.tmB, p.tmW1n, p.tmRes, p.tmOut, p.tmT1n, p.cp, p.cg);

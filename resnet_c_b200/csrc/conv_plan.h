@@ -70,6 +70,7 @@ struct ConvPlan {
                   // 3 = conv3 + next conv1 (bneck_c3n1.cuh; geometry in cg / cp), resident weights (layer2 shape),
                   // 4 = the same with streamed weights (layer3 shape),
                   // 5 = fused layer1 tail with residual tensor + the NEXT LAYER's conv1 (256 -> 128)
+    int rings;    // bneck == 4: shared-memory split of bneck_c3n1s_kernel (RNB_C3N1S_RINGS at plan time, 0 = default)
     C3n1Geom cg;
     C3n1Params cp;
     BneckGeom bg;

@@ -297,6 +297,23 @@ def test_tf32_halo_pair_kernel_equals_generic_kernel(monkeypatch, arch, batch):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("arch,batch", [("resnet50", 128), ("resnet50", 101)])
+def test_scheduling_switches_are_bit_identical(monkeypatch, arch, batch):
+    """RNB_C3N1S_RINGS (how bneck_c3n1s_kernel splits its 224 KB of shared memory between weight rings and staging
+    boxes) and RNB_BALANCE (persistent pair grids shrunk to equal tile counts per pair, conv_plan.cu::pair_count)
+    change scheduling only: logits, top-1 and block outputs must be BIT-IDENTICAL. The batch is large enough for
+    layer3 to run more pair tiles (98 / 78) than there are SM pairs, so rings wrap and the balanced grid differs."""
+    names = ("layer2.3", "layer3.0", "layer3.5", "layer4.2")
+    base = _run_with_env(monkeypatch, {"RNB_FUSE": "1", "RNB_FUSE_NEXT": "1"}, arch, batch, names)
+    for env in ({"RNB_C3N1S_RINGS": "1"}, {"RNB_C3N1S_RINGS": "2"}, {"RNB_C3N1S_RINGS": "3"}, {"RNB_BALANCE": "15"}):
+        got = _run_with_env(monkeypatch, {"RNB_FUSE": "1", "RNB_FUSE_NEXT": "1", **env}, arch, batch, names)
+        for n in names:
+            assert torch.equal(got[2][n], base[2][n]), f"{n} differs ({env})"
+        assert torch.equal(got[0], base[0]) and torch.equal(got[1], base[1]), env
+        for k in env:
+            monkeypatch.delenv(k)
+
+
 def test_launch_accounting(monkeypatch):
     monkeypatch.setenv("RNB_FUSE", "0")
     model = _model("resnet50", True, "bf16", 64, chunk=16)
