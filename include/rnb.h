@@ -117,6 +117,11 @@ double rnb_model_flops_per_image(const rnb_model_t* m);
 int rnb_model_profile(rnb_model_t* m, const float* x_dev, int batch, int iters, int* kind_out,
                       float* ms_out, double* flops_out, double* bytes_out, int max_entries,
                       int* n_entries, void* stream);
+/* Profiling aid (energy per launch, tools/energy_profile.py): enqueue conv launch `index` (0-based among the
+ * kind-2 entries of rnb_model_profile) of the plan for `batch` images `repeat` times back to back on `stream`, on the
+ * buffers of the last forward / profile pass. No synchronisation. Results of a later forward are unaffected (every
+ * launch rewrites its own output from unchanged inputs). */
+int rnb_model_repeat_launch(rnb_model_t* m, int batch, int index, int repeat, void* stream);
 /* Copy an intermediate activation of the LAST forward (chunk 0) to `out_dev` as float32 NCHW.
  * `name` is "stem" | "maxpool" | "layer{L}.{i}" (block output) | "avgpool". Returns the element
  * count through *numel (call with out_dev = NULL to query). Debug / parity use only. */

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "rnb_model_profile": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(C.c_int), _f32p,
                                     C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
                                     C.POINTER(C.c_int), _vp]),
+    "rnb_model_repeat_launch": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
     "rnb_model_get_activation": (C.c_int, [_vp, C.c_char_p, _vp, C.POINTER(C.c_int64), _vp]),
     "rnb_conv_bn_act_forward": (C.c_int, [_vp] * 8 + [C.c_int] * 10 + [_vp]),
     "rnb_stem_forward": (C.c_int, [_vp] * 7 + [C.c_int] * 4 + [_vp]),

@@ -225,6 +225,14 @@ int rnb_model_profile(rnb_model_t* m, const float* x_dev, int batch, int iters, 
                            n_entries, static_cast<cudaStream_t>(stream));
 }
 
+int rnb_model_repeat_launch(rnb_model_t* m, int batch, int index, int repeat, void* stream) {
+    if (!m) {
+        set_error("rnb_model_repeat_launch: NULL model");
+        return RNB_ERR_INVALID;
+    }
+    return m->impl.repeat_launch(batch, index, repeat, static_cast<cudaStream_t>(stream));
+}
+
 int rnb_model_get_activation(rnb_model_t* m, const char* name, float* out_dev, int64_t* numel,
                              void* stream) {
     if (!m || !name) {

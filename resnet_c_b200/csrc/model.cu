@@ -975,6 +975,21 @@ int Model::forward_any(const float* x, const uint8_t* x_u8, int batch, float* lo
     return RNB_OK;
 }
 
+int Model::repeat_launch(int batch, int index, int repeat, cudaStream_t s) {
+    if (batch <= 0 || batch > max_batch || repeat <= 0) {
+        set_error("repeat_launch: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    ChunkPlan* pp = plan_for(std::min(chunk, batch));
+    if (!pp) return RNB_ERR_CUDA;
+    if (index < 0 || index >= static_cast<int>(pp->convs.size())) {
+        set_error("repeat_launch: launch index out of range");
+        return RNB_ERR_INVALID;
+    }
+    for (int i = 0; i < repeat; ++i) RNB_CUDA(conv_plan_launch(pp->convs[index], s));
+    return RNB_OK;
+}
+
 int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, double* flops,
                    double* bytes, int max_entries, int* n_entries, cudaStream_t s) {
     if (batch <= 0 || batch > max_batch || iters <= 0 || !x || !n_entries) {

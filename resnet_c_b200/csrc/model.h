@@ -155,6 +155,7 @@ struct Model {
     int submit_host_u8(int slot, const uint8_t* x, int batch, float* logits, int32_t* top1);
     int submit_host_any(int slot, const void* x, bool u8, int batch, float* logits, int32_t* top1);
     int wait_host(int slot);
+    int repeat_launch(int batch, int index, int repeat, cudaStream_t s);
     int profile(const float* x, int batch, int iters, int* kind, float* ms, double* flops,
                 double* bytes, int max_entries, int* n_entries, cudaStream_t s);
     // stem pre-pass/conv + stem/max-pool + planned conv launches + avg-pool + fc + arg-max

@@ -314,6 +314,10 @@ class ResNet:
         return [dict(kind=self.KINDS[kind[i]], ms=ms[i], flops=flops[i], bytes=nbytes[i])
                 for i in range(n.value)]
 
+    def repeat_launch(self, batch: int, index: int, repeat: int) -> None:
+        """Enqueue conv launch `index` of the plan for `batch` images `repeat` times (profiling aid, no sync)."""
+        check(_lib.lib().rnb_model_repeat_launch(self._h, batch, index, repeat, _stream()))
+
     def activation(self, name: str) -> torch.Tensor:
         """Intermediate activation of the last forward (first chunk) as fp32 NCHW (flat)."""
         n = C.c_int64()
