@@ -191,8 +191,10 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version / debug lines to stdout by default; stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries exactly one JSON line: NCCL_DEBUG=VERSION (set on the GPU boxes) makes NCCL print its version
+        # there, whatever NCCL_DEBUG_FILE says; a level the user asked for on purpose (WARN / INFO) is left alone
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     B = args.batch
