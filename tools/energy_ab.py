@@ -14,9 +14,10 @@ from resnet_c_b200 import engine, weights  # noqa: E402
 arch = sys.argv[1] if len(sys.argv) > 1 else "resnet50"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 seconds = float(sys.argv[3]) if len(sys.argv) > 3 else 4.0
+dtype = sys.argv[4] if len(sys.argv) > 4 else "bf16"
 pynvml.nvmlInit()
 h = pynvml.nvmlDeviceGetHandleByIndex(0)
-m = engine.ResNet(arch, weights.cached_weights_dir(arch, 0, True), dtype="bf16", max_batch=B)
+m = engine.ResNet(arch, weights.cached_weights_dir(arch, 0, True), dtype=dtype, max_batch=B)
 x = weights.synthetic_images(B).cuda()
 logits, top1 = m.forward(x)
 for _ in range(20):
@@ -40,6 +41,6 @@ torch.cuda.synchronize()
 j1 = pynvml.nvmlDeviceGetTotalEnergyConsumption(h)
 ms = e0.elapsed_time(e1)
 joules = (j1 - j0) / 1e3
-print(f"{arch} B={B}: {steps} steps, {ms / steps:.4f} ms/step, {joules / steps:.4f} J/step, {joules / (ms / 1e3):.0f} W average "
+print(f"{arch} {dtype} B={B}: {steps} steps, {ms / steps:.4f} ms/step, {joules / steps:.4f} J/step, {joules / (ms / 1e3):.0f} W average "
       f"(enforced limit {limit_w:.0f} W), {joules / steps / B * 1e3:.3f} mJ/image, SM clock {min(clocks)}-{max(clocks)} MHz, "
       f"reasons 0x{reasons:x}")
