@@ -129,22 +129,38 @@ def cpu_oracle_throughput(arch: str, sample_batch: int, iters: int, warmup: int 
     return sample_batch / med, cores, med
 
 
+def per_gpu_batch(args, world: int, rank: int) -> int:
+    """Images this rank forwards per step. weak: --batch on every rank (BASELINE configs[2] at any N);
+    strong: --global-batch sharded by image (configs[3]: 2048 -> 1024 / 512 / 256 per GPU at N = 2 / 4 / 8)."""
+    if args.scaling == "weak":
+        return args.batch
+    from resnet_c_b200 import dist as rdist
+    lo, hi = rdist.shard_bounds(args.global_batch, world, rank)
+    return hi - lo
+
+
+def metric_name(args, B: int) -> str:
+    if args.scaling == "strong":
+        return f"{args.arch} inference images/sec @ global batch {args.global_batch} sharded over the GPUs"
+    return f"{args.arch} inference images/sec @ batch {B} per GPU"
+
+
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path, on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     sample = args.cpu_sample
-    # bound the whole run to a few minutes whatever K is
-    value, cores, med = cpu_oracle_throughput(args.arch, sample, max(1, min(args.steps, 10)),
-                                              max(1, min(args.warmup, 2)))
+    # --steps / --warmup are honoured as given: one step is a bounded sample (default 32 images, ~0.4 s on 16
+    # cores), so the driver's K = 20..50 still ends within a minute
+    value, cores, med = cpu_oracle_throughput(args.arch, sample, max(1, args.steps), max(0, args.warmup))
     unit = "images/s"
     line = {
         "impl": "reference",
-        "metric": f"{args.arch} inference images/sec @ batch {args.batch} per GPU",
-        "value": value, "unit": unit, "n_gpus": args.gpus, "steps": max(1, min(args.steps, 10)),
-        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": med * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "metric": metric_name(args, per_gpu_batch(args, 1 if args.scaling == "weak" else max(1, args.gpus), 0)),
+        "value": value, "unit": unit, "n_gpus": args.gpus, "steps": max(1, args.steps),
+        "warmup": max(0, args.warmup), "ms_per_step": med * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.arch} fp32 inference, {sample}-image sample of the "
                                f"batch-{args.batch} synthetic 224x224 workload, CPU",
                    "per_gpu_batch": args.batch},
@@ -158,6 +174,39 @@ def run_reference(args):
     return 0
 
 
+def oracle_parity(arch, dtype, x_host, logits_dev, top1_dev, n_sample=8):
+    """Sampled comparison of THIS rank's actual batch and weights with the oracle (CPU, the reference's PyTorch path
+    restated, fp32) — the reference's only check is top-1 (cuda/inference/main.cu:243-251 vs pytorch_inference.py:172).
+    An fp64 run of the oracle arbitrates near-ties: top-1 is counted as `decided` where the fp64 top-1 / top-2 margin
+    exceeds twice the logit tolerance of the path (random-init nets have near-ties)."""
+    import numpy as np
+    import torch
+
+    from oracle import torch_model
+    from resnet_c_b200 import weights
+
+    tol = 2e-2 if dtype == "bf16" else 1e-3
+    B = x_host.shape[0]
+    n = min(n_sample, B)
+    idx = sorted({int(round(i * (B - 1) / max(1, n - 1))) for i in range(n)})
+    sd = weights.make_state_dict(arch, 0)
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    xs = x_host[idx]
+    ref32 = torch_model.run(arch, sd, xs).numpy().astype(np.float64)
+    ref64 = torch_model.run(arch, sd, xs, dtype=torch.float64).numpy()
+    got = logits_dev[idx].float().cpu().numpy().astype(np.float64)
+    got_top1 = top1_dev[idx].cpu().numpy()
+    scale = np.abs(ref32).max(axis=1)
+    rel = float((np.abs(got - ref32).max(axis=1) / scale).max())
+    srt = np.sort(ref64, axis=1)
+    margin = (srt[:, -1] - srt[:, -2]) / np.abs(ref64).max(axis=1)
+    decided = margin > 2 * tol
+    agree = int((got_top1[decided] == ref64.argmax(1)[decided]).sum())
+    return {"images": len(idx), "rel_err": rel, "tol": tol, "top1_decided": int(decided.sum()), "top1_agree": agree,
+            "top1_agree_all": int((got_top1 == ref32.argmax(1)).sum()), "min_margin_rel": float(margin.min()),
+            "argmax_self_consistent": bool((got_top1 == got.argmax(1)).all())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,16 +215,20 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--arch", default="resnet50")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: --global-batch images sharded over the ranks (BASELINE configs[3])")
+    ap.add_argument("--global-batch", type=int, default=2048, help="total images per step with --scaling strong")
     ap.add_argument("--chunk", type=int, default=0, help="images pushed through the net at a time (0 = default)")
     ap.add_argument("--cpu-sample", type=int, default=32, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle comparison")
     ap.add_argument("--profile-out", default="", help="write the per-launch table (JSON) here")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
         return run_reference(args)
+    args.warmup = max(args.warmup, 3)
 
     import torch
 
@@ -197,20 +250,24 @@ def main():
             del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    B = args.batch
+    B = per_gpu_batch(args, world, rank)           # this rank's images per step
+    Bmax = per_gpu_batch(args, world, 0)           # largest shard (rank 0 takes the remainder first)
+    total_images = args.global_batch if args.scaling == "strong" else world * B
     wdir = weights.cached_weights_dir(args.arch, 0, root=f"/tmp/rnb_cache_rank{local_rank}" if world > 1 else None)
-    model = engine.ResNet(args.arch, wdir, dtype=args.dtype, max_batch=B, chunk=args.chunk, device=local_rank)
+    model = engine.ResNet(args.arch, wdir, dtype=args.dtype, max_batch=Bmax, chunk=args.chunk, device=local_rank)
     classes = model.num_classes
     dev = torch.device("cuda", local_rank)
     # every rank gets its own slice of the global synthetic batch
-    x = weights.synthetic_images(B, seed=1234 + rank).to(dev)
+    x_host = weights.synthetic_images(B, seed=1234 + rank)
+    x = x_host.to(dev)
     # logits [B, classes] fp32 and top-1 [B] int32 live back to back in ONE buffer per step parity, so the
     # per-step exchange is a single NCCL all-gather (4 * B * (classes + 1) bytes per rank). Two parities:
-    # the gather of step i runs on a side stream while the replica already computes step i+1.
-    per_rank = B * classes + B
-    outs = [torch.empty(per_rank, device=dev, dtype=torch.float32) for _ in range(2)]
+    # the gather of step i runs on a side stream while the replica already computes step i+1. Ragged shards
+    # (strong scaling, global batch not divisible) are padded to the largest shard for the collective.
+    per_rank = Bmax * classes + Bmax
+    outs = [torch.zeros(per_rank, device=dev, dtype=torch.float32) for _ in range(2)]
     logits_v = [o[:B * classes].view(B, classes) for o in outs]
-    top1_v = [o[B * classes:].view(torch.int32) for o in outs]
+    top1_v = [o[Bmax * classes:Bmax * classes + B].view(torch.int32) for o in outs]
     logits, top1 = logits_v[0], top1_v[0]
     if world > 1:
         gathered = [torch.empty(world * per_rank, device=dev, dtype=torch.float32) for _ in range(2)]
@@ -238,6 +295,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v: float) -> float:
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     for _ in range(args.warmup):
         step()
     barrier()
@@ -253,17 +316,50 @@ def main():
         torch.cuda.current_stream().wait_stream(comm_stream)  # the last gathers are inside the timed region
     e1.record()
     barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = t.item()
     ms_per_step = ms_total / args.steps
-    value = world * B / (ms_per_step * 1e-3)
+    value = total_images / (ms_per_step * 1e-3)
+
+    # ---- did the exchange deliver? Every rank's gathered buffer must hold, in slice r, bit for bit what rank r
+    # computed (its own slice is checked against its own output buffer; the whole buffer against rank 0's copy), for
+    # both step parities. Ranks forward different images (seed 1234 + rank), so equal slices would mean aliasing.
+    gather_ok = None
+    if world > 1:
+        bad = torch.zeros(1, device=dev, dtype=torch.int64)
+        for par in range(2):
+            mine = gathered[par][rank * per_rank:(rank + 1) * per_rank]
+            bad += (mine.view(torch.int32) != outs[par].view(torch.int32)).sum()
+            ref0 = gathered[par].clone()
+            dist.broadcast(ref0, src=0)
+            bad += (ref0.view(torch.int32) != gathered[par].view(torch.int32)).sum()
+            if rank > 0:  # another rank's logits in my slot would be an offset bug
+                other = gathered[par][:per_rank]
+                bad += int(torch.equal(other.view(torch.int32), mine.view(torch.int32)))
+        dist.all_reduce(bad, op=dist.ReduceOp.SUM)
+        gather_ok = bool(bad.item() == 0)
+
+    # ---- parity of this very batch / these very weights against the oracle (sampled), in the bench line
+    parity = None
+    if not args.no_parity:
+        pr = oracle_parity(args.arch, args.dtype, x_host, logits, top1)
+        if world > 1:
+            t = torch.tensor([pr["rel_err"], -pr["min_margin_rel"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            c = torch.tensor([pr["images"], pr["top1_decided"], pr["top1_agree"], pr["top1_agree_all"],
+                              int(pr["argmax_self_consistent"])], device=dev, dtype=torch.int64)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            pr.update(rel_err=t[0].item(), min_margin_rel=-t[1].item(), images=int(c[0]), top1_decided=int(c[1]),
+                      top1_agree=int(c[2]), top1_agree_all=int(c[3]), argmax_self_consistent=bool(c[4] == world))
+        pr["ok"] = bool(pr["rel_err"] < pr["tol"] and pr["top1_agree"] == pr["top1_decided"]
+                        and pr["argmax_self_consistent"])
+        pr["what"] = (f"{pr['images']} images sampled evenly from every rank's own batch, seed-0 default-init weights, "
+                      f"vs oracle/torch_model.py fp32 on CPU (rel_err = max|d|/max|y| per image, worst image); "
+                      f"top-1 compared where the oracle's fp64 margin > 2*tol")
+        parity = pr
 
     # ---- end to end through host buffers (H2D + forward + D2H inside the timed region)
-    xh = weights.synthetic_images(B, seed=1234 + rank).pin_memory()
+    xh = x_host.pin_memory()
     lh = torch.empty(B, classes, dtype=torch.float32).pin_memory()
     th = torch.empty(B, dtype=torch.int32).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
@@ -274,11 +370,7 @@ def main():
     for _ in range(e2e_steps):
         model.forward_host(xh, lh, th)   # synchronous: returns with the results on the host
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_sync_value = world * B * e2e_steps / t.item()
+    e2e_sync_value = total_images * e2e_steps / max_over_ranks(time.perf_counter() - t0)
     same = bool((th.to(dev) == top1).all().item())
 
     # ---- the same end-to-end work as a serving loop: two host batches in flight (submit / wait), so
@@ -298,11 +390,7 @@ def main():
         model.submit_host(i & 1, xh2[i & 1], lh2[i & 1], th2[i & 1])
         model.wait_host((i - 1) & 1)          # results of step i-1 are on the host from here on
     model.wait_host((e2e_steps - 1) & 1)
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / t.item()
+    e2e_value = total_images * e2e_steps / max_over_ranks(time.perf_counter() - t0)
     same = same and bool((th2[0].to(dev) == top1).all().item())
 
     # ---- the same serving loop fed with DECODED uint8 HWC images (rnb_model_submit_host_u8): the /255 +
@@ -322,27 +410,27 @@ def main():
             model.submit_host_u8(i & 1, xu[i & 1], lh2[i & 1], th2[i & 1])
             model.wait_host((i - 1) & 1)
         model.wait_host((e2e_steps - 1) & 1)
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_u8 = {"value": world * B * e2e_steps / t.item(), "unit": "images/s",
+        e2e_u8 = {"value": total_images * e2e_steps / max_over_ranks(time.perf_counter() - t0), "unit": "images/s",
                   "h2d_bytes_per_step": B * 3 * 224 * 224, "d2h_bytes_per_step": B * classes * 4 + B * 4,
                   "mode": "rnb_model_submit_host_u8 / rnb_model_wait_host: uint8 HWC host input, normalisation "
                           "fused into the stem pre-pass"}
 
-    # ---- roofline of the dominant kernel, measured live with CUDA events (no graph)
+    # ---- per-launch table of one step, measured live with CUDA events between launches (no graph): kind, time,
+    # algorithmic FLOPs and bytes, and the launch's own roof max(FLOP / burst tensor peak, bytes / HBM peak)
     peaks, peak_kind = load_peaks()
+    burst = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
+    sus_peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
+    hbm = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
+    tf = 0.5 if args.dtype == "tf32" else 1.0     # TF32 peak not measured: half of BF16 assumed, and said so
     prof = model.profile(x, iters=3)
     chunk_n = min(B, args.chunk) if args.chunk > 0 else min(B, int(os.environ.get("RNB_CHUNK", "0") or B))
+    for p in prof:
+        p["us"] = p.pop("ms") * 1e3
+        p["ideal_us"] = max(p["flops"] / (burst * tf * 1e12), p["bytes"] / (hbm * 1e9)) * 1e6
     conv = [p for p in prof if p["kind"] == "conv_igemm"]
-    conv_ms = sum(p["ms"] for p in conv)
+    conv_us = sum(p["us"] for p in conv)
     conv_flops = sum(p["flops"] for p in conv)
-    chunk_ms = sum(p["ms"] for p in prof)
-    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
-    if args.dtype == "tf32":
-        peak *= 0.5
+    chunk_us = sum(p["us"] for p in prof)
     traffic = None
     tpath = ROOT / "profiles" / "traffic.json"
     if tpath.exists():
@@ -350,18 +438,30 @@ def main():
             traffic = json.loads(tpath.read_text()).get(f"{args.arch}_{args.dtype}_b{B}")
         except Exception:
             traffic = None
+    # Like for like: `achieved` is the whole step as timed above (CUDA-graph replay, `value`) in algorithmic
+    # FLOP/s, against the BURST peak (the timed region is a ~0.1 s burst); the sustained leg below divides the
+    # seconds-long replay by the SUSTAINED peak. The un-graphed per-launch table explains the step, it is not the step.
+    step_tflops = value / world * model.flops_per_image / 1e12
     roofline = {
         "bound": "tensor",
-        "kernel": "tcgen05 conv launches of one step (conv_igemm / conv_igemm2 / conv3x3_halo / bneck_l1 / bneck_c3n1 kernels)",
-        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-        "peak_source": f"{peak_kind} bf16_tflops_sustained" + (" x 0.5 (tf32 assumed)" if args.dtype == "tf32" else ""),
+        "kernel": "the whole forward step as replayed from the CUDA graph (tcgen05 conv launches are "
+                  f"{conv_us / chunk_us:.0%} of its un-graphed launch time)" if chunk_us else "whole step",
+        "achieved": step_tflops, "peak": burst * tf, "unit": "TFLOP/s", "frac": step_tflops / (burst * tf),
+        "peak_source": f"{peak_kind} bf16_tflops (burst)" + (" x 0.5 (tf32 assumed)" if args.dtype == "tf32" else ""),
         "traffic": traffic,
-        "kernel_share_of_step": conv_ms / chunk_ms if chunk_ms else None,
-        "whole_net_tflops": value / world * model.flops_per_image / 1e12,
-        "whole_net_frac_of_burst": value / world * model.flops_per_image / 1e12 / float(peaks.get("bf16_tflops", 1590.0)),
+        "flops_per_image": model.flops_per_image,
+        "conv_launches": {"tflops": conv_flops / (conv_us * 1e-6) / 1e12 if conv_us else None,
+                          "frac_of_burst": conv_flops / (conv_us * 1e-6) / 1e12 / (burst * tf) if conv_us else None,
+                          "share_of_step": conv_us / chunk_us if chunk_us else None,
+                          "sum_us": conv_us, "sum_ideal_us": sum(p["ideal_us"] for p in conv),
+                          "how": "CUDA events between un-graphed launches, 3 passes (rnb_model_profile)"},
+        "step_sum_us_ungraphed": chunk_us, "step_sum_ideal_us": sum(p["ideal_us"] for p in prof),
     }
     if args.profile_out and rank == 0:
-        Path(args.profile_out).write_text(json.dumps({"chunk": chunk_n, "launches": prof}, indent=1))
+        Path(args.profile_out).write_text(json.dumps({
+            "arch": args.arch, "dtype": args.dtype, "batch": B, "chunk": chunk_n, "peaks": {
+                "bf16_tflops_burst": burst, "hbm_gbs": hbm, "tf32_factor": tf, "source": peak_kind},
+            "graph_step_us": ms_per_step * 1e3, "launches": prof}, indent=1))
 
     # ---- sustained operation: the timed region above is ~0.1 s, short enough to run before the board's power controller
     # pulls the clocks down; a B200 replaying this step draws its full 1000 W limit, and after a second the step time is
@@ -389,8 +489,12 @@ def main():
         j1 = pynvml.nvmlDeviceGetTotalEnergyConsumption(nv)
         sus_ms = s0.elapsed_time(s1) / n_sus
         joules = (j1 - j0) / 1e3 / n_sus
+        sus_tflops = B / (sus_ms * 1e-3) * model.flops_per_image / 1e12
         sustained = {"seconds": 1.5, "steps": n_sus, "ms_per_step": sus_ms, "value_per_gpu": B / (sus_ms * 1e-3),
-                     "unit": "images/s", "j_per_step": joules, "mj_per_image": joules / B * 1e3,
+                     "unit": "images/s", "tflops": sus_tflops, "peak": sus_peak * tf,
+                     "frac": sus_tflops / (sus_peak * tf), "peak_source": f"{peak_kind} bf16_tflops_sustained",
+                     "frac_of_burst": sus_tflops / (burst * tf),
+                     "j_per_step": joules, "mj_per_image": joules / B * 1e3,
                      "avg_w": joules / (sus_ms * 1e-3),
                      "power_limit_w": pynvml.nvmlDeviceGetEnforcedPowerLimit(nv) / 1e3,
                      "sm_mhz_end": pynvml.nvmlDeviceGetClockInfo(nv, pynvml.NVML_CLOCK_SM)}
@@ -411,14 +515,16 @@ def main():
                                   f"restatement of pytorch_inference.py, {cores} threads"}
 
     img_bytes = 3 * 224 * 224 * 4
+    shard = (f"{args.global_batch} images sharded {'/'.join(str(per_gpu_batch(args, world, r)) for r in range(world))}"
+             if args.scaling == "strong" else f"batch {B} per GPU")
     line = {
-        "metric": f"{args.arch} inference images/sec @ batch {B} per GPU",
+        "metric": metric_name(args, B),
         "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"{args.arch} {args.dtype} inference, batch {B} per GPU, synthetic 224x224 "
+        "config": {"workload": f"{args.arch} {args.dtype} inference, {shard}, synthetic 224x224 "
                                f"fp32 NCHW input, seeded random-init weights",
-                   "global_batch": world * B, "per_gpu_batch": B, "chunk": chunk_n,
+                   "global_batch": total_images, "per_gpu_batch": B, "chunk": chunk_n,
                    "parallelism": f"dp{world} (replica per GPU; ONE NCCL all-gather of logits+top1 per step, "
                                   f"{4 * per_rank} B per rank, on a side stream overlapping the next step)"
                    if world > 1 else "single GPU",
@@ -434,10 +540,12 @@ def main():
                 "top1_equal_to_device_path": same},
         "e2e_u8": e2e_u8,
         "gpu_launches": model.launches_per_forward(B) * args.steps,
+        "parity": parity,
+        "gather_ok": gather_ok,
         "roofline": roofline,
         "sustained": sustained,
         "cpu_baseline": cpu_baseline,
-        "tflops_per_gpu": value / world * model.flops_per_image / 1e12,
+        "tflops_per_gpu": step_tflops,
     }
     print(json.dumps(line))
     if world > 1:
