@@ -37,7 +37,13 @@ typedef struct rnb_model rnb_model_t;
 
 /* ---- library ---------------------------------------------------------------------------- */
 
-/* Select the CUDA device, check it is sm_100, raise kernel shared-memory limits. Idempotent. */
+/* Prepare CUDA device `device` (check it is sm_100, raise kernel shared-memory limits — per device) and make it the
+ * calling thread's current device. Idempotent; may be called for several devices of one process. The first call also
+ * runs a one-off self-test of the im2col TMA descriptor path on a tensor smaller than 128 KiB (a driver-dependent
+ * work-around is switched on or off according to the result; if neither variant reproduces the FP32 kernel the call
+ * fails). A model lives on the device that was current when it was created and every rnb_model_* / rnb_group_* entry
+ * point switches to that device for the duration of the call, so one process can drive replicas on several GPUs.
+ * The per-op entry points below run on the device that owns their input tensor. */
 int rnb_init(int device);
 /* Message of the last failing call on this thread ("" if none). */
 const char* rnb_last_error(void);
@@ -57,10 +63,16 @@ const char* rnb_version(void);
 int rnb_model_create(const char* arch, int dtype, const char* weights_dir, int max_batch, int chunk,
                      rnb_model_t** out);
 int rnb_model_destroy(rnb_model_t* m);
+/* Device the model lives on. */
+int rnb_model_device(const rnb_model_t* m);
+/* Plan, autotune and capture everything a forward of `batch` images needs (also the uint8 path if include_u8),
+ * ahead of time: the first forward of a new batch size otherwise does this inside the call (a device
+ * synchronisation plus trial launches — not allowed while the caller's stream is being captured). Blocking. */
+int rnb_model_warmup(rnb_model_t* m, int batch, int include_u8);
 
 /* Pre-packed weight cache. rnb_model_save_packed() writes everything rnb_model_create() derived from the
  * save_weights.py directory (BN folded into K-major BF16/TF32 conv weights, stem / FC packs, biases) as ONE
- * file: 80-byte header (magic "RNBWGT01", arch, dtype, class count, word-wise FNV-1a-64 checksum) + 256-byte-aligned
+ * file: 72-byte header (magic "RNBWGT01", arch, dtype, class count, word-wise FNV-1a-64 checksum) + 256-byte-aligned
  * tensors. rnb_model_create_packed() restores a model from it with one read and one host->device copy
  * instead of 320-932 small file reads, copies and fold kernels (tensor.cuh:126-152,184-199); a wrong magic,
  * size or checksum is an error. The packed model computes bit-identical results. */
@@ -70,7 +82,11 @@ int rnb_model_create_packed(const char* path, int max_batch, int chunk, rnb_mode
 /* Forward pass on device buffers: x_dev is [batch,3,224,224] float32 NCHW (the layout of the files
  * written by convert_imgs_to_bin.py:20-23), logits_dev is [batch,num_classes] float32,
  * top1_dev is [batch] int32 (lowest index among ties, as main.cu:243-251); either output may be
- * NULL. The whole pass is replayed from a CUDA graph cached per batch size. */
+ * NULL. The whole pass is replayed from a CUDA graph; up to four executables are kept per batch size and a call with
+ * other buffers re-targets the least recently used one (cudaGraphExecUpdate), so reuse your buffers where you can.
+ * Concurrency: all forwards of ONE model share its activation arena and are ordered one after the other on the
+ * device whatever streams they were enqueued on (an event links consecutive calls); calls on one model must come
+ * from one host thread at a time. Use one model per stream / thread for concurrent passes. */
 int rnb_model_forward(rnb_model_t* m, const float* x_dev, int batch, float* logits_dev,
                       int32_t* top1_dev, void* stream);
 
@@ -123,8 +139,11 @@ int rnb_model_profile(rnb_model_t* m, const float* x_dev, int batch, int iters, 
  * launch rewrites its own output from unchanged inputs). */
 int rnb_model_repeat_launch(rnb_model_t* m, int batch, int index, int repeat, void* stream);
 /* Copy an intermediate activation of the LAST forward (chunk 0) to `out_dev` as float32 NCHW.
- * `name` is "stem" | "maxpool" | "layer{L}.{i}" (block output) | "avgpool". Returns the element
- * count through *numel (call with out_dev = NULL to query). Debug / parity use only. */
+ * `name` is "maxpool" | "layer{L}.{i}" (block output) | "avgpool" (and "stem", the 112x112 conv1 output, only on
+ * the CUDA-core stem path: the tensor-core stem fuses conv1 + pool and never materialises it). Returns the element
+ * count through *numel (call with out_dev = NULL to query). Debug / parity use only: needs RNB_KEEP_ACTIVATIONS=1 in
+ * the environment when the model is created (otherwise the arena recycles the buffers and the call fails with
+ * RNB_ERR_UNSUPPORTED). */
 int rnb_model_get_activation(rnb_model_t* m, const char* name, float* out_dev, int64_t* numel,
                              void* stream);
 

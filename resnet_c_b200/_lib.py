@@ -37,6 +37,8 @@ PROTOTYPES = {
     "rnb_version": (C.c_char_p, []),
     "rnb_model_create": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
     "rnb_model_destroy": (C.c_int, [_vp]),
+    "rnb_model_device": (C.c_int, [_vp]),
+    "rnb_model_warmup": (C.c_int, [_vp, C.c_int, C.c_int]),
     "rnb_model_save_packed": (C.c_int, [_vp, C.c_char_p]),
     "rnb_model_create_packed": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
     "rnb_model_forward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),

@@ -51,11 +51,36 @@ def _stale(target: Path, sources: list[Path]) -> bool:
     return any(s.stat().st_mtime > t for s in sources if s.exists())
 
 
+def _includes(src: Path, seen: set[Path]) -> set[Path]:
+    """Transitive quoted #includes of `src` inside the repo (dependency scan for incremental builds)."""
+    import re
+    if src in seen or not src.exists():
+        return seen
+    seen.add(src)
+    for inc in re.findall(r'^\s*#\s*include\s*"([^"]+)"', src.read_text(), flags=re.M):
+        _includes((src.parent / inc).resolve(), seen)
+    return seen
+
+
 def build_librnb(force: bool = False) -> Path:
-    srcs = [CSRC / s for s in LIB_SOURCES]
-    deps = srcs + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "rnb.h"]
-    if force or _stale(LIB, deps):
-        _run([_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, *srcs])
+    """One object per translation unit under build/obj/ (compiled in parallel, only when the source or one of the
+    headers it includes changed), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = ROOT / "build" / "obj"
+    objdir.mkdir(parents=True, exist_ok=True)
+    jobs = []
+    objs = []
+    for name in LIB_SOURCES:
+        src = CSRC / name
+        obj = objdir / (src.stem + ".o")
+        objs.append(obj)
+        if force or _stale(obj, sorted(_includes(src.resolve(), set()))):
+            jobs.append([_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj])
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(_run, jobs))
+    if jobs or force or _stale(LIB, objs):
+        _run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs])
     return LIB
 
 

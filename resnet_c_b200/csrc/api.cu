@@ -1,6 +1,8 @@
 // api.cu — the extern "C" surface declared in include/rnb.h.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include <cstring>
 #include <mutex>
@@ -10,6 +12,7 @@
 #include "conv_plan.h"
 #include "internal.h"
 #include "model.h"
+#include "tensormap.h"
 
 struct rnb_model {
     rnb::Model impl;
@@ -19,12 +22,18 @@ namespace rnb {
 
 namespace {
 thread_local std::string g_error;
-int g_num_sms = 0;
-int g_device = -1;
+constexpr int kMaxDevices = 64;
+int g_sms[kMaxDevices] = {0};  // SM count per device; 0 = rnb_init() has not prepared that device
+bool g_selftest_done = false;  // the im2col descriptor self-test is a property of the driver: once per process
 std::mutex g_init_mutex;
 }  // namespace
 
-int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+int num_sms() {
+    int d = -1;
+    if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < kMaxDevices && g_sms[d] > 0) return g_sms[d];
+    return 148;
+}
+bool device_ready(int dev) { return dev >= 0 && dev < kMaxDevices && g_sms[dev] > 0; }
 void set_error(const std::string& msg) { g_error = msg; }
 int fail_cuda(cudaError_t e, const char* what) {
     g_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -42,11 +51,89 @@ using namespace rnb;
     } while (0)
 
 static int require_init() {
-    if (g_device < 0) {
-        set_error("rnb_init() has not been called (or failed): no CUDA device selected");
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess || !device_ready(d)) {
+        set_error("rnb_init() has not been called (or failed) for the current CUDA device");
         return RNB_ERR_CUDA;
     }
     return RNB_OK;
+}
+
+// Device that owns a device pointer (-1: not device memory / unknown).
+static int device_of(const void* p) {
+    cudaPointerAttributes a{};
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
+
+// The per-op entry points take caller-owned device tensors: they run on the device that owns `x_dev` (which must
+// have been prepared by rnb_init), not on whatever device another call selected last.
+#define API_ON_DEVICE_OF(ptr)                                                                          \
+    const int dev__ = device_of(ptr);                                                                  \
+    if (dev__ >= 0 && !device_ready(dev__)) {                                                          \
+        set_error("rnb_init(" + std::to_string(dev__) + ") has not been called for the device that owns this tensor"); \
+        return RNB_ERR_CUDA;                                                                           \
+    }                                                                                                  \
+    DeviceGuard guard__(dev__)
+
+// A sub-128-KiB im2col convolution on the tcgen05 path against the FP32 CUDA-core kernel, with the descriptor
+// work-around of tensormap.cu as the driver version suggests first and the other way round second: keeps whichever
+// reproduces the FP32 result, fails loudly if neither does (a wrong guess would silently corrupt layer4 / small batches).
+static int im2col_selftest() {
+    const char* skip = getenv("RNB_SKIP_SELFTEST");
+    if (skip && atoi(skip) != 0) return RNB_OK;
+    const int B = 1, Cin = 64, H = 8, W = 8, Cout = 64, k = 3;
+    const size_t nx = 1ull * B * Cin * H * W, nw = 1ull * Cout * Cin * k * k, ny = 1ull * B * Cout * H * W;
+    std::vector<float> hx(nx), hw(nw), want(ny), got(ny);
+    uint32_t lcg = 12345u;
+    auto rnd = [&]() {
+        lcg = lcg * 1664525u + 1013904223u;
+        return static_cast<float>((lcg >> 8) & 0xffff) / 65536.f - 0.5f;
+    };
+    for (auto& v : hx) v = rnd();
+    for (auto& v : hw) v = rnd() * 0.1f;
+    float *x = nullptr, *w = nullptr, *y = nullptr;
+    API_CUDA(cudaMalloc(&x, nx * sizeof(float)));
+    API_CUDA(cudaMalloc(&w, nw * sizeof(float)));
+    API_CUDA(cudaMalloc(&y, ny * sizeof(float)));
+    struct Free {
+        float *a, *b, *c;
+        ~Free() { cudaFree(a); cudaFree(b); cudaFree(c); }
+    } freer{x, w, y};
+    API_CUDA(cudaMemcpy(x, hx.data(), nx * sizeof(float), cudaMemcpyHostToDevice));
+    API_CUDA(cudaMemcpy(w, hw.data(), nw * sizeof(float), cudaMemcpyHostToDevice));
+    API_CUDA(launch_conv2d_f32(x, y, w, B, Cin, H, W, Cout, k, 1, 1, 0));
+    API_CUDA(cudaMemcpy(want.data(), y, ny * sizeof(float), cudaMemcpyDeviceToHost));
+    float scale = 0.f;
+    for (float v : want) scale = std::max(scale, std::fabs(v));
+    const int first = im2col_small_patch();
+    std::string detail;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int mode = attempt == 0 ? first : 1 - first;
+        set_im2col_small_patch(mode);
+        API_CUDA(cudaMemset(y, 0xff, ny * sizeof(float)));
+        int r = rnb_conv_bn_act_forward(x, w, nullptr, nullptr, nullptr, nullptr, nullptr, y, B, Cin, H, W, Cout, k, 1, 1,
+                                        0, RNB_DTYPE_BF16, nullptr);
+        if (r) return r;
+        API_CUDA(cudaStreamSynchronize(0));
+        API_CUDA(cudaMemcpy(got.data(), y, ny * sizeof(float), cudaMemcpyDeviceToHost));
+        float err = 0.f;
+        bool finite = true;
+        for (size_t i = 0; i < ny; ++i) {
+            if (!std::isfinite(got[i])) finite = false;
+            err = std::max(err, std::fabs(got[i] - want[i]));
+        }
+        if (finite && scale > 0.f && err / scale < 2e-2f) return RNB_OK;
+        detail += " [work-around " + std::string(mode ? "on" : "off") + ": rel err " +
+                  (finite ? std::to_string(err / scale) : std::string("non-finite")) + "]";
+    }
+    set_im2col_small_patch(-1);
+    set_error("rnb_init self-test failed: a 3x3 im2col convolution over a tensor smaller than 128 KiB does not match the "
+              "FP32 kernel with or without the descriptor work-around" + detail);
+    return RNB_ERR_CUDA;
 }
 
 extern "C" {
@@ -73,11 +160,24 @@ int rnb_init(int device) {
                   std::to_string(prop.minor) + "; librnb is built for sm_100a (B200) only");
         return RNB_ERR_UNSUPPORTED;
     }
-    g_num_sms = prop.multiProcessorCount;
-    API_CUDA(conv_kernels_init());
-    API_CUDA(stem_tc_init());
-    API_CUDA(stem_tc_split_init());
-    g_device = device;
+    if (device >= kMaxDevices) {
+        set_error("device index out of range");
+        return RNB_ERR_INVALID;
+    }
+    if (g_sms[device] == 0) {  // dynamic shared-memory limits are per device
+        API_CUDA(conv_kernels_init());
+        API_CUDA(stem_tc_init());
+        API_CUDA(stem_tc_split_init());
+        g_sms[device] = prop.multiProcessorCount;
+    }
+    if (!g_selftest_done) {
+        int r = im2col_selftest();
+        if (r) {
+            g_sms[device] = 0;
+            return r;
+        }
+        g_selftest_done = true;
+    }
     set_error("");
     return RNB_OK;
 }
@@ -111,6 +211,7 @@ int rnb_model_save_packed(rnb_model_t* m, const char* path) {
         set_error("rnb_model_save_packed: NULL argument");
         return RNB_ERR_INVALID;
     }
+    DeviceGuard guard(m->impl.device);
     cudaDeviceSynchronize();
     return m->impl.save_packed(path);
 }
@@ -136,11 +237,23 @@ int rnb_model_create_packed(const char* path, int max_batch, int chunk, rnb_mode
 
 int rnb_model_destroy(rnb_model_t* m) {
     if (m) {
+        DeviceGuard guard(m->impl.device);
         cudaDeviceSynchronize();
         delete m;
     }
     return RNB_OK;
 }
+
+int rnb_model_warmup(rnb_model_t* m, int batch, int include_u8) {
+    if (!m) {
+        set_error("rnb_model_warmup: NULL model");
+        return RNB_ERR_INVALID;
+    }
+    DeviceGuard guard(m->impl.device);
+    return m->impl.warmup(batch, include_u8 != 0);
+}
+
+int rnb_model_device(const rnb_model_t* m) { return m ? m->impl.device : -1; }
 
 int rnb_model_forward(rnb_model_t* m, const float* x_dev, int batch, float* logits_dev,
                       int32_t* top1_dev, void* stream) {
@@ -148,6 +261,7 @@ int rnb_model_forward(rnb_model_t* m, const float* x_dev, int batch, float* logi
         set_error("rnb_model_forward: NULL model");
         return RNB_ERR_INVALID;
     }
+    DeviceGuard guard(m->impl.device);
     return m->impl.forward(x_dev, batch, logits_dev, top1_dev, static_cast<cudaStream_t>(stream));
 }
 
@@ -157,6 +271,7 @@ int rnb_model_forward_host(rnb_model_t* m, const float* x_host, int batch, float
         set_error("rnb_model_forward_host: NULL argument");
         return RNB_ERR_INVALID;
     }
+    DeviceGuard guard(m->impl.device);
     return m->impl.forward_host(x_host, batch, logits_host, top1_host);
 }
 
@@ -166,6 +281,7 @@ int rnb_model_submit_host(rnb_model_t* m, int slot, const float* x_host, int bat
         set_error("rnb_model_submit_host: NULL argument");
         return RNB_ERR_INVALID;
     }
+    DeviceGuard guard(m->impl.device);
     return m->impl.submit_host(slot, x_host, batch, logits_host, top1_host);
 }
 
@@ -174,6 +290,7 @@ int rnb_model_set_normalization(rnb_model_t* m, const float mean[3], const float
         set_error("rnb_model_set_normalization: NULL argument");
         return RNB_ERR_INVALID;
     }
+    DeviceGuard guard(m->impl.device);
     return m->impl.set_normalization(mean, std);
 }
 
@@ -183,6 +300,7 @@ int rnb_model_forward_u8(rnb_model_t* m, const uint8_t* x_dev, int batch, float*
         set_error("rnb_model_forward_u8: NULL argument");
         return RNB_ERR_INVALID;
     }
+    DeviceGuard guard(m->impl.device);
     return m->impl.forward_u8(x_dev, batch, logits_dev, top1_dev, static_cast<cudaStream_t>(stream));
 }
 
@@ -192,6 +310,7 @@ int rnb_model_submit_host_u8(rnb_model_t* m, int slot, const uint8_t* x_host, in
         set_error("rnb_model_submit_host_u8: NULL argument");
         return RNB_ERR_INVALID;
     }
+    DeviceGuard guard(m->impl.device);
     return m->impl.submit_host_u8(slot, x_host, batch, logits_host, top1_host);
 }
 
@@ -200,6 +319,7 @@ int rnb_model_wait_host(rnb_model_t* m, int slot) {
         set_error("rnb_model_wait_host: NULL model");
         return RNB_ERR_INVALID;
     }
+    DeviceGuard guard(m->impl.device);
     return m->impl.wait_host(slot);
 }
 
@@ -207,6 +327,7 @@ int rnb_model_num_classes(const rnb_model_t* m) { return m ? m->impl.classes : 0
 int rnb_model_num_convs(const rnb_model_t* m) { return m ? m->impl.num_convs : 0; }
 int rnb_model_launches_per_forward(rnb_model_t* m, int batch) {
     if (!m || batch <= 0) return 0;
+    DeviceGuard guard(m->impl.device);
     int total = 0;
     for (int off = 0; off < batch; off += m->impl.chunk)
         total += m->impl.launches_per_chunk(std::min(m->impl.chunk, batch - off));
@@ -221,6 +342,7 @@ int rnb_model_profile(rnb_model_t* m, const float* x_dev, int batch, int iters, 
         set_error("rnb_model_profile: NULL argument");
         return RNB_ERR_INVALID;
     }
+    DeviceGuard guard(m->impl.device);
     return m->impl.profile(x_dev, batch, iters, kind_out, ms_out, flops_out, bytes_out, max_entries,
                            n_entries, static_cast<cudaStream_t>(stream));
 }
@@ -230,6 +352,7 @@ int rnb_model_repeat_launch(rnb_model_t* m, int batch, int index, int repeat, vo
         set_error("rnb_model_repeat_launch: NULL model");
         return RNB_ERR_INVALID;
     }
+    DeviceGuard guard(m->impl.device);
     return m->impl.repeat_launch(batch, index, repeat, static_cast<cudaStream_t>(stream));
 }
 
@@ -239,7 +362,13 @@ int rnb_model_get_activation(rnb_model_t* m, const char* name, float* out_dev, i
         set_error("rnb_model_get_activation: NULL argument");
         return RNB_ERR_INVALID;
     }
+    DeviceGuard guard(m->impl.device);
     Model& M = m->impl;
+    if (!M.arena.keep) {
+        set_error("rnb_model_get_activation: activations are recycled (and aliased) by the arena; create the model with "
+                  "RNB_KEEP_ACTIVATIONS=1 in the environment to keep them");
+        return RNB_ERR_UNSUPPORTED;
+    }
     auto pit = M.plans.find(M.last_chunk_n);
     if (pit == M.plans.end()) {
         set_error("rnb_model_get_activation: no forward has run yet");
@@ -274,6 +403,7 @@ int rnb_conv_bn_act_forward(const float* x_dev, const float* w_dev, const float*
                             const float* bn_var_dev, const float* residual_dev, float* out_dev,
                             int B, int Cin, int H, int W, int Cout, int k, int stride, int pad,
                             int relu, int dtype, void* stream) {
+    API_ON_DEVICE_OF(x_dev);
     int r = require_init();
     if (r) return r;
     if (!x_dev || !w_dev || !out_dev || B <= 0 || H <= 0 || W <= 0 || stride <= 0 || pad < 0) {
@@ -303,11 +433,12 @@ int rnb_conv_bn_act_forward(const float* x_dev, const float* w_dev, const float*
     const size_t w_b = 1ull * Cout * k * k * Cin * esz;
     void *xin = nullptr, *wp = nullptr, *res = nullptr, *y = nullptr;
     float* bias = nullptr;
-    API_CUDA(cudaMallocAsync(&xin, in_b, s));
-    API_CUDA(cudaMallocAsync(&wp, w_b, s));
-    API_CUDA(cudaMallocAsync(&y, out_b, s));
-    API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&bias), Cout * sizeof(float), s));
-    if (residual_dev) API_CUDA(cudaMallocAsync(&res, out_b, s));
+    AsyncTemps tmp(s);  // freed (stream-ordered) on every return below
+    API_CUDA(tmp.alloc(&xin, in_b));
+    API_CUDA(tmp.alloc(&wp, w_b));
+    API_CUDA(tmp.alloc(&y, out_b));
+    API_CUDA(tmp.alloc(reinterpret_cast<void**>(&bias), Cout * sizeof(float)));
+    if (residual_dev) API_CUDA(tmp.alloc(&res, out_b));
     API_CUDA(launch_nchw_to_nhwc(x_dev, xin, B, Cin, H * W, esz, s));
     if (residual_dev) API_CUDA(launch_nchw_to_nhwc(residual_dev, res, B, Cout, OH * OW, esz, s));
     API_CUDA(launch_fold_pack(w_dev, bn_weight_dev, bn_bias_dev, bn_mean_dev, bn_var_dev, wp, bias,
@@ -325,17 +456,13 @@ int rnb_conv_bn_act_forward(const float* x_dev, const float* w_dev, const float*
     }
     API_CUDA(conv_plan_launch(plan, s));
     API_CUDA(launch_nhwc_to_nchw(y, out_dev, B, Cout, OH * OW, esz, s));
-    API_CUDA(cudaFreeAsync(xin, s));
-    API_CUDA(cudaFreeAsync(wp, s));
-    API_CUDA(cudaFreeAsync(y, s));
-    API_CUDA(cudaFreeAsync(bias, s));
-    if (res) API_CUDA(cudaFreeAsync(res, s));
     return RNB_OK;
 }
 
 int rnb_stem_forward(const float* x_dev, const float* w_dev, const float* bn_weight_dev,
                      const float* bn_bias_dev, const float* bn_mean_dev, const float* bn_var_dev,
                      float* out_dev, int B, int H, int W, int dtype, void* stream) {
+    API_ON_DEVICE_OF(x_dev);
     int r = require_init();
     if (r) return r;
     if (!x_dev || !w_dev || !out_dev || B <= 0 || H < 7 || W < 7) {
@@ -348,50 +475,48 @@ int rnb_stem_forward(const float* x_dev, const float* w_dev, const float* bn_wei
         set_error("rnb_stem_forward: BN vectors must be all set or all NULL");
         return RNB_ERR_INVALID;
     }
+    if (dtype != RNB_DTYPE_BF16 && dtype != RNB_DTYPE_TF32) {
+        set_error("rnb_stem_forward: bad dtype");
+        return RNB_ERR_INVALID;
+    }
     const int esz = dtype == RNB_DTYPE_BF16 ? 2 : 4;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    AsyncTemps tmp(s);
     const int OH = (6 + H - 7) / 2 + 1, OW = (6 + W - 7) / 2 + 1;
     const int PH = (2 + OH - 3) / 2 + 1, PW = (2 + OW - 3) / 2 + 1;
     if (H == 224 && W == 224 && !getenv("RNB_NO_STEM_TC")) {
         // tensor-core stem (stem_tc.cu for BF16, stem_tc_split.cu for TF32)
         void *wk = nullptr, *xp = nullptr, *pool_tc = nullptr;
         float* bias_tc = nullptr;
-        API_CUDA(cudaMallocAsync(&wk, stem_any_weight_bytes(esz), s));
-        API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&bias_tc), 64 * sizeof(float), s));
-        API_CUDA(cudaMallocAsync(&xp, stem_any_input_bytes(esz, B), s));
-        API_CUDA(cudaMallocAsync(&pool_tc, 1ull * B * PH * PW * 64 * esz, s));
+        API_CUDA(tmp.alloc(&wk, stem_any_weight_bytes(esz)));
+        API_CUDA(tmp.alloc(reinterpret_cast<void**>(&bias_tc), 64 * sizeof(float)));
+        API_CUDA(tmp.alloc(&xp, stem_any_input_bytes(esz, B)));
+        API_CUDA(tmp.alloc(&pool_tc, 1ull * B * PH * PW * 64 * esz));
         API_CUDA(launch_stem_any_pack_weights(esz, w_dev, bn_weight_dev, bn_bias_dev, bn_mean_dev, bn_var_dev, wk,
                                               bias_tc, s));
         API_CUDA(launch_stem_any_part(esz, 0, x_dev, xp, wk, bias_tc, pool_tc, B, s));
         API_CUDA(launch_stem_any_part(esz, 1, x_dev, xp, wk, bias_tc, pool_tc, B, s));
         API_CUDA(launch_nhwc_to_nchw(pool_tc, out_dev, B, 64, PH * PW, esz, s));
-        API_CUDA(cudaFreeAsync(wk, s));
-        API_CUDA(cudaFreeAsync(bias_tc, s));
-        API_CUDA(cudaFreeAsync(xp, s));
-        API_CUDA(cudaFreeAsync(pool_tc, s));
         return RNB_OK;
     }
     float *wf = nullptr, *bias = nullptr;
     void *conv = nullptr, *pool = nullptr;
-    API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wf), 64 * 147 * sizeof(float), s));
-    API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&bias), 64 * sizeof(float), s));
-    API_CUDA(cudaMallocAsync(&conv, 1ull * B * OH * OW * 64 * esz, s));
-    API_CUDA(cudaMallocAsync(&pool, 1ull * B * PH * PW * 64 * esz, s));
+    API_CUDA(tmp.alloc(reinterpret_cast<void**>(&wf), 64 * 147 * sizeof(float)));
+    API_CUDA(tmp.alloc(reinterpret_cast<void**>(&bias), 64 * sizeof(float)));
+    API_CUDA(tmp.alloc(&conv, 1ull * B * OH * OW * 64 * esz));
+    API_CUDA(tmp.alloc(&pool, 1ull * B * PH * PW * 64 * esz));
     API_CUDA(launch_fold_f32(w_dev, bn_weight_dev, bn_bias_dev, bn_mean_dev, bn_var_dev, wf, bias, 64,
                              147, s));
     API_CUDA(launch_stem_conv(x_dev, wf, bias, conv, B, H, W, esz, s));
     API_CUDA(launch_maxpool_nhwc(conv, pool, B, OH, OW, 64, esz, s));
     API_CUDA(launch_nhwc_to_nchw(pool, out_dev, B, 64, PH * PW, esz, s));
-    API_CUDA(cudaFreeAsync(wf, s));
-    API_CUDA(cudaFreeAsync(bias, s));
-    API_CUDA(cudaFreeAsync(conv, s));
-    API_CUDA(cudaFreeAsync(pool, s));
     return RNB_OK;
 }
 
 int rnb_tail_forward(const float* x_dev, const float* fc_w_dev, const float* fc_b_dev,
                      float* logits_dev, int32_t* top1_dev, int B, int C, int HW, int classes,
                      void* stream) {
+    API_ON_DEVICE_OF(x_dev);
     int r = require_init();
     if (r) return r;
     if (!x_dev || !fc_w_dev || !logits_dev || B <= 0 || C <= 0 || C % 4 != 0 || HW <= 0 ||
@@ -408,20 +533,20 @@ int rnb_tail_forward(const float* x_dev, const float* fc_w_dev, const float* fc_
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     float *pooled = nullptr, *pooledT = nullptr;
-    API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pooled), 1ull * B * C * sizeof(float), s));
-    API_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pooledT), 1ull * B * C * sizeof(float), s));
+    AsyncTemps tmp(s);
+    API_CUDA(tmp.alloc(reinterpret_cast<void**>(&pooled), 1ull * B * C * sizeof(float)));
+    API_CUDA(tmp.alloc(reinterpret_cast<void**>(&pooledT), 1ull * B * C * sizeof(float)));
     API_CUDA(launch_pool2d_f32(false, x_dev, pooled, B, C, k, k, k, 1, 0, s));
     API_CUDA(launch_transpose_f32(pooled, pooledT, B, C, s));
     API_CUDA(launch_fc(pooledT, fc_w_dev, fc_b_dev, logits_dev, B, C, classes, s));
     if (top1_dev) API_CUDA(launch_argmax_f32(logits_dev, top1_dev, B, classes, s));
-    API_CUDA(cudaFreeAsync(pooled, s));
-    API_CUDA(cudaFreeAsync(pooledT, s));
     return RNB_OK;
 }
 
 // ------------------------------------------------------------------------------ per-op fp32
 int rnb_conv2d_forward(const float* x_dev, float* out_dev, const float* w_dev, int B, int Cin, int H,
                        int W, int Cout, int k, int stride, int pad, void* stream) {
+    API_ON_DEVICE_OF(x_dev);
     int r = require_init();
     if (r) return r;
     if (!x_dev || !out_dev || !w_dev || B <= 0 || Cin <= 0 || Cout <= 0 || k <= 0 || stride <= 0 ||
@@ -437,6 +562,7 @@ int rnb_conv2d_forward(const float* x_dev, float* out_dev, const float* w_dev, i
 int rnb_batchnorm2d_forward(const float* x_dev, float* out_dev, const float* weight_dev,
                             const float* bias_dev, const float* mean_dev, const float* var_dev, int B,
                             int C, int HW, void* stream) {
+    API_ON_DEVICE_OF(x_dev);
     int r = require_init();
     if (r) return r;
     if (!x_dev || !out_dev || !weight_dev || !bias_dev || !mean_dev || !var_dev || B <= 0 || C <= 0 ||
@@ -450,6 +576,7 @@ int rnb_batchnorm2d_forward(const float* x_dev, float* out_dev, const float* wei
 }
 
 int rnb_relu_forward(const float* x_dev, float* out_dev, int64_t n, void* stream) {
+    API_ON_DEVICE_OF(x_dev);
     int r = require_init();
     if (r) return r;
     if (!x_dev || !out_dev || n < 0) {
@@ -462,6 +589,7 @@ int rnb_relu_forward(const float* x_dev, float* out_dev, int64_t n, void* stream
 }
 
 int rnb_add_forward(const float* a_dev, const float* b_dev, float* out_dev, int64_t n, void* stream) {
+    API_ON_DEVICE_OF(a_dev);
     int r = require_init();
     if (r) return r;
     if (!a_dev || !b_dev || !out_dev || n < 0) {
@@ -475,6 +603,7 @@ int rnb_add_forward(const float* a_dev, const float* b_dev, float* out_dev, int6
 
 static int pool_common(bool is_max, const float* x_dev, float* out_dev, int B, int C, int H, int W,
                        int k, int stride, int pad, void* stream) {
+    API_ON_DEVICE_OF(x_dev);
     int r = require_init();
     if (r) return r;
     if (!x_dev || !out_dev || B <= 0 || C <= 0 || k <= 0 || stride <= 0 || pad < 0 ||
@@ -497,6 +626,7 @@ int rnb_avgpool2d_forward(const float* x_dev, float* out_dev, int B, int C, int 
 
 int rnb_linear_forward(const float* x_dev, float* out_dev, const float* w_dev, const float* bias_dev,
                        int B, int in_features, int out_features, void* stream) {
+    API_ON_DEVICE_OF(x_dev);
     int r = require_init();
     if (r) return r;
     if (!x_dev || !out_dev || !w_dev || B <= 0 || in_features <= 0 || out_features <= 0) {
@@ -509,6 +639,7 @@ int rnb_linear_forward(const float* x_dev, float* out_dev, const float* w_dev, c
 }
 
 int rnb_argmax_forward(const float* x_dev, int32_t* out_dev, int B, int n, void* stream) {
+    API_ON_DEVICE_OF(x_dev);
     int r = require_init();
     if (r) return r;
     if (!x_dev || !out_dev || B <= 0 || n <= 0) {
@@ -521,6 +652,7 @@ int rnb_argmax_forward(const float* x_dev, int32_t* out_dev, int B, int n, void*
 
 int rnb_softmax_topk_forward(const float* logits_dev, float* probs_full_dev, float* top_probs_dev,
                              int32_t* top_idx_dev, int B, int n, int k, void* stream) {
+    API_ON_DEVICE_OF(logits_dev);
     int r = require_init();
     if (r) return r;
     if (!logits_dev || !top_probs_dev || !top_idx_dev || B <= 0 || n <= 0 || k <= 0 || k > n || k > 32) {
@@ -533,6 +665,7 @@ int rnb_softmax_topk_forward(const float* logits_dev, float* probs_full_dev, flo
 }
 
 int rnb_save_f32(const float* dev, int64_t numel, const char* path) {
+    API_ON_DEVICE_OF(dev);
     int r = require_init();
     if (r) return r;
     if (!dev || numel <= 0 || !path) {

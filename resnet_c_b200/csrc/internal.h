@@ -7,10 +7,46 @@
 
 namespace rnb {
 
-// ---- process state (api.cu)
-int num_sms();
+// ---- process state (api.cu). Nothing here is tied to ONE device: rnb_init(d) prepares device d (kernel attributes
+// are per device) and every model remembers the device it was created on.
+int num_sms();                // SM count of the calling thread's current device (148 if rnb_init() has not seen it)
+bool device_ready(int dev);   // rnb_init(dev) has succeeded
 void set_error(const std::string& msg);
 int fail_cuda(cudaError_t e, const char* what);  // records the message, returns RNB_ERR_CUDA
+
+// Makes `dev` the calling thread's current device for the lifetime of the guard (entry points of a model /
+// group run on the model's own device whatever the caller had selected).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (dev >= 0 && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched && prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// Frees stream-ordered temporaries on EVERY exit path of the per-op entry points (api.cu).
+struct AsyncTemps {
+    cudaStream_t s;
+    void* p[8];
+    int n = 0;
+    explicit AsyncTemps(cudaStream_t stream) : s(stream) {}
+    cudaError_t alloc(void** out, size_t bytes) {
+        cudaError_t e = n < 8 ? cudaMallocAsync(out, bytes, s) : cudaErrorMemoryAllocation;
+        if (e == cudaSuccess) p[n++] = *out;
+        return e;
+    }
+    ~AsyncTemps() {
+        for (int i = 0; i < n; ++i) cudaFreeAsync(p[i], s);
+    }
+    AsyncTemps(const AsyncTemps&) = delete;
+    AsyncTemps& operator=(const AsyncTemps&) = delete;
+};
 
 // Launch with programmatic stream serialization (PDL): the kernel may be scheduled while its predecessor in the
 // stream drains; it MUST execute griddepcontrol.wait before touching anything an earlier kernel wrote (and every

@@ -42,6 +42,10 @@ void Arena::release(void* p) {
     for (auto& b : blocks_)
         if (b.p == p) b.busy = false;
 }
+void Arena::release_all() {
+    if (keep) return;
+    for (auto& b : blocks_) b.busy = false;
+}
 void Arena::free_all() {
     for (auto& b : blocks_) cudaFree(b.p);
     blocks_.clear();
@@ -81,12 +85,18 @@ int upload(const std::vector<float>& h, float** d) {
     return RNB_OK;
 }
 
+// Raw (un-folded) tensors live only while one conv is being folded; freed on every exit path of the loaders.
 struct BnDev {
     float *w = nullptr, *b = nullptr, *m = nullptr, *v = nullptr;
     void free_all() {
         cudaFree(w); cudaFree(b); cudaFree(m); cudaFree(v);
         w = b = m = v = nullptr;
     }
+    ~BnDev() { free_all(); }
+};
+struct DevTmp {
+    float* p = nullptr;
+    ~DevTmp() { cudaFree(p); }
 };
 
 int load_bn(const std::string& dir, const std::string& name, int C, BnDev& bn) {
@@ -105,20 +115,16 @@ int load_conv(const std::string& dir, const std::string& cname, const std::strin
     std::vector<float> h;
     int r;
     if ((r = read_f32_file(dir + "/" + cname + ".weight", 1ull * Cout * Cin * k * k, h))) return r;
-    float* raw = nullptr;
-    if ((r = upload(h, &raw))) return r;
+    DevTmp raw;
+    if ((r = upload(h, &raw.p))) return r;
     BnDev bn;
-    if ((r = load_bn(dir, bname, Cout, bn))) {
-        cudaFree(raw);
-        return r;
-    }
+    if ((r = load_bn(dir, bname, Cout, bn))) return r;
+    // cw.w / cw.bias belong to the model from here on (Model::~Model frees them, also after a failed load)
     cw.Cin = Cin; cw.Cout = Cout; cw.k = k; cw.stride = stride; cw.pad = pad;
     RNB_CUDA(cudaMalloc(&cw.w, 1ull * Cout * Cin * k * k * esz));
     RNB_CUDA(cudaMalloc(&cw.bias, Cout * sizeof(float)));
-    RNB_CUDA(launch_fold_pack(raw, bn.w, bn.b, bn.m, bn.v, cw.w, cw.bias, Cout, Cin, k, esz, 0));
+    RNB_CUDA(launch_fold_pack(raw.p, bn.w, bn.b, bn.m, bn.v, cw.w, cw.bias, Cout, Cin, k, esz, 0));
     RNB_CUDA(cudaDeviceSynchronize());
-    cudaFree(raw);
-    bn.free_all();
     return RNB_OK;
 }
 
@@ -136,7 +142,10 @@ const ArchSpec kArchs[] = {
 }  // namespace
 
 Model::~Model() {
-    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    DeviceGuard guard(device);
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+    if (order_ev) cudaEventDestroy(order_ev);
+    if (host_compute) cudaStreamDestroy(host_compute);
     for (auto e : copy_events) cudaEventDestroy(e);
     if (cap_stream) cudaStreamDestroy(cap_stream);
     if (side_stream) cudaStreamDestroy(side_stream);
@@ -187,6 +196,7 @@ int Model::configure(const std::string& arch_name, int dtype, int max_batch_, in
     esz = dtype == RNB_DTYPE_BF16 ? 2 : 4;
     bottleneck = spec->bottleneck;
     max_batch = max_batch_;
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
     num_sms = rnb::num_sms();
     if (chunk_ <= 0) {
         const char* env = getenv("RNB_CHUNK");
@@ -226,20 +236,18 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
     {
         std::vector<float> h;
         if ((r = read_f32_file(dir + "/conv1.weight", 64 * 147, h))) return r;
-        float* raw = nullptr;
-        if ((r = upload(h, &raw))) return r;
+        DevTmp raw;
+        if ((r = upload(h, &raw.p))) return r;
         BnDev bn;
         if ((r = load_bn(dir, "bn1", 64, bn))) return r;
         RNB_CUDA(cudaMalloc(&stem_w, 64 * 147 * sizeof(float)));
         RNB_CUDA(cudaMalloc(&stem_bias, 64 * sizeof(float)));
-        RNB_CUDA(launch_fold_f32(raw, bn.w, bn.b, bn.m, bn.v, stem_w, stem_bias, 64, 147, 0));
+        RNB_CUDA(launch_fold_f32(raw.p, bn.w, bn.b, bn.m, bn.v, stem_w, stem_bias, 64, 147, 0));
         if (stem_tc) {
             RNB_CUDA(cudaMalloc(&stem_wk, stem_any_weight_bytes(esz)));
-            RNB_CUDA(launch_stem_any_pack_weights(esz, raw, bn.w, bn.b, bn.m, bn.v, stem_wk, stem_bias, 0));
+            RNB_CUDA(launch_stem_any_pack_weights(esz, raw.p, bn.w, bn.b, bn.m, bn.v, stem_wk, stem_bias, 0));
         }
         RNB_CUDA(cudaDeviceSynchronize());
-        cudaFree(raw);
-        bn.free_all();
     }
     double macs = 64.0 * 147 * 112 * 112;
     // ---- residual layers (createLayer, main.cu:53-89; BasicBlock per torchvision)
@@ -251,7 +259,8 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
         const int out_c = bottleneck ? mid * 4 : mid;
         const int layer_stride = L == 0 ? 1 : 2;
         for (int i = 0; i < spec->blocks[L]; ++i) {
-            BlockWeights bw;
+            blocks.emplace_back();  // owned by the model at once: a failed load frees what was already folded
+            BlockWeights& bw = blocks.back();
             bw.bottleneck = bottleneck;
             bw.name = "layer" + std::to_string(L + 1) + "." + std::to_string(i);
             const std::string p = bw.name + ".";
@@ -285,7 +294,6 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
                     if ((r = upload(b3, &bw.bias3ds))) return r;
                 }
             }
-            blocks.push_back(bw);
             in_c = out_c;
             hw = out_hw;
         }
@@ -321,14 +329,34 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
         }
     }
     flops_per_image = 2.0 * macs;
+    int rs = create_streams();
+    if (rs) return rs;
+    set_error("");
+    return RNB_OK;
+}
+
+int Model::create_streams() {
     RNB_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
     RNB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     RNB_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    RNB_CUDA(cudaStreamCreateWithFlags(&host_compute, cudaStreamNonBlocking));
+    RNB_CUDA(cudaEventCreateWithFlags(&order_ev, cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) {
         RNB_CUDA(cudaEventCreateWithFlags(&fork_ev[i], cudaEventDisableTiming));
         RNB_CUDA(cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming));
     }
-    set_error("");
+    return RNB_OK;
+}
+
+// Serialise every use of the shared activation arena across streams (see model.h).
+int Model::begin_enqueue(cudaStream_t s) {
+    if (has_last && last_stream != s) RNB_CUDA(cudaStreamWaitEvent(s, order_ev, 0));
+    return RNB_OK;
+}
+int Model::end_enqueue(cudaStream_t s) {
+    RNB_CUDA(cudaEventRecord(order_ev, s));
+    last_stream = s;
+    has_last = true;
     return RNB_OK;
 }
 
@@ -537,13 +565,8 @@ int Model::load_packed(const std::string& path, int max_batch_, int chunk_) {
         *p = static_cast<uint8_t*>(blob) + off;
         off += aligned(bytes);
     });
-    RNB_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
-    RNB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    RNB_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; ++i) {
-        RNB_CUDA(cudaEventCreateWithFlags(&fork_ev[i], cudaEventDisableTiming));
-        RNB_CUDA(cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming));
-    }
+    int rs = create_streams();
+    if (rs) return rs;
     set_error("");
     return RNB_OK;
 }
@@ -559,10 +582,18 @@ ChunkPlan* Model::plan_for(int n) {
     p.n = n;
     const size_t e = esz;
     auto bytes = [&](int c, int h) { return 1ull * n * h * h * c * e; };
+    // A plan that fails half way must not leave its blocks busy: between plans nothing is (every plan releases all
+    // of its blocks at the end, chunks run back to back), so a failure simply frees the lot.
     auto fail_alloc = [&]() -> ChunkPlan* {
+        arena.release_all();
         set_error("activation arena allocation failed");
         return nullptr;
     };
+    struct PlanGuard {
+        Arena& a;
+        bool ok = false;
+        ~PlanGuard() { if (!ok) a.release_all(); }
+    } plan_guard{arena};
     const int s_hw = (6 + image - 7) / 2 + 1;     // 112
     const int p_hw = (2 + s_hw - 3) / 2 + 1;      // 56
     if (!(p.stem_out = arena.acquire(stem_tc ? stem_any_input_bytes(esz, n) : bytes(64, s_hw))))
@@ -803,6 +834,7 @@ ChunkPlan* Model::plan_for(int n) {
     arena.release(x);
     arena.release(p.pooled);
     if (p.pooled_bf16) arena.release(p.pooled_bf16);
+    plan_guard.ok = true;
     auto ins = plans.emplace(n, std::move(p));
     return &ins.first->second;
 }
@@ -910,7 +942,7 @@ int Model::set_normalization(const float* mean, const float* std) {
         }
     }
     cudaDeviceSynchronize();
-    for (auto& g : graphs) cudaGraphExecDestroy(g.second);  // the constants are baked into captured launches
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);  // the constants are baked into captured launches
     graphs.clear();
     for (int c = 0; c < 3; ++c) {
         norm_mean[c] = mean[c];
@@ -937,6 +969,20 @@ int Model::forward_any(const float* x, const uint8_t* x_u8, int batch, float* lo
         logits = scratch_logits;
     }
     const size_t img_elems = 3ull * image * image;
+    // Planning a new chunk size device-synchronises and times trial launches: not inside somebody's stream capture.
+    for (int off = 0; off < batch; off += chunk) {
+        if (plans.count(std::min(chunk, batch - off))) continue;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+            set_error("forward: this batch size has not been planned yet and the stream is capturing; call "
+                      "rnb_model_warmup(batch) first");
+            return RNB_ERR_INVALID;
+        }
+    }
+    {
+        int r = begin_enqueue(s);
+        if (r) return r;
+    }
     for (int off = 0; off < batch; off += chunk) {
         const int n = std::min(chunk, batch - off);
         ChunkPlan* p = plan_for(n);
@@ -950,28 +996,92 @@ int Model::forward_any(const float* x, const uint8_t* x_u8, int batch, float* lo
             if (r) return r;
             continue;
         }
-        const GraphKey key{n | (xu ? 1 << 30 : 0), xu ? static_cast<const void*>(xu) : static_cast<const void*>(xc), lc, tc};
+        const int shape = n | (xu ? 1 << 30 : 0);
+        const GraphKey key{shape, xu ? static_cast<const void*>(xu) : static_cast<const void*>(xc), lc, tc};
         auto g = graphs.find(key);
         if (g == graphs.end()) {
-            if (graphs.size() >= 256) {
-                for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
-                graphs.clear();
+            // executables already held for this shape, least recently used first
+            int held = 0;
+            auto lru = graphs.end();
+            for (auto it = graphs.begin(); it != graphs.end(); ++it) {
+                if (std::get<0>(it->first) != shape) continue;
+                ++held;
+                if (lru == graphs.end() || it->second.used < lru->second.used) lru = it;
             }
-            RNB_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
-            int r = enqueue_chunk(*p, xc, xu, lc, tc, cap_stream);
             cudaGraph_t graph = nullptr;
-            cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+            int r = capture_chunk(*p, xc, xu, lc, tc, &graph);
             if (r) return r;
-            if (ce != cudaSuccess) return fail_cuda(ce, "cudaStreamEndCapture");
             cudaGraphExec_t exec = nullptr;
-            ce = cudaGraphInstantiate(&exec, graph, 0);
+            if (held >= kGraphsPerShape) {
+                // re-target the least recently used executable: same topology, new pointers
+                cudaGraphExecUpdateResultInfo info{};
+                if (cudaGraphExecUpdate(lru->second.exec, graph, &info) == cudaSuccess) {
+                    exec = lru->second.exec;
+                } else {
+                    cudaGetLastError();
+                    cudaGraphExecDestroy(lru->second.exec);
+                }
+                graphs.erase(lru);
+            }
+            if (!exec) {
+                cudaError_t ce = cudaGraphInstantiate(&exec, graph, 0);
+                if (ce != cudaSuccess) {
+                    cudaGraphDestroy(graph);
+                    return fail_cuda(ce, "cudaGraphInstantiate");
+                }
+            }
             cudaGraphDestroy(graph);
-            if (ce != cudaSuccess) return fail_cuda(ce, "cudaGraphInstantiate");
-            g = graphs.emplace(key, exec).first;
+            g = graphs.emplace(key, GraphEntry{exec, 0}).first;
         }
-        RNB_CUDA(cudaGraphLaunch(g->second, s));
+        g->second.used = ++graph_clock;
+        RNB_CUDA(cudaGraphLaunch(g->second.exec, s));
+    }
+    {
+        int r = end_enqueue(s);
+        if (r) return r;
     }
     last_chunk_n = std::min(chunk, batch);
+    return RNB_OK;
+}
+
+// One chunk captured into a graph on cap_stream; the graph is destroyed on every failure path.
+int Model::capture_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1,
+                         cudaGraph_t* out) {
+    *out = nullptr;
+    RNB_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int r = enqueue_chunk(p, x, x_u8, logits, top1, cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+    if (r || ce != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        if (r) return r;
+        return fail_cuda(ce, "cudaStreamEndCapture");
+    }
+    *out = graph;
+    return RNB_OK;
+}
+
+int Model::warmup(int batch, bool include_u8) {
+    if (batch <= 0 || batch > max_batch) {
+        set_error("warmup: batch must be in [1, max_batch]");
+        return RNB_ERR_INVALID;
+    }
+    // a real forward on scratch buffers: plans every chunk size of this batch, autotunes, allocates lazily
+    // created buffers and instantiates one graph per chunk shape (later calls with other pointers re-target it)
+    const size_t img_elems = 3ull * image * image;
+    float* x = nullptr;
+    RNB_CUDA(cudaMalloc(&x, 1ull * batch * img_elems * sizeof(float)));
+    cudaMemset(x, 0, 1ull * batch * img_elems * sizeof(float));
+    if (!host_top1_dev && cudaMalloc(&host_top1_dev, 1ull * max_batch * sizeof(int32_t)) != cudaSuccess) {
+        cudaFree(x);
+        return fail_cuda(cudaGetLastError(), "warmup: cudaMalloc");
+    }
+    int r = forward(x, batch, nullptr, host_top1_dev, host_compute);
+    if (!r && include_u8) r = forward_u8(reinterpret_cast<const uint8_t*>(x), batch, nullptr, host_top1_dev, host_compute);
+    cudaError_t ce = cudaStreamSynchronize(host_compute);
+    cudaFree(x);
+    if (r) return r;
+    if (ce != cudaSuccess) return fail_cuda(ce, "warmup: cudaStreamSynchronize");
     return RNB_OK;
 }
 
@@ -986,8 +1096,10 @@ int Model::repeat_launch(int batch, int index, int repeat, cudaStream_t s) {
         set_error("repeat_launch: launch index out of range");
         return RNB_ERR_INVALID;
     }
+    int ro = begin_enqueue(s);
+    if (ro) return ro;
     for (int i = 0; i < repeat; ++i) RNB_CUDA(conv_plan_launch(pp->convs[index], s));
-    return RNB_OK;
+    return end_enqueue(s);
 }
 
 int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, double* flops,
@@ -1009,6 +1121,10 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
     if (!scratch_logits)
         RNB_CUDA(cudaMalloc(&scratch_logits, 1ull * max_batch * classes * sizeof(float)));
     if (!host_top1_dev) RNB_CUDA(cudaMalloc(&host_top1_dev, 1ull * max_batch * sizeof(int32_t)));
+    {
+        int ro = begin_enqueue(s);
+        if (ro) return ro;
+    }
     std::vector<cudaEvent_t> ev(L + 1);
     for (auto& e : ev) RNB_CUDA(cudaEventCreate(&e));
     std::vector<double> acc(L, 0.0);
@@ -1049,6 +1165,10 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
         }
     }
     for (auto& e : ev) cudaEventDestroy(e);
+    {
+        int ro = end_enqueue(s);
+        if (ro) return ro;
+    }
     int i = 0;
     auto put = [&](int k, double f, double b) {
         kind[i] = k;
@@ -1098,8 +1218,7 @@ int Model::forward_host(const float* x, int batch, float* logits, int32_t* top1)
         RNB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         copy_events.push_back(e);
     }
-    static thread_local cudaStream_t compute = nullptr;
-    if (!compute) RNB_CUDA(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+    cudaStream_t compute = host_compute;
     for (int c = 0; c < nchunks; ++c) {
         const int off = c * hchunk;
         const int n = std::min(hchunk, batch - off);

@@ -56,6 +56,7 @@ class Arena {
 public:
     void* acquire(size_t bytes);
     void release(void* p);
+    void release_all();  // mark every block free (a plan failed half way)
     void free_all();
     size_t total_bytes() const { return total_; }
     bool keep = false;  // debug: never recycle
@@ -73,6 +74,8 @@ struct Model {
     int max_batch = 0;
     int chunk = 0;
     int num_sms = 148;
+    int device = 0;         // the CUDA device this model lives on (current device at creation); the C ABI entry
+                            // points switch to it, so one process can hold replicas on several GPUs
     bool bottleneck = true;
     int final_c = 2048;
 
@@ -92,8 +95,32 @@ struct Model {
 
     Arena arena;
     std::map<int, ChunkPlan> plans;
-    using GraphKey = std::tuple<int, const void*, void*, void*>;  // (n | u8 flag << 30, x, logits, top1)
-    std::map<GraphKey, cudaGraphExec_t> graphs;
+    // CUDA graphs: one captured chunk per (n | u8 flag << 30, x, logits, top1). At most kGraphsPerShape executables
+    // are kept per (n, u8) shape; a call with new pointers beyond that RE-TARGETS the least recently used one with
+    // cudaGraphExecUpdate (a re-capture, no instantiation), so a caller that allocates fresh outputs every call pays
+    // ~0.1 ms of host time, not an instantiate, and nothing is ever flushed wholesale.
+    using GraphKey = std::tuple<int, const void*, void*, void*>;
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        uint64_t used = 0;
+    };
+    static constexpr int kGraphsPerShape = 4;
+    std::map<GraphKey, GraphEntry> graphs;
+    uint64_t graph_clock = 0;
+    int capture_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1, cudaGraph_t* out);
+    // All forwards of a model share ONE activation arena: every enqueue waits for the previous one (whatever stream it
+    // went to) and leaves an event behind, so forward() on two streams, forward_host() and submit_host() never overlap
+    // on the arena. Same-stream back-to-back forwards pay one event record per call.
+    cudaEvent_t order_ev = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
+    int begin_enqueue(cudaStream_t s);
+    int end_enqueue(cudaStream_t s);
+    cudaStream_t host_compute = nullptr;  // forward_host()'s compute stream
+    int create_streams();
+    // Planning + tile autotune + graph capture for `batch` images ahead of time, so that forward() never
+    // device-synchronises or times trial launches inside a serving loop (rnb_model_warmup).
+    int warmup(int batch, bool include_u8);
     cudaStream_t cap_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copy_events;

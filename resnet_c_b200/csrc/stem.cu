@@ -179,14 +179,9 @@ cudaError_t launch_stem_conv(const float* x, const float* w_folded, const float*
                              int B, int H, int W, int esz, cudaStream_t s) {
     const int OH = (6 + H - 7) / 2 + 1, OW = (6 + W - 7) / 2 + 1;
     dim3 grid((OW + TILE_W - 1) / TILE_W, (OH + TILE_H - 1) / TILE_H, B);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(stem_conv_kernel<__nv_bfloat16>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
-        cudaFuncSetAttribute(stem_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             STEM_SMEM);
-        attr_done = true;
-    }
+    // per device and cheap; this kernel is off the hot path (non-224 inputs / RNB_NO_STEM_TC)
+    cudaFuncSetAttribute(stem_conv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    cudaFuncSetAttribute(stem_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
     if (esz == 2)
         stem_conv_kernel<__nv_bfloat16><<<grid, STEM_THREADS, STEM_SMEM, s>>>(
             x, w_folded, bias, static_cast<__nv_bfloat16*>(out), H, W, OH, OW);

@@ -21,6 +21,7 @@ using EncodeIm2colFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 EncodeTiledFn g_tiled = nullptr;
 EncodeIm2colFn g_im2col = nullptr;
 int g_driver_version = 0;
+int g_small_patch_mode = -1;  // see set_im2col_small_patch()
 std::once_flag g_once;
 
 void resolve() {
@@ -82,9 +83,17 @@ int make_im2col_nhwc(CUtensorMap* out, TmDtype dtype, const void* base, uint64_t
     // Drivers up to 13.1 encode im2col descriptors of tensors smaller than 128 KiB with a flag the
     // hardware then mis-handles; clearing bit 21 of the second descriptor word restores the
     // documented behaviour (same work-around as CUTLASS' make_im2col_tma_copy_desc).
-    if (g_driver_version <= 13010 && N * H * W * C * es < 131072)
-        reinterpret_cast<uint64_t*>(out)[1] &= ~(1ull << 21);
+    // The version cut-off is only the first guess: rnb_init() runs a sub-128-KiB im2col convolution against the FP32
+    // kernel and switches the work-around on or off according to what the hardware actually does (api.cu).
+    const bool patch = g_small_patch_mode < 0 ? g_driver_version <= 13010 : g_small_patch_mode != 0;
+    if (patch && N * H * W * C * es < 131072) reinterpret_cast<uint64_t*>(out)[1] &= ~(1ull << 21);
     return 0;
+}
+
+void set_im2col_small_patch(int mode) { g_small_patch_mode = mode; }
+int im2col_small_patch() {
+    resolve();
+    return g_small_patch_mode < 0 ? (g_driver_version <= 13010 ? 1 : 0) : (g_small_patch_mode != 0 ? 1 : 0);
 }
 
 int make_tiled_nd(CUtensorMap* out, TmDtype dtype, const void* base, int rank, const uint64_t* dims,

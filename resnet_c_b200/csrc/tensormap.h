@@ -21,6 +21,11 @@ int make_tiled_2d(CUtensorMap* out, TmDtype dtype, const void* base, uint64_t ro
 int make_im2col_nhwc(CUtensorMap* out, TmDtype dtype, const void* base, uint64_t N, uint64_t H,
                      uint64_t W, uint64_t C, int ksize, int stride, int pad, uint32_t pixels);
 
+// Work-around for im2col descriptors of tensors smaller than 128 KiB (see tensormap.cu): -1 = decide by driver
+// version (default until rnb_init()'s self-test has run), 0 = off, 1 = on. im2col_small_patch() = what is in force.
+void set_im2col_small_patch(int mode);
+int im2col_small_patch();
+
 // Generic tiled map (up to 5-D, no swizzle option) used by the stem.
 int make_tiled_nd(CUtensorMap* out, TmDtype dtype, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, bool swizzle128);

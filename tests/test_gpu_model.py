@@ -331,3 +331,104 @@ def test_launch_accounting(monkeypatch):
     m18 = _model("resnet18", True, "tf32", 4)
     assert m18.flops_per_image == pytest.approx(3_628_146_688, rel=1e-9)
     m18.close()
+
+
+@pytest.mark.parametrize("arch,batch,dtype,nsample", [
+    ("resnet50", 256, "bf16", 8),    # BASELINE configs[2] as bench.py runs it: seed-0 DEFAULT-init weights
+    ("resnet152", 128, "bf16", 4),   # configs[4]: 1024 images over 8 GPUs = 128 per GPU
+    ("resnet18", 256, "tf32", 8),    # configs[1]
+])
+def test_stated_config_sizes_against_committed_goldens(arch, batch, dtype, nsample):
+    """The configs at their STATED batch sizes (other tile families, ragged pair grids and wave counts than the
+    B <= 4 golden cases) on the weights bench.py really uses, against the committed oracle sample
+    (tests/golden/make_golden_fullsize.py): logits within the bar on every sampled image, top-1 equal wherever the
+    oracle's fp64 margin exceeds twice the tolerance — with the evidence printed: images decided, agreement, margin."""
+    from resnet_c_b200 import weights
+    g = load_golden(f"{arch}_default_synth_b{batch}_sample{nsample}")
+    idx = g["index"]
+    model = _model(arch, False, dtype, batch)
+    logits, top1 = model.forward(weights.synthetic_images(batch).cuda())
+    torch.cuda.synchronize()
+    got, got_top1 = logits.cpu().numpy(), top1.cpu().numpy()
+    e = rel_err(got[idx], g["logits_fp32"])
+    assert e < TOL[dtype], f"{arch} B={batch} {dtype}: logits rel err {e:.3e}"
+    decided = g["margin_rel"] > 2 * TOL[dtype]
+    print(f"{arch} B={batch} {dtype}: rel err {e:.2e}; top-1 decided on {int(decided.sum())}/{len(idx)} sampled "
+          f"images (min fp64 margin {g['margin_rel'].min():.2e}), agree {int((got_top1[idx] == g['top1'])[decided].sum())}")
+    np.testing.assert_array_equal(got_top1[idx][decided], g["top1"][decided])
+    np.testing.assert_array_equal(got_top1, got.argmax(1))
+    model.close()
+
+
+@pytest.mark.parametrize("fuse", ["0", "1", "2"])
+def test_every_fusion_level_against_the_fp64_golden(monkeypatch, fuse):
+    """RNB_FUSE=2 (the DEFAULT plan: layer1 downsample folded into conv3's accumulator, i.e. one BF16 rounding of the
+    shortcut skipped) is not bit-identical to the layer-by-layer plan; pin each level's logits against the fp64 oracle
+    golden explicitly. Skipping a rounding must not make the fp64 distance worse than the bar."""
+    from resnet_c_b200 import weights
+    monkeypatch.setenv("RNB_FUSE", fuse)
+    g = load_golden("resnet50_rbn_synth_b4")
+    model = _model("resnet50", True, "bf16", 4)
+    logits, top1 = model.forward(weights.synthetic_images(4).cuda())
+    torch.cuda.synchronize()
+    e64 = rel_err(logits.cpu().numpy(), g["logits_fp64"])
+    assert e64 < TOL["bf16"], f"RNB_FUSE={fuse}: rel err vs fp64 oracle {e64:.3e}"
+    decided = g["margin_rel"] > 2 * TOL["bf16"]
+    np.testing.assert_array_equal(top1.cpu().numpy()[decided], g["top1"][decided])
+    model.close()
+
+
+def test_forwards_on_different_streams_share_the_arena_safely():
+    """All forwards of one model use ONE activation arena: calls enqueued on different streams (the caller's, the
+    pipelined host path's, forward_host's) must be ordered by the library, not overlap on the arena."""
+    from resnet_c_b200 import weights
+    B = 32
+    model = _model("resnet50", True, "bf16", B)
+    xs = [weights.synthetic_images(B, seed=s) for s in (1, 2, 3, 4)]
+    want = []
+    for x in xs:
+        l, t = model.forward(x.cuda())
+        torch.cuda.synchronize()
+        want.append((l.cpu(), t.cpu()))
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    xd = [x.cuda() for x in xs]
+    lh = torch.empty(B, model.num_classes).pin_memory()
+    th = torch.empty(B, dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            a = model.forward(xd[0])
+        with torch.cuda.stream(s2):
+            b = model.forward(xd[1])
+        model.submit_host(0, xs[2].pin_memory(), lh, th)     # third stream (pipe_compute), no wait in between
+        with torch.cuda.stream(s1):
+            c = model.forward(xd[3])
+        model.wait_host(0)
+        torch.cuda.synchronize()
+        for got, (wl, wt) in zip((a, b, (lh, th), c), (want[0], want[1], want[2], want[3])):
+            assert torch.equal(got[0].cpu(), wl) and torch.equal(got[1].cpu(), wt)
+    model.close()
+
+
+def test_fresh_output_buffers_every_call_and_warmup():
+    """Callers that allocate new outputs per call (cuda/nn.cu ResNet::predict, engine.ResNet.forward) re-target a
+    bounded set of graph executables instead of instantiating a graph per pointer set; rnb_model_warmup plans and
+    captures ahead of the first forward."""
+    from resnet_c_b200 import _lib, weights
+    from resnet_c_b200._lib import RnbError, check
+    B = 8
+    model = _model("resnet18", True, "bf16", B)
+    check(_lib.lib().rnb_model_warmup(model._h, B, 1))
+    assert _lib.lib().rnb_model_device(model._h) == torch.cuda.current_device()
+    x = weights.synthetic_images(B).cuda()
+    first, first_top1 = model.forward(x)
+    keep = []
+    for i in range(12):  # 12 distinct (logits, top1) pointer pairs: more than the 4 executables kept per shape
+        l, t = model.forward(x.clone() if i % 3 == 0 else x)
+        keep.append((l, t))
+    torch.cuda.synchronize()
+    for l, t in keep:
+        assert torch.equal(l, first) and torch.equal(t, first_top1)
+    with pytest.raises(RnbError, match="RNB_KEEP_ACTIVATIONS"):
+        model.activation("layer1.0")
+    model.close()
