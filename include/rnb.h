@@ -147,6 +147,51 @@ int rnb_model_repeat_launch(rnb_model_t* m, int batch, int index, int repeat, vo
 int rnb_model_get_activation(rnb_model_t* m, const char* name, float* out_dev, int64_t* numel,
                              void* stream);
 
+/* ---- multi-GPU: data-parallel replicas driven by ONE process. The reference has a single
+ *      device and B = 1 (cuda/inference/main.cu:230); per-image semantics are those of main.cu:168-251. ------------- */
+
+typedef struct rnb_group rnb_group_t;
+
+/* One full replica of the model on every device of `devices` (own weights, arena, stream, CUDA graphs; rnb_init() is
+ * called for each). A batch shards by image into contiguous slices, earlier replicas take the remainder
+ * (rnb_group_shard). No communication during the forward. The gather at the end is FUSED INTO THE LAST KERNELS: where
+ * devices[r] can map devices[0]'s memory (NVLink peer access, enabled here), replica r's FC epilogue (TMA store) and
+ * arg-max write their rows directly into the gathering buffers on devices[0]; otherwise (or with
+ * RNB_GROUP_GATHER=copy in the environment) they land in a local buffer and one cudaMemcpyPeerAsync per output moves
+ * them. A device may appear more than once (two replicas sharing a GPU). */
+int rnb_group_create(const char* arch, int dtype, const char* weights_dir, const int* devices, int n_devices,
+                     int max_batch_per_device, rnb_group_t** out);
+int rnb_group_destroy(rnb_group_t* g);
+int rnb_group_size(const rnb_group_t* g);
+/* Replica r (borrowed: destroyed with the group). */
+rnb_model_t* rnb_group_model(rnb_group_t* g, int r);
+/* 1 if replica r stores its results straight into the root's buffers (peer-mapped), 0 if it goes through a copy. */
+int rnb_group_direct_stores(const rnb_group_t* g, int r);
+/* Slice [*first, *first + *count) of a `batch`-image step owned by replica r. */
+int rnb_group_shard(const rnb_group_t* g, int batch, int r, int* first, int* count);
+/* Plan / autotune / capture every replica for its shard of `batch` images ahead of time (blocking). */
+int rnb_group_warmup(rnb_group_t* g, int batch);
+/* Sharded forward on device buffers. x_dev[r] is replica r's slice, [count_r,3,224,224] float32 NCHW ON devices[r];
+ * logits_root_dev [batch,classes] and top1_root_dev [batch] live ON devices[0] (either may be NULL) and receive all
+ * rows in image order. Asynchronous: every replica runs on its own stream; `root_stream` (a stream of devices[0],
+ * NULL = the group's own) is made to wait for all of them, so work enqueued on it afterwards sees the gathered
+ * results. rnb_group_synchronize() blocks until everything enqueued so far has finished. One host thread at a time. */
+int rnb_group_forward(rnb_group_t* g, const float* const* x_dev, int batch, float* logits_root_dev,
+                      int32_t* top1_root_dev, void* root_stream);
+/* Same with decoded uint8 HWC slices [count_r,224,224,3] (rnb_model_forward_u8). */
+int rnb_group_forward_u8(rnb_group_t* g, const uint8_t* const* x_dev, int batch, float* logits_root_dev,
+                         int32_t* top1_root_dev, void* root_stream);
+int rnb_group_synchronize(rnb_group_t* g);
+/* Host-buffer paths: x_host [batch,3,224,224] (pinned memory recommended); every replica copies its own slice to its
+ * device, forwards it and copies its own rows of logits_host [batch,classes] / top1_host [batch] back — the host
+ * buffer is the gather. submit/wait: two slots as rnb_model_submit_host; forward_host = submit + wait (blocking). */
+int rnb_group_submit_host(rnb_group_t* g, int slot, const float* x_host, int batch, float* logits_host,
+                          int32_t* top1_host);
+int rnb_group_submit_host_u8(rnb_group_t* g, int slot, const uint8_t* x_host, int batch, float* logits_host,
+                             int32_t* top1_host);
+int rnb_group_wait_host(rnb_group_t* g, int slot);
+int rnb_group_forward_host(rnb_group_t* g, const float* x_host, int batch, float* logits_host, int32_t* top1_host);
+
 /* ---- fused tensor-core convolution on caller-owned FP32 NCHW tensors
  *      (conv2dForwardKernel + batchNorm2dForwardKernel [+ addForwardKernel] [+ reluForwardKernel],
  *      ops.cu:14-48,139-151,153-160,130-137 as chained by layerForward, main.cu:127-166) -------- */

@@ -57,6 +57,21 @@ PROTOTYPES = {
                                     C.POINTER(C.c_int), _vp]),
     "rnb_model_repeat_launch": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
     "rnb_model_get_activation": (C.c_int, [_vp, C.c_char_p, _vp, C.POINTER(C.c_int64), _vp]),
+    "rnb_group_create": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_int,
+                                   C.POINTER(_vp)]),
+    "rnb_group_destroy": (C.c_int, [_vp]),
+    "rnb_group_size": (C.c_int, [_vp]),
+    "rnb_group_model": (_vp, [_vp, C.c_int]),
+    "rnb_group_direct_stores": (C.c_int, [_vp, C.c_int]),
+    "rnb_group_shard": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rnb_group_warmup": (C.c_int, [_vp, C.c_int]),
+    "rnb_group_forward": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, _vp, _vp, _vp]),
+    "rnb_group_forward_u8": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, _vp, _vp, _vp]),
+    "rnb_group_synchronize": (C.c_int, [_vp]),
+    "rnb_group_submit_host": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "rnb_group_submit_host_u8": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "rnb_group_wait_host": (C.c_int, [_vp, C.c_int]),
+    "rnb_group_forward_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "rnb_conv_bn_act_forward": (C.c_int, [_vp] * 8 + [C.c_int] * 10 + [_vp]),
     "rnb_stem_forward": (C.c_int, [_vp] * 7 + [C.c_int] * 4 + [_vp]),
     "rnb_tail_forward": (C.c_int, [_vp] * 5 + [C.c_int] * 4 + [_vp]),

@@ -14,10 +14,6 @@
 #include "model.h"
 #include "tensormap.h"
 
-struct rnb_model {
-    rnb::Model impl;
-};
-
 namespace rnb {
 
 namespace {
@@ -450,7 +446,9 @@ int rnb_conv_bn_act_forward(const float* x_dev, const float* w_dev, const float*
     d.in = xin; d.weight = wp; d.bias = bias; d.residual = res; d.out = y;
     ConvPlan plan;
     char err[256];
-    if (conv_plan_init(&plan, d, num_sms(), 0, err, sizeof(err))) {
+    // RNB_FORCE_TILE (tests): a conv_plan_init force_bn code, e.g. 1256 = CTA-pair tiles with BN = 256
+    const char* ft = getenv("RNB_FORCE_TILE");
+    if (conv_plan_init(&plan, d, num_sms(), ft ? atoi(ft) : 0, err, sizeof(err))) {
         set_error(err);
         return RNB_ERR_CUDA;
     }

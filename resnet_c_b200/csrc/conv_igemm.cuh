@@ -48,6 +48,11 @@ struct ConvGeom {
     // starts with the part of its input the previous kernel wrote LAST — the part still in the
     // 126 MB L2 — instead of the part that has already been evicted to HBM.
     int reverse;
+    // CTA-pair kernel only (conv_igemm2.cuh): tiles [0, split_from) are computed whole, tiles [split_from, tiles)
+    // as two independent N halves each (work units of half the duration) so that the last, partially filled
+    // wave of a persistent grid costs half a tile time. split_from is a multiple of the pair count (or 0);
+    // split_from == m_tiles * n_tiles: no split.
+    int split_from;
 };
 
 template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_, int OSZ_ = ESZ_>

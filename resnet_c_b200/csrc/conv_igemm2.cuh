@@ -21,6 +21,9 @@
 //   tmem_full[a]  one per CTA, multicast commit after the last K block of a tile
 //   tmem_empty[a] in the leader, 16 arrivals: one per epilogue warp of both CTAs (remote arrive)
 //   res_full[c] / c_full[c] / c_free[c]   per CTA (each CTA stores / prefetches the rows it owns)
+// Tail split (ConvGeom::split_from): the tiles of the last, partially filled wave are issued as two work units
+// of BN/2 columns each (own accumulator stage, B box of BN/4 rows per CTA through tmBh, instruction descriptor
+// with N = BN/2). Per column the K order is unchanged, so the result is bit-identical to the unsplit launch.
 // The epilogue works on 32 KB sub-tiles (128 rows x 256 bytes) through NCBUF rotating staging
 // buffers handed to a dedicated store warp, exactly as in the single-CTA kernel.
 #pragma once
@@ -151,7 +154,7 @@ __device__ __forceinline__ void mma_tf32_ss_2sm(uint32_t tmem_d, uint64_t adesc,
 template <class Cfg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::THREADS, 1)
 conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmOut,
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmOut,
                    const __grid_constant__ CUtensorMap tmRes, const float* __restrict__ bias,
                    const ConvGeom g) {
     using namespace ptx;
@@ -159,6 +162,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     constexpr int NSTAGE = Cfg::NSTAGE;
     constexpr int NCBUF = Cfg::NCBUF;
     constexpr int NSUB = Cfg::NSUB;
+    constexpr int HSUB = NSUB >= 2 ? NSUB / 2 : 1;  // sub-tiles of a half unit (the planner splits only if NSUB is even)
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -181,12 +185,17 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int pair = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
     const int num_tiles = g.m_tiles * g.n_tiles;       // m_tiles counts 256-pixel tiles here
-    const int my_tiles = (num_tiles - pair + num_pairs - 1) / num_pairs;
-    const int my_items = my_tiles * NSUB;              // (tile, sub-tile) epilogue work items
+    // work units: whole tiles [0, F), then the two N halves of every tile in [F, num_tiles) (see ConvGeom)
+    const int F = g.split_from;
+    const int num_units = F + 2 * (num_tiles - F);
+    const int my_tiles = (num_units - pair + num_pairs - 1) / num_pairs;   // units of this pair, whole ones first
+    const int my_full = F > pair ? (F - pair + num_pairs - 1) / num_pairs : 0;
+    const int my_items = my_full * NSUB + (my_tiles - my_full) * HSUB;      // (unit, sub-tile) epilogue work items
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (F < num_tiles) tma_prefetch_desc(&tmBh);
         tma_prefetch_desc(&tmOut);
         if (g.has_res) tma_prefetch_desc(&tmRes);
     }
@@ -219,19 +228,33 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     griddep_launch_dependents();  // see conv_igemm.cuh
     griddep_wait();
 
-    // local tile index -> (m_blk, n_blk)
-    auto tile_coords = [&](int it_local, int& m_blk, int& n_blk) {
-        const int t = pair + it_local * num_pairs;
+    // local unit index -> (m_blk, n_blk, half): half = -1 for a whole tile, 0 / 1 for the N halves of a split tile
+    auto tile_coords = [&](int it_local, int& m_blk, int& n_blk, int& half) {
+        const int u = pair + it_local * num_pairs;
+        int t = u;
+        half = -1;
+        if (u >= F) {
+            t = F + ((u - F) >> 1);
+            half = (u - F) & 1;
+        }
         const int tt = g.reverse ? num_tiles - 1 - t : t;
         n_blk = tt % g.n_tiles;
         m_blk = tt / g.n_tiles;
     };
     // epilogue work item -> first output column / first pixel row of this CTA's half
     auto item_coords = [&](int item, int& col0, int& row0) {
-        const int it_local = item / NSUB, sub = item - it_local * NSUB;
-        int m_blk, n_blk;
-        tile_coords(it_local, m_blk, n_blk);
-        col0 = n_blk * BN + sub * Cfg::EPI_N;
+        int it_local, sub;
+        if (item < my_full * NSUB) {
+            it_local = item / NSUB;
+            sub = item - it_local * NSUB;
+        } else {
+            const int j = item - my_full * NSUB;
+            it_local = my_full + j / HSUB;
+            sub = j - (j / HSUB) * HSUB;
+        }
+        int m_blk, n_blk, half;
+        tile_coords(it_local, m_blk, n_blk, half);
+        col0 = n_blk * BN + (half > 0 ? BN / 2 : 0) + sub * Cfg::EPI_N;
         row0 = m_blk * Cfg::BM + static_cast<int>(rank) * Cfg::BM_CTA;
     };
 
@@ -241,8 +264,8 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t phase = 0;
         const int ohw = g.OH * g.OW;
         for (int it = 0; it < my_tiles; ++it) {
-            int m_blk, n_blk;
-            tile_coords(it, m_blk, n_blk);
+            int m_blk, n_blk, half;
+            tile_coords(it, m_blk, n_blk, half);
             const int m0 = m_blk * Cfg::BM + static_cast<int>(rank) * Cfg::BM_CTA;
             const int img = m0 / ohw;
             const int rem = m0 - img * ohw;
@@ -250,17 +273,20 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int q = rem - p * g.OW;
             const int w0 = g.lower + q * g.stride;
             const int h0 = g.lower + p * g.stride;
-            const int nrow0 = n_blk * BN + static_cast<int>(rank) * (BN / 2);
+            const int nrow0 = half < 0 ? n_blk * BN + static_cast<int>(rank) * (BN / 2)
+                                       : n_blk * BN + half * (BN / 2) + static_cast<int>(rank) * (BN / 4);
+            const uint32_t tx_bytes = 2 * (Cfg::A_BYTES + (half < 0 ? Cfg::B_BYTES : Cfg::B_BYTES / 2));
+            const CUtensorMap* tmBu = half < 0 ? &tmB : &tmBh;
             int tap_r = 0, tap_s = 0, cblk = 0;
             for (int kb = 0; kb < g.num_kblocks; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
                     uint8_t* sa = smem_stage + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
-                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
                     tma_load_im2col_4d_2sm(sa, &tmA, &full_bar[stage], cblk * Cfg::BK, w0, h0, img,
                                            static_cast<uint16_t>(tap_s), static_cast<uint16_t>(tap_r));
-                    tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * Cfg::BK, nrow0);
+                    tma_load_2d_2sm(sb, tmBu, &full_bar[stage], kb * Cfg::BK, nrow0);
                 }
                 __syncwarp();
                 if (++cblk == g.kblocks_per_tap) {
@@ -279,8 +305,10 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else if (warp == 1) {
         // ===================================================== MMA issuer (leader CTA only)
         if (rank == 0) {
-            constexpr uint32_t idesc =
+            constexpr uint32_t idesc_full =
                 umma_instr_desc(Cfg::ESZ == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, Cfg::BM, BN);
+            constexpr uint32_t idesc_half =
+                umma_instr_desc(Cfg::ESZ == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, Cfg::BM, BN / 2);
             const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_stage), 0, 1024, UMMA_LAYOUT_SW128);
             const uint64_t b_desc0 =
                 umma_smem_desc(smem_u32(smem_stage) + Cfg::A_BYTES, 0, 1024, UMMA_LAYOUT_SW128);
@@ -292,6 +320,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
+                const uint32_t idesc = it < my_full ? idesc_full : idesc_half;
                 for (int kb = 0; kb < g.num_kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -367,8 +396,9 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            const int nsub = it < my_full ? NSUB : HSUB;
 #pragma unroll 1
-            for (int sub = 0; sub < NSUB; ++sub, ++item) {
+            for (int sub = 0; sub < nsub; ++sub, ++item) {
                 int col0, row0;
                 item_coords(item, col0, row0);
                 const int cs = item % NCBUF;
@@ -393,7 +423,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 __syncwarp();
                 if (lane == 0) {
                     // last sub-tile: this warp has drained its part of the accumulator -> tell the leader
-                    if (sub == NSUB - 1) mbar_arrive_leader(&tmem_empty[as]);
+                    if (sub == nsub - 1) mbar_arrive_leader(&tmem_empty[as]);
                     mbar_arrive(&c_full[cs]);
                 }
             }

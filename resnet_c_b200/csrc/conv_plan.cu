@@ -373,8 +373,24 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     plan->esz = esz;
     plan->ctas = ctas;
     const int tiles = g.m_tiles * g.n_tiles;
+    g.split_from = tiles;
     if (ctas == 2) {
-        const int pairs = pair_count(tiles, num_sms, 4);
+        int pairs = pair_count(tiles, num_sms, 4);
+        // Tail split (conv_igemm2.cuh): when the last wave of the persistent grid fills at most half of the
+        // pairs, its tiles run as two N halves on twice as many pairs: 98 tiles on 74 pairs take 1.5 instead
+        // of 2 tile times (layer4 at 256 images, layer3 of ResNet-152 at 128). Bit-identical. RNB_NO_SPLIT=1: off.
+        const bool no_split = getenv("RNB_NO_SPLIT") && atoi(getenv("RNB_NO_SPLIT")) != 0;
+        const int nsub = bn / (2 * (128 / esz));
+        if (!no_split && nsub % 2 == 0) {
+            const int max_pairs = num_sms / 2;
+            const int rem = tiles % pairs;
+            if (tiles > pairs && rem > 0 && 2 * rem <= pairs) {
+                g.split_from = tiles - rem;
+            } else if (2 * tiles <= max_pairs) {
+                g.split_from = 0;  // less than half a wave: every tile as two halves on 2 x tiles pairs
+                pairs = 2 * tiles;
+            }
+        }
         plan->grid = 2 * pairs;
     } else {
         plan->grid = tiles < num_sms ? tiles : num_sms;
@@ -391,6 +407,9 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     const uint64_t K = 1ull * d.ksize * d.ksize * d.Cin;
     if ((r = make_tiled_2d(&plan->tmB, dt, d.weight, d.Cout, K, ctas == 2 ? bn / 2 : bn)) != 0)
         return fail(err, errlen, "conv_plan: tiled tensor map (B) failed", r);
+    plan->tmBh = plan->tmB;
+    if (ctas == 2 && g.split_from < tiles && (r = make_tiled_2d(&plan->tmBh, dt, d.weight, d.Cout, K, bn / 4)) != 0)
+        return fail(err, errlen, "conv_plan: tiled tensor map (B, half units) failed", r);
     plan->f32out = d.out_f32 ? 1 : 0;
     if (d.out_f32) {
         if ((r = make_tiled_2d(&plan->tmOut, TmDtype::F32, d.out, M, d.out_cols, 128)) != 0)
@@ -441,7 +460,7 @@ static cudaError_t launch(const ConvPlan& p, cudaStream_t stream) {
 template <class Cfg>
 static cudaError_t launch2(const ConvPlan& p, cudaStream_t stream) {
     return launch_pdl(conv_igemm2_kernel<Cfg>, p.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, p.tmA, p.tmB,
-                      p.tmOut, p.tmRes, p.bias, p.g);
+                      p.tmBh, p.tmOut, p.tmRes, p.bias, p.g);
 }
 
 #ifdef RNB_TIMELINE

@@ -65,6 +65,7 @@ struct C3n1Desc {
 
 struct ConvPlan {
     CUtensorMap tmA, tmB, tmOut, tmRes;
+    CUtensorMap tmBh;  // CTA-pair kernel, tail split: weight boxes of bn/4 rows (ConvGeom::split_from)
     CUtensorMap tmW3, tmWds, tmW1n, tmT1n;  // fused Bottleneck tail only
     int bneck;    // 0 = plain conv, 1 = fused tail with residual tensor, 2 = fused tail with folded downsample,
                   // 3 = conv3 + next conv1 (bneck_c3n1.cuh; geometry in cg / cp), resident weights (layer2 shape),

@@ -193,3 +193,8 @@ struct Model {
 };
 
 }  // namespace rnb
+
+// the opaque handle of include/rnb.h
+struct rnb_model {
+    rnb::Model impl;
+};

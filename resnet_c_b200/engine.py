@@ -325,3 +325,80 @@ class ResNet:
         out = torch.empty(n.value, device=f"cuda:{self.device}", dtype=torch.float32)
         check(_lib.lib().rnb_model_get_activation(self._h, name.encode(), _ptr(out), C.byref(n), _stream()))
         return out
+
+
+# --------------------------------------------------------------------------- replicas on several GPUs, one process
+class ResNetGroup:
+    """rnb_group_*: one replica per device in THIS process; the batch shards by image and every replica's last
+    kernels store their rows of logits / top-1 straight into the gathering buffers on devices[0] (include/rnb.h)."""
+
+    def __init__(self, arch: str, weights_dir, devices, dtype: str = "bf16", max_batch_per_device: int = 256):
+        self.devices = [int(d) for d in devices]
+        self.arch, self.dtype = arch, dtype
+        handle = C.c_void_p()
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        check(_lib.lib().rnb_group_create(arch.encode(), DTYPES[dtype], str(weights_dir).encode(), devs,
+                                          len(self.devices), max_batch_per_device, C.byref(handle)))
+        self._h = handle
+        self.num_classes = _lib.lib().rnb_model_num_classes(_lib.lib().rnb_group_model(self._h, 0))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().rnb_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return _lib.lib().rnb_group_size(self._h)
+
+    def direct_stores(self, r: int) -> bool:
+        return bool(_lib.lib().rnb_group_direct_stores(self._h, r))
+
+    def shard(self, batch: int, r: int):
+        first, count = C.c_int(), C.c_int()
+        check(_lib.lib().rnb_group_shard(self._h, batch, r, C.byref(first), C.byref(count)))
+        return first.value, count.value
+
+    def warmup(self, batch: int) -> None:
+        check(_lib.lib().rnb_group_warmup(self._h, batch))
+
+    def forward(self, shards, logits=None, top1=None):
+        """shards[r]: replica r's slice on devices[r] (float32 [n_r,3,224,224], or uint8 [n_r,224,224,3]).
+        Returns (logits [B,classes], top1 [B]) on devices[0], valid after synchronize()."""
+        batch = sum(int(s.shape[0]) for s in shards)
+        u8 = shards[0].dtype == torch.uint8
+        root = torch.device("cuda", self.devices[0])
+        if logits is None:
+            logits = torch.empty(batch, self.num_classes, device=root, dtype=torch.float32)
+        if top1 is None:
+            top1 = torch.empty(batch, device=root, dtype=torch.int32)
+        ptrs = (C.c_void_p * len(shards))(*[s.data_ptr() if s.shape[0] else None for s in shards])
+        fn = _lib.lib().rnb_group_forward_u8 if u8 else _lib.lib().rnb_group_forward
+        check(fn(self._h, ptrs, batch, _ptr(logits), _ptr(top1), None))
+        return logits, top1
+
+    def synchronize(self) -> None:
+        check(_lib.lib().rnb_group_synchronize(self._h))
+
+    def forward_host(self, x: torch.Tensor, logits=None, top1=None):
+        """x: host [B,3,224,224] float32 -> host (logits, top1); blocking."""
+        x = x.contiguous()
+        B = x.shape[0]
+        if logits is None:
+            logits = torch.empty(B, self.num_classes, dtype=torch.float32).pin_memory()
+        if top1 is None:
+            top1 = torch.empty(B, dtype=torch.int32).pin_memory()
+        check(_lib.lib().rnb_group_forward_host(self._h, _ptr(x), B, _ptr(logits), _ptr(top1)))
+        return logits, top1
+
+    def submit_host(self, slot: int, x: torch.Tensor, logits: torch.Tensor, top1: torch.Tensor) -> None:
+        fn = _lib.lib().rnb_group_submit_host_u8 if x.dtype == torch.uint8 else _lib.lib().rnb_group_submit_host
+        check(fn(self._h, slot, _ptr(x), x.shape[0], _ptr(logits), _ptr(top1)))
+
+    def wait_host(self, slot: int) -> None:
+        check(_lib.lib().rnb_group_wait_host(self._h, slot))

@@ -137,3 +137,30 @@ def test_im2col_on_tensors_below_128_kib(oracle_lib, shape, dtype):
     Cin, Cout, H, k, stride, pad, B = shape
     e = _case(oracle_lib, Cin, Cout, H, k, stride, pad, False, True, B, dtype, seed=11)
     assert e < TOL[dtype], f"{shape} {dtype}: rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("case", [
+    # (Cin, Cout, H, k, stride, pad, residual, B, dtype, tile): pair tiles whose last wave is split into N halves
+    (256, 256, 14, 3, 1, 1, False, 128, "bf16", 1256),   # 98 tiles on 74 pairs: 24 tiles as 48 half units
+    (512, 512, 7, 1, 1, 0, True, 400, "bf16", 1256),      # 77 x 2 tiles, residual prefetch across the switch
+    (256, 256, 14, 3, 1, 1, False, 8, "bf16", 1256),      # 7 tiles: all split (14 half units)
+    (128, 128, 28, 3, 1, 1, True, 40, "tf32", 1128),      # tf32, BN = 128 (two 64-column sub-tiles)
+])
+def test_tail_split_is_bit_identical_to_whole_tiles(case, monkeypatch):
+    """conv_igemm2's tail split (ConvGeom::split_from) changes the schedule, not the arithmetic: the launch
+    with the last wave issued as N-half units equals the launch with whole tiles bit for bit."""
+    from resnet_c_b200 import engine
+    Cin, Cout, H, k, stride, pad, residual, B, dtype, tile = case
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(B, Cin, H, H, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5).cuda()
+    OH = (2 * pad + H - k) // stride + 1
+    res = torch.randn(B, Cout, OH, OH, generator=g).cuda() if residual else None
+    monkeypatch.setenv("RNB_FORCE_TILE", str(tile))
+    monkeypatch.setenv("RNB_NO_SPLIT", "1")
+    whole = engine.conv_bn_act_forward(x, w, None, res, True, stride, pad, dtype)
+    monkeypatch.setenv("RNB_NO_SPLIT", "0")
+    split = engine.conv_bn_act_forward(x, w, None, res, True, stride, pad, dtype)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, split)
+    assert float(whole.abs().max()) > 0
