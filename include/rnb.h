@@ -147,6 +147,17 @@ int rnb_model_repeat_launch(rnb_model_t* m, int batch, int index, int repeat, vo
 int rnb_model_get_activation(rnb_model_t* m, const char* name, float* out_dev, int64_t* numel,
                              void* stream);
 
+/* The step before the path, first half of the torchvision preset the reference applies to a PIL image
+ * (convert_imgs_to_bin.py:12,18): resize so that the short side is `resize` (256; long side int(resize * long / short)),
+ * antialiased bilinear with Pillow's 8-bit fixed-point arithmetic (horizontal pass, uint8 intermediate, vertical
+ * pass), then centre crop `crop` x `crop` (224; offsets int(round((size - crop) / 2.0)), half to even). Bit-exact
+ * against Pillow / torchvision. img_dev: n_images decoded images of ONE size, uint8 HWC [n][H][W][3]; out_dev
+ * [n][crop][crop][3] — the input of rnb_model_forward_u8. Coefficient tables are cached per (H, W) (the first call of
+ * a size allocates and uploads them synchronously); runs on the device that owns img_dev. JPEG decode stays on the
+ * host. */
+int rnb_resize_crop_u8(const uint8_t* img_dev, int n_images, int H, int W, uint8_t* out_dev, int resize, int crop,
+                       void* stream);
+
 /* ---- multi-GPU: data-parallel replicas driven by ONE process. The reference has a single
  *      device and B = 1 (cuda/inference/main.cu:230); per-image semantics are those of main.cu:168-251. ------------- */
 

@@ -57,6 +57,7 @@ PROTOTYPES = {
                                     C.POINTER(C.c_int), _vp]),
     "rnb_model_repeat_launch": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
     "rnb_model_get_activation": (C.c_int, [_vp, C.c_char_p, _vp, C.POINTER(C.c_int64), _vp]),
+    "rnb_resize_crop_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
     "rnb_group_create": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_int,
                                    C.POINTER(_vp)]),
     "rnb_group_destroy": (C.c_int, [_vp]),

@@ -145,6 +145,19 @@ def save_f32(t, path):
     check(_lib.lib().rnb_save_f32(_ptr(t), t.numel(), str(path).encode()))
 
 
+def resize_crop_u8(images: torch.Tensor, resize: int = 256, crop: int = 224) -> torch.Tensor:
+    """[n,H,W,3] uint8 CUDA tensor (decoded images of one size) -> [n,crop,crop,3] uint8: resize + centre crop of the
+    torchvision preset (convert_imgs_to_bin.py:12,18), Pillow arithmetic, bit-exact."""
+    if not images.is_cuda or images.dtype != torch.uint8 or images.dim() != 4 or images.shape[-1] != 3:
+        raise RnbError("resize_crop_u8 takes a [n,H,W,3] uint8 CUDA tensor")
+    images = images.contiguous()
+    n, H, W, _ = images.shape
+    out = torch.empty(n, crop, crop, 3, device=images.device, dtype=torch.uint8)
+    _lib.init(images.device.index or 0)
+    check(_lib.lib().rnb_resize_crop_u8(_ptr(images), n, H, W, _ptr(out), resize, crop, _stream()))
+    return out
+
+
 # --------------------------------------------------------------------------- fused tensor-core ops
 def conv_bn_act_forward(x, weight, bn=None, residual=None, relu=True, stride=1, padding=0,
                         dtype="bf16"):
