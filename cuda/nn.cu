@@ -48,6 +48,44 @@ bool tensorCoreEligible(const Conv2d& c)
     return (c.kernel_size == 1 || c.kernel_size == 3) && c.in_channels % 64 == 0 && c.out_channels % 64 == 0;
 }
 
+rnb_conv_params_t convParams(Conv2d& c, BatchNorm2d* bn)
+{
+    rnb_conv_params_t p{};
+    p.w = c.weight.data();
+    if (bn) {
+        p.bn_weight = bn->weight.data();
+        p.bn_bias = bn->bias.data();
+        p.bn_mean = bn->mean.data();
+        p.bn_var = bn->var.data();
+    }
+    p.Cin = asInt(c.in_channels);
+    p.Cout = asInt(c.out_channels);
+    p.k = asInt(c.kernel_size);
+    p.stride = asInt(c.stride);
+    p.pad = asInt(c.padding);
+    return p;
+}
+
+BlockPlanPtr makePlan(int kind, Precision precision, const std::vector<rnb_conv_params_t>& convs)
+{
+    rnb_block_t* b = nullptr;
+    rnbCheck(rnb_block_create(kind, static_cast<int>(precision), convs.data(), static_cast<int>(convs.size()), &b),
+             "rnb_block_create");
+    return BlockPlanPtr(b, [](rnb_block* p) { rnb_block_destroy(p); });
+}
+
+// RNB_MODULE_TC=tf32 | bf16: Conv2d::forward on tensor cores where the shape allows (default: FP32 CUDA cores)
+int moduleTcPrecision()
+{
+    static const int mode = [] {
+        const char* e = std::getenv("RNB_MODULE_TC");
+        if (!e) return -1;
+        const std::string v(e);
+        return v == "tf32" ? RNB_DTYPE_TF32 : (v == "bf16" ? RNB_DTYPE_BF16 : -1);
+    }();
+    return mode;
+}
+
 // conv -> bn -> (+residual) -> relu through the fused tcgen05 path when the shape allows it,
 // otherwise through the per-op FP32 kernels (e.g. a 3-channel input).
 void convBnAct(Conv2d& conv, BatchNorm2d& bn, FloatTensor& x, FloatTensor* residual, bool relu,
@@ -95,6 +133,17 @@ void Conv2d::forward(FloatTensor& x, FloatTensor& out)
     const auto [B, C, H, W] = x.shape().as_tuple<4>();
     assert(C == in_channels);
     assert(out.shape() == getOutShape(x.shape()));
+    if (moduleTcPrecision() >= 0 && tensorCoreEligible(*this)) {
+        if (!plan_) {
+            std::vector<rnb_conv_params_t> convs;
+            convs.push_back(convParams(*this, nullptr));
+            plan_ = makePlan(RNB_BLOCK_CONV, static_cast<Precision>(moduleTcPrecision()), convs);
+        }
+        rnbCheck(rnb_block_forward(plan_.get(), x.data(), asInt(B), asInt(H), asInt(W), nullptr, 0, out.data(), nullptr),
+                 "rnb_block_forward");
+        syncAndCheck();
+        return;
+    }
     rnbCheck(rnb_conv2d_forward(x.data(), out.data(), weight.data(), asInt(B), asInt(C), asInt(H), asInt(W),
                                 asInt(out_channels), asInt(kernel_size), asInt(stride), asInt(padding),
                                 nullptr),
@@ -180,6 +229,25 @@ void Bottleneck::forward(FloatTensor& x, FloatTensor& out)
 {
     ensureInit();
     assert(out.shape() == getOutShape(x.shape()));
+    const auto [B, C, H, W] = x.shape().as_tuple<4>();
+    if (tensorCoreEligible(conv1) && tensorCoreEligible(conv2) && tensorCoreEligible(conv3) &&
+        (!downsample || tensorCoreEligible(downsample->first))) {
+        // planned block: folded / packed weights cached, NHWC intermediates, fused layer1 tail where it applies
+        if (!plan_) {
+            std::vector<rnb_conv_params_t> convs;
+            convs.push_back(convParams(conv1, &bn1));
+            convs.push_back(convParams(conv2, &bn2));
+            convs.push_back(convParams(conv3, &bn3));
+            if (downsample) {
+                convs.push_back(convParams(downsample->first, &downsample->second));
+            }
+            plan_ = makePlan(RNB_BLOCK_BOTTLENECK, precision, convs);
+        }
+        rnbCheck(rnb_block_forward(plan_.get(), x.data(), asInt(B), asInt(H), asInt(W), nullptr, 1, out.data(), nullptr),
+                 "rnb_block_forward");
+        syncAndCheck();
+        return;
+    }
     FloatTensor shortcut(Device::GPU);
     if (downsample) {
         shortcut = FloatTensor(downsample->first.getOutShape(x.shape()), Device::GPU);
@@ -206,6 +274,22 @@ void BasicBlock::forward(FloatTensor& x, FloatTensor& out)
 {
     ensureInit();
     assert(out.shape() == getOutShape(x.shape()));
+    const auto [B, C, H, W] = x.shape().as_tuple<4>();
+    if (tensorCoreEligible(conv1) && tensorCoreEligible(conv2) && (!downsample || tensorCoreEligible(downsample->first))) {
+        if (!plan_) {
+            std::vector<rnb_conv_params_t> convs;
+            convs.push_back(convParams(conv1, &bn1));
+            convs.push_back(convParams(conv2, &bn2));
+            if (downsample) {
+                convs.push_back(convParams(downsample->first, &downsample->second));
+            }
+            plan_ = makePlan(RNB_BLOCK_BASIC, precision, convs);
+        }
+        rnbCheck(rnb_block_forward(plan_.get(), x.data(), asInt(B), asInt(H), asInt(W), nullptr, 1, out.data(), nullptr),
+                 "rnb_block_forward");
+        syncAndCheck();
+        return;
+    }
     FloatTensor shortcut(Device::GPU);
     if (downsample) {
         shortcut = FloatTensor(downsample->first.getOutShape(x.shape()), Device::GPU);

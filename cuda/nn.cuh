@@ -12,6 +12,7 @@
 #ifndef CUDA_NN_CUH
 #define CUDA_NN_CUH
 
+#include <memory>
 #include <optional>
 #include <string>
 
@@ -25,6 +26,12 @@ enum class Precision : int
     BF16 = 0,
     TF32 = 1
 };
+
+// Planned block behind a module (include/rnb.h rnb_block_*): BN folded + weights packed once, NHWC staging and launch
+// descriptors cached per input shape. Created lazily by the first forward() from the module's CURRENT weights (a copy:
+// assign new weights -> construct a new module).
+struct rnb_block;
+using BlockPlanPtr = std::shared_ptr<rnb_block>;
 
 class Conv2d
 {
@@ -56,7 +63,13 @@ public:
                       convOutputSize(x_shape[3], kernel_size, stride, padding)});
     }
 
+    // FP32 CUDA-core kernel with the reference's arithmetic order (bit-exact against ops.cu:14-48). With
+    // RNB_MODULE_TC=tf32 | bf16 in the environment, shapes the tensor cores take (k in {1,3}, channels % 64 == 0) run
+    // the tcgen05 implicit-GEMM kernel instead (<= 1e-3 / 2e-2 relative, BASELINE.json north_star).
     void forward(FloatTensor& x, FloatTensor& out);
+
+private:
+    BlockPlanPtr plan_;
 };
 
 class BatchNorm2d
@@ -213,6 +226,9 @@ public:
     }
 
     void forward(FloatTensor& x, FloatTensor& out);
+
+private:
+    BlockPlanPtr plan_;
 };
 
 // conv3x3(stride) -> bn -> relu -> conv3x3 -> bn -> (+shortcut) -> relu (torchvision BasicBlock; the
@@ -245,6 +261,9 @@ public:
     }
 
     void forward(FloatTensor& x, FloatTensor& out);
+
+private:
+    BlockPlanPtr plan_;
 };
 
 // Whole network (ResnetModel + createResnet152 + resnet152Forward + the CPU arg-max of

@@ -216,6 +216,33 @@ int rnb_conv_bn_act_forward(const float* x_dev, const float* w_dev, const float*
                             int B, int Cin, int H, int W, int Cout, int k, int stride, int pad,
                             int relu, int dtype, void* stream);
 
+/* The same as a PLANNED object, for callers that run one block many times (cuda/nn.cu's Conv2d / BasicBlock /
+ * Bottleneck modules): BN is folded and the weights are packed once, at creation (the weights are COPIED: later
+ * changes to the caller's tensors are not seen); per input shape the NHWC staging tensors and the launch descriptors
+ * are built once and cached; intermediates of a block stay NHWC between its launches. A layer1-shaped Bottleneck
+ * (64 -> 64 -> 256, stride 1, BF16) runs conv2 + conv3 + shortcut (+ downsample folded into conv3's accumulator) as
+ * ONE fused launch, like the whole-model planner. Semantics of layerForward (main.cu:127-166) / torchvision BasicBlock. */
+#define RNB_BLOCK_CONV 0        /* convs[0]                                  y = act(bn(conv(x)) [+ residual])      */
+#define RNB_BLOCK_BASIC 1       /* convs = conv1, conv2 [, downsample]       BasicBlock                             */
+#define RNB_BLOCK_BOTTLENECK 2  /* convs = conv1, conv2, conv3 [, downsample] Bottleneck (stride on conv2)          */
+typedef struct rnb_block rnb_block_t;
+typedef struct rnb_conv_params {
+    const float* w;          /* [Cout][Cin][k][k] float32, device */
+    const float* bn_weight;  /* [Cout] each, or all four NULL (no BN) */
+    const float* bn_bias;
+    const float* bn_mean;
+    const float* bn_var;
+    int Cin, Cout, k, stride, pad;
+} rnb_conv_params_t;
+int rnb_block_create(int kind, int dtype, const rnb_conv_params_t* convs, int n_convs, rnb_block_t** out);
+int rnb_block_destroy(rnb_block_t* b);
+/* x [B,Cin,H,W] -> out [B,Cout,OH,OW], float32 NCHW device tensors. residual_dev / relu: conv blocks only (a residual
+ * block adds its own shortcut and always ends in ReLU). Asynchronous on `stream`; one host thread at a time. */
+int rnb_block_forward(rnb_block_t* b, const float* x_dev, int B, int H, int W, const float* residual_dev, int relu,
+                      float* out_dev, void* stream);
+/* Tensor-core launches of the cached plan for this input shape (0 if it has not run yet). */
+int rnb_block_num_launches(rnb_block_t* b, int B, int H, int W);
+
 /* Fused stem: conv 7x7/2 pad 3 (3 -> 64) + BN + ReLU + maxpool 3x3/2 pad 1
  * (main.cu:181-192). x [B,3,H,W] -> out [B,64,OH/2,OW/2] float32 NCHW. */
 int rnb_stem_forward(const float* x_dev, const float* w_dev, const float* bn_weight_dev,

@@ -30,6 +30,13 @@ _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
 _vp = C.c_void_p
 
+class ConvParams(C.Structure):
+    """rnb_conv_params_t (include/rnb.h)."""
+    _fields_ = [("w", C.c_void_p), ("bn_weight", C.c_void_p), ("bn_bias", C.c_void_p), ("bn_mean", C.c_void_p),
+                ("bn_var", C.c_void_p), ("Cin", C.c_int), ("Cout", C.c_int), ("k", C.c_int), ("stride", C.c_int),
+                ("pad", C.c_int)]
+
+
 # name -> (restype, argtypes). Pointers to device memory are passed as integers (c_void_p).
 PROTOTYPES = {
     "rnb_init": (C.c_int, [C.c_int]),
@@ -57,6 +64,10 @@ PROTOTYPES = {
                                     C.POINTER(C.c_int), _vp]),
     "rnb_model_repeat_launch": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
     "rnb_model_get_activation": (C.c_int, [_vp, C.c_char_p, _vp, C.POINTER(C.c_int64), _vp]),
+    "rnb_block_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(ConvParams), C.c_int, C.POINTER(_vp)]),
+    "rnb_block_destroy": (C.c_int, [_vp]),
+    "rnb_block_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "rnb_block_num_launches": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     "rnb_resize_crop_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
     "rnb_group_create": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_int,
                                    C.POINTER(_vp)]),

@@ -415,3 +415,62 @@ class ResNetGroup:
 
     def wait_host(self, slot: int) -> None:
         check(_lib.lib().rnb_group_wait_host(self._h, slot))
+
+
+# --------------------------------------------------------------------------- planned block (module classes)
+class Block:
+    """rnb_block_*: one conv (+BN), BasicBlock or Bottleneck with BN folded and weights packed once (include/rnb.h).
+    `convs` is a list of dicts(w=[Cout,Cin,k,k] cuda fp32, bn=(weight,bias,mean,var)|None, stride, pad) in the
+    order conv1, conv2[, conv3][, downsample]."""
+
+    KINDS = {"conv": 0, "basic": 1, "bottleneck": 2}
+
+    def __init__(self, kind: str, convs, dtype: str = "bf16"):
+        dev = convs[0]["w"].device.index or 0
+        _lib.init(dev)
+        self.kind = kind
+        arr = (_lib.ConvParams * len(convs))()
+        self._keep = []
+        for i, c in enumerate(convs):
+            w = _f32_cuda(c["w"], "w")
+            bn = c.get("bn")
+            bnp = [None] * 4 if bn is None else [_f32_cuda(t, "bn") for t in bn]
+            self._keep += [w] + bnp
+            arr[i].w = w.data_ptr()
+            for name, t in zip(("bn_weight", "bn_bias", "bn_mean", "bn_var"), bnp):
+                setattr(arr[i], name, None if t is None else t.data_ptr())
+            arr[i].Cout, arr[i].Cin, arr[i].k = w.shape[0], w.shape[1], w.shape[2]
+            arr[i].stride, arr[i].pad = int(c.get("stride", 1)), int(c.get("pad", 0))
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            check(_lib.lib().rnb_block_create(self.KINDS[kind], DTYPES[dtype], arr, len(convs), C.byref(h)))
+        self._h = h
+        self._keep = None  # the weights were copied
+        c_last = convs[2] if kind == "bottleneck" else (convs[1] if kind == "basic" else convs[0])
+        self.cout = c_last["w"].shape[0]
+        c1, cs = convs[0], (convs[1] if kind == "bottleneck" else convs[0])
+        self._geom = (c1["w"].shape[2], int(c1.get("stride", 1)), int(c1.get("pad", 0))) if kind == "conv" else (
+            3, int(cs.get("stride", 1)), 1)
+
+    def forward(self, x, residual=None, relu=True):
+        x = _f32_cuda(x, "x")
+        B, _, H, W = x.shape
+        k, s, p = self._geom
+        out = torch.empty(B, self.cout, conv_out(H, k, s, p), conv_out(W, k, s, p), device=x.device, dtype=torch.float32)
+        res = None if residual is None else _f32_cuda(residual, "residual")
+        check(_lib.lib().rnb_block_forward(self._h, _ptr(x), B, H, W, _ptr(res), int(bool(relu)), _ptr(out), _stream()))
+        return out
+
+    def num_launches(self, B, H, W) -> int:
+        return _lib.lib().rnb_block_num_launches(self._h, B, H, W)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().rnb_block_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
