@@ -32,6 +32,11 @@ extern "C" {
  * accumulation is always FP32, logits are always FP32. */
 #define RNB_DTYPE_BF16 0
 #define RNB_DTYPE_TF32 1
+/* FP8 variant (whole-model path only): E4M3 weights with one scale per output channel and E4M3 activations with one
+ * scale per tensor, tcgen05 kind::f8f6f4 with FP32 accumulation; stem and FC stay BF16, logits FP32. The activation
+ * scales are fixed by ONE calibration pass: rnb_model_calibrate(), or implicitly the first chunk of the first
+ * forward. The reference has no reduced-precision path; the parity bar of this variant is stated in DESIGN.md. */
+#define RNB_DTYPE_FP8 2
 
 typedef struct rnb_model rnb_model_t;
 
@@ -69,6 +74,11 @@ int rnb_model_device(const rnb_model_t* m);
  * ahead of time: the first forward of a new batch size otherwise does this inside the call (a device
  * synchronisation plus trial launches — not allowed while the caller's stream is being captured). Blocking. */
 int rnb_model_warmup(rnb_model_t* m, int batch, int include_u8);
+
+/* FP8 models: fix the per-tensor activation scales from `batch` images (x_dev [batch,3,224,224] float32 NCHW,
+ * batch <= max_batch; only the first `chunk` images are used). Every conv is run on the batch with an epilogue that
+ * records max|y|; scale = max / 448 (the largest E4M3 value). Blocking. A second call is a no-op; other dtypes: no-op. */
+int rnb_model_calibrate(rnb_model_t* m, const float* x_dev, int batch);
 
 /* Pre-packed weight cache. rnb_model_save_packed() writes everything rnb_model_create() derived from the
  * save_weights.py directory (BN folded into K-major BF16/TF32 conv weights, stem / FC packs, biases) as ONE
@@ -242,6 +252,16 @@ int rnb_block_forward(rnb_block_t* b, const float* x_dev, int B, int H, int W, c
                       float* out_dev, void* stream);
 /* Tensor-core launches of the cached plan for this input shape (0 if it has not run yet). */
 int rnb_block_num_launches(rnb_block_t* b, int B, int H, int W);
+
+/* One FP8 (E4M3) convolution with explicit scales — the kernel of the RNB_DTYPE_FP8 model on caller-owned FP32 NCHW
+ * tensors (tests): x / in_scale and residual / res_scale are rounded to E4M3 (NHWC, channels zero-padded to multiples
+ * of 128), the weights are BN-folded and quantised with one scale per output channel (max|w| / 448),
+ * y = act(acc * wscale[c] * in_scale + shift[c] (+ residual_q * res_scale)) is rounded to E4M3 as y / out_scale, and
+ * out_dev receives the de-quantised result. k in {1,3}. */
+int rnb_conv_fp8_forward(const float* x_dev, const float* w_dev, const float* bn_weight_dev, const float* bn_bias_dev,
+                         const float* bn_mean_dev, const float* bn_var_dev, const float* residual_dev, float* out_dev,
+                         int B, int Cin, int H, int W, int Cout, int k, int stride, int pad, int relu, float in_scale,
+                         float res_scale, float out_scale, void* stream);
 
 /* Fused stem: conv 7x7/2 pad 3 (3 -> 64) + BN + ReLU + maxpool 3x3/2 pad 1
  * (main.cu:181-192). x [B,3,H,W] -> out [B,64,OH/2,OW/2] float32 NCHW. */

@@ -17,7 +17,8 @@ HEADER_PATH = ROOT / "include" / "rnb.h"
 RNB_OK = 0
 DTYPE_BF16 = 0
 DTYPE_TF32 = 1
-DTYPES = {"bf16": DTYPE_BF16, "tf32": DTYPE_TF32}
+DTYPE_FP8 = 2
+DTYPES = {"bf16": DTYPE_BF16, "tf32": DTYPE_TF32, "fp8": DTYPE_FP8}
 
 
 class RnbError(RuntimeError):
@@ -46,6 +47,8 @@ PROTOTYPES = {
     "rnb_model_destroy": (C.c_int, [_vp]),
     "rnb_model_device": (C.c_int, [_vp]),
     "rnb_model_warmup": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "rnb_model_calibrate": (C.c_int, [_vp, _vp, C.c_int]),
+    "rnb_conv_fp8_forward": (C.c_int, [_vp] * 8 + [C.c_int] * 9 + [C.c_float] * 3 + [_vp]),
     "rnb_model_save_packed": (C.c_int, [_vp, C.c_char_p]),
     "rnb_model_create_packed": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
     "rnb_model_forward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),

@@ -29,7 +29,7 @@ NVCC_FLAGS = [
 ]
 
 LIB_SOURCES = ["api.cu", "model.cu", "conv_plan.cu", "tensormap.cu", "ops_f32.cu", "layout.cu",
-               "stem.cu", "stem_tc.cu", "stem_tc_split.cu", "tail.cu", "group.cu", "preprocess.cu", "block.cu"]
+               "stem.cu", "stem_tc.cu", "stem_tc_split.cu", "tail.cu", "group.cu", "preprocess.cu", "block.cu", "fp8.cu"]
 
 
 def _nvcc() -> str:

@@ -251,6 +251,15 @@ int rnb_model_warmup(rnb_model_t* m, int batch, int include_u8) {
 
 int rnb_model_device(const rnb_model_t* m) { return m ? m->impl.device : -1; }
 
+int rnb_model_calibrate(rnb_model_t* m, const float* x_dev, int batch) {
+    if (!m || !x_dev || batch <= 0 || batch > m->impl.max_batch) {
+        set_error("rnb_model_calibrate: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    DeviceGuard guard(m->impl.device);
+    return m->impl.calibrate_fp8(x_dev, std::min(batch, m->impl.chunk));
+}
+
 int rnb_model_forward(rnb_model_t* m, const float* x_dev, int batch, float* logits_dev,
                       int32_t* top1_dev, void* stream) {
     if (!m) {
@@ -360,6 +369,10 @@ int rnb_model_get_activation(rnb_model_t* m, const char* name, float* out_dev, i
     }
     DeviceGuard guard(m->impl.device);
     Model& M = m->impl;
+    if (M.fp8) {
+        set_error("rnb_model_get_activation: not available for FP8 models");
+        return RNB_ERR_UNSUPPORTED;
+    }
     if (!M.arena.keep) {
         set_error("rnb_model_get_activation: activations are recycled (and aliased) by the arena; create the model with "
                   "RNB_KEEP_ACTIVATIONS=1 in the environment to keep them");
@@ -454,6 +467,58 @@ int rnb_conv_bn_act_forward(const float* x_dev, const float* w_dev, const float*
     }
     API_CUDA(conv_plan_launch(plan, s));
     API_CUDA(launch_nhwc_to_nchw(y, out_dev, B, Cout, OH * OW, esz, s));
+    return RNB_OK;
+}
+
+int rnb_conv_fp8_forward(const float* x_dev, const float* w_dev, const float* bn_weight_dev, const float* bn_bias_dev,
+                         const float* bn_mean_dev, const float* bn_var_dev, const float* residual_dev, float* out_dev,
+                         int B, int Cin, int H, int W, int Cout, int k, int stride, int pad, int relu, float in_scale,
+                         float res_scale, float out_scale, void* stream) {
+    API_ON_DEVICE_OF(x_dev);
+    int r = require_init();
+    if (r) return r;
+    const int nbn = (bn_weight_dev != nullptr) + (bn_bias_dev != nullptr) + (bn_mean_dev != nullptr) +
+                    (bn_var_dev != nullptr);
+    if (!x_dev || !w_dev || !out_dev || B <= 0 || H <= 0 || W <= 0 || stride <= 0 || pad < 0 || (k != 1 && k != 3) ||
+        (nbn != 0 && nbn != 4) || !(in_scale > 0.f) || !(out_scale > 0.f) || (residual_dev && !(res_scale > 0.f)) ||
+        2 * pad + H < k || 2 * pad + W < k) {
+        set_error("rnb_conv_fp8_forward: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int cin_p = (Cin + 127) / 128 * 128, cout_p = (Cout + 127) / 128 * 128;
+    const int OH = (2 * pad + H - k) / stride + 1, OW = (2 * pad + W - k) / stride + 1;
+    void *xin = nullptr, *wp = nullptr, *res = nullptr, *y = nullptr;
+    float *bias = nullptr, *wscale = nullptr, *vecs = nullptr;
+    AsyncTemps tmp(s);
+    API_CUDA(tmp.alloc(&xin, 1ull * B * H * W * cin_p));
+    API_CUDA(tmp.alloc(&wp, 1ull * cout_p * k * k * cin_p));
+    API_CUDA(tmp.alloc(&y, 1ull * B * OH * OW * cout_p));
+    API_CUDA(tmp.alloc(reinterpret_cast<void**>(&bias), cout_p * sizeof(float)));
+    API_CUDA(tmp.alloc(reinterpret_cast<void**>(&wscale), cout_p * sizeof(float)));
+    API_CUDA(tmp.alloc(reinterpret_cast<void**>(&vecs), 2ull * cout_p * sizeof(float)));
+    if (residual_dev) API_CUDA(tmp.alloc(&res, 1ull * B * OH * OW * cout_p));
+    API_CUDA(launch_nchw_to_nhwc_fp8(x_dev, xin, B, Cin, cin_p, H * W, 1.f / in_scale, s));
+    if (residual_dev) API_CUDA(launch_nchw_to_nhwc_fp8(residual_dev, res, B, Cout, cout_p, OH * OW, 1.f / res_scale, s));
+    API_CUDA(launch_fold_pack_fp8(w_dev, bn_weight_dev, bn_bias_dev, bn_mean_dev, bn_var_dev, wp, wscale, bias, Cout, Cin,
+                                  k, cout_p, cin_p, s));
+    ConvDesc d{};
+    d.B = B; d.H = H; d.W = W; d.Cin = cin_p; d.Cout = cout_p; d.ksize = k; d.stride = stride; d.pad = pad;
+    d.relu = relu != 0;
+    d.act = ActType::FP8;
+    d.in = xin; d.weight = wp; d.bias = bias; d.residual = res; d.out = y;
+    d.chan_scale = wscale; d.in_scale = in_scale; d.res_scale = res_scale; d.out_scale = out_scale;
+    d.fp8_vecs = vecs;
+    ConvPlan plan;
+    char err[256];
+    const char* ft = getenv("RNB_FORCE_TILE");
+    if (conv_plan_init(&plan, d, num_sms(), ft ? atoi(ft) : 0, err, sizeof(err))) {
+        set_error(err);
+        return RNB_ERR_CUDA;
+    }
+    API_CUDA(fp8_premultiply(&plan, in_scale, res_scale, out_scale, s));
+    API_CUDA(conv_plan_launch(plan, s));
+    API_CUDA(launch_nhwc_fp8_to_nchw(y, out_dev, B, Cout, cout_p, OH * OW, out_scale, s));
     return RNB_OK;
 }
 

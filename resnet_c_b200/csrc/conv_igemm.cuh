@@ -28,6 +28,8 @@
 // tensors, i.e. most of the HBM traffic of the network): it never waits for a store or issues one —
 // it only signals c_full[buf] and moves on; warp 3 does the rest.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "sm100_ptx.cuh"
 
 namespace rnb {
@@ -53,6 +55,16 @@ struct ConvGeom {
     // wave of a persistent grid costs half a tile time. split_from is a multiple of the pair count (or 0);
     // split_from == m_tiles * n_tiles: no split.
     int split_from;
+    // FP8 (E4M3) path only, ESZ == 1. Real value = stored value x scale. With the per-tensor
+    // activation scales s_in, s_res, s_out fixed by calibration and one weight scale per output channel w[c]:
+    //   q_out = RN_e4m3( relu( acc * chan_scale[c] + bias[c] + q_res * res_mul ) )
+    //   chan_scale[c] = w[c] * s_in / s_out, bias[c] = shift[c] / s_out (the `bias` kernel argument), res_mul = s_res / s_out
+    // — the per-channel vectors are pre-multiplied on the host side (conv_plan.cu::fp8_premultiply) so that the epilogue
+    // spends one FMA per output. amax != nullptr: calibration launch (s_out = 1) — the kernel also max-reduces the
+    // value before rounding (after the ReLU, rows < M only) into *amax (non-negative float bit pattern, atomicMax).
+    const float* chan_scale;
+    float res_mul;
+    float* amax;
 };
 
 template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_, int OSZ_ = ESZ_>
@@ -69,6 +81,7 @@ struct ConvCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BOX_COLS = 128 / OSZ_;      // output columns per 128-byte staging row
     static constexpr int NBOX = BN_ / BOX_COLS;
+    static_assert(BN_ % BOX_COLS == 0, "tile N must be a whole number of staging boxes (FP8: BN >= 128)");
     static constexpr int BOX_BYTES = BM * 128;
     static constexpr int CBUF_BYTES = NBOX * BOX_BYTES;
     static constexpr int TMEM_COLS = 2 * BN_;        // two accumulator stages
@@ -198,6 +211,86 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint8_t*
             }
         }
     }
+}
+
+// ---- FP8 (E4M3) epilogue
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+    uint16_t lo, hi;  // cvt packs its FIRST source into the upper byte: the element with the lower address goes second
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+    return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+__device__ __forceinline__ void unpack_e4m3x4(uint32_t v, float (&o)[4]) {
+    uint32_t h01, h23;
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h01) : "h"(static_cast<uint16_t>(v & 0xFFFFu)));
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h23) : "h"(static_cast<uint16_t>(v >> 16)));
+    const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+    const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+    o[0] = f01.x; o[1] = f01.y; o[2] = f23.x; o[3] = f23.y;
+}
+
+__device__ __forceinline__ uint32_t pack_e4m3x4_relu(float a, float b, float c, float d) {
+    uint16_t lo, hi;
+    asm("cvt.rn.satfinite.relu.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.relu.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+    return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+
+// One 32-column chunk of the accumulator on the FP8 path: 32 output bytes = two 16-byte pieces of the staging row.
+// scale32 / bias32 are PRE-MULTIPLIED per channel (ConvGeom): q = RN_e4m3(relu(acc * scale'[c] + bias'[c] + r * res'))
+// — one FMA (two with a residual) and half a convert per output. `track`: calibration launch, returns max|q value
+// before rounding| of the chunk (0 otherwise).
+__device__ __forceinline__ float epilogue_chunk_fp8(const uint32_t (&v)[32], uint8_t* row, uint32_t c16_base,
+                                                    uint32_t swz, const float* __restrict__ scale32,
+                                                    const float* __restrict__ bias32, float res_mul, int has_res,
+                                                    int relu, bool track) {
+    const uint32_t row_addr = ptx::smem_u32(row);
+    uint4 rr[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) rr[j] = lds128(row_addr + (((c16_base + j) ^ swz) << 4));
+    }
+    float4 sc[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = __ldg(reinterpret_cast<const float4*>(scale32 + j * 4));
+        b[j] = __ldg(reinterpret_cast<const float4*>(bias32 + j * 4));
+    }
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const uint32_t rw[4] = {rr[j].x, rr[j].y, rr[j].z, rr[j].w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int g4 = j * 4 + q;  // group of four columns
+            float x[4];
+            x[0] = fmaf(__uint_as_float(v[g4 * 4 + 0]), sc[g4].x, b[g4].x);
+            x[1] = fmaf(__uint_as_float(v[g4 * 4 + 1]), sc[g4].y, b[g4].y);
+            x[2] = fmaf(__uint_as_float(v[g4 * 4 + 2]), sc[g4].z, b[g4].z);
+            x[3] = fmaf(__uint_as_float(v[g4 * 4 + 3]), sc[g4].w, b[g4].w);
+            if (has_res) {
+                float r[4];
+                unpack_e4m3x4(rw[q], r);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] = fmaf(r[e], res_mul, x[e]);
+            }
+            if (track) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) amax = fmaxf(amax, relu ? x[e] : fabsf(x[e]));
+            }
+            ow[q] = relu ? pack_e4m3x4_relu(x[0], x[1], x[2], x[3]) : pack_e4m3x4(x[0], x[1], x[2], x[3]);
+        }
+        sts128(row_addr + (((c16_base + j) ^ swz) << 4), ow[0], ow[1], ow[2], ow[3]);
+    }
+    return amax;
+}
+
+// calibration launches: fold this thread's maximum into *amax (warp reduce, one atomic per warp)
+__device__ __forceinline__ void amax_commit(float* amax, float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(v));
 }
 
 // FP32-output variant (the FC layer: logits stay FP32): 32 columns = one full 128-byte staging row,
@@ -344,8 +437,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ===================================================== MMA issuer
         // Descriptors are a per-kernel constant plus (stage offset + 32-byte K step) >> 4 in the
         // address field.
-        constexpr uint32_t idesc =
-            umma_instr_desc(Cfg::ESZ == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, Cfg::BM, BN);
+        constexpr uint32_t idesc = umma_instr_desc(
+            Cfg::ESZ == 2 ? UMMA_FMT_BF16 : (Cfg::ESZ == 4 ? UMMA_FMT_TF32 : UMMA_FMT_E4M3), Cfg::BM, BN);
         const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_stage), 0, 1024, UMMA_LAYOUT_SW128);
         const uint64_t b_desc0 =
             umma_smem_desc(smem_u32(smem_stage) + Cfg::A_BYTES, 0, 1024, UMMA_LAYOUT_SW128);
@@ -369,8 +462,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const uint64_t bd = b_desc0 + soff + static_cast<uint64_t>(k * 2);
                         if (Cfg::ESZ == 2)
                             mma_f16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
-                        else
+                        else if (Cfg::ESZ == 4)
                             mma_tf32_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                        else
+                            mma_f8_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
                     }
                     tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                     if (kb == g.num_kblocks - 1) tc_commit(&tmem_full[as]);  // accumulator complete
@@ -447,6 +542,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
             const float* bias_n = bias + n_blk * BN;
+            float amax = 0.f;
 #pragma unroll 1
             for (int chunk = h; chunk < BN / 32; chunk += 2) {
                 uint32_t v[32];
@@ -455,12 +551,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tmem_ld_wait();
                 const int byte_off = chunk * 32 * Cfg::OSZ;
                 uint8_t* row = cbuf + (byte_off >> 7) * Cfg::BOX_BYTES + row_in_tile * 128;
-                if (Cfg::OSZ != Cfg::ESZ)
+                if (Cfg::ESZ == 1)
+                    amax = fmaxf(amax, epilogue_chunk_fp8(v, row, (byte_off & 127) >> 4, swz,
+                                                          g.chan_scale + n_blk * BN + chunk * 32, bias_n + chunk * 32,
+                                                          g.res_mul, g.has_res, g.relu, g.amax != nullptr));
+                else if (Cfg::OSZ != Cfg::ESZ)
                     epilogue_chunk_f32out(v, row, swz, bias_n + chunk * 32, g.relu);
                 else
-                    epilogue_chunk<Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz, bias_n + chunk * 32,
-                                             g.has_res, g.relu);
+                    epilogue_chunk<Cfg::ESZ == 1 ? 2 : Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz, bias_n + chunk * 32,
+                                                                 g.has_res, g.relu);
             }
+            if (Cfg::ESZ == 1 && g.amax) amax_commit(g.amax, m_blk * Cfg::BM + row_in_tile < g.M ? amax : 0.f);
             // accumulator drained by this warp: hand the TMEM stage back; publish the staged rows
             // to the async proxy and tell the store warp
             tc_fence_before();

@@ -44,10 +44,11 @@ struct Conv2Cfg {
     static constexpr int B_BYTES = (BN_ / 2) * 128;    // this CTA's half of the weight tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BOX_COLS = 128 / ESZ_;
-    static constexpr int EPI_N = 2 * BOX_COLS;         // columns per epilogue sub-tile (256 bytes / row)
+    static constexpr int SUB_BOXES = ESZ_ == 1 ? 1 : 2;  // 128-byte boxes per epilogue sub-tile (FP8: one box = 128 columns)
+    static constexpr int EPI_N = SUB_BOXES * BOX_COLS;   // columns per epilogue sub-tile
     static constexpr int NSUB = BN_ / EPI_N;
     static constexpr int BOX_BYTES = BM_CTA * 128;
-    static constexpr int CBUF_BYTES = 2 * BOX_BYTES;   // 32 KB
+    static constexpr int CBUF_BYTES = SUB_BOXES * BOX_BYTES;   // 32 KB (16 KB on the FP8 path)
     static constexpr int TMEM_COLS = 2 * BN_;
     static constexpr int NBAR = 2 * NSTAGE_ + 4 + 3 * NCBUF_;
     static constexpr int SMEM_BYTES =
@@ -126,6 +127,18 @@ __device__ __forceinline__ void mma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, 
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_f8_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
         "}\n"
         :
         : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
@@ -305,10 +318,9 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else if (warp == 1) {
         // ===================================================== MMA issuer (leader CTA only)
         if (rank == 0) {
-            constexpr uint32_t idesc_full =
-                umma_instr_desc(Cfg::ESZ == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, Cfg::BM, BN);
-            constexpr uint32_t idesc_half =
-                umma_instr_desc(Cfg::ESZ == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, Cfg::BM, BN / 2);
+            constexpr uint32_t fmt = Cfg::ESZ == 2 ? UMMA_FMT_BF16 : (Cfg::ESZ == 4 ? UMMA_FMT_TF32 : UMMA_FMT_E4M3);
+            constexpr uint32_t idesc_full = umma_instr_desc(fmt, Cfg::BM, BN);
+            constexpr uint32_t idesc_half = umma_instr_desc(fmt, Cfg::BM, BN / 2);
             const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_stage), 0, 1024, UMMA_LAYOUT_SW128);
             const uint64_t b_desc0 =
                 umma_smem_desc(smem_u32(smem_stage) + Cfg::A_BYTES, 0, 1024, UMMA_LAYOUT_SW128);
@@ -332,8 +344,10 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             const uint64_t bd = b_desc0 + soff + static_cast<uint64_t>(k * 2);
                             if (Cfg::ESZ == 2)
                                 mma_f16_ss_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
-                            else
+                            else if (Cfg::ESZ == 4)
                                 mma_tf32_ss_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                            else
+                                mma_f8_ss_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
                         }
                         tc_commit_2sm(&empty_bar[stage]);
                         if (kb == g.num_kblocks - 1) tc_commit_2sm(&tmem_full[as]);
@@ -355,7 +369,8 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             uint8_t* buf = smem_c + cs * Cfg::CBUF_BYTES;
             mbar_expect_tx(&res_full[cs], Cfg::CBUF_BYTES);
             tma_load_2d(buf, &tmRes, &res_full[cs], col0, row0);
-            tma_load_2d(buf + Cfg::BOX_BYTES, &tmRes, &res_full[cs], col0 + Cfg::BOX_COLS, row0);
+            if (Cfg::SUB_BOXES == 2)
+                tma_load_2d(buf + Cfg::BOX_BYTES, &tmRes, &res_full[cs], col0 + Cfg::BOX_COLS, row0);
         };
         if (g.has_res && elect_one()) {
             for (int i = 0; i < NCBUF && i < my_items; ++i) issue_residual(i);
@@ -369,7 +384,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 item_coords(item, col0, row0);
                 const uint8_t* cbuf = smem_c + cs * Cfg::CBUF_BYTES;
                 tma_store_2d(&tmOut, cbuf, col0, row0);
-                tma_store_2d(&tmOut, cbuf + Cfg::BOX_BYTES, col0 + Cfg::BOX_COLS, row0);
+                if (Cfg::SUB_BOXES == 2) tma_store_2d(&tmOut, cbuf + Cfg::BOX_BYTES, col0 + Cfg::BOX_COLS, row0);
                 tma_store_commit();
                 tma_store_wait_read<0>();
                 if (item + NCBUF < my_items) {
@@ -407,6 +422,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     mbar_wait(&res_full[cs], (item / NCBUF) & 1);
                 else if (item >= NCBUF)
                     mbar_wait(&c_free[cs], ((item / NCBUF) - 1) & 1);
+                float amax = 0.f;
 #pragma unroll 1
                 for (int chunk = h; chunk < Cfg::EPI_N / 32; chunk += 2) {
                     uint32_t v[32];
@@ -415,9 +431,15 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     tmem_ld_wait();
                     const int byte_off = chunk * 32 * Cfg::ESZ;
                     uint8_t* row = cbuf + (byte_off >> 7) * Cfg::BOX_BYTES + row_in_tile * 128;
-                    epilogue_chunk<Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz,
-                                             bias + col0 + chunk * 32, g.has_res, g.relu);
+                    if (Cfg::ESZ == 1)
+                        amax = fmaxf(amax, epilogue_chunk_fp8(v, row, (byte_off & 127) >> 4, swz,
+                                                              g.chan_scale + col0 + chunk * 32, bias + col0 + chunk * 32,
+                                                              g.res_mul, g.has_res, g.relu, g.amax != nullptr));
+                    else
+                        epilogue_chunk<Cfg::ESZ == 1 ? 2 : Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz,
+                                                                     bias + col0 + chunk * 32, g.has_res, g.relu);
                 }
+                if (Cfg::ESZ == 1 && g.amax) amax_commit(g.amax, row0 + row_in_tile < g.M ? amax : 0.f);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();

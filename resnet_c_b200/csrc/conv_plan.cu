@@ -22,6 +22,13 @@ using Cfg2Bf16N256 = Conv2Cfg<256, 2, 4, 3>;
 using Cfg2Bf16N128 = Conv2Cfg<128, 2, 5, 3>;
 using Cfg2Tf32N256 = Conv2Cfg<256, 4, 4, 3>;
 using Cfg2Tf32N128 = Conv2Cfg<128, 4, 5, 3>;
+// FP8 (E4M3, kind::f8f6f4): 128 channels per K block, 128 output bytes per staging row
+using CfgFp8N128 = ConvCfg<128, 1, 5, 3>;
+using Cfg2Fp8N256 = Conv2Cfg<256, 1, 5, 3>;
+using Cfg2Fp8N128 = Conv2Cfg<128, 1, 6, 3>;
+static_assert(CfgFp8N128::SMEM_BYTES <= 232448, "smem budget");
+static_assert(Cfg2Fp8N256::SMEM_BYTES <= 232448, "smem budget");
+static_assert(Cfg2Fp8N128::SMEM_BYTES <= 232448, "smem budget");
 // deep variants (bf16 only): one/two more pipeline stages, two staging buffers
 using CfgBf16N128D = ConvCfg<128, 2, 5, 2>;
 using CfgBf16N64F32 = ConvCfg<64, 2, 4, 3, 4>;  // BF16 operands, FP32 output (FC)
@@ -62,6 +69,9 @@ cudaError_t conv_kernels_init() {
     if ((e = set_smem2<Cfg2Bf16N128>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Tf32N256>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Tf32N128>()) != cudaSuccess) return e;
+    if ((e = set_smem<CfgFp8N128>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Fp8N256>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Fp8N128>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgBf16N128D>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgBf16N64F32>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Bf16N256D>()) != cudaSuccess) return e;
@@ -302,12 +312,18 @@ int c3n1_plan_init(ConvPlan* plan, const C3n1Desc& d, int num_sms, char* err, in
 int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn, char* err,
                    int errlen) {
     memset(plan, 0, sizeof(*plan));
+    if (d.act == ActType::FP8) {
+        if (d.out_f32 || !d.chan_scale || !d.fp8_vecs || d.Cout % 128 != 0 || !(d.out_scale > 0.f))
+            return fail(err, errlen, "conv_plan: FP8 needs channel scales + scratch, Cout % 128 == 0 and a positive output scale", -9);
+        if (force_bn == 64 || force_bn == 3064 || force_bn == 4064 || force_bn >= 10000)
+            return fail(err, errlen, "conv_plan: tile family not available in FP8", -9);
+    }
     if (d.out_f32) {
         if (d.act != ActType::BF16 || d.residual || d.out_cols <= 0 || d.out_cols > d.Cout || d.out_cols % 4 != 0)
             return fail(err, errlen, "conv_plan: FP32-output mode needs BF16 operands, no residual, out_cols % 4 == 0", -8);
         force_bn = 64;
     }
-    if (force_bn == 3064 || (force_bn == 0 && conv_plan_halo_ok(d) && !getenv("RNB_NO_HALO")))
+    if (force_bn == 3064 || (force_bn == 0 && d.act != ActType::FP8 && conv_plan_halo_ok(d) && !getenv("RNB_NO_HALO")))
         return halo_plan_init(plan, d, num_sms, err, errlen);
     if (force_bn == 4064 || (force_bn == 0 && conv_plan_halo2_ok(d) && !getenv("RNB_NO_HALO")))
         return halo2_plan_init(plan, d, num_sms, err, errlen);
@@ -374,13 +390,19 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     plan->ctas = ctas;
     const int tiles = g.m_tiles * g.n_tiles;
     g.split_from = tiles;
+    g.chan_scale = d.chan_scale;
+    g.res_mul = 1.f;
+    g.amax = nullptr;
+    plan->fp8_wscale = d.chan_scale;
+    plan->fp8_shift = d.bias;
+    plan->fp8_vecs = d.fp8_vecs;
     if (ctas == 2) {
         int pairs = pair_count(tiles, num_sms, 4);
         // Tail split (conv_igemm2.cuh): when the last wave of the persistent grid fills at most half of the
         // pairs, its tiles run as two N halves on twice as many pairs: 98 tiles on 74 pairs take 1.5 instead
         // of 2 tile times (layer4 at 256 images, layer3 of ResNet-152 at 128). Bit-identical. RNB_NO_SPLIT=1: off.
         const bool no_split = getenv("RNB_NO_SPLIT") && atoi(getenv("RNB_NO_SPLIT")) != 0;
-        const int nsub = bn / (2 * (128 / esz));
+        const int nsub = esz == 1 ? bn / 128 : bn / (2 * (128 / esz));  // Conv2Cfg::NSUB
         if (!no_split && nsub % 2 == 0) {
             const int max_pairs = num_sms / 2;
             const int rem = tiles % pairs;
@@ -399,7 +421,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     plan->bytes = 1.0 * d.B * d.H * d.W * d.Cin * esz + 1.0 * d.Cout * d.ksize * d.ksize * d.Cin * esz +
                   4.0 * d.Cout + (d.residual ? 2.0 : 1.0) * static_cast<double>(M) * d.Cout * esz;
 
-    const TmDtype dt = d.act == ActType::BF16 ? TmDtype::BF16 : TmDtype::F32;
+    const TmDtype dt = d.act == ActType::BF16 ? TmDtype::BF16 : (d.act == ActType::FP8 ? TmDtype::U8 : TmDtype::F32);
     int r;
     if ((r = make_im2col_nhwc(&plan->tmA, dt, d.in, d.B, d.H, d.W, d.Cin, d.ksize, d.stride, d.pad,
                               128)) != 0)
@@ -425,6 +447,27 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     else if ((r = make_tiled_2d(&plan->tmRes, dt, res, M, d.Cout, 128)) != 0)
         return fail(err, errlen, "conv_plan: tiled tensor map (residual) failed", r);
     return 0;
+}
+
+namespace {
+__global__ void fp8_premultiply_kernel(const float* __restrict__ wscale, const float* __restrict__ shift,
+                                       float* __restrict__ vecs, int n, float in_over_out, float inv_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        vecs[i] = wscale[i] * in_over_out;
+        vecs[n + i] = shift[i] * inv_out;
+    }
+}
+}  // namespace
+
+cudaError_t fp8_premultiply(ConvPlan* plan, float in_scale, float res_scale, float out_scale, cudaStream_t stream) {
+    const int n = plan->g.Cout;
+    fp8_premultiply_kernel<<<(n + 255) / 256, 256, 0, stream>>>(plan->fp8_wscale, plan->fp8_shift, plan->fp8_vecs, n,
+                                                               in_scale / out_scale, 1.f / out_scale);
+    plan->g.chan_scale = plan->fp8_vecs;
+    plan->bias = plan->fp8_vecs + n;
+    plan->g.res_mul = res_scale / out_scale;
+    return cudaGetLastError();
 }
 
 // Every conv kernel is launched with programmatic stream serialization (PDL): its prologue may run
@@ -516,6 +559,10 @@ cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
     if (p.halo) {
         return launch_pdl(conv3x3_halo_kernel<HaloCfg>, p.grid, HaloCfg::THREADS, HaloCfg::SMEM_BYTES, stream,
                           p.tmA, p.tmB, p.tmOut, p.bias, p.hg);
+    }
+    if (p.esz == 1) {
+        if (p.ctas == 2) return p.bn == 256 ? launch2<Cfg2Fp8N256>(p, stream) : launch2<Cfg2Fp8N128>(p, stream);
+        return launch<CfgFp8N128>(p, stream);
     }
     if (p.f32out) return launch<CfgBf16N64F32>(p, stream);
     if (p.deep && p.esz == 2) {

@@ -11,7 +11,7 @@
 
 namespace rnb {
 
-enum class ActType { BF16 = 2, TF32 = 4 };  // value = bytes per element
+enum class ActType { FP8 = 1, BF16 = 2, TF32 = 4 };  // value = bytes per element (FP8 = E4M3, scaled)
 
 struct ConvDesc {
     int B, H, W, Cin, Cout, ksize, stride, pad;
@@ -27,6 +27,11 @@ struct ConvDesc {
     // out_cols <= Cout (weights / bias are padded to Cout rows; the padded columns are clipped by TMA)
     bool out_f32 = false;
     int out_cols = 0;
+    // FP8 only (see ConvGeom): per-output-channel weight scales, per-tensor activation scales, and a device scratch
+    // of 2 * Cout floats that receives the pre-multiplied epilogue vectors (fp8_premultiply)
+    const float* chan_scale = nullptr;  // [Cout] weight scales
+    float in_scale = 1.f, res_scale = 1.f, out_scale = 1.f;
+    float* fp8_vecs = nullptr;          // [2][Cout]: chan_scale', bias'
 };
 
 // Fused layer1 Bottleneck tail (bneck_l1.cuh): conv2 3x3 + conv3 1x1 + shortcut + ReLU, optionally
@@ -90,6 +95,10 @@ struct ConvPlan {
     int grid;     // persistent CTAs
     int side;     // 1 = launched on the engine's side stream (downsample conv overlapped with conv1/conv2)
     int join;     // 1 = must wait for the side stream before it starts (consumes the downsample output)
+    // FP8: the un-multiplied vectors and the scratch the kernel reads (kept so that calibration can re-scale a plan)
+    const float* fp8_wscale;
+    const float* fp8_shift;
+    float* fp8_vecs;
     double flops;  // 2*M*N*K
     double bytes;  // algorithmic HBM bytes: input + weights + bias (+ residual) read once, output written once
 };
@@ -106,6 +115,9 @@ bool bneck_plan_ok(int H, int W, int esz);
 bool c3n1_shape_ok(int K3, int N3, int N1);
 int c3n1_plan_init(ConvPlan* plan, const C3n1Desc& d, int num_sms, char* err, int errlen);
 int bneck_plan_init(ConvPlan* plan, const BneckDesc& d, int num_sms, char* err, int errlen);
+// FP8: (re)compute the pre-multiplied epilogue vectors of a plan for the given per-tensor scales and point the launch
+// geometry at them: chan_scale' = wscale * in / out, bias' = shift / out, res_mul = res / out. Enqueued on `stream`.
+cudaError_t fp8_premultiply(ConvPlan* plan, float in_scale, float res_scale, float out_scale, cudaStream_t stream);
 // Enqueues the kernel on `stream` (no synchronisation).
 cudaError_t conv_plan_launch(const ConvPlan& plan, cudaStream_t stream);
 // One-time per process: raise the dynamic shared memory limit of every kernel instantiation.

@@ -55,6 +55,10 @@ int rnb_group_create(const char* arch, int dtype, const char* weights_dir, const
         set_error("rnb_group_create: bad argument");
         return RNB_ERR_INVALID;
     }
+    if (dtype == RNB_DTYPE_FP8) {
+        set_error("rnb_group_create: the FP8 variant is single-model (its scales come from one calibration batch)");
+        return RNB_ERR_UNSUPPORTED;
+    }
     int prev = -1;
     cudaGetDevice(&prev);
     std::unique_ptr<rnb_group> g(new rnb_group());

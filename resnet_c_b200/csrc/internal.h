@@ -100,6 +100,19 @@ cudaError_t launch_fold_f32(const float* w, const float* bn_w, const float* bn_b
                             const float* bn_v, float* w_out, float* bias, int Cout, int per_out,
                             cudaStream_t s);
 
+// ---- FP8 (E4M3) quantisation (fp8.cu). Weights: BN folded in double, one scale per output channel, channels padded
+// to Cout_pad / Cin_pad (multiples of 128); activations: per-tensor scale.
+cudaError_t launch_fold_pack_fp8(const float* w, const float* bn_w, const float* bn_b, const float* bn_m,
+                                 const float* bn_v, void* packed, float* wscale, float* bias, int Cout, int Cin, int k,
+                                 int Cout_pad, int Cin_pad, cudaStream_t s);
+cudaError_t launch_amax_bf16(const void* x, int64_t n, float* amax, cudaStream_t s);
+cudaError_t launch_quantize_pad_bf16(const void* x, void* out, int64_t rows, int C, int Cpad, float inv_scale,
+                                     cudaStream_t s);
+cudaError_t launch_nchw_to_nhwc_fp8(const float* x, void* out, int B, int C, int Cpad, int HW, float inv_scale,
+                                    cudaStream_t s);
+cudaError_t launch_nhwc_fp8_to_nchw(const void* x, float* out, int B, int C, int Cpad, int HW, float scale,
+                                    cudaStream_t s);
+
 // ---- stem + max-pool (stem.cu)
 // conv 7x7/2 pad 3, 3 -> 64, + bias + ReLU: x fp32 NCHW [B,3,H,W] -> out NHWC [B,OH,OW,64].
 cudaError_t launch_stem_conv(const float* x, const float* w_folded /*[64][3][7][7]*/,
@@ -164,8 +177,9 @@ inline cudaError_t launch_stem_any_part(int esz, int part, const float* x, void*
 // (+ optional row-major BF16 copy pooled_bf16[B][C] for the tensor-core FC; BF16 activations only)
 // With pooled_bf16 (tensor-core FC) the FP32 result is written ROW-MAJOR [B][C] instead (nobody reads it on the hot
 // path; rnb_model_get_activation hands it out).
+// esz == 1: x is E4M3 with per-tensor scale `in_scale` (pooled_bf16 required).
 cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, void* pooled_bf16, int B, int HW, int C, int esz,
-                                cudaStream_t s);
+                                cudaStream_t s, float in_scale = 1.f);
 // fc.weight [classes][C] fp32 -> [cpad][C] bf16 (zero rows beyond classes), fc.bias -> [cpad] fp32
 cudaError_t launch_fc_pack(const float* w, const float* b, void* wq, float* bq, int classes, int C, int cpad,
                            cudaStream_t s);

@@ -121,6 +121,17 @@ int load_conv(const std::string& dir, const std::string& cname, const std::strin
     if ((r = load_bn(dir, bname, Cout, bn))) return r;
     // cw.w / cw.bias belong to the model from here on (Model::~Model frees them, also after a failed load)
     cw.Cin = Cin; cw.Cout = Cout; cw.k = k; cw.stride = stride; cw.pad = pad;
+    if (esz == 1) {  // FP8: channels padded to whole 128-byte K blocks / staging boxes, per-channel scales
+        const int cin_p = (Cin + 127) / 128 * 128, cout_p = (Cout + 127) / 128 * 128;
+        cw.Cin = cin_p; cw.Cout = cout_p;
+        RNB_CUDA(cudaMalloc(&cw.w, 1ull * cout_p * cin_p * k * k));
+        RNB_CUDA(cudaMalloc(&cw.bias, cout_p * sizeof(float)));
+        RNB_CUDA(cudaMalloc(&cw.wscale, cout_p * sizeof(float)));
+        RNB_CUDA(launch_fold_pack_fp8(raw.p, bn.w, bn.b, bn.m, bn.v, cw.w, cw.wscale, cw.bias, Cout, Cin, k, cout_p,
+                                      cin_p, 0));
+        RNB_CUDA(cudaDeviceSynchronize());
+        return RNB_OK;
+    }
     RNB_CUDA(cudaMalloc(&cw.w, 1ull * Cout * Cin * k * k * esz));
     RNB_CUDA(cudaMalloc(&cw.bias, Cout * sizeof(float)));
     RNB_CUDA(launch_fold_pack(raw.p, bn.w, bn.b, bn.m, bn.v, cw.w, cw.bias, Cout, Cin, k, esz, 0));
@@ -160,6 +171,8 @@ Model::~Model() {
     }
     arena.free_all();
     cudaFree(u8_scratch);
+    cudaFree(fp8_amax_dev);
+    for (void* v : fp8_vec_allocs) cudaFree(v);
     cudaFree(host_x_dev); cudaFree(host_logits_dev); cudaFree(host_top1_dev); cudaFree(scratch_logits);
     if (blob) {  // load_packed(): every weight pointer points into this one allocation
         cudaFree(blob);
@@ -171,6 +184,7 @@ Model::~Model() {
         for (ConvWeights* c : {&b.conv1, &b.conv2, &b.conv3, &b.ds}) {
             cudaFree(c->w);
             cudaFree(c->bias);
+            cudaFree(c->wscale);
         }
         cudaFree(b.bias3ds);
     }
@@ -184,8 +198,8 @@ int Model::configure(const std::string& arch_name, int dtype, int max_batch_, in
         set_error("unknown arch '" + arch_name + "' (resnet18|34|50|101|152)");
         return RNB_ERR_INVALID;
     }
-    if (dtype != RNB_DTYPE_BF16 && dtype != RNB_DTYPE_TF32) {
-        set_error("dtype must be RNB_DTYPE_BF16 or RNB_DTYPE_TF32");
+    if (dtype != RNB_DTYPE_BF16 && dtype != RNB_DTYPE_TF32 && dtype != RNB_DTYPE_FP8) {
+        set_error("dtype must be RNB_DTYPE_BF16, RNB_DTYPE_TF32 or RNB_DTYPE_FP8");
         return RNB_ERR_INVALID;
     }
     if (max_batch_ <= 0) {
@@ -193,7 +207,8 @@ int Model::configure(const std::string& arch_name, int dtype, int max_batch_, in
         return RNB_ERR_INVALID;
     }
     arch = arch_name;
-    esz = dtype == RNB_DTYPE_BF16 ? 2 : 4;
+    esz = dtype == RNB_DTYPE_BF16 ? 2 : (dtype == RNB_DTYPE_FP8 ? 1 : 4);
+    fp8 = dtype == RNB_DTYPE_FP8;
     bottleneck = spec->bottleneck;
     max_batch = max_batch_;
     if (cudaGetDevice(&device) != cudaSuccess) device = 0;
@@ -222,6 +237,14 @@ int Model::configure(const std::string& arch_name, int dtype, int max_batch_, in
     fuse_next = !(fn && atoi(fn) == 0);
     const char* nostc0 = getenv("RNB_NO_STEM_TC");
     stem_tc = image == 224 && !(nostc0 && atoi(nostc0) != 0);
+    if (fp8) {
+        if (!stem_tc) {
+            set_error("the FP8 variant needs the tensor-core stem (224 x 224 inputs, RNB_NO_STEM_TC unset)");
+            return RNB_ERR_UNSUPPORTED;
+        }
+        fuse_level = 0;     // layer by layer: the fused Bottleneck tails are BF16 kernels
+        side_sms = 0;
+    }
     return RNB_OK;
 }
 
@@ -244,8 +267,8 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
         RNB_CUDA(cudaMalloc(&stem_bias, 64 * sizeof(float)));
         RNB_CUDA(launch_fold_f32(raw.p, bn.w, bn.b, bn.m, bn.v, stem_w, stem_bias, 64, 147, 0));
         if (stem_tc) {
-            RNB_CUDA(cudaMalloc(&stem_wk, stem_any_weight_bytes(esz)));
-            RNB_CUDA(launch_stem_any_pack_weights(esz, raw.p, bn.w, bn.b, bn.m, bn.v, stem_wk, stem_bias, 0));
+            RNB_CUDA(cudaMalloc(&stem_wk, stem_any_weight_bytes(stem_esz())));
+            RNB_CUDA(launch_stem_any_pack_weights(stem_esz(), raw.p, bn.w, bn.b, bn.m, bn.v, stem_wk, stem_bias, 0));
         }
         RNB_CUDA(cudaDeviceSynchronize());
     }
@@ -286,7 +309,7 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
                     return r;
                 macs += 1.0 * out_hw * out_hw * in_c * out_c;
                 num_convs += 1;
-                if (bottleneck) {
+                if (bottleneck && !fp8) {
                     std::vector<float> b3(out_c), bd(out_c);
                     RNB_CUDA(cudaMemcpy(b3.data(), bw.conv3.bias, out_c * sizeof(float), cudaMemcpyDeviceToHost));
                     RNB_CUDA(cudaMemcpy(bd.data(), bw.ds.bias, out_c * sizeof(float), cudaMemcpyDeviceToHost));
@@ -319,7 +342,7 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
         macs += 1.0 * classes * final_c;
         // BF16 path: FC on tensor cores (BF16 operands, FP32 accumulate and FP32 logits)
         const char* ft = getenv("RNB_FC_TC");
-        fc_tc = esz == 2 && final_c % 64 == 0 && classes % 4 == 0 && !(ft && atoi(ft) == 0);
+        fc_tc = esz <= 2 && final_c % 64 == 0 && classes % 4 == 0 && (fp8 || !(ft && atoi(ft) == 0));
         if (fc_tc) {
             classes_pad = (classes + 63) / 64 * 64;
             RNB_CUDA(cudaMalloc(&fc_wq, 1ull * classes_pad * final_c * 2));
@@ -414,7 +437,7 @@ template <class F>
 void Model::for_each_weight(F&& f) {
     f(reinterpret_cast<void**>(&stem_w), 64ull * 147 * sizeof(float));
     f(reinterpret_cast<void**>(&stem_bias), 64ull * sizeof(float));
-    if (stem_tc) f(&stem_wk, stem_any_weight_bytes(esz));
+    if (stem_tc) f(&stem_wk, stem_any_weight_bytes(stem_esz()));
     for (auto& b : blocks) {
         for (ConvWeights* c : {&b.conv1, &b.conv2, &b.conv3, &b.ds}) {
             if (c->Cout == 0) continue;  // conv3 of a BasicBlock, ds of a block without downsample
@@ -471,6 +494,10 @@ size_t aligned(size_t b) { return (b + kAlign - 1) / kAlign * kAlign; }
 }  // namespace
 
 int Model::save_packed(const std::string& path) {
+    if (fp8) {
+        set_error("save_packed: the FP8 variant has no packed format (its scales depend on the calibration batch)");
+        return RNB_ERR_UNSUPPORTED;
+    }
     size_t total = 0;
     uint32_t count = 0;
     for_each_weight([&](void**, size_t bytes) { total += aligned(bytes); ++count; });
@@ -581,7 +608,7 @@ ChunkPlan* Model::plan_for(int n) {
     ChunkPlan p;
     p.n = n;
     const size_t e = esz;
-    auto bytes = [&](int c, int h) { return 1ull * n * h * h * c * e; };
+    auto bytes = [&](int c, int h) { return 1ull * n * h * h * cpad(c) * e; };
     // A plan that fails half way must not leave its blocks busy: between plans nothing is (every plan releases all
     // of its blocks at the end, chunks run back to back), so a failure simply frees the lot.
     auto fail_alloc = [&]() -> ChunkPlan* {
@@ -596,17 +623,22 @@ ChunkPlan* Model::plan_for(int n) {
     } plan_guard{arena};
     const int s_hw = (6 + image - 7) / 2 + 1;     // 112
     const int p_hw = (2 + s_hw - 3) / 2 + 1;      // 56
-    if (!(p.stem_out = arena.acquire(stem_tc ? stem_any_input_bytes(esz, n) : bytes(64, s_hw))))
+    if (!(p.stem_out = arena.acquire(stem_tc ? stem_any_input_bytes(stem_esz(), n) : bytes(64, s_hw))))
         return fail_alloc();
+    if (fp8 && !(p.pool_raw = arena.acquire(1ull * n * p_hw * p_hw * 64 * 2))) return fail_alloc();
     if (!(p.pool_out = arena.acquire(bytes(64, p_hw)))) return fail_alloc();
     if (!stem_tc) p.named["stem"] = {p.stem_out, 64, s_hw, s_hw};
     p.named["maxpool"] = {p.pool_out, 64, p_hw, p_hw};
     arena.release(p.stem_out);  // dead once the pool has run
+    if (p.pool_raw) arena.release(p.pool_raw);  // dead once its E4M3 copy exists (launches are stream-ordered)
 
     void* x = p.pool_out;
     int hw = p_hw;
-    const ActType act = esz == 2 ? ActType::BF16 : ActType::TF32;
+    const ActType act = esz == 2 ? ActType::BF16 : (esz == 1 ? ActType::FP8 : ActType::TF32);
     char err[256];
+    // FP8: per-tensor scale of every live activation buffer (provisional 1.0 until calibrated)
+    std::map<const void*, float> scale_of;
+    scale_of[p.pool_out] = fp8_calibrated ? fp8_stem_scale : 1.f;
     int sm_budget = num_sms;  // SMs the next planned conv may use (reduced while a downsample conv runs beside it)
     auto add_conv = [&](const ConvWeights& cw, const void* in, int in_hw, const void* res, bool relu,
                         void* out) -> int {
@@ -617,6 +649,22 @@ ChunkPlan* Model::plan_for(int n) {
         // direction of the previous one, so it begins where its producer just finished (L2-hot).
         d.reverse = alternate_tiles && (p.convs.size() & 1) != 0;
         d.in = in; d.weight = cw.w; d.bias = cw.bias; d.residual = res; d.out = out;
+        if (fp8) {
+            const size_t idx = p.convs.size();
+            d.chan_scale = cw.wscale;
+            d.in_scale = scale_of[in];
+            d.res_scale = res ? scale_of[res] : 1.f;
+            d.out_scale = fp8_calibrated && idx < fp8_out_scale.size() ? fp8_out_scale[idx] : 1.f;
+            scale_of[out] = d.out_scale;
+            p.links.push_back({in, res, out});
+            float* vecs = nullptr;
+            if (cudaMalloc(&vecs, 2ull * cw.Cout * sizeof(float)) != cudaSuccess) {
+                set_error("FP8 epilogue vector allocation failed");
+                return RNB_ERR_CUDA;
+            }
+            fp8_vec_allocs.push_back(vecs);
+            d.fp8_vecs = vecs;
+        }
         ConvPlan cp;
         int rc = conv_plan_init(&cp, d, sm_budget, 0, err, sizeof(err));
         if (rc) {
@@ -638,6 +686,7 @@ ChunkPlan* Model::plan_for(int n) {
                 cudaEventCreate(&e0);
                 cudaEventCreate(&e1);
                 for (int force : cands) {
+                    if (fp8 && force != 128 && force != 1128 && force != 1256) continue;
                     if (force == 3064 && !conv_plan_halo_ok(d)) continue;
                     if (force == 4064 && !conv_plan_halo2_ok(d)) continue;
                     // deep-pipeline variants trade a staging buffer for pipeline stages: only for layers
@@ -648,6 +697,7 @@ ChunkPlan* Model::plan_for(int n) {
                     if (force == 64 && cw.Cout % 128 == 0 && 1LL * n * in_hw * in_hw > 4096) continue;
                     ConvPlan trial;
                     if (conv_plan_init(&trial, d, sm_budget, force, err, sizeof(err))) continue;
+                    if (fp8 && fp8_premultiply(&trial, d.in_scale, d.res_scale, d.out_scale, cap_stream) != cudaSuccess) continue;
                     bool ok = true;
                     for (int i = 0; i < 2 && ok; ++i) ok = conv_plan_launch(trial, cap_stream) == cudaSuccess;
                     cudaEventRecord(e0, cap_stream);
@@ -679,6 +729,10 @@ ChunkPlan* Model::plan_for(int n) {
                     p.convs.size(), n, in_hw, in_hw, cw.Cin, cw.Cout, cw.k, cw.stride, res ? 1 : 0,
                     cp.halo2 ? "halo-pair" : cp.halo ? "halo" : (cp.ctas == 2 ? (cp.deep ? "pair-deep" : "pair") : (cp.deep ? "single-deep" : "single")),
                     cp.ctas == 2 ? 256 : 128, cp.bn, cp.grid);
+        if (fp8 && fp8_premultiply(&cp, d.in_scale, d.res_scale, d.out_scale, cap_stream) != cudaSuccess) {
+            set_error("FP8 epilogue vector setup failed");
+            return RNB_ERR_CUDA;
+        }
         p.convs.push_back(cp);
         return 0;
     };
@@ -821,6 +875,7 @@ ChunkPlan* Model::plan_for(int n) {
     p.last = x;
     p.last_hw = hw * hw;
     p.last_c = final_c;
+    p.last_scale = fp8 ? scale_of[x] : 1.f;
     p.pooled = static_cast<float*>(arena.acquire(1ull * n * final_c * sizeof(float)));
     if (!p.pooled) return fail_alloc();
     p.named["avgpool"] = {p.pooled, final_c, 1, 1};
@@ -834,6 +889,7 @@ ChunkPlan* Model::plan_for(int n) {
     arena.release(x);
     arena.release(p.pooled);
     if (p.pooled_bf16) arena.release(p.pooled_bf16);
+    if (fp8) cudaStreamSynchronize(cap_stream);  // the pre-multiplied epilogue vectors were written on cap_stream
     plan_guard.ok = true;
     auto ins = plans.emplace(n, std::move(p));
     return &ins.first->second;
@@ -843,18 +899,24 @@ int Model::enqueue_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, floa
                          cudaStream_t s) {
     const int n = p.n;
     const int s_hw = (6 + image - 7) / 2 + 1;
-    if (x_u8 && !(stem_tc && esz == 2)) {
+    if (x_u8 && !(stem_tc && stem_esz() == 2)) {
         // generic path: normalise into an FP32 NCHW staging tensor, then proceed as with float input
         RNB_CUDA(launch_u8_hwc_to_f32_nchw(x_u8, u8_scratch, n, image, image, norm_mean, norm_std, s));
         x = u8_scratch;
         x_u8 = nullptr;
     }
     if (stem_tc) {
+        void* pool = fp8 ? p.pool_raw : p.pool_out;
         if (x_u8)
             RNB_CUDA(launch_stem_tc_pack_u8(x_u8, p.stem_out, n, norm_mean, norm_std, s));
         else
-            RNB_CUDA(launch_stem_any_part(esz, 0, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
-        RNB_CUDA(launch_stem_any_part(esz, 1, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
+            RNB_CUDA(launch_stem_any_part(stem_esz(), 0, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
+        RNB_CUDA(launch_stem_any_part(stem_esz(), 1, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
+        if (fp8) {
+            const int p_hw = (2 + s_hw - 3) / 2 + 1;
+            RNB_CUDA(launch_quantize_pad_bf16(p.pool_raw, p.pool_out, 1LL * n * p_hw * p_hw, 64, cpad(64),
+                                              1.f / fp8_stem_scale, s));
+        }
     } else {
         RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
         RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
@@ -863,7 +925,7 @@ int Model::enqueue_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, floa
         int rc = launch_convs(p, s, nullptr);
         if (rc) return rc;
     }
-    RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, p.pooled_bf16, n, p.last_hw, p.last_c, esz, s));
+    RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, p.pooled_bf16, n, p.last_hw, p.last_c, esz, s, p.last_scale));
     int r = enqueue_fc(p, logits, s);
     if (r) return r;
     if (top1) RNB_CUDA(launch_argmax_f32(logits, top1, n, classes, s));
@@ -926,6 +988,87 @@ int Model::enqueue_fc(ChunkPlan& p, float* logits, cudaStream_t s) {
     return RNB_OK;
 }
 
+// ------------------------------------------------------------------------------------ FP8 calibration
+// Writes the calibrated per-tensor scales into the launch geometry of a plan (plans made before / after calibration).
+int Model::apply_fp8_scales(ChunkPlan& p, cudaStream_t s) {
+    std::map<const void*, float> scale_of;
+    scale_of[p.pool_out] = fp8_stem_scale;
+    for (size_t i = 0; i < p.convs.size(); ++i) {
+        const ChunkPlan::Link& l = p.links[i];
+        RNB_CUDA(fp8_premultiply(&p.convs[i], scale_of[l.in], l.res ? scale_of[l.res] : 1.f, fp8_out_scale[i], s));
+        p.convs[i].g.amax = nullptr;
+        scale_of[l.out] = fp8_out_scale[i];
+    }
+    p.last_scale = scale_of[p.last];
+    return RNB_OK;
+}
+
+// One pass over `n` calibration images, in network order: the stem runs in BF16 and its output maximum fixes the first
+// scale; every conv is then launched twice on its already quantised inputs — once with an amax-recording epilogue
+// (output scale 1), once for real with scale = amax / 448. Blocking; runs on cap_stream.
+int Model::calibrate_fp8(const float* x, int n) {
+    if (!fp8 || fp8_calibrated) return RNB_OK;
+    cudaStream_t s = cap_stream;
+    RNB_CUDA(cudaDeviceSynchronize());
+    ChunkPlan* pp = plan_for(n);
+    if (!pp) return RNB_ERR_CUDA;
+    ChunkPlan& p = *pp;
+    if (!fp8_amax_dev) RNB_CUDA(cudaMalloc(&fp8_amax_dev, sizeof(float)));
+    const int s_hw = (6 + image - 7) / 2 + 1, p_hw = (2 + s_hw - 3) / 2 + 1;
+    auto read_amax = [&](float* out) -> int {
+        RNB_CUDA(cudaMemcpyAsync(out, fp8_amax_dev, sizeof(float), cudaMemcpyDeviceToHost, s));
+        RNB_CUDA(cudaStreamSynchronize(s));
+        return RNB_OK;
+    };
+    RNB_CUDA(launch_stem_any_part(2, 0, x, p.stem_out, stem_wk, stem_bias, p.pool_raw, n, s));
+    RNB_CUDA(launch_stem_any_part(2, 1, x, p.stem_out, stem_wk, stem_bias, p.pool_raw, n, s));
+    RNB_CUDA(cudaMemsetAsync(fp8_amax_dev, 0, sizeof(float), s));
+    RNB_CUDA(launch_amax_bf16(p.pool_raw, 1LL * n * p_hw * p_hw * 64, fp8_amax_dev, s));
+    float amax = 0.f;
+    int r = read_amax(&amax);
+    if (r) return r;
+    fp8_stem_scale = amax > 0.f ? amax / 448.f : 1.f;
+    RNB_CUDA(launch_quantize_pad_bf16(p.pool_raw, p.pool_out, 1LL * n * p_hw * p_hw, 64, cpad(64), 1.f / fp8_stem_scale, s));
+    fp8_out_scale.assign(p.convs.size(), 1.f);
+    std::map<const void*, float> scale_of;
+    scale_of[p.pool_out] = fp8_stem_scale;
+    for (size_t i = 0; i < p.convs.size(); ++i) {
+        ConvPlan& cp = p.convs[i];
+        const ChunkPlan::Link& l = p.links[i];
+        const float s_in = scale_of[l.in], s_res = l.res ? scale_of[l.res] : 1.f;
+        RNB_CUDA(fp8_premultiply(&cp, s_in, s_res, 1.f, s));
+        cp.g.amax = fp8_amax_dev;
+        RNB_CUDA(cudaMemsetAsync(fp8_amax_dev, 0, sizeof(float), s));
+        RNB_CUDA(conv_plan_launch(cp, s));
+        if ((r = read_amax(&amax))) return r;
+        if (!(amax == amax) || amax > 3.0e38f) {
+            set_error("FP8 calibration: conv #" + std::to_string(i) + " produced a non-finite maximum");
+            return RNB_ERR_CUDA;
+        }
+        const float sc = amax > 0.f ? amax / 448.f : 1.f;
+        fp8_out_scale[i] = sc;
+        RNB_CUDA(fp8_premultiply(&cp, s_in, s_res, sc, s));
+        cp.g.amax = nullptr;
+        RNB_CUDA(conv_plan_launch(cp, s));
+        scale_of[l.out] = sc;
+    }
+    RNB_CUDA(cudaStreamSynchronize(s));
+    fp8_calibrated = true;
+    for (auto& kv : plans) {
+        if ((r = apply_fp8_scales(kv.second, s))) return r;
+    }
+    RNB_CUDA(cudaStreamSynchronize(s));
+    // graphs captured with provisional scales (none in practice: calibration precedes the first capture)
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+    graphs.clear();
+    if (getenv("RNB_VERBOSE")) {
+        fprintf(stderr, "rnb fp8 calibration: stem scale %.4g;", fp8_stem_scale);
+        for (size_t i = 0; i < fp8_out_scale.size(); ++i) fprintf(stderr, " %.3g", fp8_out_scale[i]);
+        fprintf(stderr, "\n");
+    }
+    return RNB_OK;
+}
+
 int Model::forward(const float* x, int batch, float* logits, int32_t* top1, cudaStream_t s) {
     return forward_any(x, nullptr, batch, logits, top1, s);
 }
@@ -961,7 +1104,7 @@ int Model::forward_any(const float* x, const uint8_t* x_u8, int batch, float* lo
         set_error("x_dev is NULL");
         return RNB_ERR_INVALID;
     }
-    if (x_u8 && !(stem_tc && esz == 2) && !u8_scratch)
+    if (x_u8 && (!(stem_tc && stem_esz() == 2) || (fp8 && !fp8_calibrated)) && !u8_scratch)
         RNB_CUDA(cudaMalloc(&u8_scratch, 1ull * chunk * 3 * image * image * sizeof(float)));
     if (!logits) {
         if (!scratch_logits)
@@ -978,6 +1121,19 @@ int Model::forward_any(const float* x, const uint8_t* x_u8, int batch, float* lo
                       "rnb_model_warmup(batch) first");
             return RNB_ERR_INVALID;
         }
+    }
+    if (fp8 && !fp8_calibrated) {
+        // first forward of an FP8 model: its first chunk is the calibration batch (blocking; not under capture —
+        // the planning check above has already refused a capturing stream, since nothing is planned yet)
+        const int n = std::min(chunk, batch);
+        RNB_CUDA(cudaStreamSynchronize(s));
+        const float* xcal = x;
+        if (!xcal) {
+            RNB_CUDA(launch_u8_hwc_to_f32_nchw(x_u8, u8_scratch, n, image, image, norm_mean, norm_std, cap_stream));
+            xcal = u8_scratch;
+        }
+        int r = calibrate_fp8(xcal, n);
+        if (r) return r;
     }
     {
         int r = begin_enqueue(s);
@@ -1066,6 +1222,10 @@ int Model::warmup(int batch, bool include_u8) {
         set_error("warmup: batch must be in [1, max_batch]");
         return RNB_ERR_INVALID;
     }
+    if (fp8 && !fp8_calibrated) {
+        set_error("warmup: an FP8 model must be calibrated first (rnb_model_calibrate, or a first forward on real data)");
+        return RNB_ERR_INVALID;
+    }
     // a real forward on scratch buffers: plans every chunk size of this batch, autotunes, allocates lazily
     // created buffers and instantiates one graph per chunk shape (later calls with other pointers re-target it)
     const size_t img_elems = 3ull * image * image;
@@ -1109,6 +1269,10 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
         return RNB_ERR_INVALID;
     }
     const int n = std::min(chunk, batch);
+    if (fp8 && !fp8_calibrated) {
+        int rc = calibrate_fp8(x, n);
+        if (rc) return rc;
+    }
     ChunkPlan* pp = plan_for(n);
     if (!pp) return RNB_ERR_CUDA;
     ChunkPlan& p = *pp;
@@ -1132,22 +1296,26 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
     for (int it = -1; it < iters; ++it) {
         int i = 0;
         RNB_CUDA(cudaEventRecord(ev[i], s));
+        void* pool = fp8 ? p.pool_raw : p.pool_out;
         if (stem_tc)
-            RNB_CUDA(launch_stem_any_part(esz, 0, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
+            RNB_CUDA(launch_stem_any_part(stem_esz(), 0, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
         else
             RNB_CUDA(launch_stem_conv(x, stem_w, stem_bias, p.stem_out, n, image, image, esz, s));
         RNB_CUDA(cudaEventRecord(ev[++i], s));
         if (stem_tc)
-            RNB_CUDA(launch_stem_any_part(esz, 1, x, p.stem_out, stem_wk, stem_bias, p.pool_out, n, s));
+            RNB_CUDA(launch_stem_any_part(stem_esz(), 1, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
         else
             RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
+        if (fp8)  // the E4M3 copy of the stem output is booked with the stem's second launch
+            RNB_CUDA(launch_quantize_pad_bf16(p.pool_raw, p.pool_out, 1LL * n * p_hw * p_hw, 64, cpad(64),
+                                              1.f / fp8_stem_scale, s));
         RNB_CUDA(cudaEventRecord(ev[++i], s));
         {
             int rc = launch_convs(p, s, &ev[i + 1]);
             if (rc) return rc;
             i += static_cast<int>(p.convs.size());
         }
-        RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, p.pooled_bf16, n, p.last_hw, p.last_c, esz, s));
+        RNB_CUDA(launch_avgpool_nhwc(p.last, p.pooled, p.pooled_bf16, n, p.last_hw, p.last_c, esz, s, p.last_scale));
         RNB_CUDA(cudaEventRecord(ev[++i], s));
         {
             int rr = enqueue_fc(p, scratch_logits, s);
@@ -1180,9 +1348,10 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
     const double img_px = 1.0 * image * image;
     if (stem_tc) {
         // launch 0 = layout pre-pass (fp32 NCHW -> padded NHWC4 bf16), launch 1 = fused conv+BN+ReLU+pool
-        const double packed = static_cast<double>(stem_any_input_bytes(esz, 1));
+        const double packed = static_cast<double>(stem_any_input_bytes(stem_esz(), 1));
         put(0, 0.0, n * (3.0 * img_px * 4 + packed));
-        put(1, 2.0 * n * 64 * 147 * s_hw * s_hw, n * (packed + 64.0 * p_hw * p_hw * esz) + 28672.0);
+        put(1, 2.0 * n * 64 * 147 * s_hw * s_hw,
+            n * (packed + 64.0 * p_hw * p_hw * stem_esz() + (fp8 ? (64.0 * 2 + 128.0) * p_hw * p_hw : 0.0)) + 28672.0);
     } else {
         put(0, 2.0 * n * 64 * 147 * s_hw * s_hw, n * (3.0 * img_px * 4 + 64.0 * s_hw * s_hw * esz) + 64 * 148 * 4.0);
         put(1, 0.0, n * 64.0 * esz * (1.0 * s_hw * s_hw + 1.0 * p_hw * p_hw));

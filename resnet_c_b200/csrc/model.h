@@ -20,7 +20,8 @@ namespace rnb {
 struct ConvWeights {
     void* w = nullptr;       // packed [Cout][k][k][Cin] in the activation type, BN folded
     float* bias = nullptr;   // [Cout]
-    int Cin = 0, Cout = 0, k = 0, stride = 1, pad = 0;
+    float* wscale = nullptr; // FP8 path: per-output-channel weight scale [Cout]
+    int Cin = 0, Cout = 0, k = 0, stride = 1, pad = 0;  // FP8 path: channel counts padded to multiples of 128
 };
 
 struct BlockWeights {
@@ -50,6 +51,17 @@ struct ChunkPlan {
     float* fc_out = nullptr;    // logits pointer fc_plan was built for
     ConvPlan fc_plan;           // FC as a 1x1 conv on tcgen05 with FP32 output (BF16 path); valid iff pooled_bf16
     std::map<std::string, NamedAct> named;
+    // FP8 path: the stem runs in BF16 into pool_raw, pool_out is its E4M3 copy (64 -> 128 channels, zero padded);
+    // links[i] = the tensors conv i reads / adds / writes (their per-tensor scales are fixed by calibration)
+    void* pool_raw = nullptr;
+    struct Link {
+        const void* in;
+        const void* res;
+        void* out;
+    };
+    std::vector<Link> links;
+    std::vector<float*> fp8_vecs;  // per conv: 2 x Cout pre-multiplied epilogue vectors (owned by the model's arena)
+    float last_scale = 1.f;  // scale of `last`
 };
 
 class Arena {
@@ -68,7 +80,21 @@ private:
 
 struct Model {
     std::string arch;
-    int esz = 2;            // activation bytes: 2 bf16, 4 tf32
+    int esz = 2;            // activation bytes: 1 fp8 (E4M3), 2 bf16, 4 tf32
+    // FP8 variant: E4M3 weights (per-output-channel scales) and activations (per-tensor
+    // scales), kind::f8f6f4 MMAs, layer-by-layer plan; stem and FC stay BF16. The activation scales are fixed by ONE
+    // calibration pass (the first forward, or rnb_model_calibrate): every conv is run once with an amax-recording
+    // epilogue on the calibration batch, in network order, on the already quantised inputs.
+    bool fp8 = false;
+    bool fp8_calibrated = false;
+    float fp8_stem_scale = 1.f;
+    std::vector<float> fp8_out_scale;   // per conv launch, in plan order
+    float* fp8_amax_dev = nullptr;
+    int stem_esz() const { return fp8 ? 2 : esz; }
+    int cpad(int c) const { return fp8 ? (c + 127) / 128 * 128 : c; }
+    int calibrate_fp8(const float* x, int n);
+    int apply_fp8_scales(ChunkPlan& p, cudaStream_t s);
+    std::vector<void*> fp8_vec_allocs;  // device scratch of the pre-multiplied vectors of every plan
     int classes = 1000;
     int image = 224;
     int max_batch = 0;
@@ -188,7 +214,7 @@ struct Model {
     // stem pre-pass/conv + stem/max-pool + planned conv launches + avg-pool + fc + arg-max
     int launches_per_chunk(int n) {
         ChunkPlan* p = plan_for(n);
-        return p ? static_cast<int>(p->convs.size()) + 5 : 0;
+        return p ? static_cast<int>(p->convs.size()) + 5 + (fp8 ? 1 : 0) : 0;
     }
 };
 

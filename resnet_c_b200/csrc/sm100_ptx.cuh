@@ -184,6 +184,20 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uin
         : "memory");
 }
 
+// Same with 8-bit floating-point operands (kind::f8f6f4; E4M3 x E4M3 here), 32 elements of K per instruction.
+__device__ __forceinline__ void mma_f8_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread t gets lane t).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -243,7 +257,8 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
 // tcgen05 instruction descriptor for kind::f16 / kind::tf32 with FP32 accumulate, K-major A and B.
 //   [4,6) D fmt (1 = f32) | [7,10) A fmt | [10,13) B fmt (0 = f16, 1 = bf16, 2 = tf32)
 //   [15] A major, [16] B major (0 = K) | [17,23) N >> 3 | [24,29) M >> 4
-enum : uint32_t { UMMA_FMT_F16 = 0, UMMA_FMT_BF16 = 1, UMMA_FMT_TF32 = 2 };
+//   kind::f8f6f4 uses the same fields with its own format codes: 0 = E4M3, 1 = E5M2 (3 / 4 / 5 = the 6- and 4-bit types)
+enum : uint32_t { UMMA_FMT_F16 = 0, UMMA_FMT_BF16 = 1, UMMA_FMT_TF32 = 2, UMMA_FMT_E4M3 = 0 };
 __host__ __device__ constexpr uint32_t umma_instr_desc(uint32_t fmt, uint32_t M, uint32_t N) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }

@@ -8,6 +8,7 @@
 // the block's 8 classes for that k are one broadcast shared-memory read.
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "internal.h"
@@ -96,6 +97,58 @@ __global__ void avgpool_nhwc_kernel(const T* __restrict__ x, float* __restrict__
                 *reinterpret_cast<uint4*>(pooled_bf16 + 1LL * b * C + gidx * VEC) = o;
             }
         }
+    }
+}
+
+// FP8 (E4M3) input [n][HW][C] with per-tensor scale: thread = (image, 16 channels); row-major FP32 + BF16 outputs
+// (the A operand of the tensor-core FC). Sum in FP32 in pixel order, then x scale, then the double division.
+__global__ void avgpool_nhwc_fp8_kernel(const uint8_t* __restrict__ x, float* __restrict__ pooled,
+                                        __nv_bfloat16* __restrict__ pooled_bf16, int n, int HW, int C, int ksq,
+                                        float in_scale) {
+    const int groups = C / 16;
+    const int64_t total = 1LL * n * groups;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int64_t i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int gidx = static_cast<int>(i % groups);
+        const int b = static_cast<int>(i / groups);
+        const uint8_t* xp = x + 1LL * b * HW * C + gidx * 16;
+        float acc[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+        for (int p0 = 0; p0 < HW; p0 += 7) {
+            uint4 v[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j)
+                v[j] = p0 + j < HW ? __ldg(reinterpret_cast<const uint4*>(xp + 1LL * (p0 + j) * C)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t h01, h23;
+                    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h01) : "h"(static_cast<uint16_t>(u[q] & 0xFFFFu)));
+                    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h23) : "h"(static_cast<uint16_t>(u[q] >> 16)));
+                    const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+                    const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+                    acc[q * 4 + 0] += f01.x; acc[q * 4 + 1] += f01.y; acc[q * 4 + 2] += f23.x; acc[q * 4 + 3] += f23.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            acc[e] *= in_scale;
+            acc[e] = ksq > 0 ? acc[e] / static_cast<float>(ksq) / static_cast<float>(ksq) : acc[e] / static_cast<float>(HW);
+        }
+        float4* pr = reinterpret_cast<float4*>(pooled + 1LL * b * C + gidx * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pr[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+        uint4 o0, o1;
+        o0.x = pack2(acc[0], acc[1]); o0.y = pack2(acc[2], acc[3]); o0.z = pack2(acc[4], acc[5]); o0.w = pack2(acc[6], acc[7]);
+        o1.x = pack2(acc[8], acc[9]); o1.y = pack2(acc[10], acc[11]); o1.z = pack2(acc[12], acc[13]); o1.w = pack2(acc[14], acc[15]);
+        uint4* pb = reinterpret_cast<uint4*>(pooled_bf16 + 1LL * b * C + gidx * 16);
+        pb[0] = o0;
+        pb[1] = o1;
     }
 }
 
@@ -215,10 +268,17 @@ cudaError_t launch_fc_pack(const float* w, const float* b, void* wq, float* bq, 
 }
 
 cudaError_t launch_avgpool_nhwc(const void* x, float* pooledT, void* pooled_bf16, int B, int HW, int C, int esz,
-                                cudaStream_t s) {
+                                cudaStream_t s, float in_scale) {
     int ksq = 0;
     for (int k = 1; k * k <= HW; ++k)
         if (k * k == HW) ksq = k;
+    if (esz == 1) {
+        if (!pooled_bf16 || C % 16 != 0) return cudaErrorInvalidValue;
+        const int64_t tot = 1LL * B * (C / 16);
+        return launch_pdl_small(avgpool_nhwc_fp8_kernel, dim3(static_cast<int>((tot + 63) / 64)), dim3(64), 0, s,
+                                static_cast<const uint8_t*>(x), pooledT, static_cast<__nv_bfloat16*>(pooled_bf16), B, HW, C,
+                                ksq, in_scale);
+    }
     const int64_t total = 1LL * B * (C * esz / 16);
     const int blocks = static_cast<int>((total + 127) / 128);
     if (esz == 2)  // 64-thread blocks: ~145 registers per thread, and the whole grid should be resident at once

@@ -42,9 +42,10 @@ void resolve() {
 }
 
 CUtensorMapDataType to_cu(TmDtype d) {
-    return d == TmDtype::BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    return d == TmDtype::BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                              : (d == TmDtype::U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
-uint32_t esize(TmDtype d) { return d == TmDtype::BF16 ? 2u : 4u; }
+uint32_t esize(TmDtype d) { return d == TmDtype::BF16 ? 2u : (d == TmDtype::U8 ? 1u : 4u); }
 
 }  // namespace
 

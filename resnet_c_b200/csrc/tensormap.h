@@ -7,7 +7,7 @@
 
 namespace rnb {
 
-enum class TmDtype { BF16, F32 };
+enum class TmDtype { BF16, F32, U8 };  // U8: FP8 (E4M3) tensors travel as bytes
 
 // Returns 0 on success, otherwise a CUresult (or -1 if the driver entry points are unavailable).
 // All maps use 128-byte swizzle; the inner box extent is always 128 bytes.

@@ -178,6 +178,23 @@ def conv_bn_act_forward(x, weight, bn=None, residual=None, relu=True, stride=1, 
     return out
 
 
+def conv_fp8_forward(x, weight, bn=None, residual=None, relu=True, stride=1, padding=0, in_scale=1.0, res_scale=1.0,
+                     out_scale=1.0):
+    """One FP8 (E4M3) conv with explicit per-tensor scales (rnb_conv_fp8_forward); returns the de-quantised output."""
+    x, weight = _f32_cuda(x, "x"), _f32_cuda(weight, "weight")
+    B, Cin, H, W = x.shape
+    Cout, _, k, _ = weight.shape
+    out = torch.empty(B, Cout, conv_out(H, k, stride, padding), conv_out(W, k, stride, padding),
+                      device=x.device, dtype=torch.float32)
+    bnp = [None] * 4 if bn is None else [_f32_cuda(t, "bn") for t in bn]
+    res = None if residual is None else _f32_cuda(residual, "residual")
+    _lib.init(x.device.index or 0)
+    check(_lib.lib().rnb_conv_fp8_forward(_ptr(x), _ptr(weight), _ptr(bnp[0]), _ptr(bnp[1]), _ptr(bnp[2]), _ptr(bnp[3]),
+                                          _ptr(res), _ptr(out), B, Cin, H, W, Cout, k, stride, padding, int(bool(relu)),
+                                          float(in_scale), float(res_scale), float(out_scale), _stream()))
+    return out
+
+
 def stem_forward(x, weight, bn=None, dtype="bf16"):
     """conv 7x7/2 + bn + relu + maxpool 3x3/2 (main.cu:176-192)."""
     x, weight = _f32_cuda(x, "x"), _f32_cuda(weight, "weight")
@@ -236,6 +253,11 @@ class ResNet:
 
     def save_packed(self, path) -> None:
         check(_lib.lib().rnb_model_save_packed(self._h, str(path).encode()))
+
+    def calibrate(self, x: torch.Tensor) -> None:
+        """FP8 models: fix the activation scales from this batch (no-op for other dtypes / once calibrated)."""
+        x = _f32_cuda(x, "x")
+        check(_lib.lib().rnb_model_calibrate(self._h, _ptr(x), x.shape[0]))
 
     def close(self):
         if getattr(self, "_h", None):
