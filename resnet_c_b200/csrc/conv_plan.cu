@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include "conv_igemm2.cuh"
+#include "internal.h"
 #include "tensormap.h"
 
 namespace rnb {
@@ -516,6 +517,7 @@ extern "C" int rnb_debug_read_timeline(long long* host, int* counts) {
 #endif
 
 cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
+    if (p.quant) return launch_quantize_pad_bf16(p.q_src, p.q_dst, p.q_rows, p.q_c, p.q_cpad, p.q_inv_scale, stream);
     if (p.bneck == 4) {
         // how the 224 KB of shared memory are split between the weight rings and the staging boxes (bit-identical)
         const int rings = p.rings;

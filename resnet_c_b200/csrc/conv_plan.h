@@ -95,6 +95,14 @@ struct ConvPlan {
     int grid;     // persistent CTAs
     int side;     // 1 = launched on the engine's side stream (downsample conv overlapped with conv1/conv2)
     int join;     // 1 = must wait for the side stream before it starts (consumes the downsample output)
+    // quant = 1: not a conv but the BF16 -> E4M3 re-quantisation of an activation tensor (the hand-over from the BF16
+    // layers to the FP8 layers of a mixed plan): q_dst[rows][q_cpad] = RN_e4m3(q_src[rows][q_c] * q_inv_scale)
+    int quant;
+    const void* q_src;
+    void* q_dst;
+    long long q_rows;
+    int q_c, q_cpad;
+    float q_inv_scale;
     // FP8: the un-multiplied vectors and the scratch the kernel reads (kept so that calibration can re-scale a plan)
     const float* fp8_wscale;
     const float* fp8_shift;

@@ -242,8 +242,9 @@ int Model::configure(const std::string& arch_name, int dtype, int max_batch_, in
             set_error("the FP8 variant needs the tensor-core stem (224 x 224 inputs, RNB_NO_STEM_TC unset)");
             return RNB_ERR_UNSUPPORTED;
         }
-        fuse_level = 0;     // layer by layer: the fused Bottleneck tails are BF16 kernels
         side_sms = 0;
+        const char* ff = getenv("RNB_FP8_FROM");
+        fp8_first_block = ff && atoi(ff) == 0 ? 0 : spec->blocks[0];   // default: layer1 in BF16
     }
     return RNB_OK;
 }
@@ -289,6 +290,8 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
             const std::string p = bw.name + ".";
             const int stride = i == 0 ? layer_stride : 1;
             const int out_hw = hw / stride;
+            // mixed FP8 plan: the blocks before fp8_first_block keep BF16 weights
+            const int esz = fp8 && static_cast<int>(blocks.size()) - 1 < fp8_first_block ? 2 : this->esz;
             if (bottleneck) {
                 if ((r = load_conv(dir, p + "conv1", p + "bn1", in_c, mid, 1, 1, 0, esz, bw.conv1))) return r;
                 if ((r = load_conv(dir, p + "conv2", p + "bn2", mid, mid, 3, stride, 1, esz, bw.conv2))) return r;
@@ -309,7 +312,7 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
                     return r;
                 macs += 1.0 * out_hw * out_hw * in_c * out_c;
                 num_convs += 1;
-                if (bottleneck && !fp8) {
+                if (bottleneck && esz != 1) {
                     std::vector<float> b3(out_c), bd(out_c);
                     RNB_CUDA(cudaMemcpy(b3.data(), bw.conv3.bias, out_c * sizeof(float), cudaMemcpyDeviceToHost));
                     RNB_CUDA(cudaMemcpy(bd.data(), bw.ds.bias, out_c * sizeof(float), cudaMemcpyDeviceToHost));
@@ -607,8 +610,9 @@ ChunkPlan* Model::plan_for(int n) {
     if (autotune) cudaDeviceSynchronize();
     ChunkPlan p;
     p.n = n;
-    const size_t e = esz;
-    auto bytes = [&](int c, int h) { return 1ull * n * h * h * cpad(c) * e; };
+    // element size of the tensors being planned: esz, except in the BF16 head of a mixed FP8 plan
+    int cur_esz = fp8 && fp8_first_block > 0 ? 2 : esz;
+    auto bytes = [&](int c, int h) { return 1ull * n * h * h * (cur_esz == 1 ? cpad(c) : c) * cur_esz; };
     // A plan that fails half way must not leave its blocks busy: between plans nothing is (every plan releases all
     // of its blocks at the end, chunks run back to back), so a failure simply frees the lot.
     auto fail_alloc = [&]() -> ChunkPlan* {
@@ -625,7 +629,7 @@ ChunkPlan* Model::plan_for(int n) {
     const int p_hw = (2 + s_hw - 3) / 2 + 1;      // 56
     if (!(p.stem_out = arena.acquire(stem_tc ? stem_any_input_bytes(stem_esz(), n) : bytes(64, s_hw))))
         return fail_alloc();
-    if (fp8 && !(p.pool_raw = arena.acquire(1ull * n * p_hw * p_hw * 64 * 2))) return fail_alloc();
+    if (fp8 && fp8_first_block == 0 && !(p.pool_raw = arena.acquire(1ull * n * p_hw * p_hw * 64 * 2))) return fail_alloc();
     if (!(p.pool_out = arena.acquire(bytes(64, p_hw)))) return fail_alloc();
     if (!stem_tc) p.named["stem"] = {p.stem_out, 64, s_hw, s_hw};
     p.named["maxpool"] = {p.pool_out, 64, p_hw, p_hw};
@@ -634,7 +638,6 @@ ChunkPlan* Model::plan_for(int n) {
 
     void* x = p.pool_out;
     int hw = p_hw;
-    const ActType act = esz == 2 ? ActType::BF16 : (esz == 1 ? ActType::FP8 : ActType::TF32);
     char err[256];
     // FP8: per-tensor scale of every live activation buffer (provisional 1.0 until calibrated)
     std::map<const void*, float> scale_of;
@@ -644,11 +647,14 @@ ChunkPlan* Model::plan_for(int n) {
                         void* out) -> int {
         ConvDesc d{};
         d.B = n; d.H = in_hw; d.W = in_hw; d.Cin = cw.Cin; d.Cout = cw.Cout;
-        d.ksize = cw.k; d.stride = cw.stride; d.pad = cw.pad; d.relu = relu; d.act = act;
+        d.ksize = cw.k; d.stride = cw.stride; d.pad = cw.pad; d.relu = relu;
+        d.act = cur_esz == 2 ? ActType::BF16 : (cur_esz == 1 ? ActType::FP8 : ActType::TF32);
+        const bool fp8 = cur_esz == 1;  // this launch (shadows the model-wide flag inside add_conv)
         // Boustrophedon over the launch sequence: every conv walks its tiles in the opposite
         // direction of the previous one, so it begins where its producer just finished (L2-hot).
         d.reverse = alternate_tiles && (p.convs.size() & 1) != 0;
         d.in = in; d.weight = cw.w; d.bias = cw.bias; d.residual = res; d.out = out;
+        if (!fp8 && this->fp8) p.links.push_back({in, res, out});  // BF16 launch of a mixed plan: no scales
         if (fp8) {
             const size_t idx = p.convs.size();
             d.chan_scale = cw.wscale;
@@ -692,7 +698,7 @@ ChunkPlan* Model::plan_for(int n) {
                     // deep-pipeline variants trade a staging buffer for pipeline stages: only for layers
                     // whose epilogue is light (no residual prefetch) and whose K loop is long; timing a
                     // residual layer alone flatters them (measured in the full network: slower)
-                    if (force >= 10000 && (esz != 2 || res || cw.k * cw.k * cw.Cin < 256)) continue;
+                    if (force >= 10000 && (cur_esz != 2 || res || cw.k * cw.k * cw.Cin < 256)) continue;
                     if (cw.Cout % (force % 1000) != 0) continue;
                     if (force == 64 && cw.Cout % 128 == 0 && 1LL * n * in_hw * in_hw > 4096) continue;
                     ConvPlan trial;
@@ -739,12 +745,36 @@ ChunkPlan* Model::plan_for(int n) {
     void* pre_t1 = nullptr;  // this block's conv1 output, already produced by the previous fused launch
     for (size_t bi = 0; bi < blocks.size(); ++bi) {
         const BlockWeights& bw = blocks[bi];
+        if (fp8 && static_cast<int>(bi) == fp8_first_block && fp8_first_block > 0) {
+            // hand-over of a mixed plan: the BF16 activation x becomes an E4M3 tensor (scale fixed by calibration)
+            const int c = bw.bottleneck ? bw.conv1.Cin : bw.conv1.Cin;   // already padded for the FP8 block
+            const int c_real = blocks[bi - 1].bottleneck ? blocks[bi - 1].conv3.Cout : blocks[bi - 1].conv2.Cout;
+            cur_esz = 1;
+            void* xq = arena.acquire(bytes(c, hw));
+            if (!xq) return fail_alloc();
+            ConvPlan q;
+            memset(&q, 0, sizeof(q));
+            q.quant = 1;
+            q.q_src = x; q.q_dst = xq; q.q_rows = 1LL * n * hw * hw; q.q_c = c_real; q.q_cpad = cpad(c_real);
+            const size_t idx = p.convs.size();
+            const float sc = fp8_calibrated && idx < fp8_out_scale.size() ? fp8_out_scale[idx] : 1.f;
+            q.q_inv_scale = 1.f / sc;
+            q.esz = 1;
+            q.bytes = 1.0 * q.q_rows * (2.0 * q.q_c + q.q_cpad);
+            scale_of[xq] = sc;
+            p.links.push_back({x, nullptr, xq});
+            p.convs.push_back(q);
+            arena.release(x);
+            x = xq;
+        }
+        const int besz = fp8 && static_cast<int>(bi) < fp8_first_block ? 2 : esz;
+        cur_esz = besz;
         const int stride = bw.bottleneck ? bw.conv2.stride : bw.conv1.stride;
         const int out_hw = hw / stride;
         const int out_c = bw.bottleneck ? bw.conv3.Cout : bw.conv2.Cout;
         // layer1-shaped Bottleneck (64 -> 64 -> 256, stride 1): conv2 + conv3 + shortcut in one launch
         const bool fuse = fuse_level >= 1 && bw.bottleneck && stride == 1 && bw.conv2.Cin == 64 &&
-                          bw.conv2.Cout == 64 && out_c == 256 && bneck_plan_ok(hw, hw, esz);
+                          bw.conv2.Cout == 64 && out_c == 256 && bneck_plan_ok(hw, hw, besz);
         const bool fuse_ds = fuse && fuse_level >= 2 && bw.has_ds && bw.ds.stride == 1 && bw.ds.Cin == 64 &&
                              bw.bias3ds;
         void* shortcut = x;
@@ -806,6 +836,7 @@ ChunkPlan* Model::plan_for(int n) {
             if (getenv("RNB_VERBOSE"))
                 fprintf(stderr, "rnb plan: conv#%zu n=%d %dx%d fused bottleneck tail%s%s grid %d\n", p.convs.size(), n,
                         hw, hw, fuse_ds ? " +downsample" : "", next ? " +next conv1" : "", cp.grid);
+            if (fp8) p.links.push_back({nullptr, nullptr, nullptr});  // fused BF16 launch of a mixed plan
             p.convs.push_back(cp);
             arena.release(t1);
             pre_t1 = t1n;
@@ -830,7 +861,7 @@ ChunkPlan* Model::plan_for(int n) {
             // RNB_C3N1=0 off, 1 = layer2 only, default both)
             const char* c3env = getenv("RNB_C3N1");
             const int c3level = c3env ? atoi(c3env) : 2;
-            const bool c3n1 = fuse_level >= 1 && fuse_next && esz == 2 && nb && nb->bottleneck && !nb->has_ds &&
+            const bool c3n1 = fuse_level >= 1 && fuse_next && besz == 2 && nb && nb->bottleneck && !nb->has_ds &&
                               nb->conv1.Cin == out_c && nb->conv2.stride == 1 &&
                               c3n1_shape_ok(bw.conv3.Cin, out_c, nb->conv1.Cout) &&
                               c3level >= (bw.conv3.Cin == 128 ? 1 : 2);
@@ -851,6 +882,7 @@ ChunkPlan* Model::plan_for(int n) {
                 if (getenv("RNB_VERBOSE"))
                     fprintf(stderr, "rnb plan: conv#%zu n=%d %dx%d fused conv3 + next conv1 grid %d\n", p.convs.size(), n,
                             out_hw, out_hw, cp.grid);
+                if (fp8) p.links.push_back({nullptr, nullptr, nullptr});
                 p.convs.push_back(cp);
                 pre_t1 = t1n;
             } else if (add_conv(bw.conv3, t2, out_hw, shortcut, true, y)) {
@@ -906,13 +938,13 @@ int Model::enqueue_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, floa
         x_u8 = nullptr;
     }
     if (stem_tc) {
-        void* pool = fp8 ? p.pool_raw : p.pool_out;
+        void* pool = p.pool_raw ? p.pool_raw : p.pool_out;
         if (x_u8)
             RNB_CUDA(launch_stem_tc_pack_u8(x_u8, p.stem_out, n, norm_mean, norm_std, s));
         else
             RNB_CUDA(launch_stem_any_part(stem_esz(), 0, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
         RNB_CUDA(launch_stem_any_part(stem_esz(), 1, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
-        if (fp8) {
+        if (p.pool_raw) {
             const int p_hw = (2 + s_hw - 3) / 2 + 1;
             RNB_CUDA(launch_quantize_pad_bf16(p.pool_raw, p.pool_out, 1LL * n * p_hw * p_hw, 64, cpad(64),
                                               1.f / fp8_stem_scale, s));
@@ -995,8 +1027,15 @@ int Model::apply_fp8_scales(ChunkPlan& p, cudaStream_t s) {
     scale_of[p.pool_out] = fp8_stem_scale;
     for (size_t i = 0; i < p.convs.size(); ++i) {
         const ChunkPlan::Link& l = p.links[i];
-        RNB_CUDA(fp8_premultiply(&p.convs[i], scale_of[l.in], l.res ? scale_of[l.res] : 1.f, fp8_out_scale[i], s));
-        p.convs[i].g.amax = nullptr;
+        ConvPlan& cp = p.convs[i];
+        if (cp.quant) {
+            cp.q_inv_scale = 1.f / fp8_out_scale[i];
+            scale_of[l.out] = fp8_out_scale[i];
+            continue;
+        }
+        if (cp.esz != 1) continue;  // BF16 head of a mixed plan
+        RNB_CUDA(fp8_premultiply(&cp, scale_of[l.in], l.res ? scale_of[l.res] : 1.f, fp8_out_scale[i], s));
+        cp.g.amax = nullptr;
         scale_of[l.out] = fp8_out_scale[i];
     }
     p.last_scale = scale_of[p.last];
@@ -1020,21 +1059,39 @@ int Model::calibrate_fp8(const float* x, int n) {
         RNB_CUDA(cudaStreamSynchronize(s));
         return RNB_OK;
     };
-    RNB_CUDA(launch_stem_any_part(2, 0, x, p.stem_out, stem_wk, stem_bias, p.pool_raw, n, s));
-    RNB_CUDA(launch_stem_any_part(2, 1, x, p.stem_out, stem_wk, stem_bias, p.pool_raw, n, s));
-    RNB_CUDA(cudaMemsetAsync(fp8_amax_dev, 0, sizeof(float), s));
-    RNB_CUDA(launch_amax_bf16(p.pool_raw, 1LL * n * p_hw * p_hw * 64, fp8_amax_dev, s));
+    void* pool = p.pool_raw ? p.pool_raw : p.pool_out;
+    RNB_CUDA(launch_stem_any_part(2, 0, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
+    RNB_CUDA(launch_stem_any_part(2, 1, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
     float amax = 0.f;
-    int r = read_amax(&amax);
-    if (r) return r;
-    fp8_stem_scale = amax > 0.f ? amax / 448.f : 1.f;
-    RNB_CUDA(launch_quantize_pad_bf16(p.pool_raw, p.pool_out, 1LL * n * p_hw * p_hw, 64, cpad(64), 1.f / fp8_stem_scale, s));
+    int r = RNB_OK;
+    if (p.pool_raw) {  // whole network in FP8: the stem output is the first quantised tensor
+        RNB_CUDA(cudaMemsetAsync(fp8_amax_dev, 0, sizeof(float), s));
+        RNB_CUDA(launch_amax_bf16(p.pool_raw, 1LL * n * p_hw * p_hw * 64, fp8_amax_dev, s));
+        if ((r = read_amax(&amax))) return r;
+        fp8_stem_scale = amax > 0.f ? amax / 448.f : 1.f;
+        RNB_CUDA(launch_quantize_pad_bf16(p.pool_raw, p.pool_out, 1LL * n * p_hw * p_hw, 64, cpad(64), 1.f / fp8_stem_scale, s));
+    }
     fp8_out_scale.assign(p.convs.size(), 1.f);
     std::map<const void*, float> scale_of;
     scale_of[p.pool_out] = fp8_stem_scale;
     for (size_t i = 0; i < p.convs.size(); ++i) {
         ConvPlan& cp = p.convs[i];
         const ChunkPlan::Link& l = p.links[i];
+        if (cp.quant) {  // hand-over of a mixed plan: scale from the maximum of the BF16 tensor
+            RNB_CUDA(cudaMemsetAsync(fp8_amax_dev, 0, sizeof(float), s));
+            RNB_CUDA(launch_amax_bf16(cp.q_src, cp.q_rows * cp.q_c, fp8_amax_dev, s));
+            if ((r = read_amax(&amax))) return r;
+            const float sc = amax > 0.f ? amax / 448.f : 1.f;
+            fp8_out_scale[i] = sc;
+            cp.q_inv_scale = 1.f / sc;
+            RNB_CUDA(conv_plan_launch(cp, s));
+            scale_of[l.out] = sc;
+            continue;
+        }
+        if (cp.esz != 1) {  // BF16 launch
+            RNB_CUDA(conv_plan_launch(cp, s));
+            continue;
+        }
         const float s_in = scale_of[l.in], s_res = l.res ? scale_of[l.res] : 1.f;
         RNB_CUDA(fp8_premultiply(&cp, s_in, s_res, 1.f, s));
         cp.g.amax = fp8_amax_dev;
@@ -1296,7 +1353,7 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
     for (int it = -1; it < iters; ++it) {
         int i = 0;
         RNB_CUDA(cudaEventRecord(ev[i], s));
-        void* pool = fp8 ? p.pool_raw : p.pool_out;
+        void* pool = p.pool_raw ? p.pool_raw : p.pool_out;
         if (stem_tc)
             RNB_CUDA(launch_stem_any_part(stem_esz(), 0, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
         else
@@ -1306,7 +1363,7 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
             RNB_CUDA(launch_stem_any_part(stem_esz(), 1, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
         else
             RNB_CUDA(launch_maxpool_nhwc(p.stem_out, p.pool_out, n, s_hw, s_hw, 64, esz, s));
-        if (fp8)  // the E4M3 copy of the stem output is booked with the stem's second launch
+        if (p.pool_raw)  // the E4M3 copy of the stem output is booked with the stem's second launch
             RNB_CUDA(launch_quantize_pad_bf16(p.pool_raw, p.pool_out, 1LL * n * p_hw * p_hw, 64, cpad(64),
                                               1.f / fp8_stem_scale, s));
         RNB_CUDA(cudaEventRecord(ev[++i], s));
@@ -1351,13 +1408,13 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
         const double packed = static_cast<double>(stem_any_input_bytes(stem_esz(), 1));
         put(0, 0.0, n * (3.0 * img_px * 4 + packed));
         put(1, 2.0 * n * 64 * 147 * s_hw * s_hw,
-            n * (packed + 64.0 * p_hw * p_hw * stem_esz() + (fp8 ? (64.0 * 2 + 128.0) * p_hw * p_hw : 0.0)) + 28672.0);
+            n * (packed + 64.0 * p_hw * p_hw * stem_esz() + (p.pool_raw ? (64.0 * 2 + 128.0) * p_hw * p_hw : 0.0)) + 28672.0);
     } else {
         put(0, 2.0 * n * 64 * 147 * s_hw * s_hw, n * (3.0 * img_px * 4 + 64.0 * s_hw * s_hw * esz) + 64 * 148 * 4.0);
         put(1, 0.0, n * 64.0 * esz * (1.0 * s_hw * s_hw + 1.0 * p_hw * p_hw));
     }
     for (const ConvPlan& cp : p.convs) put(2, cp.flops, cp.bytes);
-    put(3, 0.0, 1.0 * n * p.last_c * (1.0 * p.last_hw * esz + 4.0));
+    put(3, 0.0, 1.0 * n * p.last_c * (1.0 * p.last_hw * esz + 4.0));  // (FP8: last_c is a multiple of 128 already)
     put(4, 2.0 * n * p.last_c * classes, 4.0 * (1.0 * n * p.last_c + 1.0 * classes * p.last_c + 1.0 * n * classes));
     put(5, 0.0, 4.0 * n * (classes + 1.0));
     return RNB_OK;

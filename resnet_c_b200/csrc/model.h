@@ -86,6 +86,10 @@ struct Model {
     // calibration pass (the first forward, or rnb_model_calibrate): every conv is run once with an amax-recording
     // epilogue on the calibration batch, in network order, on the already quantised inputs.
     bool fp8 = false;
+    // Blocks [0, fp8_first_block) run in BF16 with the fused kernels of the BF16 path, the rest in FP8; the hand-over
+    // is one re-quantisation launch. Default: layer1 stays BF16 (its 64-channel tensors would have to be padded to
+    // 128 FP8 channels: no byte saving and 2-4x the MMA work); RNB_FP8_FROM=0: the whole network in FP8.
+    int fp8_first_block = 0;
     bool fp8_calibrated = false;
     float fp8_stem_scale = 1.f;
     std::vector<float> fp8_out_scale;   // per conv launch, in plan order
@@ -214,7 +218,7 @@ struct Model {
     // stem pre-pass/conv + stem/max-pool + planned conv launches + avg-pool + fc + arg-max
     int launches_per_chunk(int n) {
         ChunkPlan* p = plan_for(n);
-        return p ? static_cast<int>(p->convs.size()) + 5 + (fp8 ? 1 : 0) : 0;
+        return p ? static_cast<int>(p->convs.size()) + 5 + (p->pool_raw ? 1 : 0) : 0;
     }
 };
 

@@ -85,14 +85,17 @@ def test_fp8_conv_with_bn_fold_and_pair_tiles(oracle_lib, monkeypatch):
     assert torch.equal(outs[128], outs[1128]) and torch.equal(outs[128], outs[1256])
 
 
+@pytest.mark.parametrize("fp8_from", ["layer2", "stem"])   # default: layer1 in BF16; RNB_FP8_FROM=0: every layer in FP8
 @pytest.mark.parametrize("name,arch,rbn,batch", [
     ("resnet18_rbn_synth_b4", "resnet18", True, 4),
     ("resnet50_rbn_synth_b4", "resnet50", True, 4),
     ("resnet50_default_synth_b2", "resnet50", False, 2),
     ("resnet152_rbn_synth_b2", "resnet152", True, 2),
 ])
-def test_fp8_model_against_fp64_golden(name, arch, rbn, batch):
+def test_fp8_model_against_fp64_golden(name, arch, rbn, batch, fp8_from, monkeypatch):
     from resnet_c_b200 import engine, weights
+    if fp8_from == "stem":
+        monkeypatch.setenv("RNB_FP8_FROM", "0")
     gold = load_golden(name)
     x = weights.synthetic_images(batch)
     m = engine.ResNet(arch, weights.cached_weights_dir(arch, 0, rbn), dtype="fp8", max_batch=batch)
@@ -102,7 +105,7 @@ def test_fp8_model_against_fp64_golden(name, arch, rbn, batch):
     assert torch.equal(logits, again)
     ref64 = gold["logits_fp64"]
     e = rel_err(logits.cpu().numpy(), ref64)
-    print(f"\\n{name}: fp8 logits rel err {e:.3e}")
+    print(f"\\n{name} (fp8 from {fp8_from}): logits rel err {e:.3e}, launches {m.launches_per_forward(batch)}")
     assert e < FP8_TOL, f"{name}: rel err {e:.3e}"
     assert top1.cpu().tolist() == logits.argmax(1).cpu().tolist()
     srt = np.sort(ref64, axis=1)
