@@ -142,10 +142,10 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, ui
 // All loads (residual from shared memory, bias) are issued before the first store so that their
 // latencies overlap (the staging row is addressed in the shared window: the compiler cannot prove
 // that a generic store does not alias the next generic load and would serialise them).
-template <int ESZ>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint8_t* row, uint32_t c16_base,
-                                               uint32_t swz, const float* __restrict__ bias32,
-                                               int has_res, int relu) {
+template <int ESZ, bool RELU>
+__device__ __forceinline__ void epilogue_chunk_t(const uint32_t (&v)[32], uint8_t* row, uint32_t c16_base,
+                                                 uint32_t swz, const float* __restrict__ bias32, int has_res) {
+    constexpr bool relu = RELU;  // compile-time: a run-time flag made ptxas issue BOTH converts, predicated
     const uint32_t row_addr = ptx::smem_u32(row);
     if (ESZ == 2) {
         uint4 rr[4];
@@ -213,6 +213,17 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint8_t*
     }
 }
 
+// run-time ReLU flag -> one warp-uniform branch per chunk around two specialised bodies
+template <int ESZ>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint8_t* row, uint32_t c16_base,
+                                               uint32_t swz, const float* __restrict__ bias32,
+                                               int has_res, int relu) {
+    if (relu)
+        epilogue_chunk_t<ESZ, true>(v, row, c16_base, swz, bias32, has_res);
+    else
+        epilogue_chunk_t<ESZ, false>(v, row, c16_base, swz, bias32, has_res);
+}
+
 // ---- FP8 (E4M3) epilogue
 __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
     uint16_t lo, hi;  // cvt packs its FIRST source into the upper byte: the element with the lower address goes second
@@ -240,10 +251,11 @@ __device__ __forceinline__ uint32_t pack_e4m3x4_relu(float a, float b, float c, 
 // scale32 / bias32 are PRE-MULTIPLIED per channel (ConvGeom): q = RN_e4m3(relu(acc * scale'[c] + bias'[c] + r * res'))
 // — one FMA (two with a residual) and half a convert per output. `track`: calibration launch, returns max|q value
 // before rounding| of the chunk (0 otherwise).
-__device__ __forceinline__ float epilogue_chunk_fp8(const uint32_t (&v)[32], uint8_t* row, uint32_t c16_base,
-                                                    uint32_t swz, const float* __restrict__ scale32,
-                                                    const float* __restrict__ bias32, float res_mul, int has_res,
-                                                    int relu, bool track) {
+template <bool RELU, bool HAS_RES>
+__device__ __forceinline__ float epilogue_chunk_fp8_t(const uint32_t (&v)[32], uint8_t* row, uint32_t c16_base,
+                                                      uint32_t swz, const float* __restrict__ scale32,
+                                                      const float* __restrict__ bias32, float res_mul, bool track) {
+    constexpr bool relu = RELU, has_res = HAS_RES;
     const uint32_t row_addr = ptx::smem_u32(row);
     uint4 rr[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     if (has_res) {
@@ -284,6 +296,17 @@ __device__ __forceinline__ float epilogue_chunk_fp8(const uint32_t (&v)[32], uin
         sts128(row_addr + (((c16_base + j) ^ swz) << 4), ow[0], ow[1], ow[2], ow[3]);
     }
     return amax;
+}
+
+__device__ __forceinline__ float epilogue_chunk_fp8(const uint32_t (&v)[32], uint8_t* row, uint32_t c16_base,
+                                                    uint32_t swz, const float* __restrict__ scale32,
+                                                    const float* __restrict__ bias32, float res_mul, int has_res,
+                                                    int relu, bool track) {
+    if (has_res)
+        return relu ? epilogue_chunk_fp8_t<true, true>(v, row, c16_base, swz, scale32, bias32, res_mul, track)
+                    : epilogue_chunk_fp8_t<false, true>(v, row, c16_base, swz, scale32, bias32, res_mul, track);
+    return relu ? epilogue_chunk_fp8_t<true, false>(v, row, c16_base, swz, scale32, bias32, res_mul, track)
+                : epilogue_chunk_fp8_t<false, false>(v, row, c16_base, swz, scale32, bias32, res_mul, track);
 }
 
 // calibration launches: fold this thread's maximum into *amax (warp reduce, one atomic per warp)

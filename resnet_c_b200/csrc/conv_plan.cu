@@ -24,7 +24,10 @@ using Cfg2Bf16N128 = Conv2Cfg<128, 2, 5, 3>;
 using Cfg2Tf32N256 = Conv2Cfg<256, 4, 4, 3>;
 using Cfg2Tf32N128 = Conv2Cfg<128, 4, 5, 3>;
 // FP8 (E4M3, kind::f8f6f4): 128 channels per K block, 128 output bytes per staging row
-using CfgFp8N128 = ConvCfg<128, 1, 5, 3>;
+using CfgFp8N128 = ConvCfg<128, 1, 4, 4>;   // (4 stages, 4 staging boxes: 1 % faster than (5, 3) and (3, 6), profiles/ab_r2.txt)
+using CfgFp8N128B = ConvCfg<128, 1, 3, 6>;   // RNB_FP8_CFG=1: shallower K ring, six staging boxes (residual prefetch depth)
+using CfgFp8N128C = ConvCfg<128, 1, 5, 3>;   // RNB_FP8_CFG=2
+static_assert(CfgFp8N128B::SMEM_BYTES <= 232448 && CfgFp8N128C::SMEM_BYTES <= 232448, "smem budget");
 using Cfg2Fp8N256 = Conv2Cfg<256, 1, 5, 3>;
 using Cfg2Fp8N128 = Conv2Cfg<128, 1, 6, 3>;
 static_assert(CfgFp8N128::SMEM_BYTES <= 232448, "smem budget");
@@ -71,6 +74,8 @@ cudaError_t conv_kernels_init() {
     if ((e = set_smem2<Cfg2Tf32N256>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Tf32N128>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgFp8N128>()) != cudaSuccess) return e;
+    if ((e = set_smem<CfgFp8N128B>()) != cudaSuccess) return e;
+    if ((e = set_smem<CfgFp8N128C>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Fp8N256>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Fp8N128>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgBf16N128D>()) != cudaSuccess) return e;
@@ -564,6 +569,9 @@ cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
     }
     if (p.esz == 1) {
         if (p.ctas == 2) return p.bn == 256 ? launch2<Cfg2Fp8N256>(p, stream) : launch2<Cfg2Fp8N128>(p, stream);
+        static const int cfg = getenv("RNB_FP8_CFG") ? atoi(getenv("RNB_FP8_CFG")) : 0;
+        if (cfg == 1) return launch<CfgFp8N128B>(p, stream);
+        if (cfg == 2) return launch<CfgFp8N128C>(p, stream);
         return launch<CfgFp8N128>(p, stream);
     }
     if (p.f32out) return launch<CfgBf16N64F32>(p, stream);

@@ -116,24 +116,28 @@ __global__ void avgpool_nhwc_fp8_kernel(const uint8_t* __restrict__ x, float* __
         float acc[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-        for (int p0 = 0; p0 < HW; p0 += 7) {
-            uint4 v[7];
+        auto add_pixel = [&](const uint4& v) {
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int j = 0; j < 7; ++j)
+            for (int q = 0; q < 4; ++q) {
+                uint32_t h01, h23;
+                asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h01) : "h"(static_cast<uint16_t>(u[q] & 0xFFFFu)));
+                asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h23) : "h"(static_cast<uint16_t>(u[q] >> 16)));
+                const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+                const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+                acc[q * 4 + 0] += f01.x; acc[q * 4 + 1] += f01.y; acc[q * 4 + 2] += f23.x; acc[q * 4 + 3] += f23.y;
+            }
+        };
+        // all loads of a batch of NB pixels are issued before the first add (two latency rounds for a 7 x 7 map)
+        constexpr int NB = 25;
+        for (int p0 = 0; p0 < HW; p0 += NB) {
+            uint4 v[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
                 v[j] = p0 + j < HW ? __ldg(reinterpret_cast<const uint4*>(xp + 1LL * (p0 + j) * C)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-            for (int j = 0; j < 7; ++j) {
-                const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t h01, h23;
-                    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h01) : "h"(static_cast<uint16_t>(u[q] & 0xFFFFu)));
-                    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h23) : "h"(static_cast<uint16_t>(u[q] >> 16)));
-                    const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
-                    const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
-                    acc[q * 4 + 0] += f01.x; acc[q * 4 + 1] += f01.y; acc[q * 4 + 2] += f23.x; acc[q * 4 + 3] += f23.y;
-                }
-            }
+            for (int j = 0; j < NB; ++j)
+                if (p0 + j < HW) add_pixel(v[j]);
         }
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
