@@ -188,6 +188,9 @@ int rnb_group_size(const rnb_group_t* g);
 rnb_model_t* rnb_group_model(rnb_group_t* g, int r);
 /* 1 if replica r stores its results straight into the root's buffers (peer-mapped), 0 if it goes through a copy. */
 int rnb_group_direct_stores(const rnb_group_t* g, int r);
+/* The sharding rule by itself (no GPU needed): `total` images over `world` replicas in contiguous slices, the first
+ * total % world replicas take one image more. */
+int rnb_shard_bounds(int total, int world, int rank, int* first, int* count);
 /* Slice [*first, *first + *count) of a `batch`-image step owned by replica r. */
 int rnb_group_shard(const rnb_group_t* g, int batch, int r, int* first, int* count);
 /* Plan / autotune / capture every replica for its shard of `batch` images ahead of time (blocking). */

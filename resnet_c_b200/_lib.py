@@ -78,6 +78,7 @@ PROTOTYPES = {
     "rnb_group_size": (C.c_int, [_vp]),
     "rnb_group_model": (_vp, [_vp, C.c_int]),
     "rnb_group_direct_stores": (C.c_int, [_vp, C.c_int]),
+    "rnb_shard_bounds": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rnb_group_shard": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rnb_group_warmup": (C.c_int, [_vp, C.c_int]),
     "rnb_group_forward": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, _vp, _vp, _vp]),

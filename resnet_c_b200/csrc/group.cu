@@ -149,6 +149,15 @@ int rnb_group_direct_stores(const rnb_group_t* g, int r) {
     return g && r >= 0 && r < static_cast<int>(g->direct.size()) ? g->direct[r] : 0;
 }
 
+int rnb_shard_bounds(int total, int world, int rank, int* first, int* count) {
+    if (total < 0 || world <= 0 || rank < 0 || rank >= world || !first || !count) {
+        set_error("rnb_shard_bounds: bad argument");
+        return RNB_ERR_INVALID;
+    }
+    shard(total, world, rank, first, count);
+    return RNB_OK;
+}
+
 int rnb_group_shard(const rnb_group_t* g, int batch, int r, int* first, int* count) {
     if (!g || batch < 0 || r < 0 || r >= static_cast<int>(g->models.size()) || !first || !count) {
         set_error("rnb_group_shard: bad argument");

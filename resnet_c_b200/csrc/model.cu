@@ -643,10 +643,16 @@ ChunkPlan* Model::plan_for(int n) {
     std::map<const void*, float> scale_of;
     scale_of[p.pool_out] = fp8_calibrated ? fp8_stem_scale : 1.f;
     int sm_budget = num_sms;  // SMs the next planned conv may use (reduced while a downsample conv runs beside it)
+    // rows > 0: a 1x1 / stride-1 conv over `rows` pixel rows of its [M][C] operands (pointers already offset) instead of
+    // the whole n x in_hw x in_hw tensor — the un-fused remainder of a partially fused launch
     auto add_conv = [&](const ConvWeights& cw, const void* in, int in_hw, const void* res, bool relu,
-                        void* out) -> int {
+                        void* out, int rows = 0) -> int {
         ConvDesc d{};
         d.B = n; d.H = in_hw; d.W = in_hw; d.Cin = cw.Cin; d.Cout = cw.Cout;
+        if (rows > 0) {
+            d.B = 1; d.H = 1; d.W = rows;
+            in_hw = -rows;  // autotune key of the row-range form
+        }
         d.ksize = cw.k; d.stride = cw.stride; d.pad = cw.pad; d.relu = relu;
         d.act = cur_esz == 2 ? ActType::BF16 : (cur_esz == 1 ? ActType::FP8 : ActType::TF32);
         const bool fp8 = cur_esz == 1;  // this launch (shadows the model-wide flag inside add_conv)
@@ -868,8 +874,22 @@ ChunkPlan* Model::plan_for(int n) {
             if (c3n1) {
                 void* t1n = arena.acquire(bytes(nb->conv1.Cout, out_hw));
                 if (!t1n) return fail_alloc();
+                const int M = n * out_hw * out_hw;
+                // Wave tail of the streamed (layer3-shaped) fused launch: it cannot be split in N (conv1' consumes whole
+                // rows of y) nor in M (cta_group::2 with 64 rows per CTA costs the same cycles). When its last wave would
+                // fill at most HALF of the pairs (98 tiles on 74 pairs: ResNet-152 at 128 images), the fused launch takes
+                // the whole waves only and the remaining rows run as the two plain launches conv3 (+ shortcut) and
+                // conv1' — small tiles that fill the machine, with the tail split. Same arithmetic (the fused kernel is
+                // bit-identical to the layer-by-layer path). RNB_C3N1_HYBRID=0: off.
+                int fused_rows = M;
+                {
+                    const int tiles = (M + 255) / 256, pairs = num_sms / 2, rem = tiles % pairs;
+                    const char* hy = getenv("RNB_C3N1_HYBRID");
+                    if (bw.conv3.Cin != 128 && tiles > pairs && rem > 0 && 2 * rem <= pairs && !(hy && atoi(hy) == 0))
+                        fused_rows = (tiles - rem) * 256;
+                }
                 C3n1Desc cd{};
-                cd.M = n * out_hw * out_hw;
+                cd.M = fused_rows;
                 cd.K3 = bw.conv3.Cin; cd.N3 = out_c; cd.N1 = nb->conv1.Cout;
                 cd.reverse = alternate_tiles && (p.convs.size() & 1) != 0;
                 cd.t2 = t2; cd.w3 = bw.conv3.w; cd.bias3 = bw.conv3.bias; cd.residual = shortcut; cd.y = y;
@@ -880,10 +900,22 @@ ChunkPlan* Model::plan_for(int n) {
                     return nullptr;
                 }
                 if (getenv("RNB_VERBOSE"))
-                    fprintf(stderr, "rnb plan: conv#%zu n=%d %dx%d fused conv3 + next conv1 grid %d\n", p.convs.size(), n,
-                            out_hw, out_hw, cp.grid);
+                    fprintf(stderr, "rnb plan: conv#%zu n=%d %dx%d fused conv3 + next conv1 grid %d rows %d of %d\n",
+                            p.convs.size(), n, out_hw, out_hw, cp.grid, fused_rows, M);
                 if (fp8) p.links.push_back({nullptr, nullptr, nullptr});
                 p.convs.push_back(cp);
+                if (fused_rows < M) {
+                    const size_t e2 = 2;  // BF16
+                    auto off = [&](const void* base, int C) {
+                        return static_cast<const uint8_t*>(base) + 1ull * fused_rows * C * e2;
+                    };
+                    uint8_t* y_rem = const_cast<uint8_t*>(off(y, out_c));
+                    if (add_conv(bw.conv3, off(t2, bw.conv3.Cin), out_hw, off(shortcut, out_c), true, y_rem, M - fused_rows))
+                        return nullptr;
+                    if (add_conv(nb->conv1, y_rem, out_hw, nullptr, true, const_cast<uint8_t*>(off(t1n, nb->conv1.Cout)),
+                                 M - fused_rows))
+                        return nullptr;
+                }
                 pre_t1 = t1n;
             } else if (add_conv(bw.conv3, t2, out_hw, shortcut, true, y)) {
                 return nullptr;

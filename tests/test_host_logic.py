@@ -121,3 +121,25 @@ def test_bench_reference_arm_contract(tmp_path):
     assert d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_c_abi_shard_rule_equals_python_rule():
+    """rnb_shard_bounds (what rnb_group_* shards by, csrc/group.cu) and dist.shard_bounds (what the torchrun path
+    shards by) are the same rule — a batch split by one host can be gathered by the other. No GPU involved."""
+    import ctypes as C
+
+    from resnet_c_b200 import _lib, dist
+    lib = _lib.lib()
+    for total in (0, 1, 7, 256, 1000, 2048):
+        for world in (1, 2, 3, 8):
+            covered = 0
+            for rank in range(world):
+                first, count = C.c_int(), C.c_int()
+                assert lib.rnb_shard_bounds(total, world, rank, C.byref(first), C.byref(count)) == 0
+                lo, hi = dist.shard_bounds(total, world, rank)
+                assert (first.value, first.value + count.value) == (lo, hi)
+                covered += count.value
+            assert covered == total
+    first, count = C.c_int(), C.c_int()
+    assert lib.rnb_shard_bounds(10, 0, 0, C.byref(first), C.byref(count)) != 0
+    assert b"bad argument" in lib.rnb_last_error()
