@@ -67,7 +67,7 @@ struct ConvGeom {
     float* amax;
 };
 
-template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_, int OSZ_ = ESZ_>
+template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_, int OSZ_ = ESZ_, int EPI_WARPS_ = 8>
 struct ConvCfg {
     static constexpr int BM = 128;
     static constexpr int BN = BN_;
@@ -88,8 +88,12 @@ struct ConvCfg {
     static constexpr int NBAR = 2 * NSTAGE_ + 4 + 3 * NCBUF_;
     static constexpr int SMEM_BYTES =
         1024 /*align slack*/ + NSTAGE_ * STAGE_BYTES + NCBUF_ * CBUF_BYTES + NBAR * 8 + 16;
-    static constexpr int EPI_WARPS = 8;
+    // epilogue warps: 8 (two per TMEM lane quarter, each takes every second 32-column chunk) or 16 (four per quarter:
+    // a 128-column tile is ONE chunk per warp — for layers whose time is the epilogue's instruction stream)
+    static constexpr int EPI_WARPS = EPI_WARPS_;
     static constexpr int THREADS = 128 + EPI_WARPS * 32;
+    static_assert(EPI_WARPS_ == 8 || EPI_WARPS_ == 16, "8 or 16 epilogue warps");
+    static_assert((BN_ / 32) % (EPI_WARPS_ / 4) == 0, "the warps of a lane quarter split the 32-column chunks evenly");
     static_assert(NCBUF_ >= 2, "need at least two staging buffers");
     static_assert((BN_ / 32) % 2 == 0, "the two warps of a lane quarter split the 32-column chunks");
     static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512,
@@ -262,25 +266,26 @@ __device__ __forceinline__ float epilogue_chunk_fp8_t(const uint32_t (&v)[32], u
 #pragma unroll
         for (int j = 0; j < 2; ++j) rr[j] = lds128(row_addr + (((c16_base + j) ^ swz) << 4));
     }
-    float4 sc[8], b[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = __ldg(reinterpret_cast<const float4*>(scale32 + j * 4));
-        b[j] = __ldg(reinterpret_cast<const float4*>(bias32 + j * 4));
-    }
     float amax = 0.f;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
+        // per-channel vectors of this 16-column piece (loaded per piece: the 16-warp variant has 96 registers per thread)
+        float4 sc[4], b[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            sc[q] = __ldg(reinterpret_cast<const float4*>(scale32 + (j * 4 + q) * 4));
+            b[q] = __ldg(reinterpret_cast<const float4*>(bias32 + (j * 4 + q) * 4));
+        }
         const uint32_t rw[4] = {rr[j].x, rr[j].y, rr[j].z, rr[j].w};
         uint32_t ow[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int g4 = j * 4 + q;  // group of four columns
             float x[4];
-            x[0] = fmaf(__uint_as_float(v[g4 * 4 + 0]), sc[g4].x, b[g4].x);
-            x[1] = fmaf(__uint_as_float(v[g4 * 4 + 1]), sc[g4].y, b[g4].y);
-            x[2] = fmaf(__uint_as_float(v[g4 * 4 + 2]), sc[g4].z, b[g4].z);
-            x[3] = fmaf(__uint_as_float(v[g4 * 4 + 3]), sc[g4].w, b[g4].w);
+            x[0] = fmaf(__uint_as_float(v[g4 * 4 + 0]), sc[q].x, b[q].x);
+            x[1] = fmaf(__uint_as_float(v[g4 * 4 + 1]), sc[q].y, b[q].y);
+            x[2] = fmaf(__uint_as_float(v[g4 * 4 + 2]), sc[q].z, b[q].z);
+            x[3] = fmaf(__uint_as_float(v[g4 * 4 + 3]), sc[q].w, b[q].w);
             if (has_res) {
                 float r[4];
                 unpack_e4m3x4(rw[q], r);
@@ -567,7 +572,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const float* bias_n = bias + n_blk * BN;
             float amax = 0.f;
 #pragma unroll 1
-            for (int chunk = h; chunk < BN / 32; chunk += 2) {
+            for (int chunk = h; chunk < BN / 32; chunk += Cfg::EPI_WARPS / 4) {
                 uint32_t v[32];
                 __syncwarp();
                 tmem_ld_32x32(taddr + chunk * 32, v);

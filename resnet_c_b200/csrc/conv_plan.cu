@@ -25,6 +25,10 @@ using Cfg2Tf32N256 = Conv2Cfg<256, 4, 4, 3>;
 using Cfg2Tf32N128 = Conv2Cfg<128, 4, 5, 3>;
 // FP8 (E4M3, kind::f8f6f4): 128 channels per K block, 128 output bytes per staging row
 using CfgFp8N128 = ConvCfg<128, 1, 4, 4>;   // (4 stages, 4 staging boxes: 1 % faster than (5, 3) and (3, 6), profiles/ab_r2.txt)
+// 16 epilogue warps (one 32-column chunk per warp and tile): force_bn code 20128
+using CfgBf16N128W16 = ConvCfg<128, 2, 4, 3, 2, 16>;
+using CfgFp8N128W16 = ConvCfg<128, 1, 4, 4, 1, 16>;
+static_assert(CfgBf16N128W16::SMEM_BYTES <= 232448 && CfgFp8N128W16::SMEM_BYTES <= 232448, "smem budget");
 using CfgFp8N128B = ConvCfg<128, 1, 3, 6>;   // RNB_FP8_CFG=1: shallower K ring, six staging boxes (residual prefetch depth)
 using CfgFp8N128C = ConvCfg<128, 1, 5, 3>;   // RNB_FP8_CFG=2
 static_assert(CfgFp8N128B::SMEM_BYTES <= 232448 && CfgFp8N128C::SMEM_BYTES <= 232448, "smem budget");
@@ -75,6 +79,8 @@ cudaError_t conv_kernels_init() {
     if ((e = set_smem2<Cfg2Tf32N128>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgFp8N128>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgFp8N128B>()) != cudaSuccess) return e;
+    if ((e = set_smem<CfgBf16N128W16>()) != cudaSuccess) return e;
+    if ((e = set_smem<CfgFp8N128W16>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgFp8N128C>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Fp8N256>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Fp8N128>()) != cudaSuccess) return e;
@@ -321,7 +327,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     if (d.act == ActType::FP8) {
         if (d.out_f32 || !d.chan_scale || !d.fp8_vecs || d.Cout % 128 != 0 || !(d.out_scale > 0.f))
             return fail(err, errlen, "conv_plan: FP8 needs channel scales + scratch, Cout % 128 == 0 and a positive output scale", -9);
-        if (force_bn == 64 || force_bn == 3064 || force_bn == 4064 || force_bn >= 10000)
+        if (force_bn == 64 || force_bn == 3064 || force_bn == 4064 || (force_bn >= 10000 && force_bn < 20000))
             return fail(err, errlen, "conv_plan: tile family not available in FP8", -9);
     }
     if (d.out_f32) {
@@ -335,6 +341,13 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
         return halo2_plan_init(plan, d, num_sms, err, errlen);
     // +10000: "deep" variant of a tile family — one or two more shared-memory stages in flight paid
     // for with one staging buffer less (for layers whose K loop, not whose epilogue, is the bottleneck)
+    // +20000: single-CTA BN = 128 tiles with SIXTEEN epilogue warps (one 32-column chunk per warp and tile)
+    if (force_bn == 20128) {
+        if (d.act == ActType::TF32 || d.out_f32 || d.Cout % 128 != 0)
+            return fail(err, errlen, "conv_plan: the 16-warp epilogue exists for bf16 / fp8 tiles of 128 columns", -9);
+        plan->w16 = 1;
+        force_bn = 128;
+    }
     const int deep = force_bn >= 10000 ? 1 : 0;
     if (deep) force_bn -= 10000;
     plan->deep = deep;
@@ -569,12 +582,14 @@ cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
     }
     if (p.esz == 1) {
         if (p.ctas == 2) return p.bn == 256 ? launch2<Cfg2Fp8N256>(p, stream) : launch2<Cfg2Fp8N128>(p, stream);
+        if (p.w16) return launch<CfgFp8N128W16>(p, stream);
         static const int cfg = getenv("RNB_FP8_CFG") ? atoi(getenv("RNB_FP8_CFG")) : 0;
         if (cfg == 1) return launch<CfgFp8N128B>(p, stream);
         if (cfg == 2) return launch<CfgFp8N128C>(p, stream);
         return launch<CfgFp8N128>(p, stream);
     }
     if (p.f32out) return launch<CfgBf16N64F32>(p, stream);
+    if (p.w16 && p.esz == 2) return launch<CfgBf16N128W16>(p, stream);
     if (p.deep && p.esz == 2) {
         if (p.ctas == 2) return p.bn == 256 ? launch2<Cfg2Bf16N256D>(p, stream) : launch2<Cfg2Bf16N128D>(p, stream);
         if (p.bn == 128) return launch<CfgBf16N128D>(p, stream);

@@ -85,6 +85,7 @@ struct ConvPlan {
     const float* bias;
     int bn;       // tile N
     int ctas;     // 1 = single-CTA 128-pixel tiles, 2 = CTA-pair 256-pixel tiles (cta_group::2)
+    int w16;      // 1 = single-CTA BN = 128 kernel with 16 epilogue warps (force_bn code 20128; bf16 / fp8)
     int deep;     // 1 = deeper smem pipeline / fewer staging buffers variant of the tile family (bf16)
     int f32out;   // 1 = FP32-output variant of the single-CTA kernel (FC layer)
     int halo;     // 1 = conv3x3_halo_kernel (3x3/1, 64->64, bf16): tmA/tmOut are 4-D tiled maps, geometry in hg

@@ -692,20 +692,22 @@ ChunkPlan* Model::plan_for(int n) {
             auto hit = tuned.find(key);
             int best_force = hit != tuned.end() ? hit->second : -1;
             if (best_force < 0) {
+                // (20128, the 16-epilogue-warp variant, was a candidate for one session: never selected on any layer of any config)
                 const int cands[9] = {64, 128, 1128, 1256, 3064, 4064, 10128, 11128, 11256};
                 float best_ms = 1e30f;
                 cudaEvent_t e0, e1;
                 cudaEventCreate(&e0);
                 cudaEventCreate(&e1);
                 for (int force : cands) {
-                    if (fp8 && force != 128 && force != 1128 && force != 1256) continue;
+                    if (fp8 && force != 128 && force != 1128 && force != 1256 && force != 20128) continue;
+                    if (force == 20128 && (cur_esz == 4 || cw.Cout % 128 != 0)) continue;
                     if (force == 3064 && !conv_plan_halo_ok(d)) continue;
                     if (force == 4064 && !conv_plan_halo2_ok(d)) continue;
                     // deep-pipeline variants trade a staging buffer for pipeline stages: only for layers
                     // whose epilogue is light (no residual prefetch) and whose K loop is long; timing a
                     // residual layer alone flatters them (measured in the full network: slower)
                     if (force >= 10000 && (cur_esz != 2 || res || cw.k * cw.k * cw.Cin < 256)) continue;
-                    if (cw.Cout % (force % 1000) != 0) continue;
+                    if (force != 20128 && cw.Cout % (force % 1000) != 0) continue;
                     if (force == 64 && cw.Cout % 128 == 0 && 1LL * n * in_hw * in_hw > 4096) continue;
                     ConvPlan trial;
                     if (conv_plan_init(&trial, d, sm_budget, force, err, sizeof(err))) continue;
@@ -739,7 +741,7 @@ ChunkPlan* Model::plan_for(int n) {
         if (getenv("RNB_VERBOSE"))
             fprintf(stderr, "rnb plan: conv#%zu n=%d %dx%d %d->%d k%d s%d res=%d : %s tile %dx%d grid %d\n",
                     p.convs.size(), n, in_hw, in_hw, cw.Cin, cw.Cout, cw.k, cw.stride, res ? 1 : 0,
-                    cp.halo2 ? "halo-pair" : cp.halo ? "halo" : (cp.ctas == 2 ? (cp.deep ? "pair-deep" : "pair") : (cp.deep ? "single-deep" : "single")),
+                    cp.halo2 ? "halo-pair" : cp.halo ? "halo" : (cp.ctas == 2 ? (cp.deep ? "pair-deep" : (cp.g.split_from < cp.g.m_tiles * cp.g.n_tiles ? "pair-split" : "pair")) : (cp.deep ? "single-deep" : (cp.w16 ? "single-16w" : "single"))),
                     cp.ctas == 2 ? 256 : 128, cp.bn, cp.grid);
         if (fp8 && fp8_premultiply(&cp, d.in_scale, d.res_scale, d.out_scale, cap_stream) != cudaSuccess) {
             set_error("FP8 epilogue vector setup failed");
@@ -747,6 +749,16 @@ ChunkPlan* Model::plan_for(int n) {
         }
         p.convs.push_back(cp);
         return 0;
+    };
+    // The streamed (layer3-shaped) fused conv3 + conv1' launch has no tail split; the plain launches have. When its last
+    // wave would fill at most half of the CTA pairs (98 tiles on 74 pairs: 128 images at 14 x 14), layer3 runs un-fused
+    // with split tails instead — measured 3.545 vs 3.601 ms for ResNet-152 at 128 images (profiles/ab_r2.txt),
+    // bit-identical. RNB_C3N1_AUTO=0: always fuse.
+    auto c3n1s_short_tail = [&](int M, int k3) {
+        const char* au = getenv("RNB_C3N1_AUTO");
+        if (k3 == 128 || (au && atoi(au) == 0)) return false;
+        const int tiles = (M + 255) / 256, pairs = num_sms / 2, rem = tiles % pairs;
+        return tiles > pairs && rem > 0 && 2 * rem <= pairs;
     };
     void* pre_t1 = nullptr;  // this block's conv1 output, already produced by the previous fused launch
     for (size_t bi = 0; bi < blocks.size(); ++bi) {
@@ -870,22 +882,21 @@ ChunkPlan* Model::plan_for(int n) {
             const bool c3n1 = fuse_level >= 1 && fuse_next && besz == 2 && nb && nb->bottleneck && !nb->has_ds &&
                               nb->conv1.Cin == out_c && nb->conv2.stride == 1 &&
                               c3n1_shape_ok(bw.conv3.Cin, out_c, nb->conv1.Cout) &&
-                              c3level >= (bw.conv3.Cin == 128 ? 1 : 2);
+                              c3level >= (bw.conv3.Cin == 128 ? 1 : 2) && !c3n1s_short_tail(n * out_hw * out_hw, bw.conv3.Cin);
             if (c3n1) {
                 void* t1n = arena.acquire(bytes(nb->conv1.Cout, out_hw));
                 if (!t1n) return fail_alloc();
                 const int M = n * out_hw * out_hw;
                 // Wave tail of the streamed (layer3-shaped) fused launch: it cannot be split in N (conv1' consumes whole
-                // rows of y) nor in M (cta_group::2 with 64 rows per CTA costs the same cycles). When its last wave would
-                // fill at most HALF of the pairs (98 tiles on 74 pairs: ResNet-152 at 128 images), the fused launch takes
-                // the whole waves only and the remaining rows run as the two plain launches conv3 (+ shortcut) and
-                // conv1' — small tiles that fill the machine, with the tail split. Same arithmetic (the fused kernel is
-                // bit-identical to the layer-by-layer path). RNB_C3N1_HYBRID=0: off.
+                // rows of y) nor in M (cta_group::2 with 64 rows per CTA costs the same cycles). RNB_C3N1_HYBRID=1
+                // (opt-in, bit-identical, measured SLOWER: ResNet-152 B=128 3.76 vs 3.60 ms — two more launches per block
+                // cost more than the saved half wave): the fused launch takes the whole waves only and the remaining
+                // rows run as the plain conv3 (+ shortcut) and conv1' launches.
                 int fused_rows = M;
                 {
                     const int tiles = (M + 255) / 256, pairs = num_sms / 2, rem = tiles % pairs;
                     const char* hy = getenv("RNB_C3N1_HYBRID");
-                    if (bw.conv3.Cin != 128 && tiles > pairs && rem > 0 && 2 * rem <= pairs && !(hy && atoi(hy) == 0))
+                    if (bw.conv3.Cin != 128 && tiles > pairs && rem > 0 && 2 * rem <= pairs && hy && atoi(hy) != 0)
                         fused_rows = (tiles - rem) * 256;
                 }
                 C3n1Desc cd{};

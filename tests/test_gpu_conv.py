@@ -164,3 +164,29 @@ def test_tail_split_is_bit_identical_to_whole_tiles(case, monkeypatch):
     torch.cuda.synchronize()
     assert torch.equal(whole, split)
     assert float(whole.abs().max()) > 0
+
+
+@pytest.mark.parametrize("case", [
+    # (Cin, Cout, H, k, stride, pad, residual, B)
+    (512, 2048, 7, 1, 1, 0, True, 16),     # layer4 conv3 + shortcut: the epilogue-bound shape the variant is for
+    (128, 128, 14, 3, 1, 1, False, 5),
+])
+def test_sixteen_epilogue_warps_equal_eight(case, monkeypatch):
+    """ConvCfg<..., EPI_WARPS = 16> (force code 20128) splits the same 32-column chunks over twice as many warps:
+    bit-identical to the 8-warp kernel, BF16 and FP8."""
+    from resnet_c_b200 import engine
+    Cin, Cout, H, k, stride, pad, residual, B = case
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, Cin, H, H, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5).cuda()
+    OH = (2 * pad + H - k) // stride + 1
+    res = torch.randn(B, Cout, OH, OH, generator=g).cuda() if residual else None
+    outs = {}
+    for tile in ("128", "20128"):
+        monkeypatch.setenv("RNB_FORCE_TILE", tile)
+        outs[tile] = (engine.conv_bn_act_forward(x, w, None, res, True, stride, pad, "bf16"),
+                      engine.conv_fp8_forward(x, w, None, res, True, stride, pad, 2.0 ** -6, 2.0 ** -6, 2.0 ** -5))
+    torch.cuda.synchronize()
+    assert torch.equal(outs["128"][0], outs["20128"][0])
+    assert torch.equal(outs["128"][1], outs["20128"][1])
+    assert float(outs["128"][0].abs().max()) > 0 and float(outs["128"][1].abs().max()) > 0

@@ -305,10 +305,12 @@ def test_scheduling_switches_are_bit_identical(monkeypatch, arch, batch):
     layer3 to run more pair tiles (98 / 78) than there are SM pairs, so rings wrap and the balanced grid differs."""
     names = ("layer2.3", "layer3.0", "layer3.5", "layer4.2")
     base = _run_with_env(monkeypatch, {"RNB_FUSE": "1", "RNB_FUSE_NEXT": "1"}, arch, batch, names)
-    # round 2: RNB_C3N1_HYBRID=0 (the fused layer3 tail also takes its last, partial wave instead of handing those rows
-    # to the plain conv3 / conv1' launches) and RNB_NO_SPLIT=1 (whole tiles in the last wave of the CTA-pair convs)
+    # round 2: RNB_C3N1_AUTO=0 (layer3 fused although its last wave is short: the default un-fuses it at these batch
+    # sizes), RNB_C3N1_HYBRID=1 (fused launch over the whole waves, plain launches over the remaining rows) and
+    # RNB_NO_SPLIT=1 (whole tiles in the last wave of the CTA-pair convs)
     for env in ({"RNB_C3N1S_RINGS": "1"}, {"RNB_C3N1S_RINGS": "2"}, {"RNB_C3N1S_RINGS": "3"}, {"RNB_BALANCE": "15"},
-                {"RNB_C3N1_HYBRID": "0"}, {"RNB_NO_SPLIT": "1"}, {"RNB_C3N1_HYBRID": "0", "RNB_NO_SPLIT": "1"}):
+                {"RNB_C3N1_AUTO": "0"}, {"RNB_C3N1_AUTO": "0", "RNB_C3N1_HYBRID": "1"}, {"RNB_NO_SPLIT": "1"},
+                {"RNB_C3N1_AUTO": "0", "RNB_NO_SPLIT": "1"}):
         got = _run_with_env(monkeypatch, {"RNB_FUSE": "1", "RNB_FUSE_NEXT": "1", **env}, arch, batch, names)
         for n in names:
             assert torch.equal(got[2][n], base[2][n]), f"{n} differs ({env})"
