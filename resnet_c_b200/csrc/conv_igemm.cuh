@@ -579,17 +579,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tmem_ld_wait();
                 const int byte_off = chunk * 32 * Cfg::OSZ;
                 uint8_t* row = cbuf + (byte_off >> 7) * Cfg::BOX_BYTES + row_in_tile * 128;
-                if (Cfg::ESZ == 1)
+                if (Cfg::OSZ == 1)
                     amax = fmaxf(amax, epilogue_chunk_fp8(v, row, (byte_off & 127) >> 4, swz,
                                                           g.chan_scale + n_blk * BN + chunk * 32, bias_n + chunk * 32,
                                                           g.res_mul, g.has_res, g.relu, g.amax != nullptr));
                 else if (Cfg::OSZ != Cfg::ESZ)
                     epilogue_chunk_f32out(v, row, swz, bias_n + chunk * 32, g.relu);
                 else
-                    epilogue_chunk<Cfg::ESZ == 1 ? 2 : Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz, bias_n + chunk * 32,
+                    epilogue_chunk<Cfg::OSZ == 1 ? 2 : Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz, bias_n + chunk * 32,
                                                                  g.has_res, g.relu);
             }
-            if (Cfg::ESZ == 1 && g.amax) amax_commit(g.amax, m_blk * Cfg::BM + row_in_tile < g.M ? amax : 0.f);
+            if (Cfg::OSZ == 1 && g.amax) amax_commit(g.amax, m_blk * Cfg::BM + row_in_tile < g.M ? amax : 0.f);
             // accumulator drained by this warp: hand the TMEM stage back; publish the staged rows
             // to the async proxy and tell the store warp
             tc_fence_before();

@@ -31,20 +31,22 @@
 
 namespace rnb {
 
-template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_>
+template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_, int OSZ_ = ESZ_>
 struct Conv2Cfg {
     static constexpr int BM = 256;                    // pixels per CTA pair
     static constexpr int BM_CTA = 128;                // pixels per CTA
     static constexpr int BN = BN_;
     static constexpr int ESZ = ESZ_;
+    static constexpr int OSZ = OSZ_;                   // output (and residual) element bytes; OSZ = 1 with ESZ = 2:
+                                                       // BF16 operands, E4M3 output (hand-over of a mixed FP8 plan)
     static constexpr int BK = 128 / ESZ_;
     static constexpr int NSTAGE = NSTAGE_;
     static constexpr int NCBUF = NCBUF_;
     static constexpr int A_BYTES = BM_CTA * 128;
     static constexpr int B_BYTES = (BN_ / 2) * 128;    // this CTA's half of the weight tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BOX_COLS = 128 / ESZ_;
-    static constexpr int SUB_BOXES = ESZ_ == 1 ? 1 : 2;  // 128-byte boxes per epilogue sub-tile (FP8: one box = 128 columns)
+    static constexpr int BOX_COLS = 128 / OSZ_;
+    static constexpr int SUB_BOXES = OSZ_ == 1 ? 1 : 2;  // 128-byte boxes per epilogue sub-tile (FP8: one box = 128 columns)
     static constexpr int EPI_N = SUB_BOXES * BOX_COLS;   // columns per epilogue sub-tile
     static constexpr int NSUB = BN_ / EPI_N;
     static constexpr int BOX_BYTES = BM_CTA * 128;
@@ -429,17 +431,17 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     __syncwarp();
                     tmem_ld_32x32(taddr + sub * Cfg::EPI_N + chunk * 32, v);
                     tmem_ld_wait();
-                    const int byte_off = chunk * 32 * Cfg::ESZ;
+                    const int byte_off = chunk * 32 * Cfg::OSZ;
                     uint8_t* row = cbuf + (byte_off >> 7) * Cfg::BOX_BYTES + row_in_tile * 128;
-                    if (Cfg::ESZ == 1)
+                    if (Cfg::OSZ == 1)
                         amax = fmaxf(amax, epilogue_chunk_fp8(v, row, (byte_off & 127) >> 4, swz,
                                                               g.chan_scale + col0 + chunk * 32, bias + col0 + chunk * 32,
                                                               g.res_mul, g.has_res, g.relu, g.amax != nullptr));
                     else
-                        epilogue_chunk<Cfg::ESZ == 1 ? 2 : Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz,
+                        epilogue_chunk<Cfg::OSZ == 1 ? 2 : Cfg::ESZ>(v, row, (byte_off & 127) >> 4, swz,
                                                                      bias + col0 + chunk * 32, g.has_res, g.relu);
                 }
-                if (Cfg::ESZ == 1 && g.amax) amax_commit(g.amax, row0 + row_in_tile < g.M ? amax : 0.f);
+                if (Cfg::OSZ == 1 && g.amax) amax_commit(g.amax, row0 + row_in_tile < g.M ? amax : 0.f);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();

@@ -25,6 +25,13 @@ using Cfg2Tf32N256 = Conv2Cfg<256, 4, 4, 3>;
 using Cfg2Tf32N128 = Conv2Cfg<128, 4, 5, 3>;
 // FP8 (E4M3, kind::f8f6f4): 128 channels per K block, 128 output bytes per staging row
 using CfgFp8N128 = ConvCfg<128, 1, 4, 4>;   // (4 stages, 4 staging boxes: 1 % faster than (5, 3) and (3, 6), profiles/ab_r2.txt)
+// BF16 operands, E4M3 output (hand-over convs of the mixed FP8 plan)
+using CfgBf16N128F8 = ConvCfg<128, 2, 4, 3, 1>;
+using Cfg2Bf16N256F8 = Conv2Cfg<256, 2, 4, 3, 1>;
+using Cfg2Bf16N128F8 = Conv2Cfg<128, 2, 5, 3, 1>;
+static_assert(CfgBf16N128F8::SMEM_BYTES <= 232448 && Cfg2Bf16N256F8::SMEM_BYTES <= 232448 &&
+                  Cfg2Bf16N128F8::SMEM_BYTES <= 232448,
+              "smem budget");
 // 16 epilogue warps (one 32-column chunk per warp and tile): force_bn code 20128
 using CfgBf16N128W16 = ConvCfg<128, 2, 4, 3, 2, 16>;
 using CfgFp8N128W16 = ConvCfg<128, 1, 4, 4, 1, 16>;
@@ -79,6 +86,9 @@ cudaError_t conv_kernels_init() {
     if ((e = set_smem2<Cfg2Tf32N128>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgFp8N128>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgFp8N128B>()) != cudaSuccess) return e;
+    if ((e = set_smem<CfgBf16N128F8>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Bf16N256F8>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Bf16N128F8>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgBf16N128W16>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgFp8N128W16>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgFp8N128C>()) != cudaSuccess) return e;
@@ -324,7 +334,9 @@ int c3n1_plan_init(ConvPlan* plan, const C3n1Desc& d, int num_sms, char* err, in
 int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn, char* err,
                    int errlen) {
     memset(plan, 0, sizeof(*plan));
-    if (d.act == ActType::FP8) {
+    if (d.out_fp8 && d.act != ActType::BF16)
+        return fail(err, errlen, "conv_plan: E4M3 output with other operands than BF16 is the FP8 path itself", -9);
+    if (d.act == ActType::FP8 || d.out_fp8) {
         if (d.out_f32 || !d.chan_scale || !d.fp8_vecs || d.Cout % 128 != 0 || !(d.out_scale > 0.f))
             return fail(err, errlen, "conv_plan: FP8 needs channel scales + scratch, Cout % 128 == 0 and a positive output scale", -9);
         if (force_bn == 64 || force_bn == 3064 || force_bn == 4064 || (force_bn >= 10000 && force_bn < 20000))
@@ -335,7 +347,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
             return fail(err, errlen, "conv_plan: FP32-output mode needs BF16 operands, no residual, out_cols % 4 == 0", -8);
         force_bn = 64;
     }
-    if (force_bn == 3064 || (force_bn == 0 && d.act != ActType::FP8 && conv_plan_halo_ok(d) && !getenv("RNB_NO_HALO")))
+    if (force_bn == 3064 || (force_bn == 0 && d.act != ActType::FP8 && !d.out_fp8 && conv_plan_halo_ok(d) && !getenv("RNB_NO_HALO")))
         return halo_plan_init(plan, d, num_sms, err, errlen);
     if (force_bn == 4064 || (force_bn == 0 && conv_plan_halo2_ok(d) && !getenv("RNB_NO_HALO")))
         return halo2_plan_init(plan, d, num_sms, err, errlen);
@@ -343,7 +355,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     // for with one staging buffer less (for layers whose K loop, not whose epilogue, is the bottleneck)
     // +20000: single-CTA BN = 128 tiles with SIXTEEN epilogue warps (one 32-column chunk per warp and tile)
     if (force_bn == 20128) {
-        if (d.act == ActType::TF32 || d.out_f32 || d.Cout % 128 != 0)
+        if (d.act == ActType::TF32 || d.out_f32 || d.out_fp8 || d.Cout % 128 != 0)
             return fail(err, errlen, "conv_plan: the 16-warp epilogue exists for bf16 / fp8 tiles of 128 columns", -9);
         plan->w16 = 1;
         force_bn = 128;
@@ -352,6 +364,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     if (deep) force_bn -= 10000;
     plan->deep = deep;
     const int esz = static_cast<int>(d.act);
+    const int osz = d.out_fp8 ? 1 : esz;
     const int bk = 128 / esz;
     if (d.ksize != 1 && d.ksize != 3) return fail(err, errlen, "conv_plan: ksize must be 1 or 3", -2);
     if (d.Cin % bk != 0) return fail(err, errlen, "conv_plan: Cin must be a multiple of the K block", -3);
@@ -406,6 +419,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     plan->bias = d.bias;
     plan->bn = bn;
     plan->esz = esz;
+    plan->osz = osz;
     plan->ctas = ctas;
     const int tiles = g.m_tiles * g.n_tiles;
     g.split_from = tiles;
@@ -421,7 +435,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
         // pairs, its tiles run as two N halves on twice as many pairs: 98 tiles on 74 pairs take 1.5 instead
         // of 2 tile times (layer4 at 256 images, layer3 of ResNet-152 at 128). Bit-identical. RNB_NO_SPLIT=1: off.
         const bool no_split = getenv("RNB_NO_SPLIT") && atoi(getenv("RNB_NO_SPLIT")) != 0;
-        const int nsub = esz == 1 ? bn / 128 : bn / (2 * (128 / esz));  // Conv2Cfg::NSUB
+        const int nsub = osz == 1 ? bn / 128 : bn / (2 * (128 / esz));  // Conv2Cfg::NSUB
         if (!no_split && nsub % 2 == 0) {
             const int max_pairs = num_sms / 2;
             const int rem = tiles % pairs;
@@ -438,7 +452,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     }
     plan->flops = 2.0 * static_cast<double>(M) * d.Cout * (1.0 * d.ksize * d.ksize * d.Cin);
     plan->bytes = 1.0 * d.B * d.H * d.W * d.Cin * esz + 1.0 * d.Cout * d.ksize * d.ksize * d.Cin * esz +
-                  4.0 * d.Cout + (d.residual ? 2.0 : 1.0) * static_cast<double>(M) * d.Cout * esz;
+                  4.0 * d.Cout + (d.residual ? 2.0 : 1.0) * static_cast<double>(M) * d.Cout * osz;
 
     const TmDtype dt = d.act == ActType::BF16 ? TmDtype::BF16 : (d.act == ActType::FP8 ? TmDtype::U8 : TmDtype::F32);
     int r;
@@ -458,12 +472,12 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
         plan->bytes = 1.0 * d.B * d.H * d.W * d.Cin * esz + 1.0 * d.out_cols * d.Cin * esz + 4.0 * d.out_cols +
                       4.0 * static_cast<double>(M) * d.out_cols;
         plan->flops = 2.0 * static_cast<double>(M) * d.out_cols * d.Cin;
-    } else if ((r = make_tiled_2d(&plan->tmOut, dt, d.out, M, d.Cout, 128)) != 0)
+    } else if ((r = make_tiled_2d(&plan->tmOut, d.out_fp8 ? TmDtype::U8 : dt, d.out, M, d.Cout, 128)) != 0)
         return fail(err, errlen, "conv_plan: tiled tensor map (out) failed", r);
     const void* res = d.residual ? d.residual : d.out;
     if (d.out_f32)
         plan->tmRes = plan->tmOut;
-    else if ((r = make_tiled_2d(&plan->tmRes, dt, res, M, d.Cout, 128)) != 0)
+    else if ((r = make_tiled_2d(&plan->tmRes, d.out_fp8 ? TmDtype::U8 : dt, res, M, d.Cout, 128)) != 0)
         return fail(err, errlen, "conv_plan: tiled tensor map (residual) failed", r);
     return 0;
 }
@@ -589,6 +603,10 @@ cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
         return launch<CfgFp8N128>(p, stream);
     }
     if (p.f32out) return launch<CfgBf16N64F32>(p, stream);
+    if (p.esz == 2 && p.osz == 1) {
+        if (p.ctas == 2) return p.bn == 256 ? launch2<Cfg2Bf16N256F8>(p, stream) : launch2<Cfg2Bf16N128F8>(p, stream);
+        return launch<CfgBf16N128F8>(p, stream);
+    }
     if (p.w16 && p.esz == 2) return launch<CfgBf16N128W16>(p, stream);
     if (p.deep && p.esz == 2) {
         if (p.ctas == 2) return p.bn == 256 ? launch2<Cfg2Bf16N256D>(p, stream) : launch2<Cfg2Bf16N128D>(p, stream);

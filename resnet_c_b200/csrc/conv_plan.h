@@ -32,6 +32,9 @@ struct ConvDesc {
     const float* chan_scale = nullptr;  // [Cout] weight scales
     float in_scale = 1.f, res_scale = 1.f, out_scale = 1.f;
     float* fp8_vecs = nullptr;          // [2][Cout]: chan_scale', bias'
+    // BF16 operands, E4M3 output (act == BF16): the hand-over conv of a mixed FP8 plan. chan_scale = a vector of ones,
+    // in_scale = 1; residual (if any) is E4M3 too.
+    bool out_fp8 = false;
 };
 
 // Fused layer1 Bottleneck tail (bneck_l1.cuh): conv2 3x3 + conv3 1x1 + shortcut + ReLU, optionally
@@ -92,6 +95,7 @@ struct ConvPlan {
     HaloGeom hg;
     int halo2;    // 1 = conv3x3_halo2_kernel (3x3/1, 64->64, tf32, CTA pair): tmA/tmRes/tmOut are 4-D maps, geometry in h2g
     Halo2Geom h2g;
+    int osz;      // output element bytes (= esz except for the BF16 -> E4M3 hand-over convs)
     int esz;      // element bytes
     int grid;     // persistent CTAs
     int side;     // 1 = launched on the engine's side stream (downsample conv overlapped with conv1/conv2)

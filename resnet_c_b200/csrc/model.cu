@@ -172,6 +172,7 @@ Model::~Model() {
     arena.free_all();
     cudaFree(u8_scratch);
     cudaFree(fp8_amax_dev);
+    cudaFree(fp8_ones);
     for (void* v : fp8_vec_allocs) cudaFree(v);
     cudaFree(host_x_dev); cudaFree(host_logits_dev); cudaFree(host_top1_dev); cudaFree(scratch_logits);
     if (blob) {  // load_packed(): every weight pointer points into this one allocation
@@ -245,6 +246,8 @@ int Model::configure(const std::string& arch_name, int dtype, int max_batch_, in
         side_sms = 0;
         const char* ff = getenv("RNB_FP8_FROM");
         fp8_first_block = ff && atoi(ff) == 0 ? 0 : spec->blocks[0];   // default: layer1 in BF16
+        const char* ho = getenv("RNB_FP8_HANDOVER");
+        fp8_fused_handover = fp8_first_block > 0 && !(ho && atoi(ho) == 0);
     }
     return RNB_OK;
 }
@@ -291,16 +294,20 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
             const int stride = i == 0 ? layer_stride : 1;
             const int out_hw = hw / stride;
             // mixed FP8 plan: the blocks before fp8_first_block keep BF16 weights
-            const int esz = fp8 && static_cast<int>(blocks.size()) - 1 < fp8_first_block ? 2 : this->esz;
+            const int bidx = static_cast<int>(blocks.size()) - 1;
+            const int esz = fp8 && bidx < fp8_first_block ? 2 : this->esz;
+            // fused hand-over: conv1 and the downsample of the first FP8 block keep BF16 weights (E4M3 output)
+            const bool will_ds = i == 0 && (stride != 1 || in_c != out_c);
+            const int esz_in = fp8 && fp8_fused_handover && bidx == fp8_first_block && will_ds ? 2 : esz;
             if (bottleneck) {
-                if ((r = load_conv(dir, p + "conv1", p + "bn1", in_c, mid, 1, 1, 0, esz, bw.conv1))) return r;
+                if ((r = load_conv(dir, p + "conv1", p + "bn1", in_c, mid, 1, 1, 0, esz_in, bw.conv1))) return r;
                 if ((r = load_conv(dir, p + "conv2", p + "bn2", mid, mid, 3, stride, 1, esz, bw.conv2))) return r;
                 if ((r = load_conv(dir, p + "conv3", p + "bn3", mid, out_c, 1, 1, 0, esz, bw.conv3))) return r;
                 macs += 1.0 * hw * hw * in_c * mid + 1.0 * out_hw * out_hw * mid * mid * 9 +
                         1.0 * out_hw * out_hw * mid * out_c;
                 num_convs += 3;
             } else {
-                if ((r = load_conv(dir, p + "conv1", p + "bn1", in_c, mid, 3, stride, 1, esz, bw.conv1))) return r;
+                if ((r = load_conv(dir, p + "conv1", p + "bn1", in_c, mid, 3, stride, 1, esz_in, bw.conv1))) return r;
                 if ((r = load_conv(dir, p + "conv2", p + "bn2", mid, mid, 3, 1, 1, esz, bw.conv2))) return r;
                 macs += 1.0 * out_hw * out_hw * in_c * mid * 9 + 1.0 * out_hw * out_hw * mid * mid * 9;
                 num_convs += 2;
@@ -308,11 +315,11 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
             if (i == 0 && (stride != 1 || in_c != out_c)) {  // main.cu:71
                 bw.has_ds = true;
                 if ((r = load_conv(dir, p + "downsample.0", p + "downsample.1", in_c, out_c, 1, stride, 0,
-                                   esz, bw.ds)))
+                                   esz_in, bw.ds)))
                     return r;
                 macs += 1.0 * out_hw * out_hw * in_c * out_c;
                 num_convs += 1;
-                if (bottleneck && esz != 1) {
+                if (bottleneck && esz != 1 && esz_in == esz) {
                     std::vector<float> b3(out_c), bd(out_c);
                     RNB_CUDA(cudaMemcpy(b3.data(), bw.conv3.bias, out_c * sizeof(float), cudaMemcpyDeviceToHost));
                     RNB_CUDA(cudaMemcpy(bd.data(), bw.ds.bias, out_c * sizeof(float), cudaMemcpyDeviceToHost));
@@ -355,6 +362,10 @@ int Model::load(const std::string& arch_name, int dtype, const std::string& dir,
         }
     }
     flops_per_image = 2.0 * macs;
+    if (fp8) {
+        std::vector<float> ones(4096, 1.f);
+        if ((r = upload(ones, &fp8_ones))) return r;
+    }
     int rs = create_streams();
     if (rs) return rs;
     set_error("");
@@ -642,6 +653,7 @@ ChunkPlan* Model::plan_for(int n) {
     // FP8: per-tensor scale of every live activation buffer (provisional 1.0 until calibrated)
     std::map<const void*, float> scale_of;
     scale_of[p.pool_out] = fp8_calibrated ? fp8_stem_scale : 1.f;
+    const void* handover_src = nullptr;  // BF16 input of the first FP8 block while that block is being planned
     int sm_budget = num_sms;  // SMs the next planned conv may use (reduced while a downsample conv runs beside it)
     // rows > 0: a 1x1 / stride-1 conv over `rows` pixel rows of its [M][C] operands (pointers already offset) instead of
     // the whole n x in_hw x in_hw tensor — the un-fused remainder of a partially fused launch
@@ -654,7 +666,10 @@ ChunkPlan* Model::plan_for(int n) {
             in_hw = -rows;  // autotune key of the row-range form
         }
         d.ksize = cw.k; d.stride = cw.stride; d.pad = cw.pad; d.relu = relu;
-        d.act = cur_esz == 2 ? ActType::BF16 : (cur_esz == 1 ? ActType::FP8 : ActType::TF32);
+        // hand-over conv of a mixed FP8 plan: BF16 input tensor + BF16 weights, E4M3 output
+        const bool ho = handover_src != nullptr && in == handover_src;
+        d.act = ho ? ActType::BF16 : (cur_esz == 2 ? ActType::BF16 : (cur_esz == 1 ? ActType::FP8 : ActType::TF32));
+        d.out_fp8 = ho;
         const bool fp8 = cur_esz == 1;  // this launch (shadows the model-wide flag inside add_conv)
         // Boustrophedon over the launch sequence: every conv walks its tiles in the opposite
         // direction of the previous one, so it begins where its producer just finished (L2-hot).
@@ -663,8 +678,8 @@ ChunkPlan* Model::plan_for(int n) {
         if (!fp8 && this->fp8) p.links.push_back({in, res, out});  // BF16 launch of a mixed plan: no scales
         if (fp8) {
             const size_t idx = p.convs.size();
-            d.chan_scale = cw.wscale;
-            d.in_scale = scale_of[in];
+            d.chan_scale = ho ? fp8_ones : cw.wscale;
+            d.in_scale = ho ? 1.f : scale_of[in];
             d.res_scale = res ? scale_of[res] : 1.f;
             d.out_scale = fp8_calibrated && idx < fp8_out_scale.size() ? fp8_out_scale[idx] : 1.f;
             scale_of[out] = d.out_scale;
@@ -763,7 +778,12 @@ ChunkPlan* Model::plan_for(int n) {
     void* pre_t1 = nullptr;  // this block's conv1 output, already produced by the previous fused launch
     for (size_t bi = 0; bi < blocks.size(); ++bi) {
         const BlockWeights& bw = blocks[bi];
-        if (fp8 && static_cast<int>(bi) == fp8_first_block && fp8_first_block > 0) {
+        handover_src = nullptr;
+        if (fp8 && static_cast<int>(bi) == fp8_first_block && fp8_first_block > 0 && fp8_fused_handover && bw.has_ds &&
+            bw.conv1.wscale == nullptr) {
+            // fused hand-over: this block's conv1 and downsample read the BF16 x themselves and write E4M3
+            handover_src = x;
+        } else if (fp8 && static_cast<int>(bi) == fp8_first_block && fp8_first_block > 0) {
             // hand-over of a mixed plan: the BF16 activation x becomes an E4M3 tensor (scale fixed by calibration)
             const int c = bw.bottleneck ? bw.conv1.Cin : bw.conv1.Cin;   // already padded for the FP8 block
             const int c_real = blocks[bi - 1].bottleneck ? blocks[bi - 1].conv3.Cout : blocks[bi - 1].conv2.Cout;
@@ -1076,8 +1096,10 @@ int Model::apply_fp8_scales(ChunkPlan& p, cudaStream_t s) {
             scale_of[l.out] = fp8_out_scale[i];
             continue;
         }
-        if (cp.esz != 1) continue;  // BF16 head of a mixed plan
-        RNB_CUDA(fp8_premultiply(&cp, scale_of[l.in], l.res ? scale_of[l.res] : 1.f, fp8_out_scale[i], s));
+        if (!cp.fp8_vecs) continue;  // BF16 head of a mixed plan
+        // (a BF16 input — the hand-over convs — has no entry: scale 1)
+        const float s_in = scale_of.count(l.in) ? scale_of[l.in] : 1.f;
+        RNB_CUDA(fp8_premultiply(&cp, s_in, l.res ? scale_of[l.res] : 1.f, fp8_out_scale[i], s));
         cp.g.amax = nullptr;
         scale_of[l.out] = fp8_out_scale[i];
     }
@@ -1131,11 +1153,11 @@ int Model::calibrate_fp8(const float* x, int n) {
             scale_of[l.out] = sc;
             continue;
         }
-        if (cp.esz != 1) {  // BF16 launch
+        if (!cp.fp8_vecs) {  // BF16 launch
             RNB_CUDA(conv_plan_launch(cp, s));
             continue;
         }
-        const float s_in = scale_of[l.in], s_res = l.res ? scale_of[l.res] : 1.f;
+        const float s_in = scale_of.count(l.in) ? scale_of[l.in] : 1.f, s_res = l.res ? scale_of[l.res] : 1.f;
         RNB_CUDA(fp8_premultiply(&cp, s_in, s_res, 1.f, s));
         cp.g.amax = fp8_amax_dev;
         RNB_CUDA(cudaMemsetAsync(fp8_amax_dev, 0, sizeof(float), s));

@@ -90,6 +90,11 @@ struct Model {
     // is one re-quantisation launch. Default: layer1 stays BF16 (its 64-channel tensors would have to be padded to
     // 128 FP8 channels: no byte saving and 2-4x the MMA work); RNB_FP8_FROM=0: the whole network in FP8.
     int fp8_first_block = 0;
+    // Hand-over of the mixed plan: the first FP8 block's conv1 and downsample read the BF16 block input DIRECTLY
+    // (BF16 weights, BF16 MMAs) and write E4M3 — no separate re-quantisation pass over the 411 MB tensor.
+    // RNB_FP8_HANDOVER=0: one quantize_pad launch instead (both convs then run in FP8).
+    bool fp8_fused_handover = false;
+    float* fp8_ones = nullptr;           // [4096] ones: the "weight scale" of a BF16-operand conv with E4M3 output
     bool fp8_calibrated = false;
     float fp8_stem_scale = 1.f;
     std::vector<float> fp8_out_scale;   // per conv launch, in plan order

@@ -85,7 +85,9 @@ def test_fp8_conv_with_bn_fold_and_pair_tiles(oracle_lib, monkeypatch):
     assert torch.equal(outs[128], outs[1128]) and torch.equal(outs[128], outs[1256])
 
 
-@pytest.mark.parametrize("fp8_from", ["layer2", "stem"])   # default: layer1 in BF16; RNB_FP8_FROM=0: every layer in FP8
+# default: layer1 in BF16, the first FP8 block's conv1 / downsample read BF16 and write E4M3; RNB_FP8_HANDOVER=0: one
+# re-quantisation launch instead; RNB_FP8_FROM=0: every layer in FP8
+@pytest.mark.parametrize("fp8_from", ["layer2", "layer2-requant", "stem"])
 @pytest.mark.parametrize("name,arch,rbn,batch", [
     ("resnet18_rbn_synth_b4", "resnet18", True, 4),
     ("resnet50_rbn_synth_b4", "resnet50", True, 4),
@@ -96,6 +98,8 @@ def test_fp8_model_against_fp64_golden(name, arch, rbn, batch, fp8_from, monkeyp
     from resnet_c_b200 import engine, weights
     if fp8_from == "stem":
         monkeypatch.setenv("RNB_FP8_FROM", "0")
+    if fp8_from == "layer2-requant":
+        monkeypatch.setenv("RNB_FP8_HANDOVER", "0")
     gold = load_golden(name)
     x = weights.synthetic_images(batch)
     m = engine.ResNet(arch, weights.cached_weights_dir(arch, 0, rbn), dtype="fp8", max_batch=batch)
