@@ -50,7 +50,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms. The process is started BEFORE the warm-up steps (its
+    start-up — NVML initialisation takes driver locks — must not overlap the timed region: it stalled the host's
+    launches there, most visibly with two streams in flight) and keeps sampling through the timed region; the
+    summary uses the samples that arrived between mark_begin() and mark_end() (+- one period), all of them if none."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -60,6 +63,13 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.lines = []
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def start(self):
         try:
@@ -73,12 +83,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -86,7 +96,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = [ln for t, ln in self.lines
+                 if self.t_begin is not None and self.t_end is not None and self.t_begin - 0.06 <= t <= self.t_end + 0.06]
+        if not lines:
+            lines = [ln for _, ln in self.lines]
+        for ln in lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -302,14 +316,15 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step()
@@ -317,6 +332,7 @@ def main():
         torch.cuda.current_stream().wait_stream(comm_stream)  # the last gathers are inside the timed region
     e1.record()
     barrier()
+    sampler.mark_end()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps

@@ -333,6 +333,11 @@ int rnb_model_num_convs(const rnb_model_t* m) { return m ? m->impl.num_convs : 0
 int rnb_model_launches_per_forward(rnb_model_t* m, int batch) {
     if (!m || batch <= 0) return 0;
     DeviceGuard guard(m->impl.device);
+    auto lc = m->impl.lane_choice.find(batch);
+    if (lc != m->impl.lane_choice.end() && lc->second == 2 && m->impl.lane2) {  // two half batches on two streams
+        const int n0 = (batch + 1) / 2;
+        return m->impl.launches_per_chunk(n0) + m->impl.lane2->launches_per_chunk(batch - n0);
+    }
     int total = 0;
     for (int off = 0; off < batch; off += m->impl.chunk)
         total += m->impl.launches_per_chunk(std::min(m->impl.chunk, batch - off));

@@ -175,6 +175,10 @@ Model::~Model() {
     cudaFree(fp8_ones);
     for (void* v : fp8_vec_allocs) cudaFree(v);
     cudaFree(host_x_dev); cudaFree(host_logits_dev); cudaFree(host_top1_dev); cudaFree(scratch_logits);
+    if (lane_fork) cudaEventDestroy(lane_fork);
+    if (lane_join) cudaEventDestroy(lane_join);
+    lane2.reset();
+    if (is_lane) return;  // the weights belong to the model this lane was made from
     if (blob) {  // load_packed(): every weight pointer points into this one allocation
         cudaFree(blob);
         return;
@@ -1213,7 +1217,90 @@ int Model::set_normalization(const float* mean, const float* std) {
         norm_mean[c] = mean[c];
         norm_std[c] = std[c];
     }
+    if (lane2) return lane2->set_normalization(mean, std);
     return RNB_OK;
+}
+
+// ------------------------------------------------------------------------------------ two lanes
+int Model::make_lane() {
+    std::unique_ptr<Model> l(new Model());
+    l->is_lane = true;
+    l->arch = arch; l->esz = esz; l->classes = classes; l->image = image; l->max_batch = max_batch; l->chunk = chunk;
+    l->num_sms = num_sms; l->device = device; l->bottleneck = bottleneck; l->final_c = final_c;
+    l->stem_w = stem_w; l->stem_bias = stem_bias; l->stem_wk = stem_wk; l->stem_tc = stem_tc;
+    l->blocks = blocks;
+    l->fc_w = fc_w; l->fc_b = fc_b; l->fc_wq = fc_wq; l->fc_bq = fc_bq; l->classes_pad = classes_pad; l->fc_tc = fc_tc;
+    l->num_convs = num_convs; l->flops_per_image = flops_per_image;
+    for (int c = 0; c < 3; ++c) {
+        l->norm_mean[c] = norm_mean[c];
+        l->norm_std[c] = norm_std[c];
+    }
+    l->use_graph = use_graph; l->alternate_tiles = alternate_tiles; l->autotune = autotune; l->side_sms = 0;
+    l->fuse_level = fuse_level; l->fuse_next = fuse_next; l->arena.keep = arena.keep;
+    int r = l->create_streams();
+    if (r) return r;
+    RNB_CUDA(cudaEventCreateWithFlags(&lane_fork, cudaEventDisableTiming));
+    RNB_CUDA(cudaEventCreateWithFlags(&lane_join, cudaEventDisableTiming));
+    lane2 = std::move(l);
+    return RNB_OK;
+}
+
+int Model::forward_two(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1, cudaStream_t s) {
+    const int n0 = (batch + 1) / 2, n1 = batch - n0;
+    const size_t img = 3ull * image * image;
+    cudaStream_t s2 = lane2->host_compute;
+    RNB_CUDA(cudaEventRecord(lane_fork, s));
+    RNB_CUDA(cudaStreamWaitEvent(s2, lane_fork, 0));
+    int r = forward_one(x, x_u8, n0, logits, top1, s);
+    if (r) return r;
+    r = lane2->forward_one(x ? x + n0 * img : nullptr, x_u8 ? x_u8 + n0 * img : nullptr, n1,
+                           logits ? logits + 1ull * n0 * classes : nullptr, top1 ? top1 + n0 : nullptr, s2);
+    if (r) return r;
+    RNB_CUDA(cudaEventRecord(lane_join, s2));
+    RNB_CUDA(cudaStreamWaitEvent(s, lane_join, 0));
+    return RNB_OK;
+}
+
+// 1 or 2 lanes for this batch size; the first use of a size times both forms on the caller's buffers (blocking)
+int Model::lanes_for(int batch, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1, cudaStream_t s) {
+    if (is_lane || fp8 || batch < 2 || batch > chunk || arena.keep) return 1;
+    auto it = lane_choice.find(batch);
+    if (it != lane_choice.end()) return it->second;
+    const int forced = getenv("RNB_LANES") ? atoi(getenv("RNB_LANES")) : 0;
+    int choice = 1;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+    if (forced == 1 || forced == 2) {
+        choice = forced;
+    } else if (autotune && !capturing && logits) {
+        if (!lane2 && make_lane()) return 1;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        float ms[2] = {1e30f, 1e30f};
+        for (int form = 0; form < 2; ++form) {
+            bool ok = true;
+            for (int i = 0; i < 2 && ok; ++i)
+                ok = (form ? forward_two(x, x_u8, batch, logits, top1, s) : forward_one(x, x_u8, batch, logits, top1, s)) == RNB_OK;
+            cudaEventRecord(e0, s);
+            for (int i = 0; i < 4 && ok; ++i)
+                ok = (form ? forward_two(x, x_u8, batch, logits, top1, s) : forward_one(x, x_u8, batch, logits, top1, s)) == RNB_OK;
+            cudaEventRecord(e1, s);
+            if (cudaStreamSynchronize(s) == cudaSuccess && ok) cudaEventElapsedTime(&ms[form], e0, e1);
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        choice = ms[1] < 0.98f * ms[0] ? 2 : 1;
+        if (getenv("RNB_VERBOSE"))
+            fprintf(stderr, "rnb lanes: batch %d one lane %.3f ms, two lanes %.3f ms per step -> %d\n", batch, ms[0] / 4,
+                    ms[1] / 4, choice);
+    }
+    else {
+        return 1;  // no decision possible now (no output buffer to time on, or the stream is capturing): ask again later
+    }
+    if (choice == 2 && !lane2 && make_lane()) choice = 1;
+    lane_choice[batch] = choice;
+    return choice;
 }
 
 int Model::forward_any(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1,
@@ -1226,6 +1313,12 @@ int Model::forward_any(const float* x, const uint8_t* x_u8, int batch, float* lo
         set_error("x_dev is NULL");
         return RNB_ERR_INVALID;
     }
+    if (lanes_for(batch, x, x_u8, logits, top1, s) == 2) return forward_two(x, x_u8, batch, logits, top1, s);
+    return forward_one(x, x_u8, batch, logits, top1, s);
+}
+
+int Model::forward_one(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1,
+                       cudaStream_t s) {
     if (x_u8 && (!(stem_tc && stem_esz() == 2) || (fp8 && !fp8_calibrated)) && !u8_scratch)
         RNB_CUDA(cudaMalloc(&u8_scratch, 1ull * chunk * 3 * image * image * sizeof(float)));
     if (!logits) {

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <map>
+#include <memory>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -183,6 +184,20 @@ struct Model {
     int fuse_level = 2;
     bool fuse_next = true;
     std::map<std::tuple<int, int, int, int, int, int, int, int>, int> tuned;  // layer shape (+ SM budget) -> force_bn code
+
+    // Two lanes (round 2): a batch whose layers leave the persistent grids with short last waves (ResNet-152 at 128
+    // images: 98 tiles on 74 CTA pairs in all of layer3) runs as TWO half batches on two streams — a second engine state
+    // (arena, plans, graphs, streams) that SHARES the weights — so that the idle SMs of one half's tail run the other
+    // half's tiles. Per-image results do not depend on the batch they are in (bit-exact), so the output is unchanged.
+    // Decided per batch size at first use by timing both forms (RNB_LANES=1 / 2 forces; needs RNB_AUTOTUNE).
+    std::unique_ptr<Model> lane2;
+    bool is_lane = false;                 // lane2 of another model: does not own the weights
+    std::map<int, int> lane_choice;       // batch -> 1 | 2
+    cudaEvent_t lane_fork = nullptr, lane_join = nullptr;
+    int make_lane();
+    int forward_one(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1, cudaStream_t s);
+    int forward_two(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1, cudaStream_t s);
+    int lanes_for(int batch, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1, cudaStream_t s);
 
     ~Model();
     int load(const std::string& arch, int dtype, const std::string& dir, int max_batch, int chunk);

@@ -437,3 +437,28 @@ def test_fresh_output_buffers_every_call_and_warmup():
     with pytest.raises(RnbError, match="RNB_KEEP_ACTIVATIONS"):
         model.activation("layer1.0")
     model.close()
+
+
+@pytest.mark.parametrize("arch,batch", [("resnet50", 37), ("resnet18", 6)])
+def test_two_lanes_equal_one_lane(monkeypatch, arch, batch):
+    """RNB_LANES=2: the batch runs as two half batches on two streams (a second arena / plan / graph set sharing the
+    weights, csrc/model.cu forward_two). Per-image results do not depend on the batch an image is in, so logits and
+    top-1 are BIT-IDENTICAL to the one-lane forward — device, uint8 and host paths."""
+    from resnet_c_b200 import weights
+    x = weights.synthetic_images(batch)
+    xu = weights.synthetic_images_u8(batch, seed=9)
+    outs = {}
+    for lanes in ("1", "2"):
+        monkeypatch.setenv("RNB_LANES", lanes)
+        m = _model(arch, True, "bf16", batch)
+        lg, t1 = m.forward(x.cuda())
+        lg2, _ = m.forward(x.cuda())                    # graph replay
+        lu, tu = m.forward_u8(xu.cuda())
+        hl, ht = m.forward_host(x.pin_memory())
+        torch.cuda.synchronize()
+        assert torch.equal(lg, lg2)
+        outs[lanes] = (lg.cpu(), t1.cpu(), lu.cpu(), tu.cpu(), hl.clone(), ht.clone(), m.launches_per_forward(batch))
+        m.close()
+    for a, b in zip(outs["1"][:6], outs["2"][:6]):
+        assert torch.equal(a, b)
+    assert outs["2"][6] > outs["1"][6]
