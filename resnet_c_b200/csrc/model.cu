@@ -172,7 +172,7 @@ Model::~Model() {
     arena.free_all();
     cudaFree(u8_scratch);
     cudaFree(fp8_amax_dev);
-    cudaFree(fp8_ones);
+    if (!is_lane) cudaFree(fp8_ones);
     for (void* v : fp8_vec_allocs) cudaFree(v);
     cudaFree(host_x_dev); cudaFree(host_logits_dev); cudaFree(host_top1_dev); cudaFree(scratch_logits);
     if (lane_fork) cudaEventDestroy(lane_fork);
@@ -1237,6 +1237,10 @@ int Model::make_lane() {
     }
     l->use_graph = use_graph; l->alternate_tiles = alternate_tiles; l->autotune = autotune; l->side_sms = 0;
     l->fuse_level = fuse_level; l->fuse_next = fuse_next; l->arena.keep = arena.keep;
+    // FP8: the lane runs with the SAME calibrated scales (a lane is only made after calibration)
+    l->fp8 = fp8; l->fp8_first_block = fp8_first_block; l->fp8_fused_handover = fp8_fused_handover;
+    l->fp8_calibrated = fp8_calibrated; l->fp8_stem_scale = fp8_stem_scale; l->fp8_out_scale = fp8_out_scale;
+    l->fp8_ones = fp8_ones;
     int r = l->create_streams();
     if (r) return r;
     RNB_CUDA(cudaEventCreateWithFlags(&lane_fork, cudaEventDisableTiming));
@@ -1263,7 +1267,7 @@ int Model::forward_two(const float* x, const uint8_t* x_u8, int batch, float* lo
 
 // 1 or 2 lanes for this batch size; the first use of a size times both forms on the caller's buffers (blocking)
 int Model::lanes_for(int batch, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1, cudaStream_t s) {
-    if (is_lane || fp8 || batch < 2 || batch > chunk || arena.keep) return 1;
+    if (is_lane || (fp8 && !fp8_calibrated) || batch < 2 || batch > chunk || arena.keep) return 1;
     auto it = lane_choice.find(batch);
     if (it != lane_choice.end()) return it->second;
     const int forced = getenv("RNB_LANES") ? atoi(getenv("RNB_LANES")) : 0;
@@ -1451,8 +1455,15 @@ int Model::warmup(int batch, bool include_u8) {
         cudaFree(x);
         return fail_cuda(cudaGetLastError(), "warmup: cudaMalloc");
     }
-    int r = forward(x, batch, nullptr, host_top1_dev, host_compute);
-    if (!r && include_u8) r = forward_u8(reinterpret_cast<const uint8_t*>(x), batch, nullptr, host_top1_dev, host_compute);
+    // (a real logits buffer, so that the one-lane / two-lane decision for this batch size is timed here and not in
+    // the first serving call)
+    if (!scratch_logits && cudaMalloc(&scratch_logits, 1ull * max_batch * classes * sizeof(float)) != cudaSuccess) {
+        cudaFree(x);
+        return fail_cuda(cudaGetLastError(), "warmup: cudaMalloc");
+    }
+    int r = forward(x, batch, scratch_logits, host_top1_dev, host_compute);
+    if (!r && include_u8)
+        r = forward_u8(reinterpret_cast<const uint8_t*>(x), batch, scratch_logits, host_top1_dev, host_compute);
     cudaError_t ce = cudaStreamSynchronize(host_compute);
     cudaFree(x);
     if (r) return r;
