@@ -769,16 +769,7 @@ ChunkPlan* Model::plan_for(int n) {
         p.convs.push_back(cp);
         return 0;
     };
-    // The streamed (layer3-shaped) fused conv3 + conv1' launch has no tail split; the plain launches have. When its last
-    // wave would fill at most half of the CTA pairs (98 tiles on 74 pairs: 128 images at 14 x 14), layer3 runs un-fused
-    // with split tails instead — measured 3.545 vs 3.601 ms for ResNet-152 at 128 images (profiles/ab_r2.txt),
-    // bit-identical. RNB_C3N1_AUTO=0: always fuse.
-    auto c3n1s_short_tail = [&](int M, int k3) {
-        const char* au = getenv("RNB_C3N1_AUTO");
-        if (k3 == 128 || (au && atoi(au) == 0)) return false;
-        const int tiles = (M + 255) / 256, pairs = num_sms / 2, rem = tiles % pairs;
-        return tiles > pairs && rem > 0 && 2 * rem <= pairs;
-    };
+    const bool c3n1_auto = !(getenv("RNB_C3N1_AUTO") && atoi(getenv("RNB_C3N1_AUTO")) == 0);
     void* pre_t1 = nullptr;  // this block's conv1 output, already produced by the previous fused launch
     for (size_t bi = 0; bi < blocks.size(); ++bi) {
         const BlockWeights& bw = blocks[bi];
@@ -906,8 +897,64 @@ ChunkPlan* Model::plan_for(int n) {
             const bool c3n1 = fuse_level >= 1 && fuse_next && besz == 2 && nb && nb->bottleneck && !nb->has_ds &&
                               nb->conv1.Cin == out_c && nb->conv2.stride == 1 &&
                               c3n1_shape_ok(bw.conv3.Cin, out_c, nb->conv1.Cout) &&
-                              c3level >= (bw.conv3.Cin == 128 ? 1 : 2) && !c3n1s_short_tail(n * out_hw * out_hw, bw.conv3.Cin);
-            if (c3n1) {
+                              c3level >= (bw.conv3.Cin == 128 ? 1 : 2);
+            // fused (one launch: conv3 + shortcut + next conv1) or plain (two launches with tile autotune and tail
+            // split)? Which wins depends on how the tile count of THIS batch size falls on the 74 CTA pairs (fused
+            // layer3 at 98 tiles: a full wave + a third; at 149: two waves + one tile), so with the autotuner on the
+            // first such block of a shape is timed both ways on its real buffers (RNB_C3N1_AUTO=0: always fused).
+            bool c3n1_use = c3n1;
+            if (c3n1 && autotune && c3n1_auto) {
+                const std::tuple<int, int, int, int> key{n * out_hw * out_hw, bw.conv3.Cin, out_c, nb->conv1.Cout};
+                auto hit = tuned_c3n1.find(key);
+                if (hit != tuned_c3n1.end()) {
+                    c3n1_use = hit->second != 0;
+                } else {
+                    void* t1n_trial = arena.acquire(bytes(nb->conv1.Cout, out_hw));
+                    if (!t1n_trial) return fail_alloc();
+                    const size_t first = p.convs.size();
+                    float ms_plain = 1e30f, ms_fused = 1e30f;
+                    cudaEvent_t e0, e1;
+                    cudaEventCreate(&e0);
+                    cudaEventCreate(&e1);
+                    if (!add_conv(bw.conv3, t2, out_hw, shortcut, true, y) &&
+                        !add_conv(nb->conv1, y, out_hw, nullptr, true, t1n_trial)) {
+                        bool ok = true;
+                        for (int i = 0; i < 7 && ok; ++i) {
+                            if (i == 2) cudaEventRecord(e0, cap_stream);
+                            ok = conv_plan_launch(p.convs[first], cap_stream) == cudaSuccess &&
+                                 conv_plan_launch(p.convs[first + 1], cap_stream) == cudaSuccess;
+                        }
+                        cudaEventRecord(e1, cap_stream);
+                        if (cudaStreamSynchronize(cap_stream) == cudaSuccess && ok) cudaEventElapsedTime(&ms_plain, e0, e1);
+                    }
+                    p.convs.resize(first);
+                    if (fp8) p.links.resize(first);
+                    C3n1Desc td{};
+                    td.M = n * out_hw * out_hw;
+                    td.K3 = bw.conv3.Cin; td.N3 = out_c; td.N1 = nb->conv1.Cout;
+                    td.t2 = t2; td.w3 = bw.conv3.w; td.bias3 = bw.conv3.bias; td.residual = shortcut; td.y = y;
+                    td.w1n = nb->conv1.w; td.bias1n = nb->conv1.bias; td.t1n = t1n_trial;
+                    ConvPlan tf;
+                    if (!c3n1_plan_init(&tf, td, num_sms, err, sizeof(err))) {
+                        bool ok = true;
+                        for (int i = 0; i < 7 && ok; ++i) {
+                            if (i == 2) cudaEventRecord(e0, cap_stream);
+                            ok = conv_plan_launch(tf, cap_stream) == cudaSuccess;
+                        }
+                        cudaEventRecord(e1, cap_stream);
+                        if (cudaStreamSynchronize(cap_stream) == cudaSuccess && ok) cudaEventElapsedTime(&ms_fused, e0, e1);
+                    }
+                    cudaEventDestroy(e0);
+                    cudaEventDestroy(e1);
+                    arena.release(t1n_trial);
+                    c3n1_use = ms_fused <= 1.03f * ms_plain;  // the fused form unless the plain one is clearly faster
+                    tuned_c3n1[key] = c3n1_use ? 1 : 0;
+                    if (getenv("RNB_VERBOSE"))
+                        fprintf(stderr, "rnb plan: conv3 + next conv1 at M=%d (%d -> %d -> %d): fused %.1f us, plain %.1f us\n",
+                                std::get<0>(key), bw.conv3.Cin, out_c, nb->conv1.Cout, ms_fused * 200.f, ms_plain * 200.f);
+                }
+            }
+            if (c3n1_use) {
                 void* t1n = arena.acquire(bytes(nb->conv1.Cout, out_hw));
                 if (!t1n) return fail_alloc();
                 const int M = n * out_hw * out_hw;

@@ -184,6 +184,7 @@ struct Model {
     int fuse_level = 2;
     bool fuse_next = true;
     std::map<std::tuple<int, int, int, int, int, int, int, int>, int> tuned;  // layer shape (+ SM budget) -> force_bn code
+    std::map<std::tuple<int, int, int, int>, int> tuned_c3n1;  // (M, K3, N3, N1) -> 1 fused conv3 + conv1' launch, 0 two plain launches
 
     // Two lanes (round 2): a batch whose layers leave the persistent grids with short last waves (ResNet-152 at 128
     // images: 98 tiles on 74 CTA pairs in all of layer3) runs as TWO half batches on two streams — a second engine state
