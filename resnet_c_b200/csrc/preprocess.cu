@@ -109,6 +109,14 @@ const ResizePlan* plan_for(int H, int W, int resize, int crop, std::string* err)
     const auto key = std::make_tuple(dev, H, W, resize, crop);
     auto it = g_plans.find(key);
     if (it != g_plans.end()) return &it->second;
+    if (g_plans.size() >= 256) {  // a caller cycling through arbitrary image sizes: start over rather than grow for ever
+        cudaDeviceSynchronize();  // no launch may still read the tables
+        for (auto& kv : g_plans) {
+            ResizePlan& q = kv.second;
+            cudaFree(q.x_lo); cudaFree(q.x_n); cudaFree(q.x_k); cudaFree(q.y_lo); cudaFree(q.y_n); cudaFree(q.y_k);
+        }
+        g_plans.clear();
+    }
     // torchvision _compute_resized_output_size: short side -> resize, long side int(resize * long / short)
     const int shrt = W <= H ? W : H, lng = W <= H ? H : W;
     const int new_long = static_cast<int>(static_cast<double>(resize) * lng / shrt);
