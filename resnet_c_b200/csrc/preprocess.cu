@@ -102,13 +102,17 @@ cudaError_t upload(int** dst, const std::vector<int>& src) {
     return cudaMemcpy(*dst, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice);
 }
 
-const ResizePlan* plan_for(int H, int W, int resize, int crop, std::string* err) {
+// (the plan is returned BY VALUE: the cache may be flushed by another thread once the lock is released)
+bool plan_for(int H, int W, int resize, int crop, ResizePlan* out, std::string* err) {
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(g_plan_mutex);
     const auto key = std::make_tuple(dev, H, W, resize, crop);
     auto it = g_plans.find(key);
-    if (it != g_plans.end()) return &it->second;
+    if (it != g_plans.end()) {
+        *out = it->second;
+        return true;
+    }
     if (g_plans.size() >= 256) {  // a caller cycling through arbitrary image sizes: start over rather than grow for ever
         cudaDeviceSynchronize();  // no launch may still read the tables
         for (auto& kv : g_plans) {
@@ -123,7 +127,7 @@ const ResizePlan* plan_for(int H, int W, int resize, int crop, std::string* err)
     const int nh = W <= H ? new_long : resize, nw = W <= H ? resize : new_long;
     if (nh < crop || nw < crop) {
         *err = "rnb_resize_crop_u8: the resized image is smaller than the crop";
-        return nullptr;
+        return false;
     }
     const int top = round_half_even_div2(nh - crop), left = round_half_even_div2(nw - crop);
     const AxisCoeffs cx = axis_coeffs(W, nw, left, crop), cy = axis_coeffs(H, nh, top, crop);
@@ -139,9 +143,11 @@ const ResizePlan* plan_for(int H, int W, int resize, int crop, std::string* err)
         upload(&p.x_k, cx.kk) != cudaSuccess || upload(&p.y_lo, cy.lo) != cudaSuccess ||
         upload(&p.y_n, cy.n) != cudaSuccess || upload(&p.y_k, cy.kk) != cudaSuccess) {
         *err = std::string("rnb_resize_crop_u8: coefficient upload failed: ") + cudaGetErrorString(cudaGetLastError());
-        return nullptr;
+        return false;
     }
-    return &g_plans.emplace(key, p).first->second;
+    g_plans.emplace(key, p);
+    *out = p;
+    return true;
 }
 
 __device__ __forceinline__ uint8_t clip8(int acc) {
@@ -205,7 +211,8 @@ extern "C" int rnb_resize_crop_u8(const uint8_t* img_dev, int n_images, int H, i
     else
         cudaGetLastError();
     std::string err;
-    const ResizePlan* p = plan_for(H, W, resize, crop, &err);
+    ResizePlan plan{};
+    const ResizePlan* p = plan_for(H, W, resize, crop, &plan, &err) ? &plan : nullptr;
     int rc = RNB_OK;
     if (!p) {
         set_error(err);
