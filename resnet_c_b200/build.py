@@ -87,7 +87,7 @@ def build_librnb(force: bool = False) -> Path:
 def build_selftest(force: bool = False) -> Path:
     out = ROOT / "build" / "conv_selftest"
     out.parent.mkdir(exist_ok=True)
-    srcs = [ROOT / "tools" / "conv_selftest.cu", CSRC / "conv_plan.cu", CSRC / "tensormap.cu"]
+    srcs = [ROOT / "tools" / "conv_selftest.cu", CSRC / "conv_plan.cu", CSRC / "tensormap.cu", CSRC / "fp8.cu"]
     deps = srcs + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh"))
     if force or _stale(out, deps):
         _run([_nvcc(), *NVCC_FLAGS, "-Xcompiler", "-fopenmp", "-o", out, *srcs])
