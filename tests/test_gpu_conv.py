@@ -190,3 +190,16 @@ def test_sixteen_epilogue_warps_equal_eight(case, monkeypatch):
     assert torch.equal(outs["128"][0], outs["20128"][0])
     assert torch.equal(outs["128"][1], outs["20128"][1])
     assert float(outs["128"][0].abs().max()) > 0 and float(outs["128"][1].abs().max()) > 0
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+def test_standalone_conv_selftest_binary(dtype):
+    """build/conv_selftest (tools/conv_selftest.cu): the conv kernel against a host loop with no Python in between —
+    kept green so that a C++-only bring-up of the kernel stays possible."""
+    import subprocess
+    from conftest import ROOT
+    exe = ROOT / "build" / "conv_selftest"
+    if not exe.exists():
+        pytest.skip("build/conv_selftest not built")
+    r = subprocess.run([str(exe), dtype], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-500:])

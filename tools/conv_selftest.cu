@@ -90,6 +90,7 @@ int main(int argc, char** argv) {
 
     int failures = 0;
     for (const Shape& s : shapes) {
+        if (tf32 && s.bn == 3064) continue;  // the BF16 halo-resident kernel (its TF32 sibling is force code 4064)
         const int OH = (2 * s.pad + s.H - s.k) / s.stride + 1;
         const int OW = (2 * s.pad + s.W - s.k) / s.stride + 1;
         const size_t n_in = 1ull * s.B * s.H * s.W * s.Cin;
