@@ -137,3 +137,43 @@ def test_fp8_scales_are_fixed_after_calibration():
     assert torch.equal(la[2:3], l1)
     a.close()
     b.close()
+
+
+def test_fp8_host_and_uint8_paths_equal_the_device_path(golden_dir):
+    """Every entry path of an FP8 model runs the same calibrated plan: forward_host, the pipelined submit/wait path and
+    the uint8 input path (normalisation fused into the stem pre-pass) give bit-identical logits."""
+    from resnet_c_b200 import engine, weights
+    from oracle import preprocess
+    wdir = weights.cached_weights_dir("resnet50", 0, True)
+    m = engine.ResNet("resnet50", wdir, dtype="fp8", max_batch=4)
+    xu = weights.synthetic_images_u8(4, seed=2)
+    x = preprocess.normalize_u8(xu)
+    m.calibrate(x.cuda())
+    lg, t1 = m.forward(x.cuda())
+    lu, tu = m.forward_u8(xu.cuda())
+    hl, ht = m.forward_host(x.pin_memory())
+    sl, st = torch.empty(4, m.num_classes).pin_memory(), torch.empty(4, dtype=torch.int32).pin_memory()
+    m.submit_host(0, x.pin_memory(), sl, st)
+    m.wait_host(0)
+    torch.cuda.synchronize()
+    assert torch.equal(lg, lu) and torch.equal(t1, tu)
+    assert torch.equal(lg.cpu(), hl) and torch.equal(t1.cpu(), ht)
+    assert torch.equal(hl, sl) and torch.equal(ht, st)
+    m.close()
+
+
+def test_fp8_refusals():
+    """What the FP8 variant does not do fails loudly: packed weight files, warm-up before calibration, groups."""
+    from resnet_c_b200 import engine, weights
+    from resnet_c_b200._lib import RnbError
+    wdir = weights.cached_weights_dir("resnet18", 0, True)
+    m = engine.ResNet("resnet18", wdir, dtype="fp8", max_batch=2)
+    with pytest.raises(RnbError, match="packed"):
+        m.save_packed("/tmp/rnb_fp8_should_not_exist.bin")
+    import ctypes as C
+    from resnet_c_b200 import _lib
+    assert _lib.lib().rnb_model_warmup(m._h, 2, 0) != 0
+    assert b"calibrated" in _lib.lib().rnb_last_error()
+    m.close()
+    with pytest.raises(RnbError, match="single-model"):
+        engine.ResNetGroup("resnet18", wdir, [0, 0], dtype="fp8", max_batch_per_device=2)

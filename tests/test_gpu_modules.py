@@ -176,3 +176,24 @@ def test_cxx_conv2d_module_tensor_core_switch(oracle_lib, tmp_path):
         else:
             e = rel_err(got, want)
             assert 0 < e < tol, e
+
+
+def test_block_and_preprocess_argument_errors():
+    """Bad requests come back as error codes with a message (nothing aborts, nothing is launched)."""
+    import ctypes as C
+    from resnet_c_b200 import _lib, engine
+    from resnet_c_b200._lib import RnbError
+    g = torch.Generator().manual_seed(1)
+    with pytest.raises(RnbError, match="unsupported conv"):      # 3 input channels: not a tensor-core shape
+        engine.Block("conv", [dict(w=torch.randn(64, 3, 3, 3, generator=g).cuda(), bn=None, stride=1, pad=1)], "bf16")
+    with pytest.raises(RnbError, match="Bottleneck 3"):          # wrong conv count for the kind
+        engine.Block("bottleneck", [dict(w=torch.randn(64, 64, 1, 1, generator=g).cuda(), bn=None)], "bf16")
+    blk = engine.Block("conv", [dict(w=torch.randn(64, 64, 1, 1, generator=g).cuda(), bn=None)], "bf16")
+    with pytest.raises(RnbError):                                # NULL output
+        _lib.check(_lib.lib().rnb_block_forward(blk._h, C.c_void_p(1), 1, 8, 8, None, 1, None, None))
+    blk.close()
+    small = torch.zeros(1, 100, 300, 3, dtype=torch.uint8).cuda()
+    with pytest.raises(RnbError, match="bad argument"):
+        engine.resize_crop_u8(small, resize=200, crop=224)       # crop larger than the resize target
+    out = engine.resize_crop_u8(small)                           # 100 x 300 -> 256 x 768 -> centre 224 x 224: fine
+    assert out.shape == (1, 224, 224, 3) and int(out.sum()) == 0
