@@ -31,7 +31,11 @@
 
 namespace rnb {
 
-template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_, int OSZ_ = ESZ_>
+// RESB_KB_ > 0: RESIDENT weights — the layer's whole weight matrix (RESB_KB_ K blocks, one N tile) is loaded into
+// shared memory ONCE per CTA and only the A operand streams. For the 128-channel 3x3 convs of layer2 (18 K blocks,
+// 144 KB per CTA) the per-tile weight reloads were a third of an L2 -> SM traffic that sits at the fabric limit
+// (profiles/l2conv3x3_r1.md: 231 of 694 MB); paid for with a 3-deep A ring and ONE staging buffer.
+template <int BN_, int ESZ_, int NSTAGE_, int NCBUF_, int OSZ_ = ESZ_, int RESB_KB_ = 0>
 struct Conv2Cfg {
     static constexpr int BM = 256;                    // pixels per CTA pair
     static constexpr int BM_CTA = 128;                // pixels per CTA
@@ -44,7 +48,9 @@ struct Conv2Cfg {
     static constexpr int NCBUF = NCBUF_;
     static constexpr int A_BYTES = BM_CTA * 128;
     static constexpr int B_BYTES = (BN_ / 2) * 128;    // this CTA's half of the weight tile
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int RESB_KB = RESB_KB_;
+    static constexpr int RES_BYTES = RESB_KB_ * B_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + (RESB_KB_ > 0 ? 0 : B_BYTES);
     static constexpr int BOX_COLS = 128 / OSZ_;
     static constexpr int SUB_BOXES = OSZ_ == 1 ? 1 : 2;  // 128-byte boxes per epilogue sub-tile (FP8: one box = 128 columns)
     static constexpr int EPI_N = SUB_BOXES * BOX_COLS;   // columns per epilogue sub-tile
@@ -52,12 +58,13 @@ struct Conv2Cfg {
     static constexpr int BOX_BYTES = BM_CTA * 128;
     static constexpr int CBUF_BYTES = SUB_BOXES * BOX_BYTES;   // 32 KB (16 KB on the FP8 path)
     static constexpr int TMEM_COLS = 2 * BN_;
-    static constexpr int NBAR = 2 * NSTAGE_ + 4 + 3 * NCBUF_;
+    static constexpr int NBAR = 2 * NSTAGE_ + 4 + 3 * NCBUF_ + 1;   // + b_full (resident weights)
     static constexpr int SMEM_BYTES =
-        1024 + NSTAGE_ * STAGE_BYTES + NCBUF_ * CBUF_BYTES + NBAR * 8 + 16;
+        1024 + RES_BYTES + NSTAGE_ * STAGE_BYTES + NCBUF_ * CBUF_BYTES + NBAR * 8 + 16;
     static constexpr int EPI_WARPS = 8;
     static constexpr int THREADS = 128 + EPI_WARPS * 32;
-    static_assert(NCBUF_ >= 2, "need at least two staging buffers");
+    static_assert(NCBUF_ >= 1, "need a staging buffer");
+    static_assert(RES_BYTES % 1024 == 0, "the stage ring behind the resident weights must stay 1024-byte aligned");
     static_assert(BN_ % EPI_N == 0, "tile N must be a multiple of the epilogue sub-tile");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
 };
@@ -182,8 +189,9 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
-    uint8_t* smem_stage = smem;
-    uint8_t* smem_c = smem + NSTAGE * Cfg::STAGE_BYTES;
+    uint8_t* smem_res = smem;                       // resident weights (RESB_KB K blocks of this CTA's N half), or empty
+    uint8_t* smem_stage = smem + Cfg::RES_BYTES;
+    uint8_t* smem_c = smem_stage + NSTAGE * Cfg::STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + NCBUF * Cfg::CBUF_BYTES);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + NSTAGE;
@@ -192,6 +200,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint64_t* res_full = bars + 2 * NSTAGE + 4;
     uint64_t* c_full = res_full + NCBUF;
     uint64_t* c_free = c_full + NCBUF;
+    uint64_t* b_full = c_free + NCBUF;              // leader: the resident weights of BOTH CTAs have landed
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
 
     const int warp = threadIdx.x >> 5;
@@ -228,6 +237,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_init(&c_full[i], Cfg::EPI_WARPS);
             mbar_init(&c_free[i], 1);
         }
+        mbar_init(b_full, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -275,6 +285,16 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     if (warp == 0) {
         // ===================================================== TMA producer (both CTAs)
+        if (Cfg::RESB_KB > 0) {
+            // resident weights: every K block of this CTA's half of the (single) N tile, once
+            if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(b_full, 2 * Cfg::RES_BYTES);
+                for (int kb = 0; kb < Cfg::RESB_KB; ++kb)
+                    tma_load_2d_2sm(smem_res + kb * Cfg::B_BYTES, &tmB, b_full, kb * Cfg::BK,
+                                    static_cast<int>(rank) * (BN / 2));
+            }
+            __syncwarp();
+        }
         int stage = 0;
         uint32_t phase = 0;
         const int ohw = g.OH * g.OW;
@@ -290,7 +310,8 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int h0 = g.lower + p * g.stride;
             const int nrow0 = half < 0 ? n_blk * BN + static_cast<int>(rank) * (BN / 2)
                                        : n_blk * BN + half * (BN / 2) + static_cast<int>(rank) * (BN / 4);
-            const uint32_t tx_bytes = 2 * (Cfg::A_BYTES + (half < 0 ? Cfg::B_BYTES : Cfg::B_BYTES / 2));
+            const uint32_t tx_bytes =
+                Cfg::RESB_KB > 0 ? 2 * Cfg::A_BYTES : 2 * (Cfg::A_BYTES + (half < 0 ? Cfg::B_BYTES : Cfg::B_BYTES / 2));
             const CUtensorMap* tmBu = half < 0 ? &tmB : &tmBh;
             int tap_r = 0, tap_s = 0, cblk = 0;
             for (int kb = 0; kb < g.num_kblocks; ++kb) {
@@ -301,7 +322,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
                     tma_load_im2col_4d_2sm(sa, &tmA, &full_bar[stage], cblk * Cfg::BK, w0, h0, img,
                                            static_cast<uint16_t>(tap_s), static_cast<uint16_t>(tap_r));
-                    tma_load_2d_2sm(sb, tmBu, &full_bar[stage], kb * Cfg::BK, nrow0);
+                    if (Cfg::RESB_KB == 0) tma_load_2d_2sm(sb, tmBu, &full_bar[stage], kb * Cfg::BK, nrow0);
                 }
                 __syncwarp();
                 if (++cblk == g.kblocks_per_tap) {
@@ -326,6 +347,11 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_stage), 0, 1024, UMMA_LAYOUT_SW128);
             const uint64_t b_desc0 =
                 umma_smem_desc(smem_u32(smem_stage) + Cfg::A_BYTES, 0, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t b_res0 = umma_smem_desc(smem_u32(smem_res), 0, 1024, UMMA_LAYOUT_SW128);
+            if (Cfg::RESB_KB > 0) {
+                mbar_wait(b_full, 0);
+                tc_fence_after();
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int it = 0; it < my_tiles; ++it) {
@@ -343,7 +369,9 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t ad = a_desc0 + soff + static_cast<uint64_t>(k * 2);
-                            const uint64_t bd = b_desc0 + soff + static_cast<uint64_t>(k * 2);
+                            const uint64_t bd = Cfg::RESB_KB > 0
+                                                    ? b_res0 + static_cast<uint64_t>((kb * Cfg::B_BYTES) >> 4) + static_cast<uint64_t>(k * 2)
+                                                    : b_desc0 + soff + static_cast<uint64_t>(k * 2);
                             if (Cfg::ESZ == 2)
                                 mma_f16_ss_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
                             else if (Cfg::ESZ == 4)

@@ -32,6 +32,13 @@ using Cfg2Bf16N128F8 = Conv2Cfg<128, 2, 5, 3, 1>;
 static_assert(CfgBf16N128F8::SMEM_BYTES <= 232448 && Cfg2Bf16N256F8::SMEM_BYTES <= 232448 &&
                   Cfg2Bf16N128F8::SMEM_BYTES <= 232448,
               "smem budget");
+// deepest rings (bf16): eight / six stages in flight and ONE staging buffer — force codes 12128 / 12256
+using Cfg2Bf16N128DD = Conv2Cfg<128, 2, 8, 1>;
+using Cfg2Bf16N256DD = Conv2Cfg<256, 2, 6, 1>;
+static_assert(Cfg2Bf16N128DD::SMEM_BYTES <= 232448 && Cfg2Bf16N256DD::SMEM_BYTES <= 232448, "smem budget");
+// resident weights (3x3, 128 -> 128: 18 K blocks = 144 KB per CTA), 3-deep A ring, one staging buffer: force_bn code 31128
+using Cfg2Bf16N128R = Conv2Cfg<128, 2, 3, 1, 2, 18>;
+static_assert(Cfg2Bf16N128R::SMEM_BYTES <= 232448, "smem budget");
 // 16 epilogue warps (one 32-column chunk per warp and tile): force_bn code 20128
 using CfgBf16N128W16 = ConvCfg<128, 2, 4, 3, 2, 16>;
 using CfgFp8N128W16 = ConvCfg<128, 1, 4, 4, 1, 16>;
@@ -89,6 +96,9 @@ cudaError_t conv_kernels_init() {
     if ((e = set_smem<CfgBf16N128F8>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Bf16N256F8>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Bf16N128F8>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Bf16N128R>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Bf16N128DD>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Bf16N256DD>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgBf16N128W16>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgFp8N128W16>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgFp8N128C>()) != cudaSuccess) return e;
@@ -353,6 +363,14 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
         return halo2_plan_init(plan, d, num_sms, err, errlen);
     // +10000: "deep" variant of a tile family — one or two more shared-memory stages in flight paid
     // for with one staging buffer less (for layers whose K loop, not whose epilogue, is the bottleneck)
+    // 31128: CTA-pair BN = 128 tiles with the whole weight matrix resident in shared memory (one N tile, 18 K blocks)
+    bool resb = false;
+    if (force_bn == 31128) {
+        if (d.act != ActType::BF16 || d.out_f32 || d.out_fp8 || d.Cout != 128 || d.ksize * d.ksize * d.Cin != 18 * 64)
+            return fail(err, errlen, "conv_plan: the resident-weight kernel is the bf16 3x3 128 -> 128 one", -9);
+        resb = true;
+        force_bn = 1128;
+    }
     // +20000: single-CTA BN = 128 tiles with SIXTEEN epilogue warps (one 32-column chunk per warp and tile)
     if (force_bn == 20128) {
         if (d.act == ActType::TF32 || d.out_f32 || d.out_fp8 || d.Cout % 128 != 0)
@@ -360,7 +378,14 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
         plan->w16 = 1;
         force_bn = 128;
     }
-    const int deep = force_bn >= 10000 ? 1 : 0;
+    // +10000 / +11000: deep (one / two more stages, two staging buffers) / deepest (ring as deep as shared memory allows,
+    // one staging buffer; CTA pairs only) variants of a tile family
+    int deep = force_bn >= 10000 ? 1 : 0;
+    if (force_bn == 12128 || force_bn == 12256) {
+        if (d.act != ActType::BF16) return fail(err, errlen, "conv_plan: the deepest-ring variants are bf16 kernels", -9);
+        deep = 2;
+        force_bn -= 1000;
+    }
     if (deep) force_bn -= 10000;
     plan->deep = deep;
     const int esz = static_cast<int>(d.act);
@@ -421,6 +446,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     plan->esz = esz;
     plan->osz = osz;
     plan->ctas = ctas;
+    plan->resb = resb ? 1 : 0;
     const int tiles = g.m_tiles * g.n_tiles;
     g.split_from = tiles;
     g.chan_scale = d.chan_scale;
@@ -436,7 +462,7 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
         // of 2 tile times (layer4 at 256 images, layer3 of ResNet-152 at 128). Bit-identical. RNB_NO_SPLIT=1: off.
         const bool no_split = getenv("RNB_NO_SPLIT") && atoi(getenv("RNB_NO_SPLIT")) != 0;
         const int nsub = osz == 1 ? bn / 128 : bn / (2 * (128 / esz));  // Conv2Cfg::NSUB
-        if (!no_split && nsub % 2 == 0) {
+        if (!no_split && nsub % 2 == 0 && !resb) {
             const int max_pairs = num_sms / 2;
             const int rem = tiles % pairs;
             if (tiles > pairs && rem > 0 && 2 * rem <= pairs) {
@@ -608,10 +634,13 @@ cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
         return launch<CfgBf16N128F8>(p, stream);
     }
     if (p.w16 && p.esz == 2) return launch<CfgBf16N128W16>(p, stream);
+    if (p.deep == 2 && p.esz == 2 && p.ctas == 2)
+        return p.bn == 256 ? launch2<Cfg2Bf16N256DD>(p, stream) : launch2<Cfg2Bf16N128DD>(p, stream);
     if (p.deep && p.esz == 2) {
         if (p.ctas == 2) return p.bn == 256 ? launch2<Cfg2Bf16N256D>(p, stream) : launch2<Cfg2Bf16N128D>(p, stream);
         if (p.bn == 128) return launch<CfgBf16N128D>(p, stream);
     }
+    if (p.resb) return launch2<Cfg2Bf16N128R>(p, stream);
     if (p.ctas == 2) {
         if (p.esz == 2) return p.bn == 256 ? launch2<Cfg2Bf16N256>(p, stream) : launch2<Cfg2Bf16N128>(p, stream);
         return p.bn == 256 ? launch2<Cfg2Tf32N256>(p, stream) : launch2<Cfg2Tf32N128>(p, stream);

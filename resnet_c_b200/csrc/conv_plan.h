@@ -88,6 +88,7 @@ struct ConvPlan {
     const float* bias;
     int bn;       // tile N
     int ctas;     // 1 = single-CTA 128-pixel tiles, 2 = CTA-pair 256-pixel tiles (cta_group::2)
+    int resb;     // 1 = CTA-pair BN = 128 kernel with RESIDENT weights (force_bn code 31128: 3x3, 128 -> 128, bf16)
     int w16;      // 1 = single-CTA BN = 128 kernel with 16 epilogue warps (force_bn code 20128; bf16 / fp8)
     int deep;     // 1 = deeper smem pipeline / fewer staging buffers variant of the tile family (bf16)
     int f32out;   // 1 = FP32-output variant of the single-CTA kernel (FC layer)

@@ -712,21 +712,22 @@ ChunkPlan* Model::plan_for(int n) {
             int best_force = hit != tuned.end() ? hit->second : -1;
             if (best_force < 0) {
                 // (20128, the 16-epilogue-warp variant, was a candidate for one session: never selected on any layer of any config)
-                const int cands[9] = {64, 128, 1128, 1256, 3064, 4064, 10128, 11128, 11256};
+                const int cands[12] = {64, 128, 1128, 1256, 3064, 4064, 10128, 11128, 11256, 12128, 12256, 31128};
                 float best_ms = 1e30f;
                 cudaEvent_t e0, e1;
                 cudaEventCreate(&e0);
                 cudaEventCreate(&e1);
                 for (int force : cands) {
-                    if (fp8 && force != 128 && force != 1128 && force != 1256 && force != 20128) continue;
+                    if (fp8 && force != 128 && force != 1128 && force != 1256) continue;
                     if (force == 20128 && (cur_esz == 4 || cw.Cout % 128 != 0)) continue;
+                    if (force == 31128 && (cur_esz != 2 || ho || cw.Cout != 128 || cw.k != 3 || cw.Cin != 128)) continue;
                     if (force == 3064 && !conv_plan_halo_ok(d)) continue;
                     if (force == 4064 && !conv_plan_halo2_ok(d)) continue;
                     // deep-pipeline variants trade a staging buffer for pipeline stages: only for layers
                     // whose epilogue is light (no residual prefetch) and whose K loop is long; timing a
                     // residual layer alone flatters them (measured in the full network: slower)
                     if (force >= 10000 && (cur_esz != 2 || res || cw.k * cw.k * cw.Cin < 256)) continue;
-                    if (force != 20128 && cw.Cout % (force % 1000) != 0) continue;
+                    if (cw.Cout % (force % 1000) != 0) continue;
                     if (force == 64 && cw.Cout % 128 == 0 && 1LL * n * in_hw * in_hw > 4096) continue;
                     ConvPlan trial;
                     if (conv_plan_init(&trial, d, sm_budget, force, err, sizeof(err))) continue;
@@ -739,6 +740,9 @@ ChunkPlan* Model::plan_for(int n) {
                     if (cudaStreamSynchronize(cap_stream) != cudaSuccess || !ok) continue;
                     float ms = 0.f;
                     cudaEventElapsedTime(&ms, e0, e1);
+                    if (getenv("RNB_VERBOSE") && atoi(getenv("RNB_VERBOSE")) >= 2)
+                        fprintf(stderr, "rnb autotune: n=%d %dx%d %d->%d k%d s%d res=%d : tile code %d %.1f us\n", n, in_hw,
+                                in_hw, cw.Cin, cw.Cout, cw.k, cw.stride, res ? 1 : 0, force, ms * 200.f);
                     if (ms < best_ms) {
                         best_ms = ms;
                         best_force = force;
@@ -760,7 +764,7 @@ ChunkPlan* Model::plan_for(int n) {
         if (getenv("RNB_VERBOSE"))
             fprintf(stderr, "rnb plan: conv#%zu n=%d %dx%d %d->%d k%d s%d res=%d : %s tile %dx%d grid %d\n",
                     p.convs.size(), n, in_hw, in_hw, cw.Cin, cw.Cout, cw.k, cw.stride, res ? 1 : 0,
-                    cp.halo2 ? "halo-pair" : cp.halo ? "halo" : (cp.ctas == 2 ? (cp.deep ? "pair-deep" : (cp.g.split_from < cp.g.m_tiles * cp.g.n_tiles ? "pair-split" : "pair")) : (cp.deep ? "single-deep" : (cp.w16 ? "single-16w" : "single"))),
+                    cp.halo2 ? "halo-pair" : cp.halo ? "halo" : (cp.ctas == 2 ?  (cp.deep == 2 ? "pair-deepest" : cp.deep ? "pair-deep" : (cp.resb ? "pair-resident-B" : (cp.g.split_from < cp.g.m_tiles * cp.g.n_tiles ? "pair-split" : "pair"))) : (cp.deep ? "single-deep" : (cp.w16 ? "single-16w" : "single"))),
                     cp.ctas == 2 ? 256 : 128, cp.bn, cp.grid);
         if (fp8 && fp8_premultiply(&cp, d.in_scale, d.res_scale, d.out_scale, cap_stream) != cudaSuccess) {
             set_error("FP8 epilogue vector setup failed");

@@ -203,3 +203,53 @@ def test_standalone_conv_selftest_binary(dtype):
         pytest.skip("build/conv_selftest not built")
     r = subprocess.run([str(exe), dtype], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-500:])
+
+
+@pytest.mark.parametrize("case", [
+    # (H, stride, residual, B): 3x3, 128 -> 128 (layer2 conv2 of the Bottleneck nets)
+    (28, 1, False, 40),    # 123 pair tiles on 74 pairs
+    (56, 2, False, 9),     # stride 2 (layer2.0), ragged last tile
+    (28, 1, True, 3),      # with a residual through the single staging buffer
+])
+def test_resident_weight_kernel_equals_streaming_kernel(case, monkeypatch):
+    """Conv2Cfg<128, 2, 3, 1, 2, 18> (force code 31128): the weight matrix of a 128-channel 3x3 conv stays in shared
+    memory for the whole launch, only the im2col operand streams. Same K order, same epilogue: bit-identical to the
+    streaming CTA-pair kernel (1128)."""
+    from resnet_c_b200 import engine
+    H, stride, residual, B = case
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(B, 128, H, H, generator=g).cuda()
+    w = (torch.randn(128, 128, 3, 3, generator=g) * 0.04).cuda()
+    bn = tuple(t.cuda() for t in (torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1,
+                                  torch.randn(128, generator=g) * 0.1, torch.rand(128, generator=g) + 0.5))
+    OH = (2 + H - 3) // stride + 1
+    res = torch.randn(B, 128, OH, OH, generator=g).cuda() if residual else None
+    outs = {}
+    for tile in ("1128", "31128"):
+        monkeypatch.setenv("RNB_FORCE_TILE", tile)
+        outs[tile] = engine.conv_bn_act_forward(x, w, bn, res, True, stride, 1, "bf16")
+    torch.cuda.synchronize()
+    assert torch.equal(outs["1128"], outs["31128"])
+    assert float(outs["1128"].abs().max()) > 0
+
+
+@pytest.mark.parametrize("case", [
+    # (C, H, B, tile codes): every tile family a 3x3 layer admits computes the same bits
+    (128, 28, 40, ("128", "1128", "11128", "12128", "31128")),
+    (256, 14, 64, ("128", "1128", "1256", "11256", "12256")),
+])
+def test_tile_families_are_bit_identical(case, monkeypatch):
+    """Single-CTA / CTA-pair tiles, deep (more ring stages, two staging buffers), deepest (12128 / 12256: eight / six
+    stages, ONE staging buffer) and resident-weight variants differ in scheduling only."""
+    from resnet_c_b200 import engine
+    C, H, B, tiles = case
+    g = torch.Generator().manual_seed(43)
+    x = torch.randn(B, C, H, H, generator=g).cuda()
+    w = (torch.randn(C, C, 3, 3, generator=g) * 0.03).cuda()
+    outs = []
+    for tile in tiles:
+        monkeypatch.setenv("RNB_FORCE_TILE", tile)
+        outs.append(engine.conv_bn_act_forward(x, w, None, None, True, 1, 1, "bf16"))
+    torch.cuda.synchronize()
+    for t, o in zip(tiles[1:], outs[1:]):
+        assert torch.equal(outs[0], o), f"tile code {t} differs from {tiles[0]}"
