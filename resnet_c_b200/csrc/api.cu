@@ -78,7 +78,13 @@ static int device_of(const void* p) {
 // A sub-128-KiB im2col convolution on the tcgen05 path against the FP32 CUDA-core kernel, with the descriptor
 // work-around of tensormap.cu as the driver version suggests first and the other way round second: keeps whichever
 // reproduces the FP32 result, fails loudly if neither does (a wrong guess would silently corrupt layer4 / small batches).
+static thread_local bool g_in_selftest = false;  // the self-test runs the default tile choice whatever RNB_FORCE_TILE says
+
 static int im2col_selftest() {
+    struct Flag {
+        Flag() { g_in_selftest = true; }
+        ~Flag() { g_in_selftest = false; }
+    } in_selftest;
     const char* skip = getenv("RNB_SKIP_SELFTEST");
     if (skip && atoi(skip) != 0) return RNB_OK;
     const int B = 1, Cin = 64, H = 8, W = 8, Cout = 64, k = 3;
@@ -465,7 +471,7 @@ int rnb_conv_bn_act_forward(const float* x_dev, const float* w_dev, const float*
     ConvPlan plan;
     char err[256];
     // RNB_FORCE_TILE (tests): a conv_plan_init force_bn code, e.g. 1256 = CTA-pair tiles with BN = 256
-    const char* ft = getenv("RNB_FORCE_TILE");
+    const char* ft = g_in_selftest ? nullptr : getenv("RNB_FORCE_TILE");
     if (conv_plan_init(&plan, d, num_sms(), ft ? atoi(ft) : 0, err, sizeof(err))) {
         set_error(err);
         return RNB_ERR_CUDA;
