@@ -33,6 +33,9 @@ static_assert(CfgBf16N128F8::SMEM_BYTES <= 232448 && Cfg2Bf16N256F8::SMEM_BYTES 
                   Cfg2Bf16N128F8::SMEM_BYTES <= 232448,
               "smem budget");
 // deepest rings (bf16): eight / six stages in flight and ONE staging buffer — force codes 12128 / 12256
+using Cfg2Fp8N128DD = Conv2Cfg<128, 1, 8, 1>;
+using Cfg2Fp8N256DD = Conv2Cfg<256, 1, 6, 1>;
+static_assert(Cfg2Fp8N128DD::SMEM_BYTES <= 232448 && Cfg2Fp8N256DD::SMEM_BYTES <= 232448, "smem budget");
 using Cfg2Bf16N128DD = Conv2Cfg<128, 2, 8, 1>;
 using Cfg2Bf16N256DD = Conv2Cfg<256, 2, 6, 1>;
 static_assert(Cfg2Bf16N128DD::SMEM_BYTES <= 232448 && Cfg2Bf16N256DD::SMEM_BYTES <= 232448, "smem budget");
@@ -98,6 +101,8 @@ cudaError_t conv_kernels_init() {
     if ((e = set_smem2<Cfg2Bf16N128F8>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Bf16N128R>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Bf16N128DD>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Fp8N128DD>()) != cudaSuccess) return e;
+    if ((e = set_smem2<Cfg2Fp8N256DD>()) != cudaSuccess) return e;
     if ((e = set_smem2<Cfg2Bf16N256DD>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgBf16N128W16>()) != cudaSuccess) return e;
     if ((e = set_smem<CfgFp8N128W16>()) != cudaSuccess) return e;
@@ -349,7 +354,8 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     if (d.act == ActType::FP8 || d.out_fp8) {
         if (d.out_f32 || !d.chan_scale || !d.fp8_vecs || d.Cout % 128 != 0 || !(d.out_scale > 0.f))
             return fail(err, errlen, "conv_plan: FP8 needs channel scales + scratch, Cout % 128 == 0 and a positive output scale", -9);
-        if (force_bn == 64 || force_bn == 3064 || force_bn == 4064 || (force_bn >= 10000 && force_bn < 20000))
+        if (force_bn == 64 || force_bn == 3064 || force_bn == 4064 ||
+            (force_bn >= 10000 && force_bn < 20000 && !(d.act == ActType::FP8 && (force_bn == 12128 || force_bn == 12256))))
             return fail(err, errlen, "conv_plan: tile family not available in FP8", -9);
     }
     if (d.out_f32) {
@@ -382,7 +388,8 @@ int conv_plan_init(ConvPlan* plan, const ConvDesc& d, int num_sms, int force_bn,
     // one staging buffer; CTA pairs only) variants of a tile family
     int deep = force_bn >= 10000 ? 1 : 0;
     if (force_bn == 12128 || force_bn == 12256) {
-        if (d.act != ActType::BF16) return fail(err, errlen, "conv_plan: the deepest-ring variants are bf16 kernels", -9);
+        if (d.act == ActType::TF32 || d.out_fp8)
+            return fail(err, errlen, "conv_plan: the deepest-ring variants are bf16 / fp8 kernels", -9);
         deep = 2;
         force_bn -= 1000;
     }
@@ -621,6 +628,7 @@ cudaError_t conv_plan_launch(const ConvPlan& p, cudaStream_t stream) {
                           p.tmA, p.tmB, p.tmOut, p.bias, p.hg);
     }
     if (p.esz == 1) {
+        if (p.ctas == 2 && p.deep == 2) return p.bn == 256 ? launch2<Cfg2Fp8N256DD>(p, stream) : launch2<Cfg2Fp8N128DD>(p, stream);
         if (p.ctas == 2) return p.bn == 256 ? launch2<Cfg2Fp8N256>(p, stream) : launch2<Cfg2Fp8N128>(p, stream);
         if (p.w16) return launch<CfgFp8N128W16>(p, stream);
         static const int cfg = getenv("RNB_FP8_CFG") ? atoi(getenv("RNB_FP8_CFG")) : 0;

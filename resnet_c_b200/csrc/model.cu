@@ -718,7 +718,8 @@ ChunkPlan* Model::plan_for(int n) {
                 cudaEventCreate(&e0);
                 cudaEventCreate(&e1);
                 for (int force : cands) {
-                    if (fp8 && force != 128 && force != 1128 && force != 1256) continue;
+                    if (fp8 && force != 128 && force != 1128 && force != 1256 && !((force == 12128 || force == 12256) && !ho))
+                        continue;
                     if (force == 20128 && (cur_esz == 4 || cw.Cout % 128 != 0)) continue;
                     if (force == 31128 && (cur_esz != 2 || ho || cw.Cout != 128 || cw.k != 3 || cw.Cin != 128)) continue;
                     if (force == 3064 && !conv_plan_halo_ok(d)) continue;
@@ -726,7 +727,9 @@ ChunkPlan* Model::plan_for(int n) {
                     // deep-pipeline variants trade a staging buffer for pipeline stages: only for layers
                     // whose epilogue is light (no residual prefetch) and whose K loop is long; timing a
                     // residual layer alone flatters them (measured in the full network: slower)
-                    if (force >= 10000 && (cur_esz != 2 || res || cw.k * cw.k * cw.Cin < 256)) continue;
+                    if (force >= 10000 && ((cur_esz != 2 && !(cur_esz == 1 && (force == 12128 || force == 12256))) || res ||
+                                           cw.k * cw.k * cw.Cin < 256))
+                        continue;
                     if (cw.Cout % (force % 1000) != 0) continue;
                     if (force == 64 && cw.Cout % 128 == 0 && 1LL * n * in_hw * in_hw > 4096) continue;
                     ConvPlan trial;
