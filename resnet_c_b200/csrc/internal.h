@@ -129,11 +129,17 @@ cudaError_t stem_tc_init();
 cudaError_t launch_stem_tc_pack_weights(const float* w, const float* bn_w, const float* bn_b,
                                         const float* bn_m, const float* bn_v, void* wk, float* bias,
                                         cudaStream_t s);
-// Two launches: NCHW fp32 -> padded NHWC4 bf16 (scratch `xp`), then conv7x7/2 + BN + ReLU + maxpool.
+// conv7x7/2 + BN + ReLU + maxpool from NCHW fp32. Default: ONE launch (part 1; part 0 is a no-op) whose loader warps
+// build the padded NHWC4 bf16 rows in shared memory; RNB_STEM_FUSED=0: part 0 = layout pre-pass into the scratch
+// `xp`, part 1 = the same kernel fed from `xp` by bulk copies.
+bool stem_fused_enabled();
 cudaError_t launch_stem_tc(const float* x, void* xp, const void* wk, const float* bias, void* out, int B,
                            cudaStream_t s);
 cudaError_t launch_stem_tc_part(int part, const float* x, void* xp, const void* wk, const float* bias,
                                 void* out, int B, cudaStream_t s);
+// the kernel fed from an already packed tensor (uint8 input: launch_stem_tc_pack_u8 first)
+cudaError_t launch_stem_tc_from_packed(const void* xp, const void* wk, const float* bias, void* out, int B,
+                                       cudaStream_t s);
 
 // Decoded-image input (uint8 HWC [B][224][224][3]) with the /255 + mean/std normalisation of
 // convert_imgs_to_bin.py:18 fused in: straight into the packed stem input (BF16 path) ...

@@ -475,7 +475,7 @@ void Model::for_each_weight(F&& f) {
 namespace {
 struct PackedHeader {
     char magic[8];        // "RNBWGT01"
-    uint32_t version;     // 1
+    uint32_t version;     // 2 (1: the first stem weight layout [kh][j][oc][e], window starting at tap 0)
     uint32_t esz;         // 2 = BF16 operands, 4 = TF32
     char arch[16];
     uint32_t classes, classes_pad;
@@ -529,7 +529,7 @@ int Model::save_packed(const std::string& path) {
     if (ce != cudaSuccess) return fail_cuda(ce, "save_packed: cudaMemcpy");
     PackedHeader h{};
     memcpy(h.magic, "RNBWGT01", 8);
-    h.version = 1;
+    h.version = 2;
     h.esz = static_cast<uint32_t>(esz);
     snprintf(h.arch, sizeof(h.arch), "%s", arch.c_str());
     h.classes = classes; h.classes_pad = classes_pad;
@@ -565,7 +565,7 @@ int Model::load_packed(const std::string& path, int max_batch_, int chunk_) {
     }
     f.seekg(0);
     f.read(reinterpret_cast<char*>(&h), sizeof(h));
-    if (memcmp(h.magic, "RNBWGT01", 8) != 0 || h.version != 1 || (h.esz != 2 && h.esz != 4)) {
+    if (memcmp(h.magic, "RNBWGT01", 8) != 0 || h.version != 2 || (h.esz != 2 && h.esz != 4)) {
         set_error("packed weight file " + path + ": bad magic / version");
         return RNB_ERR_IO;
     }
@@ -1060,11 +1060,13 @@ int Model::enqueue_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, floa
     }
     if (stem_tc) {
         void* pool = p.pool_raw ? p.pool_raw : p.pool_out;
-        if (x_u8)
+        if (x_u8) {
             RNB_CUDA(launch_stem_tc_pack_u8(x_u8, p.stem_out, n, norm_mean, norm_std, s));
-        else
+            RNB_CUDA(launch_stem_tc_from_packed(p.stem_out, stem_wk, stem_bias, pool, n, s));
+        } else {
             RNB_CUDA(launch_stem_any_part(stem_esz(), 0, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
-        RNB_CUDA(launch_stem_any_part(stem_esz(), 1, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
+            RNB_CUDA(launch_stem_any_part(stem_esz(), 1, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
+        }
         if (p.pool_raw) {
             const int p_hw = (2 + s_hw - 3) / 2 + 1;
             RNB_CUDA(launch_quantize_pad_bf16(p.pool_raw, p.pool_out, 1LL * n * p_hw * p_hw, 64, cpad(64),
@@ -1628,10 +1630,14 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
     const double img_px = 1.0 * image * image;
     if (stem_tc) {
         // launch 0 = layout pre-pass (fp32 NCHW -> padded NHWC4 bf16), launch 1 = fused conv+BN+ReLU+pool
+        // (BF16 stem, fused form: launch 0 does not exist — its entry times an empty interval — and launch 1 reads the
+        // FP32 image itself)
+        const bool fused = stem_esz() == 2 && stem_fused_enabled();
         const double packed = static_cast<double>(stem_any_input_bytes(stem_esz(), 1));
-        put(0, 0.0, n * (3.0 * img_px * 4 + packed));
+        put(0, 0.0, fused ? 0.0 : n * (3.0 * img_px * 4 + packed));
         put(1, 2.0 * n * 64 * 147 * s_hw * s_hw,
-            n * (packed + 64.0 * p_hw * p_hw * stem_esz() + (p.pool_raw ? (64.0 * 2 + 128.0) * p_hw * p_hw : 0.0)) + 28672.0);
+            n * ((fused ? 3.0 * img_px * 4 : packed) + 64.0 * p_hw * p_hw * stem_esz() +
+                 (p.pool_raw ? (64.0 * 2 + 128.0) * p_hw * p_hw : 0.0)) + 28672.0);
     } else {
         put(0, 2.0 * n * 64 * 147 * s_hw * s_hw, n * (3.0 * img_px * 4 + 64.0 * s_hw * s_hw * esz) + 64 * 148 * 4.0);
         put(1, 0.0, n * 64.0 * esz * (1.0 * s_hw * s_hw + 1.0 * p_hw * p_hw));

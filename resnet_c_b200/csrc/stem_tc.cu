@@ -4,21 +4,30 @@
 // chained at /root/reference/cuda/inference/main.cu:176-192 (on CUDA cores the stem is
 // FP32-compute-bound, 60 GFLOP per 256-batch; on tensor cores it is a ~0.1 ms memory pass).
 //
-// Trick: no im2col is ever built. A pre-pass (stem_pack_kernel) rewrites the FP32 NCHW image as
-// zero-padded NHWC4 BF16 ("RGB0" pixels of 8 bytes, 232 pixels per row). Two adjacent pixels form a
-// 16-byte "super-pixel"; because the conv stride is 2, the window of output column ow starts at
-// super-pixel ow and spans 4 of them (7 taps + 1 zero-weight tap). So for a fixed filter row kh the
-// A operand A[ow][j*8+e] = row[(ow+j)*8 + e] is a Hankel matrix that a NO-SWIZZLE K-major UMMA
-// descriptor reads directly from the contiguous row in shared memory: 16 bytes between consecutive M
-// rows (SBO = 128 per 8 rows) and 16 bytes between consecutive K core matrices (LBO = 16) — the
-// descriptor simply overlaps. One output row (128 lanes, 112 valid) x 64 channels accumulates over
-// 7 kh x 2 MMAs (K = 16 each) into a 64-column TMEM slot.
+// Trick: no im2col is ever built. The image lives in shared memory as zero-padded NHWC4 BF16 rows ("RGB0" pixels of
+// 8 bytes, 232 pixels per row: 4 + 224 + 4). Two adjacent pixels form a 16-byte "super-pixel"; because the conv
+// stride is 2, the window of output column ow starts at super-pixel ow and spans 4 of them (a zero-weight tap + the
+// 7 real ones). So for a fixed filter row kh the A operand A[ow][j*8+e] = row[(ow+j)*8 + e] is a Hankel matrix that a
+// NO-SWIZZLE K-major UMMA descriptor reads directly from the contiguous row: 16 bytes between consecutive M rows
+// (SBO = 128 per 8 rows) and 16 bytes between consecutive K core matrices (LBO = 16) — the descriptor simply
+// overlaps itself. One conv row (128 lanes, 112 valid) x 64 channels accumulates over 7 kh x 2 MMAs (K = 16 each).
 //
-// Work unit = (image, 3 pooled rows) = 7 conv rows (one is shared with the neighbour unit, 7/6
-// redundancy) = 19 padded input rows (35 KB, ONE bulk copy) -> 7 TMEM slots (448 columns).
-// Warp roles: warp 0 producer (bulk copies), warp 1 MMA issuer, warp 2 TMEM alloc, warps 4..7
-// epilogue: bias + ReLU, vertical max over 3 slots in registers, horizontal max through shared
-// memory, coalesced NHWC BF16 stores of the pooled row.
+// Round 2 (second form). tools/mma_bench.cu measured what one of these MMAs costs: max(N / 2, 32 + N / 4) clocks —
+// the tensor pipe's N / 2 or the shared-memory fetch of its operands (128 B per clock: 32 wavefronts for the 128 x 16
+// A slice + N / 4 for B), whatever the layout. At N = 64 that is 48 clocks instead of 32: the old kernel (one conv
+// row per MMA) was bound by the operand fetch. So
+//  * work unit = a PAIR of conv rows (2k, 2k+1) = one pooled row k; an input row that both conv rows read (5 of the
+//    9 a pair touches) is fetched ONCE by an N = 128 MMA whose B operand is [W_kh | W_kh-2] and whose accumulator
+//    spans both rows' TMEM columns: 19 MMAs / 1056 clocks per pair instead of 28 / 1344;
+//  * the input streams through a ring of 4-row chunks (8 x 7.25 KB) instead of 19-row units, so every image row is
+//    brought in once, and — MODE 1 — the loader warps build the NHWC4 BF16 rows in shared memory straight from the
+//    caller's FP32 NCHW tensor: the layout pre-pass (stem_pack_kernel, 266 MB of HBM traffic per 256 images) is
+//    gone from the float path (it remains for uint8 input, which feeds the same kernel through bulk copies: MODE 0);
+//  * the pooled row's third conv row (2k - 1) is the previous pair's second row, carried in registers; a CTA whose
+//    contiguous range of pairs starts inside an image first computes the pair before its range to obtain it.
+// Warp roles: warps 0, 2, 3 loaders (MODE 1) / warp 0 bulk-copy producer (MODE 0), warp 1 MMA issuer, warp 2 also
+// TMEM alloc, warps 4..11 epilogue: vertical max in registers, bias + ReLU, horizontal max through shared memory,
+// coalesced NHWC BF16 stores of the pooled row. TMEM: 4 pair slots x 128 columns.
 #include <cstdint>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -31,26 +40,31 @@ namespace rnb {
 namespace {
 
 constexpr int IMG = 224;
-constexpr int PAD_W = 232;            // 3 + 224 + 5 pixels
+constexpr int PAD_W = 232;            // 4 + 224 + 4 pixels (padded pixel = image column + 4)
 constexpr int PAD_H = 235;            // 5 + 224 + 6 rows (padded row pr = ih + 5)
 constexpr int ROW_BYTES = PAD_W * 8;  // 1856
-constexpr int CONV = 112, POOL = 56;
-constexpr int ROWS_PER_UNIT = 7;      // conv rows (TMEM slots)
-constexpr int POOLED_PER_UNIT = 3;
-constexpr int UNITS_PER_IMG = (POOL + POOLED_PER_UNIT - 1) / POOLED_PER_UNIT;  // 19
-constexpr int IN_ROWS = 2 * ROWS_PER_UNIT + 5;                                  // 19
-constexpr int IN_BYTES = IN_ROWS * ROW_BYTES;                                   // 35264
-constexpr int IN_SLOT_BYTES = ((IN_BYTES + 512 + 1023) / 1024) * 1024;          // + read-past slack
-constexpr int W_BYTES = 28 * 1024;    // [kh*4 + j][64 oc][8 e] bf16
+constexpr int POOL = 56;
+constexpr int PAIRS = POOL;           // conv-row pairs (= pooled rows) per image
+constexpr int CHUNK_ROWS = 4;         // input rows per ring chunk: chunk c of an image = image rows 4c-4 .. 4c-1
+constexpr int CHUNK_BYTES = CHUNK_ROWS * ROW_BYTES;  // 7424
+constexpr int NCH = 8;                // ring depth in chunks; pair k reads chunks k, k+1, k+2
+constexpr int RING_BYTES = NCH * CHUNK_BYTES + 512;  // + read-past slack (lanes 112..127 read into the next row)
+constexpr int W_BYTES = 28 * 1024;    // [j][pos(kh)][64 oc][8 e] bf16
 constexpr int VBUF_BYTES = 112 * 128; // [ow][64 ch] bf16, 16-byte chunks XOR-swizzled by (ow & 7)
-constexpr int NBAR = 4 + 2 * ROWS_PER_UNIT;
-constexpr int STEM_SMEM = 1024 + 2 * IN_SLOT_BYTES + W_BYTES + 2 * VBUF_BYTES + NBAR * 8 + 16;
+constexpr int NSLOT = 4;              // TMEM pair slots (128 columns each)
+constexpr int NBAR = 2 * NCH + 2 * NSLOT;
+constexpr int STEM_SMEM = 1024 + RING_BYTES + W_BYTES + 2 * VBUF_BYTES + NBAR * 8 + 16;
 constexpr int EPI_THREADS = 256;                 // 8 epilogue warps
 constexpr int STEM_TC_THREADS = 128 + EPI_THREADS;
+
+// position of filter row kh inside a K chunk's group of weight blocks: [W6 W4 W2 W0 | W5 W3 W1], so that the block
+// after W_kh is W_kh-2 and an N = 128 MMA starting at W_kh covers both conv rows of a pair
+__host__ __device__ constexpr int wpos(int kh) { return (kh & 1) ? 4 + (5 - kh) / 2 : (6 - kh) / 2; }
 
 // x [B,3,224,224] fp32 -> xp [B][235][232][4] bf16, zero border and zero 4th channel.
 // One thread per group of 4 padded pixels (PAD_W = 232 = 58 groups): interior groups read one float4
 // from each colour plane (image column 4g-4 .. 4g-1 for group g >= 1; 224 = 56 groups) and write 32 B.
+// (Only the RNB_STEM_FUSED=0 fallback of the float path runs this: the fused kernel builds the rows itself.)
 __global__ void stem_pack_kernel(const float* __restrict__ x, uint4* __restrict__ xp, int B) {
     constexpr int GROUPS = PAD_W / 4;  // 58
     const int64_t total = 1LL * B * PAD_H * GROUPS;
@@ -63,26 +77,15 @@ __global__ void stem_pack_kernel(const float* __restrict__ x, uint4* __restrict_
         const int b = static_cast<int>(t / PAD_H);
         const int ih = pr - 5;
         float r[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f}, bl[4] = {0.f, 0.f, 0.f, 0.f};
-        if (ih >= 0 && ih < IMG) {
-            // padded pixels 4g..4g+3 are image columns 4g-3..4g: not 16-byte aligned, so read the two
-            // aligned float4s that cover them (columns 4g-4..4g-1 and 4g..4g+3) and pick
-            const float* row = x + (1LL * b * 3 * IMG + ih) * IMG;
-            const int c0 = 4 * gidx - 4;
-            float lo[3][4], hi[3][4];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float* pl = row + 1LL * c * IMG * IMG;
-                const float4 a = (c0 >= 0 && c0 < IMG) ? __ldg(reinterpret_cast<const float4*>(pl + c0))
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 d = (c0 + 4 < IMG) ? __ldg(reinterpret_cast<const float4*>(pl + c0 + 4))
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-                lo[c][0] = a.x; lo[c][1] = a.y; lo[c][2] = a.z; lo[c][3] = a.w;
-                hi[c][0] = d.x; hi[c][1] = d.y; hi[c][2] = d.z; hi[c][3] = d.w;
-            }
-            // image column of padded pixel 4g+j is 4g+j-3 = c0 + 1 + j
-            r[0] = lo[0][1]; r[1] = lo[0][2]; r[2] = lo[0][3]; r[3] = hi[0][0];
-            g[0] = lo[1][1]; g[1] = lo[1][2]; g[2] = lo[1][3]; g[3] = hi[1][0];
-            bl[0] = lo[2][1]; bl[1] = lo[2][2]; bl[2] = lo[2][3]; bl[3] = hi[2][0];
+        const int c0 = 4 * gidx - 4;  // padded pixels 4g..4g+3 are image columns 4g-4..4g-1: one aligned float4 per plane
+        if (ih >= 0 && ih < IMG && c0 >= 0 && c0 < IMG) {
+            const float* row = x + (1LL * b * 3 * IMG + ih) * IMG + c0;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(row));
+            const float4 d = __ldg(reinterpret_cast<const float4*>(row + 1LL * IMG * IMG));
+            const float4 e = __ldg(reinterpret_cast<const float4*>(row + 2LL * IMG * IMG));
+            r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+            g[0] = d.x; g[1] = d.y; g[2] = d.z; g[3] = d.w;
+            bl[0] = e.x; bl[1] = e.y; bl[2] = e.z; bl[3] = e.w;
         }
         uint4 o0, o1;
         auto px = [&](int j, uint32_t& a, uint32_t& c) {
@@ -123,7 +126,7 @@ __global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ x, uint4* __rest
             const uint8_t* row = x + (1LL * b * IMG + ih) * IMG * 3;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int iw = 4 * gidx - 3 + j;  // image column of padded pixel 4g + j
+                const int iw = 4 * gidx - 4 + j;  // image column of padded pixel 4g + j
                 if (iw >= 0 && iw < IMG) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
@@ -161,8 +164,9 @@ __global__ void u8_hwc_to_f32_nchw_kernel(const uint8_t* __restrict__ x, float* 
     }
 }
 
-// w [64][3][7][7] fp32 + BN -> wk [kh*4+j][oc][e] bf16 with e = (kw - 2j)*4 + c, kw in {2j, 2j+1};
-// kw = 7 and c = 3 are zero. bias[oc] = folded BN shift.
+// w [64][3][7][7] fp32 + BN -> wk [j][wpos(kh)][oc][e] bf16: K chunk j of filter row kh holds window pixels
+// p = 2j, 2j+1 (p = kw + 1; the window of output column ow starts at padded pixel 2*ow, one pixel left of tap 0),
+// e = (p - 2j)*4 + c. p = 0 and c = 3 are zero. bias[oc] = folded BN shift.
 __global__ void stem_pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
                                          const float* __restrict__ bn_b, const float* __restrict__ bn_m,
                                          const float* __restrict__ bn_v, __nv_bfloat16* __restrict__ wk,
@@ -171,15 +175,15 @@ __global__ void stem_pack_weights_kernel(const float* __restrict__ w, const floa
     if (i >= 28 * 64 * 8) return;
     const int e = i & 7, oc = (i >> 3) & 63, chunk = i >> 9;
     const int kh = chunk >> 2, j = chunk & 3;
-    const int kw = 2 * j + (e >> 2), c = e & 3;
+    const int kw = 2 * j + (e >> 2) - 1, c = e & 3;
     double scale = 1.0, shift = 0.0;
     if (bn_w) {
         scale = static_cast<double>(bn_w[oc]) / sqrt(static_cast<double>(bn_v[oc]) + 1e-5);
         shift = static_cast<double>(bn_b[oc]) - static_cast<double>(bn_m[oc]) * scale;
     }
     float v = 0.f;
-    if (kw < 7 && c < 3) v = static_cast<float>(static_cast<double>(w[((oc * 3 + c) * 7 + kh) * 7 + kw]) * scale);
-    wk[i] = __float2bfloat16_rn(v);
+    if (kw >= 0 && kw < 7 && c < 3) v = static_cast<float>(static_cast<double>(w[((oc * 3 + c) * 7 + kh) * 7 + kw]) * scale);
+    wk[((j * 7 + wpos(kh)) * 64 + oc) * 8 + e] = __float2bfloat16_rn(v);
     if (chunk == 0 && e == 0) bias[oc] = static_cast<float>(shift);
 }
 
@@ -203,41 +207,99 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
+// The sequence of work every role of a CTA walks in lock step: the CTA's contiguous range of pairs [p, p_end),
+// preceded by the pair before it when the range starts inside an image (`warm`: computed only for the conv row it
+// hands to the first real pair). `cn` counts the input chunks issued so far: a step that starts a segment (the first
+// step, or the first pair of an image) brings three new chunks (k, k+1, k+2), every other step one (k+2), and a
+// step reads the last three.
+struct StemSteps {
+    int p, p_end, cn, step;
+    bool warm;
+    __device__ StemSteps(int p_begin, int p_end_)
+        : p(p_begin), p_end(p_end_), cn(0), step(0), warm(p_begin < p_end_ && (p_begin % PAIRS) != 0) {}
+    __device__ bool done() const { return p >= p_end; }
+    __device__ int b() const { return p / PAIRS; }
+    __device__ int k() const { return p % PAIRS - (warm ? 1 : 0); }
+    __device__ bool seg_start() const { return step == 0 || k() == 0; }
+    __device__ int new_chunks() const { return seg_start() ? 3 : 1; }
+    __device__ void next() {
+        cn += new_chunks();
+        if (warm) warm = false; else ++p;
+        ++step;
+    }
+};
+
+// One ring chunk (image rows 4c-4 .. 4c-1 of image b) built by ONE warp from the FP32 NCHW tensor: 4 rows x 56
+// groups of 4 pixels = 7 groups per lane, all 21 float4 loads in flight, then RGB0 BF16 pixels, 32 bytes per group.
+// Chunks 0 and 57 lie outside the image (zero rows). The 32-byte halo columns on either side are never written
+// (zeroed once in the prologue).
+__device__ __forceinline__ void stem_fill_chunk_f32(uint8_t* dst, const float* __restrict__ x, int b, int c, int lane) {
+    if (c == 0 || c == PAIRS + 1) {
+        for (int i = lane; i < CHUNK_BYTES / 16; i += 32) reinterpret_cast<uint4*>(dst)[i] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const float* img = x + (1LL * b * 3 * IMG + (4 * c - 4)) * IMG;
+    float4 v[7][3];
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+        const int id = it * 32 + lane, rr = id / 56, g = id - rr * 56;
+        const float* src = img + rr * IMG + 4 * g;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+            v[it][ch] = __ldg(reinterpret_cast<const float4*>(src + 1LL * ch * IMG * IMG));
+    }
+    // a lane's 32 bytes are two 16-byte halves; lanes 4..7 of every eight store the second half first, so that the
+    // eight lanes of a quarter warp hit eight different 16-byte bank groups (the groups are 32 bytes apart)
+    const int first = (lane >> 2) & 1;
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+        const int id = it * 32 + lane, rr = id / 56, g = id - rr * 56;
+        uint4 h[2];
+        h[0].x = pack_bf16x2(v[it][0].x, v[it][1].x); h[0].y = pack_bf16x2(v[it][2].x, 0.f);
+        h[0].z = pack_bf16x2(v[it][0].y, v[it][1].y); h[0].w = pack_bf16x2(v[it][2].y, 0.f);
+        h[1].x = pack_bf16x2(v[it][0].z, v[it][1].z); h[1].y = pack_bf16x2(v[it][2].z, 0.f);
+        h[1].z = pack_bf16x2(v[it][0].w, v[it][1].w); h[1].w = pack_bf16x2(v[it][2].w, 0.f);
+        uint4* o = reinterpret_cast<uint4*>(dst + rr * ROW_BYTES + 32 * g + 32);
+        o[first] = first ? h[1] : h[0];
+        o[first ^ 1] = first ? h[0] : h[1];
+    }
+}
+
+// MODE 0: input = the packed NHWC4 BF16 tensor xp (bulk copies); MODE 1: input = FP32 NCHW x (loader warps).
+template <int MODE>
 __global__ void __launch_bounds__(STEM_TC_THREADS, 1)
-stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
+stem_tc_kernel(const void* __restrict__ xin, const uint8_t* __restrict__ wk,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B) {
     using namespace ptx;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
-    uint8_t* in_slot = smem;                              // 2 x IN_SLOT_BYTES
-    uint8_t* wsm = smem + 2 * IN_SLOT_BYTES;              // W_BYTES
+    uint8_t* ring = smem;                                 // NCH chunks + slack
+    uint8_t* wsm = smem + RING_BYTES;                     // W_BYTES
     uint8_t* vbuf = wsm + W_BYTES;                        // 2 x VBUF_BYTES
     uint64_t* bars = reinterpret_cast<uint64_t*>(vbuf + 2 * VBUF_BYTES);
-    uint64_t* in_full = bars;        // [2]
-    uint64_t* in_empty = bars + 2;   // [2]
-    uint64_t* slot_full = bars + 4;  // [7]
-    uint64_t* slot_empty = bars + 4 + ROWS_PER_UNIT;  // [7]
+    uint64_t* ch_full = bars;                   // [NCH]
+    uint64_t* ch_empty = bars + NCH;            // [NCH]
+    uint64_t* acc_full = bars + 2 * NCH;        // [NSLOT]
+    uint64_t* acc_empty = bars + 2 * NCH + NSLOT;  // [NSLOT]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + NBAR);
 
-    const int warp = threadIdx.x >> 5;
-    const int num_units = B * UNITS_PER_IMG;
-    // Each CTA takes a CONTIGUOUS range of units, so that most units follow the previous unit of the same image: the conv
-    // row the two share (slot 0 of the new unit = slot 6 of the old one) is then neither recomputed nor re-read — the
-    // epilogue already holds it in registers (`carry`). One seventh of the MMAs of this tensor-bound kernel disappears.
-    const int upc = num_units / static_cast<int>(gridDim.x), urem = num_units % static_cast<int>(gridDim.x);
-    const int u_begin = static_cast<int>(blockIdx.x) * upc + min(static_cast<int>(blockIdx.x), urem);
-    const int u_end = u_begin + upc + (static_cast<int>(blockIdx.x) < urem ? 1 : 0);
-    auto continues = [&](int u) { return u > u_begin && (u % UNITS_PER_IMG) != 0; };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_pairs = B * PAIRS;
+    // Each CTA takes a CONTIGUOUS range of pairs: consecutive pairs of an image share two of their three input
+    // chunks and the conv row between them.
+    const int ppc = num_pairs / static_cast<int>(gridDim.x), prem = num_pairs % static_cast<int>(gridDim.x);
+    const int p_begin = static_cast<int>(blockIdx.x) * ppc + min(static_cast<int>(blockIdx.x), prem);
+    const int p_end = p_begin + ppc + (static_cast<int>(blockIdx.x) < prem ? 1 : 0);
 
     if (threadIdx.x == 32) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&in_full[i], 1);
-            mbar_init(&in_empty[i], 1);
+        for (int i = 0; i < NCH; ++i) {
+            mbar_init(&ch_full[i], MODE == 0 ? 1 : 32);
+            mbar_init(&ch_empty[i], 1);
         }
-        for (int i = 0; i < ROWS_PER_UNIT; ++i) {
-            mbar_init(&slot_full[i], 1);
-            mbar_init(&slot_empty[i], EPI_THREADS);
+        for (int i = 0; i < NSLOT; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], EPI_THREADS);
         }
         fence_mbar_init();
     }
@@ -246,72 +308,98 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
         tmem_alloc(tmem_ptr_smem, 512);
         tmem_relinquish();
     }
-    // weights -> smem (28 KB, once per CTA), zero the read-past slack of both input slots
+    // weights -> smem (28 KB, once per CTA); zero the ring (halo columns, read-past slack)
     for (int i = threadIdx.x; i < W_BYTES / 16; i += STEM_TC_THREADS)
         reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(wk) + i);
-    for (int i = threadIdx.x; i < 2 * (IN_SLOT_BYTES - IN_BYTES) / 16; i += STEM_TC_THREADS) {
-        const int s = i / ((IN_SLOT_BYTES - IN_BYTES) / 16), o = i % ((IN_SLOT_BYTES - IN_BYTES) / 16);
-        reinterpret_cast<uint4*>(in_slot + s * IN_SLOT_BYTES + IN_BYTES)[o] = make_uint4(0, 0, 0, 0);
-    }
+    for (int i = threadIdx.x; i < RING_BYTES / 16; i += STEM_TC_THREADS)
+        reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();  // generic-proxy writes above are read by the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    // PDL: the prologue above (barriers, TMEM, weights — constants) overlaps the tail of the layout pre-pass, and
+    // PDL: the prologue above (barriers, TMEM, weights — constants) overlaps the tail of the previous kernel, and
     // the first conv kernel's prologue overlaps this kernel's tail
     griddep_launch_dependents();
     griddep_wait();
 
-    if (warp == 0) {
-        // ===================================================== producer: one bulk copy per unit
-        int it = 0;
-        for (int u = u_begin; u < u_end; ++u, ++it) {
-            const int s = it & 1;
-            mbar_wait(&in_empty[s], ((it >> 1) & 1) ^ 1);
-            if (elect_one()) {
-                const int b = u / UNITS_PER_IMG, v = u - b * UNITS_PER_IMG;
-                const uint8_t* src = xp + (1LL * b * PAD_H + 12 * v) * ROW_BYTES;  // padded rows 12v .. 12v+18
-                mbar_expect_tx(&in_full[s], IN_BYTES);
-                bulk_copy_g2s(in_slot + s * IN_SLOT_BYTES, src, IN_BYTES, &in_full[s]);
+    if (warp == 0 || (MODE == 1 && (warp == 2 || warp == 3))) {
+        // ===================================================== input: chunks into the ring, in stream order
+        const int widx = warp == 0 ? 0 : warp - 1;  // loader index 0..2 (MODE 1: chunk n belongs to loader n % 3)
+        for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
+            const int b = st.b(), nnew = st.new_chunks();
+            const int c_first = st.k() + 3 - nnew;
+            for (int i = 0; i < nnew; ++i) {
+                const int n = st.cn + i, c = c_first + i;
+                if (MODE == 1 && (n % 3) != widx) continue;
+                mbar_wait(&ch_empty[n & (NCH - 1)], ((n / NCH) & 1) ^ 1);
+                uint8_t* dst = ring + (n & (NCH - 1)) * CHUNK_BYTES;
+                if (MODE == 0) {
+                    if (elect_one()) {
+                        // image rows 4c-4 .. 4c-1 = padded rows 4c+1 .. 4c+4
+                        const uint8_t* src = static_cast<const uint8_t*>(xin) + (1LL * b * PAD_H + 4 * c + 1) * ROW_BYTES;
+                        mbar_expect_tx(&ch_full[n & (NCH - 1)], CHUNK_BYTES);
+                        bulk_copy_g2s(dst, src, CHUNK_BYTES, &ch_full[n & (NCH - 1)]);
+                    }
+                    __syncwarp();
+                } else {
+                    stem_fill_chunk_f32(dst, static_cast<const float*>(xin), b, c, lane);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&ch_full[n & (NCH - 1)]);
+                }
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        constexpr uint32_t idesc = umma_instr_desc(UMMA_FMT_BF16, 128, 64);
-        const uint64_t a_desc0 = umma_smem_desc(smem_u32(in_slot), 16, 128, UMMA_LAYOUT_NONE);
-        const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 1024, 128, UMMA_LAYOUT_NONE);
-        int it = 0;
-        uint32_t n0 = 0;  // uses of slot 0 so far
-        for (int u = u_begin; u < u_end; ++u, ++it) {
-            const int s = it & 1;
-            mbar_wait(&in_full[s], (it >> 1) & 1);
-            const bool cont = continues(u);
-            for (int r = cont ? 1 : 0; r < ROWS_PER_UNIT; ++r) {
-                // slot 0 is skipped by continuing units: its barriers count their own uses
-                mbar_wait(&slot_empty[r], r == 0 ? (n0 & 1) ^ 1 : (it & 1) ^ 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t d_tmem = tmem_base + r * 64;
+        constexpr uint32_t idesc64 = umma_instr_desc(UMMA_FMT_BF16, 128, 64);
+        constexpr uint32_t idesc128 = umma_instr_desc(UMMA_FMT_BF16, 128, 128);
+        const uint64_t a_desc0 = umma_smem_desc(smem_u32(ring), 16, 128, UMMA_LAYOUT_NONE);
+        const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 7 * 1024, 128, UMMA_LAYOUT_NONE);
+        for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
+            const int cn_after = st.cn + st.new_chunks();
+            const int j = st.step;
+            StemSteps nx = st;
+            nx.next();
+            const bool seg_ends = nx.done() || nx.seg_start();
+            for (int m = cn_after - 3; m < cn_after; ++m) mbar_wait(&ch_full[m & (NCH - 1)], (m / NCH) & 1);
+            mbar_wait(&acc_empty[j & (NSLOT - 1)], ((j / NSLOT) & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d0 = tmem_base + (j & (NSLOT - 1)) * 128, d1 = d0 + 64;
+                // input row t of the pair (image row 4k-3+t) = row (1+t) & 3 of chunk cn_after-3 + (1+t)/4;
+                // K step i (+32 bytes) covers window pixels 4i .. 4i+3, weight chunks j = 2i, 2i+1
+                auto arow = [&](int t, int i) {
+                    const int m = cn_after - 3 + ((1 + t) >> 2);
+                    return a_desc0 + static_cast<uint64_t>(
+                                         ((m & (NCH - 1)) * CHUNK_BYTES + ((1 + t) & 3) * ROW_BYTES + 32 * i) >> 4);
+                };
+                auto wblk = [&](int kh, int i) {
+                    return b_desc0 + static_cast<uint64_t>(((2 * i * 7 + wpos(kh)) * 1024) >> 4);
+                };
 #pragma unroll
-                    for (int kh = 0; kh < 7; ++kh) {
-                        // conv row r of the unit reads padded input rows 2r + kh of the slot
-                        const uint64_t a_row = a_desc0 + static_cast<uint64_t>(
-                                                             (s * IN_SLOT_BYTES + (2 * r + kh) * ROW_BYTES) >> 4);
+                for (int t = 0; t < 9; ++t) {
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const uint64_t ad = a_row + static_cast<uint64_t>(i * 2);            // +32 B: j += 2
-                            const uint64_t bd = b_desc0 + static_cast<uint64_t>(((kh * 4 + 2 * i) * 1024) >> 4);
-                            mma_f16_ss(d_tmem, ad, bd, idesc, (kh | i) != 0);
+                    for (int i = 0; i < 2; ++i) {
+                        if (t < 2) {                       // first conv row only: kh = t
+                            mma_f16_ss(d0, arow(t, i), wblk(t, i), idesc64, (t | i) != 0);
+                        } else if (t == 2 && i == 0) {     // the second row's accumulator starts here: two N = 64
+                            mma_f16_ss(d0, arow(t, i), wblk(2, i), idesc64, 1);
+                            mma_f16_ss(d1, arow(t, i), wblk(0, i), idesc64, 0);
+                        } else if (t < 7) {                // both rows: [W_t | W_t-2], one fetch of the input row
+                            mma_f16_ss(d0, arow(t, i), wblk(t, i), idesc128, 1);
+                        } else {                           // second conv row only: kh = t - 2
+                            mma_f16_ss(d1, arow(t, i), wblk(t - 2, i), idesc64, 1);
                         }
                     }
-                    tc_commit(&slot_full[r]);
-                    if (r == ROWS_PER_UNIT - 1) tc_commit(&in_empty[s]);  // input slot fully consumed
                 }
-                __syncwarp();
+                tc_commit(&acc_full[j & (NSLOT - 1)]);
+                tc_commit(&ch_empty[(cn_after - 3) & (NCH - 1)]);  // the oldest chunk is dead after this pair
+                if (seg_ends) {
+                    tc_commit(&ch_empty[(cn_after - 2) & (NCH - 1)]);
+                    tc_commit(&ch_empty[(cn_after - 1) & (NCH - 1)]);
+                }
             }
-            if (!cont) ++n0;
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===================================================== epilogue
@@ -319,106 +407,73 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
         // two warps of a quarter split the 64 channels (half 0 / half 1).
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
-        const int et = q * 32 + (threadIdx.x & 31);   // conv output column ow == TMEM lane
+        const int et = q * 32 + lane;                 // conv output column ow == TMEM lane
         const int etid = threadIdx.x - 128;           // 0..255 within the epilogue group
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32;
         float bias_r[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) bias_r[i] = __ldg(bias + half * 32 + i);
-        int it = 0;
-        int vb = 0;  // vbuf ping-pong
-        uint32_t n0 = 0;  // uses of slot 0 so far
-        float carry[32];  // the last conv row of the previous pooled row (and of the previous unit)
+        int vb = 0;       // vbuf ping-pong
+        float carry[32];  // conv row 2k-1: the second row of the previous pair
 #pragma unroll
         for (int i = 0; i < 32; ++i) carry[i] = -INFINITY;
-        for (int u = u_begin; u < u_end; ++u, ++it) {
-            const int b = u / UNITS_PER_IMG, v = u - b * UNITS_PER_IMG;
-            const uint32_t par = it & 1;
-            const bool cont = continues(u);
+        for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
+            const int b = st.b(), k = st.k(), j = st.step;
+            const bool warm = st.warm;
+            mbar_wait(&acc_full[j & (NSLOT - 1)], (j / NSLOT) & 1);
+            tc_fence_after();
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32(lane_addr + (j & (NSLOT - 1)) * 128, ra);
+            tmem_ld_32x32(lane_addr + (j & (NSLOT - 1)) * 128 + 64, rb);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&acc_empty[j & (NSLOT - 1)]);
+            // vertical max over conv rows 2k-1, 2k, 2k+1. max_r(x_r + b) = max_r(x_r) + b; the row above the image
+            // (k = 0) is simply left out (ReLU output is >= 0)
+            float m[32];
 #pragma unroll
-            for (int p = 0; p < POOLED_PER_UNIT; ++p) {
-                const int ph = v * POOLED_PER_UNIT + p;
-                // slots 2p, 2p+1, 2p+2 hold conv rows oh = 6v - 1 + slot
-                if (p == 0 && !cont) mbar_wait(&slot_full[0], n0 & 1);
-                mbar_wait(&slot_full[2 * p + 1], par);
-                mbar_wait(&slot_full[2 * p + 2], par);
-                tc_fence_after();
-                // vertical max over the three conv rows of this pooled row. max_k(x_k + b) =
-                // max_k(x_k) + b and ReLU output is >= 0, so a missing row (-1 or 112) is simply
-                // left out; the middle row 2*ph always exists for a stored pooled row.
-                // the conv row shared
-                // by two consecutive pooled rows (slot 2p+2 == slot 2(p+1)) is read once and carried in
-                // registers.
-                float m[32];
-#pragma unroll
-                for (int k = (p == 0 ? 0 : 1); k < 3; ++k) {
-                    if (p == 0 && k == 0 && cont) continue;  // that row is `carry`
-                    const int oh = 6 * v - 1 + 2 * p + k;
-                    uint32_t raw[32];
-                    __syncwarp();
-                    tmem_ld_32x32(lane_addr + (2 * p + k) * 64, raw);
-                    tmem_ld_wait();
-                    if (k == 0) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) m[i] = oh >= 0 ? __uint_as_float(raw[i]) : -INFINITY;
-                    } else {
-                        const bool valid = oh < CONV;
-                        if (k == 1 && (p > 0 || cont)) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) m[i] = carry[i];
-                        }
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float x = valid ? __uint_as_float(raw[i]) : -INFINITY;
-                            m[i] = fmaxf(m[i], x);
-                            if (k == 2) carry[i] = x;
-                        }
-                    }
-                }
-                if (et < CONV) {
-                    uint8_t* vrow = vbuf + vb * VBUF_BYTES + et * 128;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float x[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) x[e] = fmaxf(m[j * 8 + e] + bias_r[j * 8 + e], 0.f);
-                        uint4 o;
-                        o.x = pack_bf16x2(x[0], x[1]);
-                        o.y = pack_bf16x2(x[2], x[3]);
-                        o.z = pack_bf16x2(x[4], x[5]);
-                        o.w = pack_bf16x2(x[6], x[7]);
-                        *reinterpret_cast<uint4*>(vrow + (((half * 4 + j) ^ (et & 7)) << 4)) = o;
-                    }
-                }
-                // slots 2p and 2p+1 are drained; 2p+2 is re-read by the next pooled row (or drained
-                // with the last one)
-                tc_fence_before();
-                if (p > 0 || !cont) mbar_arrive(&slot_empty[2 * p]);
-                mbar_arrive(&slot_empty[2 * p + 1]);
-                if (p == POOLED_PER_UNIT - 1) mbar_arrive(&slot_empty[2 * p + 2]);
-                named_bar_sync(1, EPI_THREADS);
-                // horizontal 3-tap max (cols 2pw-1, 2pw, 2pw+1) and coalesced store of the pooled row
-                if (ph < POOL) {
-                    const uint8_t* vr = vbuf + vb * VBUF_BYTES;
-                    __nv_bfloat16* orow = out + ((1LL * b * POOL + ph) * POOL) * 64;
-                    for (int task = etid; task < POOL * 8; task += EPI_THREADS) {
-                        const int pw = task >> 3, c16 = task & 7;
-                        const int c0 = 2 * pw;
-                        uint4 a = *reinterpret_cast<const uint4*>(vr + c0 * 128 + ((c16 ^ (c0 & 7)) << 4));
-                        const uint4 c = *reinterpret_cast<const uint4*>(vr + (c0 + 1) * 128 + ((c16 ^ ((c0 + 1) & 7)) << 4));
-                        a.x = bf16x2_max(a.x, c.x); a.y = bf16x2_max(a.y, c.y);
-                        a.z = bf16x2_max(a.z, c.z); a.w = bf16x2_max(a.w, c.w);
-                        if (pw > 0) {
-                            const uint4 l = *reinterpret_cast<const uint4*>(vr + (c0 - 1) * 128 + ((c16 ^ ((c0 - 1) & 7)) << 4));
-                            a.x = bf16x2_max(a.x, l.x); a.y = bf16x2_max(a.y, l.y);
-                            a.z = bf16x2_max(a.z, l.z); a.w = bf16x2_max(a.w, l.w);
-                        }
-                        *reinterpret_cast<uint4*>(orow + pw * 64 + c16 * 8) = a;
-                    }
-                }
-                vb ^= 1;
+            for (int i = 0; i < 32; ++i) {
+                const float top = k == 0 ? -INFINITY : carry[i];
+                m[i] = fmaxf(fmaxf(top, __uint_as_float(ra[i])), __uint_as_float(rb[i]));
+                carry[i] = __uint_as_float(rb[i]);
             }
-            if (!cont) ++n0;
+            if (warm) continue;  // the pair before this CTA's range: only its second conv row was wanted
+            if (et < 112) {
+                uint8_t* vrow = vbuf + vb * VBUF_BYTES + et * 128;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    float x[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] = fmaxf(m[jj * 8 + e] + bias_r[jj * 8 + e], 0.f);
+                    uint4 o;
+                    o.x = pack_bf16x2(x[0], x[1]);
+                    o.y = pack_bf16x2(x[2], x[3]);
+                    o.z = pack_bf16x2(x[4], x[5]);
+                    o.w = pack_bf16x2(x[6], x[7]);
+                    *reinterpret_cast<uint4*>(vrow + (((half * 4 + jj) ^ (et & 7)) << 4)) = o;
+                }
+            }
+            named_bar_sync(1, EPI_THREADS);
+            // horizontal 3-tap max (cols 2pw-1, 2pw, 2pw+1) and coalesced store of the pooled row
+            {
+                const uint8_t* vr = vbuf + vb * VBUF_BYTES;
+                __nv_bfloat16* orow = out + ((1LL * b * POOL + k) * POOL) * 64;
+                for (int task = etid; task < POOL * 8; task += EPI_THREADS) {
+                    const int pw = task >> 3, c16 = task & 7;
+                    const int c0 = 2 * pw;
+                    uint4 a = *reinterpret_cast<const uint4*>(vr + c0 * 128 + ((c16 ^ (c0 & 7)) << 4));
+                    const uint4 c = *reinterpret_cast<const uint4*>(vr + (c0 + 1) * 128 + ((c16 ^ ((c0 + 1) & 7)) << 4));
+                    a.x = bf16x2_max(a.x, c.x); a.y = bf16x2_max(a.y, c.y);
+                    a.z = bf16x2_max(a.z, c.z); a.w = bf16x2_max(a.w, c.w);
+                    if (pw > 0) {
+                        const uint4 l = *reinterpret_cast<const uint4*>(vr + (c0 - 1) * 128 + ((c16 ^ ((c0 - 1) & 7)) << 4));
+                        a.x = bf16x2_max(a.x, l.x); a.y = bf16x2_max(a.y, l.y);
+                        a.z = bf16x2_max(a.z, l.z); a.w = bf16x2_max(a.w, l.w);
+                    }
+                    *reinterpret_cast<uint4*>(orow + pw * 64 + c16 * 8) = a;
+                }
+            }
+            vb ^= 1;
         }
     }
 
@@ -432,6 +487,11 @@ stem_tc_kernel(const uint8_t* __restrict__ xp, const uint8_t* __restrict__ wk,
 
 }  // namespace
 
+bool stem_fused_enabled() {
+    static const bool on = !(getenv("RNB_STEM_FUSED") && atoi(getenv("RNB_STEM_FUSED")) == 0);
+    return on;
+}
+
 size_t stem_tc_packed_input_bytes(int B) { return 1ull * B * PAD_H * ROW_BYTES; }
 size_t stem_tc_packed_weight_bytes() { return W_BYTES; }
 
@@ -444,27 +504,43 @@ cudaError_t launch_stem_tc_pack_weights(const float* w, const float* bn_w, const
 }
 
 cudaError_t stem_tc_init() {
-    return cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
 }
 
-// part 0: x fp32 NCHW [B,3,224,224] -> xp (scratch of stem_tc_packed_input_bytes(B));
-// part 1: xp -> out NHWC bf16 [B,56,56,64].
+static cudaError_t launch_stem_tc_kernel(int mode, const void* in, const void* wk, const float* bias, void* out, int B,
+                                         cudaStream_t s) {
+    const int pairs = B * PAIRS;
+    const int grid = pairs < num_sms() ? pairs : num_sms();
+    if (mode == 0)
+        return launch_pdl_small(stem_tc_kernel<0>, dim3(grid), dim3(STEM_TC_THREADS), STEM_SMEM, s, in,
+                                static_cast<const uint8_t*>(wk), bias, static_cast<__nv_bfloat16*>(out), B);
+    return launch_pdl_small(stem_tc_kernel<1>, dim3(grid), dim3(STEM_TC_THREADS), STEM_SMEM, s, in,
+                            static_cast<const uint8_t*>(wk), bias, static_cast<__nv_bfloat16*>(out), B);
+}
+
+// xp (packed NHWC4 BF16, written by a pack kernel) -> out NHWC bf16 [B,56,56,64]
+cudaError_t launch_stem_tc_from_packed(const void* xp, const void* wk, const float* bias, void* out, int B,
+                                       cudaStream_t s) {
+    return launch_stem_tc_kernel(0, xp, wk, bias, out, B, s);
+}
+
+// The float path in two "parts" (the callers time them separately). Fused form (default): part 0 does nothing and
+// part 1 reads x fp32 NCHW [B,3,224,224] directly. RNB_STEM_FUSED=0: part 0 = layout pre-pass x -> xp (scratch of
+// stem_tc_packed_input_bytes(B)), part 1 = xp -> out.
 cudaError_t launch_stem_tc_part(int part, const float* x, void* xp, const void* wk, const float* bias,
                                 void* out, int B, cudaStream_t s) {
+    if (stem_fused_enabled()) return part == 0 ? cudaSuccess : launch_stem_tc_kernel(1, x, wk, bias, out, B, s);
     if (part == 0) {
         const int64_t total = 1LL * B * PAD_H * (PAD_W / 4);
         int64_t blocks = (total + 255) / 256;
         const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
         if (blocks > cap) blocks = cap;
         stem_pack_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(x, static_cast<uint4*>(xp), B);
-    } else {
-        const int units = B * UNITS_PER_IMG;
-        const int grid = units < num_sms() ? units : num_sms();
-        return launch_pdl_small(stem_tc_kernel, dim3(grid), dim3(STEM_TC_THREADS), STEM_SMEM, s,
-                                static_cast<const uint8_t*>(xp), static_cast<const uint8_t*>(wk), bias,
-                                static_cast<__nv_bfloat16*>(out), B);
+        return cudaGetLastError();
     }
-    return cudaGetLastError();
+    return launch_stem_tc_kernel(0, xp, wk, bias, out, B, s);
 }
 
 // part 0 from decoded uint8 HWC images (see stem_pack_u8_kernel)
