@@ -202,6 +202,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return r;
 }
 
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
     __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);
@@ -233,9 +247,9 @@ struct StemSteps {
 // groups of 4 pixels = 7 groups per lane, all 21 float4 loads in flight, then RGB0 BF16 pixels, 32 bytes per group.
 // Chunks 0 and 57 lie outside the image (zero rows). The 32-byte halo columns on either side are never written
 // (zeroed once in the prologue).
-__device__ __forceinline__ void stem_fill_chunk_f32(uint8_t* dst, const float* __restrict__ x, int b, int c, int lane) {
+__device__ __forceinline__ void stem_fill_chunk_f32(uint32_t dst, const float* __restrict__ x, int b, int c, int lane) {
     if (c == 0 || c == PAIRS + 1) {
-        for (int i = lane; i < CHUNK_BYTES / 16; i += 32) reinterpret_cast<uint4*>(dst)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = lane; i < CHUNK_BYTES / 16; i += 32) st_shared_v4(dst + 16 * i, 0, 0, 0, 0);
         return;
     }
     const float* img = x + (1LL * b * 3 * IMG + (4 * c - 4)) * IMG;
@@ -259,9 +273,10 @@ __device__ __forceinline__ void stem_fill_chunk_f32(uint8_t* dst, const float* _
         h[0].z = pack_bf16x2(v[it][0].y, v[it][1].y); h[0].w = pack_bf16x2(v[it][2].y, 0.f);
         h[1].x = pack_bf16x2(v[it][0].z, v[it][1].z); h[1].y = pack_bf16x2(v[it][2].z, 0.f);
         h[1].z = pack_bf16x2(v[it][0].w, v[it][1].w); h[1].w = pack_bf16x2(v[it][2].w, 0.f);
-        uint4* o = reinterpret_cast<uint4*>(dst + rr * ROW_BYTES + 32 * g + 32);
-        o[first] = first ? h[1] : h[0];
-        o[first ^ 1] = first ? h[0] : h[1];
+        const uint32_t o = dst + rr * ROW_BYTES + 32 * g + 32;
+        const uint4 h0 = first ? h[1] : h[0], h1 = first ? h[0] : h[1];
+        st_shared_v4(o + 16 * first, h0.x, h0.y, h0.z, h0.w);
+        st_shared_v4(o + 16 * (first ^ 1), h1.x, h1.y, h1.z, h1.w);
     }
 }
 
@@ -343,7 +358,7 @@ stem_tc_kernel(const void* __restrict__ xin, const uint8_t* __restrict__ wk,
                     }
                     __syncwarp();
                 } else {
-                    stem_fill_chunk_f32(dst, static_cast<const float*>(xin), b, c, lane);
+                    stem_fill_chunk_f32(smem_u32(dst), static_cast<const float*>(xin), b, c, lane);
                     fence_proxy_async_smem();
                     mbar_arrive(&ch_full[n & (NCH - 1)]);
                 }
@@ -405,6 +420,11 @@ stem_tc_kernel(const void* __restrict__ xin, const uint8_t* __restrict__ wk,
         // ===================================================== epilogue
         // 8 warps: warp quarter q = warp & 3 owns TMEM lanes 32q..32q+31 (conv columns ow), and the
         // two warps of a quarter split the 64 channels (half 0 / half 1).
+        // (Measured and dropped, all bit-identical — tools/stem_epi_ab.py, gpurun_out/stem_epi_ab.txt: the two channel
+        // halves as independent groups with their own staging rows and named barrier: 116-120 us against 114; the same
+        // with the next pair's TMEM loads issued before the horizontal pass: 131 us. The MMA issuer waits for TMEM slots,
+        // i.e. the epilogue paces the kernel, but its pace is set by shared-memory loads that queue behind the tensor
+        // core's operand fetch, not by a latency chain that a second group would hide.)
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
         const int et = q * 32 + lane;                 // conv output column ow == TMEM lane
@@ -439,38 +459,43 @@ stem_tc_kernel(const void* __restrict__ xin, const uint8_t* __restrict__ wk,
             }
             if (warm) continue;  // the pair before this CTA's range: only its second conv row was wanted
             if (et < 112) {
-                uint8_t* vrow = vbuf + vb * VBUF_BYTES + et * 128;
+                const uint32_t vrow = smem_u32(vbuf) + vb * VBUF_BYTES + et * 128;
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    float x[8];
+                    uint32_t o[4];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] = fmaxf(m[jj * 8 + e] + bias_r[jj * 8 + e], 0.f);
-                    uint4 o;
-                    o.x = pack_bf16x2(x[0], x[1]);
-                    o.y = pack_bf16x2(x[2], x[3]);
-                    o.z = pack_bf16x2(x[4], x[5]);
-                    o.w = pack_bf16x2(x[6], x[7]);
-                    *reinterpret_cast<uint4*>(vrow + (((half * 4 + jj) ^ (et & 7)) << 4)) = o;
+                    for (int e = 0; e < 4; ++e)  // bias, ReLU and the BF16 rounding in one convert
+                        o[e] = pack_relu_bf16x2(m[jj * 8 + 2 * e] + bias_r[jj * 8 + 2 * e],
+                                                m[jj * 8 + 2 * e + 1] + bias_r[jj * 8 + 2 * e + 1]);
+                    st_shared_v4(vrow + (((half * 4 + jj) ^ (et & 7)) << 4), o[0], o[1], o[2], o[3]);
                 }
             }
             named_bar_sync(1, EPI_THREADS);
-            // horizontal 3-tap max (cols 2pw-1, 2pw, 2pw+1) and coalesced store of the pooled row
+            // horizontal 3-tap max (cols 2pw-1, 2pw, 2pw+1) and coalesced store of the pooled row: 448 16-byte tasks on
+            // 256 threads; all of a thread's loads are issued before the first max (they queue behind the tensor
+            // core's operand fetch)
             {
-                const uint8_t* vr = vbuf + vb * VBUF_BYTES;
+                const uint32_t vr = smem_u32(vbuf) + vb * VBUF_BYTES;
                 __nv_bfloat16* orow = out + ((1LL * b * POOL + k) * POOL) * 64;
-                for (int task = etid; task < POOL * 8; task += EPI_THREADS) {
-                    const int pw = task >> 3, c16 = task & 7;
-                    const int c0 = 2 * pw;
-                    uint4 a = *reinterpret_cast<const uint4*>(vr + c0 * 128 + ((c16 ^ (c0 & 7)) << 4));
-                    const uint4 c = *reinterpret_cast<const uint4*>(vr + (c0 + 1) * 128 + ((c16 ^ ((c0 + 1) & 7)) << 4));
-                    a.x = bf16x2_max(a.x, c.x); a.y = bf16x2_max(a.y, c.y);
-                    a.z = bf16x2_max(a.z, c.z); a.w = bf16x2_max(a.w, c.w);
-                    if (pw > 0) {
-                        const uint4 l = *reinterpret_cast<const uint4*>(vr + (c0 - 1) * 128 + ((c16 ^ ((c0 - 1) & 7)) << 4));
-                        a.x = bf16x2_max(a.x, l.x); a.y = bf16x2_max(a.y, l.y);
-                        a.z = bf16x2_max(a.z, l.z); a.w = bf16x2_max(a.w, l.w);
-                    }
-                    *reinterpret_cast<uint4*>(orow + pw * 64 + c16 * 8) = a;
+                auto at = [&](int col, int c16) { return vr + col * 128 + ((c16 ^ (col & 7)) << 4); };
+                const int c16 = etid & 7, pw0 = etid >> 3, pw1 = pw0 + 32;
+                const bool two = pw1 < POOL;
+                uint4 a0 = ld_shared_v4(at(2 * pw0, c16));
+                const uint4 r0 = ld_shared_v4(at(2 * pw0 + 1, c16));
+                const uint4 l0 = pw0 > 0 ? ld_shared_v4(at(2 * pw0 - 1, c16)) : a0;
+                uint4 a1 = a0, r1 = a0, l1 = a0;
+                if (two) {
+                    a1 = ld_shared_v4(at(2 * pw1, c16));
+                    r1 = ld_shared_v4(at(2 * pw1 + 1, c16));
+                    l1 = ld_shared_v4(at(2 * pw1 - 1, c16));
+                }
+                a0.x = bf16x2_max(bf16x2_max(a0.x, r0.x), l0.x); a0.y = bf16x2_max(bf16x2_max(a0.y, r0.y), l0.y);
+                a0.z = bf16x2_max(bf16x2_max(a0.z, r0.z), l0.z); a0.w = bf16x2_max(bf16x2_max(a0.w, r0.w), l0.w);
+                *reinterpret_cast<uint4*>(orow + pw0 * 64 + c16 * 8) = a0;
+                if (two) {
+                    a1.x = bf16x2_max(bf16x2_max(a1.x, r1.x), l1.x); a1.y = bf16x2_max(bf16x2_max(a1.y, r1.y), l1.y);
+                    a1.z = bf16x2_max(bf16x2_max(a1.z, r1.z), l1.z); a1.w = bf16x2_max(bf16x2_max(a1.w, r1.w), l1.w);
+                    *reinterpret_cast<uint4*>(orow + pw1 * 64 + c16 * 8) = a1;
                 }
             }
             vb ^= 1;
