@@ -1630,9 +1630,9 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
     const double img_px = 1.0 * image * image;
     if (stem_tc) {
         // launch 0 = layout pre-pass (fp32 NCHW -> padded NHWC4 bf16), launch 1 = fused conv+BN+ReLU+pool
-        // (BF16 stem, fused form: launch 0 does not exist — its entry times an empty interval — and launch 1 reads the
-        // FP32 image itself)
-        const bool fused = stem_esz() == 2 && stem_fused_enabled();
+        // (fused form: launch 0 does not exist — its entry times an empty interval — and launch 1 reads the FP32 image
+        // itself)
+        const bool fused = stem_esz() == 4 || stem_fused_enabled();  // (the TF32 split stem has no two-launch form)
         const double packed = static_cast<double>(stem_any_input_bytes(stem_esz(), 1));
         put(0, 0.0, fused ? 0.0 : n * (3.0 * img_px * 4 + packed));
         put(1, 2.0 * n * 64 * 147 * s_hw * s_hw,

@@ -18,6 +18,9 @@
 
 namespace rnb {
 
+bool stem_fused_enabled();  // stem_tc.cu
+
+
 struct ConvWeights {
     void* w = nullptr;       // packed [Cout][k][k][Cin] in the activation type, BN folded
     float* bias = nullptr;   // [Cout]
@@ -239,7 +242,9 @@ struct Model {
     // stem pre-pass/conv + stem/max-pool + planned conv launches + avg-pool + fc + arg-max
     int launches_per_chunk(int n) {
         ChunkPlan* p = plan_for(n);
-        return p ? static_cast<int>(p->convs.size()) + 5 + (p->pool_raw ? 1 : 0) : 0;
+        // (float input; the tensor-core stems are one launch — unless RNB_STEM_FUSED=0 — the CUDA-core stem two)
+        const int stem = stem_tc && (stem_esz() == 4 || stem_fused_enabled()) ? 1 : 2;
+        return p ? static_cast<int>(p->convs.size()) + stem + 3 + (p->pool_raw ? 1 : 0) : 0;
     }
 };
 

@@ -34,32 +34,22 @@
 
 #include "internal.h"
 #include "sm100_ptx.cuh"
+#include "stem_tc_common.cuh"
 
 namespace rnb {
 
 namespace {
 
-constexpr int IMG = 224;
-constexpr int PAD_W = 232;            // 4 + 224 + 4 pixels (padded pixel = image column + 4)
-constexpr int PAD_H = 235;            // 5 + 224 + 6 rows (padded row pr = ih + 5)
-constexpr int ROW_BYTES = PAD_W * 8;  // 1856
-constexpr int POOL = 56;
-constexpr int PAIRS = POOL;           // conv-row pairs (= pooled rows) per image
-constexpr int CHUNK_ROWS = 4;         // input rows per ring chunk: chunk c of an image = image rows 4c-4 .. 4c-1
-constexpr int CHUNK_BYTES = CHUNK_ROWS * ROW_BYTES;  // 7424
+using namespace stemtc;
+
 constexpr int NCH = 8;                // ring depth in chunks; pair k reads chunks k, k+1, k+2
 constexpr int RING_BYTES = NCH * CHUNK_BYTES + 512;  // + read-past slack (lanes 112..127 read into the next row)
 constexpr int W_BYTES = 28 * 1024;    // [j][pos(kh)][64 oc][8 e] bf16
 constexpr int VBUF_BYTES = 112 * 128; // [ow][64 ch] bf16, 16-byte chunks XOR-swizzled by (ow & 7)
-constexpr int NSLOT = 4;              // TMEM pair slots (128 columns each)
 constexpr int NBAR = 2 * NCH + 2 * NSLOT;
 constexpr int STEM_SMEM = 1024 + RING_BYTES + W_BYTES + 2 * VBUF_BYTES + NBAR * 8 + 16;
 constexpr int EPI_THREADS = 256;                 // 8 epilogue warps
 constexpr int STEM_TC_THREADS = 128 + EPI_THREADS;
-
-// position of filter row kh inside a K chunk's group of weight blocks: [W6 W4 W2 W0 | W5 W3 W1], so that the block
-// after W_kh is W_kh-2 and an N = 128 MMA starting at W_kh covers both conv rows of a pair
-__host__ __device__ constexpr int wpos(int kh) { return (kh & 1) ? 4 + (5 - kh) / 2 : (6 - kh) / 2; }
 
 // x [B,3,224,224] fp32 -> xp [B][235][232][4] bf16, zero border and zero 4th channel.
 // One thread per group of 4 padded pixels (PAD_W = 232 = 58 groups): interior groups read one float4
@@ -186,62 +176,6 @@ __global__ void stem_pack_weights_kernel(const float* __restrict__ w, const floa
     wk[((j * 7 + wpos(kh)) * 64 + oc) * 8 + e] = __float2bfloat16_rn(v);
     if (chunk == 0 && e == 0) bias[oc] = static_cast<float>(shift);
 }
-
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes,
-                                              uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            ptx::smem_u32(smem_dst)),
-        "l"(gsrc), "r"(bytes), "r"(ptx::smem_u32(bar))
-        : "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-
-__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
-    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-    return *reinterpret_cast<uint32_t*>(&r);
-}
-
-// The sequence of work every role of a CTA walks in lock step: the CTA's contiguous range of pairs [p, p_end),
-// preceded by the pair before it when the range starts inside an image (`warm`: computed only for the conv row it
-// hands to the first real pair). `cn` counts the input chunks issued so far: a step that starts a segment (the first
-// step, or the first pair of an image) brings three new chunks (k, k+1, k+2), every other step one (k+2), and a
-// step reads the last three.
-struct StemSteps {
-    int p, p_end, cn, step;
-    bool warm;
-    __device__ StemSteps(int p_begin, int p_end_)
-        : p(p_begin), p_end(p_end_), cn(0), step(0), warm(p_begin < p_end_ && (p_begin % PAIRS) != 0) {}
-    __device__ bool done() const { return p >= p_end; }
-    __device__ int b() const { return p / PAIRS; }
-    __device__ int k() const { return p % PAIRS - (warm ? 1 : 0); }
-    __device__ bool seg_start() const { return step == 0 || k() == 0; }
-    __device__ int new_chunks() const { return seg_start() ? 3 : 1; }
-    __device__ void next() {
-        cn += new_chunks();
-        if (warm) warm = false; else ++p;
-        ++step;
-    }
-};
 
 // One ring chunk (image rows 4c-4 .. 4c-1 of image b) built by ONE warp from the FP32 NCHW tensor: 4 rows x 56
 // groups of 4 pixels = 7 groups per lane, all 21 float4 loads in flight, then RGB0 BF16 pixels, 32 bytes per group.
@@ -420,11 +354,14 @@ stem_tc_kernel(const void* __restrict__ xin, const uint8_t* __restrict__ wk,
         // ===================================================== epilogue
         // 8 warps: warp quarter q = warp & 3 owns TMEM lanes 32q..32q+31 (conv columns ow), and the
         // two warps of a quarter split the 64 channels (half 0 / half 1).
-        // (Measured and dropped, all bit-identical — tools/stem_epi_ab.py, gpurun_out/stem_epi_ab.txt: the two channel
-        // halves as independent groups with their own staging rows and named barrier: 116-120 us against 114; the same
-        // with the next pair's TMEM loads issued before the horizontal pass: 131 us. The MMA issuer waits for TMEM slots,
-        // i.e. the epilogue paces the kernel, but its pace is set by shared-memory loads that queue behind the tensor
-        // core's operand fetch, not by a latency chain that a second group would hide.)
+        // (Measured and dropped, all bit-identical — tools/stem_epi_ab.py, profiles/stem_r2.md: the two channel halves as
+        // independent groups with their own staging rows and named barrier: 116-120 us against 114; the same with the
+        // next pair's TMEM loads issued before the horizontal pass: 131 us; the horizontal max by warp shuffles on an
+        // overlapping lane -> column map (SBO = 112: every warp owns all columns of 14 pooled outputs; no staging, no
+        // barrier): 128 against 120. The MMA issuer waits for TMEM slots, i.e. the epilogue paces the kernel, but its
+        // pace is set by LSU traffic (shared loads, shuffles) that queues behind the tensor core's operand fetch —
+        // ncu: tensor-core wavefronts 52 % + LSU wavefronts 46 % of the shared-memory data pipe — not by a latency
+        // chain that a second group would hide.)
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
         const int et = q * 32 + lane;                 // conv output column ow == TMEM lane

@@ -7,43 +7,37 @@
 // stem_tc.cu either (16-byte core-matrix rows are 4 fp32 = one pixel, but the conv stride is two
 // pixels). Instead every operand is split into two BF16 terms, x = x_hi + x_lo, w = w_hi + w_lo, and
 //   x*w  ~=  x_hi*w_hi + x_hi*w_lo + x_lo*w_hi          (dropped term ~2^-16 relative)
-// is accumulated by THREE tcgen05.mma per K step into the same FP32 TMEM accumulator. Input layout,
-// Hankel descriptors, work units and warp roles are exactly those of stem_tc.cu; differences:
-//   * the pre-pass writes two packed images (hi, lo); a unit is two 35 KB bulk copies;
-//   * weights are two 28 KB matrices;
-//   * the output is FP32 NHWC rounded to TF32 (the activation type of the TF32 path), so the
-//     horizontal-pool staging row is 256 bytes and there is room for only one staging buffer.
-// The stem MMAs are cheap (the layer is 3 % of the network's FLOPs), tripling them costs ~0.15 ms per
-// 256-batch against 2.2 ms for the FP32 CUDA-core stem it replaces.
+// is accumulated by THREE tcgen05.mma per K step into the same FP32 TMEM accumulator.
+//
+// Structure = stem_tc.cu's second form (round 2): conv-row PAIRS whose shared input rows are fetched once by
+// N = 128 MMAs, a ring of 4-row input chunks (here two rings: hi and lo terms), loader warps that build the NHWC4
+// rows from the caller's FP32 NCHW tensor — the layout pre-pass (two packed images, 380 MB of HBM traffic per 256
+// images) is gone — and the third conv row of a pooled row carried in registers. Differences from the BF16 kernel:
+//   * 3 x 19 MMAs per pair; weights are two 28 KB matrices;
+//   * the output is FP32 NHWC rounded to TF32 (the activation type of the TF32 path): 256-byte staging rows.
 #include <cstdint>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "internal.h"
 #include "sm100_ptx.cuh"
+#include "stem_tc_common.cuh"
 
 namespace rnb {
 
 namespace {
 
-constexpr int IMG = 224;
-constexpr int PAD_W = 232;
-constexpr int PAD_H = 235;
-constexpr int ROW_BYTES = PAD_W * 8;
-constexpr int CONV = 112, POOL = 56;
-constexpr int ROWS_PER_UNIT = 7;
-constexpr int POOLED_PER_UNIT = 3;
-constexpr int UNITS_PER_IMG = (POOL + POOLED_PER_UNIT - 1) / POOLED_PER_UNIT;
-constexpr int IN_ROWS = 2 * ROWS_PER_UNIT + 5;
-constexpr int IN_BYTES = IN_ROWS * ROW_BYTES;                            // 35264
-constexpr int IN_SLOT_BYTES = ((IN_BYTES + 512 + 1023) / 1024) * 1024;   // 35840 (hi or lo)
-constexpr int W_BYTES = 28 * 1024;                                       // hi or lo
-constexpr int VROW = 256;                                                // 64 ch x fp32
+using namespace stemtc;
+
+constexpr int NCH = 6;                                 // ring depth in chunks (pair k reads chunks k, k+1, k+2)
+constexpr int RING_BYTES = NCH * CHUNK_BYTES + 512;    // one ring (hi or lo) + read-past slack
+constexpr int W_BYTES = 28 * 1024;                     // hi or lo, [j][wpos(kh)][64 oc][8 e] bf16
+constexpr int VROW = 256;                              // 64 ch x fp32
 constexpr int VBUF_BYTES = 112 * VROW;
-constexpr int NBAR = 4 + 2 * ROWS_PER_UNIT;
+constexpr int NBAR = 2 * NCH + 2 * NSLOT;
 constexpr int EPI_THREADS = 256;
 constexpr int THREADS = 128 + EPI_THREADS;
-constexpr int SMEM = 1024 + 2 * 2 * IN_SLOT_BYTES + 2 * W_BYTES + VBUF_BYTES + NBAR * 8 + 16;
+constexpr int SMEM = 1024 + 2 * RING_BYTES + 2 * W_BYTES + 2 * VBUF_BYTES + NBAR * 8 + 16;
 static_assert(SMEM <= 232448, "smem budget");
 
 __device__ __forceinline__ float rna_tf32(float x) {
@@ -52,41 +46,8 @@ __device__ __forceinline__ float rna_tf32(float x) {
     return __uint_as_float(r);
 }
 
-// x [B,3,224,224] fp32 -> xp[0] = hi, xp[1] = lo, each [B][235][232][4] bf16 (see stem_tc.cu).
-__global__ void stem_pack_split_kernel(const float* __restrict__ x, uint2* __restrict__ xp_hi,
-                                       uint2* __restrict__ xp_lo, int B) {
-    const int64_t total = 1LL * B * PAD_H * PAD_W;
-    for (int64_t i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
-         i += 1LL * gridDim.x * blockDim.x) {
-        const int pw = static_cast<int>(i % PAD_W);
-        int64_t t = i / PAD_W;
-        const int pr = static_cast<int>(t % PAD_H);
-        const int b = static_cast<int>(t / PAD_H);
-        const int ih = pr - 5, iw = pw - 3;
-        uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
-        if (ih >= 0 && ih < IMG && iw >= 0 && iw < IMG) {
-            const float* p = x + (1LL * b * 3 * IMG + ih) * IMG + iw;
-            float v[3], h[3], l[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                v[c] = __ldg(p + 1LL * c * IMG * IMG);
-                h[c] = __bfloat162float(__float2bfloat16_rn(v[c]));
-                l[c] = v[c] - h[c];  // exact in fp32
-            }
-            __nv_bfloat162 a = __floats2bfloat162_rn(h[0], h[1]), c2 = __floats2bfloat162_rn(h[2], 0.f);
-            hi.x = *reinterpret_cast<uint32_t*>(&a);
-            hi.y = *reinterpret_cast<uint32_t*>(&c2);
-            a = __floats2bfloat162_rn(l[0], l[1]);
-            c2 = __floats2bfloat162_rn(l[2], 0.f);
-            lo.x = *reinterpret_cast<uint32_t*>(&a);
-            lo.y = *reinterpret_cast<uint32_t*>(&c2);
-        }
-        xp_hi[i] = hi;
-        xp_lo[i] = lo;
-    }
-}
-
-// Folded weights split into hi / lo BF16 matrices, layout [kh*4+j][oc][e] (see stem_tc.cu).
+// Folded weights split into hi / lo BF16 matrices, layout [j][wpos(kh)][oc][e] (see stem_tc.cu: K chunk j of filter
+// row kh holds window pixels p = 2j, 2j+1 with p = kw + 1).
 __global__ void stem_pack_weights_split_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
                                                const float* __restrict__ bn_b, const float* __restrict__ bn_m,
                                                const float* __restrict__ bn_v, __nv_bfloat16* __restrict__ wk_hi,
@@ -95,64 +56,104 @@ __global__ void stem_pack_weights_split_kernel(const float* __restrict__ w, cons
     if (i >= 28 * 64 * 8) return;
     const int e = i & 7, oc = (i >> 3) & 63, chunk = i >> 9;
     const int kh = chunk >> 2, j = chunk & 3;
-    const int kw = 2 * j + (e >> 2), c = e & 3;
+    const int kw = 2 * j + (e >> 2) - 1, c = e & 3;
     double scale = 1.0, shift = 0.0;
     if (bn_w) {
         scale = static_cast<double>(bn_w[oc]) / sqrt(static_cast<double>(bn_v[oc]) + 1e-5);
         shift = static_cast<double>(bn_b[oc]) - static_cast<double>(bn_m[oc]) * scale;
     }
     float v = 0.f;
-    if (kw < 7 && c < 3) v = static_cast<float>(static_cast<double>(w[((oc * 3 + c) * 7 + kh) * 7 + kw]) * scale);
+    if (kw >= 0 && kw < 7 && c < 3) v = static_cast<float>(static_cast<double>(w[((oc * 3 + c) * 7 + kh) * 7 + kw]) * scale);
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    wk_hi[i] = h;
-    wk_lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    const int o = ((j * 7 + wpos(kh)) * 64 + oc) * 8 + e;
+    wk_hi[o] = h;
+    wk_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
     if (chunk == 0 && e == 0) bias[oc] = static_cast<float>(shift);
 }
 
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            ptx::smem_u32(smem_dst)),
-        "l"(gsrc), "r"(bytes), "r"(ptx::smem_u32(bar))
-        : "memory");
+// One chunk (image rows 4c-4 .. 4c-1 of image b) of BOTH rings, built by one warp from the FP32 NCHW tensor:
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (the difference is exact in FP32). See stem_fill_chunk_f32.
+__device__ __forceinline__ void stem_fill_chunk_split(uint32_t dst_hi, uint32_t dst_lo, const float* __restrict__ x,
+                                                      int b, int c, int lane) {
+    if (c == 0 || c == PAIRS + 1) {
+        for (int i = lane; i < CHUNK_BYTES / 16; i += 32) {
+            st_shared_v4(dst_hi + 16 * i, 0, 0, 0, 0);
+            st_shared_v4(dst_lo + 16 * i, 0, 0, 0, 0);
+        }
+        return;
+    }
+    const float* img = x + (1LL * b * 3 * IMG + (4 * c - 4)) * IMG;
+    float4 v[7][3];
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+        const int id = it * 32 + lane, rr = id / 56, g = id - rr * 56;
+        const float* src = img + rr * IMG + 4 * g;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+            v[it][ch] = __ldg(reinterpret_cast<const float4*>(src + 1LL * ch * IMG * IMG));
+    }
+    const int first = (lane >> 2) & 1;  // bank-conflict-free store order, as in stem_fill_chunk_f32
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+        const int id = it * 32 + lane, rr = id / 56, g = id - rr * 56;
+        const uint32_t off = rr * ROW_BYTES + 32 * g + 32;
+        float px[4][3], hi[4][3], lo[4][3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            px[0][ch] = v[it][ch].x; px[1][ch] = v[it][ch].y; px[2][ch] = v[it][ch].z; px[3][ch] = v[it][ch].w;
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                hi[p][ch] = __bfloat162float(__float2bfloat16_rn(px[p][ch]));
+                lo[p][ch] = px[p][ch] - hi[p][ch];
+            }
+        uint32_t wh[8], wl[8];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            wh[2 * p] = pack_bf16x2(hi[p][0], hi[p][1]); wh[2 * p + 1] = pack_bf16x2(hi[p][2], 0.f);
+            wl[2 * p] = pack_bf16x2(lo[p][0], lo[p][1]); wl[2 * p + 1] = pack_bf16x2(lo[p][2], 0.f);
+        }
+        const int f4 = 4 * first, s4 = 4 * (first ^ 1);
+        st_shared_v4(dst_hi + off + 4 * f4, first ? wh[4] : wh[0], first ? wh[5] : wh[1], first ? wh[6] : wh[2], first ? wh[7] : wh[3]);
+        st_shared_v4(dst_hi + off + 4 * s4, first ? wh[0] : wh[4], first ? wh[1] : wh[5], first ? wh[2] : wh[6], first ? wh[3] : wh[7]);
+        st_shared_v4(dst_lo + off + 4 * f4, first ? wl[4] : wl[0], first ? wl[5] : wl[1], first ? wl[6] : wl[2], first ? wl[7] : wl[3]);
+        st_shared_v4(dst_lo + off + 4 * s4, first ? wl[0] : wl[4], first ? wl[1] : wl[5], first ? wl[2] : wl[6], first ? wl[3] : wl[7]);
+    }
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-stem_tc_split_kernel(const uint8_t* __restrict__ xp_hi, const uint8_t* __restrict__ xp_lo,
-                     const uint8_t* __restrict__ wk_hi, const uint8_t* __restrict__ wk_lo,
+stem_tc_split_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wk_hi, const uint8_t* __restrict__ wk_lo,
                      const float* __restrict__ bias, float* __restrict__ out, int B) {
     using namespace ptx;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
-    // input slots: [slot 0 hi][slot 0 lo][slot 1 hi][slot 1 lo]
-    uint8_t* in_slot = smem;
-    uint8_t* wsm = smem + 4 * IN_SLOT_BYTES;   // [hi 28 KB][lo 28 KB]
-    uint8_t* vbuf = wsm + 2 * W_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(vbuf + VBUF_BYTES);
-    uint64_t* in_full = bars;
-    uint64_t* in_empty = bars + 2;
-    uint64_t* slot_full = bars + 4;
-    uint64_t* slot_empty = bars + 4 + ROWS_PER_UNIT;
+    uint8_t* ring = smem;                       // [hi ring][lo ring]
+    uint8_t* wsm = smem + 2 * RING_BYTES;       // [hi 28 KB][lo 28 KB]
+    uint8_t* vbuf = wsm + 2 * W_BYTES;          // 2 x VBUF_BYTES
+    uint64_t* bars = reinterpret_cast<uint64_t*>(vbuf + 2 * VBUF_BYTES);
+    uint64_t* ch_full = bars;                       // [NCH]
+    uint64_t* ch_empty = bars + NCH;                // [NCH]
+    uint64_t* acc_full = bars + 2 * NCH;            // [NSLOT]
+    uint64_t* acc_empty = bars + 2 * NCH + NSLOT;   // [NSLOT]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + NBAR);
 
-    const int warp = threadIdx.x >> 5;
-    const int num_units = B * UNITS_PER_IMG;
-    // contiguous unit range per CTA; the conv row shared with the previous unit of the same image is carried in
-    // registers by the epilogue instead of being recomputed (see stem_tc.cu)
-    const int upc = num_units / static_cast<int>(gridDim.x), urem = num_units % static_cast<int>(gridDim.x);
-    const int u_begin = static_cast<int>(blockIdx.x) * upc + min(static_cast<int>(blockIdx.x), urem);
-    const int u_end = u_begin + upc + (static_cast<int>(blockIdx.x) < urem ? 1 : 0);
-    auto continues = [&](int u) { return u > u_begin && (u % UNITS_PER_IMG) != 0; };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_pairs = B * PAIRS;
+    const int ppc = num_pairs / static_cast<int>(gridDim.x), prem = num_pairs % static_cast<int>(gridDim.x);
+    const int p_begin = static_cast<int>(blockIdx.x) * ppc + min(static_cast<int>(blockIdx.x), prem);
+    const int p_end = p_begin + ppc + (static_cast<int>(blockIdx.x) < prem ? 1 : 0);
 
     if (threadIdx.x == 32) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&in_full[i], 1);
-            mbar_init(&in_empty[i], 1);
+        for (int i = 0; i < NCH; ++i) {
+            mbar_init(&ch_full[i], 32);
+            mbar_init(&ch_empty[i], 1);
         }
-        for (int i = 0; i < ROWS_PER_UNIT; ++i) {
-            mbar_init(&slot_full[i], 1);
-            mbar_init(&slot_empty[i], EPI_THREADS);
+        for (int i = 0; i < NSLOT; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], EPI_THREADS);
         }
         fence_mbar_init();
     }
@@ -165,152 +166,151 @@ stem_tc_split_kernel(const uint8_t* __restrict__ xp_hi, const uint8_t* __restric
         reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(wk_hi) + i);
         reinterpret_cast<uint4*>(wsm + W_BYTES)[i] = __ldg(reinterpret_cast<const uint4*>(wk_lo) + i);
     }
-    constexpr int SLACK16 = (IN_SLOT_BYTES - IN_BYTES) / 16;
-    for (int i = threadIdx.x; i < 4 * SLACK16; i += THREADS)
-        reinterpret_cast<uint4*>(in_slot + (i / SLACK16) * IN_SLOT_BYTES + IN_BYTES)[i % SLACK16] =
-            make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 2 * RING_BYTES / 16; i += THREADS)   // halo columns, read-past slack
+        reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 0) {
-        // ===================================================== producer: two bulk copies per unit
-        int it = 0;
-        for (int u = u_begin; u < u_end; ++u, ++it) {
-            const int s = it & 1;
-            mbar_wait(&in_empty[s], ((it >> 1) & 1) ^ 1);
-            if (elect_one()) {
-                const int b = u / UNITS_PER_IMG, v = u - b * UNITS_PER_IMG;
-                const int64_t off = (1LL * b * PAD_H + 12 * v) * ROW_BYTES;
-                mbar_expect_tx(&in_full[s], 2 * IN_BYTES);
-                bulk_copy_g2s(in_slot + (2 * s) * IN_SLOT_BYTES, xp_hi + off, IN_BYTES, &in_full[s]);
-                bulk_copy_g2s(in_slot + (2 * s + 1) * IN_SLOT_BYTES, xp_lo + off, IN_BYTES, &in_full[s]);
+    if (warp == 0 || warp == 2 || warp == 3) {
+        // ===================================================== loaders: chunk n belongs to loader n % 3
+        const int widx = warp == 0 ? 0 : warp - 1;
+        for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
+            const int b = st.b(), nnew = st.new_chunks();
+            const int c_first = st.k() + 3 - nnew;
+            for (int i = 0; i < nnew; ++i) {
+                const int n = st.cn + i, c = c_first + i;
+                if ((n % 3) != widx) continue;
+                mbar_wait(&ch_empty[n % NCH], ((n / NCH) & 1) ^ 1);
+                const uint32_t dst = smem_u32(ring) + (n % NCH) * CHUNK_BYTES;
+                stem_fill_chunk_split(dst, dst + RING_BYTES, x, b, c, lane);
+                fence_proxy_async_smem();
+                mbar_arrive(&ch_full[n % NCH]);
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer: 3 split products per K step
-        constexpr uint32_t idesc = umma_instr_desc(UMMA_FMT_BF16, 128, 64);
-        const uint64_t a_desc0 = umma_smem_desc(smem_u32(in_slot), 16, 128, UMMA_LAYOUT_NONE);
-        const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 1024, 128, UMMA_LAYOUT_NONE);
-        constexpr uint64_t A_LO = IN_SLOT_BYTES >> 4;   // hi -> lo image inside a slot
-        constexpr uint64_t B_LO = W_BYTES >> 4;         // hi -> lo weights
-        int it = 0;
-        uint32_t n0 = 0;  // uses of slot 0 so far (continuing units skip it)
-        for (int u = u_begin; u < u_end; ++u, ++it) {
-            const int s = it & 1;
-            mbar_wait(&in_full[s], (it >> 1) & 1);
-            const bool cont = continues(u);
-            if (!cont) ++n0;
-            for (int r = cont ? 1 : 0; r < ROWS_PER_UNIT; ++r) {
-                mbar_wait(&slot_empty[r], r == 0 ? (n0 & 1) : (it & 1) ^ 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t d_tmem = tmem_base + r * 64;
+        constexpr uint32_t idesc64 = umma_instr_desc(UMMA_FMT_BF16, 128, 64);
+        constexpr uint32_t idesc128 = umma_instr_desc(UMMA_FMT_BF16, 128, 128);
+        const uint64_t a_desc0 = umma_smem_desc(smem_u32(ring), 16, 128, UMMA_LAYOUT_NONE);
+        const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 7 * 1024, 128, UMMA_LAYOUT_NONE);
+        constexpr uint64_t A_LO = RING_BYTES >> 4;   // hi -> lo ring
+        constexpr uint64_t B_LO = W_BYTES >> 4;      // hi -> lo weights
+        for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
+            const int cn_after = st.cn + st.new_chunks();
+            const int j = st.step;
+            StemSteps nx = st;
+            nx.next();
+            const bool seg_ends = nx.done() || nx.seg_start();
+            for (int m = cn_after - 3; m < cn_after; ++m) mbar_wait(&ch_full[m % NCH], (m / NCH) & 1);
+            mbar_wait(&acc_empty[j & (NSLOT - 1)], ((j / NSLOT) & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d0 = tmem_base + (j & (NSLOT - 1)) * 128, d1 = d0 + 64;
+                auto arow = [&](int t, int i) {
+                    const int m = cn_after - 3 + ((1 + t) >> 2);
+                    return a_desc0 + static_cast<uint64_t>(
+                                         ((m % NCH) * CHUNK_BYTES + ((1 + t) & 3) * ROW_BYTES + 32 * i) >> 4);
+                };
+                auto wblk = [&](int kh, int i) {
+                    return b_desc0 + static_cast<uint64_t>(((2 * i * 7 + wpos(kh)) * 1024) >> 4);
+                };
+                // x_hi * w_hi, x_hi * w_lo, x_lo * w_hi into one accumulator
+                auto mma3 = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+                    mma_f16_ss(d, ad, bd, idesc, acc);
+                    mma_f16_ss(d, ad, bd + B_LO, idesc, 1);
+                    mma_f16_ss(d, ad + A_LO, bd, idesc, 1);
+                };
 #pragma unroll
-                    for (int kh = 0; kh < 7; ++kh) {
-                        const uint64_t a_row = a_desc0 + static_cast<uint64_t>(
-                                                             (2 * s * IN_SLOT_BYTES + (2 * r + kh) * ROW_BYTES) >> 4);
+                for (int t = 0; t < 9; ++t) {
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const uint64_t ad = a_row + static_cast<uint64_t>(i * 2);
-                            const uint64_t bd = b_desc0 + static_cast<uint64_t>(((kh * 4 + 2 * i) * 1024) >> 4);
-                            mma_f16_ss(d_tmem, ad, bd, idesc, (kh | i) != 0);   // x_hi * w_hi
-                            mma_f16_ss(d_tmem, ad, bd + B_LO, idesc, 1);        // x_hi * w_lo
-                            mma_f16_ss(d_tmem, ad + A_LO, bd, idesc, 1);        // x_lo * w_hi
+                    for (int i = 0; i < 2; ++i) {
+                        if (t < 2) {
+                            mma3(d0, arow(t, i), wblk(t, i), idesc64, (t | i) != 0);
+                        } else if (t == 2 && i == 0) {
+                            mma3(d0, arow(t, i), wblk(2, i), idesc64, 1);
+                            mma3(d1, arow(t, i), wblk(0, i), idesc64, 0);
+                        } else if (t < 7) {
+                            mma3(d0, arow(t, i), wblk(t, i), idesc128, 1);
+                        } else {
+                            mma3(d1, arow(t, i), wblk(t - 2, i), idesc64, 1);
                         }
                     }
-                    tc_commit(&slot_full[r]);
-                    if (r == ROWS_PER_UNIT - 1) tc_commit(&in_empty[s]);
                 }
-                __syncwarp();
+                tc_commit(&acc_full[j & (NSLOT - 1)]);
+                tc_commit(&ch_empty[(cn_after - 3) % NCH]);
+                if (seg_ends) {
+                    tc_commit(&ch_empty[(cn_after - 2) % NCH]);
+                    tc_commit(&ch_empty[(cn_after - 1) % NCH]);
+                }
             }
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===================================================== epilogue (FP32 / TF32-rounded output)
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
-        const int et = q * 32 + (threadIdx.x & 31);
+        const int et = q * 32 + lane;
         const int etid = threadIdx.x - 128;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32;
-        int it = 0;
-        uint32_t n0 = 0;  // uses of slot 0 so far
-        float carry[32];  // the last conv row of the previous pooled row (and of the previous unit)
+        float bias_r[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bias_r[i] = __ldg(bias + half * 32 + i);
+        int vb = 0;
+        float carry[32];  // conv row 2k-1: the second row of the previous pair
 #pragma unroll
         for (int i = 0; i < 32; ++i) carry[i] = -INFINITY;
-        for (int u = u_begin; u < u_end; ++u, ++it) {
-            const int b = u / UNITS_PER_IMG, v = u - b * UNITS_PER_IMG;
-            const uint32_t par = it & 1;
-            const bool cont = continues(u);
-            if (!cont) ++n0;
-            for (int p = 0; p < POOLED_PER_UNIT; ++p) {
-                const int ph = v * POOLED_PER_UNIT + p;
-                if (p == 0 && !cont) mbar_wait(&slot_full[0], (n0 & 1) ^ 1);
-                mbar_wait(&slot_full[2 * p + 1], par);
-                mbar_wait(&slot_full[2 * p + 2], par);
-                tc_fence_after();
-                float m[32];
+        for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
+            const int b = st.b(), k = st.k(), j = st.step;
+            const bool warm = st.warm;
+            mbar_wait(&acc_full[j & (NSLOT - 1)], (j / NSLOT) & 1);
+            tc_fence_after();
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32(lane_addr + (j & (NSLOT - 1)) * 128, ra);
+            tmem_ld_32x32(lane_addr + (j & (NSLOT - 1)) * 128 + 64, rb);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&acc_empty[j & (NSLOT - 1)]);
+            float m[32];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (k == 0 && (p > 0 || cont)) {  // read once, as row k = 2 of the previous pooled row
+            for (int i = 0; i < 32; ++i) {
+                const float top = k == 0 ? -INFINITY : carry[i];
+                m[i] = fmaxf(fmaxf(top, __uint_as_float(ra[i])), __uint_as_float(rb[i]));
+                carry[i] = __uint_as_float(rb[i]);
+            }
+            if (warm) continue;
+            if (et < 112) {
+                const uint32_t vrow = smem_u32(vbuf) + vb * VBUF_BYTES + et * VROW + half * 128;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) m[i] = carry[i];
-                        continue;
-                    }
-                    const int oh = 6 * v - 1 + 2 * p + k;
-                    uint32_t raw[32];
-                    __syncwarp();
-                    tmem_ld_32x32(lane_addr + (2 * p + k) * 64, raw);
-                    tmem_ld_wait();
-                    const bool valid = oh >= 0 && oh < CONV;
+                for (int jj = 0; jj < 8; ++jj) {
+                    float o[4];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float x = valid ? __uint_as_float(raw[i]) : -INFINITY;
-                        m[i] = k == 0 ? x : fmaxf(m[i], x);
-                        if (k == 2) carry[i] = x;
-                    }
-                }
-                tc_fence_before();
-                if (p > 0 || !cont) mbar_arrive(&slot_empty[2 * p]);
-                mbar_arrive(&slot_empty[2 * p + 1]);
-                if (p == POOLED_PER_UNIT - 1) mbar_arrive(&slot_empty[2 * p + 2]);
-                // single staging buffer: the previous pooled row's horizontal pass must be over
-                named_bar_sync(1, EPI_THREADS);
-                if (et < CONV) {
-                    uint8_t* vrow = vbuf + et * VROW + half * 128;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 o;
-                        o.x = rna_tf32(fmaxf(m[j * 4 + 0] + __ldg(bias + half * 32 + j * 4 + 0), 0.f));
-                        o.y = rna_tf32(fmaxf(m[j * 4 + 1] + __ldg(bias + half * 32 + j * 4 + 1), 0.f));
-                        o.z = rna_tf32(fmaxf(m[j * 4 + 2] + __ldg(bias + half * 32 + j * 4 + 2), 0.f));
-                        o.w = rna_tf32(fmaxf(m[j * 4 + 3] + __ldg(bias + half * 32 + j * 4 + 3), 0.f));
-                        *reinterpret_cast<float4*>(vrow + ((j ^ (et & 7)) << 4)) = o;
-                    }
-                }
-                named_bar_sync(2, EPI_THREADS);
-                if (ph < POOL) {
-                    float* orow = out + ((1LL * b * POOL + ph) * POOL) * 64;
-                    for (int task = etid; task < POOL * 16; task += EPI_THREADS) {
-                        const int pw = task >> 4, c16 = task & 15;   // 16 chunks of 4 floats per pixel
-                        const int hh = c16 >> 3, cj = c16 & 7;
-                        const int c0 = 2 * pw;
-                        auto ld = [&](int row) {
-                            return *reinterpret_cast<const float4*>(vbuf + row * VROW + hh * 128 + ((cj ^ (row & 7)) << 4));
-                        };
-                        float4 a = ld(c0);
-                        const float4 c = ld(c0 + 1);
-                        a.x = fmaxf(a.x, c.x); a.y = fmaxf(a.y, c.y); a.z = fmaxf(a.z, c.z); a.w = fmaxf(a.w, c.w);
-                        if (pw > 0) {
-                            const float4 l = ld(c0 - 1);
-                            a.x = fmaxf(a.x, l.x); a.y = fmaxf(a.y, l.y); a.z = fmaxf(a.z, l.z); a.w = fmaxf(a.w, l.w);
-                        }
-                        *reinterpret_cast<float4*>(orow + pw * 64 + c16 * 4) = a;
-                    }
+                    for (int e = 0; e < 4; ++e) o[e] = rna_tf32(fmaxf(m[jj * 4 + e] + bias_r[jj * 4 + e], 0.f));
+                    st_shared_v4(vrow + ((jj ^ (et & 7)) << 4), __float_as_uint(o[0]), __float_as_uint(o[1]),
+                                 __float_as_uint(o[2]), __float_as_uint(o[3]));
                 }
             }
+            named_bar_sync(1, EPI_THREADS);
+            {
+                const uint32_t vr = smem_u32(vbuf) + vb * VBUF_BYTES;
+                float* orow = out + ((1LL * b * POOL + k) * POOL) * 64;
+                for (int task = etid; task < POOL * 16; task += EPI_THREADS) {
+                    const int pw = task >> 4, c16 = task & 15;   // 16 chunks of 4 floats per pixel
+                    const int hh = c16 >> 3, cj = c16 & 7;
+                    const int c0 = 2 * pw;
+                    auto ld = [&](int row) { return ld_shared_v4(vr + row * VROW + hh * 128 + ((cj ^ (row & 7)) << 4)); };
+                    const uint4 a = ld(c0), c = ld(c0 + 1), l = pw > 0 ? ld(c0 - 1) : a;
+                    float4 r;
+                    r.x = fmaxf(fmaxf(__uint_as_float(a.x), __uint_as_float(c.x)), __uint_as_float(l.x));
+                    r.y = fmaxf(fmaxf(__uint_as_float(a.y), __uint_as_float(c.y)), __uint_as_float(l.y));
+                    r.z = fmaxf(fmaxf(__uint_as_float(a.z), __uint_as_float(c.z)), __uint_as_float(l.z));
+                    r.w = fmaxf(fmaxf(__uint_as_float(a.w), __uint_as_float(c.w)), __uint_as_float(l.w));
+                    *reinterpret_cast<float4*>(orow + pw * 64 + c16 * 4) = r;
+                }
+            }
+            vb ^= 1;
         }
     }
 
@@ -324,7 +324,9 @@ stem_tc_split_kernel(const uint8_t* __restrict__ xp_hi, const uint8_t* __restric
 
 }  // namespace
 
-size_t stem_tc_split_packed_input_bytes(int B) { return 2ull * B * PAD_H * ROW_BYTES; }
+// no layout pre-pass any more: the scratch tensor of the two-launch form is not used (a token size keeps the
+// callers' allocation paths unchanged)
+size_t stem_tc_split_packed_input_bytes(int) { return 256; }
 size_t stem_tc_split_packed_weight_bytes() { return 2 * W_BYTES; }
 
 cudaError_t stem_tc_split_init() {
@@ -340,25 +342,15 @@ cudaError_t launch_stem_tc_split_pack_weights(const float* w, const float* bn_w,
     return cudaGetLastError();
 }
 
-// part 0: x fp32 NCHW -> xp (hi image followed by lo image); part 1: xp -> out NHWC fp32 [B,56,56,64].
-cudaError_t launch_stem_tc_split_part(int part, const float* x, void* xp, const void* wk, const float* bias,
+// part 0: nothing (kept so that the callers' two-part timing stays uniform); part 1: x fp32 NCHW -> out NHWC fp32
+// [B,56,56,64].
+cudaError_t launch_stem_tc_split_part(int part, const float* x, void* /*xp*/, const void* wk, const float* bias,
                                       void* out, int B, cudaStream_t s) {
-    uint8_t* hi = static_cast<uint8_t*>(xp);
-    uint8_t* lo = hi + 1ull * B * PAD_H * ROW_BYTES;
-    if (part == 0) {
-        const int64_t total = 1LL * B * PAD_H * PAD_W;
-        int64_t blocks = (total + 255) / 256;
-        const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
-        if (blocks > cap) blocks = cap;
-        stem_pack_split_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(x, reinterpret_cast<uint2*>(hi),
-                                                                      reinterpret_cast<uint2*>(lo), B);
-    } else {
-        const int units = B * UNITS_PER_IMG;
-        const int grid = units < num_sms() ? units : num_sms();
-        const uint8_t* w_hi = static_cast<const uint8_t*>(wk);
-        stem_tc_split_kernel<<<grid, THREADS, SMEM, s>>>(hi, lo, w_hi, w_hi + W_BYTES, bias,
-                                                        static_cast<float*>(out), B);
-    }
+    if (part == 0) return cudaSuccess;
+    const int pairs = B * PAIRS;
+    const int grid = pairs < num_sms() ? pairs : num_sms();
+    const uint8_t* w_hi = static_cast<const uint8_t*>(wk);
+    stem_tc_split_kernel<<<grid, THREADS, SMEM, s>>>(x, w_hi, w_hi + W_BYTES, bias, static_cast<float*>(out), B);
     return cudaGetLastError();
 }
 
