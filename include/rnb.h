@@ -82,7 +82,8 @@ int rnb_model_calibrate(rnb_model_t* m, const float* x_dev, int batch);
 
 /* Pre-packed weight cache. rnb_model_save_packed() writes everything rnb_model_create() derived from the
  * save_weights.py directory (BN folded into K-major BF16/TF32 conv weights, stem / FC packs, biases) as ONE
- * file: 72-byte header (magic "RNBWGT01", arch, dtype, class count, word-wise FNV-1a-64 checksum) + 256-byte-aligned
+ * file: 72-byte header (magic "RNBWGT01", format version — 2 since the stem's weight blocks were re-ordered; files of
+ * another version are refused —, arch, dtype, class count, word-wise FNV-1a-64 checksum) + 256-byte-aligned
  * tensors. rnb_model_create_packed() restores a model from it with one read and one host->device copy
  * instead of 320-932 small file reads, copies and fold kernels (tensor.cuh:126-152,184-199); a wrong magic,
  * size or checksum is an error. The packed model computes bit-identical results. */

@@ -1,6 +1,7 @@
-"""GPU: A/B of the stem kernel's epilogue variants (RNB_STEM_EPI = 0..3, read per launch) on one box: per-launch time of
-the stem from the un-graphed event profile and a checksum of the logits (all variants must agree bit for bit).
-Run with RNB_NO_GRAPH=1 so that forward() launches the kernels directly."""
+"""GPU: A/B harness used for the stem kernel's epilogue variants (an RNB_STEM_EPI switch read per launch; the variants
+themselves were measured slower and removed from stem_tc.cu — profiles/stem_r2.md section 3 keeps the numbers): per-launch
+time of the stem from the un-graphed event profile and a checksum of the logits (all variants agreed bit for bit).
+Run with RNB_NO_GRAPH=1 so that forward() launches the kernels directly; with one variant it is a stem timer."""
 import hashlib
 import os
 import sys
