@@ -81,13 +81,49 @@ __global__ void __launch_bounds__(128, 1) k(const uint8_t* g, int N, int mma_ite
     if (warp == 2) { __syncwarp(); tmem_dealloc(tb, 512); }
 }
 
-static void run(const uint8_t* g, int N, int mma_iters, int copies, int lsu, long long* out) {
+// copies only, `nst` stages of `stage` bytes in flight (is the rate above a latency limit: bytes in flight / round trip?)
+__global__ void __launch_bounds__(128, 1) kc(const uint8_t* g, int nst, int stage, int copies, long long* out) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* R = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    __shared__ uint64_t cbar[16];
+    if (threadIdx.x == 0) { for (int i = 0; i < 16; ++i) mbar_init(&cbar[i], 1); fence_mbar_init(); }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint8_t* src = g + static_cast<size_t>(blockIdx.x) * 65536;
+        long long t0 = clock64();
+        if (elect_one()) {
+            for (int c = 0; c < copies; ++c) {
+                const int s = c % nst;
+                if (c >= nst) mbar_wait(&cbar[s], ((c / nst) - 1) & 1);
+                mbar_expect_tx(&cbar[s], stage);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(R + s * stage)), "l"(src + (s * stage) % 65536), "r"(stage), "r"(smem_u32(&cbar[s])) : "memory");
+            }
+            for (int c = copies; c < copies + nst; ++c) { const int s = c % nst; mbar_wait(&cbar[s], ((c / nst) - 1) & 1); }
+        }
+        __syncwarp();
+        long long t1 = clock64();
+        if (elect_one() && blockIdx.x == 0) out[0] = t1 - t0;
+    }
+}
+static void runc(const uint8_t* g, int nst, int stage, long long* out) {
+    const int copies = (64 << 20) / stage / 16;
     cudaMemset(out, 0, 32);
-    k<<<148, 128, 1024 + 65536 + NST * STAGE + 16384>>>(g, N, mma_iters, copies, lsu, out);
+    kc<<<148, 128, 1024 + 200 * 1024>>>(g, nst, stage, copies, out);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h = 0;
+    cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
+    printf("copies only: %2d stages x %5d B = %3d KB in flight: %-8s %6.1f B/clk/SM\n", nst, stage, nst * stage / 1024,
+           cudaGetErrorString(e), double(copies) * stage / double(h));
+}
+
+static void run(const uint8_t* g, int N, int mma_iters, int copies, int lsu, long long* out, int grid = 148) {
+    cudaMemset(out, 0, 32);
+    k<<<grid, 128, 1024 + 65536 + NST * STAGE + 16384>>>(g, N, mma_iters, copies, lsu, out);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[4] = {0, 0, 0, 0};
     cudaMemcpy(h, out, 32, cudaMemcpyDeviceToHost);
-    printf("N=%3d mma=%5d copies=%5d lsu=%6d: %-8s", N, mma_iters, copies, lsu, cudaGetErrorString(e));
+    printf("grid=%3d N=%3d mma=%5d copies=%5d lsu=%6d: %-8s", grid, N, mma_iters, copies, lsu, cudaGetErrorString(e));
     if (mma_iters) printf("  %6.1f clk per MMA (floor %d)", double(h[0]) / mma_iters, N / 2);
     if (copies) printf("  copies %5.1f B/clk/SM", double(copies) * STAGE / double(h[1]));
     if (lsu) printf("  lsu %5.1f clk per st+ld pair", double(h[2]) / lsu);
@@ -110,5 +146,11 @@ int main() {
         run(g, N, 8192, 0, 8192 * 4, out);
         run(g, N, 8192, N == 64 ? 1024 : N == 128 ? 1536 : 3072, 8192 * 2, out);
     }
+    cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 200 * 1024);
+    for (int nst : {2, 4, 8, 12}) runc(g, nst, 16384, out);
+    for (int nst : {4, 8, 16}) runc(g, nst, 8192, out);
+    for (int nst : {2, 4, 6}) runc(g, nst, 32768, out);
+    // is the 65 B/clk an SM ingest limit or an aggregate (L2 / crossbar) one? fewer SMs pulling:
+    for (int grid : {8, 16, 37, 74, 111, 148}) run(g, 128, 0, 4096, 0, out, grid);
     return 0;
 }
