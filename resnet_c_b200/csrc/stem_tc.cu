@@ -29,12 +29,14 @@
 // TMEM alloc, warps 4..11 epilogue: vertical max in registers, bias + ReLU, horizontal max through shared memory,
 // coalesced NHWC BF16 stores of the pooled row. TMEM: 4 pair slots x 128 columns.
 #include <cstdint>
+#include <cstdio>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "internal.h"
 #include "sm100_ptx.cuh"
 #include "stem_tc_common.cuh"
+#include "tensormap.h"
 
 namespace rnb {
 
@@ -187,6 +189,12 @@ __device__ __forceinline__ void stem_fill_chunk_f32(uint32_t dst, const float* _
         return;
     }
     const float* img = x + (1LL * b * 3 * IMG + (4 * c - 4)) * IMG;
+    // the chunk this warp fills next (three chunks on) is requested into L2 now: a loader warp has one chunk of loads
+    // in flight, and at HBM latency that was not enough once the MMA side stopped being the bottleneck
+    if (lane < 3 && c + 3 <= PAIRS) {
+        const float* nxt = img + 1LL * lane * IMG * IMG + 12 * IMG;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"(4 * IMG * 4) : "memory");
+    }
     float4 v[7][3];
 #pragma unroll
     for (int it = 0; it < 7; ++it) {
@@ -307,9 +315,7 @@ stem_tc_kernel(const void* __restrict__ xin, const uint8_t* __restrict__ wk,
         for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
             const int cn_after = st.cn + st.new_chunks();
             const int j = st.step;
-            StemSteps nx = st;
-            nx.next();
-            const bool seg_ends = nx.done() || nx.seg_start();
+            const bool seg_ends = st.seg_ends();
             for (int m = cn_after - 3; m < cn_after; ++m) mbar_wait(&ch_full[m & (NCH - 1)], (m / NCH) & 1);
             mbar_wait(&acc_empty[j & (NSLOT - 1)], ((j / NSLOT) & 1) ^ 1);
             tc_fence_after();
@@ -447,6 +453,331 @@ stem_tc_kernel(const void* __restrict__ xin, const uint8_t* __restrict__ wk,
     }
 }
 
+
+// ===================================================================================================================
+// Third form ("transposed", FORM 1): the WEIGHTS are the A operand and live in TMEM, the image rows are the B operand.
+//   D[(conv row a | b, oc)][ow] (+)= [W_t ; W_t-2][128 x 16] . row_t[112 x 16]^T      (tcgen05.mma, A from TMEM)
+// * the tensor core fetches only the 112 x 32-byte image slice per MMA from shared memory (28 wavefronts instead of
+//   64): the shared-memory data pipe that bounded the second form (operand fetch 52 % + LSU 46 %) is half empty and the
+//   kernel is paced by the MMA stream itself — 18 MMAs x 56 clocks per pair (no special cases: a conv row that does not
+//   read input row t has zero weights in its half of A);
+// * TMEM lane = 32q + 16*rowsel + ocl (channel 16q + ocl), TMEM column = output column: a thread holds one conv row of
+//   one channel, so the horizontal 3-tap max is plain register arithmetic; the vertical max needs the partner lane
+//   (lane ^ 16: the pair's other conv row) — values are exchanged AFTER bias + ReLU + BF16 rounding (all monotone, so
+//   they commute with max), two pooled columns per register: 7 shuffles per thread and pair;
+// * the pooled row is staged as a plain [56][64] BF16 image and leaves by ONE bulk copy per pair.
+constexpr int STEM_T_THREADS = STEM_TC_THREADS + 32;   // + a second MMA issuer (warp 12)
+constexpr int T_NBLK = 18;                 // A blocks: input row t = 0..8 of the pair x K step i
+constexpr int T_NSLOT = 3;                 // TMEM: D slots of 112 columns at 0, 112, 224; weights at 336 .. 479
+constexpr int T_D_PITCH = 112;
+constexpr int T_A_COL = T_NSLOT * T_D_PITCH;
+constexpr int T_WSTAGE_BYTES = 28 * 32;    // one epilogue warp's block: [28 pooled columns][16 ch] bf16
+constexpr int T_STAGE_BYTES = 8 * T_WSTAGE_BYTES;   // x 2 buffers
+constexpr int T_NBAR = 2 * NCH + 2 * T_NSLOT;
+constexpr int STEM_T_SMEM = 1024 + RING_BYTES + 2 * T_STAGE_BYTES + T_NBAR * 8 + 16;
+constexpr size_t T_W_BYTES = static_cast<size_t>(T_NBLK) * 128 * 8 * 4;
+
+// w [64][3][7][7] fp32 + BN -> wt [block = 2t + i][m][8] u32: row m = 32q + 16*rowsel + ocl holds, as 16 BF16 (two per
+// word, low half first), window pixels 4i .. 4i+3 x 4 channels of filter row t (rowsel 0, t <= 6) or t - 2 (rowsel 1,
+// t >= 2) of output channel 16q + ocl; everything else is zero.
+__global__ void stem_pack_weights_t_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
+                                           const float* __restrict__ bn_v, uint32_t* __restrict__ wt) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= T_NBLK * 128 * 8) return;
+    const int col = idx & 7, m = (idx >> 3) & 127, blk = idx >> 10;
+    const int t = blk >> 1, i = blk & 1;
+    const int q = m >> 5, rs = (m >> 4) & 1, oc = 16 * q + (m & 15);
+    const int kh = rs ? t - 2 : t;
+    const bool row_ok = rs ? t >= 2 : t <= 6;
+    double scale = 1.0;
+    if (bn_w) scale = static_cast<double>(bn_w[oc]) / sqrt(static_cast<double>(bn_v[oc]) + 1e-5);
+    float v[2];
+    for (int h = 0; h < 2; ++h) {
+        const int e16 = 2 * col + h, pix = 4 * i + (e16 >> 2), c = e16 & 3, kw = pix - 1;
+        v[h] = 0.f;
+        if (row_ok && kw >= 0 && kw < 7 && c < 3)
+            v[h] = static_cast<float>(static_cast<double>(w[((oc * 3 + c) * 7 + kh) * 7 + kw]) * scale);
+    }
+    wt[idx] = pack_bf16x2(v[0], v[1]);
+}
+
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+                 :
+                 : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(STEM_T_THREADS, 1)
+stem_tc_t_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restrict__ xin,
+                 const uint32_t* __restrict__ wt, const float* __restrict__ bias, int B, int dbg, long long* dbg_out) {
+    using namespace ptx;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* stage = smem;                                // 2 x T_STAGE_BYTES (7 KB each: 1024-byte aligned, 128 B swizzle)
+    uint8_t* ring = smem + 2 * T_STAGE_BYTES;             // NCH chunks + slack
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + RING_BYTES);
+    uint64_t* ch_full = bars;                      // [NCH]
+    uint64_t* ch_empty = bars + NCH;               // [NCH]
+    uint64_t* acc_full = bars + 2 * NCH;           // [T_NSLOT]
+    uint64_t* acc_empty = bars + 2 * NCH + T_NSLOT;  // [T_NSLOT]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + T_NBAR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_pairs = B * PAIRS;
+    const int ppc = num_pairs / static_cast<int>(gridDim.x), prem = num_pairs % static_cast<int>(gridDim.x);
+    const int p_begin = static_cast<int>(blockIdx.x) * ppc + min(static_cast<int>(blockIdx.x), prem);
+    const int p_end = p_begin + ppc + (static_cast<int>(blockIdx.x) < prem ? 1 : 0);
+
+    if (threadIdx.x == 32) {
+        for (int i = 0; i < NCH; ++i) {
+            mbar_init(&ch_full[i], MODE == 0 ? 1 : 32);
+            mbar_init(&ch_empty[i], 2);   // both MMA issuers release every chunk
+        }
+        for (int i = 0; i < T_NSLOT; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], EPI_THREADS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        __syncwarp();
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < RING_BYTES / 16; i += STEM_T_THREADS)   // halo columns, read-past slack
+        reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    if (warp >= 4 && warp < 12) {
+        // weights -> TMEM (constants): the two warps of a lane quarter write nine A blocks each, lane = row m
+        const int q = warp & 3, m = 32 * q + lane;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + T_A_COL;
+        for (int blk = (warp - 4) >> 2; blk < T_NBLK; blk += 2) {
+            const uint4* src = reinterpret_cast<const uint4*>(wt + (blk * 128 + m) * 8);
+            const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+            const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            tmem_st_32x8(lane_base + blk * 8, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    griddep_launch_dependents();
+    griddep_wait();
+
+    if (warp == 0 || (MODE == 1 && (warp == 2 || warp == 3))) {
+        // ===================================================== input: chunks into the ring, in stream order
+        const int widx = warp == 0 ? 0 : warp - 1;
+        for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
+            const int b = st.b(), nnew = st.new_chunks();
+            const int c_first = st.k() + 3 - nnew;
+            for (int i = 0; i < nnew; ++i) {
+                const int n = st.cn + i, c = c_first + i;
+                if (MODE == 1 && (n % 3) != widx) continue;
+                mbar_wait(&ch_empty[n & (NCH - 1)], ((n / NCH) & 1) ^ 1);
+                uint8_t* dst = ring + (n & (NCH - 1)) * CHUNK_BYTES;
+                if (MODE == 0) {
+                    if (elect_one()) {
+                        const uint8_t* src = static_cast<const uint8_t*>(xin) + (1LL * b * PAD_H + 4 * c + 1) * ROW_BYTES;
+                        mbar_expect_tx(&ch_full[n & (NCH - 1)], CHUNK_BYTES);
+                        bulk_copy_g2s(dst, src, CHUNK_BYTES, &ch_full[n & (NCH - 1)]);
+                    }
+                    __syncwarp();
+                } else {
+                    if (!(dbg & 4)) stem_fill_chunk_f32(smem_u32(dst), static_cast<const float*>(xin), b, c, lane);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&ch_full[n & (NCH - 1)]);
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 12) {
+        // ===================================================== MMA issuers: 18 x (M = 128, N = 112, K = 16), A from TMEM
+        // TWO issuing warps take alternate steps. Measured with clock probes on a single issuer (RNB_STEM_DBG=16): per
+        // pair 1117 clocks inside the 18 MMA instructions (the tensor pipe's queue holds about two MMAs, so the
+        // issuer is blocked for the pipe's 1008 clocks) and then 430 clocks of its own latency — two barrier polls of
+        // ~100 clocks each even when the barrier is complete, commits, loop — during which the pipe ran dry: 60 %
+        // active. With two issuers one warp's polls overlap the other warp's MMAs.
+        // Chunks: a warp releases (tcgen05.commit on ch_empty, count 2) every chunk older than the first chunk of ITS
+        // next step, including chunks only the other warp reads; the two warps are never more than two steps apart
+        // (three accumulator slots), so a release cannot reach into the previous round of the ring.
+        const int X = warp == 1 ? 0 : 1;
+        constexpr uint32_t idesc = umma_instr_desc(UMMA_FMT_BF16, 128, 112);
+        const uint64_t b_desc0 = umma_smem_desc(smem_u32(ring), 16, 128, UMMA_LAYOUT_NONE);
+        int rel = 0;   // next chunk this warp has to release
+        long long tw_ch = 0, tw_acc = 0, t_issue = 0, t_rest = 0, t_prev = clock64();
+        for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
+            const int j = st.step;
+            if ((j & 1) != X) continue;
+            const int cn_after = st.cn + st.new_chunks();
+            // first chunk of this warp's next step (j + 2), or the total number of chunks if there is none
+            StemSteps la = st;
+            la.next();
+            int rel_end = la.cn;
+            if (!la.done()) {
+                la.next();
+                rel_end = la.done() ? la.cn : la.cn + la.new_chunks() - 3;
+            }
+            long long t0 = clock64();
+            t_rest += t0 - t_prev;
+            for (int m = cn_after - 3; m < cn_after; ++m) mbar_wait(&ch_full[m & (NCH - 1)], (m / NCH) & 1);
+            long long t1 = clock64();
+            mbar_wait(&acc_empty[j % T_NSLOT], ((j / T_NSLOT) & 1) ^ 1);
+            long long t2 = clock64();
+            tw_ch += t1 - t0;
+            tw_acc += t2 - t1;
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d = tmem_base + (j % T_NSLOT) * T_D_PITCH;
+                const uint32_t a0 = tmem_base + T_A_COL;
+                // input row t of the pair = row (1 + t) & 3 of chunk cn_after - 3 + (1 + t) / 4
+                const uint64_t c0 = b_desc0 + static_cast<uint64_t>((((cn_after - 3) & (NCH - 1)) * CHUNK_BYTES) >> 4);
+                const uint64_t c1 = b_desc0 + static_cast<uint64_t>((((cn_after - 2) & (NCH - 1)) * CHUNK_BYTES) >> 4);
+                const uint64_t c2 = b_desc0 + static_cast<uint64_t>((((cn_after - 1) & (NCH - 1)) * CHUNK_BYTES) >> 4);
+                if (!(dbg & 2)) {
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const uint64_t row = (t < 3 ? c0 : t < 7 ? c1 : c2) + static_cast<uint64_t>((((1 + t) & 3) * ROW_BYTES) >> 4);
+                        mma_f16_ts(d, a0 + 16 * t, row, idesc, t != 0);
+                        mma_f16_ts(d, a0 + 16 * t + 8, row + 2, idesc, 1);
+                    }
+                }
+                tc_commit(&acc_full[j % T_NSLOT]);
+                for (int n = rel; n < rel_end; ++n) tc_commit(&ch_empty[n & (NCH - 1)]);
+            }
+            rel = rel_end;
+            __syncwarp();
+            t_prev = clock64();
+            t_issue += t_prev - t2;
+        }
+        if ((dbg & 16) && dbg_out && blockIdx.x == 0 && lane == 0 && X == 0) {
+            dbg_out[0] = tw_ch; dbg_out[1] = tw_acc; dbg_out[2] = t_issue; dbg_out[3] = t_rest; dbg_out[4] = (p_end - p_begin) / 2;
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===================================================== epilogue
+        // warp quarter q = warp & 3: lanes 0..15 = conv row a (2k), lanes 16..31 = conv row b (2k+1) of channels
+        // 16q .. 16q+15; the two warps of a quarter split the pooled columns (h = 0: 0..27, h = 1: 28..55).
+        // The eight warps never meet: each stages its own [28 pooled columns][16 channels] block (32-byte rows: the
+        // 32-bit stores of a warp fall into 32 different banks) and sends it off with its own TMA store; the next
+        // pair's accumulators are requested as soon as this pair's have been reduced to 14 registers.
+        const int q = warp & 3, h = (warp - 4) >> 2;
+        const int rs = lane >> 4, oc = 16 * q + (lane & 15);
+        const float bias_c = __ldg(bias + oc);
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (h ? 48 : 0);
+        uint8_t* const stg = stage + (warp - 4) * (2 * T_WSTAGE_BYTES);
+        uint32_t carry[7];  // conv row 2k-1 (the previous pair's row b), this lane's 14 pooled columns, after bias + ReLU
+#pragma unroll
+        for (int u = 0; u < 7; ++u) carry[u] = 0u;
+        int vb = 0;
+        uint32_t c0[32], c1[32];   // 64 output columns of this lane's conv row: 0..63 (h = 0) or 48..111 (h = 1)
+        StemSteps st(p_begin, p_end);
+        if (!st.done()) {
+            mbar_wait(&acc_full[0], 0);
+            tc_fence_after();
+            tmem_ld_32x32(lane_addr, c0);
+            tmem_ld_32x32(lane_addr + 32, c1);
+        }
+        while (!st.done()) {
+            const int b = st.b(), k = st.k(), j = st.step;
+            const bool warm = st.warm;
+            st.next();
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&acc_empty[j % T_NSLOT]);
+            auto col = [&](int i) { return __uint_as_float(i < 32 ? c0[i] : c1[i - 32]); };
+            // horizontal 3-tap max, bias, ReLU, BF16: pooled column 28h + jj reads columns 2jj-1, 2jj, 2jj+1 (+8 for h = 1)
+            uint32_t yp[14];
+            if (h == 0) {   // (warp-uniform: two fully unrolled bodies with compile-time register indices)
+#pragma unroll
+                for (int jj = 0; jj < 28; jj += 2) {
+                    const int i0 = 2 * jj, i1 = i0 + 2;
+                    const float y0 = fmaxf(fmaxf(col(i0), col(i0 + 1)), i0 > 0 ? col(i0 - 1) : col(i0)) + bias_c;
+                    const float y1 = fmaxf(fmaxf(col(i1), col(i1 + 1)), col(i1 - 1)) + bias_c;
+                    yp[jj >> 1] = pack_relu_bf16x2(y0, y1);
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 28; jj += 2) {
+                    const int i0 = 2 * jj + 8, i1 = i0 + 2;
+                    const float y0 = fmaxf(fmaxf(col(i0), col(i0 + 1)), col(i0 - 1)) + bias_c;
+                    const float y1 = fmaxf(fmaxf(col(i1), col(i1 + 1)), col(i1 - 1)) + bias_c;
+                    yp[jj >> 1] = pack_relu_bf16x2(y0, y1);
+                }
+            }
+            if (!st.done()) {   // the next pair's accumulators
+                const int jn = st.step;
+                mbar_wait(&acc_full[jn % T_NSLOT], (jn / T_NSLOT) & 1);
+                tc_fence_after();
+                tmem_ld_32x32(lane_addr + (jn % T_NSLOT) * T_D_PITCH, c0);
+                tmem_ld_32x32(lane_addr + (jn % T_NSLOT) * T_D_PITCH + 32, c1);
+            }
+            if (k == 0) {
+#pragma unroll
+                for (int u = 0; u < 7; ++u) carry[u] = 0u;   // no conv row above the image (ReLU output is >= 0)
+            }
+            // vertical max with the partner lane (the pair's other conv row): lanes 0..15 finish pooled columns
+            // 28h + 0..13, lanes 16..31 columns 28h + 14..27; each lane sends the half the other one finishes
+            uint32_t res[7];
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                const uint32_t mine = rs ? yp[7 + u] : yp[u];
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, rs ? yp[u] : yp[7 + u], 16);
+                const uint32_t rowb = rs ? mine : other;
+                res[u] = bf16x2_max(bf16x2_max(mine, other), carry[u]);
+                carry[u] = rowb;
+            }
+            if (warm) continue;  // the pair before this CTA's range: only its second conv row was wanted
+            if (lane == 0) tma_store_wait_read<1>();   // the store that last read this staging buffer (two pairs ago)
+            __syncwarp();
+            {
+                // channel pairs: the even lane of two neighbouring channels takes pooled column 2u of both, the odd
+                // lane column 2u+1 — one 32-bit store each
+                const int odd = lane & 1;
+                const uint32_t sbase = smem_u32(stg) + vb * T_WSTAGE_BYTES + (14 * rs + odd) * 32 + ((lane & 15) >> 1) * 4;
+#pragma unroll
+                for (int u = 0; u < 7; ++u) {
+                    const uint32_t recv = __shfl_xor_sync(0xffffffffu, res[u], 1);
+                    const uint32_t word = odd ? __byte_perm(recv, res[u], 0x7632) : __byte_perm(res[u], recv, 0x5410);
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + 2 * u * 32), "r"(word) : "memory");
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tm_out, stg + vb * T_WSTAGE_BYTES, 16 * q, (b * POOL + k) * POOL + 28 * h);
+                tma_store_commit();
+            }
+            vb ^= 1;
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 }  // namespace
 
 bool stem_fused_enabled() {
@@ -455,31 +786,65 @@ bool stem_fused_enabled() {
 }
 
 size_t stem_tc_packed_input_bytes(int B) { return 1ull * B * PAD_H * ROW_BYTES; }
-size_t stem_tc_packed_weight_bytes() { return W_BYTES; }
+// [second form: 28 KB of K-chunk blocks for shared memory][third form: 18 A blocks for TMEM]
+size_t stem_tc_packed_weight_bytes() { return W_BYTES + T_W_BYTES; }
 
 cudaError_t launch_stem_tc_pack_weights(const float* w, const float* bn_w, const float* bn_b,
                                         const float* bn_m, const float* bn_v, void* wk, float* bias,
                                         cudaStream_t s) {
     stem_pack_weights_kernel<<<(28 * 64 * 8 + 255) / 256, 256, 0, s>>>(
         w, bn_w, bn_b, bn_m, bn_v, static_cast<__nv_bfloat16*>(wk), bias);
+    stem_pack_weights_t_kernel<<<(T_NBLK * 128 * 8 + 255) / 256, 256, 0, s>>>(
+        w, bn_w, bn_v, reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(wk) + W_BYTES));
     return cudaGetLastError();
 }
 
 cudaError_t stem_tc_init() {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_T_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_t_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_T_SMEM);
+    return e;
 }
 
 static cudaError_t launch_stem_tc_kernel(int mode, const void* in, const void* wk, const float* bias, void* out, int B,
                                          cudaStream_t s) {
     const int pairs = B * PAIRS;
     const int grid = pairs < num_sms() ? pairs : num_sms();
+    const char* f = getenv("RNB_STEM_FORM");  // 1 (default): weights in TMEM, image rows as the B operand; 0: second form
+    const int form = f ? atoi(f) : 1;
+    const char* dg = getenv("RNB_STEM_DBG");   // timing experiments (wrong results): 1 = no epilogue work, 2 = no MMAs, 4 = no loads
+    const int dbg = dg ? atoi(dg) : 0;
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+    if (form == 1) {
+        const uint32_t* wt = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(wk) + W_BYTES);
+        // output [B*56*56 pooled pixels][64 ch] bf16; one store = 28 pooled pixels x 16 channels (an epilogue warp's block)
+        CUtensorMap tm;
+        {
+            const uint64_t dims[2] = {64, 1ull * B * POOL * POOL}, strides[1] = {128};
+            const uint32_t box[2] = {16, 28};
+            if (make_tiled_nd(&tm, TmDtype::BF16, out, 2, dims, strides, box, false) != 0) return cudaErrorInvalidValue;
+        }
+        static long long* dbg_buf = nullptr;
+        if ((dbg & 16) && !dbg_buf) cudaMalloc(&dbg_buf, 64);
+        cudaError_t e = mode == 0 ? launch_pdl_small(stem_tc_t_kernel<0>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in,
+                                                     wt, bias, B, dbg, dbg_buf)
+                                  : launch_pdl_small(stem_tc_t_kernel<1>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in,
+                                                     wt, bias, B, dbg, dbg_buf);
+        if ((dbg & 16) && e == cudaSuccess) {
+            long long h[5];
+            cudaStreamSynchronize(s);
+            cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "stem issuer (CTA 0, %lld pairs): per pair clocks: wait chunks %.0f, wait acc %.0f, issue+commit %.0f, rest %.0f\n",
+                    h[4], double(h[0]) / h[4], double(h[1]) / h[4], double(h[2]) / h[4], double(h[3]) / h[4]);
+        }
+        return e;
+    }
     if (mode == 0)
         return launch_pdl_small(stem_tc_kernel<0>, dim3(grid), dim3(STEM_TC_THREADS), STEM_SMEM, s, in,
-                                static_cast<const uint8_t*>(wk), bias, static_cast<__nv_bfloat16*>(out), B);
+                                static_cast<const uint8_t*>(wk), bias, o, B);
     return launch_pdl_small(stem_tc_kernel<1>, dim3(grid), dim3(STEM_TC_THREADS), STEM_SMEM, s, in,
-                            static_cast<const uint8_t*>(wk), bias, static_cast<__nv_bfloat16*>(out), B);
+                            static_cast<const uint8_t*>(wk), bias, o, B);
 }
 
 // xp (packed NHWC4 BF16, written by a pack kernel) -> out NHWC bf16 [B,56,56,64]

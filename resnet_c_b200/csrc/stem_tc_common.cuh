@@ -65,18 +65,29 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 // step, or the first pair of an image) brings three new chunks (k, k+1, k+2), every other step one (k+2), and a
 // step reads the last three.
 struct StemSteps {
-    int p, p_end, cn, step;
+    int p, p_end, cn, step, bb, kk;   // (bb, kk) = image and pair-in-image of p, kept incrementally (no divisions per step)
     bool warm;
     __device__ StemSteps(int p_begin, int p_end_)
-        : p(p_begin), p_end(p_end_), cn(0), step(0), warm(p_begin < p_end_ && (p_begin % PAIRS) != 0) {}
+        : p(p_begin), p_end(p_end_), cn(0), step(0), bb(p_begin / PAIRS), kk(p_begin % PAIRS),
+          warm(p_begin < p_end_ && (p_begin % PAIRS) != 0) {}
     __device__ bool done() const { return p >= p_end; }
-    __device__ int b() const { return p / PAIRS; }
-    __device__ int k() const { return p % PAIRS - (warm ? 1 : 0); }
+    __device__ int b() const { return bb; }
+    __device__ int k() const { return kk - (warm ? 1 : 0); }
     __device__ bool seg_start() const { return step == 0 || k() == 0; }
     __device__ int new_chunks() const { return seg_start() ? 3 : 1; }
+    // the next step starts a new segment (another image) or does not exist: this step's chunks all die with it
+    __device__ bool seg_ends() const { return !warm && (p + 1 >= p_end || kk + 1 == PAIRS); }
     __device__ void next() {
         cn += new_chunks();
-        if (warm) warm = false; else ++p;
+        if (warm) {
+            warm = false;
+        } else {
+            ++p;
+            if (++kk == PAIRS) {
+                kk = 0;
+                ++bb;
+            }
+        }
         ++step;
     }
 };

@@ -201,9 +201,7 @@ stem_tc_split_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wk
         for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
             const int cn_after = st.cn + st.new_chunks();
             const int j = st.step;
-            StemSteps nx = st;
-            nx.next();
-            const bool seg_ends = nx.done() || nx.seg_start();
+            const bool seg_ends = st.seg_ends();
             for (int m = cn_after - 3; m < cn_after; ++m) mbar_wait(&ch_full[m % NCH], (m / NCH) & 1);
             mbar_wait(&acc_empty[j & (NSLOT - 1)], ((j / NSLOT) & 1) ^ 1);
             tc_fence_after();

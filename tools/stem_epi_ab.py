@@ -12,15 +12,16 @@ import torch  # noqa: E402
 from resnet_c_b200 import engine, weights  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ["0", "1", "2", "3"]
+variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ["0", "1"]
+switch = sys.argv[3] if len(sys.argv) > 3 else "RNB_STEM_FORM"   # a switch the library reads per launch
 m = engine.ResNet("resnet50", weights.cached_weights_dir("resnet50", 0, True), dtype="bf16", max_batch=B)
 x = weights.synthetic_images(B).cuda()
 logits, top1 = m.forward(x)
 for rep in range(2):
     for v in variants:
-        os.environ["RNB_STEM_EPI"] = v
+        os.environ[switch] = v
         m.forward(x, logits, top1)
         torch.cuda.synchronize()
         sha = hashlib.sha256(logits.cpu().numpy().tobytes()).hexdigest()[:12]
         prof = m.profile(x, iters=5)
-        print(f"epi {v}: stem launches {prof[0]['ms'] * 1e3:.1f} + {prof[1]['ms'] * 1e3:.1f} us, logits {sha}", flush=True)
+        print(f"{switch}={v}: stem launches {prof[0]['ms'] * 1e3:.1f} + {prof[1]['ms'] * 1e3:.1f} us, logits {sha}", flush=True)
