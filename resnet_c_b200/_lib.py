@@ -7,11 +7,13 @@ compute call fails loudly when there is no B200 — there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import re
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-LIB_PATH = Path(__file__).resolve().parent / "librnb.so"
+# RNB_LIB: another build of the same C ABI (A/B runs of two library versions on one box, tools/ab_lib.sh)
+LIB_PATH = Path(os.environ["RNB_LIB"]).resolve() if os.environ.get("RNB_LIB") else Path(__file__).resolve().parent / "librnb.so"
 HEADER_PATH = ROOT / "include" / "rnb.h"
 
 RNB_OK = 0

@@ -1,33 +1,38 @@
 // stem_tc.cu — the network stem on tcgen05 tensor cores (BF16 path):
-//   conv 7x7/2 pad 3 (3 -> 64) + folded BN + ReLU + max-pool 3x3/2 pad 1, fused in ONE kernel,
+//   conv 7x7/2 pad 3 (3 -> 64) + folded BN + ReLU + max-pool 3x3/2 pad 1, fused in ONE kernel that reads the FP32 image,
 // replacing conv2dForwardKernel + batchNorm2dForwardKernel + reluForwardKernel + maxPool2dKernel as
 // chained at /root/reference/cuda/inference/main.cu:176-192 (on CUDA cores the stem is
-// FP32-compute-bound, 60 GFLOP per 256-batch; on tensor cores it is a ~0.1 ms memory pass).
+// FP32-compute-bound, 60 GFLOP per 256-batch; on tensor cores it is a ~0.1 ms pass).
 //
-// Trick: no im2col is ever built. The image lives in shared memory as zero-padded NHWC4 BF16 rows ("RGB0" pixels of
-// 8 bytes, 232 pixels per row: 4 + 224 + 4). Two adjacent pixels form a 16-byte "super-pixel"; because the conv
-// stride is 2, the window of output column ow starts at super-pixel ow and spans 4 of them (a zero-weight tap + the
-// 7 real ones). So for a fixed filter row kh the A operand A[ow][j*8+e] = row[(ow+j)*8 + e] is a Hankel matrix that a
-// NO-SWIZZLE K-major UMMA descriptor reads directly from the contiguous row: 16 bytes between consecutive M rows
-// (SBO = 128 per 8 rows) and 16 bytes between consecutive K core matrices (LBO = 16) — the descriptor simply
-// overlaps itself. One conv row (128 lanes, 112 valid) x 64 channels accumulates over 7 kh x 2 MMAs (K = 16 each).
+// No im2col is ever built. The image lives in shared memory as zero-padded NHWC4 BF16 rows ("RGB0" pixels of 8 bytes,
+// 232 pixels per row: 4 + 224 + 4). Two adjacent pixels form a 16-byte "super-pixel"; because the conv stride is 2,
+// the window of output column ow starts at super-pixel ow and spans 4 of them (a zero-weight tap + the 7 real ones).
+// For a fixed filter row the operand X[ow][j*8+e] = row[(ow+j)*8 + e] is a Hankel matrix that a NO-SWIZZLE K-major
+// UMMA descriptor reads directly from the contiguous row: 16 bytes between consecutive rows (SBO = 128 per 8 rows)
+// and 16 bytes between consecutive K core matrices (LBO = 16) — the descriptor simply overlaps itself.
 //
-// Round 2 (second form). tools/mma_bench.cu measured what one of these MMAs costs: max(N / 2, 32 + N / 4) clocks —
-// the tensor pipe's N / 2 or the shared-memory fetch of its operands (128 B per clock: 32 wavefronts for the 128 x 16
-// A slice + N / 4 for B), whatever the layout. At N = 64 that is 48 clocks instead of 32: the old kernel (one conv
-// row per MMA) was bound by the operand fetch. So
-//  * work unit = a PAIR of conv rows (2k, 2k+1) = one pooled row k; an input row that both conv rows read (5 of the
-//    9 a pair touches) is fetched ONCE by an N = 128 MMA whose B operand is [W_kh | W_kh-2] and whose accumulator
-//    spans both rows' TMEM columns: 19 MMAs / 1056 clocks per pair instead of 28 / 1344;
-//  * the input streams through a ring of 4-row chunks (8 x 7.25 KB) instead of 19-row units, so every image row is
-//    brought in once, and — MODE 1 — the loader warps build the NHWC4 BF16 rows in shared memory straight from the
-//    caller's FP32 NCHW tensor: the layout pre-pass (stem_pack_kernel, 266 MB of HBM traffic per 256 images) is
-//    gone from the float path (it remains for uint8 input, which feeds the same kernel through bulk copies: MODE 0);
-//  * the pooled row's third conv row (2k - 1) is the previous pair's second row, carried in registers; a CTA whose
-//    contiguous range of pairs starts inside an image first computes the pair before its range to obtain it.
-// Warp roles: warps 0, 2, 3 loaders (MODE 1) / warp 0 bulk-copy producer (MODE 0), warp 1 MMA issuer, warp 2 also
-// TMEM alloc, warps 4..11 epilogue: vertical max in registers, bias + ReLU, horizontal max through shared memory,
-// coalesced NHWC BF16 stores of the pooled row. TMEM: 4 pair slots x 128 columns.
+// Form of the kernel (the third of round 2; profiles/stem_r2.md has the measurements behind every step):
+//  * work unit = a PAIR of conv rows (2k, 2k+1) = one pooled row k. The WEIGHTS are the A operand and live in TMEM,
+//    the image rows are the B operand:  D[(conv row a | b, oc)][ow] (+)= [W_t ; W_t-2][128 x 16] . row_t[112 x 16]^T
+//    for the 9 input rows t of the pair and the 2 K steps: 18 x (M = 128, N = 112, K = 16) at the tensor pipe's floor
+//    of 56 clocks (tools/mma_bench.cu: an MMA costs max(N/2, operand fetch) and only the 28 wavefronts of the image
+//    slice come from shared memory; the first two forms fetched 48-64 per MMA and were bound by that pipe). A conv
+//    row that does not read input row t has zero weights in its half of A, so there are no special cases.
+//  * the input streams through a ring of eight 4-row chunks; three loader warps build the NHWC4 BF16 rows straight
+//    from the caller's FP32 NCHW tensor (MODE 1; an L2 prefetch runs three chunks ahead) — there is no layout pre-pass.
+//    uint8 input keeps its normalising pre-pass and feeds the same kernel through bulk copies (MODE 0).
+//  * TWO MMA issuer warps take alternate pairs: the tensor pipe's queue holds about two MMAs, and one issuer's barrier
+//    polls and bookkeeping (~430 clocks per pair) left the pipe dry 40 % of the time.
+//  * TMEM lane = 32q + 16*rowsel + ocl (channel 16q + ocl), TMEM column = output column: a thread holds one conv row
+//    of one channel, so the horizontal 3-tap max is register arithmetic; the vertical max needs the partner lane
+//    (lane ^ 16) — values are exchanged AFTER bias + ReLU + BF16 rounding (monotone, they commute with max), two
+//    pooled columns per register: 7 shuffles per thread and pair. The pooled row's third conv row (2k - 1) is the
+//    previous pair's second row, carried in registers; a CTA whose contiguous range of pairs starts inside an image
+//    first computes the pair before its range to obtain it.
+//  * the eight epilogue warps never meet: each stages its [28 pooled columns][16 channels] block and sends it off with
+//    its own TMA store; the next pair's accumulators are requested as soon as this pair's are reduced.
+// Warps: 0, 2, 3 loaders (MODE 1) / 0 bulk-copy producer (MODE 0); 1 and 12 MMA issuers; 2 also TMEM alloc; 4..11
+// epilogue. TMEM: three accumulator slots of 112 columns + 144 columns of weights.
 #include <cstdint>
 #include <cstdio>
 #include <cuda_bf16.h>
@@ -45,13 +50,8 @@ namespace {
 using namespace stemtc;
 
 constexpr int NCH = 8;                // ring depth in chunks; pair k reads chunks k, k+1, k+2
-constexpr int RING_BYTES = NCH * CHUNK_BYTES + 512;  // + read-past slack (lanes 112..127 read into the next row)
-constexpr int W_BYTES = 28 * 1024;    // [j][pos(kh)][64 oc][8 e] bf16
-constexpr int VBUF_BYTES = 112 * 128; // [ow][64 ch] bf16, 16-byte chunks XOR-swizzled by (ow & 7)
-constexpr int NBAR = 2 * NCH + 2 * NSLOT;
-constexpr int STEM_SMEM = 1024 + RING_BYTES + W_BYTES + 2 * VBUF_BYTES + NBAR * 8 + 16;
+constexpr int RING_BYTES = NCH * CHUNK_BYTES + 512;  // + slack
 constexpr int EPI_THREADS = 256;                 // 8 epilogue warps
-constexpr int STEM_TC_THREADS = 128 + EPI_THREADS;
 
 // x [B,3,224,224] fp32 -> xp [B][235][232][4] bf16, zero border and zero 4th channel.
 // One thread per group of 4 padded pixels (PAD_W = 232 = 58 groups): interior groups read one float4
@@ -156,29 +156,6 @@ __global__ void u8_hwc_to_f32_nchw_kernel(const uint8_t* __restrict__ x, float* 
     }
 }
 
-// w [64][3][7][7] fp32 + BN -> wk [j][wpos(kh)][oc][e] bf16: K chunk j of filter row kh holds window pixels
-// p = 2j, 2j+1 (p = kw + 1; the window of output column ow starts at padded pixel 2*ow, one pixel left of tap 0),
-// e = (p - 2j)*4 + c. p = 0 and c = 3 are zero. bias[oc] = folded BN shift.
-__global__ void stem_pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
-                                         const float* __restrict__ bn_b, const float* __restrict__ bn_m,
-                                         const float* __restrict__ bn_v, __nv_bfloat16* __restrict__ wk,
-                                         float* __restrict__ bias) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 28 * 64 * 8) return;
-    const int e = i & 7, oc = (i >> 3) & 63, chunk = i >> 9;
-    const int kh = chunk >> 2, j = chunk & 3;
-    const int kw = 2 * j + (e >> 2) - 1, c = e & 3;
-    double scale = 1.0, shift = 0.0;
-    if (bn_w) {
-        scale = static_cast<double>(bn_w[oc]) / sqrt(static_cast<double>(bn_v[oc]) + 1e-5);
-        shift = static_cast<double>(bn_b[oc]) - static_cast<double>(bn_m[oc]) * scale;
-    }
-    float v = 0.f;
-    if (kw >= 0 && kw < 7 && c < 3) v = static_cast<float>(static_cast<double>(w[((oc * 3 + c) * 7 + kh) * 7 + kw]) * scale);
-    wk[((j * 7 + wpos(kh)) * 64 + oc) * 8 + e] = __float2bfloat16_rn(v);
-    if (chunk == 0 && e == 0) bias[oc] = static_cast<float>(shift);
-}
-
 // One ring chunk (image rows 4c-4 .. 4c-1 of image b) built by ONE warp from the FP32 NCHW tensor: 4 rows x 56
 // groups of 4 pixels = 7 groups per lane, all 21 float4 loads in flight, then RGB0 BF16 pixels, 32 bytes per group.
 // Chunks 0 and 57 lie outside the image (zero rows). The 32-byte halo columns on either side are never written
@@ -222,251 +199,7 @@ __device__ __forceinline__ void stem_fill_chunk_f32(uint32_t dst, const float* _
     }
 }
 
-// MODE 0: input = the packed NHWC4 BF16 tensor xp (bulk copies); MODE 1: input = FP32 NCHW x (loader warps).
-template <int MODE>
-__global__ void __launch_bounds__(STEM_TC_THREADS, 1)
-stem_tc_kernel(const void* __restrict__ xin, const uint8_t* __restrict__ wk,
-               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B) {
-    using namespace ptx;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~static_cast<uintptr_t>(1023));
-    uint8_t* ring = smem;                                 // NCH chunks + slack
-    uint8_t* wsm = smem + RING_BYTES;                     // W_BYTES
-    uint8_t* vbuf = wsm + W_BYTES;                        // 2 x VBUF_BYTES
-    uint64_t* bars = reinterpret_cast<uint64_t*>(vbuf + 2 * VBUF_BYTES);
-    uint64_t* ch_full = bars;                   // [NCH]
-    uint64_t* ch_empty = bars + NCH;            // [NCH]
-    uint64_t* acc_full = bars + 2 * NCH;        // [NSLOT]
-    uint64_t* acc_empty = bars + 2 * NCH + NSLOT;  // [NSLOT]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + NBAR);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_pairs = B * PAIRS;
-    // Each CTA takes a CONTIGUOUS range of pairs: consecutive pairs of an image share two of their three input
-    // chunks and the conv row between them.
-    const int ppc = num_pairs / static_cast<int>(gridDim.x), prem = num_pairs % static_cast<int>(gridDim.x);
-    const int p_begin = static_cast<int>(blockIdx.x) * ppc + min(static_cast<int>(blockIdx.x), prem);
-    const int p_end = p_begin + ppc + (static_cast<int>(blockIdx.x) < prem ? 1 : 0);
-
-    if (threadIdx.x == 32) {
-        for (int i = 0; i < NCH; ++i) {
-            mbar_init(&ch_full[i], MODE == 0 ? 1 : 32);
-            mbar_init(&ch_empty[i], 1);
-        }
-        for (int i = 0; i < NSLOT; ++i) {
-            mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], EPI_THREADS);
-        }
-        fence_mbar_init();
-    }
-    if (warp == 2) {
-        __syncwarp();
-        tmem_alloc(tmem_ptr_smem, 512);
-        tmem_relinquish();
-    }
-    // weights -> smem (28 KB, once per CTA); zero the ring (halo columns, read-past slack)
-    for (int i = threadIdx.x; i < W_BYTES / 16; i += STEM_TC_THREADS)
-        reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(wk) + i);
-    for (int i = threadIdx.x; i < RING_BYTES / 16; i += STEM_TC_THREADS)
-        reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async_smem();  // generic-proxy writes above are read by the tensor core (async proxy)
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    // PDL: the prologue above (barriers, TMEM, weights — constants) overlaps the tail of the previous kernel, and
-    // the first conv kernel's prologue overlaps this kernel's tail
-    griddep_launch_dependents();
-    griddep_wait();
-
-    if (warp == 0 || (MODE == 1 && (warp == 2 || warp == 3))) {
-        // ===================================================== input: chunks into the ring, in stream order
-        const int widx = warp == 0 ? 0 : warp - 1;  // loader index 0..2 (MODE 1: chunk n belongs to loader n % 3)
-        for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
-            const int b = st.b(), nnew = st.new_chunks();
-            const int c_first = st.k() + 3 - nnew;
-            for (int i = 0; i < nnew; ++i) {
-                const int n = st.cn + i, c = c_first + i;
-                if (MODE == 1 && (n % 3) != widx) continue;
-                mbar_wait(&ch_empty[n & (NCH - 1)], ((n / NCH) & 1) ^ 1);
-                uint8_t* dst = ring + (n & (NCH - 1)) * CHUNK_BYTES;
-                if (MODE == 0) {
-                    if (elect_one()) {
-                        // image rows 4c-4 .. 4c-1 = padded rows 4c+1 .. 4c+4
-                        const uint8_t* src = static_cast<const uint8_t*>(xin) + (1LL * b * PAD_H + 4 * c + 1) * ROW_BYTES;
-                        mbar_expect_tx(&ch_full[n & (NCH - 1)], CHUNK_BYTES);
-                        bulk_copy_g2s(dst, src, CHUNK_BYTES, &ch_full[n & (NCH - 1)]);
-                    }
-                    __syncwarp();
-                } else {
-                    stem_fill_chunk_f32(smem_u32(dst), static_cast<const float*>(xin), b, c, lane);
-                    fence_proxy_async_smem();
-                    mbar_arrive(&ch_full[n & (NCH - 1)]);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        constexpr uint32_t idesc64 = umma_instr_desc(UMMA_FMT_BF16, 128, 64);
-        constexpr uint32_t idesc128 = umma_instr_desc(UMMA_FMT_BF16, 128, 128);
-        const uint64_t a_desc0 = umma_smem_desc(smem_u32(ring), 16, 128, UMMA_LAYOUT_NONE);
-        const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 7 * 1024, 128, UMMA_LAYOUT_NONE);
-        for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
-            const int cn_after = st.cn + st.new_chunks();
-            const int j = st.step;
-            const bool seg_ends = st.seg_ends();
-            for (int m = cn_after - 3; m < cn_after; ++m) mbar_wait(&ch_full[m & (NCH - 1)], (m / NCH) & 1);
-            mbar_wait(&acc_empty[j & (NSLOT - 1)], ((j / NSLOT) & 1) ^ 1);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t d0 = tmem_base + (j & (NSLOT - 1)) * 128, d1 = d0 + 64;
-                // input row t of the pair (image row 4k-3+t) = row (1+t) & 3 of chunk cn_after-3 + (1+t)/4;
-                // K step i (+32 bytes) covers window pixels 4i .. 4i+3, weight chunks j = 2i, 2i+1
-                auto arow = [&](int t, int i) {
-                    const int m = cn_after - 3 + ((1 + t) >> 2);
-                    return a_desc0 + static_cast<uint64_t>(
-                                         ((m & (NCH - 1)) * CHUNK_BYTES + ((1 + t) & 3) * ROW_BYTES + 32 * i) >> 4);
-                };
-                auto wblk = [&](int kh, int i) {
-                    return b_desc0 + static_cast<uint64_t>(((2 * i * 7 + wpos(kh)) * 1024) >> 4);
-                };
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        if (t < 2) {                       // first conv row only: kh = t
-                            mma_f16_ss(d0, arow(t, i), wblk(t, i), idesc64, (t | i) != 0);
-                        } else if (t == 2 && i == 0) {     // the second row's accumulator starts here: two N = 64
-                            mma_f16_ss(d0, arow(t, i), wblk(2, i), idesc64, 1);
-                            mma_f16_ss(d1, arow(t, i), wblk(0, i), idesc64, 0);
-                        } else if (t < 7) {                // both rows: [W_t | W_t-2], one fetch of the input row
-                            mma_f16_ss(d0, arow(t, i), wblk(t, i), idesc128, 1);
-                        } else {                           // second conv row only: kh = t - 2
-                            mma_f16_ss(d1, arow(t, i), wblk(t - 2, i), idesc64, 1);
-                        }
-                    }
-                }
-                tc_commit(&acc_full[j & (NSLOT - 1)]);
-                tc_commit(&ch_empty[(cn_after - 3) & (NCH - 1)]);  // the oldest chunk is dead after this pair
-                if (seg_ends) {
-                    tc_commit(&ch_empty[(cn_after - 2) & (NCH - 1)]);
-                    tc_commit(&ch_empty[(cn_after - 1) & (NCH - 1)]);
-                }
-            }
-            __syncwarp();
-        }
-    } else if (warp >= 4) {
-        // ===================================================== epilogue
-        // 8 warps: warp quarter q = warp & 3 owns TMEM lanes 32q..32q+31 (conv columns ow), and the
-        // two warps of a quarter split the 64 channels (half 0 / half 1).
-        // (Measured and dropped, all bit-identical — tools/stem_epi_ab.py, profiles/stem_r2.md: the two channel halves as
-        // independent groups with their own staging rows and named barrier: 116-120 us against 114; the same with the
-        // next pair's TMEM loads issued before the horizontal pass: 131 us; the horizontal max by warp shuffles on an
-        // overlapping lane -> column map (SBO = 112: every warp owns all columns of 14 pooled outputs; no staging, no
-        // barrier): 128 against 120. The MMA issuer waits for TMEM slots, i.e. the epilogue paces the kernel, but its
-        // pace is set by LSU traffic (shared loads, shuffles) that queues behind the tensor core's operand fetch —
-        // ncu: tensor-core wavefronts 52 % + LSU wavefronts 46 % of the shared-memory data pipe — not by a latency
-        // chain that a second group would hide.)
-        const int q = warp & 3;
-        const int half = (warp - 4) >> 2;
-        const int et = q * 32 + lane;                 // conv output column ow == TMEM lane
-        const int etid = threadIdx.x - 128;           // 0..255 within the epilogue group
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32;
-        float bias_r[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) bias_r[i] = __ldg(bias + half * 32 + i);
-        int vb = 0;       // vbuf ping-pong
-        float carry[32];  // conv row 2k-1: the second row of the previous pair
-#pragma unroll
-        for (int i = 0; i < 32; ++i) carry[i] = -INFINITY;
-        for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
-            const int b = st.b(), k = st.k(), j = st.step;
-            const bool warm = st.warm;
-            mbar_wait(&acc_full[j & (NSLOT - 1)], (j / NSLOT) & 1);
-            tc_fence_after();
-            uint32_t ra[32], rb[32];
-            tmem_ld_32x32(lane_addr + (j & (NSLOT - 1)) * 128, ra);
-            tmem_ld_32x32(lane_addr + (j & (NSLOT - 1)) * 128 + 64, rb);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&acc_empty[j & (NSLOT - 1)]);
-            // vertical max over conv rows 2k-1, 2k, 2k+1. max_r(x_r + b) = max_r(x_r) + b; the row above the image
-            // (k = 0) is simply left out (ReLU output is >= 0)
-            float m[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float top = k == 0 ? -INFINITY : carry[i];
-                m[i] = fmaxf(fmaxf(top, __uint_as_float(ra[i])), __uint_as_float(rb[i]));
-                carry[i] = __uint_as_float(rb[i]);
-            }
-            if (warm) continue;  // the pair before this CTA's range: only its second conv row was wanted
-            if (et < 112) {
-                const uint32_t vrow = smem_u32(vbuf) + vb * VBUF_BYTES + et * 128;
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    uint32_t o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)  // bias, ReLU and the BF16 rounding in one convert
-                        o[e] = pack_relu_bf16x2(m[jj * 8 + 2 * e] + bias_r[jj * 8 + 2 * e],
-                                                m[jj * 8 + 2 * e + 1] + bias_r[jj * 8 + 2 * e + 1]);
-                    st_shared_v4(vrow + (((half * 4 + jj) ^ (et & 7)) << 4), o[0], o[1], o[2], o[3]);
-                }
-            }
-            named_bar_sync(1, EPI_THREADS);
-            // horizontal 3-tap max (cols 2pw-1, 2pw, 2pw+1) and coalesced store of the pooled row: 448 16-byte tasks on
-            // 256 threads; all of a thread's loads are issued before the first max (they queue behind the tensor
-            // core's operand fetch)
-            {
-                const uint32_t vr = smem_u32(vbuf) + vb * VBUF_BYTES;
-                __nv_bfloat16* orow = out + ((1LL * b * POOL + k) * POOL) * 64;
-                auto at = [&](int col, int c16) { return vr + col * 128 + ((c16 ^ (col & 7)) << 4); };
-                const int c16 = etid & 7, pw0 = etid >> 3, pw1 = pw0 + 32;
-                const bool two = pw1 < POOL;
-                uint4 a0 = ld_shared_v4(at(2 * pw0, c16));
-                const uint4 r0 = ld_shared_v4(at(2 * pw0 + 1, c16));
-                const uint4 l0 = pw0 > 0 ? ld_shared_v4(at(2 * pw0 - 1, c16)) : a0;
-                uint4 a1 = a0, r1 = a0, l1 = a0;
-                if (two) {
-                    a1 = ld_shared_v4(at(2 * pw1, c16));
-                    r1 = ld_shared_v4(at(2 * pw1 + 1, c16));
-                    l1 = ld_shared_v4(at(2 * pw1 - 1, c16));
-                }
-                a0.x = bf16x2_max(bf16x2_max(a0.x, r0.x), l0.x); a0.y = bf16x2_max(bf16x2_max(a0.y, r0.y), l0.y);
-                a0.z = bf16x2_max(bf16x2_max(a0.z, r0.z), l0.z); a0.w = bf16x2_max(bf16x2_max(a0.w, r0.w), l0.w);
-                *reinterpret_cast<uint4*>(orow + pw0 * 64 + c16 * 8) = a0;
-                if (two) {
-                    a1.x = bf16x2_max(bf16x2_max(a1.x, r1.x), l1.x); a1.y = bf16x2_max(bf16x2_max(a1.y, r1.y), l1.y);
-                    a1.z = bf16x2_max(bf16x2_max(a1.z, r1.z), l1.z); a1.w = bf16x2_max(bf16x2_max(a1.w, r1.w), l1.w);
-                    *reinterpret_cast<uint4*>(orow + pw1 * 64 + c16 * 8) = a1;
-                }
-            }
-            vb ^= 1;
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        __syncwarp();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
-
-
-// ===================================================================================================================
-// Third form ("transposed", FORM 1): the WEIGHTS are the A operand and live in TMEM, the image rows are the B operand.
-//   D[(conv row a | b, oc)][ow] (+)= [W_t ; W_t-2][128 x 16] . row_t[112 x 16]^T      (tcgen05.mma, A from TMEM)
-// * the tensor core fetches only the 112 x 32-byte image slice per MMA from shared memory (28 wavefronts instead of
-//   64): the shared-memory data pipe that bounded the second form (operand fetch 52 % + LSU 46 %) is half empty and the
-//   kernel is paced by the MMA stream itself — 18 MMAs x 56 clocks per pair (no special cases: a conv row that does not
-//   read input row t has zero weights in its half of A);
-// * TMEM lane = 32q + 16*rowsel + ocl (channel 16q + ocl), TMEM column = output column: a thread holds one conv row of
-//   one channel, so the horizontal 3-tap max is plain register arithmetic; the vertical max needs the partner lane
-//   (lane ^ 16: the pair's other conv row) — values are exchanged AFTER bias + ReLU + BF16 rounding (all monotone, so
-//   they commute with max), two pooled columns per register: 7 shuffles per thread and pair;
-// * the pooled row is staged as a plain [56][64] BF16 image and leaves by ONE bulk copy per pair.
-constexpr int STEM_T_THREADS = STEM_TC_THREADS + 32;   // + a second MMA issuer (warp 12)
+constexpr int STEM_T_THREADS = 128 + EPI_THREADS + 32;   // warps 0..3, eight epilogue warps, the second MMA issuer
 constexpr int T_NBLK = 18;                 // A blocks: input row t = 0..8 of the pair x K step i
 constexpr int T_NSLOT = 3;                 // TMEM: D slots of 112 columns at 0, 112, 224; weights at 336 .. 479
 constexpr int T_D_PITCH = 112;
@@ -480,8 +213,10 @@ constexpr size_t T_W_BYTES = static_cast<size_t>(T_NBLK) * 128 * 8 * 4;
 // w [64][3][7][7] fp32 + BN -> wt [block = 2t + i][m][8] u32: row m = 32q + 16*rowsel + ocl holds, as 16 BF16 (two per
 // word, low half first), window pixels 4i .. 4i+3 x 4 channels of filter row t (rowsel 0, t <= 6) or t - 2 (rowsel 1,
 // t >= 2) of output channel 16q + ocl; everything else is zero.
-__global__ void stem_pack_weights_t_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
-                                           const float* __restrict__ bn_v, uint32_t* __restrict__ wt) {
+__global__ void stem_pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
+                                         const float* __restrict__ bn_b, const float* __restrict__ bn_m,
+                                         const float* __restrict__ bn_v, uint32_t* __restrict__ wt,
+                                         float* __restrict__ bias) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= T_NBLK * 128 * 8) return;
     const int col = idx & 7, m = (idx >> 3) & 127, blk = idx >> 10;
@@ -489,8 +224,12 @@ __global__ void stem_pack_weights_t_kernel(const float* __restrict__ w, const fl
     const int q = m >> 5, rs = (m >> 4) & 1, oc = 16 * q + (m & 15);
     const int kh = rs ? t - 2 : t;
     const bool row_ok = rs ? t >= 2 : t <= 6;
-    double scale = 1.0;
-    if (bn_w) scale = static_cast<double>(bn_w[oc]) / sqrt(static_cast<double>(bn_v[oc]) + 1e-5);
+    double scale = 1.0, shift = 0.0;
+    if (bn_w) {
+        scale = static_cast<double>(bn_w[oc]) / sqrt(static_cast<double>(bn_v[oc]) + 1e-5);
+        shift = static_cast<double>(bn_b[oc]) - static_cast<double>(bn_m[oc]) * scale;
+    }
+    if (blk == 0 && col == 0 && ((m >> 4) & 1) == 0) bias[oc] = static_cast<float>(shift);   // folded BN shift
     float v[2];
     for (int h = 0; h < 2; ++h) {
         const int e16 = 2 * col + h, pix = 4 * i + (e16 >> 2), c = e16 & 3, kw = pix - 1;
@@ -501,29 +240,10 @@ __global__ void stem_pack_weights_t_kernel(const float* __restrict__ w, const fl
     wt[idx] = pack_bf16x2(v[0], v[1]);
 }
 
-__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}\n"
-        :
-        : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
-                 :
-                 : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(STEM_T_THREADS, 1)
-stem_tc_t_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restrict__ xin,
-                 const uint32_t* __restrict__ wt, const float* __restrict__ bias, int B, int dbg, long long* dbg_out) {
+stem_tc_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restrict__ xin,
+                 const uint32_t* __restrict__ wt, const float* __restrict__ bias, int B) {
     using namespace ptx;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -603,7 +323,7 @@ stem_tc_t_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restr
                     }
                     __syncwarp();
                 } else {
-                    if (!(dbg & 4)) stem_fill_chunk_f32(smem_u32(dst), static_cast<const float*>(xin), b, c, lane);
+                    stem_fill_chunk_f32(smem_u32(dst), static_cast<const float*>(xin), b, c, lane);
                     fence_proxy_async_smem();
                     mbar_arrive(&ch_full[n & (NCH - 1)]);
                 }
@@ -611,8 +331,8 @@ stem_tc_t_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restr
         }
     } else if (warp == 1 || warp == 12) {
         // ===================================================== MMA issuers: 18 x (M = 128, N = 112, K = 16), A from TMEM
-        // TWO issuing warps take alternate steps. Measured with clock probes on a single issuer (RNB_STEM_DBG=16): per
-        // pair 1117 clocks inside the 18 MMA instructions (the tensor pipe's queue holds about two MMAs, so the
+        // TWO issuing warps take alternate steps. Measured with clock probes on a single issuer (git history, commit
+        // "Stem, third form"; profiles/stem_r2.md): per pair 1117 clocks inside the 18 MMA instructions (the tensor pipe's queue holds about two MMAs, so the
         // issuer is blocked for the pipe's 1008 clocks) and then 430 clocks of its own latency — two barrier polls of
         // ~100 clocks each even when the barrier is complete, commits, loop — during which the pipe ran dry: 60 %
         // active. With two issuers one warp's polls overlap the other warp's MMAs.
@@ -623,7 +343,6 @@ stem_tc_t_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restr
         constexpr uint32_t idesc = umma_instr_desc(UMMA_FMT_BF16, 128, 112);
         const uint64_t b_desc0 = umma_smem_desc(smem_u32(ring), 16, 128, UMMA_LAYOUT_NONE);
         int rel = 0;   // next chunk this warp has to release
-        long long tw_ch = 0, tw_acc = 0, t_issue = 0, t_rest = 0, t_prev = clock64();
         for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
             const int j = st.step;
             if ((j & 1) != X) continue;
@@ -636,14 +355,8 @@ stem_tc_t_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restr
                 la.next();
                 rel_end = la.done() ? la.cn : la.cn + la.new_chunks() - 3;
             }
-            long long t0 = clock64();
-            t_rest += t0 - t_prev;
             for (int m = cn_after - 3; m < cn_after; ++m) mbar_wait(&ch_full[m & (NCH - 1)], (m / NCH) & 1);
-            long long t1 = clock64();
             mbar_wait(&acc_empty[j % T_NSLOT], ((j / T_NSLOT) & 1) ^ 1);
-            long long t2 = clock64();
-            tw_ch += t1 - t0;
-            tw_acc += t2 - t1;
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t d = tmem_base + (j % T_NSLOT) * T_D_PITCH;
@@ -652,24 +365,17 @@ stem_tc_t_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restr
                 const uint64_t c0 = b_desc0 + static_cast<uint64_t>((((cn_after - 3) & (NCH - 1)) * CHUNK_BYTES) >> 4);
                 const uint64_t c1 = b_desc0 + static_cast<uint64_t>((((cn_after - 2) & (NCH - 1)) * CHUNK_BYTES) >> 4);
                 const uint64_t c2 = b_desc0 + static_cast<uint64_t>((((cn_after - 1) & (NCH - 1)) * CHUNK_BYTES) >> 4);
-                if (!(dbg & 2)) {
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const uint64_t row = (t < 3 ? c0 : t < 7 ? c1 : c2) + static_cast<uint64_t>((((1 + t) & 3) * ROW_BYTES) >> 4);
-                        mma_f16_ts(d, a0 + 16 * t, row, idesc, t != 0);
-                        mma_f16_ts(d, a0 + 16 * t + 8, row + 2, idesc, 1);
-                    }
+                for (int t = 0; t < 9; ++t) {
+                    const uint64_t row = (t < 3 ? c0 : t < 7 ? c1 : c2) + static_cast<uint64_t>((((1 + t) & 3) * ROW_BYTES) >> 4);
+                    mma_f16_ts(d, a0 + 16 * t, row, idesc, t != 0);
+                    mma_f16_ts(d, a0 + 16 * t + 8, row + 2, idesc, 1);
                 }
                 tc_commit(&acc_full[j % T_NSLOT]);
                 for (int n = rel; n < rel_end; ++n) tc_commit(&ch_empty[n & (NCH - 1)]);
             }
             rel = rel_end;
             __syncwarp();
-            t_prev = clock64();
-            t_issue += t_prev - t2;
-        }
-        if ((dbg & 16) && dbg_out && blockIdx.x == 0 && lane == 0 && X == 0) {
-            dbg_out[0] = tw_ch; dbg_out[1] = tw_acc; dbg_out[2] = t_issue; dbg_out[3] = t_rest; dbg_out[4] = (p_end - p_begin) / 2;
         }
     } else if (warp >= 4 && warp < 12) {
         // ===================================================== epilogue
@@ -786,24 +492,19 @@ bool stem_fused_enabled() {
 }
 
 size_t stem_tc_packed_input_bytes(int B) { return 1ull * B * PAD_H * ROW_BYTES; }
-// [second form: 28 KB of K-chunk blocks for shared memory][third form: 18 A blocks for TMEM]
-size_t stem_tc_packed_weight_bytes() { return W_BYTES + T_W_BYTES; }
+size_t stem_tc_packed_weight_bytes() { return T_W_BYTES; }
 
 cudaError_t launch_stem_tc_pack_weights(const float* w, const float* bn_w, const float* bn_b,
                                         const float* bn_m, const float* bn_v, void* wk, float* bias,
                                         cudaStream_t s) {
-    stem_pack_weights_kernel<<<(28 * 64 * 8 + 255) / 256, 256, 0, s>>>(
-        w, bn_w, bn_b, bn_m, bn_v, static_cast<__nv_bfloat16*>(wk), bias);
-    stem_pack_weights_t_kernel<<<(T_NBLK * 128 * 8 + 255) / 256, 256, 0, s>>>(
-        w, bn_w, bn_v, reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(wk) + W_BYTES));
+    stem_pack_weights_kernel<<<(T_NBLK * 128 * 8 + 255) / 256, 256, 0, s>>>(w, bn_w, bn_b, bn_m, bn_v,
+                                                                         static_cast<uint32_t*>(wk), bias);
     return cudaGetLastError();
 }
 
 cudaError_t stem_tc_init() {
-    cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_T_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_t_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_T_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_T_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_T_SMEM);
     return e;
 }
 
@@ -811,40 +512,15 @@ static cudaError_t launch_stem_tc_kernel(int mode, const void* in, const void* w
                                          cudaStream_t s) {
     const int pairs = B * PAIRS;
     const int grid = pairs < num_sms() ? pairs : num_sms();
-    const char* f = getenv("RNB_STEM_FORM");  // 1 (default): weights in TMEM, image rows as the B operand; 0: second form
-    const int form = f ? atoi(f) : 1;
-    const char* dg = getenv("RNB_STEM_DBG");   // timing experiments (wrong results): 1 = no epilogue work, 2 = no MMAs, 4 = no loads
-    const int dbg = dg ? atoi(dg) : 0;
-    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
-    if (form == 1) {
-        const uint32_t* wt = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(wk) + W_BYTES);
-        // output [B*56*56 pooled pixels][64 ch] bf16; one store = 28 pooled pixels x 16 channels (an epilogue warp's block)
-        CUtensorMap tm;
-        {
-            const uint64_t dims[2] = {64, 1ull * B * POOL * POOL}, strides[1] = {128};
-            const uint32_t box[2] = {16, 28};
-            if (make_tiled_nd(&tm, TmDtype::BF16, out, 2, dims, strides, box, false) != 0) return cudaErrorInvalidValue;
-        }
-        static long long* dbg_buf = nullptr;
-        if ((dbg & 16) && !dbg_buf) cudaMalloc(&dbg_buf, 64);
-        cudaError_t e = mode == 0 ? launch_pdl_small(stem_tc_t_kernel<0>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in,
-                                                     wt, bias, B, dbg, dbg_buf)
-                                  : launch_pdl_small(stem_tc_t_kernel<1>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in,
-                                                     wt, bias, B, dbg, dbg_buf);
-        if ((dbg & 16) && e == cudaSuccess) {
-            long long h[5];
-            cudaStreamSynchronize(s);
-            cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "stem issuer (CTA 0, %lld pairs): per pair clocks: wait chunks %.0f, wait acc %.0f, issue+commit %.0f, rest %.0f\n",
-                    h[4], double(h[0]) / h[4], double(h[1]) / h[4], double(h[2]) / h[4], double(h[3]) / h[4]);
-        }
-        return e;
-    }
+    // output [B*56*56 pooled pixels][64 ch] bf16; one store = 28 pooled pixels x 16 channels (an epilogue warp's block)
+    CUtensorMap tm;
+    const uint64_t dims[2] = {64, 1ull * B * POOL * POOL}, strides[1] = {128};
+    const uint32_t box[2] = {16, 28};
+    if (make_tiled_nd(&tm, TmDtype::BF16, out, 2, dims, strides, box, false) != 0) return cudaErrorInvalidValue;
+    const uint32_t* wt = static_cast<const uint32_t*>(wk);
     if (mode == 0)
-        return launch_pdl_small(stem_tc_kernel<0>, dim3(grid), dim3(STEM_TC_THREADS), STEM_SMEM, s, in,
-                                static_cast<const uint8_t*>(wk), bias, o, B);
-    return launch_pdl_small(stem_tc_kernel<1>, dim3(grid), dim3(STEM_TC_THREADS), STEM_SMEM, s, in,
-                            static_cast<const uint8_t*>(wk), bias, o, B);
+        return launch_pdl_small(stem_tc_kernel<0>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in, wt, bias, B);
+    return launch_pdl_small(stem_tc_kernel<1>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in, wt, bias, B);
 }
 
 // xp (packed NHWC4 BF16, written by a pack kernel) -> out NHWC bf16 [B,56,56,64]

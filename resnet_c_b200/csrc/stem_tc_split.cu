@@ -9,12 +9,13 @@
 //   x*w  ~=  x_hi*w_hi + x_hi*w_lo + x_lo*w_hi          (dropped term ~2^-16 relative)
 // is accumulated by THREE tcgen05.mma per K step into the same FP32 TMEM accumulator.
 //
-// Structure = stem_tc.cu's second form (round 2): conv-row PAIRS whose shared input rows are fetched once by
-// N = 128 MMAs, a ring of 4-row input chunks (here two rings: hi and lo terms), loader warps that build the NHWC4
-// rows from the caller's FP32 NCHW tensor — the layout pre-pass (two packed images, 380 MB of HBM traffic per 256
-// images) is gone — and the third conv row of a pooled row carried in registers. Differences from the BF16 kernel:
-//   * 3 x 19 MMAs per pair; weights are two 28 KB matrices;
-//   * the output is FP32 NHWC rounded to TF32 (the activation type of the TF32 path): 256-byte staging rows.
+// Structure = stem_tc.cu's (third form of round 2): weights (hi and lo: 36 A blocks = 288 TMEM columns) as the A
+// operand in TMEM, the image rows (two rings: hi and lo terms) as the B operand, conv-row pairs, two alternating MMA
+// issuer warps, loader warps that build the NHWC4 rows from the caller's FP32 NCHW tensor, independent per-warp
+// epilogues with their own TMA stores. Differences from the BF16 kernel:
+//   * 3 x 18 MMAs per pair; two accumulator slots (2 x 112 + 288 = 512 TMEM columns);
+//   * the output is FP32 NHWC rounded to TF32 (the activation type of the TF32 path): the partner-lane exchange moves
+//     one value per register (lanes 0..15 finish the even pooled columns of their half, lanes 16..31 the odd ones).
 #include <cstdint>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -22,6 +23,7 @@
 #include "internal.h"
 #include "sm100_ptx.cuh"
 #include "stem_tc_common.cuh"
+#include "tensormap.h"
 
 namespace rnb {
 
@@ -29,16 +31,21 @@ namespace {
 
 using namespace stemtc;
 
-constexpr int NCH = 6;                                 // ring depth in chunks (pair k reads chunks k, k+1, k+2)
-constexpr int RING_BYTES = NCH * CHUNK_BYTES + 512;    // one ring (hi or lo) + read-past slack
-constexpr int W_BYTES = 28 * 1024;                     // hi or lo, [j][wpos(kh)][64 oc][8 e] bf16
-constexpr int VROW = 256;                              // 64 ch x fp32
-constexpr int VBUF_BYTES = 112 * VROW;
-constexpr int NBAR = 2 * NCH + 2 * NSLOT;
+constexpr int NCH = 8;                                 // ring depth in chunks (pair k reads chunks k, k+1, k+2)
+constexpr int RING_BYTES = NCH * CHUNK_BYTES + 512;    // one ring (hi or lo) + slack
 constexpr int EPI_THREADS = 256;
-constexpr int THREADS = 128 + EPI_THREADS;
-constexpr int SMEM = 1024 + 2 * RING_BYTES + 2 * W_BYTES + 2 * VBUF_BYTES + NBAR * 8 + 16;
+constexpr int THREADS = 128 + EPI_THREADS + 32;        // warps 0..3, eight epilogue warps, the second MMA issuer
+constexpr int S_NBLK = 36;                             // A blocks: (input row t, K step i) x (hi, lo)
+constexpr int S_NSLOT = 2;                             // TMEM: D slots of 112 columns at 0 and 112; weights at 224 .. 511
+constexpr int S_D_PITCH = 112;
+constexpr int S_A_COL = S_NSLOT * S_D_PITCH;
+constexpr int S_WSTAGE_BYTES = 28 * 64;                // one epilogue warp's block: [28 pooled columns][16 ch] fp32
+constexpr int S_STAGE_BYTES = 8 * S_WSTAGE_BYTES;      // x 2 buffers
+constexpr int NBAR = 2 * NCH + 2 * S_NSLOT;
+constexpr int SMEM = 1024 + 2 * S_STAGE_BYTES + 2 * RING_BYTES + NBAR * 8 + 16;
+constexpr size_t S_W_BYTES = static_cast<size_t>(S_NBLK) * 128 * 8 * 4;
 static_assert(SMEM <= 232448, "smem budget");
+static_assert(S_A_COL + S_NBLK * 8 <= 512, "TMEM budget");
 
 __device__ __forceinline__ float rna_tf32(float x) {
     uint32_t r;
@@ -46,29 +53,36 @@ __device__ __forceinline__ float rna_tf32(float x) {
     return __uint_as_float(r);
 }
 
-// Folded weights split into hi / lo BF16 matrices, layout [j][wpos(kh)][oc][e] (see stem_tc.cu: K chunk j of filter
-// row kh holds window pixels p = 2j, 2j+1 with p = kw + 1).
+// w [64][3][7][7] fp32 + BN -> wt [block = (2t + i)*2 + part][m][8] u32 (part 0 = hi, 1 = lo BF16 term): row
+// m = 32q + 16*rowsel + ocl holds, as 16 BF16 (two per word, low half first), window pixels 4i .. 4i+3 x 4 channels of
+// filter row t (rowsel 0, t <= 6) or t - 2 (rowsel 1, t >= 2) of output channel 16q + ocl; everything else is zero.
 __global__ void stem_pack_weights_split_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
                                                const float* __restrict__ bn_b, const float* __restrict__ bn_m,
-                                               const float* __restrict__ bn_v, __nv_bfloat16* __restrict__ wk_hi,
-                                               __nv_bfloat16* __restrict__ wk_lo, float* __restrict__ bias) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 28 * 64 * 8) return;
-    const int e = i & 7, oc = (i >> 3) & 63, chunk = i >> 9;
-    const int kh = chunk >> 2, j = chunk & 3;
-    const int kw = 2 * j + (e >> 2) - 1, c = e & 3;
+                                               const float* __restrict__ bn_v, uint32_t* __restrict__ wt,
+                                               float* __restrict__ bias) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S_NBLK * 128 * 8) return;
+    const int col = idx & 7, m = (idx >> 3) & 127, blk = idx >> 10;
+    const int part = blk & 1, t = blk >> 2, i = (blk >> 1) & 1;
+    const int q = m >> 5, rs = (m >> 4) & 1, oc = 16 * q + (m & 15);
+    const int kh = rs ? t - 2 : t;
+    const bool row_ok = rs ? t >= 2 : t <= 6;
     double scale = 1.0, shift = 0.0;
     if (bn_w) {
         scale = static_cast<double>(bn_w[oc]) / sqrt(static_cast<double>(bn_v[oc]) + 1e-5);
         shift = static_cast<double>(bn_b[oc]) - static_cast<double>(bn_m[oc]) * scale;
     }
-    float v = 0.f;
-    if (kw >= 0 && kw < 7 && c < 3) v = static_cast<float>(static_cast<double>(w[((oc * 3 + c) * 7 + kh) * 7 + kw]) * scale);
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const int o = ((j * 7 + wpos(kh)) * 64 + oc) * 8 + e;
-    wk_hi[o] = h;
-    wk_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
-    if (chunk == 0 && e == 0) bias[oc] = static_cast<float>(shift);
+    if (blk == 0 && col == 0 && rs == 0) bias[oc] = static_cast<float>(shift);
+    float v[2];
+    for (int h = 0; h < 2; ++h) {
+        const int e16 = 2 * col + h, pix = 4 * i + (e16 >> 2), c = e16 & 3, kw = pix - 1;
+        float x = 0.f;
+        if (row_ok && kw >= 0 && kw < 7 && c < 3)
+            x = static_cast<float>(static_cast<double>(w[((oc * 3 + c) * 7 + kh) * 7 + kw]) * scale);
+        const float hi = __bfloat162float(__float2bfloat16_rn(x));
+        v[h] = part ? x - hi : hi;
+    }
+    wt[idx] = pack_bf16x2(v[0], v[1]);
 }
 
 // One chunk (image rows 4c-4 .. 4c-1 of image b) of BOTH rings, built by one warp from the FP32 NCHW tensor:
@@ -83,6 +97,10 @@ __device__ __forceinline__ void stem_fill_chunk_split(uint32_t dst_hi, uint32_t 
         return;
     }
     const float* img = x + (1LL * b * 3 * IMG + (4 * c - 4)) * IMG;
+    if (lane < 3 && c + 3 <= PAIRS) {   // the chunk this warp fills next, requested into L2 now (see stem_tc.cu)
+        const float* nxt = img + 1LL * lane * IMG * IMG + 12 * IMG;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"(4 * IMG * 4) : "memory");
+    }
     float4 v[7][3];
 #pragma unroll
     for (int it = 0; it < 7; ++it) {
@@ -124,20 +142,19 @@ __device__ __forceinline__ void stem_fill_chunk_split(uint32_t dst_hi, uint32_t 
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-stem_tc_split_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wk_hi, const uint8_t* __restrict__ wk_lo,
-                     const float* __restrict__ bias, float* __restrict__ out, int B) {
+stem_tc_split_kernel(const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ x,
+                     const uint32_t* __restrict__ wt, const float* __restrict__ bias, int B) {
     using namespace ptx;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
-    uint8_t* ring = smem;                       // [hi ring][lo ring]
-    uint8_t* wsm = smem + 2 * RING_BYTES;       // [hi 28 KB][lo 28 KB]
-    uint8_t* vbuf = wsm + 2 * W_BYTES;          // 2 x VBUF_BYTES
-    uint64_t* bars = reinterpret_cast<uint64_t*>(vbuf + 2 * VBUF_BYTES);
+    uint8_t* stage = smem;                          // 2 x S_STAGE_BYTES
+    uint8_t* ring = smem + 2 * S_STAGE_BYTES;       // [hi ring][lo ring]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * RING_BYTES);
     uint64_t* ch_full = bars;                       // [NCH]
     uint64_t* ch_empty = bars + NCH;                // [NCH]
-    uint64_t* acc_full = bars + 2 * NCH;            // [NSLOT]
-    uint64_t* acc_empty = bars + 2 * NCH + NSLOT;   // [NSLOT]
+    uint64_t* acc_full = bars + 2 * NCH;            // [S_NSLOT]
+    uint64_t* acc_empty = bars + 2 * NCH + S_NSLOT; // [S_NSLOT]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + NBAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -149,9 +166,9 @@ stem_tc_split_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wk
     if (threadIdx.x == 32) {
         for (int i = 0; i < NCH; ++i) {
             mbar_init(&ch_full[i], 32);
-            mbar_init(&ch_empty[i], 1);
+            mbar_init(&ch_empty[i], 2);   // both MMA issuers release every chunk
         }
-        for (int i = 0; i < NSLOT; ++i) {
+        for (int i = 0; i < S_NSLOT; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], EPI_THREADS);
         }
@@ -162,17 +179,28 @@ stem_tc_split_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wk
         tmem_alloc(tmem_ptr_smem, 512);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < W_BYTES / 16; i += THREADS) {
-        reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(wk_hi) + i);
-        reinterpret_cast<uint4*>(wsm + W_BYTES)[i] = __ldg(reinterpret_cast<const uint4*>(wk_lo) + i);
-    }
-    for (int i = threadIdx.x; i < 2 * RING_BYTES / 16; i += THREADS)   // halo columns, read-past slack
+    for (int i = threadIdx.x; i < 2 * RING_BYTES / 16; i += THREADS)   // halo columns, slack
         reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (warp >= 4 && warp < 12) {
+        // weights -> TMEM (constants): the two warps of a lane quarter write 18 A blocks each, lane = row m
+        const int q = warp & 3, m = 32 * q + lane;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + S_A_COL;
+        for (int blk = (warp - 4) >> 2; blk < S_NBLK; blk += 2) {
+            const uint4* src = reinterpret_cast<const uint4*>(wt + (blk * 128 + m) * 8);
+            const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+            const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            tmem_st_32x8(lane_base + blk * 8, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     if (warp == 0 || warp == 2 || warp == 3) {
         // ===================================================== loaders: chunk n belongs to loader n % 3
@@ -183,133 +211,143 @@ stem_tc_split_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wk
             for (int i = 0; i < nnew; ++i) {
                 const int n = st.cn + i, c = c_first + i;
                 if ((n % 3) != widx) continue;
-                mbar_wait(&ch_empty[n % NCH], ((n / NCH) & 1) ^ 1);
-                const uint32_t dst = smem_u32(ring) + (n % NCH) * CHUNK_BYTES;
+                mbar_wait(&ch_empty[n & (NCH - 1)], ((n / NCH) & 1) ^ 1);
+                const uint32_t dst = smem_u32(ring) + (n & (NCH - 1)) * CHUNK_BYTES;
                 stem_fill_chunk_split(dst, dst + RING_BYTES, x, b, c, lane);
                 fence_proxy_async_smem();
-                mbar_arrive(&ch_full[n % NCH]);
+                mbar_arrive(&ch_full[n & (NCH - 1)]);
             }
         }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer: 3 split products per K step
-        constexpr uint32_t idesc64 = umma_instr_desc(UMMA_FMT_BF16, 128, 64);
-        constexpr uint32_t idesc128 = umma_instr_desc(UMMA_FMT_BF16, 128, 128);
-        const uint64_t a_desc0 = umma_smem_desc(smem_u32(ring), 16, 128, UMMA_LAYOUT_NONE);
-        const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 7 * 1024, 128, UMMA_LAYOUT_NONE);
-        constexpr uint64_t A_LO = RING_BYTES >> 4;   // hi -> lo ring
-        constexpr uint64_t B_LO = W_BYTES >> 4;      // hi -> lo weights
+    } else if (warp == 1 || warp == 12) {
+        // ===================================================== MMA issuers (alternate steps; see stem_tc.cu)
+        const int X = warp == 1 ? 0 : 1;
+        constexpr uint32_t idesc = umma_instr_desc(UMMA_FMT_BF16, 128, 112);
+        const uint64_t b_desc0 = umma_smem_desc(smem_u32(ring), 16, 128, UMMA_LAYOUT_NONE);
+        constexpr uint64_t X_LO = RING_BYTES >> 4;   // hi -> lo ring
+        int rel = 0;   // next chunk this warp has to release
         for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
-            const int cn_after = st.cn + st.new_chunks();
             const int j = st.step;
-            const bool seg_ends = st.seg_ends();
-            for (int m = cn_after - 3; m < cn_after; ++m) mbar_wait(&ch_full[m % NCH], (m / NCH) & 1);
-            mbar_wait(&acc_empty[j & (NSLOT - 1)], ((j / NSLOT) & 1) ^ 1);
+            if ((j & 1) != X) continue;
+            const int cn_after = st.cn + st.new_chunks();
+            StemSteps la = st;   // first chunk of this warp's next step (j + 2), or the total number of chunks
+            la.next();
+            int rel_end = la.cn;
+            if (!la.done()) {
+                la.next();
+                rel_end = la.done() ? la.cn : la.cn + la.new_chunks() - 3;
+            }
+            for (int m = cn_after - 3; m < cn_after; ++m) mbar_wait(&ch_full[m & (NCH - 1)], (m / NCH) & 1);
+            mbar_wait(&acc_empty[j % S_NSLOT], ((j / S_NSLOT) & 1) ^ 1);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t d0 = tmem_base + (j & (NSLOT - 1)) * 128, d1 = d0 + 64;
-                auto arow = [&](int t, int i) {
-                    const int m = cn_after - 3 + ((1 + t) >> 2);
-                    return a_desc0 + static_cast<uint64_t>(
-                                         ((m % NCH) * CHUNK_BYTES + ((1 + t) & 3) * ROW_BYTES + 32 * i) >> 4);
-                };
-                auto wblk = [&](int kh, int i) {
-                    return b_desc0 + static_cast<uint64_t>(((2 * i * 7 + wpos(kh)) * 1024) >> 4);
-                };
-                // x_hi * w_hi, x_hi * w_lo, x_lo * w_hi into one accumulator
-                auto mma3 = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
-                    mma_f16_ss(d, ad, bd, idesc, acc);
-                    mma_f16_ss(d, ad, bd + B_LO, idesc, 1);
-                    mma_f16_ss(d, ad + A_LO, bd, idesc, 1);
-                };
+                const uint32_t d = tmem_base + (j % S_NSLOT) * S_D_PITCH;
+                const uint32_t a0 = tmem_base + S_A_COL;
+                const uint64_t c0 = b_desc0 + static_cast<uint64_t>((((cn_after - 3) & (NCH - 1)) * CHUNK_BYTES) >> 4);
+                const uint64_t c1 = b_desc0 + static_cast<uint64_t>((((cn_after - 2) & (NCH - 1)) * CHUNK_BYTES) >> 4);
+                const uint64_t c2 = b_desc0 + static_cast<uint64_t>((((cn_after - 1) & (NCH - 1)) * CHUNK_BYTES) >> 4);
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
+                    const uint64_t row = (t < 3 ? c0 : t < 7 ? c1 : c2) + static_cast<uint64_t>((((1 + t) & 3) * ROW_BYTES) >> 4);
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        if (t < 2) {
-                            mma3(d0, arow(t, i), wblk(t, i), idesc64, (t | i) != 0);
-                        } else if (t == 2 && i == 0) {
-                            mma3(d0, arow(t, i), wblk(2, i), idesc64, 1);
-                            mma3(d1, arow(t, i), wblk(0, i), idesc64, 0);
-                        } else if (t < 7) {
-                            mma3(d0, arow(t, i), wblk(t, i), idesc128, 1);
-                        } else {
-                            mma3(d1, arow(t, i), wblk(t - 2, i), idesc64, 1);
-                        }
+                        const uint32_t a_hi = a0 + ((2 * t + i) * 2) * 8, a_lo = a_hi + 8;
+                        mma_f16_ts(d, a_hi, row + 2 * i, idesc, (t | i) != 0);      // w_hi * x_hi
+                        mma_f16_ts(d, a_lo, row + 2 * i, idesc, 1);                  // w_lo * x_hi
+                        mma_f16_ts(d, a_hi, row + 2 * i + X_LO, idesc, 1);           // w_hi * x_lo
                     }
                 }
-                tc_commit(&acc_full[j & (NSLOT - 1)]);
-                tc_commit(&ch_empty[(cn_after - 3) % NCH]);
-                if (seg_ends) {
-                    tc_commit(&ch_empty[(cn_after - 2) % NCH]);
-                    tc_commit(&ch_empty[(cn_after - 1) % NCH]);
-                }
+                tc_commit(&acc_full[j % S_NSLOT]);
+                for (int n = rel; n < rel_end; ++n) tc_commit(&ch_empty[n & (NCH - 1)]);
             }
+            rel = rel_end;
             __syncwarp();
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 12) {
         // ===================================================== epilogue (FP32 / TF32-rounded output)
-        const int q = warp & 3;
-        const int half = (warp - 4) >> 2;
-        const int et = q * 32 + lane;
-        const int etid = threadIdx.x - 128;
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32;
-        float bias_r[32];
+        // warp quarter q = warp & 3: lanes 0..15 = conv row a (2k), lanes 16..31 = conv row b (2k+1) of channels
+        // 16q .. 16q+15; the two warps of a quarter split the pooled columns (h = 0: 0..27, h = 1: 28..55)
+        const int q = warp & 3, h = (warp - 4) >> 2;
+        const int rs = lane >> 4, oc = 16 * q + (lane & 15);
+        const float bias_c = __ldg(bias + oc);
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (h ? 48 : 0);
+        uint8_t* const stg = stage + (warp - 4) * (2 * S_WSTAGE_BYTES);
+        float carry[14];  // conv row 2k-1 (the previous pair's row b) at the 14 pooled columns this lane finishes
 #pragma unroll
-        for (int i = 0; i < 32; ++i) bias_r[i] = __ldg(bias + half * 32 + i);
+        for (int u = 0; u < 14; ++u) carry[u] = 0.f;
         int vb = 0;
-        float carry[32];  // conv row 2k-1: the second row of the previous pair
-#pragma unroll
-        for (int i = 0; i < 32; ++i) carry[i] = -INFINITY;
-        for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
+        uint32_t c0[32], c1[32];   // 64 output columns of this lane's conv row: 0..63 (h = 0) or 48..111 (h = 1)
+        StemSteps st(p_begin, p_end);
+        if (!st.done()) {
+            mbar_wait(&acc_full[0], 0);
+            tc_fence_after();
+            tmem_ld_32x32(lane_addr, c0);
+            tmem_ld_32x32(lane_addr + 32, c1);
+        }
+        while (!st.done()) {
             const int b = st.b(), k = st.k(), j = st.step;
             const bool warm = st.warm;
-            mbar_wait(&acc_full[j & (NSLOT - 1)], (j / NSLOT) & 1);
-            tc_fence_after();
-            uint32_t ra[32], rb[32];
-            tmem_ld_32x32(lane_addr + (j & (NSLOT - 1)) * 128, ra);
-            tmem_ld_32x32(lane_addr + (j & (NSLOT - 1)) * 128 + 64, rb);
+            st.next();
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&acc_empty[j & (NSLOT - 1)]);
-            float m[32];
+            mbar_arrive(&acc_empty[j % S_NSLOT]);
+            auto col = [&](int i) { return __uint_as_float(i < 32 ? c0[i] : c1[i - 32]); };
+            // horizontal 3-tap max, bias, ReLU, TF32 rounding (all monotone: they commute with the vertical max)
+            float y[28];
+            if (h == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float top = k == 0 ? -INFINITY : carry[i];
-                m[i] = fmaxf(fmaxf(top, __uint_as_float(ra[i])), __uint_as_float(rb[i]));
-                carry[i] = __uint_as_float(rb[i]);
-            }
-            if (warm) continue;
-            if (et < 112) {
-                const uint32_t vrow = smem_u32(vbuf) + vb * VBUF_BYTES + et * VROW + half * 128;
+                for (int jj = 0; jj < 28; ++jj) {
+                    const int i0 = 2 * jj;
+                    y[jj] = rna_tf32(fmaxf(fmaxf(fmaxf(col(i0), col(i0 + 1)), i0 > 0 ? col(i0 - 1) : col(i0)) + bias_c, 0.f));
+                }
+            } else {
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    float o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = rna_tf32(fmaxf(m[jj * 4 + e] + bias_r[jj * 4 + e], 0.f));
-                    st_shared_v4(vrow + ((jj ^ (et & 7)) << 4), __float_as_uint(o[0]), __float_as_uint(o[1]),
-                                 __float_as_uint(o[2]), __float_as_uint(o[3]));
+                for (int jj = 0; jj < 28; ++jj) {
+                    const int i0 = 2 * jj + 8;
+                    y[jj] = rna_tf32(fmaxf(fmaxf(fmaxf(col(i0), col(i0 + 1)), col(i0 - 1)) + bias_c, 0.f));
                 }
             }
-            named_bar_sync(1, EPI_THREADS);
+            if (!st.done()) {   // the next pair's accumulators
+                const int jn = st.step;
+                mbar_wait(&acc_full[jn % S_NSLOT], (jn / S_NSLOT) & 1);
+                tc_fence_after();
+                tmem_ld_32x32(lane_addr + (jn % S_NSLOT) * S_D_PITCH, c0);
+                tmem_ld_32x32(lane_addr + (jn % S_NSLOT) * S_D_PITCH + 32, c1);
+            }
+            if (k == 0) {
+#pragma unroll
+                for (int u = 0; u < 14; ++u) carry[u] = 0.f;   // no conv row above the image (ReLU output is >= 0)
+            }
+            // vertical max with the partner lane (the pair's other conv row): lanes 0..15 finish the even pooled
+            // columns of this warp's 28, lanes 16..31 the odd ones; each lane sends what the other one finishes
+            float res[14];
+#pragma unroll
+            for (int u = 0; u < 14; ++u) {
+                const float mine = rs ? y[2 * u + 1] : y[2 * u];
+                const float other = __shfl_xor_sync(0xffffffffu, rs ? y[2 * u] : y[2 * u + 1], 16);
+                const float rowb = rs ? mine : other;
+                res[u] = fmaxf(fmaxf(mine, other), carry[u]);
+                carry[u] = rowb;
+            }
+            if (warm) continue;  // the pair before this CTA's range: only its second conv row was wanted
+            if (lane == 0) tma_store_wait_read<1>();   // the store that last read this staging buffer (two pairs ago)
+            __syncwarp();
             {
-                const uint32_t vr = smem_u32(vbuf) + vb * VBUF_BYTES;
-                float* orow = out + ((1LL * b * POOL + k) * POOL) * 64;
-                for (int task = etid; task < POOL * 16; task += EPI_THREADS) {
-                    const int pw = task >> 4, c16 = task & 15;   // 16 chunks of 4 floats per pixel
-                    const int hh = c16 >> 3, cj = c16 & 7;
-                    const int c0 = 2 * pw;
-                    auto ld = [&](int row) { return ld_shared_v4(vr + row * VROW + hh * 128 + ((cj ^ (row & 7)) << 4)); };
-                    const uint4 a = ld(c0), c = ld(c0 + 1), l = pw > 0 ? ld(c0 - 1) : a;
-                    float4 r;
-                    r.x = fmaxf(fmaxf(__uint_as_float(a.x), __uint_as_float(c.x)), __uint_as_float(l.x));
-                    r.y = fmaxf(fmaxf(__uint_as_float(a.y), __uint_as_float(c.y)), __uint_as_float(l.y));
-                    r.z = fmaxf(fmaxf(__uint_as_float(a.z), __uint_as_float(c.z)), __uint_as_float(l.z));
-                    r.w = fmaxf(fmaxf(__uint_as_float(a.w), __uint_as_float(c.w)), __uint_as_float(l.w));
-                    *reinterpret_cast<float4*>(orow + pw * 64 + c16 * 4) = r;
-                }
+                // [28 pooled columns][16 ch] fp32, 64-byte rows: lanes 0..15 write row 2u, lanes 16..31 row 2u+1 —
+                // 32 consecutive words per instruction
+                const uint32_t sbase = smem_u32(stg) + vb * S_WSTAGE_BYTES + rs * 64 + (lane & 15) * 4;
+#pragma unroll
+                for (int u = 0; u < 14; ++u)
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + 2 * u * 64), "r"(__float_as_uint(res[u])) : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tm_out, stg + vb * S_WSTAGE_BYTES, 16 * q, (b * POOL + k) * POOL + 28 * h);
+                tma_store_commit();
             }
             vb ^= 1;
         }
+        if (lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -322,10 +360,10 @@ stem_tc_split_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wk
 
 }  // namespace
 
-// no layout pre-pass any more: the scratch tensor of the two-launch form is not used (a token size keeps the
-// callers' allocation paths unchanged)
+// no layout pre-pass: the scratch tensor of the two-launch form is not used (a token size keeps the callers'
+// allocation paths unchanged)
 size_t stem_tc_split_packed_input_bytes(int) { return 256; }
-size_t stem_tc_split_packed_weight_bytes() { return 2 * W_BYTES; }
+size_t stem_tc_split_packed_weight_bytes() { return S_W_BYTES; }
 
 cudaError_t stem_tc_split_init() {
     return cudaFuncSetAttribute(stem_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -334,9 +372,8 @@ cudaError_t stem_tc_split_init() {
 cudaError_t launch_stem_tc_split_pack_weights(const float* w, const float* bn_w, const float* bn_b,
                                               const float* bn_m, const float* bn_v, void* wk, float* bias,
                                               cudaStream_t s) {
-    __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(wk);
-    stem_pack_weights_split_kernel<<<(28 * 64 * 8 + 255) / 256, 256, 0, s>>>(w, bn_w, bn_b, bn_m, bn_v, hi,
-                                                                          hi + W_BYTES / 2, bias);
+    stem_pack_weights_split_kernel<<<(S_NBLK * 128 * 8 + 255) / 256, 256, 0, s>>>(w, bn_w, bn_b, bn_m, bn_v,
+                                                                               static_cast<uint32_t*>(wk), bias);
     return cudaGetLastError();
 }
 
@@ -347,8 +384,12 @@ cudaError_t launch_stem_tc_split_part(int part, const float* x, void* /*xp*/, co
     if (part == 0) return cudaSuccess;
     const int pairs = B * PAIRS;
     const int grid = pairs < num_sms() ? pairs : num_sms();
-    const uint8_t* w_hi = static_cast<const uint8_t*>(wk);
-    stem_tc_split_kernel<<<grid, THREADS, SMEM, s>>>(x, w_hi, w_hi + W_BYTES, bias, static_cast<float*>(out), B);
+    // output [B*56*56 pooled pixels][64 ch] fp32; one store = 28 pooled pixels x 16 channels (an epilogue warp's block)
+    CUtensorMap tm;
+    const uint64_t dims[2] = {64, 1ull * B * POOL * POOL}, strides[1] = {256};
+    const uint32_t box[2] = {16, 28};
+    if (make_tiled_nd(&tm, TmDtype::F32, out, 2, dims, strides, box, false) != 0) return cudaErrorInvalidValue;
+    stem_tc_split_kernel<<<grid, THREADS, SMEM, s>>>(tm, x, static_cast<const uint32_t*>(wk), bias, B);
     return cudaGetLastError();
 }
 
