@@ -16,6 +16,7 @@
 #ifndef RNB_H
 #define RNB_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -101,10 +102,16 @@ int rnb_model_create_packed(const char* path, int max_batch, int chunk, rnb_mode
 int rnb_model_forward(rnb_model_t* m, const float* x_dev, int batch, float* logits_dev,
                       int32_t* top1_dev, void* stream);
 
-/* Same through HOST buffers (what main.cu does with loadToCuda / fc_out.cpu()): copies the input
- * host->device chunk by chunk overlapped with compute, runs the pass, copies logits/top-1 back and
- * synchronises. Pinned host memory is used as-is; pageable memory goes through the driver's
- * staging. */
+/* Same through HOST buffers (what main.cu does with loadToCuda / fc_out.cpu(), cuda/inference/main.cu:233-251):
+ * copies the input host->device chunk by chunk overlapped with compute, runs the pass, copies logits/top-1 back and
+ * synchronises. Pinned host memory is used as-is; pageable memory goes through the driver's staging.
+ * Host packing (BF16 and FP8 models, 224 x 224): the stem's first act on an FP32 image is to round it to BF16, and
+ * 602 KB per image over PCIe bounds the end-to-end rate, so the host paths can round on the HOST cores (a pool of
+ * up to 16 threads, RNB_HOST_THREADS; the same round-to-nearest-even, results bit-identical) into a pinned staging
+ * buffer and upload half the bytes, piece by piece while the next piece is being rounded. Pageable input then needs
+ * no driver staging either. The first host call of a model with pageable input, and the first with pinned input,
+ * time both forms on a sample of their batch and keep the faster one for that kind of memory; RNB_HOST_PACK=0 / 1
+ * or rnb_model_set_host_pack() force it. */
 int rnb_model_forward_host(rnb_model_t* m, const float* x_host, int batch, float* logits_host,
                            int32_t* top1_host);
 
@@ -116,6 +123,22 @@ int rnb_model_forward_host(rnb_model_t* m, const float* x_host, int batch, float
 int rnb_model_submit_host(rnb_model_t* m, int slot, const float* x_host, int batch, float* logits_host,
                           int32_t* top1_host);
 int rnb_model_wait_host(rnb_model_t* m, int slot);
+
+/* Host packing control and introspection. mode: -1 decide by timing at the next host call (default), 0 plain FP32
+ * copies, 1 round to BF16 on the host (RNB_ERR_UNSUPPORTED on a model whose stem does not take BF16 input: tf32,
+ * or images other than 224 x 224). rnb_model_host_pack() returns what the most recent host call did (0 / 1; -1 =
+ * nothing decided yet) and, when gbps != NULL, what that decision measured: conversion rate (FP32 bytes read), FP32
+ * H2D, BF16 H2D, in GB/s (zeros when it was forced). rnb_host_pack_threads(): threads a conversion uses, the caller included. */
+int rnb_model_set_host_pack(rnb_model_t* m, int mode);
+int rnb_model_host_pack(const rnb_model_t* m, double gbps[3]);
+int rnb_host_pack_threads(void);
+/* The conversion itself on host memory (no GPU involved): dst[i] = BF16(src[i]), round to nearest even, NaN ->
+ * 0x7FFF, by the same thread pool. What the packed host paths upload. */
+int rnb_f32_to_bf16_host(const float* src, uint16_t* dst, size_t n);
+/* Forward on a DEVICE tensor that already holds such BF16 values, [batch,3,224,224] NCHW: bit-identical to
+ * rnb_model_forward() on the FP32 tensor it was rounded from (BF16 / FP8 models only). */
+int rnb_model_forward_bf16(rnb_model_t* m, const uint16_t* x_dev, int batch, float* logits_dev,
+                           int32_t* top1_dev, void* stream);
 
 /* Decoded-image input: x is uint8 HWC [batch][224][224][3] — the output of JPEG decode + resize 256 +
  * centre-crop 224 (convert_imgs_to_bin.py:12). The remaining step of that script (:18, torchvision

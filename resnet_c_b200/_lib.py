@@ -60,6 +60,11 @@ PROTOTYPES = {
     "rnb_model_set_normalization": (C.c_int, [_vp, _f32p, _f32p]),
     "rnb_model_forward_u8": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
     "rnb_model_submit_host_u8": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "rnb_model_set_host_pack": (C.c_int, [_vp, C.c_int]),
+    "rnb_model_host_pack": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "rnb_host_pack_threads": (C.c_int, []),
+    "rnb_f32_to_bf16_host": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "rnb_model_forward_bf16": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
     "rnb_model_num_classes": (C.c_int, [_vp]),
     "rnb_model_num_convs": (C.c_int, [_vp]),
     "rnb_model_launches_per_forward": (C.c_int, [_vp, C.c_int]),

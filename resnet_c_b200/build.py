@@ -29,7 +29,9 @@ NVCC_FLAGS = [
 ]
 
 LIB_SOURCES = ["api.cu", "model.cu", "conv_plan.cu", "tensormap.cu", "ops_f32.cu", "layout.cu",
-               "stem.cu", "stem_tc.cu", "stem_tc_split.cu", "tail.cu", "group.cu", "preprocess.cu", "block.cu", "fp8.cu"]
+               "stem.cu", "stem_tc.cu", "stem_tc_split.cu", "tail.cu", "group.cu", "preprocess.cu", "block.cu", "fp8.cu",
+               "host_pack.cpp"]   # (.cpp: plain host code, compiled by g++ — AVX2 intrinsics, no CUDA)
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-pthread"]
 
 
 def _nvcc() -> str:
@@ -75,7 +77,10 @@ def build_librnb(force: bool = False) -> Path:
         obj = objdir / (src.stem + ".o")
         objs.append(obj)
         if force or _stale(obj, sorted(_includes(src.resolve(), set()))):
-            jobs.append([_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj])
+            if src.suffix == ".cpp":
+                jobs.append([os.environ.get("CXX", "g++"), *CXX_FLAGS, "-c", src, "-o", obj])
+            else:
+                jobs.append([_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj])
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(_run, jobs))

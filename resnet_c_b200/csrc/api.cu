@@ -9,6 +9,7 @@
 #include <string>
 
 #include "../../include/rnb.h"
+#include "host_pack.h"
 #include "conv_plan.h"
 #include "internal.h"
 #include "model.h"
@@ -323,6 +324,52 @@ int rnb_model_submit_host_u8(rnb_model_t* m, int slot, const uint8_t* x_host, in
     }
     DeviceGuard guard(m->impl.device);
     return m->impl.submit_host_u8(slot, x_host, batch, logits_host, top1_host);
+}
+
+int rnb_model_set_host_pack(rnb_model_t* m, int mode) {
+    if (!m || mode < -1 || mode > 1) {
+        set_error("rnb_model_set_host_pack: NULL model or mode outside -1 .. 1");
+        return RNB_ERR_INVALID;
+    }
+    if (mode == 1 && !m->impl.accepts_bf16_input()) {
+        set_error("rnb_model_set_host_pack: this model's stem does not take BF16 input (bf16 / fp8 models at 224 x 224 do)");
+        return RNB_ERR_UNSUPPORTED;
+    }
+    m->impl.host_pack_mode = mode;
+    m->impl.host_pack_last = mode;
+    for (int k = 0; k < 2; ++k) {
+        m->impl.host_pack_decided[k] = -1;
+        for (double& g : m->impl.host_pack_gbps[k]) g = 0;
+    }
+    return RNB_OK;
+}
+
+int rnb_model_host_pack(const rnb_model_t* m, double gbps[3]) {
+    if (!m) return -1;
+    if (gbps)
+        for (int i = 0; i < 3; ++i) gbps[i] = m->impl.host_pack_gbps[m->impl.host_pack_last_kind][i];
+    return m->impl.host_pack_last;
+}
+
+int rnb_host_pack_threads(void) { return rnb::HostPacker::instance().threads(); }
+
+int rnb_f32_to_bf16_host(const float* src, uint16_t* dst, size_t n) {
+    if ((!src || !dst) && n) {
+        set_error("rnb_f32_to_bf16_host: NULL argument");
+        return RNB_ERR_INVALID;
+    }
+    rnb::HostPacker::instance().run(src, dst, n, n, [](size_t, size_t) {});
+    return RNB_OK;
+}
+
+int rnb_model_forward_bf16(rnb_model_t* m, const uint16_t* x_dev, int batch, float* logits_dev,
+                           int32_t* top1_dev, void* stream) {
+    if (!m || !x_dev) {
+        set_error("rnb_model_forward_bf16: NULL argument");
+        return RNB_ERR_INVALID;
+    }
+    DeviceGuard guard(m->impl.device);
+    return m->impl.forward_bf16(x_dev, batch, logits_dev, top1_dev, static_cast<cudaStream_t>(stream));
 }
 
 int rnb_model_wait_host(rnb_model_t* m, int slot) {

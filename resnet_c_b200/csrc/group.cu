@@ -71,6 +71,9 @@ int rnb_group_create(const char* arch, int dtype, const char* weights_dir, const
         if ((rc = rnb_init(dev)) != RNB_OK) break;  // also makes `dev` current
         rnb_model_t* m = nullptr;
         if ((rc = rnb_model_create(arch, dtype, weights_dir, max_batch_per_device, 0, &m)) != RNB_OK) break;
+        // the replicas' host paths are fed one after the other by the calling thread: no host-side BF16 rounding
+        // (it would serialise the replicas; RNB_HOST_PACK=1 still forces it)
+        if (!(getenv("RNB_HOST_PACK") && atoi(getenv("RNB_HOST_PACK")) == 1)) m->impl.host_pack_mode = 0;
         g->models.push_back(m);
         g->devices.push_back(dev);
         cudaStream_t s = nullptr;

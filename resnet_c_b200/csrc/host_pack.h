@@ -1,0 +1,40 @@
+// host_pack.h — CPU side of the host-input paths (rnb_model_forward_host / rnb_model_submit_host).
+//
+// The reference hands the network FP32 NCHW images from host memory (cuda/inference/main.cu:233-236: Tensor::load of
+// the .bin that convert_imgs_to_bin.py wrote, then one cudaMemcpy). On the BF16 / FP8 paths the first thing the stem
+// does with such an image is round it to BF16, and 602 KB per image over PCIe is what bounds the end-to-end rate
+// (DESIGN.md section 6). So the host paths round on the CPU — the SAME round-to-nearest-even, bit for bit — into a
+// pinned staging buffer and upload half the bytes; the stem then reads BF16 NCHW (stem_tc.cu, MODE 2).
+// Plain C++ (compiled by g++, no CUDA): model.cu owns the staging buffers, streams and copies.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <functional>
+
+namespace rnb {
+
+// dst[i] = BF16(src[i]), round to nearest even; NaN -> 0x7FFF (what cvt.rn.bf16x2.f32 produces). Single thread.
+void f32_to_bf16_rne(const float* src, uint16_t* dst, size_t n);
+
+// A process-wide pool of sleeping worker threads. run() converts src[0, n) into dst with the workers AND the calling
+// thread, and calls ready(first_element, count) on the CALLING thread for every consecutive piece of `piece` elements
+// as soon as that piece is complete, in order (the caller queues the piece's H2D copy there, so the upload of piece i
+// overlaps the conversion of piece i + 1). One run() at a time (callers from several threads are serialised).
+class HostPacker {
+public:
+    static HostPacker& instance();
+    int threads() const { return nthreads_; }   // participants of a run(), the caller included
+    void run(const float* src, uint16_t* dst, size_t n, size_t piece,
+             const std::function<void(size_t first, size_t count)>& ready);
+    HostPacker(const HostPacker&) = delete;
+    HostPacker& operator=(const HostPacker&) = delete;
+
+private:
+    HostPacker();
+    ~HostPacker();
+    struct Impl;
+    Impl* impl_;
+    int nthreads_;
+};
+
+}  // namespace rnb

@@ -2,6 +2,7 @@
 #include "model.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -9,6 +10,7 @@
 #include <memory>
 
 #include "../../include/rnb.h"
+#include "host_pack.h"
 #include "internal.h"
 
 namespace rnb {
@@ -166,6 +168,7 @@ Model::~Model() {
     if (pipe_compute) cudaStreamDestroy(pipe_compute);
     for (HostSlot& hs : slots) {
         cudaFree(hs.x_dev); cudaFree(hs.logits_dev); cudaFree(hs.top1_dev);
+        if (hs.stage) cudaFreeHost(hs.stage);
         if (hs.copied) cudaEventDestroy(hs.copied);
         if (hs.done) cudaEventDestroy(hs.done);
     }
@@ -175,6 +178,7 @@ Model::~Model() {
     if (!is_lane) cudaFree(fp8_ones);
     for (void* v : fp8_vec_allocs) cudaFree(v);
     cudaFree(host_x_dev); cudaFree(host_logits_dev); cudaFree(host_top1_dev); cudaFree(scratch_logits);
+    if (host_stage) cudaFreeHost(host_stage);
     if (lane_fork) cudaEventDestroy(lane_fork);
     if (lane_join) cudaEventDestroy(lane_join);
     lane2.reset();
@@ -1048,10 +1052,15 @@ ChunkPlan* Model::plan_for(int n) {
     return &ins.first->second;
 }
 
-int Model::enqueue_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1,
-                         cudaStream_t s) {
+int Model::enqueue_chunk(ChunkPlan& p, InRef in, float* logits, int32_t* top1, cudaStream_t s) {
     const int n = p.n;
     const int s_hw = (6 + image - 7) / 2 + 1;
+    const float* x = in.f32();
+    const uint8_t* x_u8 = in.u8();
+    if (in.kind == InRef::BF16_NCHW && !accepts_bf16_input()) {
+        set_error("BF16 NCHW input needs the one-launch BF16 tensor-core stem (bf16 / fp8 model, 224 x 224)");
+        return RNB_ERR_UNSUPPORTED;
+    }
     if (x_u8 && !(stem_tc && stem_esz() == 2)) {
         // generic path: normalise into an FP32 NCHW staging tensor, then proceed as with float input
         RNB_CUDA(launch_u8_hwc_to_f32_nchw(x_u8, u8_scratch, n, image, image, norm_mean, norm_std, s));
@@ -1063,6 +1072,8 @@ int Model::enqueue_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, floa
         if (x_u8) {
             RNB_CUDA(launch_stem_tc_pack_u8(x_u8, p.stem_out, n, norm_mean, norm_std, s));
             RNB_CUDA(launch_stem_tc_from_packed(p.stem_out, stem_wk, stem_bias, pool, n, s));
+        } else if (in.kind == InRef::BF16_NCHW) {
+            RNB_CUDA(launch_stem_tc_from_bf16(in.p, stem_wk, stem_bias, pool, n, s));
         } else {
             RNB_CUDA(launch_stem_any_part(stem_esz(), 0, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
             RNB_CUDA(launch_stem_any_part(stem_esz(), 1, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
@@ -1252,11 +1263,19 @@ int Model::calibrate_fp8(const float* x, int n) {
 }
 
 int Model::forward(const float* x, int batch, float* logits, int32_t* top1, cudaStream_t s) {
-    return forward_any(x, nullptr, batch, logits, top1, s);
+    return forward_any(InRef{x, InRef::F32_NCHW}, batch, logits, top1, s);
 }
 
 int Model::forward_u8(const uint8_t* x, int batch, float* logits, int32_t* top1, cudaStream_t s) {
-    return forward_any(nullptr, x, batch, logits, top1, s);
+    return forward_any(InRef{x, InRef::U8_HWC}, batch, logits, top1, s);
+}
+
+int Model::forward_bf16(const uint16_t* x, int batch, float* logits, int32_t* top1, cudaStream_t s) {
+    if (!accepts_bf16_input()) {
+        set_error("BF16 NCHW input needs the one-launch BF16 tensor-core stem (bf16 / fp8 model, 224 x 224)");
+        return RNB_ERR_UNSUPPORTED;
+    }
+    return forward_any(InRef{x, InRef::BF16_NCHW}, batch, logits, top1, s);
 }
 
 int Model::set_normalization(const float* mean, const float* std) {
@@ -1305,15 +1324,15 @@ int Model::make_lane() {
     return RNB_OK;
 }
 
-int Model::forward_two(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1, cudaStream_t s) {
+int Model::forward_two(InRef in, int batch, float* logits, int32_t* top1, cudaStream_t s) {
     const int n0 = (batch + 1) / 2, n1 = batch - n0;
     const size_t img = 3ull * image * image;
     cudaStream_t s2 = lane2->host_compute;
     RNB_CUDA(cudaEventRecord(lane_fork, s));
     RNB_CUDA(cudaStreamWaitEvent(s2, lane_fork, 0));
-    int r = forward_one(x, x_u8, n0, logits, top1, s);
+    int r = forward_one(in, n0, logits, top1, s);
     if (r) return r;
-    r = lane2->forward_one(x ? x + n0 * img : nullptr, x_u8 ? x_u8 + n0 * img : nullptr, n1,
+    r = lane2->forward_one(in.at(n0 * img), n1,
                            logits ? logits + 1ull * n0 * classes : nullptr, top1 ? top1 + n0 : nullptr, s2);
     if (r) return r;
     RNB_CUDA(cudaEventRecord(lane_join, s2));
@@ -1322,7 +1341,7 @@ int Model::forward_two(const float* x, const uint8_t* x_u8, int batch, float* lo
 }
 
 // 1 or 2 lanes for this batch size; the first use of a size times both forms on the caller's buffers (blocking)
-int Model::lanes_for(int batch, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1, cudaStream_t s) {
+int Model::lanes_for(int batch, InRef in, float* logits, int32_t* top1, cudaStream_t s) {
     if (is_lane || (fp8 && !fp8_calibrated) || batch < 2 || batch > chunk || arena.keep) return 1;
     auto it = lane_choice.find(batch);
     if (it != lane_choice.end()) return it->second;
@@ -1341,10 +1360,10 @@ int Model::lanes_for(int batch, const float* x, const uint8_t* x_u8, float* logi
         for (int form = 0; form < 2; ++form) {
             bool ok = true;
             for (int i = 0; i < 2 && ok; ++i)
-                ok = (form ? forward_two(x, x_u8, batch, logits, top1, s) : forward_one(x, x_u8, batch, logits, top1, s)) == RNB_OK;
+                ok = (form ? forward_two(in, batch, logits, top1, s) : forward_one(in, batch, logits, top1, s)) == RNB_OK;
             cudaEventRecord(e0, s);
             for (int i = 0; i < 4 && ok; ++i)
-                ok = (form ? forward_two(x, x_u8, batch, logits, top1, s) : forward_one(x, x_u8, batch, logits, top1, s)) == RNB_OK;
+                ok = (form ? forward_two(in, batch, logits, top1, s) : forward_one(in, batch, logits, top1, s)) == RNB_OK;
             cudaEventRecord(e1, s);
             if (cudaStreamSynchronize(s) == cudaSuccess && ok) cudaEventElapsedTime(&ms[form], e0, e1);
         }
@@ -1363,22 +1382,26 @@ int Model::lanes_for(int batch, const float* x, const uint8_t* x_u8, float* logi
     return choice;
 }
 
-int Model::forward_any(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1,
-                       cudaStream_t s) {
+int Model::forward_any(InRef in, int batch, float* logits, int32_t* top1, cudaStream_t s) {
     if (batch <= 0 || batch > max_batch) {
         set_error("batch must be in [1, max_batch]");
         return RNB_ERR_INVALID;
     }
-    if (!x && !x_u8) {
+    if (!in.p) {
         set_error("x_dev is NULL");
         return RNB_ERR_INVALID;
     }
-    if (lanes_for(batch, x, x_u8, logits, top1, s) == 2) return forward_two(x, x_u8, batch, logits, top1, s);
-    return forward_one(x, x_u8, batch, logits, top1, s);
+    if (lanes_for(batch, in, logits, top1, s) == 2) return forward_two(in, batch, logits, top1, s);
+    return forward_one(in, batch, logits, top1, s);
 }
 
-int Model::forward_one(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1,
-                       cudaStream_t s) {
+int Model::forward_one(InRef in, int batch, float* logits, int32_t* top1, cudaStream_t s) {
+    const float* x = in.f32();
+    const uint8_t* x_u8 = in.u8();
+    if (in.kind == InRef::BF16_NCHW && fp8 && !fp8_calibrated) {
+        set_error("an FP8 model is calibrated on FP32 or uint8 input: calibrate before feeding BF16 input");
+        return RNB_ERR_INVALID;
+    }
     if (x_u8 && (!(stem_tc && stem_esz() == 2) || (fp8 && !fp8_calibrated)) && !u8_scratch)
         RNB_CUDA(cudaMalloc(&u8_scratch, 1ull * chunk * 3 * image * image * sizeof(float)));
     if (!logits) {
@@ -1418,17 +1441,16 @@ int Model::forward_one(const float* x, const uint8_t* x_u8, int batch, float* lo
         const int n = std::min(chunk, batch - off);
         ChunkPlan* p = plan_for(n);
         if (!p) return RNB_ERR_CUDA;
-        const float* xc = x ? x + off * img_elems : nullptr;
-        const uint8_t* xu = x_u8 ? x_u8 + off * img_elems : nullptr;
+        const InRef inc = in.at(off * img_elems);
         float* lc = logits + 1ull * off * classes;
         int32_t* tc = top1 ? top1 + off : nullptr;
         if (!use_graph) {
-            int r = enqueue_chunk(*p, xc, xu, lc, tc, s);
+            int r = enqueue_chunk(*p, inc, lc, tc, s);
             if (r) return r;
             continue;
         }
-        const int shape = n | (xu ? 1 << 30 : 0);
-        const GraphKey key{shape, xu ? static_cast<const void*>(xu) : static_cast<const void*>(xc), lc, tc};
+        const int shape = n | (inc.kind << 29);   // (U8_HWC = bit 29, BF16_NCHW = bit 30)
+        const GraphKey key{shape, inc.p, lc, tc};
         auto g = graphs.find(key);
         if (g == graphs.end()) {
             // executables already held for this shape, least recently used first
@@ -1440,7 +1462,7 @@ int Model::forward_one(const float* x, const uint8_t* x_u8, int batch, float* lo
                 if (lru == graphs.end() || it->second.used < lru->second.used) lru = it;
             }
             cudaGraph_t graph = nullptr;
-            int r = capture_chunk(*p, xc, xu, lc, tc, &graph);
+            int r = capture_chunk(*p, inc, lc, tc, &graph);
             if (r) return r;
             cudaGraphExec_t exec = nullptr;
             if (held >= kGraphsPerShape) {
@@ -1476,11 +1498,10 @@ int Model::forward_one(const float* x, const uint8_t* x_u8, int batch, float* lo
 }
 
 // One chunk captured into a graph on cap_stream; the graph is destroyed on every failure path.
-int Model::capture_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1,
-                         cudaGraph_t* out) {
+int Model::capture_chunk(ChunkPlan& p, InRef in, float* logits, int32_t* top1, cudaGraph_t* out) {
     *out = nullptr;
     RNB_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
-    const int r = enqueue_chunk(p, x, x_u8, logits, top1, cap_stream);
+    const int r = enqueue_chunk(p, in, logits, top1, cap_stream);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
     if (r || ce != cudaSuccess) {
@@ -1520,6 +1541,9 @@ int Model::warmup(int batch, bool include_u8) {
     int r = forward(x, batch, scratch_logits, host_top1_dev, host_compute);
     if (!r && include_u8)
         r = forward_u8(reinterpret_cast<const uint8_t*>(x), batch, scratch_logits, host_top1_dev, host_compute);
+    // the graph of the host paths' BF16 input form (host_pack.h), unless packing is ruled out already
+    if (!r && accepts_bf16_input() && host_pack_mode != 0)
+        r = forward_bf16(reinterpret_cast<const uint16_t*>(x), batch, scratch_logits, host_top1_dev, host_compute);
     cudaError_t ce = cudaStreamSynchronize(host_compute);
     cudaFree(x);
     if (r) return r;
@@ -1649,6 +1673,71 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
     return RNB_OK;
 }
 
+// FP32 host input of a BF16-stem model: round on the host, upload half the bytes? Decided once per model (see model.h).
+bool Model::host_pack_for(const float* x, int batch, uint16_t** stage, float* x_dev) {
+    host_pack_last = 0;
+    if (!accepts_bf16_input() || (fp8 && !fp8_calibrated)) return false;   // (calibration reads the FP32 image)
+    if (host_pack_mode < 0) {
+        const char* e = getenv("RNB_HOST_PACK");
+        if (e && (atoi(e) == 0 || atoi(e) == 1)) host_pack_mode = atoi(e);
+    }
+    if (host_pack_mode == 0) return false;
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, x) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const int kind = pinned ? 1 : 0;
+    host_pack_last_kind = kind;
+    if (host_pack_mode < 0 && host_pack_decided[kind] == 0) return false;
+    const size_t img_elems = 3ull * image * image;
+    if (!*stage && cudaHostAlloc(reinterpret_cast<void**>(stage), 1ull * max_batch * img_elems * sizeof(uint16_t),
+                                 cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        *stage = nullptr;
+        host_pack_mode = 0;   // no pinned memory to stage in: the plain copy still works
+        return false;
+    }
+    if (host_pack_mode == 1 || host_pack_decided[kind] == 1) {
+        host_pack_last = 1;
+        return true;
+    }
+    // Time both forms on samples of this very batch (its memory: pinned or pageable, its NUMA placement): the
+    // conversion with the pool, then a plain FP32 copy and a BF16 copy of the same images. Two rounds, the second
+    // one counts — on OTHER images where the batch has them, so that the conversion reads memory, not cache.
+    using clk = std::chrono::steady_clock;
+    const int ns = std::min(batch, 32);
+    const size_t n = static_cast<size_t>(ns) * img_elems;
+    HostPacker& hp = HostPacker::instance();
+    double t[3] = {0, 0, 0};
+    for (int rep = 0; rep < 2; ++rep) {
+        const float* xs = x + (rep == 1 && batch >= 2 * ns ? n : 0);
+        auto t0 = clk::now();
+        hp.run(xs, *stage, n, n, [](size_t, size_t) {});
+        t[0] = std::chrono::duration<double>(clk::now() - t0).count();
+        for (int form = 1; form <= 2; ++form) {
+            cudaStreamSynchronize(copy_stream);
+            t0 = clk::now();
+            if (form == 1) cudaMemcpyAsync(x_dev, xs, n * sizeof(float), cudaMemcpyHostToDevice, copy_stream);
+            else cudaMemcpyAsync(x_dev, *stage, n * sizeof(uint16_t), cudaMemcpyHostToDevice, copy_stream);
+            cudaStreamSynchronize(copy_stream);
+            t[form] = std::chrono::duration<double>(clk::now() - t0).count();
+        }
+    }
+    if (cudaGetLastError() != cudaSuccess) {
+        host_pack_decided[kind] = 0;
+        return false;
+    }
+    for (int i = 0; i < 3; ++i) host_pack_gbps[kind][i] = (i == 2 ? 2.0 : 4.0) * n / std::max(t[i], 1e-9) * 1e-9;
+    // packed: conversion and the half-size copy overlap piece by piece; it has to beat the plain copy clearly
+    host_pack_decided[kind] = std::max(t[0], t[2]) < 0.85 * t[1] ? 1 : 0;
+    if (getenv("RNB_VERBOSE"))
+        fprintf(stderr, "rnb host pack (%s input): %d threads convert %.1f GB/s (FP32 read), H2D FP32 %.1f GB/s, H2D BF16 "
+                        "%.1f GB/s -> %s\n", pinned ? "pinned" : "pageable", hp.threads(), host_pack_gbps[kind][0],
+                host_pack_gbps[kind][1], host_pack_gbps[kind][2],
+                host_pack_decided[kind] ? "round to BF16 on the host" : "plain FP32 copy");
+    host_pack_last = host_pack_decided[kind];
+    return host_pack_last == 1;
+}
+
 int Model::forward_host(const float* x, int batch, float* logits, int32_t* top1) {
     if (batch <= 0 || batch > max_batch) {
         set_error("batch must be in [1, max_batch]");
@@ -1674,20 +1763,38 @@ int Model::forward_host(const float* x, int batch, float* logits, int32_t* top1)
         copy_events.push_back(e);
     }
     cudaStream_t compute = host_compute;
-    for (int c = 0; c < nchunks; ++c) {
-        const int off = c * hchunk;
-        const int n = std::min(hchunk, batch - off);
-        RNB_CUDA(cudaMemcpyAsync(host_x_dev + off * img_elems, x + off * img_elems,
-                                 n * img_elems * sizeof(float), cudaMemcpyHostToDevice, copy_stream));
-        RNB_CUDA(cudaEventRecord(copy_events[c], copy_stream));
-    }
-    for (int c = 0; c < nchunks; ++c) {
-        const int off = c * hchunk;
-        const int n = std::min(hchunk, batch - off);
-        RNB_CUDA(cudaStreamWaitEvent(compute, copy_events[c], 0));
-        int r = forward(host_x_dev + off * img_elems, n, host_logits_dev + 1ull * off * classes,
-                        host_top1_dev + off, compute);
-        if (r) return r;
+    if (host_pack_for(x, batch, &host_stage, host_x_dev)) {
+        // the host cores round piece c to BF16 while piece c-1 crosses PCIe and piece c-2 runs
+        uint16_t* xd = reinterpret_cast<uint16_t*>(host_x_dev);
+        int rc = RNB_OK;
+        cudaError_t ce = cudaSuccess;
+        HostPacker::instance().run(x, host_stage, batch * img_elems, hchunk * img_elems, [&](size_t first, size_t count) {
+            if (rc != RNB_OK || ce != cudaSuccess) return;
+            const int off = static_cast<int>(first / img_elems), n = static_cast<int>(count / img_elems);
+            ce = cudaMemcpyAsync(xd + first, host_stage + first, count * sizeof(uint16_t), cudaMemcpyHostToDevice, copy_stream);
+            if (ce == cudaSuccess) ce = cudaEventRecord(copy_events[off / hchunk], copy_stream);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(compute, copy_events[off / hchunk], 0);
+            if (ce == cudaSuccess)
+                rc = forward_bf16(xd + first, n, host_logits_dev + 1ull * off * classes, host_top1_dev + off, compute);
+        });
+        RNB_CUDA(ce);
+        if (rc) return rc;
+    } else {
+        for (int c = 0; c < nchunks; ++c) {
+            const int off = c * hchunk;
+            const int n = std::min(hchunk, batch - off);
+            RNB_CUDA(cudaMemcpyAsync(host_x_dev + off * img_elems, x + off * img_elems,
+                                     n * img_elems * sizeof(float), cudaMemcpyHostToDevice, copy_stream));
+            RNB_CUDA(cudaEventRecord(copy_events[c], copy_stream));
+        }
+        for (int c = 0; c < nchunks; ++c) {
+            const int off = c * hchunk;
+            const int n = std::min(hchunk, batch - off);
+            RNB_CUDA(cudaStreamWaitEvent(compute, copy_events[c], 0));
+            int r = forward(host_x_dev + off * img_elems, n, host_logits_dev + 1ull * off * classes,
+                            host_top1_dev + off, compute);
+            if (r) return r;
+        }
     }
     if (logits)
         RNB_CUDA(cudaMemcpyAsync(logits, host_logits_dev, 1ull * batch * classes * sizeof(float),
@@ -1735,13 +1842,32 @@ int Model::submit_host_any(int slot, const void* x, bool u8, int batch, float* l
         RNB_CUDA(cudaEventCreateWithFlags(&hs.done, cudaEventDisableTiming));
     }
     if (!pipe_compute) RNB_CUDA(cudaStreamCreateWithFlags(&pipe_compute, cudaStreamNonBlocking));
-    // uint8 input: a quarter of the bytes cross PCIe (the device buffer is reused as a byte buffer)
-    RNB_CUDA(cudaMemcpyAsync(hs.x_dev, x, batch * img_elems * (u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice,
-                             copy_stream));
-    RNB_CUDA(cudaEventRecord(hs.copied, copy_stream));
-    RNB_CUDA(cudaStreamWaitEvent(pipe_compute, hs.copied, 0));
-    int r = u8 ? forward_u8(reinterpret_cast<const uint8_t*>(hs.x_dev), batch, hs.logits_dev, hs.top1_dev, pipe_compute)
+    int r;
+    if (!u8 && host_pack_for(static_cast<const float*>(x), batch, &hs.stage, hs.x_dev)) {
+        // FP32 input of a BF16-stem model: the host cores round it to BF16 (bit for bit what the stem would do) in
+        // 16-image pieces, each uploaded as soon as it is complete — half the bytes cross PCIe. This call returns when
+        // the last piece is queued; the GPU is busy with the other slot's batch meanwhile.
+        uint16_t* xd = reinterpret_cast<uint16_t*>(hs.x_dev);
+        uint16_t* stage = hs.stage;
+        cudaError_t ce = cudaSuccess;
+        HostPacker::instance().run(static_cast<const float*>(x), stage, batch * img_elems, 16 * img_elems,
+                                   [&](size_t first, size_t count) {
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(xd + first, stage + first, count * sizeof(uint16_t), cudaMemcpyHostToDevice, copy_stream);
+        });
+        RNB_CUDA(ce);
+        RNB_CUDA(cudaEventRecord(hs.copied, copy_stream));
+        RNB_CUDA(cudaStreamWaitEvent(pipe_compute, hs.copied, 0));
+        r = forward_bf16(xd, batch, hs.logits_dev, hs.top1_dev, pipe_compute);
+    } else {
+        // uint8 input: a quarter of the bytes cross PCIe (the device buffer is reused as a byte buffer)
+        RNB_CUDA(cudaMemcpyAsync(hs.x_dev, x, batch * img_elems * (u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice,
+                                 copy_stream));
+        RNB_CUDA(cudaEventRecord(hs.copied, copy_stream));
+        RNB_CUDA(cudaStreamWaitEvent(pipe_compute, hs.copied, 0));
+        r = u8 ? forward_u8(reinterpret_cast<const uint8_t*>(hs.x_dev), batch, hs.logits_dev, hs.top1_dev, pipe_compute)
                : forward(hs.x_dev, batch, hs.logits_dev, hs.top1_dev, pipe_compute);
+    }
     if (r) return r;
     if (logits)
         RNB_CUDA(cudaMemcpyAsync(logits, hs.logits_dev, 1ull * batch * classes * sizeof(float),

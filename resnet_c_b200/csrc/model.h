@@ -82,6 +82,18 @@ private:
     size_t total_ = 0;
 };
 
+// One batch of input images on the device, in one of the accepted formats (every format has 3 * image * image
+// elements per image, so a sub-batch is an element offset away).
+struct InRef {
+    enum Kind { F32_NCHW = 0, U8_HWC = 1, BF16_NCHW = 2 };
+    const void* p = nullptr;
+    int kind = F32_NCHW;
+    size_t elem_bytes() const { return kind == F32_NCHW ? 4 : kind == U8_HWC ? 1 : 2; }
+    InRef at(size_t elems) const { return InRef{p ? static_cast<const char*>(p) + elems * elem_bytes() : nullptr, kind}; }
+    const float* f32() const { return kind == F32_NCHW ? static_cast<const float*>(p) : nullptr; }
+    const uint8_t* u8() const { return kind == U8_HWC ? static_cast<const uint8_t*>(p) : nullptr; }
+};
+
 struct Model {
     std::string arch;
     int esz = 2;            // activation bytes: 1 fp8 (E4M3), 2 bf16, 4 tf32
@@ -134,7 +146,7 @@ struct Model {
 
     Arena arena;
     std::map<int, ChunkPlan> plans;
-    // CUDA graphs: one captured chunk per (n | u8 flag << 30, x, logits, top1). At most kGraphsPerShape executables
+    // CUDA graphs: one captured chunk per (n | input kind << 29, x, logits, top1). At most kGraphsPerShape executables
     // are kept per (n, u8) shape; a call with new pointers beyond that RE-TARGETS the least recently used one with
     // cudaGraphExecUpdate (a re-capture, no instantiation), so a caller that allocates fresh outputs every call pays
     // ~0.1 ms of host time, not an instantiate, and nothing is ever flushed wholesale.
@@ -146,7 +158,7 @@ struct Model {
     static constexpr int kGraphsPerShape = 4;
     std::map<GraphKey, GraphEntry> graphs;
     uint64_t graph_clock = 0;
-    int capture_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1, cudaGraph_t* out);
+    int capture_chunk(ChunkPlan& p, InRef in, float* logits, int32_t* top1, cudaGraph_t* out);
     // All forwards of a model share ONE activation arena: every enqueue waits for the previous one (whatever stream it
     // went to) and leaves an event behind, so forward() on two streams, forward_host() and submit_host() never overlap
     // on the arena. Same-stream back-to-back forwards pay one event record per call.
@@ -199,9 +211,9 @@ struct Model {
     std::map<int, int> lane_choice;       // batch -> 1 | 2
     cudaEvent_t lane_fork = nullptr, lane_join = nullptr;
     int make_lane();
-    int forward_one(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1, cudaStream_t s);
-    int forward_two(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1, cudaStream_t s);
-    int lanes_for(int batch, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1, cudaStream_t s);
+    int forward_one(InRef in, int batch, float* logits, int32_t* top1, cudaStream_t s);
+    int forward_two(InRef in, int batch, float* logits, int32_t* top1, cudaStream_t s);
+    int lanes_for(int batch, InRef in, float* logits, int32_t* top1, cudaStream_t s);
 
     ~Model();
     int load(const std::string& arch, int dtype, const std::string& dir, int max_batch, int chunk);
@@ -215,16 +227,32 @@ struct Model {
     template <class F> void for_each_weight(F&& f);  // every device weight buffer, deterministic order
     void* blob = nullptr;                        // load_packed(): the one device allocation all weights point into
     ChunkPlan* plan_for(int n);
-    // x_u8 != nullptr: decoded uint8 HWC input (x is then ignored), normalised with norm_mean / norm_std
-    int enqueue_chunk(ChunkPlan& p, const float* x, const uint8_t* x_u8, float* logits, int32_t* top1, cudaStream_t s);
+    // uint8 HWC input is normalised with norm_mean / norm_std; BF16 NCHW input needs the BF16 tensor-core stem
+    int enqueue_chunk(ChunkPlan& p, InRef in, float* logits, int32_t* top1, cudaStream_t s);
     int enqueue_fc(ChunkPlan& p, float* logits, cudaStream_t s);
     int forward(const float* x, int batch, float* logits, int32_t* top1, cudaStream_t s);
     int forward_u8(const uint8_t* x, int batch, float* logits, int32_t* top1, cudaStream_t s);
-    int forward_any(const float* x, const uint8_t* x_u8, int batch, float* logits, int32_t* top1, cudaStream_t s);
+    // x = the FP32 image rounded to BF16 (nearest-even), NCHW: bit-identical to forward() on the BF16 / FP8 paths
+    int forward_bf16(const uint16_t* x, int batch, float* logits, int32_t* top1, cudaStream_t s);
+    bool accepts_bf16_input() const { return stem_tc && stem_esz() == 2 && stem_fused_enabled(); }
+    int forward_any(InRef in, int batch, float* logits, int32_t* top1, cudaStream_t s);
     int set_normalization(const float* mean, const float* std);
     int forward_host(const float* x, int batch, float* logits, int32_t* top1);
+    // Host packing (host_pack.h): FP32 host input of a BF16-stem model is rounded to BF16 by the host cores and half the
+    // bytes cross PCIe. host_pack_mode: 0 / 1 forced (RNB_HOST_PACK, rnb_model_set_host_pack), -1 = the first host call
+    // with pageable input and the first with pinned input each time the conversion and both copies on a sample of
+    // their own batch and keep the faster form for that kind of memory. A group (rnb_group_*) turns it off: its
+    // replicas are fed one after the other by ONE host thread.
+    int host_pack_mode = -1;
+    int host_pack_decided[2] = {-1, -1};    // auto mode: [pageable, pinned] -> 0 | 1
+    int host_pack_last = -1;                // what the most recent host call did
+    double host_pack_gbps[2][3] = {{0, 0, 0}, {0, 0, 0}};   // per kind of memory: conversion (FP32 bytes read), FP32 H2D, BF16 H2D
+    int host_pack_last_kind = 0;
+    uint16_t* host_stage = nullptr;          // pinned staging of forward_host
+    bool host_pack_for(const float* x, int batch, uint16_t** stage, float* x_dev);
     // pipelined host path: two slots, each with its own device input / output buffers
     struct HostSlot {
+        uint16_t* stage = nullptr;   // pinned: the batch rounded to BF16 by the host cores (host_pack.h)
         float* x_dev = nullptr;
         float* logits_dev = nullptr;
         int32_t* top1_dev = nullptr;

@@ -20,6 +20,8 @@
 //    row that does not read input row t has zero weights in its half of A, so there are no special cases.
 //  * the input streams through a ring of eight 4-row chunks; three loader warps build the NHWC4 BF16 rows straight
 //    from the caller's FP32 NCHW tensor (MODE 1; an L2 prefetch runs three chunks ahead) — there is no layout pre-pass.
+//    MODE 2 is the same loader over a BF16 NCHW tensor: what the host paths upload when they round the FP32 image
+//    to BF16 on the CPU (host_pack.cu) — the rounding this loader would apply anyway, at half the PCIe bytes.
 //    uint8 input keeps its normalising pre-pass and feeds the same kernel through bulk copies (MODE 0).
 //  * TWO MMA issuer warps take alternate pairs: the tensor pipe's queue holds about two MMAs, and one issuer's barrier
 //    polls and bookkeeping (~430 clocks per pair) left the pipe dry 40 % of the time.
@@ -31,7 +33,7 @@
 //    first computes the pair before its range to obtain it.
 //  * the eight epilogue warps never meet: each stages its [28 pooled columns][16 channels] block and sends it off with
 //    its own TMA store; the next pair's accumulators are requested as soon as this pair's are reduced.
-// Warps: 0, 2, 3 loaders (MODE 1) / 0 bulk-copy producer (MODE 0); 1 and 12 MMA issuers; 2 also TMEM alloc; 4..11
+// Warps: 0, 2, 3 loaders (MODE 1, 2) / 0 bulk-copy producer (MODE 0); 1 and 12 MMA issuers; 2 also TMEM alloc; 4..11
 // epilogue. TMEM: three accumulator slots of 112 columns + 144 columns of weights.
 #include <cstdint>
 #include <cstdio>
@@ -199,6 +201,43 @@ __device__ __forceinline__ void stem_fill_chunk_f32(uint32_t dst, const float* _
     }
 }
 
+// The same chunk from a BF16 NCHW tensor (MODE 2): 8-byte loads of 4 pixels per colour plane, RGB0 pixels assembled
+// with byte permutes — values already rounded by the host, so the ring holds bit for bit what MODE 1 builds.
+__device__ __forceinline__ void stem_fill_chunk_bf16(uint32_t dst, const uint16_t* __restrict__ x, int b, int c, int lane) {
+    if (c == 0 || c == PAIRS + 1) {
+        for (int i = lane; i < CHUNK_BYTES / 16; i += 32) st_shared_v4(dst + 16 * i, 0, 0, 0, 0);
+        return;
+    }
+    const uint16_t* img = x + (1LL * b * 3 * IMG + (4 * c - 4)) * IMG;
+    if (lane < 3 && c + 3 <= PAIRS) {
+        const uint16_t* nxt = img + 1LL * lane * IMG * IMG + 12 * IMG;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"(4 * IMG * 2) : "memory");
+    }
+    uint2 v[7][3];
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+        const int id = it * 32 + lane, rr = id / 56, g = id - rr * 56;
+        const uint16_t* src = img + rr * IMG + 4 * g;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+            v[it][ch] = __ldg(reinterpret_cast<const uint2*>(src + 1LL * ch * IMG * IMG));
+    }
+    const int first = (lane >> 2) & 1;
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+        const int id = it * 32 + lane, rr = id / 56, g = id - rr * 56;
+        uint4 h[2];
+        h[0].x = __byte_perm(v[it][0].x, v[it][1].x, 0x5410); h[0].y = v[it][2].x & 0xffffu;
+        h[0].z = __byte_perm(v[it][0].x, v[it][1].x, 0x7632); h[0].w = v[it][2].x >> 16;
+        h[1].x = __byte_perm(v[it][0].y, v[it][1].y, 0x5410); h[1].y = v[it][2].y & 0xffffu;
+        h[1].z = __byte_perm(v[it][0].y, v[it][1].y, 0x7632); h[1].w = v[it][2].y >> 16;
+        const uint32_t o = dst + rr * ROW_BYTES + 32 * g + 32;
+        const uint4 h0 = first ? h[1] : h[0], h1 = first ? h[0] : h[1];
+        st_shared_v4(o + 16 * first, h0.x, h0.y, h0.z, h0.w);
+        st_shared_v4(o + 16 * (first ^ 1), h1.x, h1.y, h1.z, h1.w);
+    }
+}
+
 constexpr int STEM_T_THREADS = 128 + EPI_THREADS + 32;   // warps 0..3, eight epilogue warps, the second MMA issuer
 constexpr int T_NBLK = 18;                 // A blocks: input row t = 0..8 of the pair x K step i
 constexpr int T_NSLOT = 3;                 // TMEM: D slots of 112 columns at 0, 112, 224; weights at 336 .. 479
@@ -304,7 +343,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restric
     griddep_launch_dependents();
     griddep_wait();
 
-    if (warp == 0 || (MODE == 1 && (warp == 2 || warp == 3))) {
+    if (warp == 0 || (MODE != 0 && (warp == 2 || warp == 3))) {
         // ===================================================== input: chunks into the ring, in stream order
         const int widx = warp == 0 ? 0 : warp - 1;
         for (StemSteps st(p_begin, p_end); !st.done(); st.next()) {
@@ -312,7 +351,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restric
             const int c_first = st.k() + 3 - nnew;
             for (int i = 0; i < nnew; ++i) {
                 const int n = st.cn + i, c = c_first + i;
-                if (MODE == 1 && (n % 3) != widx) continue;
+                if (MODE != 0 && (n % 3) != widx) continue;
                 mbar_wait(&ch_empty[n & (NCH - 1)], ((n / NCH) & 1) ^ 1);
                 uint8_t* dst = ring + (n & (NCH - 1)) * CHUNK_BYTES;
                 if (MODE == 0) {
@@ -323,7 +362,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restric
                     }
                     __syncwarp();
                 } else {
-                    stem_fill_chunk_f32(smem_u32(dst), static_cast<const float*>(xin), b, c, lane);
+                    if (MODE == 1) stem_fill_chunk_f32(smem_u32(dst), static_cast<const float*>(xin), b, c, lane);
+                    else stem_fill_chunk_bf16(smem_u32(dst), static_cast<const uint16_t*>(xin), b, c, lane);
                     fence_proxy_async_smem();
                     mbar_arrive(&ch_full[n & (NCH - 1)]);
                 }
@@ -505,6 +545,7 @@ cudaError_t launch_stem_tc_pack_weights(const float* w, const float* bn_w, const
 cudaError_t stem_tc_init() {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_T_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_T_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_T_SMEM);
     return e;
 }
 
@@ -520,7 +561,15 @@ static cudaError_t launch_stem_tc_kernel(int mode, const void* in, const void* w
     const uint32_t* wt = static_cast<const uint32_t*>(wk);
     if (mode == 0)
         return launch_pdl_small(stem_tc_kernel<0>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in, wt, bias, B);
+    if (mode == 2)
+        return launch_pdl_small(stem_tc_kernel<2>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in, wt, bias, B);
     return launch_pdl_small(stem_tc_kernel<1>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in, wt, bias, B);
+}
+
+// x BF16 NCHW [B,3,224,224] (the FP32 image rounded to nearest-even by the host, host_pack.cu) -> out: one launch
+cudaError_t launch_stem_tc_from_bf16(const void* x_bf16, const void* wk, const float* bias, void* out, int B,
+                                     cudaStream_t s) {
+    return launch_stem_tc_kernel(2, x_bf16, wk, bias, out, B, s);
 }
 
 // xp (packed NHWC4 BF16, written by a pack kernel) -> out NHWC bf16 [B,56,56,64]

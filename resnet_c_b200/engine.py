@@ -305,6 +305,31 @@ class ResNet:
             raise RnbError("submit_host takes a contiguous float32 host tensor")
         check(_lib.lib().rnb_model_submit_host(self._h, slot, _ptr(x), x.shape[0], _ptr(logits), _ptr(top1)))
 
+    def forward_bf16(self, x: torch.Tensor, logits=None, top1=None):
+        """x: [B,3,224,224] bfloat16 CUDA tensor = the FP32 image rounded to nearest even (what the packed host paths
+        upload). Bit-identical to forward() on the FP32 tensor; BF16 / FP8 models only."""
+        if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 4:
+            raise RnbError("forward_bf16 takes a [B,3,H,W] bfloat16 CUDA tensor")
+        x = x.contiguous()
+        B = x.shape[0]
+        if logits is None:
+            logits = torch.empty(B, self.num_classes, device=x.device, dtype=torch.float32)
+        if top1 is None:
+            top1 = torch.empty(B, device=x.device, dtype=torch.int32)
+        check(_lib.lib().rnb_model_forward_bf16(self._h, _ptr(x), B, _ptr(logits), _ptr(top1), _stream()))
+        return logits, top1
+
+    def set_host_pack(self, mode: int) -> None:
+        """Host paths: -1 decide by timing at the next host call, 0 plain FP32 copies, 1 round to BF16 on the host."""
+        check(_lib.lib().rnb_model_set_host_pack(self._h, int(mode)))
+
+    def host_pack(self) -> dict:
+        """Current choice of the host paths and what the decision measured (GB/s; zeros when forced)."""
+        g = (C.c_double * 3)()
+        choice = _lib.lib().rnb_model_host_pack(self._h, g)
+        return {"choice": choice, "threads": _lib.lib().rnb_host_pack_threads(), "convert_gbps": g[0],
+                "h2d_f32_gbps": g[1], "h2d_bf16_gbps": g[2]}
+
     def forward_u8(self, x: torch.Tensor, logits=None, top1=None):
         """x: [B,224,224,3] uint8 CUDA tensor (decoded, resized, cropped image, HWC). The /255 + mean/std
         normalisation of convert_imgs_to_bin.py:18 runs inside the stem's layout pre-pass."""

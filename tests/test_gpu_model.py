@@ -183,6 +183,60 @@ def test_uint8_input_path_is_bit_identical_to_float_input(arch, dtype, golden_di
     model.close()
 
 
+@pytest.mark.parametrize("arch,dtype,B", [("resnet50", "bf16", 37), ("resnet18", "bf16", 70), ("resnet50", "fp8", 20)])
+def test_host_packed_input_is_bit_identical_to_fp32_input(arch, dtype, B):
+    """The host paths' packed form (csrc/host_pack.cpp: the host cores round the FP32 image to BF16, half the bytes
+    cross PCIe, the stem loads BF16 NCHW — stem_tc_kernel<2>) against the plain FP32 form: identical logits and top-1
+    from rnb_model_forward_bf16 on a device tensor, from forward_host and from both slots of submit_host, with
+    pinned and pageable input and a batch that is not a multiple of the 16-image upload pieces."""
+    from resnet_c_b200 import weights
+    x = weights.synthetic_images(B, seed=7)
+    x[0, 0, 0, :4] = torch.tensor([-0.0, 1e-40, 1.00390625, -2.51171875])   # signed zero, a denormal, two ties
+    model = _model(arch, True, dtype, B)
+    want, want_top1 = model.forward(x.cuda())
+    got, got_top1 = model.forward_bf16(x.cuda().to(torch.bfloat16))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want) and torch.equal(got_top1, want_top1)
+    want, want_top1 = want.cpu(), want_top1.cpu()
+    for mode in (1, 0):
+        model.set_host_pack(mode)
+        for xin in (x.pin_memory(), x.clone()):
+            lh, th = model.forward_host(xin)
+            assert torch.equal(lh, want) and torch.equal(th, want_top1), (mode, xin.is_pinned())
+            outs = [(torch.empty(B, model.num_classes).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory())
+                    for _ in range(2)]
+            for slot in (0, 1):
+                model.submit_host(slot, xin, *outs[slot])
+            for slot in (0, 1):
+                model.wait_host(slot)
+                assert torch.equal(outs[slot][0], want) and torch.equal(outs[slot][1], want_top1), (mode, slot)
+        assert model.host_pack()["choice"] == mode
+    # left to itself the model times both forms on the first host call and keeps one of them
+    model.set_host_pack(-1)
+    lh, th = model.forward_host(x.pin_memory())
+    assert torch.equal(lh, want)
+    info = model.host_pack()
+    assert info["choice"] in (0, 1) and info["convert_gbps"] > 0 and info["h2d_f32_gbps"] > 0
+    model.close()
+
+
+def test_host_pack_is_refused_where_the_stem_takes_no_bf16_input():
+    from resnet_c_b200 import weights
+    from resnet_c_b200._lib import RnbError
+    model = _model("resnet18", True, "tf32", 2)
+    x = weights.synthetic_images(2)
+    with pytest.raises(RnbError):
+        model.set_host_pack(1)
+    with pytest.raises(RnbError):
+        model.forward_bf16(x.cuda().to(torch.bfloat16))
+    with pytest.raises(RnbError):
+        model.set_host_pack(2)
+    want, _ = model.forward(x.cuda())
+    lh, _ = model.forward_host(x.pin_memory())     # the plain path is what runs
+    assert torch.equal(lh, want.cpu()) and model.host_pack()["choice"] in (-1, 0)
+    model.close()
+
+
 def test_uint8_reference_image_top1(golden_dir):
     """The reference's own scenario from the decoded JPEG: ResNet-152 -> 176, ResNet-18 -> 238."""
     from resnet_c_b200 import weights

@@ -143,3 +143,50 @@ def test_c_abi_shard_rule_equals_python_rule():
     first, count = C.c_int(), C.c_int()
     assert lib.rnb_shard_bounds(10, 0, 0, C.byref(first), C.byref(count)) != 0
     assert b"bad argument" in lib.rnb_last_error()
+
+
+def _bf16_bits_torch(x: torch.Tensor) -> np.ndarray:
+    return x.to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+
+
+@pytest.mark.parametrize("n, offset", [(0, 0), (1, 0), (15, 0), (16, 0), (17, 3), (32768, 0), (32769, 1), (3 * 224 * 224 * 5 + 7, 0)])
+def test_host_bf16_rounding_is_round_to_nearest_even(n, offset):
+    """rnb_f32_to_bf16_host (the host cores' half of the packed host paths, csrc/host_pack.cpp) against torch's
+    FP32 -> BF16 cast, bit for bit: random values of every magnitude, ties, denormals, infinities; ragged sizes and
+    a destination that is not 32-byte aligned (vector body + scalar tail, streaming and plain stores)."""
+    from resnet_c_b200 import _lib
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(1234 + n)
+    bits = torch.randint(-2**31, 2**31 - 1, (n,), generator=g, dtype=torch.int64).to(torch.int32)
+    x = bits.view(torch.float32).clone()
+    if n >= 16:
+        special = torch.tensor([0.0, -0.0, float("inf"), -float("inf"), 1.0, 1.00390625, 1.01171875, 3.3895314e38,
+                                1e-40, -1e-40, 1.1754944e-38, 65504.0, 0.5 + 2**-9, 0.5 + 3 * 2**-9, -2.5, 1e-45],
+                               dtype=torch.float32)
+        x[:16] = special
+    finite_or_inf = ~torch.isnan(x)
+    out = np.zeros(n + 64, dtype=np.uint16)
+    dst = out[offset:offset + n]
+    assert lib.rnb_f32_to_bf16_host(x.data_ptr(), dst.ctypes.data, n) == 0
+    want = _bf16_bits_torch(x)
+    m = finite_or_inf.numpy()
+    np.testing.assert_array_equal(dst[m], want[m])
+    # NaN: the GPU's cvt.rn.bf16.f32 produces the canonical 0x7FFF, and so does the host
+    assert (dst[~m] == 0x7FFF).all()
+    assert (out[:offset] == 0).all() and (out[offset + n:] == 0).all()   # nothing written outside [0, n)
+    assert lib.rnb_host_pack_threads() >= 1
+
+
+def test_host_bf16_rounding_thread_count_follows_the_environment():
+    code = ("from resnet_c_b200 import _lib; import numpy as np; l = _lib.lib(); print(l.rnb_host_pack_threads());"
+            "x = np.linspace(-3, 3, 200001, dtype=np.float32); o = np.zeros_like(x, dtype=np.uint16);"
+            "assert l.rnb_f32_to_bf16_host(x.ctypes.data, o.ctypes.data, x.size) == 0;"
+            "print(int(o.astype(np.uint64).sum()))")
+    outs = []
+    for threads in ("1", "3"):
+        env = dict(os.environ, RNB_HOST_THREADS=threads, PYTHONPATH=str(ROOT))
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
+        lines = r.stdout.split()
+        assert lines[0] == threads
+        outs.append(lines[1])
+    assert outs[0] == outs[1]   # the partitioning does not change the result
