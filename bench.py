@@ -391,6 +391,7 @@ def main():
     lh = torch.empty(B, classes, dtype=torch.float32).pin_memory()
     th = torch.empty(B, dtype=torch.int32).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
+    barrier()   # the first host call times host cores and PCIe (host packing): every rank at once, as in the loop below
     for _ in range(2):
         model.forward_host(xh, lh, th)
     barrier()
@@ -421,22 +422,25 @@ def main():
         model.wait_host((e2e_steps - 1) & 1)
         return total_images * e2e_steps / max_over_ranks(time.perf_counter() - t0)
 
-    # Host packing (csrc/host_pack.cpp): on the BF16 / FP8 paths the host cores round the FP32 batch to BF16 — what
-    # the stem does first anyway, bit-identical — and half the bytes cross PCIe. The model decided for or against it
-    # by timing both forms during the forward_host warm-up above; `e2e.value` is the form it chose, and when that is
-    # the packed form the plain FP32-copy form is timed beside it.
+    # Host packing (csrc/host_pack.cpp): on the BF16 / FP8 paths the host cores round the leading images of every FP32
+    # batch to BF16 — what the stem does first anyway, bit-identical — so that half their bytes cross PCIe, while the
+    # other images cross as FP32; the model fixed the proportion by timing conversion and copies during the
+    # forward_host warm-up above. `e2e.value` is the form it chose; when that involves the host cores, the plain
+    # FP32-copy form is timed beside it.
     e2e_value = serve_loop()
     same = same and bool((th2[0].to(dev) == top1).all().item())
     host_pack = model.host_pack() if hasattr(model, "host_pack") else {"choice": 0}
     packed = host_pack.get("choice") == 1
     e2e_plain_value = None
-    if packed:
+    # (every rank decides for itself, and serve_loop() holds collectives: the ranks must agree on running it again)
+    if max_over_ranks(1.0 if packed else 0.0) > 0:
         model.set_host_pack(0)
         e2e_plain_value = serve_loop()
         same = same and bool((th2[0].to(dev) == top1).all().item())
-        model.set_host_pack(1)
+        model.set_host_pack_fraction(host_pack.get("fraction", 0.0))
     img_bytes = 3 * 224 * 224 * 4
-    h2d_bytes = B * img_bytes // 2 if packed else B * img_bytes
+    n_packed = int(round(host_pack.get("fraction", 0.0) * B)) if packed else 0
+    h2d_bytes = n_packed * img_bytes // 2 + (B - n_packed) * img_bytes
 
     # ---- the same serving loop fed with DECODED uint8 HWC images (rnb_model_submit_host_u8): the /255 +
     # mean/std normalisation of convert_imgs_to_bin.py:18 runs on the GPU inside the stem pre-pass, so a
@@ -582,8 +586,9 @@ def main():
                 "d2h_bytes_per_step": B * classes * 4 + B * 4, "steps": e2e_steps,
                 "mode": "rnb_model_submit_host / rnb_model_wait_host, 2 host batches in flight "
                         "(H2D of step i+1 overlaps the forward of step i); FP32 NCHW input in pinned host buffers"
-                        + ("; the host cores round each batch to BF16 inside submit (bit-identical to the stem's own "
-                           "rounding) and BF16 crosses PCIe" if packed else "; FP32 crosses PCIe"),
+                        + (f"; the host cores round {n_packed} of the {B} images of each batch to BF16 inside submit "
+                           f"(bit-identical to the stem's own rounding), those cross PCIe as BF16, the others as FP32"
+                           if packed else "; FP32 crosses PCIe"),
                 "host_input_bytes_per_step": B * img_bytes,
                 "host_pack": host_pack,
                 "fp32_copy_value": e2e_plain_value,

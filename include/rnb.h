@@ -108,10 +108,12 @@ int rnb_model_forward(rnb_model_t* m, const float* x_dev, int batch, float* logi
  * Host packing (BF16 and FP8 models, 224 x 224): the stem's first act on an FP32 image is to round it to BF16, and
  * 602 KB per image over PCIe bounds the end-to-end rate, so the host paths can round on the HOST cores (a pool of
  * up to 16 threads, RNB_HOST_THREADS; the same round-to-nearest-even, results bit-identical) into a pinned staging
- * buffer and upload half the bytes, piece by piece while the next piece is being rounded. Pageable input then needs
- * no driver staging either. The first host call of a model with pageable input, and the first with pinned input,
- * time both forms on a sample of their batch and keep the faster one for that kind of memory; RNB_HOST_PACK=0 / 1
- * or rnb_model_set_host_pack() force it. */
+ * buffer and upload half the bytes, piece by piece while the next piece is being rounded. Cores and link share a
+ * batch: the leading images go through the cores as BF16 while the rest crosses the link as FP32, in the proportion
+ * that lets both finish together (the stem reads either form). Pageable input then needs no driver staging either.
+ * The first host call of a model with pageable input, and the first with pinned input, time conversion and copies on
+ * samples of their batch and fix that proportion for that kind of memory (none, if the plain copy is not clearly
+ * slower); RNB_HOST_PACK=0 / 1 or rnb_model_set_host_pack() force none / all. */
 int rnb_model_forward_host(rnb_model_t* m, const float* x_host, int batch, float* logits_host,
                            int32_t* top1_host);
 
@@ -125,12 +127,16 @@ int rnb_model_submit_host(rnb_model_t* m, int slot, const float* x_host, int bat
 int rnb_model_wait_host(rnb_model_t* m, int slot);
 
 /* Host packing control and introspection. mode: -1 decide by timing at the next host call (default), 0 plain FP32
- * copies, 1 round to BF16 on the host (RNB_ERR_UNSUPPORTED on a model whose stem does not take BF16 input: tf32,
- * or images other than 224 x 224). rnb_model_host_pack() returns what the most recent host call did (0 / 1; -1 =
- * nothing decided yet) and, when gbps != NULL, what that decision measured: conversion rate (FP32 bytes read), FP32
- * H2D, BF16 H2D, in GB/s (zeros when it was forced). rnb_host_pack_threads(): threads a conversion uses, the caller included. */
+ * copies, 1 round every image to BF16 on the host (RNB_ERR_UNSUPPORTED on a model whose stem does not take BF16
+ * input: tf32, or images other than 224 x 224). rnb_model_host_pack() returns what the most recent host call did
+ * (0 none / 1 some or all; -1 = no host call yet) and, when info != NULL: info[0..2] = what the decision measured —
+ * conversion rate (FP32 bytes read), FP32 H2D, BF16 H2D, in GB/s (zeros when forced) — and info[3] = the fraction
+ * of a batch's images rounded on the host. rnb_host_pack_threads(): threads a conversion uses, caller included. */
 int rnb_model_set_host_pack(rnb_model_t* m, int mode);
-int rnb_model_host_pack(const rnb_model_t* m, double gbps[3]);
+/* Fixes the proportion instead of measuring it: `fraction` of every batch's images (in whole 16-image pieces) is
+ * rounded on the host, the rest crosses PCIe as FP32. 0 <= fraction <= 1. */
+int rnb_model_set_host_pack_fraction(rnb_model_t* m, double fraction);
+int rnb_model_host_pack(const rnb_model_t* m, double info[4]);
 int rnb_host_pack_threads(void);
 /* The conversion itself on host memory (no GPU involved): dst[i] = BF16(src[i]), round to nearest even, NaN ->
  * 0x7FFF, by the same thread pool. What the packed host paths upload. */

@@ -338,17 +338,37 @@ int rnb_model_set_host_pack(rnb_model_t* m, int mode) {
     m->impl.host_pack_mode = mode;
     m->impl.host_pack_last = mode;
     for (int k = 0; k < 2; ++k) {
-        m->impl.host_pack_decided[k] = -1;
+        m->impl.host_pack_frac[k] = -1;
         for (double& g : m->impl.host_pack_gbps[k]) g = 0;
     }
     return RNB_OK;
 }
 
-int rnb_model_host_pack(const rnb_model_t* m, double gbps[3]) {
+int rnb_model_set_host_pack_fraction(rnb_model_t* m, double fraction) {
+    if (!m || !(fraction >= 0.0 && fraction <= 1.0)) {
+        set_error("rnb_model_set_host_pack_fraction: NULL model or fraction outside [0, 1]");
+        return RNB_ERR_INVALID;
+    }
+    if (fraction > 0 && !m->impl.accepts_bf16_input()) {
+        set_error("rnb_model_set_host_pack_fraction: this model's stem does not take BF16 input");
+        return RNB_ERR_UNSUPPORTED;
+    }
+    m->impl.host_pack_mode = -1;
+    m->impl.host_pack_last = -1;
+    for (int k = 0; k < 2; ++k) {
+        m->impl.host_pack_frac[k] = fraction;
+        for (double& g : m->impl.host_pack_gbps[k]) g = 0;
+    }
+    return RNB_OK;
+}
+
+int rnb_model_host_pack(const rnb_model_t* m, double info[4]) {
     if (!m) return -1;
-    if (gbps)
-        for (int i = 0; i < 3; ++i) gbps[i] = m->impl.host_pack_gbps[m->impl.host_pack_last_kind][i];
-    return m->impl.host_pack_last;
+    if (info) {
+        for (int i = 0; i < 3; ++i) info[i] = m->impl.host_pack_gbps[m->impl.host_pack_last_kind][i];
+        info[3] = std::max(0.0, m->impl.host_pack_last);
+    }
+    return m->impl.host_pack_last < 0 ? -1 : m->impl.host_pack_last > 0 ? 1 : 0;
 }
 
 int rnb_host_pack_threads(void) { return rnb::HostPacker::instance().threads(); }

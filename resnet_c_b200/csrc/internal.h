@@ -140,9 +140,10 @@ cudaError_t launch_stem_tc_part(int part, const float* x, void* xp, const void* 
 // the kernel fed from an already packed tensor (uint8 input: launch_stem_tc_pack_u8 first)
 cudaError_t launch_stem_tc_from_packed(const void* xp, const void* wk, const float* bias, void* out, int B,
                                        cudaStream_t s);
-// the kernel fed from a BF16 NCHW tensor (the FP32 image rounded to nearest-even on the host: host_pack.cu)
-cudaError_t launch_stem_tc_from_bf16(const void* x_bf16, const void* wk, const float* bias, void* out, int B,
-                                     cudaStream_t s);
+// the kernel fed with images [0, nb) from a BF16 NCHW tensor (the FP32 image rounded to nearest-even on the host:
+// host_pack.cpp) and images [nb, B) from an FP32 NCHW tensor, both indexed by the image number in the batch
+cudaError_t launch_stem_tc_from_mixed(const void* x_bf16, const float* x_f32, int nb, const void* wk, const float* bias,
+                                      void* out, int B, cudaStream_t s);
 
 // Decoded-image input (uint8 HWC [B][224][224][3]) with the /255 + mean/std normalisation of
 // convert_imgs_to_bin.py:18 fused in: straight into the packed stem input (BF16 path) ...

@@ -166,11 +166,13 @@ Model::~Model() {
     for (auto e : join_ev) if (e) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (pipe_compute) cudaStreamDestroy(pipe_compute);
+    if (pipe_d2h) cudaStreamDestroy(pipe_d2h);
     for (HostSlot& hs : slots) {
         cudaFree(hs.x_dev); cudaFree(hs.logits_dev); cudaFree(hs.top1_dev);
         if (hs.stage) cudaFreeHost(hs.stage);
         if (hs.copied) cudaEventDestroy(hs.copied);
         if (hs.done) cudaEventDestroy(hs.done);
+        if (hs.computed) cudaEventDestroy(hs.computed);
     }
     arena.free_all();
     cudaFree(u8_scratch);
@@ -1073,7 +1075,7 @@ int Model::enqueue_chunk(ChunkPlan& p, InRef in, float* logits, int32_t* top1, c
             RNB_CUDA(launch_stem_tc_pack_u8(x_u8, p.stem_out, n, norm_mean, norm_std, s));
             RNB_CUDA(launch_stem_tc_from_packed(p.stem_out, stem_wk, stem_bias, pool, n, s));
         } else if (in.kind == InRef::BF16_NCHW) {
-            RNB_CUDA(launch_stem_tc_from_bf16(in.p, stem_wk, stem_bias, pool, n, s));
+            RNB_CUDA(launch_stem_tc_from_mixed(in.p, in.p2, std::min(in.nb, n), stem_wk, stem_bias, pool, n, s));
         } else {
             RNB_CUDA(launch_stem_any_part(stem_esz(), 0, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
             RNB_CUDA(launch_stem_any_part(stem_esz(), 1, x, p.stem_out, stem_wk, stem_bias, pool, n, s));
@@ -1275,7 +1277,7 @@ int Model::forward_bf16(const uint16_t* x, int batch, float* logits, int32_t* to
         set_error("BF16 NCHW input needs the one-launch BF16 tensor-core stem (bf16 / fp8 model, 224 x 224)");
         return RNB_ERR_UNSUPPORTED;
     }
-    return forward_any(InRef{x, InRef::BF16_NCHW}, batch, logits, top1, s);
+    return forward_any(InRef{x, InRef::BF16_NCHW, nullptr, batch}, batch, logits, top1, s);
 }
 
 int Model::set_normalization(const float* mean, const float* std) {
@@ -1332,7 +1334,7 @@ int Model::forward_two(InRef in, int batch, float* logits, int32_t* top1, cudaSt
     RNB_CUDA(cudaStreamWaitEvent(s2, lane_fork, 0));
     int r = forward_one(in, n0, logits, top1, s);
     if (r) return r;
-    r = lane2->forward_one(in.at(n0 * img), n1,
+    r = lane2->forward_one(in.at(n0, img), n1,
                            logits ? logits + 1ull * n0 * classes : nullptr, top1 ? top1 + n0 : nullptr, s2);
     if (r) return r;
     RNB_CUDA(cudaEventRecord(lane_join, s2));
@@ -1441,7 +1443,7 @@ int Model::forward_one(InRef in, int batch, float* logits, int32_t* top1, cudaSt
         const int n = std::min(chunk, batch - off);
         ChunkPlan* p = plan_for(n);
         if (!p) return RNB_ERR_CUDA;
-        const InRef inc = in.at(off * img_elems);
+        const InRef inc = in.at(off, img_elems);
         float* lc = logits + 1ull * off * classes;
         int32_t* tc = top1 ? top1 + off : nullptr;
         if (!use_graph) {
@@ -1449,8 +1451,10 @@ int Model::forward_one(InRef in, int batch, float* logits, int32_t* top1, cudaSt
             if (r) return r;
             continue;
         }
-        const int shape = n | (inc.kind << 29);   // (U8_HWC = bit 29, BF16_NCHW = bit 30)
-        const GraphKey key{shape, inc.p, lc, tc};
+        // (U8_HWC = bit 29, BF16_NCHW = bit 30; the count of BF16 images of a mixed batch above bit 32)
+        const int64_t shape = n | (inc.kind << 29) |
+                              (inc.kind == InRef::BF16_NCHW ? static_cast<int64_t>(std::min(inc.nb, n)) << 32 : 0);
+        const GraphKey key{shape, inc.p, inc.p2, lc, tc};
         auto g = graphs.find(key);
         if (g == graphs.end()) {
             // executables already held for this shape, least recently used first
@@ -1542,7 +1546,7 @@ int Model::warmup(int batch, bool include_u8) {
     if (!r && include_u8)
         r = forward_u8(reinterpret_cast<const uint8_t*>(x), batch, scratch_logits, host_top1_dev, host_compute);
     // the graph of the host paths' BF16 input form (host_pack.h), unless packing is ruled out already
-    if (!r && accepts_bf16_input() && host_pack_mode != 0)
+    if (!r && accepts_bf16_input() && host_pack_mode != 0)   // (a mixed batch has its own graph: captured at first use)
         r = forward_bf16(reinterpret_cast<const uint16_t*>(x), batch, scratch_logits, host_top1_dev, host_compute);
     cudaError_t ce = cudaStreamSynchronize(host_compute);
     cudaFree(x);
@@ -1673,69 +1677,91 @@ int Model::profile(const float* x, int batch, int iters, int* kind, float* ms, d
     return RNB_OK;
 }
 
-// FP32 host input of a BF16-stem model: round on the host, upload half the bytes? Decided once per model (see model.h).
-bool Model::host_pack_for(const float* x, int batch, uint16_t** stage, float* x_dev) {
+// FP32 host input of a BF16-stem model: how many leading images of the batch do the host cores round to BF16 (half the
+// bytes on PCIe) while the rest crosses as FP32? Fixed once per model and kind of host memory (see model.h).
+int Model::host_pack_for(const float* x, int batch, uint16_t** stage, float* x_dev) {
     host_pack_last = 0;
-    if (!accepts_bf16_input() || (fp8 && !fp8_calibrated)) return false;   // (calibration reads the FP32 image)
+    if (!accepts_bf16_input() || (fp8 && !fp8_calibrated)) return 0;   // (calibration reads the FP32 image)
     if (host_pack_mode < 0) {
         const char* e = getenv("RNB_HOST_PACK");
         if (e && (atoi(e) == 0 || atoi(e) == 1)) host_pack_mode = atoi(e);
     }
-    if (host_pack_mode == 0) return false;
+    if (host_pack_mode == 0) return 0;
     cudaPointerAttributes attr{};
     const bool pinned = cudaPointerGetAttributes(&attr, x) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     const int kind = pinned ? 1 : 0;
     host_pack_last_kind = kind;
-    if (host_pack_mode < 0 && host_pack_decided[kind] == 0) return false;
+    if (host_pack_mode < 0 && host_pack_frac[kind] == 0) return 0;
     const size_t img_elems = 3ull * image * image;
     if (!*stage && cudaHostAlloc(reinterpret_cast<void**>(stage), 1ull * max_batch * img_elems * sizeof(uint16_t),
                                  cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError();
         *stage = nullptr;
         host_pack_mode = 0;   // no pinned memory to stage in: the plain copy still works
-        return false;
+        return 0;
     }
-    if (host_pack_mode == 1 || host_pack_decided[kind] == 1) {
-        host_pack_last = 1;
-        return true;
-    }
-    // Time both forms on samples of this very batch (its memory: pinned or pageable, its NUMA placement): the
-    // conversion with the pool, then a plain FP32 copy and a BF16 copy of the same images. Two rounds, the second
-    // one counts — on OTHER images where the batch has them, so that the conversion reads memory, not cache.
+    // the share of a batch, in whole 16-image upload pieces; a remainder below one piece joins the other side
+    auto images_of = [&](double frac) {
+        int nb = static_cast<int>(frac * batch / 16.0 + 0.5) * 16;
+        if (nb < 16 && frac < 1.0) nb = 0;
+        if (nb > batch - 16 || frac >= 1.0) nb = batch;
+        host_pack_last = static_cast<double>(nb) / batch;
+        return nb;
+    };
+    if (host_pack_mode == 1) return images_of(1.0);
+    if (host_pack_frac[kind] > 0) return images_of(host_pack_frac[kind]);
+    // Time the parts on samples of this very batch (its memory: pinned or pageable, its NUMA placement): a plain FP32
+    // copy, the conversion with the pool, a BF16 copy of the result. Two rounds, the second one counts — on OTHER
+    // images where the batch has them, so that the conversion reads memory, not cache; a copy is timed as the faster
+    // of two in a row (the first one after an idle stretch has been seen 8x slower).
     using clk = std::chrono::steady_clock;
     const int ns = std::min(batch, 32);
     const size_t n = static_cast<size_t>(ns) * img_elems;
     HostPacker& hp = HostPacker::instance();
     double t[3] = {0, 0, 0};
+    auto time_copy = [&](const void* src, size_t bytes) {
+        double best = 1e30;
+        for (int again = 0; again < 2; ++again) {
+            cudaStreamSynchronize(copy_stream);
+            const auto t0 = clk::now();
+            cudaMemcpyAsync(x_dev, src, bytes, cudaMemcpyHostToDevice, copy_stream);
+            cudaStreamSynchronize(copy_stream);
+            best = std::min(best, std::chrono::duration<double>(clk::now() - t0).count());
+        }
+        return best;
+    };
     for (int rep = 0; rep < 2; ++rep) {
         const float* xs = x + (rep == 1 && batch >= 2 * ns ? n : 0);
-        auto t0 = clk::now();
+        // (the FP32 copy first: once the cores have read the sample, the DMA engine finds it in their caches and the
+        // copy runs at 60 % of its rate from memory — which is where a serving loop's batches are)
+        t[1] = time_copy(xs, n * sizeof(float));
+        const auto t0 = clk::now();
         hp.run(xs, *stage, n, n, [](size_t, size_t) {});
         t[0] = std::chrono::duration<double>(clk::now() - t0).count();
-        for (int form = 1; form <= 2; ++form) {
-            cudaStreamSynchronize(copy_stream);
-            t0 = clk::now();
-            if (form == 1) cudaMemcpyAsync(x_dev, xs, n * sizeof(float), cudaMemcpyHostToDevice, copy_stream);
-            else cudaMemcpyAsync(x_dev, *stage, n * sizeof(uint16_t), cudaMemcpyHostToDevice, copy_stream);
-            cudaStreamSynchronize(copy_stream);
-            t[form] = std::chrono::duration<double>(clk::now() - t0).count();
-        }
+        t[2] = time_copy(*stage, n * sizeof(uint16_t));
     }
     if (cudaGetLastError() != cudaSuccess) {
-        host_pack_decided[kind] = 0;
-        return false;
+        host_pack_frac[kind] = 0;
+        return 0;
     }
     for (int i = 0; i < 3; ++i) host_pack_gbps[kind][i] = (i == 2 ? 2.0 : 4.0) * n / std::max(t[i], 1e-9) * 1e-9;
-    // packed: conversion and the half-size copy overlap piece by piece; it has to beat the plain copy clearly
-    host_pack_decided[kind] = std::max(t[0], t[2]) < 0.85 * t[1] ? 1 : 0;
+    // Seconds per FP32 byte of the batch: c on the cores (inside a serving loop the pool reaches about 0.8 of what a
+    // cold sample shows: every core also feeds the DMA engine), l1 on the link as FP32, l2 on the link as BF16. A
+    // fraction f on the cores costs f c of core time and f l2 + (1 - f) l1 of link time; they finish together at
+    // f = l1 / (c + l1 - l2). Below a fifth it is not worth the threads; the gain must be clear (15 %).
+    const double c = t[0] / 0.8, l1 = t[1], l2 = t[2];
+    double f = c + l1 - l2 > 0 ? l1 / (c + l1 - l2) : 1.0;
+    f = std::min(1.0, std::max(0.0, f));
+    if (f > 0.93) f = 1.0;
+    const double t_mixed = std::max(f * c, f * l2 + (1.0 - f) * l1);
+    if (f < 0.2 || t_mixed > 0.85 * l1) f = 0.0;
+    host_pack_frac[kind] = f;
     if (getenv("RNB_VERBOSE"))
         fprintf(stderr, "rnb host pack (%s input): %d threads convert %.1f GB/s (FP32 read), H2D FP32 %.1f GB/s, H2D BF16 "
-                        "%.1f GB/s -> %s\n", pinned ? "pinned" : "pageable", hp.threads(), host_pack_gbps[kind][0],
-                host_pack_gbps[kind][1], host_pack_gbps[kind][2],
-                host_pack_decided[kind] ? "round to BF16 on the host" : "plain FP32 copy");
-    host_pack_last = host_pack_decided[kind];
-    return host_pack_last == 1;
+                        "%.1f GB/s -> %.0f %% of every batch rounded to BF16 on the host\n", pinned ? "pinned" : "pageable",
+                hp.threads(), host_pack_gbps[kind][0], host_pack_gbps[kind][1], host_pack_gbps[kind][2], 100.0 * f);
+    return f > 0 ? images_of(f) : 0;
 }
 
 int Model::forward_host(const float* x, int batch, float* logits, int32_t* top1) {
@@ -1763,8 +1789,10 @@ int Model::forward_host(const float* x, int batch, float* logits, int32_t* top1)
         copy_events.push_back(e);
     }
     cudaStream_t compute = host_compute;
-    if (host_pack_for(x, batch, &host_stage, host_x_dev)) {
+    if (2 * host_pack_for(x, batch, &host_stage, host_x_dev) >= batch) {
+        // (all or nothing here: the pieces of this path are separate forward passes)
         // the host cores round piece c to BF16 while piece c-1 crosses PCIe and piece c-2 runs
+        host_pack_last = 1;
         uint16_t* xd = reinterpret_cast<uint16_t*>(host_x_dev);
         int rc = RNB_OK;
         cudaError_t ce = cudaSuccess;
@@ -1840,25 +1868,32 @@ int Model::submit_host_any(int slot, const void* x, bool u8, int batch, float* l
         RNB_CUDA(cudaMalloc(&hs.top1_dev, 1ull * max_batch * sizeof(int32_t)));
         RNB_CUDA(cudaEventCreateWithFlags(&hs.copied, cudaEventDisableTiming));
         RNB_CUDA(cudaEventCreateWithFlags(&hs.done, cudaEventDisableTiming));
+        RNB_CUDA(cudaEventCreateWithFlags(&hs.computed, cudaEventDisableTiming));
     }
     if (!pipe_compute) RNB_CUDA(cudaStreamCreateWithFlags(&pipe_compute, cudaStreamNonBlocking));
+    if (!pipe_d2h) RNB_CUDA(cudaStreamCreateWithFlags(&pipe_d2h, cudaStreamNonBlocking));
     int r;
-    if (!u8 && host_pack_for(static_cast<const float*>(x), batch, &hs.stage, hs.x_dev)) {
-        // FP32 input of a BF16-stem model: the host cores round it to BF16 (bit for bit what the stem would do) in
-        // 16-image pieces, each uploaded as soon as it is complete — half the bytes cross PCIe. This call returns when
-        // the last piece is queued; the GPU is busy with the other slot's batch meanwhile.
-        uint16_t* xd = reinterpret_cast<uint16_t*>(hs.x_dev);
-        uint16_t* stage = hs.stage;
+    const int nb = u8 ? 0 : host_pack_for(static_cast<const float*>(x), batch, &hs.stage, hs.x_dev);
+    if (nb > 0) {
+        // FP32 input of a BF16-stem model: the host cores round the first nb images to BF16 (bit for bit what the stem
+        // would do) in 16-image pieces, each uploaded as soon as it is complete — half the bytes on PCIe — while the
+        // link is busy with the other images as FP32 (queued first: they need no core). This call returns when the
+        // last piece is queued; the GPU is busy with the other slot's batch meanwhile.
+        const float* xf = static_cast<const float*>(x);
+        uint16_t* xd = reinterpret_cast<uint16_t*>(hs.x_dev);   // BF16 images [0, nb) at the front of the buffer; the FP32
+        uint16_t* stage = hs.stage;                             // images behind them keep their FP32 positions
+        if (nb < batch)
+            RNB_CUDA(cudaMemcpyAsync(hs.x_dev + nb * img_elems, xf + nb * img_elems, (batch - nb) * img_elems * sizeof(float),
+                                     cudaMemcpyHostToDevice, copy_stream));
         cudaError_t ce = cudaSuccess;
-        HostPacker::instance().run(static_cast<const float*>(x), stage, batch * img_elems, 16 * img_elems,
-                                   [&](size_t first, size_t count) {
+        HostPacker::instance().run(xf, stage, nb * img_elems, 16 * img_elems, [&](size_t first, size_t count) {
             if (ce == cudaSuccess)
                 ce = cudaMemcpyAsync(xd + first, stage + first, count * sizeof(uint16_t), cudaMemcpyHostToDevice, copy_stream);
         });
         RNB_CUDA(ce);
         RNB_CUDA(cudaEventRecord(hs.copied, copy_stream));
         RNB_CUDA(cudaStreamWaitEvent(pipe_compute, hs.copied, 0));
-        r = forward_bf16(xd, batch, hs.logits_dev, hs.top1_dev, pipe_compute);
+        r = forward_any(InRef{xd, InRef::BF16_NCHW, hs.x_dev, nb}, batch, hs.logits_dev, hs.top1_dev, pipe_compute);
     } else {
         // uint8 input: a quarter of the bytes cross PCIe (the device buffer is reused as a byte buffer)
         RNB_CUDA(cudaMemcpyAsync(hs.x_dev, x, batch * img_elems * (u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice,
@@ -1869,13 +1904,17 @@ int Model::submit_host_any(int slot, const void* x, bool u8, int batch, float* l
                : forward(hs.x_dev, batch, hs.logits_dev, hs.top1_dev, pipe_compute);
     }
     if (r) return r;
+    // results go back on their own stream: the other slot's forward pass, queued behind this one on pipe_compute,
+    // starts as soon as this one ends instead of after the 1 MB D2H copy
+    RNB_CUDA(cudaEventRecord(hs.computed, pipe_compute));
+    RNB_CUDA(cudaStreamWaitEvent(pipe_d2h, hs.computed, 0));
     if (logits)
         RNB_CUDA(cudaMemcpyAsync(logits, hs.logits_dev, 1ull * batch * classes * sizeof(float),
-                                 cudaMemcpyDeviceToHost, pipe_compute));
+                                 cudaMemcpyDeviceToHost, pipe_d2h));
     if (top1)
         RNB_CUDA(cudaMemcpyAsync(top1, hs.top1_dev, 1ull * batch * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                 pipe_compute));
-    RNB_CUDA(cudaEventRecord(hs.done, pipe_compute));
+                                 pipe_d2h));
+    RNB_CUDA(cudaEventRecord(hs.done, pipe_d2h));
     hs.pending = true;
     return RNB_OK;
 }

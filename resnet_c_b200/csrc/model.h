@@ -83,13 +83,23 @@ private:
 };
 
 // One batch of input images on the device, in one of the accepted formats (every format has 3 * image * image
-// elements per image, so a sub-batch is an element offset away).
+// elements per image). BF16_NCHW is the packed host paths' form and may be mixed: images [0, nb) are BF16 at p, images
+// [nb, batch) FP32 at p2, both tensors indexed by the image number in the batch.
 struct InRef {
     enum Kind { F32_NCHW = 0, U8_HWC = 1, BF16_NCHW = 2 };
     const void* p = nullptr;
     int kind = F32_NCHW;
+    const float* p2 = nullptr;
+    int nb = 0;
     size_t elem_bytes() const { return kind == F32_NCHW ? 4 : kind == U8_HWC ? 1 : 2; }
-    InRef at(size_t elems) const { return InRef{p ? static_cast<const char*>(p) + elems * elem_bytes() : nullptr, kind}; }
+    // the sub-batch that starts `images` images further on
+    InRef at(size_t images, size_t img_elems) const {
+        InRef r = *this;
+        if (p) r.p = static_cast<const char*>(p) + images * img_elems * elem_bytes();
+        if (p2) r.p2 = p2 + images * img_elems;
+        r.nb = nb > static_cast<int>(images) ? nb - static_cast<int>(images) : 0;
+        return r;
+    }
     const float* f32() const { return kind == F32_NCHW ? static_cast<const float*>(p) : nullptr; }
     const uint8_t* u8() const { return kind == U8_HWC ? static_cast<const uint8_t*>(p) : nullptr; }
 };
@@ -150,7 +160,7 @@ struct Model {
     // are kept per (n, u8) shape; a call with new pointers beyond that RE-TARGETS the least recently used one with
     // cudaGraphExecUpdate (a re-capture, no instantiation), so a caller that allocates fresh outputs every call pays
     // ~0.1 ms of host time, not an instantiate, and nothing is ever flushed wholesale.
-    using GraphKey = std::tuple<int, const void*, void*, void*>;
+    using GraphKey = std::tuple<int64_t, const void*, const void*, void*, void*>;   // shape, x, x2 (mixed input), logits, top1
     struct GraphEntry {
         cudaGraphExec_t exec = nullptr;
         uint64_t used = 0;
@@ -239,27 +249,31 @@ struct Model {
     int set_normalization(const float* mean, const float* std);
     int forward_host(const float* x, int batch, float* logits, int32_t* top1);
     // Host packing (host_pack.h): FP32 host input of a BF16-stem model is rounded to BF16 by the host cores and half the
-    // bytes cross PCIe. host_pack_mode: 0 / 1 forced (RNB_HOST_PACK, rnb_model_set_host_pack), -1 = the first host call
-    // with pageable input and the first with pinned input each time the conversion and both copies on a sample of
-    // their own batch and keep the faster form for that kind of memory. A group (rnb_group_*) turns it off: its
-    // replicas are fed one after the other by ONE host thread.
+    // bytes cross PCIe — for a FRACTION of every batch: host cores (conversion rate Rc) and the PCIe link work side by
+    // side, the leading images of a batch going through the cores as BF16, the rest straight over the link as FP32, in
+    // the proportion that lets both finish together. host_pack_mode: 0 / 1 forced, none / all (RNB_HOST_PACK,
+    // rnb_model_set_host_pack); -1 = the first host call with pageable input and the first with pinned input each
+    // time the conversion and both copies on samples of their own batch and fix the fraction for that kind of
+    // memory. A group (rnb_group_*) turns it off: its replicas are fed one after the other by ONE host thread.
     int host_pack_mode = -1;
-    int host_pack_decided[2] = {-1, -1};    // auto mode: [pageable, pinned] -> 0 | 1
-    int host_pack_last = -1;                // what the most recent host call did
+    double host_pack_frac[2] = {-1, -1};    // auto mode: [pageable, pinned] -> fraction of the images rounded on the host
+    double host_pack_last = -1;             // the fraction the most recent host call used
     double host_pack_gbps[2][3] = {{0, 0, 0}, {0, 0, 0}};   // per kind of memory: conversion (FP32 bytes read), FP32 H2D, BF16 H2D
     int host_pack_last_kind = 0;
     uint16_t* host_stage = nullptr;          // pinned staging of forward_host
-    bool host_pack_for(const float* x, int batch, uint16_t** stage, float* x_dev);
+    // how many leading images of this batch the host cores round to BF16 (0 = plain FP32 copies)
+    int host_pack_for(const float* x, int batch, uint16_t** stage, float* x_dev);
     // pipelined host path: two slots, each with its own device input / output buffers
     struct HostSlot {
         uint16_t* stage = nullptr;   // pinned: the batch rounded to BF16 by the host cores (host_pack.h)
         float* x_dev = nullptr;
         float* logits_dev = nullptr;
         int32_t* top1_dev = nullptr;
-        cudaEvent_t copied = nullptr, done = nullptr;
+        cudaEvent_t copied = nullptr, computed = nullptr, done = nullptr;
         bool pending = false;
     } slots[2];
     cudaStream_t pipe_compute = nullptr;
+    cudaStream_t pipe_d2h = nullptr;   // the slots' device -> host copies (not in the way of the next forward pass)
     int submit_host(int slot, const float* x, int batch, float* logits, int32_t* top1);
     int submit_host_u8(int slot, const uint8_t* x, int batch, float* logits, int32_t* top1);
     int submit_host_any(int slot, const void* x, bool u8, int batch, float* logits, int32_t* top1);

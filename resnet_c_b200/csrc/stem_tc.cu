@@ -20,8 +20,9 @@
 //    row that does not read input row t has zero weights in its half of A, so there are no special cases.
 //  * the input streams through a ring of eight 4-row chunks; three loader warps build the NHWC4 BF16 rows straight
 //    from the caller's FP32 NCHW tensor (MODE 1; an L2 prefetch runs three chunks ahead) — there is no layout pre-pass.
-//    MODE 2 is the same loader over a BF16 NCHW tensor: what the host paths upload when they round the FP32 image
-//    to BF16 on the CPU (host_pack.cu) — the rounding this loader would apply anyway, at half the PCIe bytes.
+//    MODE 2 serves the packed host paths (host_pack.cpp): the first `nb` images of the batch come from a BF16 NCHW
+//    tensor — the FP32 image rounded to BF16 by the host cores, the rounding this loader would apply anyway, at half
+//    the PCIe bytes — and the rest from an FP32 NCHW tensor, so that host cores and PCIe can share a batch.
 //    uint8 input keeps its normalising pre-pass and feeds the same kernel through bulk copies (MODE 0).
 //  * TWO MMA issuer warps take alternate pairs: the tensor pipe's queue holds about two MMAs, and one issuer's barrier
 //    polls and bookkeeping (~430 clocks per pair) left the pipe dry 40 % of the time.
@@ -282,7 +283,8 @@ __global__ void stem_pack_weights_kernel(const float* __restrict__ w, const floa
 template <int MODE>
 __global__ void __launch_bounds__(STEM_T_THREADS, 1)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restrict__ xin,
-                 const uint32_t* __restrict__ wt, const float* __restrict__ bias, int B) {
+                 const uint32_t* __restrict__ wt, const float* __restrict__ bias, int B,
+                 const float* __restrict__ xin_f32, int nb) {   // (MODE 2: images >= nb are read from xin_f32)
     using namespace ptx;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -363,7 +365,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_out, const void* __restric
                     __syncwarp();
                 } else {
                     if (MODE == 1) stem_fill_chunk_f32(smem_u32(dst), static_cast<const float*>(xin), b, c, lane);
-                    else stem_fill_chunk_bf16(smem_u32(dst), static_cast<const uint16_t*>(xin), b, c, lane);
+                    else if (b < nb) stem_fill_chunk_bf16(smem_u32(dst), static_cast<const uint16_t*>(xin), b, c, lane);
+                    else stem_fill_chunk_f32(smem_u32(dst), xin_f32, b, c, lane);
                     fence_proxy_async_smem();
                     mbar_arrive(&ch_full[n & (NCH - 1)]);
                 }
@@ -550,7 +553,7 @@ cudaError_t stem_tc_init() {
 }
 
 static cudaError_t launch_stem_tc_kernel(int mode, const void* in, const void* wk, const float* bias, void* out, int B,
-                                         cudaStream_t s) {
+                                         cudaStream_t s, const float* in_f32 = nullptr, int nb = 0) {
     const int pairs = B * PAIRS;
     const int grid = pairs < num_sms() ? pairs : num_sms();
     // output [B*56*56 pooled pixels][64 ch] bf16; one store = 28 pooled pixels x 16 channels (an epilogue warp's block)
@@ -560,16 +563,20 @@ static cudaError_t launch_stem_tc_kernel(int mode, const void* in, const void* w
     if (make_tiled_nd(&tm, TmDtype::BF16, out, 2, dims, strides, box, false) != 0) return cudaErrorInvalidValue;
     const uint32_t* wt = static_cast<const uint32_t*>(wk);
     if (mode == 0)
-        return launch_pdl_small(stem_tc_kernel<0>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in, wt, bias, B);
+        return launch_pdl_small(stem_tc_kernel<0>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in, wt, bias, B,
+                                in_f32, nb);
     if (mode == 2)
-        return launch_pdl_small(stem_tc_kernel<2>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in, wt, bias, B);
-    return launch_pdl_small(stem_tc_kernel<1>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in, wt, bias, B);
+        return launch_pdl_small(stem_tc_kernel<2>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in, wt, bias, B,
+                                in_f32, nb);
+    return launch_pdl_small(stem_tc_kernel<1>, dim3(grid), dim3(STEM_T_THREADS), STEM_T_SMEM, s, tm, in, wt, bias, B,
+                            in_f32, nb);
 }
 
-// x BF16 NCHW [B,3,224,224] (the FP32 image rounded to nearest-even by the host, host_pack.cu) -> out: one launch
-cudaError_t launch_stem_tc_from_bf16(const void* x_bf16, const void* wk, const float* bias, void* out, int B,
-                                     cudaStream_t s) {
-    return launch_stem_tc_kernel(2, x_bf16, wk, bias, out, B, s);
+// Images [0, nb) from x_bf16 (BF16 NCHW: the FP32 image rounded to nearest-even by the host, host_pack.cpp), images
+// [nb, B) from x_f32 (FP32 NCHW, indexed by the same image number) -> out: one launch
+cudaError_t launch_stem_tc_from_mixed(const void* x_bf16, const float* x_f32, int nb, const void* wk, const float* bias,
+                                      void* out, int B, cudaStream_t s) {
+    return launch_stem_tc_kernel(2, x_bf16, wk, bias, out, B, s, x_f32, nb);
 }
 
 // xp (packed NHWC4 BF16, written by a pack kernel) -> out NHWC bf16 [B,56,56,64]

@@ -320,15 +320,21 @@ class ResNet:
         return logits, top1
 
     def set_host_pack(self, mode: int) -> None:
-        """Host paths: -1 decide by timing at the next host call, 0 plain FP32 copies, 1 round to BF16 on the host."""
+        """Host paths: -1 decide by timing at the next host call, 0 plain FP32 copies, 1 round every image to BF16 on the
+        host cores."""
         check(_lib.lib().rnb_model_set_host_pack(self._h, int(mode)))
+
+    def set_host_pack_fraction(self, fraction: float) -> None:
+        """Host paths: this fraction of every batch (whole 16-image pieces) is rounded to BF16 on the host cores, the
+        rest crosses PCIe as FP32."""
+        check(_lib.lib().rnb_model_set_host_pack_fraction(self._h, float(fraction)))
 
     def host_pack(self) -> dict:
         """Current choice of the host paths and what the decision measured (GB/s; zeros when forced)."""
-        g = (C.c_double * 3)()
+        g = (C.c_double * 4)()
         choice = _lib.lib().rnb_model_host_pack(self._h, g)
-        return {"choice": choice, "threads": _lib.lib().rnb_host_pack_threads(), "convert_gbps": g[0],
-                "h2d_f32_gbps": g[1], "h2d_bf16_gbps": g[2]}
+        return {"choice": choice, "fraction": g[3], "threads": _lib.lib().rnb_host_pack_threads(),
+                "convert_gbps": g[0], "h2d_f32_gbps": g[1], "h2d_bf16_gbps": g[2]}
 
     def forward_u8(self, x: torch.Tensor, logits=None, top1=None):
         """x: [B,224,224,3] uint8 CUDA tensor (decoded, resized, cropped image, HWC). The /255 + mean/std

@@ -183,7 +183,7 @@ def test_uint8_input_path_is_bit_identical_to_float_input(arch, dtype, golden_di
     model.close()
 
 
-@pytest.mark.parametrize("arch,dtype,B", [("resnet50", "bf16", 37), ("resnet18", "bf16", 70), ("resnet50", "fp8", 20)])
+@pytest.mark.parametrize("arch,dtype,B", [("resnet50", "bf16", 37), ("resnet18", "bf16", 70), ("resnet50", "fp8", 40)])
 def test_host_packed_input_is_bit_identical_to_fp32_input(arch, dtype, B):
     """The host paths' packed form (csrc/host_pack.cpp: the host cores round the FP32 image to BF16, half the bytes
     cross PCIe, the stem loads BF16 NCHW — stem_tc_kernel<2>) against the plain FP32 form: identical logits and top-1
@@ -198,8 +198,13 @@ def test_host_packed_input_is_bit_identical_to_fp32_input(arch, dtype, B):
     torch.cuda.synchronize()
     assert torch.equal(got, want) and torch.equal(got_top1, want_top1)
     want, want_top1 = want.cpu(), want_top1.cpu()
-    for mode in (1, 0):
-        model.set_host_pack(mode)
+    for mode in (1, 0.5, 0):
+        # all images through the host cores / a mixed batch (the leading 16 or 32 images as BF16, the rest as FP32 in
+        # ONE stem launch) / plain FP32 copies
+        if mode == 0.5:
+            model.set_host_pack_fraction(0.5)
+        else:
+            model.set_host_pack(mode)
         for xin in (x.pin_memory(), x.clone()):
             lh, th = model.forward_host(xin)
             assert torch.equal(lh, want) and torch.equal(th, want_top1), (mode, xin.is_pinned())
@@ -210,7 +215,9 @@ def test_host_packed_input_is_bit_identical_to_fp32_input(arch, dtype, B):
             for slot in (0, 1):
                 model.wait_host(slot)
                 assert torch.equal(outs[slot][0], want) and torch.equal(outs[slot][1], want_top1), (mode, slot)
-        assert model.host_pack()["choice"] == mode
+        info = model.host_pack()
+        assert info["choice"] == (1 if mode else 0)
+        assert info["fraction"] == (mode if mode != 0.5 else {37: 16 / 37, 70: 32 / 70, 40: 16 / 40}[B])
     # left to itself the model times both forms on the first host call and keeps one of them
     model.set_host_pack(-1)
     lh, th = model.forward_host(x.pin_memory())
