@@ -190,3 +190,21 @@ def test_host_bf16_rounding_thread_count_follows_the_environment():
         assert lines[0] == threads
         outs.append(lines[1])
     assert outs[0] == outs[1]   # the partitioning does not change the result
+
+
+def test_host_pack_pool_is_race_free_under_thread_sanitizer(tmp_path):
+    """csrc/host_pack.cpp under -fsanitize=thread: three caller threads share the process-wide pool; pieces must be
+    announced once, in order and complete, results equal the scalar conversion, and TSAN must stay silent."""
+    exe = tmp_path / "host_pack_stress"
+    build = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=thread", "-o", str(exe),
+                            str(ROOT / "tests" / "host_pack_stress.cpp"),
+                            str(ROOT / "resnet_c_b200" / "csrc" / "host_pack.cpp")], capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr:
+        pytest.skip("no thread sanitizer runtime in this toolchain")
+    assert build.returncode == 0, build.stderr
+    for threads in ("1", "6"):
+        r = subprocess.run([str(exe)], env=dict(os.environ, RNB_HOST_THREADS=threads), capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "failures 0" in r.stdout and f"threads {threads} " in r.stdout
+        assert "ThreadSanitizer" not in r.stderr

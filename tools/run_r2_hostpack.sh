@@ -1,4 +1,5 @@
 #!/bin/bash
+# host packing: its GPU tests, then the interleaved A/B of the serving loop (profiles/e2e_hostpack_ab_r2.txt)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_model.py -x -q -m gpu -k "host_pack or uint8_input" 2>&1 | tail -5 > gpurun_out/hp_tests.txt
 cat gpurun_out/hp_tests.txt

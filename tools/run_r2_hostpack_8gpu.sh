@@ -1,5 +1,5 @@
 #!/bin/bash
-# 8 GPUs, one process per GPU: the torchrun bench with the host-packing decision made under contention (every rank at
+# (8x the box time is charged: keep both runs short) 8 GPUs, one process per GPU: the torchrun bench with the host-packing decision made under contention (every rank at
 # once), and the same with RNB_HOST_PACK=0 (plain FP32 copies) for comparison
 mkdir -p gpurun_out
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
