@@ -433,7 +433,8 @@ def main():
     packed = host_pack.get("choice") == 1
     e2e_plain_value = None
     # (every rank decides for itself, and serve_loop() holds collectives: the ranks must agree on running it again)
-    if max_over_ranks(1.0 if packed else 0.0) > 0:
+    from resnet_c_b200 import dist as rdist
+    if rdist.any_rank(packed, device=dev):
         model.set_host_pack(0)
         e2e_plain_value = serve_loop()
         same = same and bool((th2[0].to(dev) == top1).all().item())

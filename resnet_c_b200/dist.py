@@ -20,6 +20,18 @@ def shard_bounds(total: int, world: int, rank: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def any_rank(flag: bool, device=None, group=None) -> bool:
+    """True on EVERY rank if `flag` is true on any of them (one all-reduce; no process group = this rank alone).
+    For decisions a rank takes by itself — e.g. the host-packing choice each replica times on its own — when the
+    code that follows holds collectives: every rank has to take the same branch."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return bool(t.item())
+
+
 def gather_results(logits: torch.Tensor, top1: torch.Tensor, total: int, group=None):
     """All-gather per-rank (logits [n_r, classes], top1 [n_r]) into ([total, classes], [total]) in image
     order. Ragged shards are padded to the largest shard for the collective and trimmed afterwards."""

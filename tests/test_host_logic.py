@@ -107,6 +107,42 @@ def test_gather_world_size_2_gloo(tmp_path, total):
     assert r.stdout.count("ok") == 2
 
 
+_ANY_WORKER = textwrap.dedent("""
+    import sys, torch.distributed as dist
+    sys.path.insert(0, {root!r})
+    from resnet_c_b200 import dist as rdist
+    assert rdist.any_rank(True) is True and rdist.any_rank(False) is False     # no process group: this rank alone
+    dist.init_process_group("gloo")
+    rank = dist.get_rank()
+    # rank 1 alone decides "yes" (a replica that chose host packing): both ranks must take the branch, and the
+    # collectives inside it must pair up
+    for flags in ((False, True), (True, False), (False, False), (True, True)):
+        got = rdist.any_rank(flags[rank])
+        assert got == any(flags), (flags, rank, got)
+        if got:
+            dist.barrier()
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_rank_local_decisions_are_agreed_before_collectives_gloo(tmp_path):
+    """bench.py times the plain-copy serving loop (barriers inside) when the model chose host packing; every rank
+    decides on its own timings, so the branch is taken on all ranks or none (an 8-GPU run hung on exactly this)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_ANY_WORKER.format(root=str(ROOT)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    port = 29500 + (os.getpid() + 977) % 2000
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
+    # and bench.py goes through it
+    assert "rdist.any_rank(packed" in (ROOT / "bench.py").read_text()
+
+
 def test_bench_reference_arm_contract(tmp_path):
     """`bench.py --impl reference` prints ONE JSON line with the keys the driver reads."""
     import json
