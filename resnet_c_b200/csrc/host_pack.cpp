@@ -12,6 +12,7 @@
 #include <vector>
 
 #include <immintrin.h>
+#include <pthread.h>
 #include <sched.h>
 
 namespace rnb {
@@ -78,6 +79,10 @@ int default_threads() {
 
 constexpr size_t ITEM = 32768;  // elements per work item: 128 KB read, 64 KB written
 
+// A forked child inherits the pool object but none of its threads (and possibly a locked mutex): it converts on the
+// calling thread alone.
+std::atomic<bool> g_forked_child{false};
+
 }  // namespace
 
 void f32_to_bf16_rne(const float* src, uint16_t* dst, size_t n) {
@@ -128,6 +133,7 @@ struct HostPacker::Impl {
 
 HostPacker::HostPacker() : impl_(new Impl), nthreads_(default_threads()) {
     for (int t = 1; t < nthreads_; ++t) impl_->workers.emplace_back([this] { impl_->worker(); });
+    pthread_atfork(nullptr, nullptr, [] { g_forked_child.store(true, std::memory_order_relaxed); });
 }
 
 HostPacker::~HostPacker() {
@@ -149,6 +155,14 @@ void HostPacker::run(const float* src, uint16_t* dst, size_t n, size_t piece,
                      const std::function<void(size_t, size_t)>& ready) {
     if (n == 0) return;
     if (piece == 0 || piece > n) piece = n;
+    if (g_forked_child.load(std::memory_order_relaxed)) {   // no workers here: piece by piece on this thread
+        for (size_t first = 0; first < n; first += piece) {
+            const size_t count = std::min(piece, n - first);
+            f32_to_bf16_rne(src + first, dst + first, count);
+            ready(first, count);
+        }
+        return;
+    }
     Impl& J = *impl_;
     std::lock_guard<std::mutex> run_lock(J.run_mutex);
     const size_t npieces = (n + piece - 1) / piece;

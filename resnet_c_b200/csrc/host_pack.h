@@ -19,7 +19,8 @@ void f32_to_bf16_rne(const float* src, uint16_t* dst, size_t n);
 // A process-wide pool of sleeping worker threads. run() converts src[0, n) into dst with the workers AND the calling
 // thread, and calls ready(first_element, count) on the CALLING thread for every consecutive piece of `piece` elements
 // as soon as that piece is complete, in order (the caller queues the piece's H2D copy there, so the upload of piece i
-// overlaps the conversion of piece i + 1). One run() at a time (callers from several threads are serialised).
+// overlaps the conversion of piece i + 1). One run() at a time (callers from several threads are serialised). A
+// forked child process has no workers: there run() converts on the calling thread.
 class HostPacker {
 public:
     static HostPacker& instance();

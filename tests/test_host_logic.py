@@ -244,3 +244,27 @@ def test_host_pack_pool_is_race_free_under_thread_sanitizer(tmp_path):
         assert r.returncode == 0, r.stdout + r.stderr
         assert "failures 0" in r.stdout and f"threads {threads} " in r.stdout
         assert "ThreadSanitizer" not in r.stderr
+
+
+def test_host_bf16_rounding_survives_a_fork():
+    """The pool's threads do not exist in a forked child: the conversion must still complete there (on the calling
+    thread), not wait for workers that are gone."""
+    code = textwrap.dedent("""
+        import os, sys, numpy as np
+        from resnet_c_b200 import _lib
+        l = _lib.lib()
+        x = np.linspace(-5, 5, 300001, dtype=np.float32)
+        want = np.zeros(x.size, dtype=np.uint16)
+        assert l.rnb_f32_to_bf16_host(x.ctypes.data, want.ctypes.data, x.size) == 0      # starts the pool
+        pid = os.fork()
+        if pid == 0:
+            got = np.zeros(x.size, dtype=np.uint16)
+            ok = l.rnb_f32_to_bf16_host(x.ctypes.data, got.ctypes.data, x.size) == 0 and (got == want).all()
+            os._exit(0 if ok else 3)
+        _, status = os.waitpid(pid, 0)
+        print("child", os.WEXITSTATUS(status) if os.WIFEXITED(status) else -1)
+    """)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, RNB_HOST_THREADS="4", PYTHONPATH=str(ROOT)),
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "child 0" in r.stdout
