@@ -113,7 +113,7 @@ int rnb_model_forward(rnb_model_t* m, const float* x_dev, int batch, float* logi
  * that lets both finish together (the stem reads either form). Pageable input then needs no driver staging either.
  * The first host call of a model with pageable input, and the first with pinned input, time conversion and copies on
  * samples of their batch and fix that proportion for that kind of memory (none, if the plain copy is not clearly
- * slower); RNB_HOST_PACK=0 / 1 or rnb_model_set_host_pack() force none / all. */
+ * slower; batches of fewer than 32 images are copied plainly and leave the question open); RNB_HOST_PACK=0 / 1 or rnb_model_set_host_pack() force none / all. */
 int rnb_model_forward_host(rnb_model_t* m, const float* x_host, int batch, float* logits_host,
                            int32_t* top1_host);
 

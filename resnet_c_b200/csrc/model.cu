@@ -1711,6 +1711,9 @@ int Model::host_pack_for(const float* x, int batch, uint16_t** stage, float* x_d
     };
     if (host_pack_mode == 1) return images_of(1.0);
     if (host_pack_frac[kind] > 0) return images_of(host_pack_frac[kind]);
+    // a small batch says nothing about a serving loop (thread wake-ups and launch latencies, not rates): it goes the
+    // plain way and the question stays open for the first batch of at least 32 images
+    if (batch < 32) return 0;
     // Time the parts on samples of this very batch (its memory: pinned or pageable, its NUMA placement): a plain FP32
     // copy, the conversion with the pool, a BF16 copy of the result. Two rounds, the second one counts — on OTHER
     // images where the batch has them, so that the conversion reads memory, not cache; a copy is timed as the faster
