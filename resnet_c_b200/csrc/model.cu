@@ -1693,6 +1693,9 @@ int Model::host_pack_for(const float* x, int batch, uint16_t** stage, float* x_d
     const int kind = pinned ? 1 : 0;
     host_pack_last_kind = kind;
     if (host_pack_mode < 0 && host_pack_frac[kind] == 0) return 0;
+    // a small batch says nothing about a serving loop (thread wake-ups and launch latencies, not rates): it goes the
+    // plain way, without staging memory, and the question stays open for the first batch of at least 32 images
+    if (host_pack_mode < 0 && host_pack_frac[kind] < 0 && batch < 32) return 0;
     const size_t img_elems = 3ull * image * image;
     if (!*stage && cudaHostAlloc(reinterpret_cast<void**>(stage), 1ull * max_batch * img_elems * sizeof(uint16_t),
                                  cudaHostAllocDefault) != cudaSuccess) {
@@ -1711,9 +1714,6 @@ int Model::host_pack_for(const float* x, int batch, uint16_t** stage, float* x_d
     };
     if (host_pack_mode == 1) return images_of(1.0);
     if (host_pack_frac[kind] > 0) return images_of(host_pack_frac[kind]);
-    // a small batch says nothing about a serving loop (thread wake-ups and launch latencies, not rates): it goes the
-    // plain way and the question stays open for the first batch of at least 32 images
-    if (batch < 32) return 0;
     // Time the parts on samples of this very batch (its memory: pinned or pageable, its NUMA placement): a plain FP32
     // copy, the conversion with the pool, a BF16 copy of the result. Two rounds, the second one counts — on OTHER
     // images where the batch has them, so that the conversion reads memory, not cache; a copy is timed as the faster
