@@ -43,6 +43,16 @@ int main(int argc, char** argv)
     for (uint64_t b = 0; b < B; ++b) {
         std::cout << "max index is " << top1[b] << std::endl;
     }
+    if (std::getenv("RNB_CHECK_HOST_PATH")) {
+        // the same batch through host tensors (upload + forward + read-back in one call): must give the same answer
+        FloatTensor logits_cpu(model.getOutShape(batch_cpu.shape()), Device::CPU);
+        const std::vector<int32_t> top1_host = model.predictHost(batch_cpu, logits_cpu);
+        FloatTensor logits_dev_cpu = logits.cpu();
+        const bool same = top1_host == top1 &&
+                          !std::memcmp(logits_cpu.data(), logits_dev_cpu.data(), logits_cpu.numel() * sizeof(float));
+        std::cout << "host path: " << (same ? "identical" : "DIFFERENT") << std::endl;
+        if (!same) return 1;
+    }
     if (const char* dump = std::getenv("RNB_DUMP_LOGITS")) {
         logits.cpu().save(dump);  // raw float32 [B, classes], the reference's "cuda_out.bin" idea
     }

@@ -354,6 +354,17 @@ void ResNet::forward(FloatTensor& x, FloatTensor& logits)
     syncAndCheck();
 }
 
+std::vector<int32_t> ResNet::predictHost(FloatTensor& x_cpu, FloatTensor& logits_cpu)
+{
+    assert(x_cpu.device == Device::CPU && logits_cpu.device == Device::CPU);
+    assert(logits_cpu.shape() == getOutShape(x_cpu.shape()));
+    const uint64_t B = x_cpu.shape().at(0);
+    std::vector<int32_t> top1(B);
+    rnbCheck(rnb_model_forward_host(handle_, x_cpu.data(), asInt(B), logits_cpu.data(), top1.data()),
+             "rnb_model_forward_host");   // synchronous: results are on the host when it returns
+    return top1;
+}
+
 std::vector<int32_t> ResNet::predict(FloatTensor& x, FloatTensor& logits)
 {
     const uint64_t B = x.shape().at(0);

@@ -290,6 +290,11 @@ public:
     void forward(FloatTensor& x, FloatTensor& logits);
     // Same, and also returns the per-image arg-max (first maximum wins) on the host.
     std::vector<int32_t> predict(FloatTensor& x, FloatTensor& logits);
+    // The reference's whole sequence from HOST tensors (Tensor::load -> loadToCuda -> forward -> cpu(),
+    // cuda/inference/main.cu:233-251) in one call: x and logits live on the CPU. Input upload, forward pass and
+    // read-back are pipelined inside (rnb_model_forward_host); on the BF16 path the host cores may round part of the
+    // batch to BF16 so that half of its bytes cross PCIe — the logits are bit-identical to predict() either way.
+    std::vector<int32_t> predictHost(FloatTensor& x_cpu, FloatTensor& logits_cpu);
     // Decoded images: x_u8_dev is uint8 HWC [B,224,224,3] on the GPU; the /255 + mean/std normalisation of
     // convert_imgs_to_bin.py:18 runs inside the stem pre-pass (bit-identical to predict() on the float tensor).
     std::vector<int32_t> predictU8(const uint8_t* x_u8_dev, uint64_t B, FloatTensor& logits);
