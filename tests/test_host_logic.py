@@ -219,13 +219,14 @@ def test_host_bf16_rounding_thread_count_follows_the_environment():
             "assert l.rnb_f32_to_bf16_host(x.ctypes.data, o.ctypes.data, x.size) == 0;"
             "print(int(o.astype(np.uint64).sum()))")
     outs = []
-    for threads in ("1", "3"):
-        env = dict(os.environ, RNB_HOST_THREADS=threads, PYTHONPATH=str(ROOT))
+    # (default = AVX2 where the CPU has it; the other two runs take the AVX-512 form, if the CPU has it, and the scalar one)
+    for threads, isa in (("1", ""), ("3", "avx512"), ("2", "scalar")):
+        env = dict(os.environ, RNB_HOST_THREADS=threads, RNB_HOST_ISA=isa, PYTHONPATH=str(ROOT))
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
         lines = r.stdout.split()
         assert lines[0] == threads
         outs.append(lines[1])
-    assert outs[0] == outs[1]   # the partitioning does not change the result
+    assert outs[0] == outs[1] == outs[2]   # neither the partitioning nor the instruction set changes the result
 
 
 def test_host_pack_pool_is_race_free_under_thread_sanitizer(tmp_path):
