@@ -269,3 +269,18 @@ def test_host_bf16_rounding_survives_a_fork():
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert "child 0" in r.stdout
+
+
+def test_input_reference_sub_batch_arithmetic(tmp_path):
+    """InRef (csrc/model.h): offsets into FP32 / uint8 / mixed BF16 + FP32 batches as the chunk loop and the two-lane
+    split take them — host-only program built with nvcc (tests/inref_check.cu), no GPU involved."""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        pytest.skip("nvcc not available")
+    exe = tmp_path / "inref_check"
+    b = subprocess.run([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(exe),
+                        str(ROOT / "tests" / "inref_check.cu")], capture_output=True, text=True, timeout=600)
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "inref ok" in r.stdout, r.stdout + r.stderr
