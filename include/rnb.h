@@ -138,6 +138,12 @@ int rnb_model_set_host_pack(rnb_model_t* m, int mode);
 int rnb_model_set_host_pack_fraction(rnb_model_t* m, double fraction);
 int rnb_model_host_pack(const rnb_model_t* m, double info[4]);
 int rnb_host_pack_threads(void);
+/* The split rule by itself (no GPU needed): from a conversion rate (GB/s of FP32 input read by the pool on a cold
+ * sample), the rate of plain FP32 copies and the rate of BF16 copies from the staging buffer (GB/s), the fraction of
+ * a batch's images the host paths would round on the host — f = l1 / (c + l1 - l2) in seconds per FP32 byte, c taken
+ * at 0.8 of the sampled rate; 1 above 0.93, 0 below 0.2 or with less than 15 % to gain — and, through *images (may be
+ * NULL), how many leading images of a `batch` that is (whole 16-image pieces). */
+double rnb_host_pack_split(double convert_gbps, double h2d_f32_gbps, double h2d_bf16_gbps, int batch, int* images);
 /* The conversion itself on host memory (no GPU involved): dst[i] = BF16(src[i]), round to nearest even, NaN ->
  * 0x7FFF, by the same thread pool. What the packed host paths upload. */
 int rnb_f32_to_bf16_host(const float* src, uint16_t* dst, size_t n);

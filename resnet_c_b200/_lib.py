@@ -64,6 +64,7 @@ PROTOTYPES = {
     "rnb_model_set_host_pack_fraction": (C.c_int, [_vp, C.c_double]),
     "rnb_model_host_pack": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "rnb_host_pack_threads": (C.c_int, []),
+    "rnb_host_pack_split": (C.c_double, [C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int)]),
     "rnb_f32_to_bf16_host": (C.c_int, [_vp, _vp, C.c_size_t]),
     "rnb_model_forward_bf16": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
     "rnb_model_num_classes": (C.c_int, [_vp]),

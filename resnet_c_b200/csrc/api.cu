@@ -373,6 +373,14 @@ int rnb_model_host_pack(const rnb_model_t* m, double info[4]) {
 
 int rnb_host_pack_threads(void) { return rnb::HostPacker::instance().threads(); }
 
+double rnb_host_pack_split(double convert_gbps, double h2d_f32_gbps, double h2d_bf16_gbps, int batch, int* images) {
+    double f = 0.0;
+    if (convert_gbps > 0 && h2d_f32_gbps > 0 && h2d_bf16_gbps > 0)   // times for one FP32 gigabyte of input
+        f = rnb::host_pack_split(1.0 / convert_gbps, 1.0 / h2d_f32_gbps, 0.5 / h2d_bf16_gbps);
+    if (images) *images = rnb::host_pack_images(f, batch);
+    return f;
+}
+
 int rnb_f32_to_bf16_host(const float* src, uint16_t* dst, size_t n) {
     if ((!src || !dst) && n) {
         set_error("rnb_f32_to_bf16_host: NULL argument");

@@ -128,6 +128,27 @@ void f32_to_bf16_rne(const float* src, uint16_t* dst, size_t n) {
     }
 }
 
+double host_pack_split(double t_convert, double t_copy_f32, double t_copy_bf16) {
+    if (!(t_convert > 0) || !(t_copy_f32 > 0) || !(t_copy_bf16 > 0)) return 0.0;
+    const double c = t_convert / 0.8, l1 = t_copy_f32, l2 = t_copy_bf16;
+    double f = c + l1 - l2 > 0 ? l1 / (c + l1 - l2) : 1.0;
+    f = std::min(1.0, std::max(0.0, f));
+    if (f > 0.93) f = 1.0;
+    const double t_mixed = std::max(f * c, f * l2 + (1.0 - f) * l1);
+    if (f < 0.2 || t_mixed > 0.85 * l1) f = 0.0;
+    return f;
+}
+
+int host_pack_images(double frac, int batch) {
+    if (batch <= 0 || !(frac > 0)) return 0;
+    if (frac >= 1.0) return batch;
+    if (batch < 32) return frac >= 0.5 ? batch : 0;   // too small to split: the larger side takes it all
+    int nb = static_cast<int>(frac * batch / 16.0 + 0.5) * 16;
+    if (nb < 16) nb = 0;
+    if (nb > batch - 16) nb = batch;
+    return nb;
+}
+
 struct HostPacker::Impl {
     std::vector<std::thread> workers;
     std::mutex run_mutex;              // one run() at a time

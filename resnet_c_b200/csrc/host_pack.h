@@ -16,6 +16,16 @@ namespace rnb {
 // dst[i] = BF16(src[i]), round to nearest even; NaN -> 0x7FFF (what cvt.rn.bf16x2.f32 produces). Single thread.
 void f32_to_bf16_rne(const float* src, uint16_t* dst, size_t n);
 
+// The split rule of the packed host paths. With c, l1, l2 seconds per FP32 byte of a batch on the cores, on the link as
+// FP32 and on the link as BF16 (c = cold-sample conversion time / 0.8: inside a serving loop every core also feeds
+// the DMA engine), a fraction f of the images through the cores costs f c of core time and f l2 + (1 - f) l1 of link
+// time; both finish together at f = l1 / (c + l1 - l2). Returns that fraction — 1 above 0.93, 0 below a fifth or when
+// less than 15 % would be gained over plain copies. Arguments: the three times measured on the same sample.
+double host_pack_split(double t_convert, double t_copy_f32, double t_copy_bf16);
+// The leading images of a `batch` that go through the cores for fraction `frac`: whole 16-image upload pieces; a
+// remainder below one piece joins the other side, and a batch of fewer than 32 images goes to the larger side whole.
+int host_pack_images(double frac, int batch);
+
 // A process-wide pool of sleeping worker threads. run() converts src[0, n) into dst with the workers AND the calling
 // thread, and calls ready(first_element, count) on the CALLING thread for every consecutive piece of `piece` elements
 // as soon as that piece is complete, in order (the caller queues the piece's H2D copy there, so the upload of piece i

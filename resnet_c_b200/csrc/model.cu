@@ -1706,9 +1706,7 @@ int Model::host_pack_for(const float* x, int batch, uint16_t** stage, float* x_d
     }
     // the share of a batch, in whole 16-image upload pieces; a remainder below one piece joins the other side
     auto images_of = [&](double frac) {
-        int nb = static_cast<int>(frac * batch / 16.0 + 0.5) * 16;
-        if (nb < 16 && frac < 1.0) nb = 0;
-        if (nb > batch - 16 || frac >= 1.0) nb = batch;
+        const int nb = host_pack_images(frac, batch);
         host_pack_last = static_cast<double>(nb) / batch;
         return nb;
     };
@@ -1749,16 +1747,8 @@ int Model::host_pack_for(const float* x, int batch, uint16_t** stage, float* x_d
         return 0;
     }
     for (int i = 0; i < 3; ++i) host_pack_gbps[kind][i] = (i == 2 ? 2.0 : 4.0) * n / std::max(t[i], 1e-9) * 1e-9;
-    // Seconds per FP32 byte of the batch: c on the cores (inside a serving loop the pool reaches about 0.8 of what a
-    // cold sample shows: every core also feeds the DMA engine), l1 on the link as FP32, l2 on the link as BF16. A
-    // fraction f on the cores costs f c of core time and f l2 + (1 - f) l1 of link time; they finish together at
-    // f = l1 / (c + l1 - l2). Below a fifth it is not worth the threads; the gain must be clear (15 %).
-    const double c = t[0] / 0.8, l1 = t[1], l2 = t[2];
-    double f = c + l1 - l2 > 0 ? l1 / (c + l1 - l2) : 1.0;
-    f = std::min(1.0, std::max(0.0, f));
-    if (f > 0.93) f = 1.0;
-    const double t_mixed = std::max(f * c, f * l2 + (1.0 - f) * l1);
-    if (f < 0.2 || t_mixed > 0.85 * l1) f = 0.0;
+    // cores and link share a batch in the proportion that lets both finish together (host_pack.h)
+    const double f = host_pack_split(t[0], t[1], t[2]);
     host_pack_frac[kind] = f;
     if (getenv("RNB_VERBOSE"))
         fprintf(stderr, "rnb host pack (%s input): %d threads convert %.1f GB/s (FP32 read), H2D FP32 %.1f GB/s, H2D BF16 "

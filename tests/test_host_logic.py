@@ -284,3 +284,33 @@ def test_input_reference_sub_batch_arithmetic(tmp_path):
     assert b.returncode == 0, b.stderr[-2000:]
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "inref ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_host_pack_split_rule():
+    """rnb_host_pack_split (csrc/host_pack.cpp): the share of a batch the host cores round to BF16, from measured
+    rates — checked on the figures the B200 boxes printed (profiles/e2e_hostpack_ab_r2.txt, hostpack_8gpu_r2.txt)."""
+    import ctypes as C
+    from resnet_c_b200 import _lib
+    lib = _lib.lib()
+
+    def split(conv, f32, bf16, batch=256):
+        n = C.c_int(-1)
+        f = lib.rnb_host_pack_split(conv, f32, bf16, batch, C.byref(n))
+        return f, n.value
+
+    f, n = split(76.1, 53.8, 52.3)                 # one GPU, 16 cores, pinned input: 73 % -> 192 of 256 images
+    assert abs(f - 0.73) < 0.01 and n == 192
+    f, n = split(74.8, 5.5, 52.3)                  # pageable input (the plain copy crawls): everything through the cores
+    assert f == 1.0 and n == 256
+    for conv, f32, bf16 in [(12.8, 51.2, 38.7), (9.9, 39.8, 34.3), (10.9, 24.5, 20.2)]:   # 8 ranks share 32 cores
+        assert split(conv, f32, bf16) == (0.0, 0)
+    f, n = split(12.0, 24.3, 28.8)                 # ... the one rank that saw a slow link at that moment
+    assert abs(f - 0.32) < 0.01 and n == 80
+    assert split(0.0, 50.0, 50.0) == (0.0, 0) and split(50.0, 0.0, 50.0) == (0.0, 0)
+    # whole 16-image pieces; short remainders join the other side; small batches are not split
+    assert [split(76.1, 53.8, 52.3, b)[1] for b in (37, 40, 70, 128, 31, 8, 1)] == [37, 40, 48, 96, 31, 8, 1]
+    assert [split(20.0, 40.0, 40.0, b)[1] for b in (256, 31, 8)] == [80, 0, 0]    # f = 0.33: the larger side is the link
+    # by construction both sides finish together: core time = link time at the returned fraction
+    f, _ = split(40.0, 50.0, 50.0)
+    core, link = f / (40.0 * 0.8), f * 0.5 / 50.0 + (1 - f) / 50.0
+    assert 0.2 < f < 0.93 and abs(core - link) < 1e-12
