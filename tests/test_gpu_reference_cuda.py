@@ -8,7 +8,6 @@ the GPU box, the sources do not).
     vs  resnet_infer (our whole-model driver)  vs  the golden top-1 of the reference's PyTorch class.
 """
 import ctypes as C
-import os
 import re
 import subprocess
 
@@ -131,18 +130,3 @@ def test_whole_model_driver(r152_workdir, dtype):
                        text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     assert _max_index(r.stdout) == expect * 3
-
-
-@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
-def test_whole_model_driver_from_host_tensors(r152_workdir, dtype):
-    """ResNet::predictHost (cuda/nn.cuh): the reference's load -> loadToCuda -> forward -> cpu() sequence in one call on
-    CPU tensors, with the host cores rounding the batch to BF16 where the stem takes it (forced here; the TF32 model
-    keeps plain copies): logits bit-identical to the device-tensor path, the reference's index for every image."""
-    assert INFER_BIN.exists(), "build/resnet_infer missing: run python -m resnet_c_b200.build dropin"
-    expect = load_golden("ref_class_resnet152")["top1"].tolist()
-    env = dict(os.environ, RNB_CHECK_HOST_PATH="1", RNB_HOST_PACK="1")
-    r = subprocess.run([str(INFER_BIN), "resnet152", dtype, "40"], cwd=r152_workdir, capture_output=True,
-                       text=True, timeout=900, env=env)
-    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-2000:]
-    assert "host path: identical" in r.stdout
-    assert _max_index(r.stdout) == expect * 40
